@@ -1,0 +1,656 @@
+// orb_oracle.cpp — CPU ORACLE.  TEST INFRASTRUCTURE ONLY.
+//
+// A from-scratch CPU restatement of TC2LI_SLAM::ORBextractor (reference:
+// slam_framework/src/ORBextractor.cc, include/ORBextractor.h) together with the OpenCV / libstdc++ /
+// glibc primitives it calls (restated from their published semantics; OpenCV is
+// NOT vendored by the reference and its C++ SDK is absent from this image).
+//
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may load this
+// library; it is the checker and the timed CPU baseline, never a product code path.  The product
+// (tc2li_slam_b200/csrc) shares no code with this file.
+//
+// Pinning: the reference ships no tests or golden vectors for this path ("parity unpinned" by the
+// reference itself).  This oracle is pinned instead by (1) bit-exact agreement of every primitive with
+// cv2 4.13 (tests/test_oracle_vs_cv2.py), (2) the six known-answer cases of SURVEY.md Appendix C
+// (tests/test_oracle_known_answers.py), (3) whole-pipeline agreement with the *verbatim* reference
+// translation unit compiled against stand-in OpenCV headers (oracle/_ref, tests/test_oracle_vs_ref.py).
+//
+// Build: g++ -O3 -ffp-contract=off (no FMA contraction: the canonical arithmetic), libstdc++ std::sort,
+// glibc sinf/cosf.
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <list>
+#include <vector>
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// A.0 integer rounding helpers (cvRound = round-half-to-even via the current rounding mode)
+// ---------------------------------------------------------------------------------------------
+inline int cv_round(float v) { return (int)lrintf(v); }
+inline int cv_round(double v) { return (int)lrint(v); }
+inline short sat_short(int v) { return (short)(v < -32768 ? -32768 : (v > 32767 ? 32767 : v)); }
+
+const int kEdge = 19;       // EDGE_THRESHOLD, ORBextractor.cc:47
+const int kHalfPatch = 15;  // HALF_PATCH_SIZE, ORBextractor.cc:46
+const int kPatch = 31;      // PATCH_SIZE, ORBextractor.cc:45
+
+static const signed char kPattern[1024] = {
+#include "orb_pattern.inc"
+};
+
+struct Plane {
+    int w = 0, h = 0;
+    std::vector<uint8_t> d;
+    void alloc(int w_, int h_) { w = w_; h = h_; d.assign((size_t)w * h, 0); }
+    uint8_t* row(int y) { return d.data() + (size_t)y * w; }
+    const uint8_t* row(int y) const { return d.data() + (size_t)y * w; }
+};
+
+struct KeyPoint {  // layout-identical to cv::KeyPoint (28 bytes)
+    float x, y, size, angle, response;
+    int32_t octave, class_id;
+};
+static_assert(sizeof(KeyPoint) == 28, "cv::KeyPoint layout");
+
+struct Cand {  // FAST candidate relative to (minBorderX, minBorderY), ORBextractor.cc:837-842
+    float x, y, response;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Synthetic input generator orbx-synth-v1 — pure integer arithmetic.
+// ---------------------------------------------------------------------------------------------
+inline uint32_t lowbias32(uint32_t v) {
+    v ^= v >> 16; v *= 0x7feb352dU; v ^= v >> 15; v *= 0x846ca68bU; v ^= v >> 16;
+    return v;
+}
+inline uint32_t lat(uint32_t ix, uint32_t iy, uint32_t S, uint32_t seed) {
+    return lowbias32((ix * 73856093U) ^ (iy * 19349663U) ^ (S * 83492791U) ^ (seed * 2654435761U)) & 255U;
+}
+inline uint32_t octv(uint32_t x, uint32_t y, uint32_t S, uint32_t seed) {
+    uint32_t ix = x / S, iy = y / S, fx = x % S, fy = y % S;
+    uint64_t acc = (uint64_t)(S - fx) * (S - fy) * lat(ix, iy, S, seed) + (uint64_t)fx * (S - fy) * lat(ix + 1, iy, S, seed) +
+                   (uint64_t)(S - fx) * fy * lat(ix, iy + 1, S, seed) + (uint64_t)fx * fy * lat(ix + 1, iy + 1, S, seed);
+    return (uint32_t)(acc / ((uint64_t)S * S));
+}
+void synth_v1(uint8_t* out, int W, int H, uint32_t seed, int xoff, uint32_t noise_xor) {
+    for (int yy = 0; yy < H; ++yy)
+        for (int xx = 0; xx < W; ++xx) {
+            uint32_t x = (uint32_t)(xx + xoff), y = (uint32_t)yy;
+            uint32_t base = (4 * octv(x, y, 64, seed) + 3 * octv(x, y, 32, seed) + 2 * octv(x, y, 16, seed) + octv(x, y, 8, seed)) / 10;
+            uint32_t blk = lat(x / 24, y / 18, 999, seed);
+            uint32_t noise = lowbias32((x * 0x9E3779B1U) ^ (y * 0x85EBCA77U) ^ ((seed ^ noise_xor) * 0xC2B2AE3DU)) & 7U;
+            uint32_t p = (3 * base + 2 * blk) / 5 + noise;
+            out[(size_t)yy * W + xx] = (uint8_t)(p > 255 ? 255 : p);
+        }
+}
+
+// ---------------------------------------------------------------------------------------------
+// A.1 cv::resize(INTER_LINEAR) for 8UC1 (called at ORBextractor.cc:1156).  Fixed-point bilinear with
+// 11-bit coefficients; the vertical pass drops 4 bits before the 16-bit multiply.
+// ---------------------------------------------------------------------------------------------
+void resize_linear_8u(const uint8_t* src, int sw, int sh, size_t sstride, uint8_t* dst, int dw, int dh, size_t dstride) {
+    // cv::resize derives inv_scale = dsize/ssize when dsize is given, and hal::resize then uses scale = 1/inv_scale.
+    const double scale_x = 1.0 / ((double)dw / sw), scale_y = 1.0 / ((double)dh / sh);
+    std::vector<int> xofs(dw), yofs(dh);
+    std::vector<short> ax(2 * (size_t)dw), by(2 * (size_t)dh);
+    for (int dx = 0; dx < dw; ++dx) {
+        float fx = (float)((dx + 0.5) * scale_x - 0.5);
+        int sx = (int)std::floor(fx);
+        fx -= sx;
+        if (sx < 0) { fx = 0; sx = 0; }
+        if (sx >= sw - 1) { fx = 0; sx = sw - 1; }
+        xofs[dx] = sx;
+        ax[2 * dx] = sat_short(cv_round((1.f - fx) * 2048.f));
+        ax[2 * dx + 1] = sat_short(cv_round(fx * 2048.f));
+    }
+    for (int dy = 0; dy < dh; ++dy) {
+        float fy = (float)((dy + 0.5) * scale_y - 0.5);
+        int sy = (int)std::floor(fy);
+        fy -= sy;
+        yofs[dy] = sy;
+        by[2 * dy] = sat_short(cv_round((1.f - fy) * 2048.f));
+        by[2 * dy + 1] = sat_short(cv_round(fy * 2048.f));
+    }
+    std::vector<int> r0(dw), r1(dw);
+    int have0 = -1000000, have1 = -1000000;
+    auto hpass = [&](int sy, std::vector<int>& out) {
+        const uint8_t* S = src + (size_t)sy * sstride;
+        for (int dx = 0; dx < dw; ++dx) {
+            int sx = xofs[dx];
+            int sx1 = sx + 1 < sw ? sx + 1 : sw - 1;
+            out[dx] = S[sx] * ax[2 * dx] + S[sx1] * ax[2 * dx + 1];
+        }
+    };
+    for (int dy = 0; dy < dh; ++dy) {
+        int sy0 = std::min(std::max(yofs[dy], 0), sh - 1);
+        int sy1 = std::min(std::max(yofs[dy] + 1, 0), sh - 1);
+        if (sy0 == have1) { r0.swap(r1); std::swap(have0, have1); }
+        if (sy0 != have0) { hpass(sy0, r0); have0 = sy0; }
+        if (sy1 == have0) { r1 = r0; have1 = sy1; }
+        else if (sy1 != have1) { hpass(sy1, r1); have1 = sy1; }
+        const int b0 = by[2 * dy], b1 = by[2 * dy + 1];
+        uint8_t* D = dst + (size_t)dy * dstride;
+        for (int dx = 0; dx < dw; ++dx) {
+            int v = (((b0 * (r0[dx] >> 4)) >> 16) + ((b1 * (r1[dx] >> 4)) >> 16) + 2) >> 2;
+            D[dx] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+        }
+    }
+}
+
+inline int reflect101(int i, int n) {  // A.2 BORDER_REFLECT_101
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) {
+        if (i < 0) i = -i;
+        else i = 2 * (n - 1) - i;
+    }
+    return i;
+}
+
+// ---------------------------------------------------------------------------------------------
+// A.3 GaussianBlur(7x7, sigma 2) on 8U (ORBextractor.cc:1106): separable 8.8 fixed-point filter.
+// ---------------------------------------------------------------------------------------------
+void gaussian_blur7_8u(const uint8_t* src, int w, int h, size_t sstride, uint8_t* dst, size_t dstride, const int taps[7]) {
+    std::vector<uint16_t> hbuf((size_t)w * h);
+    for (int y = 0; y < h; ++y) {
+        const uint8_t* S = src + (size_t)y * sstride;
+        uint16_t* Hh = hbuf.data() + (size_t)y * w;
+        for (int x = 0; x < w; ++x) {
+            uint32_t acc = 0;
+            if (x >= 3 && x + 3 < w)
+                for (int k = 0; k < 7; ++k) acc += (uint32_t)taps[k] * S[x + k - 3];
+            else
+                for (int k = 0; k < 7; ++k) acc += (uint32_t)taps[k] * S[reflect101(x + k - 3, w)];
+            Hh[x] = (uint16_t)(acc > 65535 ? 65535 : acc);
+        }
+    }
+    for (int y = 0; y < h; ++y) {
+        const uint16_t* R[7];
+        for (int k = 0; k < 7; ++k) R[k] = hbuf.data() + (size_t)reflect101(y + k - 3, h) * w;
+        uint8_t* D = dst + (size_t)y * dstride;
+        for (int x = 0; x < w; ++x) {
+            uint32_t acc = 0;
+            for (int k = 0; k < 7; ++k) acc += (uint32_t)taps[k] * R[k][x];
+            uint32_t v = (acc + 32768U) >> 16;
+            D[x] = (uint8_t)(v > 255 ? 255 : v);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// A.4 cv::FAST(img, kps, t, true) TYPE_9_16 on a w x h crop (ORBextractor.cc:800,819).
+// Output in raster order: (x, y, score) with score = (largest t' at which the pixel is still a corner),
+// i.e. max over the 16 arcs of 9 of min |ring - v| on one side, minus 1.
+// ---------------------------------------------------------------------------------------------
+static const int kRingDx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+static const int kRingDy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+
+inline bool has_arc9(uint32_t m) {  // 9 contiguous set bits in a circular 16-bit mask
+    m |= m << 16;
+    m &= m >> 1;  // runs of >=2
+    m &= m >> 2;  // >=4
+    m &= m >> 4;  // >=8
+    m &= m >> 1;  // >=9
+    return (m & 0xFFFFu) != 0;
+}
+
+inline int arc_score(const int d[16]) {  // max over starts of min over 9 contiguous of d
+    int m2[16], m4[16], m8[16], best = -1000;
+    for (int i = 0; i < 16; ++i) m2[i] = std::min(d[i], d[(i + 1) & 15]);
+    for (int i = 0; i < 16; ++i) m4[i] = std::min(m2[i], m2[(i + 2) & 15]);
+    for (int i = 0; i < 16; ++i) m8[i] = std::min(m4[i], m4[(i + 4) & 15]);
+    for (int i = 0; i < 16; ++i) best = std::max(best, std::min(m8[i], d[(i + 8) & 15]));
+    return best;
+}
+
+struct FastKp { int x, y, score; };
+
+void fast9_nms(const uint8_t* img, int w, int h, size_t stride, int t, std::vector<FastKp>& out) {
+    out.clear();
+    if (w < 7 || h < 7) return;
+    int off[16];
+    for (int k = 0; k < 16; ++k) off[k] = kRingDy[k] * (int)stride + kRingDx[k];
+    // score rows with a zero rim; three-row rolling window for the 3x3 non-max suppression
+    std::vector<int> buf((size_t)3 * w, 0);
+    auto score_row = [&](int y, int* sc) {
+        std::fill(sc, sc + w, 0);
+        if (y < 3 || y >= h - 3) return;
+        const uint8_t* p = img + (size_t)y * stride;
+        for (int x = 3; x < w - 3; ++x) {
+            const int v = p[x], lo = v - t, hi = v + t;
+            // an arc of 9 covers one of every opposite pair: cheap necessary test first
+            const int a0 = p[x + off[0]], a8 = p[x + off[8]];
+            bool br = (a0 > hi) || (a8 > hi), dk = (a0 < lo) || (a8 < lo);
+            if (!br && !dk) continue;
+            const int a4 = p[x + off[4]], a12 = p[x + off[12]];
+            br = br && ((a4 > hi) || (a12 > hi));
+            dk = dk && ((a4 < lo) || (a12 < lo));
+            if (!br && !dk) continue;
+            uint32_t mb = 0, md = 0;
+            int r[16];
+            for (int k = 0; k < 16; ++k) {
+                r[k] = p[x + off[k]];
+                mb |= (uint32_t)(r[k] > hi) << k;
+                md |= (uint32_t)(r[k] < lo) << k;
+            }
+            int d[16], s = 0;
+            if (br && has_arc9(mb)) {
+                for (int k = 0; k < 16; ++k) d[k] = r[k] - v;
+                s = arc_score(d);
+            } else if (dk && has_arc9(md)) {
+                for (int k = 0; k < 16; ++k) d[k] = v - r[k];
+                s = arc_score(d);
+            } else
+                continue;
+            sc[x] = s - 1;  // s > t >= 0 here
+        }
+    };
+    int* prev = buf.data();
+    int* cur = buf.data() + w;
+    int* next = buf.data() + 2 * (size_t)w;
+    score_row(2, prev);
+    score_row(3, cur);
+    for (int y = 3; y < h - 3; ++y) {
+        score_row(y + 1, next);
+        for (int x = 3; x < w - 3; ++x) {
+            const int s = cur[x];
+            if (s <= 0) continue;  // corners have score >= t >= 1
+            if (s > cur[x - 1] && s > cur[x + 1] && s > prev[x - 1] && s > prev[x] && s > prev[x + 1] && s > next[x - 1] && s > next[x] &&
+                s > next[x + 1])
+                out.push_back({x, y, s});
+        }
+        int* tmp = prev; prev = cur; cur = next; next = tmp;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// A.5 cv::fastAtan2 (scalar path, float32, no FMA; degrees in [0,360)) — used at ORBextractor.cc:76
+// ---------------------------------------------------------------------------------------------
+float fast_atan2(float y, float x) {
+    const float scale = (float)(180.0 / 3.14159265358979323846);
+    const float p1 = 0.9997878412794807f * scale, p3 = -0.3258083974640975f * scale, p5 = 0.1555786518463281f * scale,
+                p7 = -0.04432655554792128f * scale;
+    const float eps = (float)2.2204460492503131e-16;  // (float)DBL_EPSILON
+    float ax = std::fabs(x), ay = std::fabs(y), a, c, c2;
+    if (ax >= ay) {
+        c = ay / (ax + eps);
+        c2 = c * c;
+        a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    } else {
+        c = ax / (ay + eps);
+        c2 = c * c;
+        a = 90.f - (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    }
+    if (x < 0) a = 180.f - a;
+    if (y < 0) a = 360.f - a;
+    return a;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The extractor (ORBextractor.cc:383-443 ctor, :755-870 key points, :529-753 octree, :1060-1168)
+// ---------------------------------------------------------------------------------------------
+struct QNode {  // ExtractorNode, ORBextractor.h:39-50 (rectangle kept as two corners; the reference's
+                // four corners always form an axis-aligned rectangle)
+    int x0, y0, x1, y1;
+    std::vector<int> keys;  // indices into the candidate vector, order preserved
+    bool noMore = false;
+    std::list<QNode>::iterator self;
+};
+
+struct Extractor {
+    int nfeatures, nlevels, iniTh, minTh;
+    double scaleFactor;  // ORBextractor.h:105 — double member
+    std::vector<float> sf, isf, sig2, isig2;
+    std::vector<int> quota, umax;
+    int taps[7] = {18, 34, 48, 56, 48, 34, 18};
+
+    // per-call state (stage dumps)
+    std::vector<Plane> pyr, blurred;
+    std::vector<std::vector<Cand>> cands;
+    std::vector<int> fallbackCells;
+    std::vector<std::vector<KeyPoint>> selected;  // level coordinates, with angle
+    std::vector<KeyPoint> kps;
+    std::vector<uint8_t> desc;
+    int monoIndex = 0;
+
+    Extractor(int nf, float s, int nl, int ini, int mn) : nfeatures(nf), nlevels(nl), iniTh(ini), minTh(mn), scaleFactor(s) {
+        sf.resize(nl); sig2.resize(nl); isf.resize(nl); isig2.resize(nl);
+        sf[0] = 1.0f; sig2[0] = 1.0f;
+        for (int i = 1; i < nl; ++i) {
+            sf[i] = (float)(sf[i - 1] * scaleFactor);  // float * double -> double -> float (ORBextractor.cc:394)
+            sig2[i] = sf[i] * sf[i];
+        }
+        for (int i = 0; i < nl; ++i) { isf[i] = 1.0f / sf[i]; isig2[i] = 1.0f / sig2[i]; }
+        quota.resize(nl);
+        float factor = (float)(1.0f / scaleFactor);
+        float nDesired = nfeatures * (1 - factor) / (1 - (float)std::pow((double)factor, (double)nlevels));
+        int sum = 0;
+        for (int l = 0; l < nl - 1; ++l) {
+            quota[l] = cv_round(nDesired);
+            sum += quota[l];
+            nDesired *= factor;
+        }
+        quota[nl - 1] = std::max(nfeatures - sum, 0);
+        // circular patch row half-widths (ORBextractor.cc:427-442)
+        umax.assign(kHalfPatch + 1, 0);
+        int vmax = (int)std::floor(kHalfPatch * std::sqrt(2.f) / 2 + 1);
+        int vmin = (int)std::ceil(kHalfPatch * std::sqrt(2.f) / 2);
+        const double hp2 = kHalfPatch * kHalfPatch;
+        for (int v = 0; v <= vmax; ++v) umax[v] = cv_round(std::sqrt(hp2 - v * v));
+        for (int v = kHalfPatch, v0 = 0; v >= vmin; --v) {
+            while (umax[v0] == umax[v0 + 1]) ++v0;
+            umax[v] = v0;
+            ++v0;
+        }
+    }
+
+    // ORBextractor.cc:1143-1168 (the 19-px border is not materialised: nothing on the path reads it)
+    void computePyramid(const uint8_t* img, int w, int h, size_t stride) {
+        pyr.assign(nlevels, Plane());
+        for (int l = 0; l < nlevels; ++l) {
+            float scale = isf[l];
+            int lw = cv_round((float)w * scale), lh = cv_round((float)h * scale);
+            pyr[l].alloc(lw, lh);
+            if (l == 0)
+                for (int y = 0; y < h; ++y) std::memcpy(pyr[0].row(y), img + (size_t)y * stride, w);
+            else
+                resize_linear_8u(pyr[l - 1].d.data(), pyr[l - 1].w, pyr[l - 1].h, pyr[l - 1].w, pyr[l].d.data(), lw, lh, lw);
+        }
+    }
+
+    // ORBextractor.cc:454-510
+    static void divide(const QNode& n, const std::vector<Cand>& c, QNode ch[4]) {
+        const int halfX = (int)std::ceil((float)(n.x1 - n.x0) / 2);
+        const int halfY = (int)std::ceil((float)(n.y1 - n.y0) / 2);
+        const int mx = n.x0 + halfX, my = n.y0 + halfY;
+        ch[0].x0 = n.x0; ch[0].y0 = n.y0; ch[0].x1 = mx;   ch[0].y1 = my;
+        ch[1].x0 = mx;   ch[1].y0 = n.y0; ch[1].x1 = n.x1; ch[1].y1 = my;
+        ch[2].x0 = n.x0; ch[2].y0 = my;   ch[2].x1 = mx;   ch[2].y1 = n.y1;
+        ch[3].x0 = mx;   ch[3].y0 = my;   ch[3].x1 = n.x1; ch[3].y1 = n.y1;
+        for (int k : n.keys) {
+            const Cand& p = c[k];
+            int q = (p.x < mx) ? ((p.y < my) ? 0 : 2) : ((p.y < my) ? 1 : 3);
+            ch[q].keys.push_back(k);
+        }
+        for (int q = 0; q < 4; ++q) ch[q].noMore = (ch[q].keys.size() == 1);
+    }
+
+    // ORBextractor.cc:529-753.  Returns indices into `c`, in final list order.
+    std::vector<int> distributeOctTree(const std::vector<Cand>& c, int minX, int maxX, int minY, int maxY, int N) {
+        const int nIni = (int)std::round((float)(maxX - minX) / (maxY - minY));
+        const float hX = (float)(maxX - minX) / nIni;
+        std::list<QNode> nodes;
+        std::vector<QNode*> ini(nIni);
+        for (int i = 0; i < nIni; ++i) {
+            QNode n;
+            n.x0 = (int)(hX * (float)i); n.x1 = (int)(hX * (float)(i + 1));
+            n.y0 = 0; n.y1 = maxY - minY;
+            nodes.push_back(n);
+            ini[i] = &nodes.back();
+        }
+        for (size_t i = 0; i < c.size(); ++i) ini[(int)(c[i].x / hX)]->keys.push_back((int)i);
+        for (auto it = nodes.begin(); it != nodes.end();) {
+            if (it->keys.size() == 1) { it->noMore = true; ++it; }
+            else if (it->keys.empty()) it = nodes.erase(it);
+            else ++it;
+        }
+        typedef std::pair<int, QNode*> SP;
+        auto cmp = [](const SP& a, const SP& b) {  // compareNodes, ORBextractor.cc:512-527
+            if (a.first < b.first) return true;
+            if (a.first > b.first) return false;
+            return a.second->x0 < b.second->x0;
+        };
+        auto pushChildren = [&](QNode ch[4], std::vector<SP>& rec, int* nToExpand) {
+            for (int q = 0; q < 4; ++q) {
+                if (ch[q].keys.empty()) continue;
+                nodes.push_front(ch[q]);
+                if (ch[q].keys.size() > 1) {
+                    if (nToExpand) ++*nToExpand;
+                    rec.push_back(SP((int)ch[q].keys.size(), &nodes.front()));
+                    nodes.front().self = nodes.begin();
+                }
+            }
+        };
+        bool finish = false;
+        std::vector<SP> rec;
+        while (!finish) {
+            int prevSize = (int)nodes.size();
+            int nToExpand = 0;
+            rec.clear();
+            for (auto it = nodes.begin(); it != nodes.end();) {
+                if (it->noMore) { ++it; continue; }
+                QNode ch[4];
+                divide(*it, c, ch);
+                pushChildren(ch, rec, &nToExpand);
+                it = nodes.erase(it);
+            }
+            if ((int)nodes.size() >= N || (int)nodes.size() == prevSize) finish = true;
+            else if ((int)nodes.size() + nToExpand * 3 > N) {
+                while (!finish) {
+                    prevSize = (int)nodes.size();
+                    std::vector<SP> prev = rec;
+                    rec.clear();
+                    std::sort(prev.begin(), prev.end(), cmp);  // libstdc++ introsort: tie order is part of the result
+                    for (int j = (int)prev.size() - 1; j >= 0; --j) {
+                        QNode ch[4];
+                        divide(*prev[j].second, c, ch);
+                        pushChildren(ch, rec, nullptr);
+                        nodes.erase(prev[j].second->self);
+                        if ((int)nodes.size() >= N) break;
+                    }
+                    if ((int)nodes.size() >= N || (int)nodes.size() == prevSize) finish = true;
+                }
+            }
+        }
+        std::vector<int> out;
+        out.reserve(nodes.size());
+        for (const QNode& n : nodes) {  // best response per node, first wins ties (ORBextractor.cc:732-750)
+            int best = n.keys[0];
+            float br = c[best].response;
+            for (size_t k = 1; k < n.keys.size(); ++k)
+                if (c[n.keys[k]].response > br) { best = n.keys[k]; br = c[best].response; }
+            out.push_back(best);
+        }
+        return out;
+    }
+
+    // ORBextractor.cc:50-77
+    float icAngle(const Plane& im, int x, int y) const {
+        int m01 = 0, m10 = 0;
+        const uint8_t* center = im.row(y) + x;
+        for (int u = -kHalfPatch; u <= kHalfPatch; ++u) m10 += u * center[u];
+        const int step = im.w;
+        for (int v = 1; v <= kHalfPatch; ++v) {
+            int vsum = 0, d = umax[v];
+            for (int u = -d; u <= d; ++u) {
+                int vp = center[u + v * step], vm = center[u - v * step];
+                vsum += (vp - vm);
+                m10 += u * (vp + vm);
+            }
+            m01 += v * vsum;
+        }
+        return fast_atan2((float)m01, (float)m10);
+    }
+
+    // ORBextractor.cc:755-870.  Returns false when a level is too small for the cell grid (the reference
+    // would divide by zero there).
+    bool computeKeyPoints() {
+        cands.assign(nlevels, {});
+        fallbackCells.assign(nlevels, 0);
+        selected.assign(nlevels, {});
+        const float W = 35;
+        std::vector<FastKp> cell;
+        for (int l = 0; l < nlevels; ++l) {
+            const Plane& im = pyr[l];
+            const int minBX = kEdge - 3, minBY = minBX, maxBX = im.w - kEdge + 3, maxBY = im.h - kEdge + 3;
+            const float width = (float)(maxBX - minBX), height = (float)(maxBY - minBY);
+            const int nCols = (int)(width / W), nRows = (int)(height / W);
+            if (nCols < 1 || nRows < 1) return false;
+            const int wCell = (int)std::ceil(width / nCols), hCell = (int)std::ceil(height / nRows);
+            std::vector<Cand>& vc = cands[l];
+            for (int i = 0; i < nRows; ++i) {
+                const int iniY = minBY + i * hCell;
+                int maxY = iniY + hCell + 6;
+                if (iniY >= maxBY - 3) continue;
+                if (maxY > maxBY) maxY = maxBY;
+                for (int j = 0; j < nCols; ++j) {
+                    const int iniX = minBX + j * wCell;
+                    int maxX = iniX + wCell + 6;
+                    if (iniX >= maxBX - 6) continue;
+                    if (maxX > maxBX) maxX = maxBX;
+                    const uint8_t* crop = im.row(iniY) + iniX;
+                    fast9_nms(crop, maxX - iniX, maxY - iniY, im.w, iniTh, cell);
+                    if (cell.empty()) {
+                        fast9_nms(crop, maxX - iniX, maxY - iniY, im.w, minTh, cell);
+                        ++fallbackCells[l];
+                    }
+                    for (const FastKp& k : cell) vc.push_back({(float)(k.x + j * wCell), (float)(k.y + i * hCell), (float)k.score});
+                }
+            }
+            std::vector<int> keep = distributeOctTree(vc, minBX, maxBX, minBY, maxBY, quota[l]);
+            const int scaledPatch = (int)(kPatch * sf[l]);
+            for (int idx : keep) {
+                KeyPoint kp;
+                kp.x = vc[idx].x + minBX; kp.y = vc[idx].y + minBY;
+                kp.size = (float)scaledPatch; kp.angle = -1.f; kp.response = vc[idx].response;
+                kp.octave = l; kp.class_id = -1;
+                selected[l].push_back(kp);
+            }
+        }
+        for (int l = 0; l < nlevels; ++l)
+            for (KeyPoint& kp : selected[l]) kp.angle = icAngle(pyr[l], cv_round(kp.x), cv_round(kp.y));
+        return true;
+    }
+
+    // ORBextractor.cc:81-120
+    static void descriptor(const KeyPoint& kp, const Plane& im, uint8_t* out) {
+        const float factorPI = (float)(3.14159265358979323846 / 180.f);
+        float angle = (float)kp.angle * factorPI;
+        float a = cosf(angle), b = sinf(angle);
+        const uint8_t* center = im.row(cv_round(kp.y)) + cv_round(kp.x);
+        const int step = im.w;
+        const signed char* pat = kPattern;
+        auto val = [&](int idx) -> int {
+            float px = (float)pat[2 * idx], py = (float)pat[2 * idx + 1];
+            return center[cv_round(px * b + py * a) * step + cv_round(px * a - py * b)];
+        };
+        for (int i = 0; i < 32; ++i, pat += 32) {
+            int v = 0;
+            for (int k = 0; k < 8; ++k) v |= (val(2 * k) < val(2 * k + 1)) << k;
+            out[i] = (uint8_t)v;
+        }
+    }
+
+    // ORBextractor.cc:1060-1141.  Returns monoIndex, -1 for an empty image, -2 when the image is too small.
+    int extract(const uint8_t* img, int w, int h, size_t stride, int lap0, int lap1) {
+        kps.clear(); desc.clear(); monoIndex = 0;
+        if (!img || w <= 0 || h <= 0) return -1;
+        computePyramid(img, w, h, stride);
+        blurred.assign(nlevels, Plane());
+        if (!computeKeyPoints()) return -2;
+        int n = 0;
+        for (int l = 0; l < nlevels; ++l) n += (int)selected[l].size();
+        kps.assign(n, KeyPoint());
+        desc.assign((size_t)n * 32, 0);
+        int mono = 0, stereo = n - 1;
+        uint8_t d[32];
+        for (int l = 0; l < nlevels; ++l) {
+            if (selected[l].empty()) continue;
+            blurred[l].alloc(pyr[l].w, pyr[l].h);
+            gaussian_blur7_8u(pyr[l].d.data(), pyr[l].w, pyr[l].h, pyr[l].w, blurred[l].d.data(), pyr[l].w, taps);
+            const float scale = sf[l];
+            for (const KeyPoint& src : selected[l]) {
+                descriptor(src, blurred[l], d);
+                KeyPoint kp = src;
+                if (l != 0) { kp.x *= scale; kp.y *= scale; }
+                int dst = (kp.x >= lap0 && kp.x <= lap1) ? stereo-- : mono++;
+                kps[dst] = kp;
+                std::memcpy(&desc[(size_t)dst * 32], d, 32);
+            }
+        }
+        monoIndex = mono;
+        return mono;
+    }
+};
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// C API (ctypes) — used by tests/, smoke() and bench.py's CPU-baseline legs only.
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+void* orbo_create(int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh) {
+    return new Extractor(nfeatures, scaleFactor, nlevels, iniTh, minTh);
+}
+void orbo_destroy(void* h) { delete (Extractor*)h; }
+void orbo_set_blur_taps(void* h, const int* taps) { std::memcpy(((Extractor*)h)->taps, taps, 7 * sizeof(int)); }
+int orbo_extract(void* h, const uint8_t* img, int w, int hh, int stride, int lap0, int lap1) {
+    return ((Extractor*)h)->extract(img, w, hh, (size_t)stride, lap0, lap1);
+}
+int orbo_num_keypoints(void* h) { return (int)((Extractor*)h)->kps.size(); }
+void orbo_get_keypoints(void* h, void* out) {
+    Extractor* e = (Extractor*)h;
+    if (!e->kps.empty()) std::memcpy(out, e->kps.data(), e->kps.size() * sizeof(KeyPoint));
+}
+void orbo_get_descriptors(void* h, uint8_t* out) {
+    Extractor* e = (Extractor*)h;
+    if (!e->desc.empty()) std::memcpy(out, e->desc.data(), e->desc.size());
+}
+void orbo_get_tables(void* h, float* sf, float* isf, float* sig2, float* isig2, int* quota, int* umax) {
+    Extractor* e = (Extractor*)h;
+    for (int i = 0; i < e->nlevels; ++i) { sf[i] = e->sf[i]; isf[i] = e->isf[i]; sig2[i] = e->sig2[i]; isig2[i] = e->isig2[i]; quota[i] = e->quota[i]; }
+    for (int i = 0; i < 16; ++i) umax[i] = e->umax[i];
+}
+void orbo_level_size(void* h, int l, int* w, int* hh) { Extractor* e = (Extractor*)h; *w = e->pyr[l].w; *hh = e->pyr[l].h; }
+void orbo_get_level(void* h, int l, uint8_t* out) { Extractor* e = (Extractor*)h; std::memcpy(out, e->pyr[l].d.data(), e->pyr[l].d.size()); }
+int orbo_get_blurred(void* h, int l, uint8_t* out) {
+    Extractor* e = (Extractor*)h;
+    if (e->blurred[l].d.empty()) return 0;
+    std::memcpy(out, e->blurred[l].d.data(), e->blurred[l].d.size());
+    return 1;
+}
+int orbo_num_candidates(void* h, int l) { return (int)((Extractor*)h)->cands[l].size(); }
+void orbo_get_candidates(void* h, int l, float* xyr) {
+    Extractor* e = (Extractor*)h;
+    if (!e->cands[l].empty()) std::memcpy(xyr, e->cands[l].data(), e->cands[l].size() * sizeof(Cand));
+}
+int orbo_num_fallback_cells(void* h, int l) { return ((Extractor*)h)->fallbackCells[l]; }
+int orbo_num_selected(void* h, int l) { return (int)((Extractor*)h)->selected[l].size(); }
+void orbo_get_selected(void* h, int l, void* out) {
+    Extractor* e = (Extractor*)h;
+    if (!e->selected[l].empty()) std::memcpy(out, e->selected[l].data(), e->selected[l].size() * sizeof(KeyPoint));
+}
+// primitives, for direct checks against cv2
+void orbo_synth_v1(uint8_t* out, int W, int H, uint32_t seed, int xoff, uint32_t noise_xor) { synth_v1(out, W, H, seed, xoff, noise_xor); }
+void orbo_resize(const uint8_t* src, int sw, int sh, int sstride, uint8_t* dst, int dw, int dh, int dstride) {
+    resize_linear_8u(src, sw, sh, (size_t)sstride, dst, dw, dh, (size_t)dstride);
+}
+void orbo_blur(const uint8_t* src, int w, int h, int sstride, uint8_t* dst, int dstride, const int* taps) {
+    gaussian_blur7_8u(src, w, h, (size_t)sstride, dst, (size_t)dstride, taps);
+}
+int orbo_fast(const uint8_t* img, int w, int h, int stride, int t, int* xys, int cap) {
+    std::vector<FastKp> v;
+    fast9_nms(img, w, h, (size_t)stride, t, v);
+    int n = (int)std::min<size_t>(v.size(), (size_t)cap);
+    for (int i = 0; i < n; ++i) { xys[3 * i] = v[i].x; xys[3 * i + 1] = v[i].y; xys[3 * i + 2] = v[i].score; }
+    return (int)v.size();
+}
+float orbo_fast_atan2(float y, float x) { return fast_atan2(y, x); }
+void orbo_sincos(float angle, float* s, float* c) { *s = sinf(angle); *c = cosf(angle); }
+// std::sort on (key, id) pairs with the reference comparator semantics (key = (nKeys, UL.x) packed by the caller):
+// used to check the product's libstdc++-exact sort port.
+void orbo_std_sort_pairs(int* firsts, int* seconds, int n) {
+    std::vector<std::pair<std::pair<int, int>, int>> v(n);
+    for (int i = 0; i < n; ++i) v[i] = {{firsts[i], seconds[i]}, i};
+    std::sort(v.begin(), v.end(), [](const std::pair<std::pair<int, int>, int>& a, const std::pair<std::pair<int, int>, int>& b) {
+        if (a.first.first < b.first.first) return true;
+        if (a.first.first > b.first.first) return false;
+        return a.first.second < b.first.second;
+    });
+    for (int i = 0; i < n; ++i) { firsts[i] = v[i].second; }  // permutation: output slot i holds input index
+    (void)seconds;
+}
+}

@@ -1,0 +1,187 @@
+"""ctypes front-end of the CPU oracle (oracle/orb_oracle.cpp).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this module; the product
+package (tc2li_slam_b200) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "liborb_oracle.so")
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+assert KP_DTYPE.itemsize == 28
+
+
+def build(force=False):
+    if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(os.path.join(_HERE, "orb_oracle.cpp")):
+        subprocess.check_call(["make", "-C", _HERE, "liborb_oracle.so"], stdout=subprocess.DEVNULL)
+    return _LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(build())
+        L.orbo_create.restype = C.c_void_p
+        L.orbo_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.orbo_destroy.argtypes = [C.c_void_p]
+        L.orbo_set_blur_taps.argtypes = [C.c_void_p, C.c_void_p]
+        L.orbo_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.orbo_num_keypoints.argtypes = [C.c_void_p]
+        L.orbo_get_keypoints.argtypes = [C.c_void_p, C.c_void_p]
+        L.orbo_get_descriptors.argtypes = [C.c_void_p, C.c_void_p]
+        L.orbo_get_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+        L.orbo_level_size.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.orbo_get_level.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.orbo_get_blurred.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.orbo_num_candidates.argtypes = [C.c_void_p, C.c_int]
+        L.orbo_get_candidates.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.orbo_num_fallback_cells.argtypes = [C.c_void_p, C.c_int]
+        L.orbo_num_selected.argtypes = [C.c_void_p, C.c_int]
+        L.orbo_get_selected.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.orbo_synth_v1.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_uint32]
+        L.orbo_resize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.orbo_blur.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        L.orbo_fast.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.orbo_fast_atan2.restype = C.c_float
+        L.orbo_fast_atan2.argtypes = [C.c_float, C.c_float]
+        L.orbo_sincos.argtypes = [C.c_float, C.c_void_p, C.c_void_p]
+        L.orbo_std_sort_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def synth_v1(w, h, seed, xoff=0, noise_xor=0):
+    """orbx-synth-v1.  Right image of a stereo pair: xoff=16, noise_xor=0x5bd1e995."""
+    out = np.empty((h, w), np.uint8)
+    lib().orbo_synth_v1(_p(out), w, h, seed & 0xFFFFFFFF, xoff, noise_xor & 0xFFFFFFFF)
+    return out
+
+
+def resize(src, dw, dh):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty((dh, dw), np.uint8)
+    lib().orbo_resize(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(dst), dw, dh, dw)
+    return dst
+
+
+def blur(src, taps=(18, 34, 48, 56, 48, 34, 18)):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty_like(src)
+    t = np.asarray(taps, np.int32)
+    lib().orbo_blur(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(dst), dst.strides[0], _p(t))
+    return dst
+
+
+def fast(img, t):
+    """FAST-9/16 + NMS on a crop; returns int array [n,3] of (x, y, score) in raster order."""
+    img = np.ascontiguousarray(img, np.uint8)
+    cap = img.size // 4 + 16
+    out = np.empty((cap, 3), np.int32)
+    n = lib().orbo_fast(_p(img), img.shape[1], img.shape[0], img.strides[0], t, _p(out), cap)
+    return out[:n].copy()
+
+
+def fast_atan2(y, x):
+    return lib().orbo_fast_atan2(float(y), float(x))
+
+
+def sincos(angle):
+    s, c = C.c_float(), C.c_float()
+    lib().orbo_sincos(float(angle), C.byref(s), C.byref(c))
+    return s.value, c.value
+
+
+def std_sort_perm(nkeys, ulx):
+    """Permutation produced by libstdc++ std::sort with the reference comparator on (nKeys, UL.x) pairs."""
+    a = np.ascontiguousarray(nkeys, np.int32).copy()
+    b = np.ascontiguousarray(ulx, np.int32).copy()
+    lib().orbo_std_sort_pairs(_p(a), _p(b), len(a))
+    return a
+
+
+class OracleExtractor:
+    """Mirror of TC2LI_SLAM::ORBextractor (ORBextractor.h:52-118) on the CPU oracle."""
+
+    def __init__(self, nfeatures=2000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+        self.nlevels = nlevels
+        self.nfeatures = nfeatures
+        self._h = C.c_void_p(lib().orbo_create(nfeatures, scale_factor, nlevels, ini_th, min_th))
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().orbo_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def set_blur_taps(self, taps):
+        t = np.asarray(taps, np.int32)
+        lib().orbo_set_blur_taps(self._h, _p(t))
+
+    def tables(self):
+        n = self.nlevels
+        sf, isf, s2, is2 = (np.empty(n, np.float32) for _ in range(4))
+        quota = np.empty(n, np.int32)
+        umax = np.empty(16, np.int32)
+        lib().orbo_get_tables(self._h, _p(sf), _p(isf), _p(s2), _p(is2), _p(quota), _p(umax))
+        return dict(scale_factors=sf, inv_scale_factors=isf, level_sigma2=s2, inv_level_sigma2=is2, features_per_level=quota, umax=umax)
+
+    def __call__(self, image, lapping=(0, 0)):
+        """Returns (mono_index, keypoints[N] structured, descriptors[N,32])."""
+        if image is None or image.size == 0:
+            return -1, np.empty(0, KP_DTYPE), np.empty((0, 32), np.uint8)
+        image = np.asarray(image)
+        assert image.dtype == np.uint8 and image.ndim == 2
+        if image.strides[1] != 1:
+            image = np.ascontiguousarray(image)
+        r = lib().orbo_extract(self._h, _p(image), image.shape[1], image.shape[0], image.strides[0], int(lapping[0]), int(lapping[1]))
+        if r < 0:
+            return r, np.empty(0, KP_DTYPE), np.empty((0, 32), np.uint8)
+        n = lib().orbo_num_keypoints(self._h)
+        kps = np.empty(n, KP_DTYPE)
+        desc = np.empty((n, 32), np.uint8)
+        lib().orbo_get_keypoints(self._h, _p(kps))
+        lib().orbo_get_descriptors(self._h, _p(desc))
+        return r, kps, desc
+
+    # ---- stage dumps of the last call ----
+    def level(self, l):
+        w, h = C.c_int(), C.c_int()
+        lib().orbo_level_size(self._h, l, C.byref(w), C.byref(h))
+        out = np.empty((h.value, w.value), np.uint8)
+        lib().orbo_get_level(self._h, l, _p(out))
+        return out
+
+    def blurred(self, l):
+        out = np.empty_like(self.level(l))
+        return out if lib().orbo_get_blurred(self._h, l, _p(out)) else None
+
+    def candidates(self, l):
+        """float32 [n,3] (x, y, response); x,y relative to (16,16), cell-row-major then raster order."""
+        n = lib().orbo_num_candidates(self._h, l)
+        out = np.empty((n, 3), np.float32)
+        lib().orbo_get_candidates(self._h, l, _p(out))
+        return out
+
+    def fallback_cells(self, l):
+        return lib().orbo_num_fallback_cells(self._h, l)
+
+    def selected(self, l):
+        n = lib().orbo_num_selected(self._h, l)
+        out = np.empty(n, KP_DTYPE)
+        lib().orbo_get_selected(self._h, l, _p(out))
+        return out
