@@ -1,0 +1,171 @@
+/* orbx.h — C ABI of the B200-native ORB feature-extraction front-end.
+ *
+ * Drop-in boundary for TC2LI_SLAM::ORBextractor (reference: slam_framework/include/ORBextractor.h:52-118,
+ * slam_framework/src/ORBextractor.cc:383-443, 1060-1168).  The reference has no FFI layer of its own: the seam is
+ * the C++ class, whose replacement (tc2li_slam_b200/compat/ORBextractor.h) is a header-only shim over this ABI.
+ * Plain pointers and sizes only; no C++, CUDA or torch types cross this boundary.
+ *
+ * Threading (mirrors ORBextractor.h:92 / Frame.cc:139-142): calls on ONE handle are serialised by the caller;
+ * calls on DIFFERENT handles may run concurrently from different host threads (each handle owns its CUDA stream
+ * and device buffers).  All functions return ORBX_OK (0) or a negative orbx_status unless stated otherwise.
+ */
+#ifndef ORBX_H
+#define ORBX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORBX_MAX_LEVELS 16
+#define ORBX_MAX_DIM 4096 /* candidate coordinates are packed in 12 bits */
+
+typedef enum orbx_status {
+    ORBX_OK = 0,
+    ORBX_ERR_EMPTY = -1,     /* empty image: the value ORBextractor::operator() returns (ORBextractor.cc:1063-1064) */
+    ORBX_ERR_TOO_SMALL = -2, /* some pyramid level has no 35-px FAST cell (the reference divides by zero there) */
+    ORBX_ERR_ARG = -3,
+    ORBX_ERR_CUDA = -4,
+    ORBX_ERR_CAPACITY = -5, /* caller's output capacity < orbx_max_keypoints() */
+    ORBX_ERR_TOO_LARGE = -6 /* width or height > ORBX_MAX_DIM, or per-level quota too large for one CTA's shared memory */
+} orbx_status;
+
+/* Layout-identical to cv::KeyPoint (28 bytes): pt.x, pt.y, size, angle, response, octave, class_id.
+ * class_id stays -1, response is the FAST score, size = (float)(int)(31 * mvScaleFactor[octave]) (ORBextractor.cc:854-864). */
+typedef struct orbx_keypoint {
+    float x, y, size, angle, response;
+    int32_t octave, class_id;
+} orbx_keypoint;
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Single-image handle == one ORBextractor instance
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct orbx_extractor orbx_extractor;
+
+/* replaces ORBextractor::ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST) (ORBextractor.cc:383-443);
+ * `device` = CUDA device ordinal.  Fails with ORBX_ERR_CUDA when no usable GPU exists: there is no CPU fallback. */
+int orbx_create(int nfeatures, float scale_factor, int nlevels, int ini_th_fast, int min_th_fast, int device, orbx_extractor** out);
+void orbx_destroy(orbx_extractor* h);
+
+/* replace GetLevels / GetScaleFactor / GetScaleFactors / GetInverseScaleFactors / GetScaleSigmaSquares /
+ * GetInverseScaleSigmaSquares (ORBextractor.h:70-90); `out` receives nlevels floats.  features_per_level mirrors the
+ * protected mnFeaturesPerLevel (ORBextractor.cc:408-419) for tests. */
+int orbx_get_levels(const orbx_extractor* h);
+float orbx_get_scale_factor(const orbx_extractor* h);
+int orbx_get_scale_factors(const orbx_extractor* h, float* out);
+int orbx_get_inverse_scale_factors(const orbx_extractor* h, float* out);
+int orbx_get_scale_sigma_squares(const orbx_extractor* h, float* out);
+int orbx_get_inverse_scale_sigma_squares(const orbx_extractor* h, float* out);
+int orbx_get_features_per_level(const orbx_extractor* h, int* out);
+
+/* Upper bound of keypoints one call can emit: sum over levels of (quota + 3, at least 4 * initial nodes);
+ * the reference overshoots nfeatures by up to 2 per level (ORBextractor.cc:720-721). */
+int orbx_max_keypoints(const orbx_extractor* h);
+
+/* GaussianBlur 8.8 fixed-point taps (default {18,34,48,56,48,34,18} = OpenCV >= 4.5; OpenCV 4.2 rounded each tap
+ * independently).  Replaces nothing in the reference: it pins the un-vendored OpenCV version. */
+int orbx_set_blur_taps(orbx_extractor* h, const int taps[7]);
+
+/* replaces int ORBextractor::operator()(image, mask, keypoints, descriptors, vLappingArea) (ORBextractor.cc:1060-1141).
+ * image: 8-bit gray, `stride` bytes per row, HOST memory.  lap0/lap1 = vLappingArea[0..1].
+ * keypoints[capacity], descriptors[capacity*32] are HOST buffers, capacity >= orbx_max_keypoints().
+ * *n_keypoints = N, *mono_index = the reference's return value (keypoints outside the lapping area come first, the
+ * ones inside are filled from the back).  Returns ORBX_ERR_EMPTY (-1) for a null/empty image like the reference. */
+int orbx_extract(orbx_extractor* h, const uint8_t* image, int width, int height, size_t stride, int lap0, int lap1,
+                 orbx_keypoint* keypoints, uint8_t* descriptors, int capacity, int* n_keypoints, int* mono_index);
+
+/* replaces the two std::thread extractions of Frame::Frame (Frame.cc:139-142, 1090-1094): both images are issued on
+ * the two handles' own CUDA streams before either is waited for.  lap_left / lap_right = {x0, x1} as Frame::ExtractORB
+ * builds them (Frame.cc:445-455). */
+int orbx_extract_stereo(orbx_extractor* left, orbx_extractor* right, const uint8_t* image_left, const uint8_t* image_right,
+                        int width, int height, size_t stride_left, size_t stride_right, const int lap_left[2], const int lap_right[2],
+                        orbx_keypoint* kps_left, uint8_t* desc_left, int cap_left, int* n_left, int* mono_left,
+                        orbx_keypoint* kps_right, uint8_t* desc_right, int cap_right, int* n_right, int* mono_right);
+
+/* replace the public member mvImagePyramid (ORBextractor.h:92), read by Frame::ComputeStereoMatches
+ * (Frame.cc:848,938,948,953): size and (lazy) device->host copy of level `level` of the last extracted image.
+ * border = 0 copies w x h pixels to dst; border = 19 writes the (w+38) x (h+38) BORDER_REFLECT_101 image the
+ * reference allocates (ORBextractor.cc:1149-1165), dst pointing at its first byte. */
+int orbx_get_level_size(const orbx_extractor* h, int level, int* width, int* height);
+int orbx_get_level(orbx_extractor* h, int level, uint8_t* dst, size_t dst_stride, int border);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Batched extractor: n images of one shape per launch set (frames x {left,right} are just consecutive images).
+ * This is the throughput path (BASELINE.json configs[4]); the single-image handle above is a batch of one.
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct orbx_batch orbx_batch;
+
+int orbx_batch_create(int nfeatures, float scale_factor, int nlevels, int ini_th_fast, int min_th_fast, int device, int width, int height,
+                      int max_images, orbx_batch** out);
+void orbx_batch_destroy(orbx_batch* b);
+int orbx_batch_max_keypoints(const orbx_batch* b); /* per image: K */
+int orbx_batch_max_images(const orbx_batch* b);
+int orbx_batch_set_blur_taps(orbx_batch* b, const int taps[7]);
+/* run on a caller-owned CUDA stream (cudaStream_t passed as void*; NULL restores the handle's own stream) */
+int orbx_batch_set_stream(orbx_batch* b, void* cuda_stream);
+void* orbx_batch_get_stream(const orbx_batch* b);
+
+/* inputs: host images (async H2D; pinned memory makes it overlap), device images (D2D), or the on-device synthetic
+ * generator orbx-synth-v1.  Image i of a stereo batch: frame = i/2, right image when i is odd
+ * (sampled at x+16, noise seed ^ 0x5bd1e995); seed = seed0 + frame. */
+int orbx_batch_upload(orbx_batch* b, const uint8_t* host_images, size_t row_stride, size_t image_stride, int first_image, int n_images);
+int orbx_batch_upload_device(orbx_batch* b, const uint8_t* dev_images, size_t row_stride, size_t image_stride, int first_image, int n_images);
+int orbx_batch_synth(orbx_batch* b, uint32_t seed0, int first_image, int n_images, int stereo);
+
+/* all kernels of the hot path for images [0, n_images), asynchronous on the handle's stream.
+ * lapping: n_images x {lap0, lap1} (host ints) or NULL for {0,0} everywhere. */
+int orbx_batch_run(orbx_batch* b, int n_images, const int* lapping);
+/* async D2H of the results + stream synchronisation.  keypoints [n_images][K], descriptors [n_images][K][32],
+ * counts [n_images], mono_index [n_images]; any pointer may be NULL to skip that array. */
+int orbx_batch_download(orbx_batch* b, int n_images, orbx_keypoint* keypoints, uint8_t* descriptors, int* counts, int* mono_index);
+int orbx_batch_sync(orbx_batch* b);
+int orbx_batch_get_level_size(const orbx_batch* b, int level, int* width, int* height);
+int orbx_batch_get_level(orbx_batch* b, int image, int level, uint8_t* dst, size_t dst_stride, int border);
+
+/* per-stage device timing of the last orbx_batch_run (CUDA events on the launching stream), enabled by
+ * orbx_batch_enable_timing(b, 1).  Stages: 0 pyramid, 1 FAST, 2 blur, 3 octree select, 4 assemble, 5 orient+describe. */
+#define ORBX_NUM_STAGES 6
+int orbx_batch_enable_timing(orbx_batch* b, int on);
+int orbx_batch_stage_ms(orbx_batch* b, float ms[ORBX_NUM_STAGES]);
+int orbx_batch_kernel_launches(const orbx_batch* b); /* kernels launched by one orbx_batch_run */
+
+/* stage dumps for the parity tests (synchronise the stream).  Candidates come back in the reference's order
+ * (cell row-major, raster inside the cell, after the per-cell iniTh/minTh decision): x, y relative to (16,16), response. */
+int orbx_batch_debug_blurred(orbx_batch* b, int image, int level, uint8_t* dst, size_t dst_stride);
+int orbx_batch_debug_candidates(orbx_batch* b, int image, int level, float* xyr, int capacity, int* n);
+int orbx_batch_debug_selected(orbx_batch* b, int image, int level, float* xyr, int capacity, int* n);
+
+int orbx_batch_debug_fallback_cells(orbx_batch* b, int image, int level, int* n_fallback);
+orbx_batch* orbx_extractor_batch(orbx_extractor* h); /* the batch-of-one behind a single-image handle (NULL before the first call) */
+
+/* page-locked host memory, so that the uploads / downloads above overlap with kernels of other handles */
+void* orbx_alloc_pinned(size_t bytes);
+void orbx_free_pinned(void* p);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Host-only helpers (no GPU needed): the constants ORBextractor's constructor derives (ORBextractor.cc:383-443) and the
+ * per-level geometry (level size :1147-1148, FAST grid :771-777, quadtree roots :533, keypoint capacity).
+ * out[8] = {w, h, nCols, nRows, wCell, hCell, nIni, capacity}.
+ * ---------------------------------------------------------------------------------------------------------------- */
+int orbx_tables(int nfeatures, float scale_factor, int nlevels, int ini_th_fast, int min_th_fast, float* scale_factors, float* inv_scale_factors,
+                float* level_sigma2, float* inv_level_sigma2, int* features_per_level, int umax[16]);
+int orbx_level_geometry(int nfeatures, float scale_factor, int nlevels, int width, int height, int level, int out[8]);
+
+/* test hooks for the exactness-critical routines.  orbx_debug_sort: libstdc++-exact std::sort emulation on n keys
+ * (ORBextractor.cc:674); perm[i] = input index that ends in slot i; force_depth >= 0 overrides the introsort depth limit
+ * (exercises the heap fallback); on_device = 1 runs it in a CUDA thread as the quadtree kernel does.
+ * orbx_debug_sincos: the kernel's sinf/cosf of angle_deg * (float)(pi/180) (ORBextractor.cc:86-88);
+ * orbx_debug_atan2: the kernel's cv::fastAtan2 (ORBextractor.cc:76). */
+int orbx_debug_sort(const uint32_t* keys, int n, int* perm, int force_depth, int on_device);
+int orbx_debug_sincos(const float* angles_deg, float* out_sin, float* out_cos, int n);
+int orbx_debug_atan2(const float* y, const float* x, float* out, int n);
+
+const char* orbx_version(void);
+const char* orbx_last_error(void); /* thread-local description of the last failure */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORBX_H */

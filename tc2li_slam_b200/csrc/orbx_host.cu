@@ -1,0 +1,800 @@
+// orbx_host.cu — host side of the C ABI (include/orbx.h): geometry, device buffers, launch sequence, copies.
+//
+// Mirrors, on the host, what TC2LI_SLAM::ORBextractor computes once per instance (ORBextractor.cc:383-443: scale tables,
+// per-level quotas, umax) and per call outside the pixel loops (level sizes ORBextractor.cc:1147-1148, cell grid
+// :759-777, quadtree roots :533-535), and OpenCV's bilinear-resize coefficient tables.  Everything per
+// pixel / per candidate / per keypoint runs in the CUDA kernels of this directory.  There is no CPU fallback: without a
+// usable device every entry point fails with ORBX_ERR_CUDA.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "orbx_internal.cuh"
+#include "stdsort_emul.cuh"
+
+namespace orbx {
+void launch_debug_sort_impl(unsigned long long* buf, int n, int forceDepth, cudaStream_t s);
+cudaError_t octree_configure(int maxNodeCap);
+}
+
+using namespace orbx;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+int cuda_fail(cudaError_t e, const char* what) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return ORBX_ERR_CUDA;
+}
+#define CU(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) return cuda_fail(e__, #x); } while (0)
+
+static const signed char kPatternHost[1024] = {
+#include "orb_pattern.inc"
+};
+
+inline int cv_round(float v) { return (int)lrintf(v); }    // cvRound: round half to even
+inline int cv_round_d(double v) { return (int)lrint(v); }
+inline short sat_short(int v) { return (short)(v < -32768 ? -32768 : (v > 32767 ? 32767 : v)); }
+
+struct Params {
+    int nfeatures, nlevels, iniTh, minTh;
+    float scaleFactorF;
+    std::vector<float> sf, isf, sig2, isig2;
+    std::vector<int> quota;
+    int umax[16];
+};
+
+// ORBextractor::ORBextractor (ORBextractor.cc:383-443)
+int make_params(int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh, Params& p) {
+    if (nlevels < 1 || nlevels > ORBX_MAX_LEVELS) return fail(ORBX_ERR_ARG, "nlevels must be in [1, ORBX_MAX_LEVELS]");
+    if (nfeatures < 1 || nfeatures > 30000) return fail(ORBX_ERR_ARG, "nfeatures must be in [1, 30000]");
+    if (!(scaleFactor > 1.0f) || scaleFactor > 4.f) return fail(ORBX_ERR_ARG, "scaleFactor must be in (1, 4]");
+    if (minTh < 1 || iniTh < minTh || iniTh > 254) return fail(ORBX_ERR_ARG, "need 1 <= minThFAST <= iniThFAST <= 254");
+    p.nfeatures = nfeatures; p.nlevels = nlevels; p.iniTh = iniTh; p.minTh = minTh; p.scaleFactorF = scaleFactor;
+    const double sfd = (double)scaleFactor;  // the member is a double initialised from the float argument (ORBextractor.h:105)
+    p.sf.assign(nlevels, 1.f); p.sig2.assign(nlevels, 1.f); p.isf.assign(nlevels, 1.f); p.isig2.assign(nlevels, 1.f);
+    for (int i = 1; i < nlevels; ++i) {
+        p.sf[i] = (float)((double)p.sf[i - 1] * sfd);
+        p.sig2[i] = p.sf[i] * p.sf[i];
+    }
+    for (int i = 0; i < nlevels; ++i) { p.isf[i] = 1.0f / p.sf[i]; p.isig2[i] = 1.0f / p.sig2[i]; }
+    p.quota.assign(nlevels, 0);
+    const float factor = (float)(1.0 / sfd);  // 1.0f / double
+    float nDesired = (float)nfeatures * (1.f - factor) / (1.f - (float)std::pow((double)factor, (double)nlevels));
+    int sum = 0;
+    for (int l = 0; l < nlevels - 1; ++l) {
+        p.quota[l] = cv_round(nDesired);
+        sum += p.quota[l];
+        nDesired *= factor;
+    }
+    p.quota[nlevels - 1] = std::max(nfeatures - sum, 0);
+    // circular patch: umax[v] = half width of row v (ORBextractor.cc:427-442)
+    int um[kHalfPatch + 2] = {0};
+    const int vmax = (int)std::floor(kHalfPatch * std::sqrt(2.f) / 2 + 1);
+    const int vmin = (int)std::ceil(kHalfPatch * std::sqrt(2.f) / 2);
+    const double hp2 = (double)kHalfPatch * kHalfPatch;
+    for (int v = 0; v <= vmax; ++v) um[v] = cv_round_d(std::sqrt(hp2 - (double)v * v));
+    for (int v = kHalfPatch, v0 = 0; v >= vmin; --v) {
+        while (um[v0] == um[v0 + 1]) ++v0;
+        um[v] = v0;
+        ++v0;
+    }
+    for (int v = 0; v < 16; ++v) p.umax[v] = um[v];
+    return ORBX_OK;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------------------
+struct orbx_batch {
+    Params p;
+    Geom g;
+    Buffers buf;
+    int device = 0, width = 0, height = 0, maxImages = 0;
+    int taps[7] = {18, 34, 48, 56, 48, 34, 18};
+    cudaStream_t own = nullptr, stream = nullptr;
+    std::vector<void*> allocs;
+    ResizeTab tabs[ORBX_MAX_LEVELS];
+    size_t pyrBytes = 0, candElems = 0;
+    uint8_t* borderScratch = nullptr;
+    size_t borderScratchBytes = 0;
+    bool timing = false;
+    cudaEvent_t ev[ORBX_NUM_STAGES + 1] = {};
+    int launches = 0;
+    int lastImages = 0;
+    std::vector<int> hostLap;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(orbx_batch* b, T** out, size_t count) {
+    void* p = nullptr;
+    CU(cudaMalloc(&p, std::max<size_t>(count * sizeof(T), 256)));
+    b->allocs.push_back(p);
+    *out = (T*)p;
+    return ORBX_OK;
+}
+
+// level sizes, FAST grid, quadtree roots, capacities
+int make_geom(const Params& p, int W, int H, int maxImages, Geom& g) {
+    std::memset(&g, 0, sizeof(g));
+    if (W > ORBX_MAX_DIM || H > ORBX_MAX_DIM) return fail(ORBX_ERR_TOO_LARGE, "image larger than ORBX_MAX_DIM");
+    g.nlevels = p.nlevels; g.iniTh = p.iniTh; g.minTh = p.minTh; g.maxImages = maxImages;
+    unsigned long long planeOff = 0, candOff = 0;
+    int selOff = 0, cellOff = 0;
+    for (int l = 0; l < p.nlevels; ++l) {
+        LevelGeom& L = g.lv[l];
+        L.w = cv_round((float)W * p.isf[l]);  // ORBextractor.cc:1147-1148: always from the ORIGINAL size
+        L.h = cv_round((float)H * p.isf[l]);
+        const int bw = L.w - 2 * kBorder, bh = L.h - 2 * kBorder;  // maxBorder - minBorder
+        if (bw < 35 || bh < 35) return fail(ORBX_ERR_TOO_SMALL, "a pyramid level is smaller than one 35-px FAST cell");
+        L.pitch = (int)align_up((size_t)L.w, 128);
+        const float width = (float)bw, height = (float)bh;
+        L.nCols = (int)(width / 35.f);
+        L.nRows = (int)(height / 35.f);
+        L.wCell = (int)std::ceil(width / (float)L.nCols);
+        L.hCell = (int)std::ceil(height / (float)L.nRows);
+        if (L.wCell > kMaxCell || L.hCell > kMaxCell) return fail(ORBX_ERR_TOO_LARGE, "FAST cell larger than the kernel tile");
+        L.quota = p.quota[l];
+        L.nIni = (int)std::round((float)bw / (float)bh);  // ORBextractor.cc:533
+        if (L.nIni < 1) return fail(ORBX_ERR_TOO_SMALL, "portrait level: the reference's quadtree has no root node (nIni == 0)");
+        L.hX = (float)bw / (float)L.nIni;
+        // strict 3x3 maxima: at most one per 2x2 block of each cell interior
+        L.candCap = L.nCols * L.nRows * ((L.wCell + 1) / 2) * ((L.hCell + 1) / 2);
+        L.selCap = std::max(L.quota + 3, 4 * L.nIni);
+        L.nodeCap = L.selCap + 8;
+        if (L.nodeCap > 16383) return fail(ORBX_ERR_TOO_LARGE, "per-level quota too large");
+        L.selOff = selOff; selOff += L.selCap;
+        L.cellOff = cellOff; cellOff += L.nCols * L.nRows;
+        L.sf = p.sf[l];
+        L.kpSize = (float)(int)(31 * p.sf[l]);  // PATCH_SIZE*mvScaleFactor[level] truncated (ORBextractor.cc:854)
+        L.planeBytes = (unsigned long long)L.pitch * L.h;
+        L.planeOff = planeOff; planeOff += L.planeBytes * maxImages;
+        L.candOff = candOff; candOff += (unsigned long long)L.candCap * maxImages;
+    }
+    g.K = selOff;
+    g.cellsPerImage = cellOff;
+    if (g.K > 32767) return fail(ORBX_ERR_TOO_LARGE, "keypoint capacity per image exceeds 32767");
+    return ORBX_OK;
+}
+
+// cv::resize INTER_LINEAR 8U coefficient tables: 11-bit fixed point, clamped source index on x
+void make_resize_tables(int sn, int dn, bool clampIndex, std::vector<short>& ofs, std::vector<short>& coef) {
+    ofs.resize(dn); coef.resize(2 * (size_t)dn);
+    const double scale = 1.0 / ((double)dn / (double)sn);
+    for (int d = 0; d < dn; ++d) {
+        float f = (float)(((double)d + 0.5) * scale - 0.5);
+        int s = (int)std::floor(f);
+        f -= (float)s;
+        if (clampIndex) {
+            if (s < 0) { f = 0.f; s = 0; }
+            if (s >= sn - 1) { f = 0.f; s = sn - 1; }
+        }
+        ofs[d] = (short)s;
+        coef[2 * d] = sat_short(cv_round((1.f - f) * 2048.f));
+        coef[2 * d + 1] = sat_short(cv_round(f * 2048.f));
+    }
+}
+
+int batch_alloc(orbx_batch* b) {
+    const Geom& g = b->g;
+    const int n = b->maxImages;
+    const LevelGeom& last = g.lv[g.nlevels - 1];
+    b->pyrBytes = (size_t)(last.planeOff + last.planeBytes * n);
+    b->candElems = (size_t)(last.candOff + (unsigned long long)last.candCap * n);
+    Buffers& B = b->buf;
+    int r;
+    if ((r = dev_alloc(b, &B.pyr, b->pyrBytes))) return r;
+    if ((r = dev_alloc(b, &B.blur, b->pyrBytes))) return r;
+    if ((r = dev_alloc(b, &B.cand, b->candElems))) return r;
+    if ((r = dev_alloc(b, &B.pnode, b->candElems))) return r;
+    if ((r = dev_alloc(b, &B.candCount, (size_t)n * ORBX_MAX_LEVELS))) return r;
+    if ((r = dev_alloc(b, &B.cellFlags, (size_t)n * g.cellsPerImage))) return r;
+    if ((r = dev_alloc(b, &B.sel, (size_t)n * g.K))) return r;
+    if ((r = dev_alloc(b, &B.selCount, (size_t)n * ORBX_MAX_LEVELS))) return r;
+    if ((r = dev_alloc(b, &B.lapping, (size_t)n * 2))) return r;
+    if ((r = dev_alloc(b, &B.kps, (size_t)n * g.K))) return r;
+    if ((r = dev_alloc(b, &B.desc, (size_t)n * g.K * 32))) return r;
+    if ((r = dev_alloc(b, &B.work, (size_t)n * g.K))) return r;
+    if ((r = dev_alloc(b, &B.outCount, (size_t)n))) return r;
+    if ((r = dev_alloc(b, &B.outMono, (size_t)n))) return r;
+    if ((r = dev_alloc(b, &B.errFlag, 1))) return r;
+    CU(cudaMemset(B.errFlag, 0, sizeof(int)));
+    CU(cudaMemset(B.lapping, 0, (size_t)n * 2 * sizeof(int)));
+    CU(cudaMemset(B.pyr, 0, b->pyrBytes));
+    // resize tables
+    for (int l = 1; l < g.nlevels; ++l) {
+        std::vector<short> xo, xa, yo, yb;
+        make_resize_tables(g.lv[l - 1].w, g.lv[l].w, true, xo, xa);
+        make_resize_tables(g.lv[l - 1].h, g.lv[l].h, false, yo, yb);
+        short *dxo, *dxa, *dyo, *dyb;
+        if ((r = dev_alloc(b, &dxo, xo.size()))) return r;
+        if ((r = dev_alloc(b, &dxa, xa.size()))) return r;
+        if ((r = dev_alloc(b, &dyo, yo.size()))) return r;
+        if ((r = dev_alloc(b, &dyb, yb.size()))) return r;
+        CU(cudaMemcpy(dxo, xo.data(), xo.size() * 2, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(dxa, xa.data(), xa.size() * 2, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(dyo, yo.data(), yo.size() * 2, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(dyb, yb.data(), yb.size() * 2, cudaMemcpyHostToDevice));
+        b->tabs[l] = ResizeTab{dxo, dxa, dyo, dyb};
+    }
+    return ORBX_OK;
+}
+
+int check_images(const orbx_batch* b, int first, int n) {
+    if (!b) return fail(ORBX_ERR_ARG, "null batch");
+    if (first < 0 || n < 0 || first + n > b->maxImages) return fail(ORBX_ERR_ARG, "image range outside [0, max_images)");
+    return ORBX_OK;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* orbx_version(void) { return "orbx 0.1 (sm_100a)"; }
+const char* orbx_last_error(void) { return g_err.c_str(); }
+
+int orbx_batch_create(int nfeatures, float scale_factor, int nlevels, int ini_th_fast, int min_th_fast, int device, int width, int height,
+                      int max_images, orbx_batch** out) {
+    if (!out) return fail(ORBX_ERR_ARG, "null out pointer");
+    *out = nullptr;
+    if (width <= 0 || height <= 0) return fail(ORBX_ERR_EMPTY, "empty image");
+    if (max_images < 1 || max_images > 65535) return fail(ORBX_ERR_ARG, "max_images must be in [1, 65535]");
+    orbx_batch* b = new orbx_batch();
+    int r = make_params(nfeatures, scale_factor, nlevels, ini_th_fast, min_th_fast, b->p);
+    if (r == ORBX_OK) r = make_geom(b->p, width, height, max_images, b->g);
+    if (r != ORBX_OK) { delete b; return r; }
+    b->device = device; b->width = width; b->height = height; b->maxImages = max_images;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || device < 0 || device >= ndev) {
+        delete b;
+        return fail(ORBX_ERR_CUDA, e != cudaSuccess ? std::string("no usable CUDA device: ") + cudaGetErrorString(e)
+                                                    : std::string("CUDA device ordinal out of range (there is no CPU fallback)"));
+    }
+    DeviceGuard dg(device);
+    auto bail = [&](int code) { orbx_batch_destroy(b); return code; };
+    if ((e = cudaStreamCreateWithFlags(&b->own, cudaStreamNonBlocking)) != cudaSuccess) return bail(cuda_fail(e, "cudaStreamCreate"));
+    b->stream = b->own;
+    if ((r = batch_alloc(b)) != ORBX_OK) return bail(r);
+    if ((e = upload_describe_constants(kPatternHost, b->p.umax)) != cudaSuccess) return bail(cuda_fail(e, "constant upload"));
+    int maxCap = 0;
+    for (int l = 0; l < b->g.nlevels; ++l) maxCap = std::max(maxCap, b->g.lv[l].nodeCap);
+    if ((e = octree_configure(maxCap)) != cudaSuccess) return bail(cuda_fail(e, "octree shared-memory configuration"));
+    for (auto& ev : b->ev)
+        if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(cuda_fail(e, "cudaEventCreate"));
+    *out = b;
+    return ORBX_OK;
+}
+
+void orbx_batch_destroy(orbx_batch* b) {
+    if (!b) return;
+    DeviceGuard dg(b->device);
+    if (b->own) cudaStreamSynchronize(b->own);
+    for (void* p : b->allocs) cudaFree(p);
+    if (b->borderScratch) cudaFree(b->borderScratch);
+    for (auto& ev : b->ev) if (ev) cudaEventDestroy(ev);
+    if (b->own) cudaStreamDestroy(b->own);
+    delete b;
+}
+
+int orbx_batch_max_keypoints(const orbx_batch* b) { return b ? b->g.K : ORBX_ERR_ARG; }
+int orbx_batch_max_images(const orbx_batch* b) { return b ? b->maxImages : ORBX_ERR_ARG; }
+int orbx_batch_set_blur_taps(orbx_batch* b, const int taps[7]) {
+    if (!b || !taps) return fail(ORBX_ERR_ARG, "null argument");
+    int sum = 0;
+    for (int i = 0; i < 7; ++i) { if (taps[i] < 0 || taps[i] > 256) return fail(ORBX_ERR_ARG, "tap outside [0,256]"); sum += taps[i]; }
+    if (sum > 257) return fail(ORBX_ERR_ARG, "taps must sum to about 256 (8.8 fixed point)");
+    std::memcpy(b->taps, taps, sizeof(b->taps));
+    return ORBX_OK;
+}
+int orbx_batch_set_stream(orbx_batch* b, void* s) {
+    if (!b) return fail(ORBX_ERR_ARG, "null batch");
+    b->stream = s ? (cudaStream_t)s : b->own;
+    return ORBX_OK;
+}
+void* orbx_batch_get_stream(const orbx_batch* b) { return b ? (void*)b->stream : nullptr; }
+
+int orbx_batch_upload(orbx_batch* b, const uint8_t* host_images, size_t row_stride, size_t image_stride, int first, int n) {
+    int r = check_images(b, first, n);
+    if (r) return r;
+    if (!host_images) return fail(ORBX_ERR_EMPTY, "null image");
+    if (row_stride < (size_t)b->width) return fail(ORBX_ERR_ARG, "row stride smaller than the width");
+    DeviceGuard dg(b->device);
+    const LevelGeom& L0 = b->g.lv[0];
+    if (image_stride == row_stride * (size_t)b->height || n == 1) {
+        // the images form one tall 2-D array: a single strided copy (planeBytes == pitch * h)
+        CU(cudaMemcpy2DAsync(b->buf.pyr + L0.planeOff + (size_t)first * L0.planeBytes, L0.pitch, host_images, row_stride, b->width,
+                             (size_t)b->height * n, cudaMemcpyHostToDevice, b->stream));
+    } else {
+        for (int i = 0; i < n; ++i)
+            CU(cudaMemcpy2DAsync(b->buf.pyr + L0.planeOff + (size_t)(first + i) * L0.planeBytes, L0.pitch, host_images + (size_t)i * image_stride,
+                                 row_stride, b->width, b->height, cudaMemcpyHostToDevice, b->stream));
+    }
+    return ORBX_OK;
+}
+
+int orbx_batch_upload_device(orbx_batch* b, const uint8_t* dev_images, size_t row_stride, size_t image_stride, int first, int n) {
+    int r = check_images(b, first, n);
+    if (r) return r;
+    if (!dev_images) return fail(ORBX_ERR_EMPTY, "null image");
+    if (row_stride < (size_t)b->width) return fail(ORBX_ERR_ARG, "row stride smaller than the width");
+    DeviceGuard dg(b->device);
+    const LevelGeom& L0 = b->g.lv[0];
+    if (image_stride == row_stride * (size_t)b->height || n == 1) {
+        CU(cudaMemcpy2DAsync(b->buf.pyr + L0.planeOff + (size_t)first * L0.planeBytes, L0.pitch, dev_images, row_stride, b->width,
+                             (size_t)b->height * n, cudaMemcpyDeviceToDevice, b->stream));
+    } else {
+        for (int i = 0; i < n; ++i)
+            CU(cudaMemcpy2DAsync(b->buf.pyr + L0.planeOff + (size_t)(first + i) * L0.planeBytes, L0.pitch, dev_images + (size_t)i * image_stride,
+                                 row_stride, b->width, b->height, cudaMemcpyDeviceToDevice, b->stream));
+    }
+    return ORBX_OK;
+}
+
+int orbx_batch_synth(orbx_batch* b, uint32_t seed0, int first, int n, int stereo) {
+    int r = check_images(b, first, n);
+    if (r) return r;
+    if (n == 0) return ORBX_OK;
+    DeviceGuard dg(b->device);
+    const LevelGeom& L0 = b->g.lv[0];
+    launch_synth(b->buf.pyr + L0.planeOff, L0.w, L0.h, L0.pitch, (size_t)L0.planeBytes, seed0, first, n, stereo, b->stream);
+    CU(cudaGetLastError());
+    return ORBX_OK;
+}
+
+int orbx_batch_run(orbx_batch* b, int n, const int* lapping) {
+    int r = check_images(b, 0, n);
+    if (r) return r;
+    if (n == 0) return ORBX_OK;
+    DeviceGuard dg(b->device);
+    const Geom& g = b->g;
+    cudaStream_t s = b->stream;
+    int launches = 0;
+    if (lapping) {
+        b->hostLap.assign(lapping, lapping + 2 * (size_t)n);
+        CU(cudaMemcpyAsync(b->buf.lapping, b->hostLap.data(), (size_t)n * 2 * sizeof(int), cudaMemcpyHostToDevice, s));
+    } else
+        CU(cudaMemsetAsync(b->buf.lapping, 0, (size_t)n * 2 * sizeof(int), s));
+    CU(cudaMemsetAsync(b->buf.candCount, 0, (size_t)n * ORBX_MAX_LEVELS * sizeof(int), s));
+    int evi = 0;
+    auto mark = [&]() { if (b->timing) cudaEventRecord(b->ev[evi++], s); };
+    mark();
+    for (int l = 1; l < g.nlevels; ++l) { launch_pyramid_level(g, b->buf, l, b->tabs[l], n, s); ++launches; }
+    mark();
+    launch_fast(g, b->buf, n, s); ++launches;
+    mark();
+    for (int l = 0; l < g.nlevels; ++l) { launch_blur(g, b->buf, l, n, b->taps, s); ++launches; }
+    mark();
+    {
+        cudaError_t e = launch_octree(g, b->buf, n, s); ++launches;
+        if (e != cudaSuccess) return cuda_fail(e, "octree launch");
+    }
+    mark();
+    launch_assemble(g, b->buf, n, s); ++launches;
+    mark();
+    launch_describe(g, b->buf, n, s); ++launches;
+    mark();
+    CU(cudaGetLastError());
+    b->launches = launches;
+    b->lastImages = n;
+    return ORBX_OK;
+}
+
+int orbx_batch_sync(orbx_batch* b) {
+    if (!b) return fail(ORBX_ERR_ARG, "null batch");
+    DeviceGuard dg(b->device);
+    CU(cudaStreamSynchronize(b->stream));
+    return ORBX_OK;
+}
+
+int orbx_batch_download(orbx_batch* b, int n, orbx_keypoint* keypoints, uint8_t* descriptors, int* counts, int* mono_index) {
+    int r = check_images(b, 0, n);
+    if (r) return r;
+    DeviceGuard dg(b->device);
+    cudaStream_t s = b->stream;
+    const size_t K = (size_t)b->g.K;
+    int err = 0;
+    if (n) {
+        if (keypoints) CU(cudaMemcpyAsync(keypoints, b->buf.kps, n * K * sizeof(orbx_keypoint), cudaMemcpyDeviceToHost, s));
+        if (descriptors) CU(cudaMemcpyAsync(descriptors, b->buf.desc, n * K * 32, cudaMemcpyDeviceToHost, s));
+        if (counts) CU(cudaMemcpyAsync(counts, b->buf.outCount, n * sizeof(int), cudaMemcpyDeviceToHost, s));
+        if (mono_index) CU(cudaMemcpyAsync(mono_index, b->buf.outMono, n * sizeof(int), cudaMemcpyDeviceToHost, s));
+    }
+    CU(cudaMemcpyAsync(&err, b->buf.errFlag, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (err) {
+        cudaMemsetAsync(b->buf.errFlag, 0, sizeof(int), s);
+        return fail(ORBX_ERR_CAPACITY, err == 1 ? "device candidate buffer overflow" : "device quadtree capacity exceeded");
+    }
+    return ORBX_OK;
+}
+
+int orbx_batch_get_level_size(const orbx_batch* b, int level, int* width, int* height) {
+    if (!b || level < 0 || level >= b->g.nlevels) return fail(ORBX_ERR_ARG, "bad level");
+    if (width) *width = b->g.lv[level].w;
+    if (height) *height = b->g.lv[level].h;
+    return ORBX_OK;
+}
+
+static int copy_plane(orbx_batch* b, const uint8_t* base, int image, int level, uint8_t* dst, size_t dst_stride, int border) {
+    if (!b || level < 0 || level >= b->g.nlevels || image < 0 || image >= b->maxImages || !dst) return fail(ORBX_ERR_ARG, "bad argument");
+    if (border != 0 && border != kEdge) return fail(ORBX_ERR_ARG, "border must be 0 or 19");
+    DeviceGuard dg(b->device);
+    const LevelGeom& L = b->g.lv[level];
+    const uint8_t* src = base + L.planeOff + (size_t)image * L.planeBytes;
+    if (border == 0) {
+        if (dst_stride < (size_t)L.w) return fail(ORBX_ERR_ARG, "dst stride too small");
+        CU(cudaMemcpy2DAsync(dst, dst_stride, src, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost, b->stream));
+    } else {
+        const int bw = L.w + 2 * kEdge, bh = L.h + 2 * kEdge;
+        if (dst_stride < (size_t)bw) return fail(ORBX_ERR_ARG, "dst stride too small");
+        const size_t need = (size_t)bw * bh;
+        if (need > b->borderScratchBytes) {
+            if (b->borderScratch) cudaFree(b->borderScratch);
+            b->borderScratch = nullptr; b->borderScratchBytes = 0;
+            CU(cudaMalloc((void**)&b->borderScratch, need));
+            b->borderScratchBytes = need;
+        }
+        launch_border(src, L.w, L.h, L.pitch, b->borderScratch, bw, b->stream);
+        CU(cudaGetLastError());
+        CU(cudaMemcpy2DAsync(dst, dst_stride, b->borderScratch, bw, bw, bh, cudaMemcpyDeviceToHost, b->stream));
+    }
+    CU(cudaStreamSynchronize(b->stream));
+    return ORBX_OK;
+}
+
+int orbx_batch_get_level(orbx_batch* b, int image, int level, uint8_t* dst, size_t dst_stride, int border) {
+    return copy_plane(b, b ? b->buf.pyr : nullptr, image, level, dst, dst_stride, border);
+}
+int orbx_batch_debug_blurred(orbx_batch* b, int image, int level, uint8_t* dst, size_t dst_stride) {
+    return copy_plane(b, b ? b->buf.blur : nullptr, image, level, dst, dst_stride, 0);
+}
+
+int orbx_batch_enable_timing(orbx_batch* b, int on) {
+    if (!b) return fail(ORBX_ERR_ARG, "null batch");
+    b->timing = on != 0;
+    return ORBX_OK;
+}
+int orbx_batch_stage_ms(orbx_batch* b, float ms[ORBX_NUM_STAGES]) {
+    if (!b || !ms) return fail(ORBX_ERR_ARG, "null argument");
+    if (!b->timing) return fail(ORBX_ERR_ARG, "timing not enabled");
+    DeviceGuard dg(b->device);
+    CU(cudaEventSynchronize(b->ev[ORBX_NUM_STAGES]));
+    for (int i = 0; i < ORBX_NUM_STAGES; ++i) CU(cudaEventElapsedTime(&ms[i], b->ev[i], b->ev[i + 1]));
+    return ORBX_OK;
+}
+int orbx_batch_kernel_launches(const orbx_batch* b) { return b ? b->launches : ORBX_ERR_ARG; }
+
+int orbx_batch_debug_candidates(orbx_batch* b, int image, int level, float* xyr, int capacity, int* n) {
+    if (!b || level < 0 || level >= b->g.nlevels || image < 0 || image >= b->maxImages || !n) return fail(ORBX_ERR_ARG, "bad argument");
+    DeviceGuard dg(b->device);
+    const LevelGeom& L = b->g.lv[level];
+    CU(cudaStreamSynchronize(b->stream));
+    int cnt = 0;
+    CU(cudaMemcpy(&cnt, b->buf.candCount + image * ORBX_MAX_LEVELS + level, sizeof(int), cudaMemcpyDeviceToHost));
+    cnt = std::min(cnt, L.candCap);
+    *n = cnt;
+    if (!xyr || cnt == 0) return ORBX_OK;
+    std::vector<uint32_t> c(cnt);
+    CU(cudaMemcpy(c.data(), b->buf.cand + L.candOff + (size_t)image * L.candCap, (size_t)cnt * 4, cudaMemcpyDeviceToHost));
+    // the device keeps candidates unordered; present them in the reference's vector order
+    std::sort(c.begin(), c.end(), [&](uint32_t a, uint32_t d) { return cand_order_key(a, L.wCell, L.hCell) < cand_order_key(d, L.wCell, L.hCell); });
+    for (int i = 0; i < std::min(cnt, capacity); ++i) {
+        xyr[3 * i] = (float)cand_x(c[i]); xyr[3 * i + 1] = (float)cand_y(c[i]); xyr[3 * i + 2] = (float)cand_r(c[i]);
+    }
+    return ORBX_OK;
+}
+
+int orbx_batch_debug_selected(orbx_batch* b, int image, int level, float* xyr, int capacity, int* n) {
+    if (!b || level < 0 || level >= b->g.nlevels || image < 0 || image >= b->maxImages || !n) return fail(ORBX_ERR_ARG, "bad argument");
+    DeviceGuard dg(b->device);
+    const LevelGeom& L = b->g.lv[level];
+    CU(cudaStreamSynchronize(b->stream));
+    int cnt = 0;
+    CU(cudaMemcpy(&cnt, b->buf.selCount + image * ORBX_MAX_LEVELS + level, sizeof(int), cudaMemcpyDeviceToHost));
+    *n = cnt;
+    if (!xyr || cnt == 0) return ORBX_OK;
+    std::vector<uint32_t> c(cnt);
+    CU(cudaMemcpy(c.data(), b->buf.sel + (size_t)image * b->g.K + L.selOff, (size_t)cnt * 4, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < std::min(cnt, capacity); ++i) {
+        xyr[3 * i] = (float)cand_x(c[i]); xyr[3 * i + 1] = (float)cand_y(c[i]); xyr[3 * i + 2] = (float)cand_r(c[i]);
+    }
+    return ORBX_OK;
+}
+
+int orbx_batch_debug_fallback_cells(orbx_batch* b, int image, int level, int* n_fallback) {
+    if (!b || level < 0 || level >= b->g.nlevels || image < 0 || image >= b->maxImages || !n_fallback) return fail(ORBX_ERR_ARG, "bad argument");
+    DeviceGuard dg(b->device);
+    const LevelGeom& L = b->g.lv[level];
+    CU(cudaStreamSynchronize(b->stream));
+    std::vector<uint8_t> f((size_t)L.nCols * L.nRows);
+    CU(cudaMemcpy(f.data(), b->buf.cellFlags + (size_t)image * b->g.cellsPerImage + L.cellOff, f.size(), cudaMemcpyDeviceToHost));
+    int c = 0;
+    for (uint8_t v : f) c += (v == 2);
+    *n_fallback = c;
+    return ORBX_OK;
+}
+
+// ---- pinned host memory for callers that want overlapped copies ----
+void* orbx_alloc_pinned(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { g_err = "cudaHostAlloc failed"; return nullptr; }
+    return p;
+}
+void orbx_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+
+// ---- constants / host-logic hooks (no GPU needed) ----
+int orbx_tables(int nfeatures, float scale_factor, int nlevels, int ini_th_fast, int min_th_fast, float* sf, float* isf, float* sig2, float* isig2,
+                int* quota, int* umax) {
+    Params p;
+    int r = make_params(nfeatures, scale_factor, nlevels, ini_th_fast, min_th_fast, p);
+    if (r) return r;
+    for (int i = 0; i < nlevels; ++i) {
+        if (sf) sf[i] = p.sf[i];
+        if (isf) isf[i] = p.isf[i];
+        if (sig2) sig2[i] = p.sig2[i];
+        if (isig2) isig2[i] = p.isig2[i];
+        if (quota) quota[i] = p.quota[i];
+    }
+    if (umax) std::memcpy(umax, p.umax, sizeof(p.umax));
+    return ORBX_OK;
+}
+
+int orbx_level_geometry(int nfeatures, float scale_factor, int nlevels, int width, int height, int level, int out[8]) {
+    Params p;
+    int r = make_params(nfeatures, scale_factor, nlevels, 20, 7, p);
+    if (r) return r;
+    Geom g;
+    if ((r = make_geom(p, width, height, 1, g))) return r;
+    if (level < 0 || level >= nlevels || !out) return fail(ORBX_ERR_ARG, "bad level");
+    const LevelGeom& L = g.lv[level];
+    out[0] = L.w; out[1] = L.h; out[2] = L.nCols; out[3] = L.nRows; out[4] = L.wCell; out[5] = L.hCell; out[6] = L.nIni; out[7] = L.selCap;
+    return ORBX_OK;
+}
+
+// sorts n (key, index) pairs exactly like libstdc++ std::sort with a key-only comparator; perm[i] = input index at slot i.
+// on_device != 0 runs the same routine in a single CUDA thread (the way the quadtree kernel uses it).
+int orbx_debug_sort(const uint32_t* keys, int n, int* perm, int force_depth, int on_device) {
+    if (!keys || !perm || n < 0 || n > 65535) return fail(ORBX_ERR_ARG, "bad argument");
+    std::vector<unsigned long long> e(n);
+    for (int i = 0; i < n; ++i) e[i] = ((unsigned long long)keys[i] << 16) | (unsigned)i;
+    if (on_device) {
+        unsigned long long* d = nullptr;
+        CU(cudaMalloc((void**)&d, std::max<size_t>(8, (size_t)n * 8)));
+        cudaError_t er = cudaMemcpy(d, e.data(), (size_t)n * 8, cudaMemcpyHostToDevice);
+        if (er == cudaSuccess) { launch_debug_sort_impl(d, n, force_depth, 0); er = cudaDeviceSynchronize(); }
+        if (er == cudaSuccess) er = cudaMemcpy(e.data(), d, (size_t)n * 8, cudaMemcpyDeviceToHost);
+        cudaFree(d);
+        if (er != cudaSuccess) return cuda_fail(er, "device sort");
+    } else
+        StdSortEmul<16>::sort(e.data(), n, force_depth);
+    for (int i = 0; i < n; ++i) perm[i] = (int)(e[i] & 0xFFFF);
+    return ORBX_OK;
+}
+
+int orbx_debug_sincos(const float* angles_deg, float* out_sin, float* out_cos, int n) {
+    float *d = nullptr;
+    CU(cudaMalloc((void**)&d, std::max<size_t>(4, (size_t)n * 12)));
+    cudaError_t er = cudaMemcpy(d, angles_deg, (size_t)n * 4, cudaMemcpyHostToDevice);
+    if (er == cudaSuccess) { launch_debug_sincos(d, d + n, d + 2 * (size_t)n, n, 0); er = cudaDeviceSynchronize(); }
+    if (er == cudaSuccess) er = cudaMemcpy(out_sin, d + n, (size_t)n * 4, cudaMemcpyDeviceToHost);
+    if (er == cudaSuccess) er = cudaMemcpy(out_cos, d + 2 * (size_t)n, (size_t)n * 4, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (er != cudaSuccess) return cuda_fail(er, "device sincos");
+    return ORBX_OK;
+}
+
+int orbx_debug_atan2(const float* y, const float* x, float* out, int n) {
+    float *d = nullptr;
+    CU(cudaMalloc((void**)&d, std::max<size_t>(4, (size_t)n * 12)));
+    cudaError_t er = cudaMemcpy(d, y, (size_t)n * 4, cudaMemcpyHostToDevice);
+    if (er == cudaSuccess) er = cudaMemcpy(d + n, x, (size_t)n * 4, cudaMemcpyHostToDevice);
+    if (er == cudaSuccess) { launch_debug_atan2(d, d + n, d + 2 * (size_t)n, n, 0); er = cudaDeviceSynchronize(); }
+    if (er == cudaSuccess) er = cudaMemcpy(out, d + 2 * (size_t)n, (size_t)n * 4, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (er != cudaSuccess) return cuda_fail(er, "device atan2");
+    return ORBX_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------------
+// Single-image handle == one TC2LI_SLAM::ORBextractor instance: a batch of one, created lazily for the image size
+// ------------------------------------------------------------------------------------------------------------------
+struct orbx_extractor {
+    Params p;
+    int device = 0;
+    int taps[7] = {18, 34, 48, 56, 48, 34, 18};
+    orbx_batch* b = nullptr;
+    // pinned staging so that H2D / D2H are truly asynchronous with respect to the other handle of a stereo pair
+    uint8_t* pinImg = nullptr; size_t pinImgBytes = 0;
+    orbx_keypoint* pinKps = nullptr; uint8_t* pinDesc = nullptr; int* pinCnt = nullptr; size_t pinK = 0;
+};
+
+namespace {
+
+int extractor_prepare(orbx_extractor* h, int w, int hgt) {
+    if (h->b && (h->b->width != w || h->b->height != hgt)) { orbx_batch_destroy(h->b); h->b = nullptr; }
+    if (!h->b) {
+        int r = orbx_batch_create(h->p.nfeatures, h->p.scaleFactorF, h->p.nlevels, h->p.iniTh, h->p.minTh, h->device, w, hgt, 1, &h->b);
+        if (r) return r;
+        orbx_batch_set_blur_taps(h->b, h->taps);
+    }
+    DeviceGuard dg(h->device);
+    const size_t need = (size_t)w * hgt;
+    if (need > h->pinImgBytes) {
+        if (h->pinImg) cudaFreeHost(h->pinImg);
+        h->pinImg = nullptr; h->pinImgBytes = 0;
+        CU(cudaHostAlloc((void**)&h->pinImg, need, cudaHostAllocDefault));
+        h->pinImgBytes = need;
+    }
+    const size_t K = (size_t)h->b->g.K;
+    if (K > h->pinK) {
+        if (h->pinKps) cudaFreeHost(h->pinKps);
+        if (h->pinDesc) cudaFreeHost(h->pinDesc);
+        if (h->pinCnt) cudaFreeHost(h->pinCnt);
+        h->pinKps = nullptr; h->pinDesc = nullptr; h->pinCnt = nullptr; h->pinK = 0;
+        CU(cudaHostAlloc((void**)&h->pinKps, K * sizeof(orbx_keypoint), cudaHostAllocDefault));
+        CU(cudaHostAlloc((void**)&h->pinDesc, K * 32, cudaHostAllocDefault));
+        CU(cudaHostAlloc((void**)&h->pinCnt, 4 * sizeof(int), cudaHostAllocDefault));
+        h->pinK = K;
+    }
+    return ORBX_OK;
+}
+
+// stage + enqueue everything for one image; nothing waits here
+int extractor_issue(orbx_extractor* h, const uint8_t* image, int w, int hgt, size_t stride, int lap0, int lap1) {
+    int r = extractor_prepare(h, w, hgt);
+    if (r) return r;
+    for (int y = 0; y < hgt; ++y) std::memcpy(h->pinImg + (size_t)y * w, image + (size_t)y * stride, (size_t)w);
+    if ((r = orbx_batch_upload(h->b, h->pinImg, (size_t)w, (size_t)w * hgt, 0, 1))) return r;
+    const int lap[2] = {lap0, lap1};
+    if ((r = orbx_batch_run(h->b, 1, lap))) return r;
+    DeviceGuard dg(h->device);
+    orbx_batch* b = h->b;
+    cudaStream_t s = b->stream;
+    const size_t K = (size_t)b->g.K;
+    CU(cudaMemcpyAsync(h->pinKps, b->buf.kps, K * sizeof(orbx_keypoint), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(h->pinDesc, b->buf.desc, K * 32, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(h->pinCnt, b->buf.outCount, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(h->pinCnt + 1, b->buf.outMono, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(h->pinCnt + 2, b->buf.errFlag, sizeof(int), cudaMemcpyDeviceToHost, s));
+    return ORBX_OK;
+}
+
+int extractor_collect(orbx_extractor* h, orbx_keypoint* kps, uint8_t* desc, int capacity, int* n, int* mono) {
+    DeviceGuard dg(h->device);
+    CU(cudaStreamSynchronize(h->b->stream));
+    if (h->pinCnt[2]) {
+        cudaMemsetAsync(h->b->buf.errFlag, 0, sizeof(int), h->b->stream);
+        return fail(ORBX_ERR_CAPACITY, "device capacity exceeded");
+    }
+    const int N = h->pinCnt[0];
+    if (N > capacity) return fail(ORBX_ERR_CAPACITY, "output capacity smaller than the number of keypoints");
+    if (kps) std::memcpy(kps, h->pinKps, (size_t)N * sizeof(orbx_keypoint));
+    if (desc) std::memcpy(desc, h->pinDesc, (size_t)N * 32);
+    if (n) *n = N;
+    if (mono) *mono = h->pinCnt[1];
+    return ORBX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int orbx_create(int nfeatures, float scale_factor, int nlevels, int ini_th_fast, int min_th_fast, int device, orbx_extractor** out) {
+    if (!out) return fail(ORBX_ERR_ARG, "null out pointer");
+    *out = nullptr;
+    orbx_extractor* h = new orbx_extractor();
+    int r = make_params(nfeatures, scale_factor, nlevels, ini_th_fast, min_th_fast, h->p);
+    if (r) { delete h; return r; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || device < 0 || device >= ndev) {
+        delete h;
+        return fail(ORBX_ERR_CUDA, e != cudaSuccess ? std::string("no usable CUDA device: ") + cudaGetErrorString(e)
+                                                    : std::string("CUDA device ordinal out of range (there is no CPU fallback)"));
+    }
+    h->device = device;
+    *out = h;
+    return ORBX_OK;
+}
+
+void orbx_destroy(orbx_extractor* h) {
+    if (!h) return;
+    if (h->b) orbx_batch_destroy(h->b);
+    if (h->pinImg) cudaFreeHost(h->pinImg);
+    if (h->pinKps) cudaFreeHost(h->pinKps);
+    if (h->pinDesc) cudaFreeHost(h->pinDesc);
+    if (h->pinCnt) cudaFreeHost(h->pinCnt);
+    delete h;
+}
+
+int orbx_get_levels(const orbx_extractor* h) { return h ? h->p.nlevels : ORBX_ERR_ARG; }
+float orbx_get_scale_factor(const orbx_extractor* h) { return h ? h->p.scaleFactorF : 0.f; }
+static int copy_table(const orbx_extractor* h, const std::vector<float> Params::*m, float* out) {
+    if (!h || !out) return fail(ORBX_ERR_ARG, "null argument");
+    std::memcpy(out, (h->p.*m).data(), (size_t)h->p.nlevels * sizeof(float));
+    return ORBX_OK;
+}
+int orbx_get_scale_factors(const orbx_extractor* h, float* out) { return copy_table(h, &Params::sf, out); }
+int orbx_get_inverse_scale_factors(const orbx_extractor* h, float* out) { return copy_table(h, &Params::isf, out); }
+int orbx_get_scale_sigma_squares(const orbx_extractor* h, float* out) { return copy_table(h, &Params::sig2, out); }
+int orbx_get_inverse_scale_sigma_squares(const orbx_extractor* h, float* out) { return copy_table(h, &Params::isig2, out); }
+int orbx_get_features_per_level(const orbx_extractor* h, int* out) {
+    if (!h || !out) return fail(ORBX_ERR_ARG, "null argument");
+    std::memcpy(out, h->p.quota.data(), (size_t)h->p.nlevels * sizeof(int));
+    return ORBX_OK;
+}
+int orbx_max_keypoints(const orbx_extractor* h) {
+    // image-size independent bound: per level max(quota + 3, 4 * nIni) with nIni <= ORBX_MAX_DIM / 35
+    if (!h) return ORBX_ERR_ARG;
+    if (h->b) return h->b->g.K;
+    int k = 0;
+    for (int q : h->p.quota) k += std::max(q + 3, 4 * (ORBX_MAX_DIM / 35));
+    return k;
+}
+int orbx_set_blur_taps(orbx_extractor* h, const int taps[7]) {
+    if (!h || !taps) return fail(ORBX_ERR_ARG, "null argument");
+    std::memcpy(h->taps, taps, sizeof(h->taps));
+    if (h->b) return orbx_batch_set_blur_taps(h->b, taps);
+    return ORBX_OK;
+}
+
+int orbx_extract(orbx_extractor* h, const uint8_t* image, int width, int height, size_t stride, int lap0, int lap1, orbx_keypoint* keypoints,
+                 uint8_t* descriptors, int capacity, int* n_keypoints, int* mono_index) {
+    if (!h) return fail(ORBX_ERR_ARG, "null handle");
+    if (n_keypoints) *n_keypoints = 0;
+    if (mono_index) *mono_index = 0;
+    if (!image || width <= 0 || height <= 0) return fail(ORBX_ERR_EMPTY, "empty image");  // ORBextractor.cc:1063-1064
+    if (stride < (size_t)width) return fail(ORBX_ERR_ARG, "row stride smaller than the width");
+    int r = extractor_issue(h, image, width, height, stride, lap0, lap1);
+    if (r) return r;
+    return extractor_collect(h, keypoints, descriptors, capacity, n_keypoints, mono_index);
+}
+
+int orbx_extract_stereo(orbx_extractor* left, orbx_extractor* right, const uint8_t* image_left, const uint8_t* image_right, int width, int height,
+                        size_t stride_left, size_t stride_right, const int lap_left[2], const int lap_right[2], orbx_keypoint* kps_left,
+                        uint8_t* desc_left, int cap_left, int* n_left, int* mono_left, orbx_keypoint* kps_right, uint8_t* desc_right, int cap_right,
+                        int* n_right, int* mono_right) {
+    if (!left || !right || left == right) return fail(ORBX_ERR_ARG, "need two distinct handles");
+    if (!image_left || !image_right || width <= 0 || height <= 0) return fail(ORBX_ERR_EMPTY, "empty image");
+    if (stride_left < (size_t)width || stride_right < (size_t)width) return fail(ORBX_ERR_ARG, "row stride smaller than the width");
+    const int zero[2] = {0, 0};
+    if (!lap_left) lap_left = zero;
+    if (!lap_right) lap_right = zero;
+    int r = extractor_issue(left, image_left, width, height, stride_left, lap_left[0], lap_left[1]);
+    if (r) return r;
+    if ((r = extractor_issue(right, image_right, width, height, stride_right, lap_right[0], lap_right[1]))) return r;
+    r = extractor_collect(left, kps_left, desc_left, cap_left, n_left, mono_left);
+    const int r2 = extractor_collect(right, kps_right, desc_right, cap_right, n_right, mono_right);
+    return r ? r : r2;
+}
+
+int orbx_get_level_size(const orbx_extractor* h, int level, int* width, int* height) {
+    if (!h || !h->b) return fail(ORBX_ERR_ARG, "no image has been extracted yet");
+    return orbx_batch_get_level_size(h->b, level, width, height);
+}
+int orbx_get_level(orbx_extractor* h, int level, uint8_t* dst, size_t dst_stride, int border) {
+    if (!h || !h->b) return fail(ORBX_ERR_ARG, "no image has been extracted yet");
+    return orbx_batch_get_level(h->b, 0, level, dst, dst_stride, border);
+}
+orbx_batch* orbx_extractor_batch(orbx_extractor* h) { return h ? h->b : nullptr; }
+
+}  // extern "C"

@@ -1,0 +1,106 @@
+// orbx_internal.cuh — shared declarations of the sm_100a ORB front-end (host orchestration + kernels).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/orbx.h"
+
+namespace orbx {
+
+constexpr int kEdge = 19;      // EDGE_THRESHOLD (ORBextractor.cc:47)
+constexpr int kBorder = 16;    // minBorderX/Y = EDGE_THRESHOLD - 3 (ORBextractor.cc:763)
+constexpr int kHalfPatch = 15; // HALF_PATCH_SIZE (ORBextractor.cc:46)
+constexpr int kMaxCell = 72;   // wCell/hCell < 70 for any level with >= 1 cell of 35 px (ORBextractor.cc:771-777)
+
+// Per-level geometry, passed by value to every kernel (fits well inside the 4 KB parameter space).
+struct LevelGeom {
+    int w, h, pitch;                  // level size and row pitch in bytes (pitch % 128 == 0)
+    int nCols, nRows, wCell, hCell;   // FAST cell grid (ORBextractor.cc:771-777)
+    int quota;                        // mnFeaturesPerLevel[level]
+    int nIni;                         // initial quadtree nodes (ORBextractor.cc:533)
+    float hX;                         // root node width (ORBextractor.cc:535)
+    int candCap;                      // candidate capacity per image (NMS keeps <= 1 pixel per 2x2 block of a cell interior)
+    int nodeCap;                      // quadtree node-slot capacity
+    int selCap, selOff;               // selected keypoints: capacity, offset inside the per-image array
+    int cellOff;                      // offset inside the per-image cell array
+    float sf;                         // mvScaleFactor[level]
+    float kpSize;                     // (float)(int)(31 * sf)
+    unsigned long long planeOff;      // byte offset of this level's block (all images) in the pyramid / blur buffers
+    unsigned long long planeBytes;    // pitch * h
+    unsigned long long candOff;       // element offset of this level's block in the candidate buffers
+};
+
+struct Geom {
+    int nlevels;
+    int K;               // per-image keypoint capacity = sum selCap
+    int cellsPerImage;   // sum nCols*nRows
+    int iniTh, minTh;
+    int maxImages;
+    LevelGeom lv[ORBX_MAX_LEVELS];
+};
+
+// resize tables of one level (device pointers): per destination column / row
+struct ResizeTab {
+    const short* xofs;  // [w_dst]
+    const short* xa;    // [w_dst][2]
+    const short* yofs;  // [h_dst]
+    const short* yb;    // [h_dst][2]
+};
+
+// candidate packing: x' = x - 16 (12 bits) | y' = y - 16 (12 bits) | response (8 bits)
+__host__ __device__ inline uint32_t pack_cand(int xr, int yr, int resp) { return (uint32_t)xr | ((uint32_t)yr << 12) | ((uint32_t)resp << 24); }
+__host__ __device__ inline int cand_x(uint32_t c) { return (int)(c & 0xFFFu); }
+__host__ __device__ inline int cand_y(uint32_t c) { return (int)((c >> 12) & 0xFFFu); }
+__host__ __device__ inline int cand_r(uint32_t c) { return (int)(c >> 24); }
+
+// Position of a candidate in the reference's candidate vector order: cell row, cell column, then raster inside the
+// cell (ORBextractor.cc:779-846).  Smaller key = earlier in vToDistributeKeys; only its ORDER matters (tie-break of
+// the per-node maximum, ORBextractor.cc:737-747).  40 bits.
+__host__ __device__ inline unsigned long long cand_order_key(uint32_t c, int wCell, int hCell) {
+    const int x = cand_x(c), y = cand_y(c);
+    const unsigned long long ci = (unsigned long long)((y - 3) / hCell), cj = (unsigned long long)((x - 3) / wCell);
+    return (ci << 32) | (cj << 24) | ((unsigned long long)y << 12) | (unsigned long long)x;
+}
+
+// work item of the orient+describe kernel
+struct KpWork {
+    short x, y;      // level coordinates
+    short level;
+    short dst;       // output slot (keypoints[dst], descriptors[dst]); -1 = none
+};
+
+struct Buffers {
+    uint8_t* pyr;           // all levels, all images (level-major: [level][image][h][pitch])
+    uint8_t* blur;          // same layout
+    uint32_t* cand;         // [level][image][candCap]
+    uint16_t* pnode;        // same layout: quadtree node slot of each candidate
+    int* candCount;         // [image][ORBX_MAX_LEVELS]
+    uint8_t* cellFlags;     // [image][cellsPerImage]: 0 skipped, 1 had a corner above iniThFAST, 2 fell back to minThFAST
+    uint32_t* sel;          // [image][K] packed selected keypoints (level coordinates - 16), final list order
+    int* selCount;          // [image][ORBX_MAX_LEVELS]
+    int* lapping;           // [image][2]
+    orbx_keypoint* kps;     // [image][K]
+    uint8_t* desc;          // [image][K][32]
+    KpWork* work;           // [image][K]
+    int* outCount;          // [image]
+    int* outMono;           // [image]
+    int* errFlag;           // device-side error flag (capacity overflow etc.)
+};
+
+// kernel launchers (one translation unit per stage)
+void launch_synth(uint8_t* l0, int w, int h, int pitch, size_t planeBytes, uint32_t seed0, int firstImage, int nImages, int stereo, cudaStream_t s);
+void launch_pyramid_level(const Geom& g, const Buffers& b, int level, const ResizeTab& tab, int nImages, cudaStream_t s);
+void launch_fast(const Geom& g, const Buffers& b, int nImages, cudaStream_t s);
+void launch_blur(const Geom& g, const Buffers& b, int level, int nImages, const int taps[7], cudaStream_t s);
+cudaError_t launch_octree(const Geom& g, const Buffers& b, int nImages, cudaStream_t s);
+void launch_assemble(const Geom& g, const Buffers& b, int nImages, cudaStream_t s);
+void launch_describe(const Geom& g, const Buffers& b, int nImages, cudaStream_t s);
+void launch_border(const uint8_t* src, int w, int h, int pitch, uint8_t* dst, int dpitch, cudaStream_t s);
+size_t octree_smem_bytes(int nodeCap);
+cudaError_t upload_describe_constants(const signed char pattern[1024], const int umax[16]);
+
+// debug / test hooks
+void launch_debug_sincos(const float* anglesDeg, float* outSin, float* outCos, int n, cudaStream_t s);
+void launch_debug_atan2(const float* y, const float* x, float* out, int n, cudaStream_t s);
+
+}  // namespace orbx

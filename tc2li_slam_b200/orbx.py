@@ -1,0 +1,456 @@
+"""ctypes binding of liborbx.so (include/orbx.h) and the Python mirror of TC2LI_SLAM::ORBextractor.
+
+`ORBextractor` keeps the reference's class surface (slam_framework/include/ORBextractor.h:52-118): the five-argument
+constructor, `__call__(image, mask, vLappingArea)` returning `(monoIndex, keypoints, descriptors)`, the six getters and
+`mvImagePyramid`.  `StereoORBextractor` replaces the two extraction threads of Frame::Frame (Frame.cc:139-142) by two CUDA
+streams; `BatchExtractor` is the throughput path (many images of one shape per launch set).
+
+Everything here is host-side plumbing over the C ABI; all pixel work happens in the CUDA kernels of csrc/.  There is no
+CPU fallback: loading fails loudly when liborbx.so is missing, and constructing an extractor fails when no GPU is usable.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "liborbx.so")
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])  # layout of cv::KeyPoint (28 bytes)
+assert KP_DTYPE.itemsize == 28
+
+OK, ERR_EMPTY, ERR_TOO_SMALL, ERR_ARG, ERR_CUDA, ERR_CAPACITY, ERR_TOO_LARGE = 0, -1, -2, -3, -4, -5, -6
+NUM_STAGES = 6
+STAGE_NAMES = ("pyramid", "fast", "blur", "octree", "assemble", "orient_describe")
+
+
+class OrbxError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"orbx error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+_vp = C.c_void_p
+
+
+def lib():
+    """Load liborbx.so (built in-tree by `__graft_entry__.build()` / `make -C tc2li_slam_b200/csrc`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    i, f, sz, u32 = C.c_int, C.c_float, C.c_size_t, C.c_uint32
+    sig = {
+        "orbx_create": (i, [i, f, i, i, i, i, C.POINTER(_vp)]),
+        "orbx_destroy": (None, [_vp]),
+        "orbx_get_levels": (i, [_vp]),
+        "orbx_get_scale_factor": (f, [_vp]),
+        "orbx_get_scale_factors": (i, [_vp, _vp]),
+        "orbx_get_inverse_scale_factors": (i, [_vp, _vp]),
+        "orbx_get_scale_sigma_squares": (i, [_vp, _vp]),
+        "orbx_get_inverse_scale_sigma_squares": (i, [_vp, _vp]),
+        "orbx_get_features_per_level": (i, [_vp, _vp]),
+        "orbx_max_keypoints": (i, [_vp]),
+        "orbx_set_blur_taps": (i, [_vp, _vp]),
+        "orbx_extract": (i, [_vp, _vp, i, i, sz, i, i, _vp, _vp, i, _vp, _vp]),
+        "orbx_extract_stereo": (i, [_vp, _vp, _vp, _vp, i, i, sz, sz, _vp, _vp, _vp, _vp, i, _vp, _vp, _vp, _vp, i, _vp, _vp]),
+        "orbx_get_level_size": (i, [_vp, i, _vp, _vp]),
+        "orbx_get_level": (i, [_vp, i, _vp, sz, i]),
+        "orbx_extractor_batch": (_vp, [_vp]),
+        "orbx_batch_create": (i, [i, f, i, i, i, i, i, i, i, C.POINTER(_vp)]),
+        "orbx_batch_destroy": (None, [_vp]),
+        "orbx_batch_max_keypoints": (i, [_vp]),
+        "orbx_batch_max_images": (i, [_vp]),
+        "orbx_batch_set_blur_taps": (i, [_vp, _vp]),
+        "orbx_batch_set_stream": (i, [_vp, _vp]),
+        "orbx_batch_get_stream": (_vp, [_vp]),
+        "orbx_batch_upload": (i, [_vp, _vp, sz, sz, i, i]),
+        "orbx_batch_upload_device": (i, [_vp, _vp, sz, sz, i, i]),
+        "orbx_batch_synth": (i, [_vp, u32, i, i, i]),
+        "orbx_batch_run": (i, [_vp, i, _vp]),
+        "orbx_batch_download": (i, [_vp, i, _vp, _vp, _vp, _vp]),
+        "orbx_batch_sync": (i, [_vp]),
+        "orbx_batch_get_level_size": (i, [_vp, i, _vp, _vp]),
+        "orbx_batch_get_level": (i, [_vp, i, i, _vp, sz, i]),
+        "orbx_batch_enable_timing": (i, [_vp, i]),
+        "orbx_batch_stage_ms": (i, [_vp, _vp]),
+        "orbx_batch_kernel_launches": (i, [_vp]),
+        "orbx_batch_debug_blurred": (i, [_vp, i, i, _vp, sz]),
+        "orbx_batch_debug_candidates": (i, [_vp, i, i, _vp, i, _vp]),
+        "orbx_batch_debug_selected": (i, [_vp, i, i, _vp, i, _vp]),
+        "orbx_batch_debug_fallback_cells": (i, [_vp, i, i, _vp]),
+        "orbx_alloc_pinned": (_vp, [sz]),
+        "orbx_free_pinned": (None, [_vp]),
+        "orbx_tables": (i, [i, f, i, i, i, _vp, _vp, _vp, _vp, _vp, _vp]),
+        "orbx_level_geometry": (i, [i, f, i, i, i, i, _vp]),
+        "orbx_debug_sort": (i, [_vp, i, _vp, i, i]),
+        "orbx_debug_sincos": (i, [_vp, _vp, _vp, i]),
+        "orbx_debug_atan2": (i, [_vp, _vp, _vp, i]),
+        "orbx_version": (C.c_char_p, []),
+        "orbx_last_error": (C.c_char_p, []),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)  # AttributeError here == the library does not export what include/orbx.h declares
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+EXPORTED = None  # filled lazily by tests: names declared in include/orbx.h
+
+
+def _p(a):
+    return a.ctypes.data_as(_vp)
+
+
+def _check(code):
+    if code != OK:
+        raise OrbxError(code, lib().orbx_last_error().decode())
+    return code
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# host-only helpers (no GPU)
+# --------------------------------------------------------------------------------------------------------------------
+def tables(nfeatures=2000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+    """Constants of ORBextractor's constructor (ORBextractor.cc:383-443)."""
+    sf, isf, s2, is2 = (np.empty(nlevels, np.float32) for _ in range(4))
+    quota = np.empty(nlevels, np.int32)
+    umax = np.empty(16, np.int32)
+    _check(lib().orbx_tables(nfeatures, scale_factor, nlevels, ini_th, min_th, _p(sf), _p(isf), _p(s2), _p(is2), _p(quota), _p(umax)))
+    return dict(scale_factors=sf, inv_scale_factors=isf, level_sigma2=s2, inv_level_sigma2=is2, features_per_level=quota, umax=umax)
+
+
+def level_geometry(width, height, level, nfeatures=2000, scale_factor=1.2, nlevels=8):
+    out = np.empty(8, np.int32)
+    _check(lib().orbx_level_geometry(nfeatures, scale_factor, nlevels, width, height, level, _p(out)))
+    return dict(zip(("w", "h", "nCols", "nRows", "wCell", "hCell", "nIni", "capacity"), (int(v) for v in out)))
+
+
+def debug_sort(keys, force_depth=-1, on_device=False):
+    keys = np.ascontiguousarray(keys, np.uint32)
+    perm = np.empty(len(keys), np.int32)
+    _check(lib().orbx_debug_sort(_p(keys), len(keys), _p(perm), force_depth, int(on_device)))
+    return perm
+
+
+def debug_sincos(angles_deg):
+    a = np.ascontiguousarray(angles_deg, np.float32)
+    s, c = np.empty_like(a), np.empty_like(a)
+    _check(lib().orbx_debug_sincos(_p(a), _p(s), _p(c), len(a)))
+    return s, c
+
+
+def debug_atan2(y, x):
+    y = np.ascontiguousarray(y, np.float32)
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.empty_like(y)
+    _check(lib().orbx_debug_atan2(_p(y), _p(x), _p(out), len(y)))
+    return out
+
+
+class PinnedArray:
+    """Page-locked host buffer exposed as a numpy array (for overlapped H2D / D2H in the batch path)."""
+
+    def __init__(self, shape, dtype):
+        self.dtype = np.dtype(dtype)
+        self.shape = tuple(int(s) for s in np.atleast_1d(shape))
+        nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        self._ptr = lib().orbx_alloc_pinned(max(nbytes, 1))
+        if not self._ptr:
+            raise OrbxError(ERR_CUDA, lib().orbx_last_error().decode())
+        buf = (C.c_uint8 * max(nbytes, 1)).from_address(self._ptr)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def free(self):
+        if self._ptr:
+            self.array = None
+            lib().orbx_free_pinned(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# the ORBextractor mirror
+# --------------------------------------------------------------------------------------------------------------------
+def _as_gray(image):
+    if image is None:
+        return None
+    image = np.asarray(image)
+    if image.size == 0:
+        return None
+    assert image.dtype == np.uint8 and image.ndim == 2, "ORBextractor expects CV_8UC1 (ORBextractor.cc:1067)"
+    if image.strides[1] != 1:
+        image = np.ascontiguousarray(image)
+    return image
+
+
+class ORBextractor:
+    """Drop-in mirror of TC2LI_SLAM::ORBextractor (ORBextractor.h:52-118) over the CUDA path."""
+
+    HARRIS_SCORE, FAST_SCORE = 0, 1  # ORBextractor.h:56 (unused by the reference as well)
+
+    def __init__(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, device=0):
+        self._h = _vp()
+        _check(lib().orbx_create(int(nfeatures), float(scaleFactor), int(nlevels), int(iniThFAST), int(minThFAST), int(device), C.byref(self._h)))
+        self.nlevels = int(nlevels)
+        self._kcap = 0
+        self._kps = self._desc = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().orbx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- getters (ORBextractor.h:70-90) ----
+    def GetLevels(self):
+        return lib().orbx_get_levels(self._h)
+
+    def GetScaleFactor(self):
+        return lib().orbx_get_scale_factor(self._h)
+
+    def _table(self, fn, dtype=np.float32):
+        out = np.empty(self.nlevels, dtype)
+        _check(fn(self._h, _p(out)))
+        return out
+
+    def GetScaleFactors(self):
+        return self._table(lib().orbx_get_scale_factors)
+
+    def GetInverseScaleFactors(self):
+        return self._table(lib().orbx_get_inverse_scale_factors)
+
+    def GetScaleSigmaSquares(self):
+        return self._table(lib().orbx_get_scale_sigma_squares)
+
+    def GetInverseScaleSigmaSquares(self):
+        return self._table(lib().orbx_get_inverse_scale_sigma_squares)
+
+    @property
+    def mnFeaturesPerLevel(self):
+        return self._table(lib().orbx_get_features_per_level, np.int32)
+
+    def set_blur_taps(self, taps):
+        t = np.asarray(taps, np.int32)
+        _check(lib().orbx_set_blur_taps(self._h, _p(t)))
+
+    def _outputs(self):
+        cap = lib().orbx_max_keypoints(self._h)
+        if cap > self._kcap:
+            self._kps = np.empty(cap, KP_DTYPE)
+            self._desc = np.empty((cap, 32), np.uint8)
+            self._kcap = cap
+        return self._kcap
+
+    def __call__(self, image, mask=None, vLappingArea=(0, 0)):
+        """operator() (ORBextractor.cc:1060-1141).  Returns (monoIndex, keypoints[N], descriptors[N,32]);
+        monoIndex is -1 for an empty image, like the reference; `mask` is ignored, like the reference."""
+        image = _as_gray(image)
+        if image is None:
+            return -1, np.empty(0, KP_DTYPE), np.empty((0, 32), np.uint8)
+        cap = self._outputs()
+        n, mono = C.c_int(0), C.c_int(0)
+        _check(lib().orbx_extract(self._h, _p(image), image.shape[1], image.shape[0], image.strides[0], int(vLappingArea[0]), int(vLappingArea[1]),
+                                  _p(self._kps), _p(self._desc), cap, C.byref(n), C.byref(mono)))
+        return mono.value, self._kps[:n.value].copy(), self._desc[:n.value].copy()
+
+    # ---- mvImagePyramid (ORBextractor.h:92): fetched lazily from the device ----
+    def level(self, l, border=0):
+        w, h = C.c_int(), C.c_int()
+        _check(lib().orbx_get_level_size(self._h, l, C.byref(w), C.byref(h)))
+        out = np.empty((h.value + 2 * border, w.value + 2 * border), np.uint8)
+        _check(lib().orbx_get_level(self._h, l, _p(out), out.strides[0], border))
+        return out
+
+    @property
+    def mvImagePyramid(self):
+        """Levels of the last image; each is the interior view of a buffer that carries the 19-px REFLECT_101 border,
+        like the reference's cv::Mat ROIs (ORBextractor.cc:1149-1165)."""
+        return [self.level(l, 19)[19:-19, 19:-19] for l in range(self.nlevels)]
+
+    @property
+    def batch(self):
+        """The batch-of-one behind this handle (stage dumps for tests)."""
+        return BatchExtractor._wrap(lib().orbx_extractor_batch(self._h), self.nlevels)
+
+
+class StereoORBextractor:
+    """mpORBextractorLeft / mpORBextractorRight of Tracking (Tracking.cc:626-629) driven as Frame::Frame drives them
+    (Frame.cc:139-142), with the two host threads replaced by the two handles' CUDA streams."""
+
+    def __init__(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, device=0):
+        self.left = ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, device)
+        self.right = ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, device)
+
+    def __call__(self, imLeft, imRight, lapLeft=(0, 0), lapRight=(0, 0)):
+        imLeft, imRight = _as_gray(imLeft), _as_gray(imRight)
+        if imLeft is None or imRight is None:
+            e = (-1, np.empty(0, KP_DTYPE), np.empty((0, 32), np.uint8))
+            return e, e
+        assert imLeft.shape == imRight.shape
+        L, R = self.left, self.right
+        capL, capR = L._outputs(), R._outputs()
+        nl, ml, nr, mr = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
+        ll = np.asarray(lapLeft, np.int32)
+        lr = np.asarray(lapRight, np.int32)
+        _check(lib().orbx_extract_stereo(L._h, R._h, _p(imLeft), _p(imRight), imLeft.shape[1], imLeft.shape[0], imLeft.strides[0], imRight.strides[0],
+                                         _p(ll), _p(lr), _p(L._kps), _p(L._desc), capL, C.byref(nl), C.byref(ml),
+                                         _p(R._kps), _p(R._desc), capR, C.byref(nr), C.byref(mr)))
+        return ((ml.value, L._kps[:nl.value].copy(), L._desc[:nl.value].copy()),
+                (mr.value, R._kps[:nr.value].copy(), R._desc[:nr.value].copy()))
+
+    def close(self):
+        self.left.close()
+        self.right.close()
+
+
+class BatchExtractor:
+    """Many images of one shape per launch set (BASELINE.json configs[4]); frames x {left,right} are consecutive images."""
+
+    def __init__(self, width, height, max_images, nfeatures=2000, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7, device=0):
+        self._h = _vp()
+        _check(lib().orbx_batch_create(int(nfeatures), float(scaleFactor), int(nlevels), int(iniThFAST), int(minThFAST), int(device),
+                                       int(width), int(height), int(max_images), C.byref(self._h)))
+        self._own = True
+        self.nlevels = int(nlevels)
+        self.width, self.height, self.max_images = int(width), int(height), int(max_images)
+        self.K = lib().orbx_batch_max_keypoints(self._h)
+
+    @classmethod
+    def _wrap(cls, handle, nlevels):
+        if not handle:
+            return None
+        self = cls.__new__(cls)
+        self._h = _vp(handle)
+        self._own = False
+        self.nlevels = nlevels
+        self.K = lib().orbx_batch_max_keypoints(self._h)
+        self.max_images = lib().orbx_batch_max_images(self._h)
+        return self
+
+    def close(self):
+        if getattr(self, "_h", None) and self._own:
+            lib().orbx_batch_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_blur_taps(self, taps):
+        t = np.asarray(taps, np.int32)
+        _check(lib().orbx_batch_set_blur_taps(self._h, _p(t)))
+
+    def set_stream(self, cuda_stream):
+        _check(lib().orbx_batch_set_stream(self._h, _vp(cuda_stream)))
+
+    @property
+    def stream(self):
+        return lib().orbx_batch_get_stream(self._h)
+
+    def upload(self, images, first=0):
+        """images: uint8 [n, H, W] host array (pinned memory makes the copy asynchronous)."""
+        images = np.asarray(images)
+        assert images.dtype == np.uint8 and images.ndim == 3 and images.strides[2] == 1
+        _check(lib().orbx_batch_upload(self._h, _p(images), images.strides[1], images.strides[0], first, images.shape[0]))
+
+    def upload_device(self, dev_ptr, row_stride, image_stride, first, n):
+        _check(lib().orbx_batch_upload_device(self._h, _vp(dev_ptr), row_stride, image_stride, first, n))
+
+    def synth(self, seed0, n, stereo=True, first=0):
+        _check(lib().orbx_batch_synth(self._h, seed0 & 0xFFFFFFFF, first, n, int(stereo)))
+
+    def run(self, n, lapping=None):
+        lp = None
+        if lapping is not None:
+            lp = np.ascontiguousarray(lapping, np.int32).reshape(n, 2)
+        _check(lib().orbx_batch_run(self._h, n, _p(lp) if lp is not None else None))
+
+    def sync(self):
+        _check(lib().orbx_batch_sync(self._h))
+
+    def download(self, n, keypoints=None, descriptors=None, counts=None, mono=None):
+        """Fills (or allocates) host arrays [n,K] / [n,K,32] / [n] / [n]; returns them."""
+        if keypoints is None:
+            keypoints = np.empty((n, self.K), KP_DTYPE)
+        if descriptors is None:
+            descriptors = np.empty((n, self.K, 32), np.uint8)
+        if counts is None:
+            counts = np.empty(n, np.int32)
+        if mono is None:
+            mono = np.empty(n, np.int32)
+        _check(lib().orbx_batch_download(self._h, n, _p(keypoints), _p(descriptors), _p(counts), _p(mono)))
+        return keypoints, descriptors, counts, mono
+
+    def download_counts(self, n):
+        counts, mono = np.empty(n, np.int32), np.empty(n, np.int32)
+        _check(lib().orbx_batch_download(self._h, n, None, None, _p(counts), _p(mono)))
+        return counts, mono
+
+    def level_size(self, l):
+        w, h = C.c_int(), C.c_int()
+        _check(lib().orbx_batch_get_level_size(self._h, l, C.byref(w), C.byref(h)))
+        return w.value, h.value
+
+    def level(self, image, l, border=0):
+        w, h = self.level_size(l)
+        out = np.empty((h + 2 * border, w + 2 * border), np.uint8)
+        _check(lib().orbx_batch_get_level(self._h, image, l, _p(out), out.strides[0], border))
+        return out
+
+    def blurred(self, image, l):
+        w, h = self.level_size(l)
+        out = np.empty((h, w), np.uint8)
+        _check(lib().orbx_batch_debug_blurred(self._h, image, l, _p(out), out.strides[0]))
+        return out
+
+    def _xyr(self, fn, image, l):
+        n = C.c_int(0)
+        _check(fn(self._h, image, l, None, 0, C.byref(n)))
+        out = np.empty((n.value, 3), np.float32)
+        if n.value:
+            _check(fn(self._h, image, l, _p(out), n.value, C.byref(n)))
+        return out
+
+    def candidates(self, image, l):
+        """FAST candidates in the reference's order: float32 [n,3] (x, y relative to (16,16), response)."""
+        return self._xyr(lib().orbx_batch_debug_candidates, image, l)
+
+    def selected(self, image, l):
+        return self._xyr(lib().orbx_batch_debug_selected, image, l)
+
+    def fallback_cells(self, image, l):
+        n = C.c_int(0)
+        _check(lib().orbx_batch_debug_fallback_cells(self._h, image, l, C.byref(n)))
+        return n.value
+
+    def enable_timing(self, on=True):
+        _check(lib().orbx_batch_enable_timing(self._h, int(on)))
+
+    def stage_ms(self):
+        ms = np.empty(NUM_STAGES, np.float32)
+        _check(lib().orbx_batch_stage_ms(self._h, _p(ms)))
+        return dict(zip(STAGE_NAMES, (float(v) for v in ms)))
+
+    @property
+    def kernel_launches(self):
+        return lib().orbx_batch_kernel_launches(self._h)
