@@ -1,0 +1,382 @@
+#!/usr/bin/env python3
+"""bench.py — ORB stereo frames/s of the B200 path (BASELINE.json metric), with roofline and CPU baseline.
+
+Workload (BASELINE.json configs[4], the configuration the metric is quoted on): a batch of KITTI-shaped stereo frames
+(1241x376 left+right, ORBextractor(2000, 1.2, 8, 20, 7)), synthetic `orbx-synth-v1` texture, sharded by frame across the
+GPUs with no collective (weak scaling: every rank processes --pairs stereo frames per step, default 4096).
+
+  value : frames/s with the level-0 images already resident in HBM (7.8 GB per rank >> 126 MB L2), CUDA events on the
+          launching stream, max over ranks.
+  e2e   : the same metric through the public API with HOST buffers: pinned host images -> H2D -> kernels -> D2H of
+          keypoints + descriptors + counts, three pipelined handles (streams); copies inside the timed region.
+  --impl reference : the reference's CPU path (oracle/_ref when it was built, else the CPU oracle port) on all host cores.
+
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H = 1241, 376
+ORB_ARGS = (2000, 1.2, 8, 20, 7)
+METRIC = "ORB stereo frames/sec (KITTI 1241x376 left+right, 2000 kp/image, 8 levels, FAST 20/7)"
+UNIT = "frames/s"
+L2_BYTES = 126e6
+
+
+def level_sizes():
+    import tc2li_slam_b200 as T
+    return [(g["w"], g["h"]) for g in (T.level_geometry(W, H, l, *ORB_ARGS[:3]) for l in range(ORB_ARGS[2]))]
+
+
+def algorithmic_bytes(kps_per_image):
+    """compulsory bytes per IMAGE and per stage (each stage reads its input once, writes its output once)."""
+    px = [w * h for w, h in level_sizes()]
+    P, P0, P7 = sum(px), px[0], px[-1]
+    K = kps_per_image
+    return {"pyramid": (P - P7) + (P - P0), "fast": P, "blur": 2 * P, "octree": 0, "assemble": 60 * K, "orient_describe": (749 + 512) * K,
+            "total": 5 * P - P0 - P7 + 1321 * K}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm on the host cores
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_backend():
+    """oracle/_ref (verbatim reference TU compiled against stand-in OpenCV headers) when present, else the oracle port."""
+    try:
+        from oracle import pyref
+        if pyref.available():
+            return "reference", pyref.RefExtractor
+    except Exception:
+        pass
+    from oracle import pyoracle
+    return "port", pyoracle.OracleExtractor
+
+
+def cpu_images(n_pairs, seed0):
+    from oracle import pyoracle as po
+    out = np.empty((2 * n_pairs, H, W), np.uint8)
+    for f in range(n_pairs):
+        out[2 * f] = po.synth_v1(W, H, seed0 + f)
+        out[2 * f + 1] = po.synth_v1(W, H, seed0 + f, 16, 0x5bd1e995)
+    return out
+
+
+def cpu_run(images, cores, make_extractor):
+    """Extract every image, sharded over `cores` host threads (the C library releases the GIL).  Returns seconds."""
+    n = len(images)
+    exs = [make_extractor(*ORB_ARGS) for _ in range(cores)]
+    nk = [0] * cores
+
+    def work(t):
+        for i in range(t, n, cores):
+            _, k, _ = exs[t](images[i])
+            nk[t] += len(k)
+
+    t0 = time.perf_counter()
+    th = [threading.Thread(target=work, args=(t,)) for t in range(cores)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    return time.perf_counter() - t0, sum(nk)
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    kind, make = cpu_backend()
+    cores = os.cpu_count() or 1
+    pairs = max(cores, min(args.ref_pairs, 64 * cores))
+    imgs = cpu_images(pairs, 1000)
+    for _ in range(args.warmup):
+        cpu_run(imgs[: 2 * cores], cores, make)
+    times = []
+    for _ in range(args.steps):
+        dt, _ = cpu_run(imgs, cores, make)
+        times.append(dt)
+    sec = sum(times) / len(times)
+    v = pairs / sec
+    sample = f"{pairs} synthetic KITTI-shaped stereo frames per step on {cores} host threads ({kind} of ORBextractor.cc, -O3, no FMA contraction)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "KITTI-shaped stereo frames 1241x376, ORBextractor(2000,1.2,8,20,7), CPU reference path, bounded sample", "pairs_per_step": pairs},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        # under load = upper half of the samples (the sampler also sees the idle edges)
+        sm.sort()
+        load = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=4096, help="stereo frames per rank per step")
+    ap.add_argument("--group", type=int, default=0, help="images per launch set of the resident run (0 = all at once)")
+    ap.add_argument("--chunk", type=int, default=256, help="images per pipelined handle of the e2e run")
+    ap.add_argument("--ref-pairs", type=int, default=256, help="stereo frames per step of the CPU arms (bounded sample)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3  # timing hygiene: at least three warm-up steps
+
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    import tc2li_slam_b200 as T
+    from tc2li_slam_b200.orbx import Event
+
+    n_img = 2 * args.pairs
+    seed0 = 100000 * rank
+    group = args.group if args.group > 0 else n_img
+
+    # ---- resident run: all level-0 images live in the handle's pyramid buffer ----
+    big = T.BatchExtractor(W, H, n_img, *ORB_ARGS, device=local)
+    big.synth(seed0, n_img, stereo=True)
+    big.sync()
+
+    def resident_step():
+        for first in range(0, n_img, group):
+            big.run_range(first, min(group, n_img - first))
+
+    for _ in range(args.warmup):
+        resident_step()
+    big.check()
+    counts, _ = big.download_counts(n_img)
+    kp_mean = float(counts.mean())
+    ev0, ev1 = Event(), Event()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev0.record(big)
+    for _ in range(args.steps):
+        resident_step()
+    ev1.record(big)
+    ms_total = ev0.elapsed_ms(ev1)
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    ms_step = max_over_ranks(ms_total / args.steps)
+    value = args.pairs * world / (ms_step * 1e-3)
+
+    # ---- per-stage device time of one step (events between the stages), for the roofline ----
+    big.enable_timing(True)
+    stage_ms = {k: 0.0 for k in T.orbx.STAGE_NAMES}
+    reps = 2
+    for _ in range(reps):
+        for first in range(0, n_img, group):
+            big.run_range(first, min(group, n_img - first))
+            for k, v in big.stage_ms().items():
+                stage_ms[k] += v / reps
+    big.enable_timing(False)
+    launches_per_step = big.kernel_launches * ((n_img + group - 1) // group)
+    ab = algorithmic_bytes(kp_mean)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    stages = {}
+    for k, ms in stage_ms.items():
+        gbs = ab[k] * n_img / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        stages[k] = {"ms": ms, "bytes_per_image": ab[k], "GBps": gbs, "frac": gbs / peak}
+    dom = max(stage_ms, key=stage_ms.get)
+    launches_of = {"pyramid": ORB_ARGS[2] - 1, "fast": 1, "blur": ORB_ARGS[2], "octree": 1, "assemble": 1, "orient_describe": 1}
+    n_sets = (n_img + group - 1) // group
+    dom_launch_ms = stage_ms[dom] / (launches_of[dom] * n_sets)
+    dom_bytes_launch = ab[dom] * n_img / (launches_of[dom] * n_sets)
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": dom_bytes_launch / (dom_launch_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": dom_bytes_launch / (dom_launch_ms * 1e-3) / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
+                "bytes_per_launch": dom_bytes_launch, "ms_per_launch": dom_launch_ms,
+                "whole_step": {"bytes_per_frame": 2 * ab["total"], "GBps": 2 * ab["total"] * args.pairs / (ms_step * 1e-3) / 1e9,
+                               "frac": 2 * ab["total"] * args.pairs / (ms_step * 1e-3) / 1e9 / peak}}
+
+    # ---- e2e: pinned host images in, keypoints/descriptors out, three pipelined handles ----
+    e2e = None
+    pinned_in = None
+    if not args.no_e2e:
+        chunk = min(args.chunk, n_img)
+        K = big.K
+        pinned_in = T.PinnedArray((n_img, H, W), np.uint8)
+        for first in range(0, n_img, 1024):
+            n = min(1024, n_img - first)
+            big.download_images(first, n, pinned_in.array[first:first + n])
+        out_kps = T.PinnedArray((n_img, K), T.KP_DTYPE)
+        out_desc = T.PinnedArray((n_img, K, 32), np.uint8)
+        out_cnt = T.PinnedArray((n_img,), np.int32)
+        out_mono = T.PinnedArray((n_img,), np.int32)
+        handles = [T.BatchExtractor(W, H, chunk, *ORB_ARGS, device=local) for _ in range(3)]
+        ends = [Event() for _ in handles]
+        start = Event()
+
+        def e2e_step():
+            for ci, first in enumerate(range(0, n_img, chunk)):
+                n = min(chunk, n_img - first)
+                h = handles[ci % len(handles)]
+                h.upload(pinned_in.array[first:first + n])
+                h.run(n)
+                h.download_async(0, n, out_kps.array[first:first + n], out_desc.array[first:first + n], out_cnt.array[first:first + n], out_mono.array[first:first + n])
+
+        for _ in range(args.warmup):
+            e2e_step()
+        for h in handles:
+            h.check()
+        assert np.array_equal(out_cnt.array, counts), "e2e keypoint counts differ from the resident run"
+        barrier()
+        start.record(handles[0])
+        for _ in range(args.steps):
+            e2e_step()
+        for h, e in zip(handles, ends):
+            e.record(h)
+        ms_e2e = max(start.elapsed_ms(e) for e in ends) / args.steps
+        for h in handles:
+            h.check()
+        barrier()
+        ms_e2e = max_over_ranks(ms_e2e)
+        h2d = n_img * H * W
+        d2h = n_img * (K * 28 + K * 32 + 8)
+        e2e = {"value": args.pairs * world / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": ms_e2e, "pipeline": f"3 handles x {chunk} images, pinned host buffers",
+               "gpu_launches": handles[0].kernel_launches * ((n_img + chunk - 1) // chunk)}
+        for h in handles:
+            h.close()
+
+    # ---- stereo-pair latency through the reference-shaped API (BASELINE.json configs[1]) ----
+    latency = None
+    if rank == 0:
+        st = T.StereoORBextractor(*ORB_ARGS, device=local)
+        if pinned_in is not None:
+            left, right = pinned_in.array[0], pinned_in.array[1]
+        else:
+            tmp = np.empty((2, H, W), np.uint8)
+            big.download_images(0, 2, tmp)
+            left, right = tmp[0], tmp[1]
+        for _ in range(5):
+            st(left, right)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            st(left, right)
+        latency = {"stereo_pair_ms": (time.perf_counter() - t0) / 20 * 1e3, "what": "orbx_extract_stereo, host images in, host keypoints+descriptors out, 2 streams"}
+        st.close()
+
+    # ---- CPU baseline on this box's host cores (rank 0, N == 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        kind, make = cpu_backend()
+        cores = os.cpu_count() or 1
+        if pinned_in is not None:
+            src = pinned_in.array
+        else:
+            src = np.empty((min(n_img, 64), H, W), np.uint8)
+            big.download_images(0, len(src), src)
+        dt1, _ = cpu_run(src[:2], 1, make)
+        per_img = dt1 / 2
+        n_s = int(min(len(src), max(2 * cores, (15.0 * cores / per_img) // 2 * 2)))
+        dt, nk = cpu_run(src[:n_s], cores, make)
+        cpu = {"value": (n_s / 2) / dt, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"first {n_s // 2} stereo frames of this workload, sharded over {cores} host threads, {dt:.1f} s wall",
+               "single_thread_ms_per_image": per_img * 1e3}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "BASELINE.json configs[4]: batch of KITTI-shaped stereo frames 1241x376 (left+right), ORBextractor(2000,1.2,8,20,7), sharded by frame",
+                       "pairs_per_gpu_per_step": args.pairs, "images_per_launch_set": group, "keypoints_per_image": kp_mean,
+                       "l2": f"inputs {n_img * W * H / 1e9:.2f} GB per rank, larger than the {L2_BYTES / 1e6:.0f} MB L2; no flush needed"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step, "roofline": roofline, "cpu_baseline": cpu, "stages": stages, "latency": latency,
+        }
+        print(json.dumps(line))
+    big.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

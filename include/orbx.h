@@ -113,6 +113,8 @@ void* orbx_batch_get_stream(const orbx_batch* b);
 int orbx_batch_upload(orbx_batch* b, const uint8_t* host_images, size_t row_stride, size_t image_stride, int first_image, int n_images);
 int orbx_batch_upload_device(orbx_batch* b, const uint8_t* dev_images, size_t row_stride, size_t image_stride, int first_image, int n_images);
 int orbx_batch_synth(orbx_batch* b, uint32_t seed0, int first_image, int n_images, int stereo);
+/* level-0 images [first, first+n) back to a dense host array (synchronous) */
+int orbx_batch_download_images(orbx_batch* b, int first_image, int n_images, uint8_t* host_images, size_t row_stride, size_t image_stride);
 
 /* all kernels of the hot path for images [0, n_images), asynchronous on the handle's stream.
  * lapping: n_images x {lap0, lap1} (host ints) or NULL for {0,0} everywhere. */
@@ -121,6 +123,21 @@ int orbx_batch_run(orbx_batch* b, int n_images, const int* lapping);
  * counts [n_images], mono_index [n_images]; any pointer may be NULL to skip that array. */
 int orbx_batch_download(orbx_batch* b, int n_images, orbx_keypoint* keypoints, uint8_t* descriptors, int* counts, int* mono_index);
 int orbx_batch_sync(orbx_batch* b);
+/* the same on a sub-range [first, first+n) of the handle's images (lapping: n x 2 ints for that range): lets a caller keep
+ * many frames resident and process them in groups small enough for the 126 MB L2 */
+int orbx_batch_run_range(orbx_batch* b, int first, int n, const int* lapping);
+/* D2H of a sub-range without waiting (pinned destinations make it truly asynchronous); orbx_batch_check() synchronises the
+ * stream and reports device-side capacity errors */
+int orbx_batch_download_async(orbx_batch* b, int first, int n, orbx_keypoint* keypoints, uint8_t* descriptors, int* counts, int* mono_index);
+int orbx_batch_check(orbx_batch* b);
+
+/* CUDA events on the handles' streams (device-side timing, ordering between handles of a pipelined caller) */
+void* orbx_event_create(void);
+void orbx_event_destroy(void* ev);
+int orbx_event_record(void* ev, orbx_batch* b);
+int orbx_event_wait(orbx_batch* b, void* ev);
+int orbx_event_synchronize(void* ev);
+int orbx_event_elapsed_ms(void* start, void* stop, float* ms);
 int orbx_batch_get_level_size(const orbx_batch* b, int level, int* width, int* height);
 int orbx_batch_get_level(orbx_batch* b, int image, int level, uint8_t* dst, size_t dst_stride, int border);
 

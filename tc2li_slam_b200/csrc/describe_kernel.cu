@@ -26,7 +26,7 @@ cudaError_t upload_describe_constants(const signed char pattern[1024], const int
 __global__ void __launch_bounds__(256) k_assemble(const __grid_constant__ Geom g, const Buffers b) {
     __shared__ int warpTot[8];
     __shared__ int carry;  // keypoints outside the lapping window so far
-    const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int img = b.imgBase + blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int* selCount = b.selCount + img * ORBX_MAX_LEVELS;
     int total = 0;
     for (int l = 0; l < g.nlevels; ++l) total += selCount[l];
@@ -90,7 +90,7 @@ void launch_assemble(const Geom& g, const Buffers& b, int nImages, cudaStream_t 
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_describe(const __grid_constant__ Geom g, const Buffers b) {
     __shared__ signed char pat[1024];
-    const int img = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+    const int img = b.imgBase + blockIdx.y, tid = threadIdx.x, lane = tid & 31;
     for (int k = tid; k < 256; k += 256) reinterpret_cast<int*>(pat)[k] = reinterpret_cast<const int*>(c_pattern)[k];
     __syncthreads();
     const int n = b.outCount[img];

@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Geom
 
     const uint8_t* tile = reinterpret_cast<const uint8_t*>(tileW);
     uint16_t* list = reinterpret_cast<uint16_t*>(listBuf);
-    const int tid = threadIdx.x, img = blockIdx.y;
+    const int tid = threadIdx.x, img = b.imgBase + blockIdx.y;
 
     // which level / cell
     int level = 0;

@@ -82,7 +82,8 @@ void launch_pyramid_level(const Geom& g, const Buffers& b, int level, const Resi
     const LevelGeom& S = g.lv[level - 1];
     const LevelGeom& D = g.lv[level];
     dim3 grid((D.w + 127) / 128, (D.h + 7) / 8, nImages), block(32, 8);
-    k_resize<<<grid, block, 0, s>>>(b.pyr + S.planeOff, S.w, S.h, S.pitch, (size_t)S.planeBytes, b.pyr + D.planeOff, D.w, D.h, D.pitch,
+    k_resize<<<grid, block, 0, s>>>(b.pyr + S.planeOff + (size_t)b.imgBase * S.planeBytes, S.w, S.h, S.pitch, (size_t)S.planeBytes,
+                                   b.pyr + D.planeOff + (size_t)b.imgBase * D.planeBytes, D.w, D.h, D.pitch,
                                    (size_t)D.planeBytes, tab);
 }
 
@@ -138,7 +139,8 @@ void launch_blur(const Geom& g, const Buffers& b, int level, int nImages, const 
     Taps t;
     for (int i = 0; i < 7; ++i) t.k[i] = taps[i];
     dim3 grid((L.w + BT_W - 1) / BT_W, (L.h + BT_H - 1) / BT_H, nImages);
-    k_blur<<<grid, 256, 0, s>>>(b.pyr + L.planeOff, b.blur + L.planeOff, L.w, L.h, L.pitch, (size_t)L.planeBytes, t);
+    const size_t o = (size_t)L.planeOff + (size_t)b.imgBase * L.planeBytes;
+    k_blur<<<grid, 256, 0, s>>>(b.pyr + o, b.blur + o, L.w, L.h, L.pitch, (size_t)L.planeBytes, t);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

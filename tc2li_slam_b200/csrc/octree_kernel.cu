@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(OT_THREADS) k_octree(const __grid_constant__ G
     extern __shared__ __align__(16) unsigned char smemRaw[];
     __shared__ int sh_finish, sh_size, sh_err;
 
-    const int level = blockIdx.x, img = blockIdx.y, tid = threadIdx.x;
+    const int level = blockIdx.x, img = b.imgBase + blockIdx.y, tid = threadIdx.x;
     const LevelGeom& L = g.lv[level];
     const int cap = L.nodeCap, N = L.quota;
     const int n = min(b.candCount[img * ORBX_MAX_LEVELS + level], L.candCap);

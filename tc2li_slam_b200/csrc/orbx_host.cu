@@ -207,6 +207,7 @@ int batch_alloc(orbx_batch* b) {
     if ((r = dev_alloc(b, &B.outCount, (size_t)n))) return r;
     if ((r = dev_alloc(b, &B.outMono, (size_t)n))) return r;
     if ((r = dev_alloc(b, &B.errFlag, 1))) return r;
+    B.imgBase = 0;
     CU(cudaMemset(B.errFlag, 0, sizeof(int)));
     CU(cudaMemset(B.lapping, 0, (size_t)n * 2 * sizeof(int)));
     CU(cudaMemset(B.pyr, 0, b->pyrBytes));
@@ -347,6 +348,20 @@ int orbx_batch_upload_device(orbx_batch* b, const uint8_t* dev_images, size_t ro
     return ORBX_OK;
 }
 
+// level-0 images of the handle back to the host (e.g. frames produced by orbx_batch_synth): one strided copy
+int orbx_batch_download_images(orbx_batch* b, int first, int n, uint8_t* host_images, size_t row_stride, size_t image_stride) {
+    int r = check_images(b, first, n);
+    if (r) return r;
+    if (!host_images || row_stride < (size_t)b->width || image_stride != row_stride * (size_t)b->height)
+        return fail(ORBX_ERR_ARG, "need a dense [n][height][row_stride] destination");
+    DeviceGuard dg(b->device);
+    const LevelGeom& L0 = b->g.lv[0];
+    CU(cudaMemcpy2DAsync(host_images, row_stride, b->buf.pyr + L0.planeOff + (size_t)first * L0.planeBytes, L0.pitch, b->width,
+                         (size_t)b->height * n, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return ORBX_OK;
+}
+
 int orbx_batch_synth(orbx_batch* b, uint32_t seed0, int first, int n, int stereo) {
     int r = check_images(b, first, n);
     if (r) return r;
@@ -358,43 +373,49 @@ int orbx_batch_synth(orbx_batch* b, uint32_t seed0, int first, int n, int stereo
     return ORBX_OK;
 }
 
-int orbx_batch_run(orbx_batch* b, int n, const int* lapping) {
-    int r = check_images(b, 0, n);
+int orbx_batch_run_range(orbx_batch* b, int first, int n, const int* lapping) {
+    int r = check_images(b, first, n);
     if (r) return r;
     if (n == 0) return ORBX_OK;
     DeviceGuard dg(b->device);
     const Geom& g = b->g;
     cudaStream_t s = b->stream;
+    Buffers buf = b->buf;
+    buf.imgBase = first;
     int launches = 0;
     if (lapping) {
-        b->hostLap.assign(lapping, lapping + 2 * (size_t)n);
-        CU(cudaMemcpyAsync(b->buf.lapping, b->hostLap.data(), (size_t)n * 2 * sizeof(int), cudaMemcpyHostToDevice, s));
+        // (the staging vector must stay untouched until the copy has run: one slot per image of the handle)
+        b->hostLap.resize(2 * (size_t)b->maxImages);
+        std::memcpy(b->hostLap.data() + 2 * (size_t)first, lapping, 2 * (size_t)n * sizeof(int));
+        CU(cudaMemcpyAsync(buf.lapping + 2 * (size_t)first, b->hostLap.data() + 2 * (size_t)first, (size_t)n * 2 * sizeof(int), cudaMemcpyHostToDevice, s));
     } else
-        CU(cudaMemsetAsync(b->buf.lapping, 0, (size_t)n * 2 * sizeof(int), s));
-    CU(cudaMemsetAsync(b->buf.candCount, 0, (size_t)n * ORBX_MAX_LEVELS * sizeof(int), s));
+        CU(cudaMemsetAsync(buf.lapping + 2 * (size_t)first, 0, (size_t)n * 2 * sizeof(int), s));
+    CU(cudaMemsetAsync(buf.candCount + (size_t)first * ORBX_MAX_LEVELS, 0, (size_t)n * ORBX_MAX_LEVELS * sizeof(int), s));
     int evi = 0;
     auto mark = [&]() { if (b->timing) cudaEventRecord(b->ev[evi++], s); };
     mark();
-    for (int l = 1; l < g.nlevels; ++l) { launch_pyramid_level(g, b->buf, l, b->tabs[l], n, s); ++launches; }
+    for (int l = 1; l < g.nlevels; ++l) { launch_pyramid_level(g, buf, l, b->tabs[l], n, s); ++launches; }
     mark();
-    launch_fast(g, b->buf, n, s); ++launches;
+    launch_fast(g, buf, n, s); ++launches;
     mark();
-    for (int l = 0; l < g.nlevels; ++l) { launch_blur(g, b->buf, l, n, b->taps, s); ++launches; }
+    for (int l = 0; l < g.nlevels; ++l) { launch_blur(g, buf, l, n, b->taps, s); ++launches; }
     mark();
     {
-        cudaError_t e = launch_octree(g, b->buf, n, s); ++launches;
+        cudaError_t e = launch_octree(g, buf, n, s); ++launches;
         if (e != cudaSuccess) return cuda_fail(e, "octree launch");
     }
     mark();
-    launch_assemble(g, b->buf, n, s); ++launches;
+    launch_assemble(g, buf, n, s); ++launches;
     mark();
-    launch_describe(g, b->buf, n, s); ++launches;
+    launch_describe(g, buf, n, s); ++launches;
     mark();
     CU(cudaGetLastError());
     b->launches = launches;
     b->lastImages = n;
     return ORBX_OK;
 }
+
+int orbx_batch_run(orbx_batch* b, int n, const int* lapping) { return orbx_batch_run_range(b, 0, n, lapping); }
 
 int orbx_batch_sync(orbx_batch* b) {
     if (!b) return fail(ORBX_ERR_ARG, "null batch");
@@ -403,25 +424,67 @@ int orbx_batch_sync(orbx_batch* b) {
     return ORBX_OK;
 }
 
-int orbx_batch_download(orbx_batch* b, int n, orbx_keypoint* keypoints, uint8_t* descriptors, int* counts, int* mono_index) {
-    int r = check_images(b, 0, n);
+int orbx_batch_download_async(orbx_batch* b, int first, int n, orbx_keypoint* keypoints, uint8_t* descriptors, int* counts, int* mono_index) {
+    int r = check_images(b, first, n);
     if (r) return r;
+    if (n == 0) return ORBX_OK;
     DeviceGuard dg(b->device);
     cudaStream_t s = b->stream;
     const size_t K = (size_t)b->g.K;
+    if (keypoints) CU(cudaMemcpyAsync(keypoints, b->buf.kps + first * K, n * K * sizeof(orbx_keypoint), cudaMemcpyDeviceToHost, s));
+    if (descriptors) CU(cudaMemcpyAsync(descriptors, b->buf.desc + first * K * 32, n * K * 32, cudaMemcpyDeviceToHost, s));
+    if (counts) CU(cudaMemcpyAsync(counts, b->buf.outCount + first, n * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (mono_index) CU(cudaMemcpyAsync(mono_index, b->buf.outMono + first, n * sizeof(int), cudaMemcpyDeviceToHost, s));
+    return ORBX_OK;
+}
+
+int orbx_batch_check(orbx_batch* b) {
+    if (!b) return fail(ORBX_ERR_ARG, "null batch");
+    DeviceGuard dg(b->device);
     int err = 0;
-    if (n) {
-        if (keypoints) CU(cudaMemcpyAsync(keypoints, b->buf.kps, n * K * sizeof(orbx_keypoint), cudaMemcpyDeviceToHost, s));
-        if (descriptors) CU(cudaMemcpyAsync(descriptors, b->buf.desc, n * K * 32, cudaMemcpyDeviceToHost, s));
-        if (counts) CU(cudaMemcpyAsync(counts, b->buf.outCount, n * sizeof(int), cudaMemcpyDeviceToHost, s));
-        if (mono_index) CU(cudaMemcpyAsync(mono_index, b->buf.outMono, n * sizeof(int), cudaMemcpyDeviceToHost, s));
-    }
-    CU(cudaMemcpyAsync(&err, b->buf.errFlag, sizeof(int), cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
+    CU(cudaMemcpyAsync(&err, b->buf.errFlag, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
     if (err) {
-        cudaMemsetAsync(b->buf.errFlag, 0, sizeof(int), s);
+        cudaMemsetAsync(b->buf.errFlag, 0, sizeof(int), b->stream);
         return fail(ORBX_ERR_CAPACITY, err == 1 ? "device candidate buffer overflow" : "device quadtree capacity exceeded");
     }
+    return ORBX_OK;
+}
+
+int orbx_batch_download(orbx_batch* b, int n, orbx_keypoint* keypoints, uint8_t* descriptors, int* counts, int* mono_index) {
+    int r = orbx_batch_download_async(b, 0, n, keypoints, descriptors, counts, mono_index);
+    if (r) return r;
+    return orbx_batch_check(b);
+}
+
+// ---- CUDA events on the handles' streams: device-side timing and cross-handle ordering for pipelined callers ----
+void* orbx_event_create(void) {
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) { g_err = "cudaEventCreate failed"; return nullptr; }
+    return (void*)e;
+}
+void orbx_event_destroy(void* ev) { if (ev) cudaEventDestroy((cudaEvent_t)ev); }
+int orbx_event_record(void* ev, orbx_batch* b) {
+    if (!ev || !b) return fail(ORBX_ERR_ARG, "null argument");
+    DeviceGuard dg(b->device);
+    CU(cudaEventRecord((cudaEvent_t)ev, b->stream));
+    return ORBX_OK;
+}
+int orbx_event_wait(orbx_batch* b, void* ev) {
+    if (!ev || !b) return fail(ORBX_ERR_ARG, "null argument");
+    DeviceGuard dg(b->device);
+    CU(cudaStreamWaitEvent(b->stream, (cudaEvent_t)ev, 0));
+    return ORBX_OK;
+}
+int orbx_event_synchronize(void* ev) {
+    if (!ev) return fail(ORBX_ERR_ARG, "null argument");
+    CU(cudaEventSynchronize((cudaEvent_t)ev));
+    return ORBX_OK;
+}
+int orbx_event_elapsed_ms(void* start, void* stop, float* ms) {
+    if (!start || !stop || !ms) return fail(ORBX_ERR_ARG, "null argument");
+    CU(cudaEventSynchronize((cudaEvent_t)stop));
+    CU(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));
     return ORBX_OK;
 }
 

@@ -85,6 +85,7 @@ struct Buffers {
     int* outCount;          // [image]
     int* outMono;           // [image]
     int* errFlag;           // device-side error flag (capacity overflow etc.)
+    int imgBase;            // first image of this launch set (kernels index images as imgBase + blockIdx)
 };
 
 // kernel launchers (one translation unit per stage)

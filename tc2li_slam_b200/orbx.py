@@ -72,9 +72,19 @@ def lib():
         "orbx_batch_upload": (i, [_vp, _vp, sz, sz, i, i]),
         "orbx_batch_upload_device": (i, [_vp, _vp, sz, sz, i, i]),
         "orbx_batch_synth": (i, [_vp, u32, i, i, i]),
+        "orbx_batch_download_images": (i, [_vp, i, i, _vp, sz, sz]),
         "orbx_batch_run": (i, [_vp, i, _vp]),
         "orbx_batch_download": (i, [_vp, i, _vp, _vp, _vp, _vp]),
         "orbx_batch_sync": (i, [_vp]),
+        "orbx_batch_run_range": (i, [_vp, i, i, _vp]),
+        "orbx_batch_download_async": (i, [_vp, i, i, _vp, _vp, _vp, _vp]),
+        "orbx_batch_check": (i, [_vp]),
+        "orbx_event_create": (_vp, []),
+        "orbx_event_destroy": (None, [_vp]),
+        "orbx_event_record": (i, [_vp, _vp]),
+        "orbx_event_wait": (i, [_vp, _vp]),
+        "orbx_event_synchronize": (i, [_vp]),
+        "orbx_event_elapsed_ms": (i, [_vp, _vp, _vp]),
         "orbx_batch_get_level_size": (i, [_vp, i, _vp, _vp]),
         "orbx_batch_get_level": (i, [_vp, i, i, _vp, sz, i]),
         "orbx_batch_enable_timing": (i, [_vp, i]),
@@ -153,6 +163,38 @@ def debug_atan2(y, x):
     out = np.empty_like(y)
     _check(lib().orbx_debug_atan2(_p(y), _p(x), _p(out), len(y)))
     return out
+
+
+class Event:
+    """CUDA event recorded on a BatchExtractor's stream (device-side timing / ordering between handles)."""
+
+    def __init__(self):
+        self._e = lib().orbx_event_create()
+        if not self._e:
+            raise OrbxError(ERR_CUDA, lib().orbx_last_error().decode())
+
+    def record(self, batch):
+        _check(lib().orbx_event_record(self._e, batch._h))
+
+    def wait_on(self, batch):
+        """Make `batch`'s stream wait for this event."""
+        _check(lib().orbx_event_wait(batch._h, self._e))
+
+    def synchronize(self):
+        _check(lib().orbx_event_synchronize(self._e))
+
+    def elapsed_ms(self, stop):
+        ms = C.c_float(0)
+        _check(lib().orbx_event_elapsed_ms(self._e, stop._e, C.byref(ms)))
+        return ms.value
+
+    def __del__(self):
+        try:
+            if self._e:
+                lib().orbx_event_destroy(self._e)
+                self._e = None
+        except Exception:
+            pass
 
 
 class PinnedArray:
@@ -379,14 +421,35 @@ class BatchExtractor:
     def synth(self, seed0, n, stereo=True, first=0):
         _check(lib().orbx_batch_synth(self._h, seed0 & 0xFFFFFFFF, first, n, int(stereo)))
 
+    def download_images(self, first, n, out):
+        """Level-0 images [first, first+n) into a dense uint8 [n, H, W'] host array (W' >= W)."""
+        assert out.dtype == np.uint8 and out.ndim == 3 and out.strides[2] == 1 and out.strides[0] == out.strides[1] * out.shape[1]
+        _check(lib().orbx_batch_download_images(self._h, first, n, _p(out), out.strides[1], out.strides[0]))
+
     def run(self, n, lapping=None):
         lp = None
         if lapping is not None:
             lp = np.ascontiguousarray(lapping, np.int32).reshape(n, 2)
         _check(lib().orbx_batch_run(self._h, n, _p(lp) if lp is not None else None))
 
+    def run_range(self, first, n, lapping=None):
+        lp = None
+        if lapping is not None:
+            lp = np.ascontiguousarray(lapping, np.int32).reshape(n, 2)
+        _check(lib().orbx_batch_run_range(self._h, first, n, _p(lp) if lp is not None else None))
+
     def sync(self):
         _check(lib().orbx_batch_sync(self._h))
+
+    def check(self):
+        """Synchronise the stream and raise if a device-side capacity error was recorded."""
+        _check(lib().orbx_batch_check(self._h))
+
+    def download_async(self, first, n, keypoints, descriptors, counts, mono):
+        """Enqueue D2H of images [first, first+n) into the given (ideally pinned) host arrays; no wait."""
+        _check(lib().orbx_batch_download_async(self._h, first, n, _p(keypoints) if keypoints is not None else None,
+                                               _p(descriptors) if descriptors is not None else None,
+                                               _p(counts) if counts is not None else None, _p(mono) if mono is not None else None))
 
     def download(self, n, keypoints=None, descriptors=None, counts=None, mono=None):
         """Fills (or allocates) host arrays [n,K] / [n,K,32] / [n] / [n]; returns them."""
