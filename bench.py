@@ -174,6 +174,7 @@ def main():
     ap.add_argument("--ref-pairs", type=int, default=256, help="stereo frames per step of the CPU arms (bounded sample)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-latency", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing hygiene: at least three warm-up steps
@@ -329,7 +330,7 @@ def main():
 
     # ---- stereo-pair latency through the reference-shaped API (BASELINE.json configs[1]) ----
     latency = None
-    if rank == 0:
+    if rank == 0 and not args.no_latency:
         st = T.StereoORBextractor(*ORB_ARGS, device=local)
         if pinned_in is not None:
             left, right = pinned_in.array[0], pinned_in.array[1]

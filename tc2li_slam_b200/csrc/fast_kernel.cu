@@ -11,25 +11,34 @@
 // interior (3-px rim excluded).  Hence ONE score pass serves both thresholds: the cell uses iniThFAST when any survivor has
 // S > iniThFAST, otherwise minThFAST.  Pixels that are not corners at minThFAST get S := 0, which cannot change any
 // comparison.  Integer only; HBM traffic = one read of every level, the work is ALU/issue bound.
+#include <algorithm>
+
 #include "orbx_internal.cuh"
 
 namespace orbx {
 
 namespace {
 
-constexpr int TS_WORDS = 22;             // tile row stride in 32-bit words: (kMaxCell + 6 + 3 alignment slack) / 4 rounded up
-constexpr int TS = TS_WORDS * 4;         // tile row stride in bytes
-constexpr int TROWS = kMaxCell + 6;      // rows of the cell crop
-constexpr int SS = kMaxCell + 4;         // score row stride (interior + 1-px zero rim, padded)
-constexpr int MAXPIX = kMaxCell * kMaxCell;
+constexpr int FAST_THREADS = 128;
+constexpr int TSW = 23;                  // tile row stride in 32-bit words: 1 pad word + (kMaxCell + 6 + 3 alignment slack) / 4, odd
+constexpr int TS = TSW * 4;              // tile row stride in bytes (92)
+constexpr unsigned FULL = 0xFFFFFFFFu;
 
-__device__ __forceinline__ bool has_arc9(uint32_t m) {  // >= 9 contiguous set bits in a circular 16-bit mask
-    m |= m << 16;
-    m &= m >> 1;
-    m &= m >> 2;
-    m &= m >> 4;
-    m &= m >> 1;
-    return (m & 0xFFFFu) != 0;
+// >= 9 contiguous set bits in each circular 16-bit half of m (low half: bright mask, high half: dark mask)
+__device__ __forceinline__ uint32_t arc9_halves(uint32_t m) {
+    const uint32_t lo = m & 0xFFFFu, hi = m >> 16;
+    uint32_t a = lo | (lo << 16), c = hi | (hi << 16);
+    a &= a >> 1; c &= c >> 1;
+    a &= a >> 2; c &= c >> 2;
+    a &= a >> 4; c &= c >> 4;
+    a &= a >> 1; c &= c >> 1;
+    return (a & 0xFFFFu) | (c << 16);
+}
+
+// per byte: 0x80 where the byte of d exceeds t (0 <= t <= 254); kAdd = (0x7f - (t & 0x7f)) * 0x01010101
+__device__ __forceinline__ uint32_t bytes_gt(uint32_t d, uint32_t kAdd, bool tHigh) {
+    const uint32_t low = (d & 0x7f7f7f7fu) + kAdd;  // bit 7 of each byte: (d & 0x7f) > (t & 0x7f)
+    return tHigh ? (low & d) : (low | d);           // t >= 128: also needs d >= 128; t < 128: d >= 128 suffices
 }
 
 // byte offsets of the 16 ring pixels inside the shared tile
@@ -39,81 +48,135 @@ __device__ __forceinline__ bool has_arc9(uint32_t m) {  // >= 9 contiguous set b
 
 }  // namespace
 
-__global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Geom g, const Buffers b) {
-    __shared__ uint32_t tileW[TROWS * TS_WORDS];
-    __shared__ uint8_t sc[(kMaxCell + 2) * SS];
-    __shared__ uint32_t listBuf[MAXPIX / 2];  // uint16 corner list in passes A-C, packed candidates afterwards
-    __shared__ uint16_t surv[MAXPIX / 4 + kMaxCell + 8];
-    __shared__ int nList, nSurv, nOut, outBase;
+// Passes (all over one cell crop staged in shared memory; pixels are addressed by their byte offset inside the tile, the
+// score map shares the tile's layout, so no pass needs a division):
+//   A  four pixels per thread, packed in one 32-bit word: |ring - centre| > minTh at the four compass points, combined as
+//      (N|S)&(E|W) — a necessary condition for a 9-arc of either polarity (VABSDIFF4 + carry tricks);
+//      survivors (~15 % of the pixels of a textured frame) are appended to a list with ballot-aggregated offsets;
+//   A2 dense over that list: exact bright/dark masks of the 16 ring pixels (both polarities at once in 16x2 lanes: the sign
+//      bits of hi - r and r - lo) and the contiguity test -> list of corners;
+//   B  dense over the corners: arc score S;   C  cell-local 3x3 NMS, iniTh/minTh decision, packed output.
+// Shared memory (dynamic): tile [rows][92] | score map [rows][92] | list1 [maxPix] u16 | list2 [maxPix] u16.
+__global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_constant__ Geom g, const Buffers b, int tileRows, int maxPix) {
+    extern __shared__ __align__(16) uint32_t fsm[];
+    __shared__ int n1, n2, nSurv, nOut, outBase;
+    uint32_t* tileW = fsm;
+    uint32_t* scW = fsm + tileRows * TSW;
+    uint16_t* list1 = reinterpret_cast<uint16_t*>(scW + tileRows * TSW);
+    uint16_t* list2 = list1 + maxPix;
 
-    const uint8_t* tile = reinterpret_cast<const uint8_t*>(tileW);
-    uint16_t* list = reinterpret_cast<uint16_t*>(listBuf);
-    const int tid = threadIdx.x, img = b.imgBase + blockIdx.y;
+    const uint8_t* tile = reinterpret_cast<const uint8_t*>(tileW) + 4;  // skip the pad word: tile[r * TS + c] = crop byte (r, a0 + c)
+    uint8_t* sc = reinterpret_cast<uint8_t*>(scW) + 4;                   // same layout as the tile
+    const int tid = threadIdx.x, lane = tid & 31, img = b.imgBase + blockIdx.y;
 
-    // which level / cell
-    int level = 0;
-    while (level + 1 < g.nlevels && (int)blockIdx.x >= g.lv[level + 1].cellOff) ++level;
-    const LevelGeom& L = g.lv[level];
-    const int ci = (int)blockIdx.x - L.cellOff;
-    const int i = ci / L.nCols, j = ci - i * L.nCols;
-    const int maxBX = L.w - kBorder, maxBY = L.h - kBorder;
-    const int iniX = kBorder + j * L.wCell, iniY = kBorder + i * L.hCell;
-    const int cw = min(iniX + L.wCell + 6, maxBX) - iniX, ch = min(iniY + L.hCell + 6, maxBY) - iniY;
+    // cell descriptor, precomputed on the host (make_cell_table)
+    const uint4 cd = __ldg(b.cellTab + blockIdx.x);
+    const int iniX = cd.x & 0xFFFF, iniY = cd.x >> 16;
+    const int cw = cd.y & 0xFF, ch = (cd.y >> 8) & 0xFF, level = (cd.y >> 16) & 0xFF, kind = cd.y >> 24;
     uint8_t* flag = b.cellFlags + (size_t)img * g.cellsPerImage + blockIdx.x;
-    if (iniY >= maxBY - 3 || iniX >= maxBX - 6) {  // cells the reference skips (ORBextractor.cc:785-796)
-        if (tid == 0) *flag = 0;
+    if (kind != 2) {  // 0: a cell the reference skips (ORBextractor.cc:785-796); 1: crop thinner than the ring, cv::FAST yields nothing
+        if (tid == 0) *flag = kind == 0 ? 0 : 2;
         return;
     }
-    if (cw < 7 || ch < 7) {  // cv::FAST yields nothing on crops thinner than the ring, at either threshold
-        if (tid == 0) *flag = 2;
-        return;
-    }
-    const int iw = cw - 6, ih = ch - 6, npix = iw * ih;
+    const LevelGeom& L = g.lv[level];
+    const int iw = cw - 6, ih = ch - 6;
+    const int nW = cd.w & 0xFF, wFirst = (cd.w >> 8) & 0xFF, shift = (cd.w >> 16) & 0xFF;
+    const uint32_t magicW = cd.z;
 
-    // ---- stage the crop: aligned 32-bit loads, one warp per row ----
-    const uint8_t* lev = b.pyr + L.planeOff + (size_t)img * L.planeBytes;
-    const int a0 = iniX & ~3, shift = iniX - a0;
-    const int nWords = (iniX + cw - a0 + 3) >> 2;
-    for (int r = tid >> 5; r < ch; r += 8) {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(lev + (size_t)(iniY + r) * L.pitch + a0);
-        for (int c = tid & 31; c < nWords; c += 32) tileW[r * TS_WORDS + c] = __ldg(src + c);
+    // ---- stage the crop: aligned 32-bit loads; tile word (c + 1) of a row = global bytes a0 + 4c .. ----
+    {
+        const uint8_t* lev = b.pyr + L.planeOff + (size_t)img * L.planeBytes + (size_t)iniY * L.pitch + (iniX - shift);
+        const int nWords = (shift + cw + 3) >> 2;
+        const int rpi = FAST_THREADS / 32;
+        for (int r = tid >> 5; r < ch; r += rpi)
+            if (lane < nWords) tileW[r * TSW + 1 + lane] = __ldg(reinterpret_cast<const uint32_t*>(lev + (size_t)r * L.pitch) + lane);
+        uint4* z = reinterpret_cast<uint4*>(scW);
+        const int nz = (ch * TSW + 3) >> 2;
+        for (int k = tid; k < nz; k += FAST_THREADS) z[k] = make_uint4(0, 0, 0, 0);
+        if (tid == 0) { n1 = 0; n2 = 0; nSurv = 0; nOut = 0; }
     }
-    for (int k = tid; k < (ih + 2) * SS; k += 256) sc[k] = 0;
-    if (tid == 0) { nList = 0; nSurv = 0; nOut = 0; }
     __syncthreads();
 
-    // ---- pass A: which pixels are corners at minThFAST (cheap reject first) ----
+    // ---- pass A: compass test, 4 pixels per thread ----
     const int t = g.minTh;
-    const uint32_t magic = (0xFFFFFFFFu / (uint32_t)iw) + 1;  // exact p / iw for p < 2^16
-    for (int p = tid; p < npix; p += 256) {
-        const int y = (int)__umulhi((uint32_t)p, magic), x = p - y * iw;
-        const uint8_t* c = tile + (y + 3) * TS + x + 3 + shift;
-        const int v = c[0], hi = v + t, lo = v - t;
-        const int r0 = c[RING(0)], r8 = c[RING(8)];
-        bool br = (r0 > hi) | (r8 > hi), dk = (r0 < lo) | (r8 < lo);
-        if (!(br | dk)) continue;
-        const int r4 = c[RING(4)], r12 = c[RING(12)];
-        br &= (r4 > hi) | (r12 > hi);
-        dk &= (r4 < lo) | (r12 < lo);
-        if (!(br | dk)) continue;
-        uint32_t mb = 0, md = 0;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const int r = c[RING(k)];
-            mb |= (uint32_t)(r > hi) << k;
-            md |= (uint32_t)(r < lo) << k;
+    {
+        const uint32_t kAdd = (uint32_t)(0x7f - (t & 0x7f)) * 0x01010101u;
+        const bool tHigh = t >= 128;
+        const int items = ih * nW;
+        const int xb0 = 4 * wFirst - 3 - shift;  // interior x of byte 0 of the first word (<= 0)
+        for (int it0 = 0; it0 < items; it0 += FAST_THREADS) {
+            const int it = it0 + tid;
+            uint32_t F = 0;
+            int off = 0;
+            if (it < items) {
+                const int y = (int)__umulhi((uint32_t)it, magicW), cc = it - y * nW;
+                const uint32_t* row = tileW + (y + 3) * TSW + 1 + wFirst + cc;
+                const uint32_t cur = row[0], prev = row[-1], next = row[1], up = row[3 * TSW], dn = row[-3 * TSW];
+                const uint32_t e = __funnelshift_r(cur, next, 24);  // pixels at x + 3
+                const uint32_t w = __funnelshift_r(prev, cur, 8);   // pixels at x - 3
+                const uint32_t ns = bytes_gt(__vabsdiffu4(up, cur), kAdd, tHigh) | bytes_gt(__vabsdiffu4(dn, cur), kAdd, tHigh);
+                const uint32_t ew = bytes_gt(__vabsdiffu4(e, cur), kAdd, tHigh) | bytes_gt(__vabsdiffu4(w, cur), kAdd, tHigh);
+                // bytes outside the interior [0, iw) are dropped
+                const int xb = xb0 + 4 * cc;
+                const int nL = max(-xb, 0), nR = max(xb + 4 - iw, 0);
+                const uint32_t valid = (0xFFFFFFFFu << (8 * nL)) & (0xFFFFFFFFu >> (8 * nR));
+                F = ns & ew & 0x80808080u & valid;
+                off = (y + 3) * TS + 4 * (wFirst + cc);  // tile byte offset of byte 0 of this word
+            }
+            // append the flagged pixels: one shared atomic per warp
+            const unsigned b0 = __ballot_sync(FULL, F & 0x80u), b1 = __ballot_sync(FULL, F & 0x8000u), b2 = __ballot_sync(FULL, F & 0x800000u),
+                           b3 = __ballot_sync(FULL, F & 0x80000000u);
+            const int c0 = __popc(b0), c1 = c0 + __popc(b1), c2 = c1 + __popc(b2), tot = c2 + __popc(b3);
+            if (tot) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&n1, tot);
+                base = __shfl_sync(FULL, base, 0);
+                const unsigned lt = (1u << lane) - 1;
+                if (F & 0x80u) list1[base + __popc(b0 & lt)] = (uint16_t)off;
+                if (F & 0x8000u) list1[base + c0 + __popc(b1 & lt)] = (uint16_t)(off + 1);
+                if (F & 0x800000u) list1[base + c1 + __popc(b2 & lt)] = (uint16_t)(off + 2);
+                if (F & 0x80000000u) list1[base + c2 + __popc(b3 & lt)] = (uint16_t)(off + 3);
+            }
         }
-        const bool isB = br && has_arc9(mb), isD = dk && has_arc9(md);
-        if (isB | isD) list[atomicAdd(&nList, 1)] = (uint16_t)(p | (isD ? 0x8000 : 0));
     }
     __syncthreads();
 
-    // ---- pass B: arc score of the listed pixels (dense over the list: no divergence on the expensive part) ----
-    const int nl = nList;
-    for (int k = tid; k < nl; k += 256) {
-        const int e = list[k], p = e & 0x7FFF;
-        const int y = (int)__umulhi((uint32_t)p, magic), x = p - y * iw;
-        const uint8_t* c = tile + (y + 3) * TS + x + 3 + shift;
+    // ---- pass A2: exact ring masks + contiguity, dense over list1 ----
+    const int nl1 = n1;
+    for (int k0 = 0; k0 < nl1; k0 += FAST_THREADS) {
+        const int k = k0 + tid;
+        int off = 0;
+        uint32_t arcs = 0;
+        if (k < nl1) {
+            off = list1[k];
+            const uint8_t* c = tile + off;
+            const uint32_t v = c[0];
+            // 16x2 lanes: low = (v + t + 1) - (r + 1) = hi - r, high = r - lo; (r + 1) * 0xFFFF = (r << 16) | (-(r + 1) & 0xFFFF)
+            const uint32_t K = (v + t + 1) | (((uint32_t)(t - (int)v) & 0xFFFFu) << 16);
+            uint32_t m = 0;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const uint32_t r = c[RING(q)];
+                const uint32_t sdiff = __vadd2(K, r * 0xFFFFu + 0xFFFFu);
+                m |= ((sdiff >> (15 - q)) & (0x00010001u << q));  // bit q: r > hi, bit 16 + q: r < lo
+            }
+            arcs = arc9_halves(m);
+        }
+        const unsigned bal = __ballot_sync(FULL, arcs != 0);
+        if (bal) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&n2, __popc(bal));
+            base = __shfl_sync(FULL, base, 0);
+            if (arcs) list2[base + __popc(bal & ((1u << lane) - 1))] = (uint16_t)(off | ((arcs >> 16) ? 0x8000 : 0));
+        }
+    }
+    __syncthreads();
+
+    // ---- pass B: arc score of the corners ----
+    const int nl = n2;
+    for (int k = tid; k < nl; k += FAST_THREADS) {
+        const int e = list2[k], off = e & 0x7FFF;
+        const uint8_t* c = tile + off;
         const int v = c[0];
         const int sgn = (e & 0x8000) ? -1 : 1;
         int d[16];
@@ -129,21 +192,30 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Geom
         int s = 0;
 #pragma unroll
         for (int q = 0; q < 16; ++q) s = max(s, min(m8[q], d[(q + 8) & 15]));
-        sc[(y + 1) * SS + x + 1] = (uint8_t)s;  // minTh < s <= 255
+        sc[off] = (uint8_t)s;  // minTh < s <= 255
     }
     __syncthreads();
 
-    // ---- pass C: cell-local 3x3 non-maximum suppression ----
+    // ---- pass C: cell-local 3x3 non-maximum suppression.  Only interior pixels ever get a score, so the rim reads 0. ----
     int anyIni = 0;
-    for (int k = tid; k < nl; k += 256) {
-        const int p = list[k] & 0x7FFF;
-        const int y = (int)__umulhi((uint32_t)p, magic), x = p - y * iw;
-        const uint8_t* q = sc + (y + 1) * SS + x + 1;
-        const int s = q[0];
-        const bool keep = s > q[-1] && s > q[1] && s > q[-SS - 1] && s > q[-SS] && s > q[-SS + 1] && s > q[SS - 1] && s > q[SS] && s > q[SS + 1];
-        if (keep) {
-            surv[atomicAdd(&nSurv, 1)] = (uint16_t)p;
-            anyIni |= (s > g.iniTh);
+    uint16_t* surv = list1;  // list1 is dead by now
+    for (int k0 = 0; k0 < nl; k0 += FAST_THREADS) {
+        const int k = k0 + tid;
+        bool keep = false;
+        int off = 0;
+        if (k < nl) {
+            off = list2[k] & 0x7FFF;
+            const uint8_t* q = sc + off;
+            const int s = q[0];
+            keep = s > q[-1] && s > q[1] && s > q[-TS - 1] && s > q[-TS] && s > q[-TS + 1] && s > q[TS - 1] && s > q[TS] && s > q[TS + 1];
+            if (keep) anyIni |= (s > g.iniTh);
+        }
+        const unsigned bal = __ballot_sync(FULL, keep);
+        if (bal) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&nSurv, __popc(bal));
+            base = __shfl_sync(FULL, base, 0);
+            if (keep) surv[base + __popc(bal & ((1u << lane) - 1))] = (uint16_t)off;
         }
     }
     anyIni = __syncthreads_or(anyIni);
@@ -151,11 +223,14 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Geom
     // ---- emit: survivors above the cell's threshold, coordinates relative to (16,16) like the reference (ORBextractor.cc:837-842) ----
     const int th = anyIni ? g.iniTh : g.minTh;
     const int ns = nSurv;
-    for (int k = tid; k < ns; k += 256) {
-        const int p = surv[k];
-        const int y = (int)__umulhi((uint32_t)p, magic), x = p - y * iw;
-        const int s = sc[(y + 1) * SS + x + 1];
-        if (s > th) listBuf[atomicAdd(&nOut, 1)] = pack_cand(x + 3 + j * L.wCell, y + 3 + i * L.hCell, s - 1);
+    uint32_t* outBuf = reinterpret_cast<uint32_t*>(list2);  // list2 is dead after pass C; <= maxPix/4 strict local maxima
+    for (int k = tid; k < ns; k += FAST_THREADS) {
+        const int off = surv[k];
+        const int s = sc[off];
+        if (s > th) {
+            const int r = off / TS, cx = off - r * TS - shift;  // crop coordinates (the reference's cell-local keypoint position)
+            outBuf[atomicAdd(&nOut, 1)] = pack_cand(cx + (iniX - kBorder), r + (iniY - kBorder), s - 1);
+        }
     }
     __syncthreads();
     const int no = nOut;
@@ -171,13 +246,48 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Geom
             return;
         }
         uint32_t* out = b.cand + L.candOff + (size_t)img * L.candCap + base;
-        for (int k = tid; k < no; k += 256) out[k] = listBuf[k];
+        for (int k = tid; k < no; k += FAST_THREADS) out[k] = outBuf[k];
     }
 }
 
-void launch_fast(const Geom& g, const Buffers& b, int nImages, cudaStream_t s) {
+// one descriptor per cell of every level (ORBextractor.cc:779-796), built once per geometry on the host
+void make_cell_table(const Geom& g, uint4* tab, int* tileRows, int* maxPix) {
+    int rows = 0, pix = 0;
+    for (int l = 0; l < g.nlevels; ++l) {
+        const LevelGeom& L = g.lv[l];
+        const int maxBX = L.w - kBorder, maxBY = L.h - kBorder;
+        for (int i = 0; i < L.nRows; ++i)
+            for (int j = 0; j < L.nCols; ++j) {
+                const int iniX = kBorder + j * L.wCell, iniY = kBorder + i * L.hCell;
+                int cw = std::min(iniX + L.wCell + 6, maxBX) - iniX, ch = std::min(iniY + L.hCell + 6, maxBY) - iniY;
+                int kind = 2;
+                if (iniY >= maxBY - 3 || iniX >= maxBX - 6) kind = 0;
+                else if (cw < 7 || ch < 7) kind = 1;
+                uint4 d = make_uint4(0, 0, 0, 0);
+                if (kind != 2) { cw = std::max(cw, 0); ch = std::max(ch, 0); }
+                const int shift = iniX & 3, iw = cw - 6;
+                const int wFirst = (3 + shift) >> 2, nW = kind == 2 ? ((3 + shift + iw - 1) >> 2) - wFirst + 1 : 1;
+                d.x = (uint32_t)iniX | ((uint32_t)iniY << 16);
+                d.y = (uint32_t)(cw & 0xFF) | ((uint32_t)(ch & 0xFF) << 8) | ((uint32_t)l << 16) | ((uint32_t)kind << 24);
+                d.z = (0xFFFFFFFFu / (uint32_t)nW) + 1;  // exact it / nW for it < 2^16
+                d.w = (uint32_t)nW | ((uint32_t)wFirst << 8) | ((uint32_t)shift << 16);
+                tab[L.cellOff + i * L.nCols + j] = d;
+                if (kind == 2) { rows = std::max(rows, ch); pix = std::max(pix, iw * (ch - 6)); }
+            }
+    }
+    *tileRows = (std::max(rows, 7) + 3) & ~3;  // multiple of 4: keeps the score map 16-byte aligned (TSW is odd)
+    *maxPix = (std::max(pix, 8) + 7) & ~7;
+}
+
+size_t fast_smem_bytes(int tileRows, int maxPix) { return (size_t)tileRows * TSW * 4 * 2 + (size_t)maxPix * 2 * 2 + 16; }
+
+cudaError_t fast_configure(int tileRows, int maxPix) {
+    return cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(fast_smem_bytes(tileRows, maxPix), 48 * 1024));
+}
+
+void launch_fast(const Geom& g, const Buffers& b, int nImages, int tileRows, int maxPix, cudaStream_t s) {
     dim3 grid(g.cellsPerImage, nImages);
-    k_fast_cells<<<grid, 256, 0, s>>>(g, b);
+    k_fast_cells<<<grid, FAST_THREADS, fast_smem_bytes(tileRows, maxPix), s>>>(g, b, tileRows, maxPix);
 }
 
 }  // namespace orbx

@@ -88,59 +88,111 @@ void launch_pyramid_level(const Geom& g, const Buffers& b, int level, const Resi
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// 7x7 sigma=2 Gaussian blur, separable 8.8 fixed point with BORDER_REFLECT_101 at the level's own edge
-// (GaussianBlur on a clone, ORBextractor.cc:1105-1106; arithmetic SURVEY.md A.3).
+// Reflect-101 margin of every pyramid plane (3 rows / 3 columns around the interior): what GaussianBlur(...,
+// BORDER_REFLECT_101) reads beyond the edge of its (cloned, hence border-less) input (ORBextractor.cc:1105-1106).  With the
+// margin in place the blur kernel below has no edge cases.  One launch covers all levels of all images.
 // ---------------------------------------------------------------------------------------------------------------
-struct Taps { int k[7]; };
-
 __device__ __forceinline__ int reflect101(int i, int n) {
     if (i < 0) i = -i;
     if (i >= n) i = 2 * (n - 1) - i;
     return min(max(i, 0), n - 1);
 }
 
-constexpr int BT_W = 64, BT_H = 16;
+__global__ void __launch_bounds__(256) k_margin(const __grid_constant__ Geom g, const Buffers b) {
+    const int level = blockIdx.y, img = b.imgBase + blockIdx.z;
+    const LevelGeom& L = g.lv[level];
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    const int rowItems = 6 * (L.w + 6), colItems = 6 * L.h;
+    if (t >= rowItems + colItems) return;
+    int x, y;
+    if (t < rowItems) {
+        const int r = t / (L.w + 6);
+        x = t - r * (L.w + 6) - 3;
+        y = r < 3 ? r - 3 : L.h + (r - 3);
+    } else {
+        const int u = t - rowItems;
+        y = u / 6;
+        const int c = u - y * 6;
+        x = c < 3 ? c - 3 : L.w + (c - 3);
+    }
+    uint8_t* P = b.pyr + L.planeOff + (size_t)img * L.planeBytes;
+    P[(ptrdiff_t)y * L.pitch + x] = P[(size_t)reflect101(y, L.h) * L.pitch + reflect101(x, L.w)];
+}
 
-__global__ void __launch_bounds__(256) k_blur(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int w, int h, int pitch, size_t plane,
-                                              Taps taps) {
-    __shared__ uint8_t sp[BT_H + 6][BT_W + 8];
-    __shared__ uint16_t sh[BT_H + 6][BT_W];
-    const int tx0 = blockIdx.x * BT_W, ty0 = blockIdx.y * BT_H;
-    const uint8_t* S = src + (size_t)blockIdx.z * plane;
-    for (int i = threadIdx.x; i < (BT_H + 6) * (BT_W + 6); i += 256) {
-        const int r = i / (BT_W + 6), c = i - r * (BT_W + 6);
-        const int gx = reflect101(tx0 + c - 3, w), gy = reflect101(ty0 + r - 3, h);
-        sp[r][c] = __ldg(S + (size_t)gy * pitch + gx);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < (BT_H + 6) * BT_W; i += 256) {
-        const int r = i / BT_W, c = i - r * BT_W;
-        uint32_t acc = 0;
+void launch_margin(const Geom& g, const Buffers& b, int nImages, cudaStream_t s) {
+    int maxItems = 0;
+    for (int l = 0; l < g.nlevels; ++l) maxItems = max(maxItems, 6 * (g.lv[l].w + 6) + 6 * g.lv[l].h);
+    dim3 grid((maxItems + 255) / 256, g.nlevels, nImages);
+    k_margin<<<grid, 256, 0, s>>>(g, b);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 7x7 sigma=2 Gaussian blur (GaussianBlur on a clone, ORBextractor.cc:1105-1106; arithmetic SURVEY.md A.3).
+// OpenCV's 8-bit path is a separable 8.8 fixed-point filter whose row pass cannot saturate (taps sum to 256 or 257), so the
+// result is the exact integer 2-D convolution followed by one rounding, (v + 32768) >> 16.  Here: each thread owns a column
+// strip 4 pixels wide and slides down the rows.  Row pass: the 7 taps of a pixel are two 4-byte dot products (IDP.4A) on
+// byte windows cut out of three aligned 32-bit loads with PRMT.  Column pass: a chain of 6 running sums per pixel (7 IMAD
+// per pixel and row), no shared memory, no inter-thread exchange; a warp reads and writes 128 contiguous bytes per row.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int BLUR_SEG = 32;   // output rows per warp (6 extra rows of warm-up each)
+constexpr int BLUR_WARPS = 4;
+
+template <bool SAT>
+__global__ void __launch_bounds__(32 * BLUR_WARPS) k_blur(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int w, int h, int pitch,
+                                                         size_t plane, uint32_t cA, uint32_t cB, int t0, int t1, int t2, int t3, int t4, int t5, int t6) {
+    const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    const int ys = (blockIdx.y * BLUR_WARPS + threadIdx.y) * BLUR_SEG;
+    if (x0 >= w || ys >= h) return;
+    const int ye = min(ys + BLUR_SEG, h);
+    const uint8_t* S = src + (size_t)blockIdx.z * plane + x0;
+    uint8_t* D = dst + (size_t)blockIdx.z * plane + x0;
+    int a[4][6];
 #pragma unroll
-        for (int k = 0; k < 7; ++k) acc += (uint32_t)taps.k[k] * sp[r][c + k];
-        sh[r][c] = (uint16_t)min(acc, 65535u);
-    }
-    __syncthreads();
-    uint8_t* D = dst + (size_t)blockIdx.z * plane;
-    for (int i = threadIdx.x; i < BT_H * BT_W; i += 256) {
-        const int r = i / BT_W, c = i - r * BT_W;
-        const int gx = tx0 + c, gy = ty0 + r;
-        if (gx < w && gy < h) {
-            uint32_t acc = 0;
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int k = 0; k < 7; ++k) acc += (uint32_t)taps.k[k] * sh[r + k][c];
-            D[(size_t)gy * pitch + gx] = (uint8_t)min((acc + 32768u) >> 16, 255u);
+        for (int k = 0; k < 6; ++k) a[i][k] = 0;
+#pragma unroll 2
+    for (int y = ys - 3; y < ye + 3; ++y) {
+        const uint32_t* row = reinterpret_cast<const uint32_t*>(S + (ptrdiff_t)y * pitch);
+        const uint32_t prev = __ldg(row - 1), cur = __ldg(row), next = __ldg(row + 1);
+        uint32_t hrow[4];
+        hrow[0] = __dp4a(__byte_perm(prev, cur, 0x4321), cA, __dp4a(__byte_perm(cur, next, 0x4321), cB, 0u));
+        hrow[1] = __dp4a(__byte_perm(prev, cur, 0x5432), cA, __dp4a(__byte_perm(cur, next, 0x5432), cB, 0u));
+        hrow[2] = __dp4a(__byte_perm(prev, cur, 0x6543), cA, __dp4a(__byte_perm(cur, next, 0x6543), cB, 0u));
+        hrow[3] = __dp4a(cur, cA, __dp4a(next, cB, 0u));
+        uint32_t outw = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int hv = (int)hrow[i];
+            const int o = a[i][0] + t6 * hv;
+            a[i][0] = a[i][1] + t5 * hv;
+            a[i][1] = a[i][2] + t4 * hv;
+            a[i][2] = a[i][3] + t3 * hv;
+            a[i][3] = a[i][4] + t2 * hv;
+            a[i][4] = a[i][5] + t1 * hv;
+            a[i][5] = t0 * hv;
+            uint32_t r = (uint32_t)(o + 32768) >> 16;
+            if (SAT) r = min(r, 255u);
+            outw |= r << (8 * i);
         }
+        if (y >= ys + 3) *reinterpret_cast<uint32_t*>(D + (size_t)(y - 3) * pitch) = outw;
     }
 }
 
 void launch_blur(const Geom& g, const Buffers& b, int level, int nImages, const int taps[7], cudaStream_t s) {
     const LevelGeom& L = g.lv[level];
-    Taps t;
-    for (int i = 0; i < 7; ++i) t.k[i] = taps[i];
-    dim3 grid((L.w + BT_W - 1) / BT_W, (L.h + BT_H - 1) / BT_H, nImages);
+    const uint32_t cA = (uint32_t)taps[0] | ((uint32_t)taps[1] << 8) | ((uint32_t)taps[2] << 16) | ((uint32_t)taps[3] << 24);
+    const uint32_t cB = (uint32_t)taps[4] | ((uint32_t)taps[5] << 8) | ((uint32_t)taps[6] << 16);
+    int sum = 0;
+    for (int i = 0; i < 7; ++i) sum += taps[i];
+    dim3 grid((L.w + 127) / 128, (L.h + BLUR_SEG * BLUR_WARPS - 1) / (BLUR_SEG * BLUR_WARPS), nImages), block(32, BLUR_WARPS);
     const size_t o = (size_t)L.planeOff + (size_t)b.imgBase * L.planeBytes;
-    k_blur<<<grid, 256, 0, s>>>(b.pyr + o, b.blur + o, L.w, L.h, L.pitch, (size_t)L.planeBytes, t);
+    if (sum > 256)
+        k_blur<true><<<grid, block, 0, s>>>(b.pyr + o, b.blur + o, L.w, L.h, L.pitch, (size_t)L.planeBytes, cA, cB, taps[0], taps[1], taps[2], taps[3],
+                                           taps[4], taps[5], taps[6]);
+    else
+        k_blur<false><<<grid, block, 0, s>>>(b.pyr + o, b.blur + o, L.w, L.h, L.pitch, (size_t)L.planeBytes, cA, cB, taps[0], taps[1], taps[2], taps[3],
+                                            taps[4], taps[5], taps[6]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

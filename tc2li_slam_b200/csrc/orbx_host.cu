@@ -110,6 +110,7 @@ struct orbx_batch {
     int launches = 0;
     int lastImages = 0;
     std::vector<int> hostLap;
+    int fastTileRows = 0, fastMaxPix = 0;
 };
 
 namespace {
@@ -136,7 +137,7 @@ int make_geom(const Params& p, int W, int H, int maxImages, Geom& g) {
         L.h = cv_round((float)H * p.isf[l]);
         const int bw = L.w - 2 * kBorder, bh = L.h - 2 * kBorder;  // maxBorder - minBorder
         if (bw < 35 || bh < 35) return fail(ORBX_ERR_TOO_SMALL, "a pyramid level is smaller than one 35-px FAST cell");
-        L.pitch = (int)align_up((size_t)L.w, 128);
+        L.pitch = (int)align_up((size_t)L.w + 2 * kMarginX, 128);
         const float width = (float)bw, height = (float)bh;
         L.nCols = (int)(width / 35.f);
         L.nRows = (int)(height / 35.f);
@@ -156,8 +157,9 @@ int make_geom(const Params& p, int W, int H, int maxImages, Geom& g) {
         L.cellOff = cellOff; cellOff += L.nCols * L.nRows;
         L.sf = p.sf[l];
         L.kpSize = (float)(int)(31 * p.sf[l]);  // PATCH_SIZE*mvScaleFactor[level] truncated (ORBextractor.cc:854)
-        L.planeBytes = (unsigned long long)L.pitch * L.h;
-        L.planeOff = planeOff; planeOff += L.planeBytes * maxImages;
+        L.planeBytes = (unsigned long long)L.pitch * (L.h + 2 * kMarginY);
+        L.planeOff = planeOff + (unsigned long long)kMarginY * L.pitch + kMarginX;  // pixel (0,0) of image 0
+        planeOff += L.planeBytes * maxImages;
         L.candOff = candOff; candOff += (unsigned long long)L.candCap * maxImages;
     }
     g.K = selOff;
@@ -188,7 +190,7 @@ int batch_alloc(orbx_batch* b) {
     const Geom& g = b->g;
     const int n = b->maxImages;
     const LevelGeom& last = g.lv[g.nlevels - 1];
-    b->pyrBytes = (size_t)(last.planeOff + last.planeBytes * n);
+    b->pyrBytes = (size_t)(last.planeOff + last.planeBytes * n);  // (a few bytes more than needed: planeOff includes the margin offset)
     b->candElems = (size_t)(last.candOff + (unsigned long long)last.candCap * n);
     Buffers& B = b->buf;
     int r;
@@ -208,6 +210,15 @@ int batch_alloc(orbx_batch* b) {
     if ((r = dev_alloc(b, &B.outMono, (size_t)n))) return r;
     if ((r = dev_alloc(b, &B.errFlag, 1))) return r;
     B.imgBase = 0;
+    {
+        std::vector<uint4> tab((size_t)g.cellsPerImage);
+        make_cell_table(g, tab.data(), &b->fastTileRows, &b->fastMaxPix);
+        uint4* dtab = nullptr;
+        if ((r = dev_alloc(b, &dtab, tab.size()))) return r;
+        CU(cudaMemcpy(dtab, tab.data(), tab.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+        B.cellTab = dtab;
+        CU(fast_configure(b->fastTileRows, b->fastMaxPix));
+    }
     CU(cudaMemset(B.errFlag, 0, sizeof(int)));
     CU(cudaMemset(B.lapping, 0, (size_t)n * 2 * sizeof(int)));
     CU(cudaMemset(B.pyr, 0, b->pyrBytes));
@@ -311,23 +322,33 @@ int orbx_batch_set_stream(orbx_batch* b, void* s) {
 }
 void* orbx_batch_get_stream(const orbx_batch* b) { return b ? (void*)b->stream : nullptr; }
 
+// n images [height][row_stride] spaced image_stride apart -> level 0 of images [first, first+n): one 3-D strided copy
+static int copy_images_in(orbx_batch* b, const uint8_t* images, size_t row_stride, size_t image_stride, int first, int n, cudaMemcpyKind kind) {
+    const LevelGeom& L0 = b->g.lv[0];
+    uint8_t* dst0 = b->buf.pyr + L0.planeOff + (size_t)first * L0.planeBytes;
+    if (n == 1 || image_stride % row_stride != 0) {
+        for (int i = 0; i < n; ++i)
+            CU(cudaMemcpy2DAsync(dst0 + (size_t)i * L0.planeBytes, L0.pitch, images + (size_t)i * image_stride, row_stride, b->width, b->height, kind,
+                                 b->stream));
+        return ORBX_OK;
+    }
+    cudaMemcpy3DParms p = {};
+    p.srcPtr = make_cudaPitchedPtr((void*)images, row_stride, b->width, image_stride / row_stride);
+    p.dstPtr = make_cudaPitchedPtr((void*)dst0, L0.pitch, b->width, (size_t)b->height + 2 * kMarginY);
+    p.extent = make_cudaExtent(b->width, b->height, n);
+    p.kind = kind;
+    CU(cudaMemcpy3DAsync(&p, b->stream));
+    return ORBX_OK;
+}
+
 int orbx_batch_upload(orbx_batch* b, const uint8_t* host_images, size_t row_stride, size_t image_stride, int first, int n) {
     int r = check_images(b, first, n);
     if (r) return r;
     if (!host_images) return fail(ORBX_ERR_EMPTY, "null image");
     if (row_stride < (size_t)b->width) return fail(ORBX_ERR_ARG, "row stride smaller than the width");
+    if (n == 0) return ORBX_OK;
     DeviceGuard dg(b->device);
-    const LevelGeom& L0 = b->g.lv[0];
-    if (image_stride == row_stride * (size_t)b->height || n == 1) {
-        // the images form one tall 2-D array: a single strided copy (planeBytes == pitch * h)
-        CU(cudaMemcpy2DAsync(b->buf.pyr + L0.planeOff + (size_t)first * L0.planeBytes, L0.pitch, host_images, row_stride, b->width,
-                             (size_t)b->height * n, cudaMemcpyHostToDevice, b->stream));
-    } else {
-        for (int i = 0; i < n; ++i)
-            CU(cudaMemcpy2DAsync(b->buf.pyr + L0.planeOff + (size_t)(first + i) * L0.planeBytes, L0.pitch, host_images + (size_t)i * image_stride,
-                                 row_stride, b->width, b->height, cudaMemcpyHostToDevice, b->stream));
-    }
-    return ORBX_OK;
+    return copy_images_in(b, host_images, row_stride, image_stride, first, n, cudaMemcpyHostToDevice);
 }
 
 int orbx_batch_upload_device(orbx_batch* b, const uint8_t* dev_images, size_t row_stride, size_t image_stride, int first, int n) {
@@ -335,17 +356,9 @@ int orbx_batch_upload_device(orbx_batch* b, const uint8_t* dev_images, size_t ro
     if (r) return r;
     if (!dev_images) return fail(ORBX_ERR_EMPTY, "null image");
     if (row_stride < (size_t)b->width) return fail(ORBX_ERR_ARG, "row stride smaller than the width");
+    if (n == 0) return ORBX_OK;
     DeviceGuard dg(b->device);
-    const LevelGeom& L0 = b->g.lv[0];
-    if (image_stride == row_stride * (size_t)b->height || n == 1) {
-        CU(cudaMemcpy2DAsync(b->buf.pyr + L0.planeOff + (size_t)first * L0.planeBytes, L0.pitch, dev_images, row_stride, b->width,
-                             (size_t)b->height * n, cudaMemcpyDeviceToDevice, b->stream));
-    } else {
-        for (int i = 0; i < n; ++i)
-            CU(cudaMemcpy2DAsync(b->buf.pyr + L0.planeOff + (size_t)(first + i) * L0.planeBytes, L0.pitch, dev_images + (size_t)i * image_stride,
-                                 row_stride, b->width, b->height, cudaMemcpyDeviceToDevice, b->stream));
-    }
-    return ORBX_OK;
+    return copy_images_in(b, dev_images, row_stride, image_stride, first, n, cudaMemcpyDeviceToDevice);
 }
 
 // level-0 images of the handle back to the host (e.g. frames produced by orbx_batch_synth): one strided copy
@@ -355,9 +368,14 @@ int orbx_batch_download_images(orbx_batch* b, int first, int n, uint8_t* host_im
     if (!host_images || row_stride < (size_t)b->width || image_stride != row_stride * (size_t)b->height)
         return fail(ORBX_ERR_ARG, "need a dense [n][height][row_stride] destination");
     DeviceGuard dg(b->device);
+    if (n == 0) return ORBX_OK;
     const LevelGeom& L0 = b->g.lv[0];
-    CU(cudaMemcpy2DAsync(host_images, row_stride, b->buf.pyr + L0.planeOff + (size_t)first * L0.planeBytes, L0.pitch, b->width,
-                         (size_t)b->height * n, cudaMemcpyDeviceToHost, b->stream));
+    cudaMemcpy3DParms p = {};
+    p.srcPtr = make_cudaPitchedPtr((void*)(b->buf.pyr + L0.planeOff + (size_t)first * L0.planeBytes), L0.pitch, b->width, (size_t)b->height + 2 * kMarginY);
+    p.dstPtr = make_cudaPitchedPtr((void*)host_images, row_stride, b->width, b->height);
+    p.extent = make_cudaExtent(b->width, b->height, n);
+    p.kind = cudaMemcpyDeviceToHost;
+    CU(cudaMemcpy3DAsync(&p, b->stream));
     CU(cudaStreamSynchronize(b->stream));
     return ORBX_OK;
 }
@@ -395,8 +413,9 @@ int orbx_batch_run_range(orbx_batch* b, int first, int n, const int* lapping) {
     auto mark = [&]() { if (b->timing) cudaEventRecord(b->ev[evi++], s); };
     mark();
     for (int l = 1; l < g.nlevels; ++l) { launch_pyramid_level(g, buf, l, b->tabs[l], n, s); ++launches; }
+    launch_margin(g, buf, n, s); ++launches;
     mark();
-    launch_fast(g, buf, n, s); ++launches;
+    launch_fast(g, buf, n, b->fastTileRows, b->fastMaxPix, s); ++launches;
     mark();
     for (int l = 0; l < g.nlevels; ++l) { launch_blur(g, buf, l, n, b->taps, s); ++launches; }
     mark();

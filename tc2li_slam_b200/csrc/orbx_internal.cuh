@@ -10,6 +10,8 @@ namespace orbx {
 constexpr int kEdge = 19;      // EDGE_THRESHOLD (ORBextractor.cc:47)
 constexpr int kBorder = 16;    // minBorderX/Y = EDGE_THRESHOLD - 3 (ORBextractor.cc:763)
 constexpr int kHalfPatch = 15; // HALF_PATCH_SIZE (ORBextractor.cc:46)
+constexpr int kMarginX = 4;    // bytes of left margin of every plane row (3 used by the reflect-101 ring, 4 keeps rows word-aligned)
+constexpr int kMarginY = 3;    // rows of margin above and below every plane
 constexpr int kMaxCell = 72;   // wCell/hCell < 70 for any level with >= 1 cell of 35 px (ORBextractor.cc:771-777)
 
 // Per-level geometry, passed by value to every kernel (fits well inside the 4 KB parameter space).
@@ -25,8 +27,8 @@ struct LevelGeom {
     int cellOff;                      // offset inside the per-image cell array
     float sf;                         // mvScaleFactor[level]
     float kpSize;                     // (float)(int)(31 * sf)
-    unsigned long long planeOff;      // byte offset of this level's block (all images) in the pyramid / blur buffers
-    unsigned long long planeBytes;    // pitch * h
+    unsigned long long planeOff;      // byte offset of pixel (0,0) of image 0 of this level in the pyramid / blur buffers
+    unsigned long long planeBytes;    // image-to-image stride: pitch * (h + 2*kMarginY); every plane carries a margin (see k_margin)
     unsigned long long candOff;       // element offset of this level's block in the candidate buffers
 };
 
@@ -85,17 +87,21 @@ struct Buffers {
     int* outCount;          // [image]
     int* outMono;           // [image]
     int* errFlag;           // device-side error flag (capacity overflow etc.)
+    const uint4* cellTab;   // [cellsPerImage] FAST cell descriptors (make_cell_table)
     int imgBase;            // first image of this launch set (kernels index images as imgBase + blockIdx)
 };
 
 // kernel launchers (one translation unit per stage)
 void launch_synth(uint8_t* l0, int w, int h, int pitch, size_t planeBytes, uint32_t seed0, int firstImage, int nImages, int stereo, cudaStream_t s);
 void launch_pyramid_level(const Geom& g, const Buffers& b, int level, const ResizeTab& tab, int nImages, cudaStream_t s);
-void launch_fast(const Geom& g, const Buffers& b, int nImages, cudaStream_t s);
+void launch_fast(const Geom& g, const Buffers& b, int nImages, int tileRows, int maxPix, cudaStream_t s);
+void make_cell_table(const Geom& g, uint4* tab, int* tileRows, int* maxPix);
+cudaError_t fast_configure(int tileRows, int maxPix);
 void launch_blur(const Geom& g, const Buffers& b, int level, int nImages, const int taps[7], cudaStream_t s);
 cudaError_t launch_octree(const Geom& g, const Buffers& b, int nImages, cudaStream_t s);
 void launch_assemble(const Geom& g, const Buffers& b, int nImages, cudaStream_t s);
 void launch_describe(const Geom& g, const Buffers& b, int nImages, cudaStream_t s);
+void launch_margin(const Geom& g, const Buffers& b, int nImages, cudaStream_t s);
 void launch_border(const uint8_t* src, int w, int h, int pitch, uint8_t* dst, int dpitch, cudaStream_t s);
 size_t octree_smem_bytes(int nodeCap);
 cudaError_t upload_describe_constants(const signed char pattern[1024], const int umax[16]);
