@@ -78,13 +78,84 @@ __global__ void __launch_bounds__(256) k_resize(const uint8_t* __restrict__ src,
     *reinterpret_cast<uint32_t*>(dst + (size_t)blockIdx.z * dplane + (size_t)y * dpitch + x0) = out;
 }
 
+// Fast path for scale factors <= 1.25 (4 destination pixels then span at most 9 source bytes = 3 aligned words): each thread
+// owns 4 fixed destination columns and walks down RS_SEG rows.  Column coefficients and PRMT selectors live in registers,
+// a source row is three aligned 32-bit loads, the horizontal interpolation of a pixel is one PRMT + one IDP.2A
+// (coefficients as 16x2 against two source bytes), and the horizontally interpolated upper row is reused as the next
+// destination row's lower row whenever the source row index repeats.
+constexpr int RS_SEG = 16, RS_WARPS = 4;
+
+__global__ void __launch_bounds__(32 * RS_WARPS) k_resize_s12(const uint8_t* __restrict__ src, int sh, int spitch, size_t splane,
+                                                             uint8_t* __restrict__ dst, int dw, int dh, int dpitch, size_t dplane, ResizeTab t) {
+    const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    const int ys = (blockIdx.y * RS_WARPS + threadIdx.y) * RS_SEG;
+    if (x0 >= dw || ys >= dh) return;
+    const int ye = min(ys + RS_SEG, dh);
+    uint32_t coef[4], sel[4];
+    int base = 0;
+    bool hi3 = false;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int x = min(x0 + i, dw - 1);
+        const int sx = t.xofs[x];
+        coef[i] = *reinterpret_cast<const uint32_t*>(t.xa + 2 * x);  // (1-fx)*2048 | fx*2048 << 16
+        if (i == 0) base = sx & ~3;
+        int bi = sx - base;          // 0..7; byte bi + 1 may be byte 8 (third word) for the last pixel only
+        if (i == 3 && bi >= 7) { hi3 = true; bi -= 4; }
+        sel[i] = (uint32_t)bi | ((uint32_t)(bi + 1) << 4);
+    }
+    const uint8_t* S = src + (size_t)blockIdx.z * splane + base;
+    uint8_t* D = dst + (size_t)blockIdx.z * dplane + x0;
+    int cachedRow = -1;
+    uint32_t hc[4] = {0, 0, 0, 0};
+    auto hrow = [&](int sy, uint32_t h[4]) {
+        const uint32_t* row = reinterpret_cast<const uint32_t*>(S + (size_t)sy * spitch);
+        const uint32_t w0 = __ldg(row), w1 = __ldg(row + 1), w2 = __ldg(row + 2);
+        h[0] = __dp2a_lo(coef[0], __byte_perm(w0, w1, sel[0]), 0u) >> 4;
+        h[1] = __dp2a_lo(coef[1], __byte_perm(w0, w1, sel[1]), 0u) >> 4;
+        h[2] = __dp2a_lo(coef[2], __byte_perm(w0, w1, sel[2]), 0u) >> 4;
+        h[3] = __dp2a_lo(coef[3], __byte_perm(hi3 ? w1 : w0, hi3 ? w2 : w1, sel[3]), 0u) >> 4;
+    };
+    for (int y = ys; y < ye; ++y) {
+        const int yo = t.yofs[y];
+        const int sy0 = min(max(yo, 0), sh - 1), sy1 = min(max(yo + 1, 0), sh - 1);
+        const uint32_t bw = *reinterpret_cast<const uint32_t*>(t.yb + 2 * y);
+        const uint32_t b0 = bw & 0xFFFFu, b1 = bw >> 16;
+        uint32_t h0[4], h1[4];
+        if (sy0 == cachedRow) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) h0[i] = hc[i];
+        } else
+            hrow(sy0, h0);
+        if (sy1 == sy0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) h1[i] = h0[i];
+        } else
+            hrow(sy1, h1);
+        uint32_t out = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            hc[i] = h1[i];
+            const uint32_t v = (((b0 * h0[i]) >> 16) + ((b1 * h1[i]) >> 16) + 2) >> 2;  // <= 255 by construction
+            out |= v << (8 * i);
+        }
+        cachedRow = sy1;
+        *reinterpret_cast<uint32_t*>(D + (size_t)y * dpitch) = out;
+    }
+}
+
 void launch_pyramid_level(const Geom& g, const Buffers& b, int level, const ResizeTab& tab, int nImages, cudaStream_t s) {
     const LevelGeom& S = g.lv[level - 1];
     const LevelGeom& D = g.lv[level];
-    dim3 grid((D.w + 127) / 128, (D.h + 7) / 8, nImages), block(32, 8);
-    k_resize<<<grid, block, 0, s>>>(b.pyr + S.planeOff + (size_t)b.imgBase * S.planeBytes, S.w, S.h, S.pitch, (size_t)S.planeBytes,
-                                   b.pyr + D.planeOff + (size_t)b.imgBase * D.planeBytes, D.w, D.h, D.pitch,
-                                   (size_t)D.planeBytes, tab);
+    const uint8_t* sp = b.pyr + S.planeOff + (size_t)b.imgBase * S.planeBytes;
+    uint8_t* dp = b.pyr + D.planeOff + (size_t)b.imgBase * D.planeBytes;
+    if ((double)S.w <= 1.25 * D.w && (double)S.h <= 1.25 * D.h + 1 && S.w >= 16) {
+        dim3 grid((D.w + 127) / 128, (D.h + RS_SEG * RS_WARPS - 1) / (RS_SEG * RS_WARPS), nImages), block(32, RS_WARPS);
+        k_resize_s12<<<grid, block, 0, s>>>(sp, S.h, S.pitch, (size_t)S.planeBytes, dp, D.w, D.h, D.pitch, (size_t)D.planeBytes, tab);
+    } else {
+        dim3 grid((D.w + 127) / 128, (D.h + 7) / 8, nImages), block(32, 8);
+        k_resize<<<grid, block, 0, s>>>(sp, S.w, S.h, S.pitch, (size_t)S.planeBytes, dp, D.w, D.h, D.pitch, (size_t)D.planeBytes, tab);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
