@@ -87,9 +87,12 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
     {
         const uint8_t* lev = b.pyr + L.planeOff + (size_t)img * L.planeBytes + (size_t)iniY * L.pitch + (iniX - shift);
         const int nWords = (shift + cw + 3) >> 2;
-        const int rpi = FAST_THREADS / 32;
-        for (int r = tid >> 5; r < ch; r += rpi)
-            if (lane < nWords) tileW[r * TSW + 1 + lane] = __ldg(reinterpret_cast<const uint32_t*>(lev + (size_t)r * L.pitch) + lane);
+        const uint32_t magicL = (0xFFFFFFFFu / (uint32_t)nWords) + 1;
+        const int nItems = ch * nWords;
+        for (int e = tid; e < nItems; e += FAST_THREADS) {
+            const int r = (int)__umulhi((uint32_t)e, magicL), c = e - r * nWords;
+            tileW[r * TSW + 1 + c] = __ldg(reinterpret_cast<const uint32_t*>(lev + (size_t)r * L.pitch) + c);
+        }
         uint4* z = reinterpret_cast<uint4*>(scW);
         const int nz = (ch * TSW + 3) >> 2;
         for (int k = tid; k < nz; k += FAST_THREADS) z[k] = make_uint4(0, 0, 0, 0);
@@ -97,18 +100,21 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
     }
     __syncthreads();
 
-    // ---- pass A: compass test, 4 pixels per thread ----
-    const int t = g.minTh;
-    {
-        const uint32_t kAdd = (uint32_t)(0x7f - (t & 0x7f)) * 0x01010101u;
-        const bool tHigh = t >= 128;
-        const int items = ih * nW;
-        const int xb0 = 4 * wFirst - 3 - shift;  // interior x of byte 0 of the first word (<= 0)
-        for (int it0 = 0; it0 < items; it0 += FAST_THREADS) {
-            const int it = it0 + tid;
-            uint32_t F = 0;
-            int off = 0;
-            if (it < items) {
+    // Threshold attempts (ORBextractor.cc:800-820): iniThFAST first; pixels that are not corners at iniThFAST cannot suppress
+    // one that is, so the first attempt is exactly cv::FAST(cell, iniThFAST, true).  Only a cell without any survivor is
+    // redone at minThFAST (a few per cent of the cells); scores written by the first attempt stay valid for the second.
+    uint16_t* surv = list1;
+    int attempt = 0;
+    for (;; ++attempt) {
+        const int t = attempt == 0 ? g.iniTh : g.minTh;
+
+        // ---- pass A: compass test, 4 pixels per thread ----
+        {
+            const uint32_t kAdd = (uint32_t)(0x7f - (t & 0x7f)) * 0x01010101u;
+            const bool tHigh = t >= 128;
+            const int items = ih * nW;
+            const int xb0 = 4 * wFirst - 3 - shift;  // interior x of byte 0 of the first word (<= 0)
+            for (int it = tid; it < items; it += FAST_THREADS) {
                 const int y = (int)__umulhi((uint32_t)it, magicW), cc = it - y * nW;
                 const uint32_t* row = tileW + (y + 3) * TSW + 1 + wFirst + cc;
                 const uint32_t cur = row[0], prev = row[-1], next = row[1], up = row[3 * TSW], dn = row[-3 * TSW];
@@ -116,122 +122,116 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
                 const uint32_t w = __funnelshift_r(prev, cur, 8);   // pixels at x - 3
                 const uint32_t ns = bytes_gt(__vabsdiffu4(up, cur), kAdd, tHigh) | bytes_gt(__vabsdiffu4(dn, cur), kAdd, tHigh);
                 const uint32_t ew = bytes_gt(__vabsdiffu4(e, cur), kAdd, tHigh) | bytes_gt(__vabsdiffu4(w, cur), kAdd, tHigh);
-                // bytes outside the interior [0, iw) are dropped
-                const int xb = xb0 + 4 * cc;
-                const int nL = max(-xb, 0), nR = max(xb + 4 - iw, 0);
-                const uint32_t valid = (0xFFFFFFFFu << (8 * nL)) & (0xFFFFFFFFu >> (8 * nR));
-                F = ns & ew & 0x80808080u & valid;
-                off = (y + 3) * TS + 4 * (wFirst + cc);  // tile byte offset of byte 0 of this word
+                uint32_t F = ns & ew & 0x80808080u;
+                if (F) {
+                    // bytes outside the interior [0, iw) are dropped
+                    const int xb = xb0 + 4 * cc;
+                    const int nL = max(-xb, 0), nR = max(xb + 4 - iw, 0);
+                    F &= (0xFFFFFFFFu << (8 * nL)) & (0xFFFFFFFFu >> (8 * nR));
+                    if (F) {
+                        const int off = (y + 3) * TS + 4 * (wFirst + cc);  // tile byte offset of byte 0 of this word
+                        int pos = atomicAdd(&n1, __popc(F));
+                        if (F & 0x80u) list1[pos++] = (uint16_t)off;
+                        if (F & 0x8000u) list1[pos++] = (uint16_t)(off + 1);
+                        if (F & 0x800000u) list1[pos++] = (uint16_t)(off + 2);
+                        if (F & 0x80000000u) list1[pos] = (uint16_t)(off + 3);
+                    }
+                }
             }
-            // append the flagged pixels: one shared atomic per warp
-            const unsigned b0 = __ballot_sync(FULL, F & 0x80u), b1 = __ballot_sync(FULL, F & 0x8000u), b2 = __ballot_sync(FULL, F & 0x800000u),
-                           b3 = __ballot_sync(FULL, F & 0x80000000u);
-            const int c0 = __popc(b0), c1 = c0 + __popc(b1), c2 = c1 + __popc(b2), tot = c2 + __popc(b3);
-            if (tot) {
+        }
+        __syncthreads();
+
+        // ---- pass A2: exact ring masks + contiguity, dense over list1 ----
+        const int nl1 = n1;
+        for (int k0 = 0; k0 < nl1; k0 += FAST_THREADS) {
+            const int k = k0 + tid;
+            int off = 0;
+            uint32_t arcs = 0;
+            if (k < nl1) {
+                off = list1[k];
+                const uint8_t* c = tile + off;
+                const uint32_t v = c[0];
+                // 16x2 lanes: low = (v + t + 1) - (r + 1) = hi - r, high = r - lo; (r + 1) * 0xFFFF = (r << 16) | (-(r + 1) & 0xFFFF)
+                const uint32_t K = (v + t + 1) | (((uint32_t)(t - (int)v) & 0xFFFFu) << 16);
+                uint32_t m = 0;
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const uint32_t r = c[RING(q)];
+                    const uint32_t sdiff = __vadd2(K, r * 0xFFFFu + 0xFFFFu);
+                    m |= ((sdiff >> (15 - q)) & (0x00010001u << q));  // bit q: r > hi, bit 16 + q: r < lo
+                }
+                arcs = arc9_halves(m);
+            }
+            const unsigned bal = __ballot_sync(FULL, arcs != 0);
+            if (bal) {
                 int base = 0;
-                if (lane == 0) base = atomicAdd(&n1, tot);
+                if (lane == 0) base = atomicAdd(&n2, __popc(bal));
                 base = __shfl_sync(FULL, base, 0);
-                const unsigned lt = (1u << lane) - 1;
-                if (F & 0x80u) list1[base + __popc(b0 & lt)] = (uint16_t)off;
-                if (F & 0x8000u) list1[base + c0 + __popc(b1 & lt)] = (uint16_t)(off + 1);
-                if (F & 0x800000u) list1[base + c1 + __popc(b2 & lt)] = (uint16_t)(off + 2);
-                if (F & 0x80000000u) list1[base + c2 + __popc(b3 & lt)] = (uint16_t)(off + 3);
+                if (arcs) list2[base + __popc(bal & ((1u << lane) - 1))] = (uint16_t)(off | ((arcs >> 16) ? 0x8000 : 0));
             }
         }
-    }
-    __syncthreads();
+        __syncthreads();
 
-    // ---- pass A2: exact ring masks + contiguity, dense over list1 ----
-    const int nl1 = n1;
-    for (int k0 = 0; k0 < nl1; k0 += FAST_THREADS) {
-        const int k = k0 + tid;
-        int off = 0;
-        uint32_t arcs = 0;
-        if (k < nl1) {
-            off = list1[k];
+        // ---- pass B: arc score of the corners ----
+        const int nl = n2;
+        for (int k = tid; k < nl; k += FAST_THREADS) {
+            const int e = list2[k], off = e & 0x7FFF;
             const uint8_t* c = tile + off;
-            const uint32_t v = c[0];
-            // 16x2 lanes: low = (v + t + 1) - (r + 1) = hi - r, high = r - lo; (r + 1) * 0xFFFF = (r << 16) | (-(r + 1) & 0xFFFF)
-            const uint32_t K = (v + t + 1) | (((uint32_t)(t - (int)v) & 0xFFFFu) << 16);
-            uint32_t m = 0;
+            const int v = c[0];
+            const int sgn = (e & 0x8000) ? -1 : 1;
+            int d[16];
 #pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                const uint32_t r = c[RING(q)];
-                const uint32_t sdiff = __vadd2(K, r * 0xFFFFu + 0xFFFFu);
-                m |= ((sdiff >> (15 - q)) & (0x00010001u << q));  // bit q: r > hi, bit 16 + q: r < lo
+            for (int q = 0; q < 16; ++q) d[q] = sgn * ((int)c[RING(q)] - v);
+            int m2[16], m4[16], m8[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) m2[q] = min(d[q], d[(q + 1) & 15]);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) m4[q] = min(m2[q], m2[(q + 2) & 15]);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) m8[q] = min(m4[q], m4[(q + 4) & 15]);
+            int s = 0;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) s = max(s, min(m8[q], d[(q + 8) & 15]));
+            sc[off] = (uint8_t)s;  // t < s <= 255
+        }
+        __syncthreads();
+
+        // ---- pass C: cell-local 3x3 non-maximum suppression.  Only interior pixels ever get a score, so the rim reads 0. ----
+        for (int k0 = 0; k0 < nl; k0 += FAST_THREADS) {
+            const int k = k0 + tid;
+            bool keep = false;
+            int off = 0;
+            if (k < nl) {
+                off = list2[k] & 0x7FFF;
+                const uint8_t* q = sc + off;
+                const int s = q[0];
+                keep = s > q[-1] && s > q[1] && s > q[-TS - 1] && s > q[-TS] && s > q[-TS + 1] && s > q[TS - 1] && s > q[TS] && s > q[TS + 1];
             }
-            arcs = arc9_halves(m);
+            const unsigned bal = __ballot_sync(FULL, keep);
+            if (bal) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&nSurv, __popc(bal));
+                base = __shfl_sync(FULL, base, 0);
+                if (keep) surv[base + __popc(bal & ((1u << lane) - 1))] = (uint16_t)off;
+            }
         }
-        const unsigned bal = __ballot_sync(FULL, arcs != 0);
-        if (bal) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&n2, __popc(bal));
-            base = __shfl_sync(FULL, base, 0);
-            if (arcs) list2[base + __popc(bal & ((1u << lane) - 1))] = (uint16_t)(off | ((arcs >> 16) ? 0x8000 : 0));
-        }
+        __syncthreads();
+        if (nSurv > 0 || attempt == 1 || g.iniTh == g.minTh) break;
+        __syncthreads();  // everyone has read nSurv == 0
+        if (tid == 0) { n1 = 0; n2 = 0; }
+        __syncthreads();
     }
-    __syncthreads();
+    const int anyIni = attempt == 0 && nSurv > 0;
 
-    // ---- pass B: arc score of the corners ----
-    const int nl = n2;
-    for (int k = tid; k < nl; k += FAST_THREADS) {
-        const int e = list2[k], off = e & 0x7FFF;
-        const uint8_t* c = tile + off;
-        const int v = c[0];
-        const int sgn = (e & 0x8000) ? -1 : 1;
-        int d[16];
-#pragma unroll
-        for (int q = 0; q < 16; ++q) d[q] = sgn * ((int)c[RING(q)] - v);
-        int m2[16], m4[16], m8[16];
-#pragma unroll
-        for (int q = 0; q < 16; ++q) m2[q] = min(d[q], d[(q + 1) & 15]);
-#pragma unroll
-        for (int q = 0; q < 16; ++q) m4[q] = min(m2[q], m2[(q + 2) & 15]);
-#pragma unroll
-        for (int q = 0; q < 16; ++q) m8[q] = min(m4[q], m4[(q + 4) & 15]);
-        int s = 0;
-#pragma unroll
-        for (int q = 0; q < 16; ++q) s = max(s, min(m8[q], d[(q + 8) & 15]));
-        sc[off] = (uint8_t)s;  // minTh < s <= 255
-    }
-    __syncthreads();
-
-    // ---- pass C: cell-local 3x3 non-maximum suppression.  Only interior pixels ever get a score, so the rim reads 0. ----
-    int anyIni = 0;
-    uint16_t* surv = list1;  // list1 is dead by now
-    for (int k0 = 0; k0 < nl; k0 += FAST_THREADS) {
-        const int k = k0 + tid;
-        bool keep = false;
-        int off = 0;
-        if (k < nl) {
-            off = list2[k] & 0x7FFF;
-            const uint8_t* q = sc + off;
-            const int s = q[0];
-            keep = s > q[-1] && s > q[1] && s > q[-TS - 1] && s > q[-TS] && s > q[-TS + 1] && s > q[TS - 1] && s > q[TS] && s > q[TS + 1];
-            if (keep) anyIni |= (s > g.iniTh);
-        }
-        const unsigned bal = __ballot_sync(FULL, keep);
-        if (bal) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&nSurv, __popc(bal));
-            base = __shfl_sync(FULL, base, 0);
-            if (keep) surv[base + __popc(bal & ((1u << lane) - 1))] = (uint16_t)off;
-        }
-    }
-    anyIni = __syncthreads_or(anyIni);
-
-    // ---- emit: survivors above the cell's threshold, coordinates relative to (16,16) like the reference (ORBextractor.cc:837-842) ----
-    const int th = anyIni ? g.iniTh : g.minTh;
+    // ---- emit the survivors, coordinates relative to (16,16) like the reference (ORBextractor.cc:837-842) ----
     const int ns = nSurv;
     uint32_t* outBuf = reinterpret_cast<uint32_t*>(list2);  // list2 is dead after pass C; <= maxPix/4 strict local maxima
     for (int k = tid; k < ns; k += FAST_THREADS) {
         const int off = surv[k];
-        const int s = sc[off];
-        if (s > th) {
-            const int r = off / TS, cx = off - r * TS - shift;  // crop coordinates (the reference's cell-local keypoint position)
-            outBuf[atomicAdd(&nOut, 1)] = pack_cand(cx + (iniX - kBorder), r + (iniY - kBorder), s - 1);
-        }
+        const int r = off / TS, cx = off - r * TS - shift;  // crop coordinates (the reference's cell-local keypoint position)
+        outBuf[k] = pack_cand(cx + (iniX - kBorder), r + (iniY - kBorder), (int)sc[off] - 1);
     }
+    if (tid == 0) nOut = ns;
     __syncthreads();
     const int no = nOut;
     if (tid == 0) {
