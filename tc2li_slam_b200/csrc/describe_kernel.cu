@@ -88,102 +88,136 @@ __global__ void __launch_bounds__(256) k_assemble(const __grid_constant__ Geom g
 void launch_assemble(const Geom& g, const Buffers& b, int nImages, cudaStream_t s) { k_assemble<<<nImages, 256, 0, s>>>(g, b); }
 
 // ---------------------------------------------------------------------------------------------------------------
-// One warp per keypoint.  Both patches are first staged in shared memory with aligned 32-bit loads that are all in flight
-// together (9 + 13 loads per lane instead of 31 + 16 dependent byte gathers): the 31x31 patch of the unblurred level for the
-// moments, the 37x37 patch of the blurred level for the 512 rotated samples (|offset| <= 18: pattern radius 18.38).
-constexpr int DW = 8;                      // warps (keypoints) per CTA
-constexpr int PA_W = 9, PA_ROWS = 31;      // IC_Angle patch: 31 rows x 9 words
-constexpr int PB_W = 11, PB_ROWS = 37;     // descriptor patch: 37 rows x 11 words
+// k_describe: each warp walks a run of consecutive keypoints.  Per keypoint ONE lane issues two TMA box loads — the 31x31
+// patch of the unblurred level (48-byte box rows) for the moments and the 37x37 window of the blurred level (64-byte box rows) for
+// the 512 rotated samples (|offset| <= 18: pattern radius 18.38) — into the warp's own double-buffered shared memory, and
+// the next keypoint's boxes are in flight while the current one is processed (mbarrier per stage).
+//   IC_Angle: lane v+15 owns patch row v: 9 words of the box row are funnel-shifted into 8 patch-aligned words and
+//   sum u*I / sum I are 2 x 8 IDP.4A with per-lane constant weight words (circular mask folded into the weights).
+//   rBRIEF: lane i builds descriptor byte i; pattern as float4 {x0,y0,x1,y1} in shared memory.
+constexpr int DW = 8;            // warps per CTA
+constexpr int KPW = 8;           // consecutive keypoints per warp
+// TMA box origins must be 16-byte aligned in global memory: the boxes start at the aligned byte at or before the patch's
+// first column and are 15 bytes wider than the patch.
+constexpr int PA_ROW = 48, PB_ROW = 64;
+constexpr int PA_BYTES = PA_ROW * 31, PB_BYTES = PB_ROW * 37;
+constexpr int ST_A = 1536, ST_B = 2432, ST_BYTES = ST_A + ST_B;  // per stage, 128-byte aligned pieces
 
-__global__ void __launch_bounds__(32 * DW) k_describe(const __grid_constant__ Geom g, const Buffers b) {
-    __shared__ signed char pat[1024];
-    __shared__ uint32_t patchA[DW][PA_ROWS * PA_W];
-    __shared__ uint32_t patchB[DW][PB_ROWS * PB_W];
-    const int img = b.imgBase + blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    reinterpret_cast<int*>(pat)[tid] = reinterpret_cast<const int*>(c_pattern)[tid];
-    __syncthreads();
-    const int n = b.outCount[img];
-    const int k = blockIdx.x * DW + wid;
-    if (k >= n) return;
-    const KpWork wk = b.work[(size_t)img * g.K + k];
-    const LevelGeom& L = g.lv[wk.level];
-    const size_t plane = L.planeOff + (size_t)img * L.planeBytes;
-
-    // ---- stage both patches ----
-    const int xa = (wk.x - kHalfPatch) & ~3, sa = (wk.x - kHalfPatch) - xa;
-    const int xb = (wk.x - 18) & ~3, sb = (wk.x - 18) - xb;
-    {
-        const uint8_t* A = b.pyr + plane + (size_t)(wk.y - kHalfPatch) * L.pitch + xa;
-        const uint8_t* B = b.blur + plane + (size_t)(wk.y - 18) * L.pitch + xb;
-        uint32_t va[9], vb[13];
-#pragma unroll
-        for (int i = 0; i < 9; ++i) {
-            const int e = lane + 32 * i, r = e / PA_W, c = e - r * PA_W;
-            va[i] = e < PA_ROWS * PA_W ? __ldg(reinterpret_cast<const uint32_t*>(A + (size_t)r * L.pitch) + c) : 0u;
-        }
-#pragma unroll
-        for (int i = 0; i < 13; ++i) {
-            const int e = lane + 32 * i, r = e / PB_W, c = e - r * PB_W;
-            vb[i] = e < PB_ROWS * PB_W ? __ldg(reinterpret_cast<const uint32_t*>(B + (size_t)r * L.pitch) + c) : 0u;
-        }
-#pragma unroll
-        for (int i = 0; i < 9; ++i)
-            if (lane + 32 * i < PA_ROWS * PA_W) patchA[wid][lane + 32 * i] = va[i];
-#pragma unroll
-        for (int i = 0; i < 13; ++i)
-            if (lane + 32 * i < PB_ROWS * PB_W) patchB[wid][lane + 32 * i] = vb[i];
-    }
-    __syncwarp();
-
-    // ---- IC_Angle: lane u-15 owns patch column u ----
-    const int u = lane - kHalfPatch;
-    const int au = u < 0 ? -u : u;
-    int m10 = 0, m01 = 0;
-    if (lane < 31) {
-        const uint8_t* pa = reinterpret_cast<const uint8_t*>(patchA[wid]) + sa + lane;
-        int colsum = 0;
-#pragma unroll
-        for (int v = -kHalfPatch; v <= kHalfPatch; ++v) {
-            const int av = v < 0 ? -v : v;
-            if (au <= c_umax[av]) {
-                const int I = pa[(v + kHalfPatch) * (PA_W * 4)];
-                colsum += I;
-                m01 += v * I;
-            }
-        }
-        m10 = u * colsum;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        m10 += __shfl_xor_sync(0xFFFFFFFFu, m10, o);
-        m01 += __shfl_xor_sync(0xFFFFFFFFu, m01, o);
-    }
-    const float angle = fast_atan2_deg((float)m01, (float)m10);
-
-    // ---- steered BRIEF ----
-    const float factorPI = (float)(3.14159265358979323846 / 180.0);  // == (float)(CV_PI/180.f): the divisor is promoted to double
-    float sn, cs;
-    sinf_cosf_glibc(__fmul_rn(angle, factorPI), &sn, &cs);
-    const uint8_t* cb = reinterpret_cast<const uint8_t*>(patchB[wid]) + 18 * (PB_W * 4) + 18 + sb;  // the keypoint inside the staged patch
-    const signed char* p = pat + lane * 32;
-    int val = 0;
-#pragma unroll
-    for (int bit = 0; bit < 8; ++bit) {
-        const float x0 = (float)p[4 * bit], y0 = (float)p[4 * bit + 1], x1 = (float)p[4 * bit + 2], y1 = (float)p[4 * bit + 3];
-        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, sn), __fmul_rn(y0, cs)));
-        const int q0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, cs), __fmul_rn(y0, sn)));
-        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, sn), __fmul_rn(y1, cs)));
-        const int q1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, cs), __fmul_rn(y1, sn)));
-        const int t0 = cb[r0 * (PB_W * 4) + q0], t1 = cb[r1 * (PB_W * 4) + q1];
-        val |= (t0 < t1) << bit;
-    }
-    b.desc[((size_t)img * g.K + wk.dst) * 32 + lane] = (uint8_t)val;
-    if (lane == 0) b.kps[(size_t)img * g.K + wk.dst].angle = angle;
+__device__ __forceinline__ int dp4a_us(uint32_t pix, uint32_t wgt, int acc) {  // unsigned pixels x signed weights
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(pix), "r"(wgt), "r"(acc));
+    return d;
 }
 
-void launch_describe(const Geom& g, const Buffers& b, int nImages, cudaStream_t s) {
-    dim3 grid((g.K + DW - 1) / DW, nImages);
-    k_describe<<<grid, 32 * DW, 0, s>>>(g, b);
+__global__ void __launch_bounds__(32 * DW) k_describe(const __grid_constant__ Geom g, const Buffers b, const __grid_constant__ DescMaps maps) {
+    extern __shared__ __align__(128) unsigned char dsm[];
+    __shared__ __align__(16) float4 pat4[256];
+    __shared__ __align__(8) uint64_t bars[DW][2];
+    const int img = b.imgBase + blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    {
+        const signed char* q = c_pattern + 4 * tid;
+        pat4[tid] = make_float4((float)q[0], (float)q[1], (float)q[2], (float)q[3]);
+    }
+    if (lane == 0) { mbar_init(&bars[wid][0], 1); mbar_init(&bars[wid][1], 1); }
+    mbar_fence_init();
+    __syncthreads();
+    const int n = b.outCount[img];
+    const int k0 = (blockIdx.x * DW + wid) * KPW;
+    const int cnt = min(KPW, n - k0);
+    if (cnt <= 0) return;
+    unsigned char* stage = dsm + (size_t)wid * 2 * ST_BYTES;
+    const KpWork* work = b.work + (size_t)img * g.K + k0;
+
+    // per-lane weights of patch row v = lane - 15: bytes u = 4c + j - 15, kept iff |u| <= umax[|v|] (ORBextractor.cc:57-74)
+    uint32_t wu[8], w1[8];
+    {
+        const int v = lane - kHalfPatch, av = v < 0 ? -v : v;
+        const int lim = lane < 31 ? c_umax[av] : -1;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            uint32_t a = 0, o = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int u = 4 * c + j - kHalfPatch;
+                const bool in = (u < 0 ? -u : u) <= lim && u <= kHalfPatch;
+                a |= (in ? (uint32_t)(u & 0xFF) : 0u) << (8 * j);
+                o |= (in ? 1u : 0u) << (8 * j);
+            }
+            wu[c] = a; w1[c] = o;
+        }
+    }
+    const int vrow = lane - kHalfPatch;
+
+    auto issue = [&](int i) {  // lane 0: both boxes of keypoint i into stage i & 1
+        const KpWork wk = work[i];
+        unsigned char* st = stage + (i & 1) * ST_BYTES;
+        uint64_t* bar = &bars[wid][i & 1];
+        mbar_arrive_expect_tx(bar, PA_BYTES + PB_BYTES);
+        tma_load_3d(st, &maps.ic[wk.level], bar, (kMarginX + wk.x - kHalfPatch) & ~15, kMarginY + wk.y - kHalfPatch, img);
+        tma_load_3d(st + ST_A, &maps.bl[wk.level], bar, (kMarginX + wk.x - 18) & ~15, kMarginY + wk.y - 18, img);
+    };
+    if (lane == 0) issue(0);
+    for (int i = 0; i < cnt; ++i) {
+        if (lane == 0 && i + 1 < cnt) issue(i + 1);
+        const KpWork wk = work[i];
+        const unsigned char* st = stage + (i & 1) * ST_BYTES;
+        mbar_wait(&bars[wid][i & 1], (i >> 1) & 1);
+
+        // ---- IC_Angle ----
+        int m10 = 0, m01 = 0;
+        {
+            const int sa = (kMarginX + wk.x - kHalfPatch) & 15;  // patch column -15 sits at byte sa of the box row
+            const uint32_t* rowp = reinterpret_cast<const uint32_t*>(st + (lane < 31 ? lane : 0) * PA_ROW) + (sa >> 2);
+            const int bs = (sa & 3) * 8;
+            uint32_t raw[9], wds[8];
+#pragma unroll
+            for (int c = 0; c < 9; ++c) raw[c] = rowp[c];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) wds[c] = __funnelshift_r(raw[c], raw[c + 1], bs);
+            int s1 = 0;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                m10 = dp4a_us(wds[c], wu[c], m10);
+                s1 = (int)__dp4a(wds[c], w1[c], (uint32_t)s1);
+            }
+            m01 = vrow * s1;  // lane 31 has all-zero weights
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            m10 += __shfl_xor_sync(0xFFFFFFFFu, m10, o);
+            m01 += __shfl_xor_sync(0xFFFFFFFFu, m01, o);
+        }
+        const float angle = fast_atan2_deg((float)m01, (float)m10);
+
+        // ---- steered BRIEF ----
+        const float factorPI = (float)(3.14159265358979323846 / 180.0);  // == (float)(CV_PI/180.f): the divisor is promoted to double
+        float sn, cs;
+        sinf_cosf_glibc(__fmul_rn(angle, factorPI), &sn, &cs);
+        const unsigned char* cb = st + ST_A + 18 * PB_ROW + 18 + ((kMarginX + wk.x - 18) & 15);  // the keypoint inside the staged window
+        int val = 0;
+#pragma unroll
+        for (int bit = 0; bit < 8; ++bit) {
+            const float4 q = pat4[lane * 8 + bit];
+            const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(q.x, sn), __fmul_rn(q.y, cs)));
+            const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(q.x, cs), __fmul_rn(q.y, sn)));
+            const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(q.z, sn), __fmul_rn(q.w, cs)));
+            const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(q.z, cs), __fmul_rn(q.w, sn)));
+            const int t0 = cb[r0 * PB_ROW + c0], t1 = cb[r1 * PB_ROW + c1];
+            val |= (t0 < t1) << bit;
+        }
+        b.desc[((size_t)img * g.K + wk.dst) * 32 + lane] = (uint8_t)val;
+        if (lane == 0) b.kps[(size_t)img * g.K + wk.dst].angle = angle;
+        __syncwarp();  // every lane is done with this stage before lane 0 re-arms it (two iterations later)
+    }
+}
+
+cudaError_t describe_configure() {
+    return cudaFuncSetAttribute(k_describe, cudaFuncAttributeMaxDynamicSharedMemorySize, DW * 2 * ST_BYTES);
+}
+
+void launch_describe(const Geom& g, const Buffers& b, const DescMaps& maps, int nImages, cudaStream_t s) {
+    dim3 grid((g.K + DW * KPW - 1) / (DW * KPW), nImages);
+    k_describe<<<grid, 32 * DW, DW * 2 * ST_BYTES, s>>>(g, b, maps);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -15,6 +15,7 @@
 
 #include "orbx_internal.cuh"
 #include "stdsort_emul.cuh"
+#include "tma.cuh"
 
 namespace orbx {
 void launch_debug_sort_impl(unsigned long long* buf, int n, int forceDepth, cudaStream_t s);
@@ -22,6 +23,29 @@ cudaError_t octree_configure(int maxNodeCap);
 }
 
 using namespace orbx;
+
+namespace orbx {
+// cuTensorMapEncodeTiled through the runtime's driver entry point (liborbx links cudart statically and not libcuda)
+int tma_encode_3d(CUtensorMap* out, void* base, uint64_t pitch, uint64_t rows, uint64_t images, uint64_t imageStride, uint32_t boxBytes,
+                  uint32_t boxRows) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) return -1;
+        fn = (EncodeFn)p;
+    }
+    const cuuint64_t gdim[3] = {pitch, rows, images};
+    const cuuint64_t gstride[2] = {pitch, imageStride};
+    const cuuint32_t box[3] = {boxBytes, boxRows, 1};
+    const cuuint32_t estride[3] = {1, 1, 1};
+    const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+}  // namespace orbx
 
 namespace {
 
@@ -111,6 +135,7 @@ struct orbx_batch {
     int lastImages = 0;
     std::vector<int> hostLap;
     int fastTileRows = 0, fastMaxPix = 0;
+    DescMaps descMaps;
     uint8_t* stageIn = nullptr;  // dense device staging of uploaded images (PCIe copies of odd-width rows are ~6x slower than one contiguous copy)
     size_t stageBytes = 0;
 };
@@ -212,6 +237,13 @@ int batch_alloc(orbx_batch* b) {
     if ((r = dev_alloc(b, &B.outMono, (size_t)n))) return r;
     if ((r = dev_alloc(b, &B.errFlag, 1))) return r;
     B.imgBase = 0;
+    for (int l = 0; l < g.nlevels; ++l) {
+        const LevelGeom& L = g.lv[l];
+        const size_t blockOff = (size_t)L.planeOff - (size_t)kMarginY * L.pitch - kMarginX;  // first byte of this level's block
+        if (tma_encode_3d(&b->descMaps.ic[l], B.pyr + blockOff, L.pitch, L.h + 2 * kMarginY, n, L.planeBytes, 48, 31) ||
+            tma_encode_3d(&b->descMaps.bl[l], B.blur + blockOff, L.pitch, L.h + 2 * kMarginY, n, L.planeBytes, 64, 37))
+            return fail(ORBX_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+    }
     {
         std::vector<uint4> tab((size_t)g.cellsPerImage);
         make_cell_table(g, tab.data(), &b->fastTileRows, &b->fastMaxPix);
@@ -220,6 +252,7 @@ int batch_alloc(orbx_batch* b) {
         CU(cudaMemcpy(dtab, tab.data(), tab.size() * sizeof(uint4), cudaMemcpyHostToDevice));
         B.cellTab = dtab;
         CU(fast_configure(b->fastTileRows, b->fastMaxPix));
+        CU(describe_configure());
     }
     CU(cudaMemset(B.errFlag, 0, sizeof(int)));
     CU(cudaMemset(B.lapping, 0, (size_t)n * 2 * sizeof(int)));
@@ -444,7 +477,7 @@ int orbx_batch_run_range(orbx_batch* b, int first, int n, const int* lapping) {
     mark();
     launch_assemble(g, buf, n, s); ++launches;
     mark();
-    launch_describe(g, buf, n, s); ++launches;
+    launch_describe(g, buf, b->descMaps, n, s); ++launches;
     mark();
     CU(cudaGetLastError());
     b->launches = launches;

@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include "../../include/orbx.h"
+#include "tma.cuh"
 
 namespace orbx {
 
@@ -100,7 +101,12 @@ cudaError_t fast_configure(int tileRows, int maxPix);
 void launch_blur(const Geom& g, const Buffers& b, int level, int nImages, const int taps[7], cudaStream_t s);
 cudaError_t launch_octree(const Geom& g, const Buffers& b, int nImages, cudaStream_t s);
 void launch_assemble(const Geom& g, const Buffers& b, int nImages, cudaStream_t s);
-void launch_describe(const Geom& g, const Buffers& b, int nImages, cudaStream_t s);
+struct DescMaps {  // per level: 48x31 boxes of the pyramid (IC_Angle patch), 64x37 boxes of the blurred pyramid (rBRIEF window)
+    CUtensorMap ic[ORBX_MAX_LEVELS];
+    CUtensorMap bl[ORBX_MAX_LEVELS];
+};
+void launch_describe(const Geom& g, const Buffers& b, const DescMaps& maps, int nImages, cudaStream_t s);
+cudaError_t describe_configure();
 void launch_margin(const Geom& g, const Buffers& b, int nImages, cudaStream_t s);
 void launch_border(const uint8_t* src, int w, int h, int pitch, uint8_t* dst, int dpitch, cudaStream_t s);
 size_t octree_smem_bytes(int nodeCap);
