@@ -8,6 +8,9 @@
 //                computeOrbDescriptor (ORBextractor.cc:81-120) on the BLURRED level: lane i builds descriptor byte i from 16
 //                rotated samples; pattern staged in shared memory; cosf/sinf as glibc evaluates them (float_exact.cuh).
 // Both stages are gathers served by L2 (749 + 512 bytes per keypoint); no FMA contraction anywhere.
+#include <cstdlib>
+#include <type_traits>
+
 #include "float_exact.cuh"
 #include "orbx_internal.cuh"
 
@@ -88,20 +91,21 @@ __global__ void __launch_bounds__(256) k_assemble(const __grid_constant__ Geom g
 void launch_assemble(const Geom& g, const Buffers& b, int nImages, cudaStream_t s) { k_assemble<<<nImages, 256, 0, s>>>(g, b); }
 
 // ---------------------------------------------------------------------------------------------------------------
-// k_describe: each warp walks a run of consecutive keypoints.  Per keypoint ONE lane issues two TMA box loads — the 31x31
-// patch of the unblurred level (48-byte box rows) for the moments and the 37x37 window of the blurred level (64-byte box rows) for
-// the 512 rotated samples (|offset| <= 18: pattern radius 18.38) — into the warp's own double-buffered shared memory, and
-// the next keypoint's boxes are in flight while the current one is processed (mbarrier per stage).
-//   IC_Angle: lane v+15 owns patch row v: 9 words of the box row are funnel-shifted into 8 patch-aligned words and
-//   sum u*I / sum I are 2 x 8 IDP.4A with per-lane constant weight words (circular mask folded into the weights).
-//   rBRIEF: lane i builds descriptor byte i; pattern as float4 {x0,y0,x1,y1} in shared memory.
+// k_describe: a CTA of 8 warps handles 64 consecutive keypoints, 8 per warp, in three phases.
+//   1  moments: per keypoint ONE lane issues a TMA box load of the 31x31 patch of the unblurred level (box rows of 48 bytes:
+//      box origins must be 16-byte aligned in global memory, so the box starts at the aligned byte at or before column
+//      -15) into the warp's double-buffered shared memory; the next box is in flight while the current one is reduced.
+//      Lane v+15 owns patch row v: 9 words are funnel-shifted into 8 patch-aligned words, sum u*I and sum I are 2 x 8
+//      IDP.4A against per-lane constant weight words (circular mask folded in), then two warp-shuffle reductions.
+//   2  64 threads turn the 64 moment pairs into angle (cv::fastAtan2), cosf, sinf: the scalar float/double chain runs once
+//      per keypoint instead of once per lane.  Meanwhile the first two 37x37 windows of the blurred level are in flight.
+//   3  rBRIEF: lane i builds descriptor byte i from 16 rotated samples (|offset| <= 18: pattern radius 18.38) of the staged
+//      64-byte-row window; pattern as float4 {x0,y0,x1,y1} in shared memory; cvRound as add-magic (RNE, exact below 2^22).
 constexpr int DW = 8;            // warps per CTA
 constexpr int KPW = 8;           // consecutive keypoints per warp
-// TMA box origins must be 16-byte aligned in global memory: the boxes start at the aligned byte at or before the patch's
-// first column and are 15 bytes wider than the patch.
 constexpr int PA_ROW = 48, PB_ROW = 64;
 constexpr int PA_BYTES = PA_ROW * 31, PB_BYTES = PB_ROW * 37;
-constexpr int ST_A = 1536, ST_B = 2432, ST_BYTES = ST_A + ST_B;  // per stage, 128-byte aligned pieces
+constexpr int ST_BYTES = 2432;   // one stage holds either box (PB_BYTES = 2368), 128-byte aligned
 
 __device__ __forceinline__ int dp4a_us(uint32_t pix, uint32_t wgt, int acc) {  // unsigned pixels x signed weights
     int d;
@@ -113,24 +117,41 @@ __global__ void __launch_bounds__(32 * DW) k_describe(const __grid_constant__ Ge
     extern __shared__ __align__(128) unsigned char dsm[];
     __shared__ __align__(16) float4 pat4[256];
     __shared__ __align__(8) uint64_t bars[DW][2];
+    __shared__ int mom[DW * KPW][2];
+    __shared__ float2 rot[DW * KPW];  // (sin, cos)
     const int img = b.imgBase + blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    {
+    {   // pair p = 8 * byte + bit is read by lane `byte` in iteration `bit`: store it at [bit][byte] so that a warp reads 32
+        // consecutive float4 (a [byte][bit] layout makes every lane hit the same banks: 8-way conflicts)
         const signed char* q = c_pattern + 4 * tid;
-        pat4[tid] = make_float4((float)q[0], (float)q[1], (float)q[2], (float)q[3]);
+        pat4[(tid & 7) * 32 + (tid >> 3)] = make_float4((float)q[0], (float)q[1], (float)q[2], (float)q[3]);
     }
     if (lane == 0) { mbar_init(&bars[wid][0], 1); mbar_init(&bars[wid][1], 1); }
     mbar_fence_init();
     __syncthreads();
     const int n = b.outCount[img];
-    const int k0 = (blockIdx.x * DW + wid) * KPW;
-    const int cnt = min(KPW, n - k0);
-    if (cnt <= 0) return;
+    const int kBase = blockIdx.x * DW * KPW;
+    if (kBase >= n) return;
+    const int k0 = kBase + wid * KPW;
+    const int cnt = max(0, min(KPW, n - k0));
     unsigned char* stage = dsm + (size_t)wid * 2 * ST_BYTES;
     const KpWork* work = b.work + (size_t)img * g.K + k0;
+    uint32_t ph0 = 0, ph1 = 0;  // parities of the two stage barriers (uniform per warp)
 
-    // per-lane weights of patch row v = lane - 15: bytes u = 4c + j - 15, kept iff |u| <= umax[|v|] (ORBextractor.cc:57-74)
-    uint32_t wu[8], w1[8];
+    auto issueB = [&](int i) {
+        const KpWork wk = work[i];
+        uint64_t* bar = &bars[wid][i & 1];
+        mbar_arrive_expect_tx(bar, PB_BYTES);
+        tma_load_3d(stage + (i & 1) * ST_BYTES, &maps.bl[wk.level], bar, (kMarginX + wk.x - 18) & ~15, kMarginY + wk.y - 18, img);
+    };
+    auto wait_stage = [&](int st) {
+        if (st == 0) { mbar_wait(&bars[wid][0], ph0); ph0 ^= 1; }
+        else { mbar_wait(&bars[wid][1], ph1); ph1 ^= 1; }
+    };
+
+    // ---- phase 1: moments ----
     {
+        // per-lane weights of patch row v = lane - 15: bytes u = 4c + j - 15, kept iff |u| <= umax[|v|] (ORBextractor.cc:57-74)
+        uint32_t wu[8], w1[8];
         const int v = lane - kHalfPatch, av = v < 0 ? -v : v;
         const int lim = lane < 31 ? c_umax[av] : -1;
 #pragma unroll
@@ -145,69 +166,92 @@ __global__ void __launch_bounds__(32 * DW) k_describe(const __grid_constant__ Ge
             }
             wu[c] = a; w1[c] = o;
         }
-    }
-    const int vrow = lane - kHalfPatch;
-
-    auto issue = [&](int i) {  // lane 0: both boxes of keypoint i into stage i & 1
-        const KpWork wk = work[i];
-        unsigned char* st = stage + (i & 1) * ST_BYTES;
-        uint64_t* bar = &bars[wid][i & 1];
-        mbar_arrive_expect_tx(bar, PA_BYTES + PB_BYTES);
-        tma_load_3d(st, &maps.ic[wk.level], bar, (kMarginX + wk.x - kHalfPatch) & ~15, kMarginY + wk.y - kHalfPatch, img);
-        tma_load_3d(st + ST_A, &maps.bl[wk.level], bar, (kMarginX + wk.x - 18) & ~15, kMarginY + wk.y - 18, img);
-    };
-    if (lane == 0) issue(0);
-    for (int i = 0; i < cnt; ++i) {
-        if (lane == 0 && i + 1 < cnt) issue(i + 1);
-        const KpWork wk = work[i];
-        const unsigned char* st = stage + (i & 1) * ST_BYTES;
-        mbar_wait(&bars[wid][i & 1], (i >> 1) & 1);
-
-        // ---- IC_Angle ----
-        int m10 = 0, m01 = 0;
-        {
-            const int sa = (kMarginX + wk.x - kHalfPatch) & 15;  // patch column -15 sits at byte sa of the box row
-            const uint32_t* rowp = reinterpret_cast<const uint32_t*>(st + (lane < 31 ? lane : 0) * PA_ROW) + (sa >> 2);
+        auto issueA = [&](int i) {
+            const KpWork wk = work[i];
+            uint64_t* bar = &bars[wid][i & 1];
+            mbar_arrive_expect_tx(bar, PA_BYTES);
+            tma_load_3d(stage + (i & 1) * ST_BYTES, &maps.ic[wk.level], bar, (kMarginX + wk.x - kHalfPatch) & ~15, kMarginY + wk.y - kHalfPatch, img);
+        };
+        if (lane == 0 && cnt > 0) issueA(0);
+        for (int i = 0; i < cnt; ++i) {
+            if (lane == 0 && i + 1 < cnt) issueA(i + 1);
+            const int sa = (kMarginX + work[i].x - kHalfPatch) & 15;  // patch column -15 sits at byte sa of the box row
+            wait_stage(i & 1);
+            // the whole 48-byte box row as three 128-bit loads (conflict-free at this stride), then a warp-uniform word offset
+            const uint4* rowp = reinterpret_cast<const uint4*>(stage + (i & 1) * ST_BYTES + (lane < 31 ? lane : 0) * PA_ROW);
+            const uint4 q0 = rowp[0], q1 = rowp[1], q2 = rowp[2];
+            const uint32_t rw[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
             const int bs = (sa & 3) * 8;
-            uint32_t raw[9], wds[8];
+            int m10 = 0, s1 = 0;
+            auto reduce_row = [&](auto W0) {
+                constexpr int w0 = decltype(W0)::value;
 #pragma unroll
-            for (int c = 0; c < 9; ++c) raw[c] = rowp[c];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) wds[c] = __funnelshift_r(raw[c], raw[c + 1], bs);
-            int s1 = 0;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                m10 = dp4a_us(wds[c], wu[c], m10);
-                s1 = (int)__dp4a(wds[c], w1[c], (uint32_t)s1);
+                for (int c = 0; c < 8; ++c) {
+                    const uint32_t wd = __funnelshift_r(rw[w0 + c], rw[w0 + c + 1], bs);
+                    m10 = dp4a_us(wd, wu[c], m10);
+                    s1 = (int)__dp4a(wd, w1[c], (uint32_t)s1);
+                }
+            };
+            switch (sa >> 2) {
+                case 0: reduce_row(std::integral_constant<int, 0>()); break;
+                case 1: reduce_row(std::integral_constant<int, 1>()); break;
+                case 2: reduce_row(std::integral_constant<int, 2>()); break;
+                default: reduce_row(std::integral_constant<int, 3>()); break;
             }
-            m01 = vrow * s1;  // lane 31 has all-zero weights
-        }
+            int m01 = v * s1;  // lane 31 has all-zero weights
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            m10 += __shfl_xor_sync(0xFFFFFFFFu, m10, o);
-            m01 += __shfl_xor_sync(0xFFFFFFFFu, m01, o);
+            for (int o = 16; o > 0; o >>= 1) {
+                m10 += __shfl_xor_sync(0xFFFFFFFFu, m10, o);
+                m01 += __shfl_xor_sync(0xFFFFFFFFu, m01, o);
+            }
+            if (lane == 0) { mom[wid * KPW + i][0] = m01; mom[wid * KPW + i][1] = m10; }
+            __syncwarp();  // every lane is done with this stage before lane 0 re-arms it
         }
-        const float angle = fast_atan2_deg((float)m01, (float)m10);
+        // both stages are free: put the first two blurred windows in flight while phase 2 runs
+        if (lane == 0) {
+            if (cnt > 0) issueB(0);
+            if (cnt > 1) issueB(1);
+        }
+    }
+    __syncthreads();
 
-        // ---- steered BRIEF ----
+    // ---- phase 2: angle, sin, cos — one thread per keypoint ----
+    if (tid < DW * KPW && kBase + tid < n) {
+        const float angle = fast_atan2_deg((float)mom[tid][0], (float)mom[tid][1]);
         const float factorPI = (float)(3.14159265358979323846 / 180.0);  // == (float)(CV_PI/180.f): the divisor is promoted to double
         float sn, cs;
         sinf_cosf_glibc(__fmul_rn(angle, factorPI), &sn, &cs);
-        const unsigned char* cb = st + ST_A + 18 * PB_ROW + 18 + ((kMarginX + wk.x - 18) & 15);  // the keypoint inside the staged window
+        rot[tid] = make_float2(sn, cs);
+        const KpWork wk = b.work[(size_t)img * g.K + kBase + tid];
+        b.kps[(size_t)img * g.K + wk.dst].angle = angle;
+    }
+    __syncthreads();
+
+    // ---- phase 3: steered BRIEF ----
+    const float RND = 12582912.f;  // 1.5 * 2^23: (x + RND) has the round-half-even integer of x in its low mantissa bits
+    for (int i = 0; i < cnt; ++i) {
+        const KpWork wk = work[i];
+        const float2 sc = rot[wid * KPW + i];
+        const float sn = sc.x, cs = sc.y;
+        wait_stage(i & 1);
+        // sample index r * 64 + c from the biased float bits (bias B = 0x4B400000 each), in wrap-around 32-bit arithmetic
+        const unsigned char* cb = stage + (i & 1) * ST_BYTES + 18 * PB_ROW + 18 + ((kMarginX + wk.x - 18) & 15);
+        const uint32_t BIAS = (uint32_t)(0x4B400000ull * (PB_ROW + 1));
         int val = 0;
 #pragma unroll
         for (int bit = 0; bit < 8; ++bit) {
-            const float4 q = pat4[lane * 8 + bit];
-            const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(q.x, sn), __fmul_rn(q.y, cs)));
-            const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(q.x, cs), __fmul_rn(q.y, sn)));
-            const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(q.z, sn), __fmul_rn(q.w, cs)));
-            const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(q.z, cs), __fmul_rn(q.w, sn)));
-            const int t0 = cb[r0 * PB_ROW + c0], t1 = cb[r1 * PB_ROW + c1];
+            const float4 q = pat4[bit * 32 + lane];
+            const int r0 = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(q.x, sn), __fmul_rn(q.y, cs)), RND));
+            const int c0 = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(q.x, cs), __fmul_rn(q.y, sn)), RND));
+            const int r1 = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(q.z, sn), __fmul_rn(q.w, cs)), RND));
+            const int c1 = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(q.z, cs), __fmul_rn(q.w, sn)), RND));
+            const int i0 = (int)((uint32_t)r0 * PB_ROW + (uint32_t)c0 - BIAS), i1 = (int)((uint32_t)r1 * PB_ROW + (uint32_t)c1 - BIAS);
+            const int t0 = cb[i0], t1 = cb[i1];
             val |= (t0 < t1) << bit;
         }
         b.desc[((size_t)img * g.K + wk.dst) * 32 + lane] = (uint8_t)val;
-        if (lane == 0) b.kps[(size_t)img * g.K + wk.dst].angle = angle;
-        __syncwarp();  // every lane is done with this stage before lane 0 re-arms it (two iterations later)
+        __syncwarp();
+        if (lane == 0 && i + 2 < cnt) issueB(i + 2);
     }
 }
 
