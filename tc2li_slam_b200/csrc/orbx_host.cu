@@ -124,6 +124,8 @@ struct orbx_batch {
     int device = 0, width = 0, height = 0, maxImages = 0;
     int taps[7] = {18, 34, 48, 56, 48, 34, 18};
     cudaStream_t own = nullptr, stream = nullptr;
+    cudaStream_t side = nullptr;        // blur runs here, concurrently with FAST + quadtree (both only need the pyramid)
+    cudaEvent_t evPyr = nullptr, evBlur = nullptr;
     std::vector<void*> allocs;
     ResizeTab tabs[ORBX_MAX_LEVELS];
     size_t pyrBytes = 0, candElems = 0;
@@ -134,7 +136,8 @@ struct orbx_batch {
     int launches = 0;
     int lastImages = 0;
     std::vector<int> hostLap;
-    int fastTileRows = 0, fastMaxPix = 0;
+    int fastTileRows = 0, fastTs = 64, numSMs = 148;
+    FastMaps fastMaps;
     DescMaps descMaps;
     uint8_t* stageIn = nullptr;  // dense device staging of uploaded images (PCIe copies of odd-width rows are ~6x slower than one contiguous copy)
     size_t stageBytes = 0;
@@ -246,12 +249,18 @@ int batch_alloc(orbx_batch* b) {
     }
     {
         std::vector<uint4> tab((size_t)g.cellsPerImage);
-        make_cell_table(g, tab.data(), &b->fastTileRows, &b->fastMaxPix);
+        int maxCw = 0;
+        make_cell_table(g, tab.data(), &b->fastTileRows, &maxCw);
+        b->fastTs = fast_tile_stride(maxCw);
         uint4* dtab = nullptr;
         if ((r = dev_alloc(b, &dtab, tab.size()))) return r;
         CU(cudaMemcpy(dtab, tab.data(), tab.size() * sizeof(uint4), cudaMemcpyHostToDevice));
         B.cellTab = dtab;
-        CU(fast_configure(b->fastTileRows, b->fastMaxPix));
+        CU(fast_configure(b->fastTileRows, b->fastTs));
+        if (fast_encode_maps(g, B.pyr, n, b->fastTs, &b->fastMaps)) return fail(ORBX_ERR_CUDA, "cuTensorMapEncodeTiled failed (FAST tiles)");
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, b->device));
+        b->numSMs = prop.multiProcessorCount;
         CU(describe_configure());
     }
     CU(cudaMemset(B.errFlag, 0, sizeof(int)));
@@ -318,6 +327,9 @@ int orbx_batch_create(int nfeatures, float scale_factor, int nlevels, int ini_th
     auto bail = [&](int code) { orbx_batch_destroy(b); return code; };
     if ((e = cudaStreamCreateWithFlags(&b->own, cudaStreamNonBlocking)) != cudaSuccess) return bail(cuda_fail(e, "cudaStreamCreate"));
     b->stream = b->own;
+    if ((e = cudaStreamCreateWithFlags(&b->side, cudaStreamNonBlocking)) != cudaSuccess) return bail(cuda_fail(e, "cudaStreamCreate"));
+    if ((e = cudaEventCreateWithFlags(&b->evPyr, cudaEventDisableTiming)) != cudaSuccess) return bail(cuda_fail(e, "cudaEventCreate"));
+    if ((e = cudaEventCreateWithFlags(&b->evBlur, cudaEventDisableTiming)) != cudaSuccess) return bail(cuda_fail(e, "cudaEventCreate"));
     if ((r = batch_alloc(b)) != ORBX_OK) return bail(r);
     if ((e = upload_describe_constants(kPatternHost, b->p.umax)) != cudaSuccess) return bail(cuda_fail(e, "constant upload"));
     int maxCap = 0;
@@ -337,6 +349,9 @@ void orbx_batch_destroy(orbx_batch* b) {
     if (b->borderScratch) cudaFree(b->borderScratch);
     if (b->stageIn) cudaFree(b->stageIn);
     for (auto& ev : b->ev) if (ev) cudaEventDestroy(ev);
+    if (b->side) { cudaStreamSynchronize(b->side); cudaStreamDestroy(b->side); }
+    if (b->evPyr) cudaEventDestroy(b->evPyr);
+    if (b->evBlur) cudaEventDestroy(b->evBlur);
     if (b->own) cudaStreamDestroy(b->own);
     delete b;
 }
@@ -466,9 +481,19 @@ int orbx_batch_run_range(orbx_batch* b, int first, int n, const int* lapping) {
     for (int l = 1; l < g.nlevels; ++l) { launch_pyramid_level(g, buf, l, b->tabs[l], n, s); ++launches; }
     launch_margin(g, buf, n, s); ++launches;
     mark();
-    launch_fast(g, buf, n, b->fastTileRows, b->fastMaxPix, s); ++launches;
+    // FAST -> quadtree and the blur both depend only on the pyramid: the blur goes to the side stream unless per-stage
+    // timing was requested (then everything is serialised on one stream so that the events bracket single stages)
+    const bool overlap = !b->timing;
+    if (overlap) {
+        CU(cudaEventRecord(b->evPyr, s));
+        CU(cudaStreamWaitEvent(b->side, b->evPyr, 0));
+        for (int l = 0; l < g.nlevels; ++l) { launch_blur(g, buf, l, n, b->taps, b->side); ++launches; }
+        CU(cudaEventRecord(b->evBlur, b->side));
+    }
+    launch_fast(g, buf, b->fastMaps, n, b->fastTileRows, b->fastTs, b->numSMs, s); ++launches;
     mark();
-    for (int l = 0; l < g.nlevels; ++l) { launch_blur(g, buf, l, n, b->taps, s); ++launches; }
+    if (!overlap)
+        for (int l = 0; l < g.nlevels; ++l) { launch_blur(g, buf, l, n, b->taps, s); ++launches; }
     mark();
     {
         cudaError_t e = launch_octree(g, buf, n, s); ++launches;
@@ -477,6 +502,7 @@ int orbx_batch_run_range(orbx_batch* b, int first, int n, const int* lapping) {
     mark();
     launch_assemble(g, buf, n, s); ++launches;
     mark();
+    if (overlap) CU(cudaStreamWaitEvent(s, b->evBlur, 0));
     launch_describe(g, buf, b->descMaps, n, s); ++launches;
     mark();
     CU(cudaGetLastError());

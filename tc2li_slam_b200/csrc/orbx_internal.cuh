@@ -95,9 +95,14 @@ struct Buffers {
 // kernel launchers (one translation unit per stage)
 void launch_synth(uint8_t* l0, int w, int h, int pitch, size_t planeBytes, uint32_t seed0, int firstImage, int nImages, int stereo, cudaStream_t s);
 void launch_pyramid_level(const Geom& g, const Buffers& b, int level, const ResizeTab& tab, int nImages, cudaStream_t s);
-void launch_fast(const Geom& g, const Buffers& b, int nImages, int tileRows, int maxPix, cudaStream_t s);
-void make_cell_table(const Geom& g, uint4* tab, int* tileRows, int* maxPix);
-cudaError_t fast_configure(int tileRows, int maxPix);
+struct FastMaps {  // per level: {tile row bytes x (hCell + 6)} boxes of the pyramid (FAST cell crops)
+    CUtensorMap m[ORBX_MAX_LEVELS];
+};
+void launch_fast(const Geom& g, const Buffers& b, const FastMaps& maps, int nImages, int tileRows, int ts, int numSMs, cudaStream_t s);
+void make_cell_table(const Geom& g, uint4* tab, int* tileRows, int* maxCw);
+int fast_tile_stride(int maxCw);
+cudaError_t fast_configure(int tileRows, int ts);
+int fast_encode_maps(const Geom& g, uint8_t* pyr, int nImages, int ts, FastMaps* out);
 void launch_blur(const Geom& g, const Buffers& b, int level, int nImages, const int taps[7], cudaStream_t s);
 cudaError_t launch_octree(const Geom& g, const Buffers& b, int nImages, cudaStream_t s);
 void launch_assemble(const Geom& g, const Buffers& b, int nImages, cudaStream_t s);
