@@ -62,9 +62,10 @@ __device__ __forceinline__ uint32_t bytes_gt(uint32_t d, uint32_t kAdd, bool tHi
 struct CellCtx {
     const uint8_t* tile;   // crop byte (r, c) at tile[r * TS + shift + c]
     uint8_t* sc;           // score map, same layout
-    uint16_t* list1;       // compass survivors (tile offsets); NMS survivors afterwards
+    uint16_t* listW;       // words with a compass survivor: tile word index | 4 pixel flags << 12
+    uint16_t* list1;       // compass survivors (tile byte offsets); NMS survivors afterwards
     uint16_t* list2;       // corners (tile offset | 0x8000 = dark)
-    int n1, n2;            // warp-uniform fill levels
+    int nw, n1, n2;        // warp-uniform fill levels
     bool flushedB;         // list2 was flushed before the NMS: corners are no longer all listed
     int lane;
 };
@@ -130,6 +131,28 @@ __device__ __forceinline__ void flush_A2(CellCtx& c, int t) {  // exact ring mas
     c.n1 = 0;
 }
 
+// listW -> list1: one entry per flagged pixel, in order (exclusive prefix of the per-lane counts from the ballots of their bits)
+template <int TS>
+__device__ __forceinline__ void flush_W(CellCtx& c, int t) {
+    for (int k0 = 0; k0 < c.nw; k0 += 32) {
+        const int k = k0 + c.lane;
+        const int e = k < c.nw ? c.listW[k] : 0;
+        const int f4 = e >> 12, off = (e & 0xFFF) * 4;
+        const int cnt = __popc(f4);
+        if (c.n1 + 128 > CAP) flush_A2<TS>(c, t);  // warp-uniform
+        const unsigned q0 = __ballot_sync(FULL, cnt & 1), q1 = __ballot_sync(FULL, cnt & 2), q2 = __ballot_sync(FULL, cnt & 4);
+        const unsigned lt = (1u << c.lane) - 1;
+        int pos = c.n1 + __popc(q0 & lt) + 2 * __popc(q1 & lt) + 4 * __popc(q2 & lt);
+        if (f4 & 1) c.list1[pos++] = (uint16_t)off;
+        if (f4 & 2) c.list1[pos++] = (uint16_t)(off + 1);
+        if (f4 & 4) c.list1[pos++] = (uint16_t)(off + 2);
+        if (f4 & 8) c.list1[pos] = (uint16_t)(off + 3);
+        c.n1 += __popc(q0) + 2 * __popc(q1) + 4 * __popc(q2);
+    }
+    __syncwarp();
+    c.nw = 0;
+}
+
 // survivors (tile offsets in `surv`) -> global candidate list, coordinates relative to (16,16) (ORBextractor.cc:837-842)
 template <int TS>
 __device__ __forceinline__ void emit(const CellCtx& c, const uint16_t* surv, int ns, int shift, int relX, int relY, uint32_t* cand, int candCap,
@@ -157,11 +180,12 @@ __global__ void __launch_bounds__(32 * FW) k_fast_cells(const __grid_constant__ 
     extern __shared__ __align__(128) unsigned char fsm[];
     __shared__ __align__(8) uint64_t bars[FW][2];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int warpBytes = 3 * tileBytes + 2 * CAP * 2;
+    const int warpBytes = 3 * tileBytes + 3 * CAP * 2;
     unsigned char* my = fsm + (size_t)wid * warpBytes;
     CellCtx c;
     c.sc = my + 2 * tileBytes;
-    c.list1 = reinterpret_cast<uint16_t*>(my + 3 * tileBytes);
+    c.listW = reinterpret_cast<uint16_t*>(my + 3 * tileBytes);
+    c.list1 = c.listW + CAP;
     c.list2 = c.list1 + CAP;
     c.lane = lane;
     for (int k = lane; k < tileBytes / 16; k += 32) reinterpret_cast<uint4*>(c.sc)[k] = make_uint4(0, 0, 0, 0);  // stays all-zero between cells
@@ -209,50 +233,48 @@ __global__ void __launch_bounds__(32 * FW) k_fast_cells(const __grid_constant__ 
         int attempt = 0;
         for (;; ++attempt) {
             const int t = attempt == 0 ? g.iniTh : g.minTh;
-            c.n1 = 0; c.n2 = 0; c.flushedB = false;
+            c.nw = 0; c.n1 = 0; c.n2 = 0; c.flushedB = false;
 
-            // ---- pass A: compass test, 4 pixels per lane ----
+            // ---- pass A: compass test, 4 pixels per lane; words with a survivor are listed with their 4 pixel flags ----
             {
                 const uint32_t kAdd = (uint32_t)(0x7f - (t & 0x7f)) * 0x01010101u;
                 const bool tHigh = t >= 128;
                 const int items = ih * nW;
+                // bytes outside the interior [0, iw) can only sit in the first / last word of a row
                 const int xb0 = 4 * wFirst - 3 - shift;  // interior x of byte 0 of the first word (<= 0)
-                for (int it0 = 0; it0 < items; it0 += 32) {
-                    const int itx = it0 + lane;
-                    uint32_t F = 0;
-                    int off = 0;
-                    if (itx < items) {
-                        const int y = (int)__umulhi((uint32_t)itx, magicW), cc = itx - y * nW;
-                        const uint32_t* row = tileW + (y + 3) * (TS / 4) + wFirst + cc;
-                        const uint32_t cur = row[0], prev = row[-1], next = row[1], up = row[3 * (TS / 4)], dn = row[-3 * (TS / 4)];
-                        const uint32_t e = __funnelshift_r(cur, next, 24);  // pixels at x + 3
-                        const uint32_t wv = __funnelshift_r(prev, cur, 8);  // pixels at x - 3
-                        const uint32_t ns = bytes_gt(__vabsdiffu4(up, cur), kAdd, tHigh) | bytes_gt(__vabsdiffu4(dn, cur), kAdd, tHigh);
-                        const uint32_t ew = bytes_gt(__vabsdiffu4(e, cur), kAdd, tHigh) | bytes_gt(__vabsdiffu4(wv, cur), kAdd, tHigh);
-                        F = ns & ew & 0x80808080u;
-                        if (F) {  // bytes outside the interior [0, iw) are dropped
-                            const int xb = xb0 + 4 * cc;
-                            const int nL = max(-xb, 0), nR = max(xb + 4 - iw, 0);
-                            F &= (0xFFFFFFFFu << (8 * nL)) & (0xFFFFFFFFu >> (8 * nR));
-                            off = (y + 3) * TS + 4 * (wFirst + cc);  // tile byte offset of byte 0 of this word
-                        }
+                const uint32_t maskFirst = 0x80808080u << (8 * (-xb0));
+                const uint32_t maskLast = 0x80808080u >> (8 * (xb0 + 4 * nW - iw));
+                auto compass = [&](int itx, int& wofs) -> uint32_t {
+                    if (itx >= items) return 0u;
+                    const int y = (int)__umulhi((uint32_t)itx, magicW), cc = itx - y * nW;
+                    wofs = (y + 3) * (TS / 4) + wFirst + cc;
+                    const uint32_t* row = tileW + wofs;
+                    const uint32_t cur = row[0], prev = row[-1], next = row[1], up = row[3 * (TS / 4)], dn = row[-3 * (TS / 4)];
+                    const uint32_t e = __funnelshift_r(cur, next, 24);  // pixels at x + 3
+                    const uint32_t wv = __funnelshift_r(prev, cur, 8);  // pixels at x - 3
+                    const uint32_t ns = bytes_gt(__vabsdiffu4(up, cur), kAdd, tHigh) | bytes_gt(__vabsdiffu4(dn, cur), kAdd, tHigh);
+                    const uint32_t ew = bytes_gt(__vabsdiffu4(e, cur), kAdd, tHigh) | bytes_gt(__vabsdiffu4(wv, cur), kAdd, tHigh);
+                    return ns & ew & (cc == 0 ? maskFirst : 0x80808080u) & (cc == nW - 1 ? maskLast : 0x80808080u);
+                };
+                auto append = [&](uint32_t F, int wofs) {
+                    const unsigned bal = __ballot_sync(FULL, F != 0);
+                    if (bal) {
+                        if (c.nw + 32 > CAP) flush_W<TS>(c, t);  // warp-uniform
+                        // bits 7/15/23/31 -> 4 contiguous flag bits
+                        if (F) c.listW[c.nw + __popc(bal & ((1u << lane) - 1))] = (uint16_t)(wofs | ((((F >> 7) * 0x01020408u) >> 24) << 12));
+                        c.nw += __popc(bal);
                     }
-                    if (__ballot_sync(FULL, F != 0)) {
-                        if (c.n1 + 128 > CAP) flush_A2<TS>(c, t);  // warp-uniform
-                        // ordered append: exclusive prefix of the per-lane counts (0..4) from the ballots of their bits
-                        const int cnt = __popc(F);
-                        const unsigned q0 = __ballot_sync(FULL, cnt & 1), q1 = __ballot_sync(FULL, cnt & 2), q2 = __ballot_sync(FULL, cnt & 4);
-                        const unsigned lt = (1u << lane) - 1;
-                        int pos = c.n1 + __popc(q0 & lt) + 2 * __popc(q1 & lt) + 4 * __popc(q2 & lt);
-                        if (F & 0x80u) c.list1[pos++] = (uint16_t)off;
-                        if (F & 0x8000u) c.list1[pos++] = (uint16_t)(off + 1);
-                        if (F & 0x800000u) c.list1[pos++] = (uint16_t)(off + 2);
-                        if (F & 0x80000000u) c.list1[pos] = (uint16_t)(off + 3);
-                        c.n1 += __popc(q0) + 2 * __popc(q1) + 4 * __popc(q2);
-                    }
+                };
+                for (int it0 = 0; it0 < items; it0 += 64) {  // two independent items per lane per trip (ILP: 16 warps per SM)
+                    int w0 = 0, w1 = 0;
+                    const uint32_t F0 = compass(it0 + lane, w0);
+                    const uint32_t F1 = compass(it0 + 32 + lane, w1);
+                    append(F0, w0);
+                    append(F1, w1);
                 }
                 __syncwarp();
             }
+            flush_W<TS>(c, t);
             flush_A2<TS>(c, t);
             flush_B<TS>(c);
 
@@ -268,7 +290,8 @@ __global__ void __launch_bounds__(32 * FW) k_fast_cells(const __grid_constant__ 
                         off = c.list2[k] & 0x7FFF;
                         const uint8_t* q = c.sc + off;
                         const int s = q[0];
-                        keep = s > q[-1] && s > q[1] && s > q[-TS - 1] && s > q[-TS] && s > q[-TS + 1] && s > q[TS - 1] && s > q[TS] && s > q[TS + 1];
+                        const int nmax = max(max(max((int)q[-1], (int)q[1]), max((int)q[-TS - 1], (int)q[-TS])), max(max((int)q[-TS + 1], (int)q[TS - 1]), max((int)q[TS], (int)q[TS + 1])));
+                        keep = s > nmax;  // all eight loads issue together (no short-circuit chain)
                     }
                     const unsigned bal = __ballot_sync(FULL, keep);
                     if (keep) surv[ns + __popc(bal & ((1u << lane) - 1))] = (uint16_t)off;
@@ -352,7 +375,7 @@ void make_cell_table(const Geom& g, uint4* tab, int* tileRows, int* maxCw) {
 
 // box rows of 64 bytes hold crops up to 49 columns (15 alignment bytes + crop), 96 bytes up to 81 (the largest possible: 78)
 int fast_tile_stride(int maxCw) { return maxCw <= 49 ? 64 : 96; }
-static size_t fast_warp_bytes(int tileRows, int ts) { return (size_t)3 * tileRows * ts + 2 * CAP * 2; }
+static size_t fast_warp_bytes(int tileRows, int ts) { return (size_t)3 * tileRows * ts + 3 * CAP * 2; }
 
 cudaError_t fast_configure(int tileRows, int ts) {
     const int smem = (int)(FW * fast_warp_bytes(tileRows, ts));
