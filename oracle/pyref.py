@@ -1,0 +1,88 @@
+"""ctypes front-end of oracle/_ref/libref_orb.so: the reference's OWN ORBextractor.cc (compiled where it lies under
+/root/reference against the stand-in OpenCV headers of oracle/cvstub).  TEST INFRASTRUCTURE ONLY.
+
+Built by `make -C oracle ref` where /root/reference is mounted; the .so travels to the GPU box with the gpurun snapshot.
+Used to validate the restated oracle and as the CPU baseline of bench.py (`cpu_baseline.kind == "reference"`)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from .pyoracle import KP_DTYPE
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "_ref", "libref_orb.so")
+_lib = None
+
+
+def available():
+    return os.path.exists(_LIB)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        C.CDLL(os.path.join(_HERE, "liborb_oracle.so"), mode=C.RTLD_GLOBAL)  # the stub's pixel primitives
+        L = C.CDLL(_LIB)
+        L.refo_create.restype = C.c_void_p
+        L.refo_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.refo_destroy.argtypes = [C.c_void_p]
+        L.refo_set_blur_taps.argtypes = [C.c_void_p]
+        L.refo_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.refo_get_keypoints.argtypes = [C.c_void_p]
+        L.refo_get_descriptors.argtypes = [C.c_void_p]
+        L.refo_tables.argtypes = [C.c_void_p] * 5
+        L.refo_level_size.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.refo_get_level.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class RefExtractor:
+    """TC2LI_SLAM::ORBextractor itself (ORBextractor.h:52-118)."""
+
+    def __init__(self, nfeatures=2000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+        self.nlevels = nlevels
+        self._h = C.c_void_p(lib().refo_create(nfeatures, scale_factor, nlevels, ini_th, min_th))
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().refo_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def tables(self):
+        n = self.nlevels
+        a, b, c, d = (np.empty(n, np.float32) for _ in range(4))
+        lib().refo_tables(self._h, _p(a), _p(b), _p(c), _p(d))
+        return dict(scale_factors=a, inv_scale_factors=b, level_sigma2=c, inv_level_sigma2=d)
+
+    def __call__(self, image, lapping=(0, 0)):
+        if image is None or image.size == 0:
+            r = lib().refo_extract(self._h, None, 0, 0, 0, int(lapping[0]), int(lapping[1]))
+            return r, np.empty(0, KP_DTYPE), np.empty((0, 32), np.uint8)
+        image = np.asarray(image)
+        assert image.dtype == np.uint8 and image.ndim == 2
+        if image.strides[1] != 1:
+            image = np.ascontiguousarray(image)
+        r = lib().refo_extract(self._h, _p(image), image.shape[1], image.shape[0], image.strides[0], int(lapping[0]), int(lapping[1]))
+        n = lib().refo_num_keypoints()
+        kps = np.empty(n, KP_DTYPE)
+        desc = np.empty((n, 32), np.uint8)
+        if n:
+            lib().refo_get_keypoints(_p(kps))
+            lib().refo_get_descriptors(_p(desc))
+        return r, kps, desc
+
+    def level(self, l, border=0):
+        w, h = C.c_int(), C.c_int()
+        lib().refo_level_size(self._h, l, C.byref(w), C.byref(h))
+        out = np.empty((h.value + 2 * border, w.value + 2 * border), np.uint8)
+        lib().refo_get_level(self._h, l, border, _p(out))
+        return out

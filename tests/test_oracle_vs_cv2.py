@@ -1,0 +1,79 @@
+"""Pins the oracle's restated OpenCV primitives against the REAL OpenCV: the cv2 wheel of this image
+(4.13).  These are the pixel primitives the reference calls (ORBextractor.cc:76, 800, 1106, 1156, 1158) and the ones the
+stand-in headers of oracle/cvstub forward to when the reference's own translation unit is compiled (oracle/_ref).
+Bit-exact on every check.  Skipped when cv2 is not importable."""
+import numpy as np
+import pytest
+
+cv2 = pytest.importorskip("cv2")
+
+from oracle import pyoracle as po
+
+
+@pytest.fixture(autouse=True, params=[True, False], ids=["ipp_on", "ipp_off"])
+def ipp(request):
+    if hasattr(cv2, "ipp"):
+        cv2.ipp.setUseIPP(request.param)
+    cv2.setNumThreads(1)
+    yield
+
+
+@pytest.mark.parametrize("shape", [(376, 1241), (480, 752), (370, 1226), (200, 640), (135, 240)])
+def test_resize_chain_matches_cv2(shape):
+    h, w = shape
+    img = po.synth_v1(w, h, 7)
+    sf = 1.0
+    cur_o, cur_c = img, img
+    for l in range(1, 8):
+        sf = np.float32(sf * 1.2)
+        inv = np.float32(1.0) / np.float32(sf)
+        dw, dh = int(np.rint(np.float32(w) * inv)), int(np.rint(np.float32(h) * inv))
+        cur_c = cv2.resize(cur_c, (dw, dh), interpolation=cv2.INTER_LINEAR)
+        cur_o = po.resize(cur_o, dw, dh)
+        assert np.array_equal(cur_o, cur_c), f"level {l}"
+
+
+def test_resize_other_ratios():
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, (301, 517), dtype=np.uint8)
+    for dw, dh in [(345, 201), (259, 151), (470, 274), (130, 75), (516, 300)]:
+        assert np.array_equal(po.resize(img, dw, dh), cv2.resize(img, (dw, dh), interpolation=cv2.INTER_LINEAR)), (dw, dh)
+
+
+def test_border_reflect101():
+    img = po.synth_v1(97, 53, 1)
+    assert np.array_equal(np.pad(img, 19, mode="reflect"), cv2.copyMakeBorder(img, 19, 19, 19, 19, cv2.BORDER_REFLECT_101))
+
+
+@pytest.mark.parametrize("shape", [(376, 1241), (120, 200), (37, 41), (9, 300)])
+def test_gaussian_blur_matches_cv2(shape):
+    h, w = shape
+    rng = np.random.default_rng(h)
+    for img in (po.synth_v1(w, h, 3), rng.integers(0, 256, (h, w), dtype=np.uint8), (rng.integers(0, 2, (h, w)) * 255).astype(np.uint8)):
+        want = cv2.GaussianBlur(img, (7, 7), 2, None, 2, cv2.BORDER_REFLECT_101)
+        assert np.array_equal(po.blur(img), want)
+
+
+@pytest.mark.parametrize("t", [20, 12, 7, 1])
+def test_fast_matches_cv2(t):
+    rng = np.random.default_rng(t)
+    det = cv2.FastFeatureDetector_create(t, True, cv2.FAST_FEATURE_DETECTOR_TYPE_9_16)
+    imgs = [po.synth_v1(320, 200, 9)] + [po.synth_v1(1241, 376, 2)[y:y + 45, x:x + 42] for y, x in rng.integers(0, 300, (30, 2))]
+    imgs += [rng.integers(0, 256, (40, 44), dtype=np.uint8), (rng.integers(0, 2, (48, 52)) * 255).astype(np.uint8), np.full((30, 30), 9, np.uint8),
+             po.synth_v1(60, 6, 1), po.synth_v1(6, 60, 1), po.synth_v1(7, 7, 1)]
+    for img in imgs:
+        img = np.ascontiguousarray(img)
+        kps = det.detect(img)
+        want = np.array([[int(k.pt[0]), int(k.pt[1]), int(k.response)] for k in kps], np.int32).reshape(-1, 3)
+        got = po.fast(img, t)
+        assert np.array_equal(got, want), (img.shape, len(got), len(want))
+
+
+def test_fast_atan2_matches_cv2():
+    rng = np.random.default_rng(3)
+    ys = rng.integers(-2 ** 21, 2 ** 21, 20000).astype(np.float32)
+    xs = rng.integers(-2 ** 21, 2 ** 21, 20000).astype(np.float32)
+    ys[:50] = 0
+    xs[25:75] = 0
+    for y, x in zip(ys, xs):
+        assert np.float32(po.fast_atan2(y, x)) == np.float32(cv2.fastAtan2(float(y), float(x))), (y, x)
