@@ -208,8 +208,9 @@ def main():
     import tc2li_slam_b200 as T
     from tc2li_slam_b200.orbx import Event
 
+    from tc2li_slam_b200.sharding import frame_seed, weak_scaling_frames
     n_img = 2 * args.pairs
-    seed0 = 100000 * rank
+    seed0 = frame_seed(weak_scaling_frames(args.pairs, rank)[0])  # every rank extracts its own, distinct frames
     group = args.group if args.group > 0 else n_img
 
     # ---- resident run: all level-0 images live in the handle's pyramid buffer ----
