@@ -210,43 +210,70 @@ constexpr int BLUR_WARPS = 4;
 
 template <bool SAT>
 __global__ void __launch_bounds__(32 * BLUR_WARPS) k_blur(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int w, int h, int pitch,
-                                                         size_t plane, uint32_t cA, uint32_t cB, int t0, int t1, int t2, int t3, int t4, int t5, int t6) {
+                                                         size_t plane, uint32_t cA, uint32_t cB, uint32_t c67, uint32_t c56, uint32_t c45, uint32_t c34,
+                                                         uint32_t c23, uint32_t c12, uint32_t c01, uint32_t c0x) {
     const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4;
     const int ys = (blockIdx.y * BLUR_WARPS + threadIdx.y) * BLUR_SEG;
     if (x0 >= w || ys >= h) return;
     const int ye = min(ys + BLUR_SEG, h);
     const uint8_t* S = src + (size_t)blockIdx.z * plane + x0;
     uint8_t* D = dst + (size_t)blockIdx.z * plane + x0;
-    int a[4][6];
+    // Column pass two input rows at a time: P = (h[y], h[y+1]) as 16x2 lanes, and the pair's contribution to the eight output
+    // rows y-3 .. y+4 is one IDP.2A each against the tap pairs (t6,0) (t5,t6) (t4,t5) (t3,t4) (t2,t3) (t1,t2) (t0,t1) (0,t0).
+    // a[i][0..5] = running sums of output rows y-3 .. y+2 before the pair (y, y+1) is added.
+    uint32_t a[4][6];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int k = 0; k < 6; ++k) a[i][k] = 0;
-#pragma unroll 2
-    for (int y = ys - 3; y < ye + 3; ++y) {
-        const uint32_t* row = reinterpret_cast<const uint32_t*>(S + (ptrdiff_t)y * pitch);
-        const uint32_t prev = __ldg(row - 1), cur = __ldg(row), next = __ldg(row + 1);
-        uint32_t hrow[4];
-        hrow[0] = __dp4a(__byte_perm(prev, cur, 0x4321), cA, __dp4a(__byte_perm(cur, next, 0x4321), cB, 0u));
-        hrow[1] = __dp4a(__byte_perm(prev, cur, 0x5432), cA, __dp4a(__byte_perm(cur, next, 0x5432), cB, 0u));
-        hrow[2] = __dp4a(__byte_perm(prev, cur, 0x6543), cA, __dp4a(__byte_perm(cur, next, 0x6543), cB, 0u));
-        hrow[3] = __dp4a(cur, cA, __dp4a(next, cB, 0u));
-        uint32_t outw = 0;
+    // Memory-level parallelism: with ~40 warps per SM, three 128-byte loads per warp in flight are ~15 KB per SM, a third of
+    // what HBM latency x bandwidth needs.  The raw words of the NEXT four rows are therefore loaded (12 independent loads)
+    // before the current four rows are processed.
+    auto loadrow = [&](int y, uint32_t wd[3]) {  // rows beyond the margin are never needed: clamp the address
+        const uint32_t* row = reinterpret_cast<const uint32_t*>(S + (ptrdiff_t)min(y, h + 2) * pitch);
+        wd[0] = __ldg(row - 1); wd[1] = __ldg(row); wd[2] = __ldg(row + 1);
+    };
+    auto hpass = [&](const uint32_t wd[3], uint32_t hr[4]) {  // row pass of one input row
+        const uint32_t prev = wd[0], cur = wd[1], next = wd[2];
+        hr[0] = __dp4a(__byte_perm(prev, cur, 0x4321), cA, __dp4a(__byte_perm(cur, next, 0x4321), cB, 0u));
+        hr[1] = __dp4a(__byte_perm(prev, cur, 0x5432), cA, __dp4a(__byte_perm(cur, next, 0x5432), cB, 0u));
+        hr[2] = __dp4a(__byte_perm(prev, cur, 0x6543), cA, __dp4a(__byte_perm(cur, next, 0x6543), cB, 0u));
+        hr[3] = __dp4a(cur, cA, __dp4a(next, cB, 0u));
+    };
+    auto pair = [&](int y, const uint32_t wa[3], const uint32_t wb[3]) {  // input rows y, y+1 -> output rows y-3, y-2
+        uint32_t hA[4], hB[4];
+        hpass(wa, hA);
+        hpass(wb, hB);
+        uint32_t out0 = 0, out1 = 0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int hv = (int)hrow[i];
-            const int o = a[i][0] + t6 * hv;
-            a[i][0] = a[i][1] + t5 * hv;
-            a[i][1] = a[i][2] + t4 * hv;
-            a[i][2] = a[i][3] + t3 * hv;
-            a[i][3] = a[i][4] + t2 * hv;
-            a[i][4] = a[i][5] + t1 * hv;
-            a[i][5] = t0 * hv;
-            uint32_t r = (uint32_t)(o + 32768) >> 16;
-            if (SAT) r = min(r, 255u);
-            outw |= r << (8 * i);
+            const uint32_t P = __byte_perm(hA[i], hB[i], 0x5410);  // both <= 65535 (taps sum to <= 257)
+            const uint32_t o0 = __dp2a_lo(P, c67, a[i][0]);
+            const uint32_t o1 = __dp2a_lo(P, c56, a[i][1]);
+            a[i][0] = __dp2a_lo(P, c45, a[i][2]);
+            a[i][1] = __dp2a_lo(P, c34, a[i][3]);
+            a[i][2] = __dp2a_lo(P, c23, a[i][4]);
+            a[i][3] = __dp2a_lo(P, c12, a[i][5]);
+            a[i][4] = __dp2a_lo(P, c01, 0u);
+            a[i][5] = __dp2a_lo(P, c0x, 0u);
+            uint32_t r0 = (o0 + 32768u) >> 16, r1 = (o1 + 32768u) >> 16;
+            if (SAT) { r0 = min(r0, 255u); r1 = min(r1, 255u); }
+            out0 |= r0 << (8 * i);
+            out1 |= r1 << (8 * i);
         }
-        if (y >= ys + 3) *reinterpret_cast<uint32_t*>(D + (size_t)(y - 3) * pitch) = outw;
+        if (y - 3 >= ys && y - 3 < ye) *reinterpret_cast<uint32_t*>(D + (size_t)(y - 3) * pitch) = out0;
+        if (y - 2 >= ys && y - 2 < ye) *reinterpret_cast<uint32_t*>(D + (size_t)(y - 2) * pitch) = out1;
+    };
+    uint32_t cur[4][3], nxt[4][3];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) loadrow(ys - 3 + k, cur[k]);
+    for (int y = ys - 3; y <= ye + 2; y += 4) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) loadrow(y + 4 + k, nxt[k]);
+        pair(y, cur[0], cur[1]);
+        pair(y + 2, cur[2], cur[3]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { cur[k][0] = nxt[k][0]; cur[k][1] = nxt[k][1]; cur[k][2] = nxt[k][2]; }
     }
 }
 
@@ -258,12 +285,12 @@ void launch_blur(const Geom& g, const Buffers& b, int level, int nImages, const 
     for (int i = 0; i < 7; ++i) sum += taps[i];
     dim3 grid((L.w + 127) / 128, (L.h + BLUR_SEG * BLUR_WARPS - 1) / (BLUR_SEG * BLUR_WARPS), nImages), block(32, BLUR_WARPS);
     const size_t o = (size_t)L.planeOff + (size_t)b.imgBase * L.planeBytes;
+    auto pr = [&](int lo, int hi) { return (uint32_t)(lo < 0 || lo > 6 ? 0 : taps[lo]) | ((uint32_t)(hi < 0 || hi > 6 ? 0 : taps[hi]) << 8); };
+    const uint32_t c67 = pr(6, 7), c56 = pr(5, 6), c45 = pr(4, 5), c34 = pr(3, 4), c23 = pr(2, 3), c12 = pr(1, 2), c01 = pr(0, 1), c0x = pr(-1, 0);
     if (sum > 256)
-        k_blur<true><<<grid, block, 0, s>>>(b.pyr + o, b.blur + o, L.w, L.h, L.pitch, (size_t)L.planeBytes, cA, cB, taps[0], taps[1], taps[2], taps[3],
-                                           taps[4], taps[5], taps[6]);
+        k_blur<true><<<grid, block, 0, s>>>(b.pyr + o, b.blur + o, L.w, L.h, L.pitch, (size_t)L.planeBytes, cA, cB, c67, c56, c45, c34, c23, c12, c01, c0x);
     else
-        k_blur<false><<<grid, block, 0, s>>>(b.pyr + o, b.blur + o, L.w, L.h, L.pitch, (size_t)L.planeBytes, cA, cB, taps[0], taps[1], taps[2], taps[3],
-                                            taps[4], taps[5], taps[6]);
+        k_blur<false><<<grid, block, 0, s>>>(b.pyr + o, b.blur + o, L.w, L.h, L.pitch, (size_t)L.planeBytes, cA, cB, c67, c56, c45, c34, c23, c12, c01, c0x);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

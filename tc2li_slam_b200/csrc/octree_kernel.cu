@@ -19,7 +19,7 @@ namespace orbx {
 
 namespace {
 
-constexpr int OT_THREADS = 256;
+constexpr int OT_THREADS = 64;
 constexpr uint16_t NIL = 0xFFFF;
 typedef StdSortEmul<16> NodeSort;  // element = (nKeys << 12 | UL.x) << 16 | slot
 
@@ -116,11 +116,11 @@ __device__ __forceinline__ bool split_node(const OctShared& s, ListCtl& c, int n
 
 }  // namespace
 
-__global__ void __launch_bounds__(OT_THREADS) k_octree(const __grid_constant__ Geom g, const Buffers b) {
+__global__ void __launch_bounds__(OT_THREADS) k_octree(const __grid_constant__ Geom g, const Buffers b, int levelBase) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     __shared__ int sh_finish, sh_size, sh_err;
 
-    const int level = blockIdx.x, img = b.imgBase + blockIdx.y, tid = threadIdx.x;
+    const int level = levelBase + blockIdx.x, img = b.imgBase + blockIdx.y, tid = threadIdx.x;
     const LevelGeom& L = g.lv[level];
     const int cap = L.nodeCap, N = L.quota;
     const int n = min(b.candCount[img * ORBX_MAX_LEVELS + level], L.candCap);
@@ -270,11 +270,27 @@ cudaError_t octree_configure(int maxNodeCap) {
     return cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024));
 }
 
+// Levels are launched in two groups (large / small quotas) so that the small levels do not reserve the shared memory of the
+// largest one: the serial controller of a CTA is latency bound, what matters is how many CTAs are resident per SM.
 cudaError_t launch_octree(const Geom& g, const Buffers& b, int nImages, cudaStream_t s) {
     int maxCap = 0;
-    for (int l = 0; l < g.nlevels; ++l) maxCap = g.lv[l].nodeCap > maxCap ? g.lv[l].nodeCap : maxCap;
-    dim3 grid(g.nlevels, nImages);
-    k_octree<<<grid, OT_THREADS, oct_smem_bytes(maxCap), s>>>(g, b);
+    for (int l = 0; l < g.nlevels; ++l) maxCap = std::max(maxCap, g.lv[l].nodeCap);
+    // node capacities shrink with the level (quota decay): split where the capacity first drops below half of the largest
+    int split = g.nlevels;
+    for (int l = 0; l < g.nlevels; ++l)
+        if (2 * g.lv[l].nodeCap <= maxCap) { split = l; break; }
+    for (int l = split; l < g.nlevels; ++l)
+        if (2 * g.lv[l].nodeCap > maxCap) { split = g.nlevels; break; }  // not monotone: one group
+    if (split > 0) {
+        dim3 grid(split, nImages);
+        k_octree<<<grid, OT_THREADS, oct_smem_bytes(maxCap), s>>>(g, b, 0);
+    }
+    if (split < g.nlevels) {
+        int cap2 = 0;
+        for (int l = split; l < g.nlevels; ++l) cap2 = std::max(cap2, g.lv[l].nodeCap);
+        dim3 grid(g.nlevels - split, nImages);
+        k_octree<<<grid, OT_THREADS, oct_smem_bytes(cap2), s>>>(g, b, split);
+    }
     return cudaGetLastError();
 }
 

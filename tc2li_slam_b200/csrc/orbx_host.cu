@@ -496,7 +496,7 @@ int orbx_batch_run_range(orbx_batch* b, int first, int n, const int* lapping) {
         for (int l = 0; l < g.nlevels; ++l) { launch_blur(g, buf, l, n, b->taps, s); ++launches; }
     mark();
     {
-        cudaError_t e = launch_octree(g, buf, n, s); ++launches;
+        cudaError_t e = launch_octree(g, buf, n, s); launches += 2;  // two level groups
         if (e != cudaSuccess) return cuda_fail(e, "octree launch");
     }
     mark();
