@@ -208,16 +208,34 @@ void launch_margin(const Geom& g, const Buffers& b, int nImages, cudaStream_t s)
 constexpr int BLUR_SEG = 32;   // output rows per warp (6 extra rows of warm-up each)
 constexpr int BLUR_WARPS = 4;
 
+constexpr int BLUR_BOXW = 144;                  // 4 halo bytes + 128 pixels + 4 halo bytes, rounded to a multiple of 16
+constexpr int BLUR_BOXH = BLUR_SEG + 6;         // 3 rows above and below the segment
+
 template <bool SAT>
-__global__ void __launch_bounds__(32 * BLUR_WARPS) k_blur(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int w, int h, int pitch,
-                                                         size_t plane, uint32_t cA, uint32_t cB, uint32_t c67, uint32_t c56, uint32_t c45, uint32_t c34,
-                                                         uint32_t c23, uint32_t c12, uint32_t c01, uint32_t c0x) {
+__global__ void __launch_bounds__(32 * BLUR_WARPS) k_blur(const __grid_constant__ CUtensorMap srcMap, uint8_t* __restrict__ dst, int w, int h, int pitch,
+                                                         size_t plane, int imgBase, uint32_t cA, uint32_t cB, uint32_t c67, uint32_t c56, uint32_t c45,
+                                                         uint32_t c34, uint32_t c23, uint32_t c12, uint32_t c01, uint32_t c0x) {
+    // One TMA box per warp brings the warp's whole working set (144 bytes x 38 rows) into shared memory: 5.4 KB in flight per
+    // warp instead of three 128-byte loads, which is what it takes to keep HBM busy at ~40 warps per SM.
+    __shared__ __align__(128) unsigned char tile[BLUR_WARPS][(BLUR_BOXW * BLUR_BOXH + 127) / 128 * 128];
+    __shared__ __align__(8) uint64_t bars[BLUR_WARPS];
+    const int wy = threadIdx.y;
     const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4;
-    const int ys = (blockIdx.y * BLUR_WARPS + threadIdx.y) * BLUR_SEG;
-    if (x0 >= w || ys >= h) return;
+    const int ys = (blockIdx.y * BLUR_WARPS + wy) * BLUR_SEG;
+    if (threadIdx.x == 0) mbar_init(&bars[wy], 1);
+    mbar_fence_init();
+    __syncwarp();
+    if (blockIdx.x * 128 >= w || ys >= h) return;   // whole warp
+    if (threadIdx.x == 0) {
+        mbar_arrive_expect_tx(&bars[wy], BLUR_BOXW * BLUR_BOXH);
+        // box origin: byte kMarginX + x - 4 = 128 * blockIdx.x (16-byte aligned), row kMarginY + ys - 3 = ys
+        tma_load_3d(tile[wy], &srcMap, &bars[wy], blockIdx.x * 128, ys, imgBase + blockIdx.z);
+    }
+    if (x0 >= w) return;
     const int ye = min(ys + BLUR_SEG, h);
-    const uint8_t* S = src + (size_t)blockIdx.z * plane + x0;
     uint8_t* D = dst + (size_t)blockIdx.z * plane + x0;
+    mbar_wait(&bars[wy], 0);
+    const uint32_t* T = reinterpret_cast<const uint32_t*>(tile[wy]) + threadIdx.x;  // word 0 = pixels x0-4..x0-1 of box row 0 (= image row ys-3)
     // Column pass two input rows at a time: P = (h[y], h[y+1]) as 16x2 lanes, and the pair's contribution to the eight output
     // rows y-3 .. y+4 is one IDP.2A each against the tap pairs (t6,0) (t5,t6) (t4,t5) (t3,t4) (t2,t3) (t1,t2) (t0,t1) (0,t0).
     // a[i][0..5] = running sums of output rows y-3 .. y+2 before the pair (y, y+1) is added.
@@ -226,13 +244,6 @@ __global__ void __launch_bounds__(32 * BLUR_WARPS) k_blur(const uint8_t* __restr
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int k = 0; k < 6; ++k) a[i][k] = 0;
-    // Memory-level parallelism: with ~40 warps per SM, three 128-byte loads per warp in flight are ~15 KB per SM, a third of
-    // what HBM latency x bandwidth needs.  The raw words of the NEXT four rows are therefore loaded (12 independent loads)
-    // before the current four rows are processed.
-    auto loadrow = [&](int y, uint32_t wd[3]) {  // rows beyond the margin are never needed: clamp the address
-        const uint32_t* row = reinterpret_cast<const uint32_t*>(S + (ptrdiff_t)min(y, h + 2) * pitch);
-        wd[0] = __ldg(row - 1); wd[1] = __ldg(row); wd[2] = __ldg(row + 1);
-    };
     auto hpass = [&](const uint32_t wd[3], uint32_t hr[4]) {  // row pass of one input row
         const uint32_t prev = wd[0], cur = wd[1], next = wd[2];
         hr[0] = __dp4a(__byte_perm(prev, cur, 0x4321), cA, __dp4a(__byte_perm(cur, next, 0x4321), cB, 0u));
@@ -264,20 +275,15 @@ __global__ void __launch_bounds__(32 * BLUR_WARPS) k_blur(const uint8_t* __restr
         if (y - 3 >= ys && y - 3 < ye) *reinterpret_cast<uint32_t*>(D + (size_t)(y - 3) * pitch) = out0;
         if (y - 2 >= ys && y - 2 < ye) *reinterpret_cast<uint32_t*>(D + (size_t)(y - 2) * pitch) = out1;
     };
-    uint32_t cur[4][3], nxt[4][3];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) loadrow(ys - 3 + k, cur[k]);
-    for (int y = ys - 3; y <= ye + 2; y += 4) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) loadrow(y + 4 + k, nxt[k]);
-        pair(y, cur[0], cur[1]);
-        pair(y + 2, cur[2], cur[3]);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { cur[k][0] = nxt[k][0]; cur[k][1] = nxt[k][1]; cur[k][2] = nxt[k][2]; }
+    for (int y = ys - 3; y <= ye + 2; y += 2) {
+        const uint32_t* r0 = T + (y - (ys - 3)) * (BLUR_BOXW / 4);
+        const uint32_t* r1 = r0 + (y + 1 - (ys - 3) < BLUR_BOXH ? BLUR_BOXW / 4 : 0);  // the row after the last box row is never needed
+        const uint32_t wa[3] = {r0[0], r0[1], r0[2]}, wb[3] = {r1[0], r1[1], r1[2]};
+        pair(y, wa, wb);
     }
 }
 
-void launch_blur(const Geom& g, const Buffers& b, int level, int nImages, const int taps[7], cudaStream_t s) {
+void launch_blur(const Geom& g, const Buffers& b, const LevelMaps& maps, int level, int nImages, const int taps[7], cudaStream_t s) {
     const LevelGeom& L = g.lv[level];
     const uint32_t cA = (uint32_t)taps[0] | ((uint32_t)taps[1] << 8) | ((uint32_t)taps[2] << 16) | ((uint32_t)taps[3] << 24);
     const uint32_t cB = (uint32_t)taps[4] | ((uint32_t)taps[5] << 8) | ((uint32_t)taps[6] << 16);
@@ -288,9 +294,18 @@ void launch_blur(const Geom& g, const Buffers& b, int level, int nImages, const 
     auto pr = [&](int lo, int hi) { return (uint32_t)(lo < 0 || lo > 6 ? 0 : taps[lo]) | ((uint32_t)(hi < 0 || hi > 6 ? 0 : taps[hi]) << 8); };
     const uint32_t c67 = pr(6, 7), c56 = pr(5, 6), c45 = pr(4, 5), c34 = pr(3, 4), c23 = pr(2, 3), c12 = pr(1, 2), c01 = pr(0, 1), c0x = pr(-1, 0);
     if (sum > 256)
-        k_blur<true><<<grid, block, 0, s>>>(b.pyr + o, b.blur + o, L.w, L.h, L.pitch, (size_t)L.planeBytes, cA, cB, c67, c56, c45, c34, c23, c12, c01, c0x);
+        k_blur<true><<<grid, block, 0, s>>>(maps.m[level], b.blur + o, L.w, L.h, L.pitch, (size_t)L.planeBytes, b.imgBase, cA, cB, c67, c56, c45, c34, c23, c12, c01, c0x);
     else
-        k_blur<false><<<grid, block, 0, s>>>(b.pyr + o, b.blur + o, L.w, L.h, L.pitch, (size_t)L.planeBytes, cA, cB, c67, c56, c45, c34, c23, c12, c01, c0x);
+        k_blur<false><<<grid, block, 0, s>>>(maps.m[level], b.blur + o, L.w, L.h, L.pitch, (size_t)L.planeBytes, b.imgBase, cA, cB, c67, c56, c45, c34, c23, c12, c01, c0x);
+}
+
+int blur_encode_maps(const Geom& g, uint8_t* pyr, int nImages, LevelMaps* out) {
+    for (int l = 0; l < g.nlevels; ++l) {
+        const LevelGeom& L = g.lv[l];
+        const size_t blockOff = (size_t)L.planeOff - (size_t)kMarginY * L.pitch - kMarginX;
+        if (tma_encode_3d(&out->m[l], pyr + blockOff, L.pitch, L.h + 2 * kMarginY, nImages, L.planeBytes, BLUR_BOXW, BLUR_BOXH)) return -1;
+    }
+    return 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -138,6 +138,7 @@ struct orbx_batch {
     std::vector<int> hostLap;
     int fastTileRows = 0, fastTs = 64, numSMs = 148;
     FastMaps fastMaps;
+    LevelMaps blurMaps;
     DescMaps descMaps;
     uint8_t* stageIn = nullptr;  // dense device staging of uploaded images (PCIe copies of odd-width rows are ~6x slower than one contiguous copy)
     size_t stageBytes = 0;
@@ -258,6 +259,7 @@ int batch_alloc(orbx_batch* b) {
         B.cellTab = dtab;
         CU(fast_configure(b->fastTileRows, b->fastTs));
         if (fast_encode_maps(g, B.pyr, n, b->fastTs, &b->fastMaps)) return fail(ORBX_ERR_CUDA, "cuTensorMapEncodeTiled failed (FAST tiles)");
+        if (blur_encode_maps(g, B.pyr, n, &b->blurMaps)) return fail(ORBX_ERR_CUDA, "cuTensorMapEncodeTiled failed (blur tiles)");
         cudaDeviceProp prop;
         CU(cudaGetDeviceProperties(&prop, b->device));
         b->numSMs = prop.multiProcessorCount;
@@ -487,13 +489,13 @@ int orbx_batch_run_range(orbx_batch* b, int first, int n, const int* lapping) {
     if (overlap) {
         CU(cudaEventRecord(b->evPyr, s));
         CU(cudaStreamWaitEvent(b->side, b->evPyr, 0));
-        for (int l = 0; l < g.nlevels; ++l) { launch_blur(g, buf, l, n, b->taps, b->side); ++launches; }
+        for (int l = 0; l < g.nlevels; ++l) { launch_blur(g, buf, b->blurMaps, l, n, b->taps, b->side); ++launches; }
         CU(cudaEventRecord(b->evBlur, b->side));
     }
     launch_fast(g, buf, b->fastMaps, n, b->fastTileRows, b->fastTs, b->numSMs, s); ++launches;
     mark();
     if (!overlap)
-        for (int l = 0; l < g.nlevels; ++l) { launch_blur(g, buf, l, n, b->taps, s); ++launches; }
+        for (int l = 0; l < g.nlevels; ++l) { launch_blur(g, buf, b->blurMaps, l, n, b->taps, s); ++launches; }
     mark();
     {
         cudaError_t e = launch_octree(g, buf, n, s); launches += 2;  // two level groups

@@ -103,7 +103,11 @@ void make_cell_table(const Geom& g, uint4* tab, int* tileRows, int* maxCw);
 int fast_tile_stride(int maxCw);
 cudaError_t fast_configure(int tileRows, int ts);
 int fast_encode_maps(const Geom& g, uint8_t* pyr, int nImages, int ts, FastMaps* out);
-void launch_blur(const Geom& g, const Buffers& b, int level, int nImages, const int taps[7], cudaStream_t s);
+struct LevelMaps {  // one tensor map per pyramid level
+    CUtensorMap m[ORBX_MAX_LEVELS];
+};
+void launch_blur(const Geom& g, const Buffers& b, const LevelMaps& maps, int level, int nImages, const int taps[7], cudaStream_t s);
+int blur_encode_maps(const Geom& g, uint8_t* pyr, int nImages, LevelMaps* out);
 cudaError_t launch_octree(const Geom& g, const Buffers& b, int nImages, cudaStream_t s);
 void launch_assemble(const Geom& g, const Buffers& b, int nImages, cudaStream_t s);
 struct DescMaps {  // per level: 48x31 boxes of the pyramid (IC_Angle patch), 64x37 boxes of the blurred pyramid (rBRIEF window)
