@@ -79,18 +79,35 @@ __global__ void __launch_bounds__(256) k_resize(const uint8_t* __restrict__ src,
 }
 
 // Fast path for scale factors <= 1.25 (4 destination pixels then span at most 9 source bytes = 3 aligned words): each thread
-// owns 4 fixed destination columns and walks down RS_SEG rows.  Column coefficients and PRMT selectors live in registers,
-// a source row is three aligned 32-bit loads, the horizontal interpolation of a pixel is one PRMT + one IDP.2A
-// (coefficients as 16x2 against two source bytes), and the horizontally interpolated upper row is reused as the next
-// destination row's lower row whenever the source row index repeats.
+// owns 4 fixed destination columns and walks down RS_SEG rows.  The warp's whole source footprint (<= 192 bytes x 24 rows)
+// arrives with ONE TMA box load (16-byte aligned origin), so enough bytes are in flight to keep HBM busy; column
+// coefficients and PRMT selectors live in registers, a source row is three aligned 32-bit shared-memory loads, the
+// horizontal interpolation of a pixel is one PRMT + one IDP.2A (coefficients as 16x2 against two source bytes), and the
+// horizontally interpolated upper row is reused as the next destination row's lower row whenever the source row repeats.
 constexpr int RS_SEG = 16, RS_WARPS = 4;
+constexpr int RS_BOXW = 192, RS_BOXH = 24;
 
-__global__ void __launch_bounds__(32 * RS_WARPS) k_resize_s12(const uint8_t* __restrict__ src, int sh, int spitch, size_t splane,
-                                                             uint8_t* __restrict__ dst, int dw, int dh, int dpitch, size_t dplane, ResizeTab t) {
-    const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4;
-    const int ys = (blockIdx.y * RS_WARPS + threadIdx.y) * RS_SEG;
-    if (x0 >= dw || ys >= dh) return;
+__global__ void __launch_bounds__(32 * RS_WARPS) k_resize_s12(const __grid_constant__ CUtensorMap srcMap, int sh, int imgBase, uint8_t* __restrict__ dst,
+                                                             int dw, int dh, int dpitch, size_t dplane, ResizeTab t) {
+    __shared__ __align__(128) unsigned char tile[RS_WARPS][RS_BOXW * RS_BOXH];
+    __shared__ __align__(8) uint64_t bars[RS_WARPS];
+    const int wy = threadIdx.y;
+    const int xw = blockIdx.x * 128;                       // first destination column of the warp
+    const int x0 = xw + threadIdx.x * 4;
+    const int ys = (blockIdx.y * RS_WARPS + wy) * RS_SEG;
+    if (threadIdx.x == 0) mbar_init(&bars[wy], 1);
+    mbar_fence_init();
+    __syncwarp();
+    if (xw >= dw || ys >= dh) return;                      // whole warp
     const int ye = min(ys + RS_SEG, dh);
+    // box origin: the 16-byte aligned byte at or before the warp's first source pixel, the first source row of the segment
+    const int boxX = (kMarginX + (int)t.xofs[xw]) & ~15;   // byte inside the padded plane row
+    const int syMin = min(max((int)t.yofs[ys], 0), sh - 1);
+    if (threadIdx.x == 0) {
+        mbar_arrive_expect_tx(&bars[wy], RS_BOXW * RS_BOXH);
+        tma_load_3d(tile[wy], &srcMap, &bars[wy], boxX, kMarginY + syMin, imgBase + blockIdx.z);
+    }
+    if (x0 >= dw) return;
     uint32_t coef[4], sel[4];
     int base = 0;
     bool hi3 = false;
@@ -104,18 +121,19 @@ __global__ void __launch_bounds__(32 * RS_WARPS) k_resize_s12(const uint8_t* __r
         if (i == 3 && bi >= 7) { hi3 = true; bi -= 4; }
         sel[i] = (uint32_t)bi | ((uint32_t)(bi + 1) << 4);
     }
-    const uint8_t* S = src + (size_t)blockIdx.z * splane + base;
+    const unsigned char* S = tile[wy] + (kMarginX + base - boxX);  // word-aligned: the box origin is 16-byte aligned in the plane
     uint8_t* D = dst + (size_t)blockIdx.z * dplane + x0;
     int cachedRow = -1;
     uint32_t hc[4] = {0, 0, 0, 0};
     auto hrow = [&](int sy, uint32_t h[4]) {
-        const uint32_t* row = reinterpret_cast<const uint32_t*>(S + (size_t)sy * spitch);
-        const uint32_t w0 = __ldg(row), w1 = __ldg(row + 1), w2 = __ldg(row + 2);
+        const uint32_t* row = reinterpret_cast<const uint32_t*>(S + (sy - syMin) * RS_BOXW);
+        const uint32_t w0 = row[0], w1 = row[1], w2 = row[2];
         h[0] = __dp2a_lo(coef[0], __byte_perm(w0, w1, sel[0]), 0u) >> 4;
         h[1] = __dp2a_lo(coef[1], __byte_perm(w0, w1, sel[1]), 0u) >> 4;
         h[2] = __dp2a_lo(coef[2], __byte_perm(w0, w1, sel[2]), 0u) >> 4;
         h[3] = __dp2a_lo(coef[3], __byte_perm(hi3 ? w1 : w0, hi3 ? w2 : w1, sel[3]), 0u) >> 4;
     };
+    mbar_wait(&bars[wy], 0);
     for (int y = ys; y < ye; ++y) {
         const int yo = t.yofs[y];
         const int sy0 = min(max(yo, 0), sh - 1), sy1 = min(max(yo + 1, 0), sh - 1);
@@ -144,15 +162,26 @@ __global__ void __launch_bounds__(32 * RS_WARPS) k_resize_s12(const uint8_t* __r
     }
 }
 
-void launch_pyramid_level(const Geom& g, const Buffers& b, int level, const ResizeTab& tab, int nImages, cudaStream_t s) {
+// tensor maps of the SOURCE levels (level l-1 feeds level l)
+int resize_encode_maps(const Geom& g, uint8_t* pyr, int nImages, LevelMaps* out) {
+    for (int l = 0; l + 1 < g.nlevels; ++l) {
+        const LevelGeom& L = g.lv[l];
+        const size_t blockOff = (size_t)L.planeOff - (size_t)kMarginY * L.pitch - kMarginX;
+        if (tma_encode_3d(&out->m[l], pyr + blockOff, L.pitch, L.h + 2 * kMarginY, nImages, L.planeBytes, RS_BOXW, RS_BOXH)) return -1;
+    }
+    return 0;
+}
+
+void launch_pyramid_level(const Geom& g, const Buffers& b, const LevelMaps& maps, int level, const ResizeTab& tab, int nImages, cudaStream_t s) {
     const LevelGeom& S = g.lv[level - 1];
     const LevelGeom& D = g.lv[level];
-    const uint8_t* sp = b.pyr + S.planeOff + (size_t)b.imgBase * S.planeBytes;
     uint8_t* dp = b.pyr + D.planeOff + (size_t)b.imgBase * D.planeBytes;
-    if ((double)S.w <= 1.25 * D.w && (double)S.h <= 1.25 * D.h + 1 && S.w >= 16) {
+    // the box must cover the source footprint of 128 destination columns x 16 rows: scale <= 1.25 in both directions
+    if ((double)S.w <= 1.25 * D.w && (double)S.h <= 1.25 * D.h && S.w >= 16) {
         dim3 grid((D.w + 127) / 128, (D.h + RS_SEG * RS_WARPS - 1) / (RS_SEG * RS_WARPS), nImages), block(32, RS_WARPS);
-        k_resize_s12<<<grid, block, 0, s>>>(sp, S.h, S.pitch, (size_t)S.planeBytes, dp, D.w, D.h, D.pitch, (size_t)D.planeBytes, tab);
+        k_resize_s12<<<grid, block, 0, s>>>(maps.m[level - 1], S.h, b.imgBase, dp, D.w, D.h, D.pitch, (size_t)D.planeBytes, tab);
     } else {
+        const uint8_t* sp = b.pyr + S.planeOff + (size_t)b.imgBase * S.planeBytes;
         dim3 grid((D.w + 127) / 128, (D.h + 7) / 8, nImages), block(32, 8);
         k_resize<<<grid, block, 0, s>>>(sp, S.w, S.h, S.pitch, (size_t)S.planeBytes, dp, D.w, D.h, D.pitch, (size_t)D.planeBytes, tab);
     }

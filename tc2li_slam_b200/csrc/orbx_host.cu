@@ -138,7 +138,7 @@ struct orbx_batch {
     std::vector<int> hostLap;
     int fastTileRows = 0, fastTs = 64, numSMs = 148;
     FastMaps fastMaps;
-    LevelMaps blurMaps;
+    LevelMaps blurMaps, resizeMaps;
     DescMaps descMaps;
     uint8_t* stageIn = nullptr;  // dense device staging of uploaded images (PCIe copies of odd-width rows are ~6x slower than one contiguous copy)
     size_t stageBytes = 0;
@@ -260,6 +260,7 @@ int batch_alloc(orbx_batch* b) {
         CU(fast_configure(b->fastTileRows, b->fastTs));
         if (fast_encode_maps(g, B.pyr, n, b->fastTs, &b->fastMaps)) return fail(ORBX_ERR_CUDA, "cuTensorMapEncodeTiled failed (FAST tiles)");
         if (blur_encode_maps(g, B.pyr, n, &b->blurMaps)) return fail(ORBX_ERR_CUDA, "cuTensorMapEncodeTiled failed (blur tiles)");
+        if (resize_encode_maps(g, B.pyr, n, &b->resizeMaps)) return fail(ORBX_ERR_CUDA, "cuTensorMapEncodeTiled failed (resize tiles)");
         cudaDeviceProp prop;
         CU(cudaGetDeviceProperties(&prop, b->device));
         b->numSMs = prop.multiProcessorCount;
@@ -480,7 +481,7 @@ int orbx_batch_run_range(orbx_batch* b, int first, int n, const int* lapping) {
     int evi = 0;
     auto mark = [&]() { if (b->timing) cudaEventRecord(b->ev[evi++], s); };
     mark();
-    for (int l = 1; l < g.nlevels; ++l) { launch_pyramid_level(g, buf, l, b->tabs[l], n, s); ++launches; }
+    for (int l = 1; l < g.nlevels; ++l) { launch_pyramid_level(g, buf, b->resizeMaps, l, b->tabs[l], n, s); ++launches; }
     launch_margin(g, buf, n, s); ++launches;
     mark();
     // FAST -> quadtree and the blur both depend only on the pyramid: the blur goes to the side stream unless per-stage

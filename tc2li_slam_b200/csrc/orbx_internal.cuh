@@ -94,7 +94,7 @@ struct Buffers {
 
 // kernel launchers (one translation unit per stage)
 void launch_synth(uint8_t* l0, int w, int h, int pitch, size_t planeBytes, uint32_t seed0, int firstImage, int nImages, int stereo, cudaStream_t s);
-void launch_pyramid_level(const Geom& g, const Buffers& b, int level, const ResizeTab& tab, int nImages, cudaStream_t s);
+
 struct FastMaps {  // per level: {tile row bytes x (hCell + 6)} boxes of the pyramid (FAST cell crops)
     CUtensorMap m[ORBX_MAX_LEVELS];
 };
@@ -108,6 +108,8 @@ struct LevelMaps {  // one tensor map per pyramid level
 };
 void launch_blur(const Geom& g, const Buffers& b, const LevelMaps& maps, int level, int nImages, const int taps[7], cudaStream_t s);
 int blur_encode_maps(const Geom& g, uint8_t* pyr, int nImages, LevelMaps* out);
+void launch_pyramid_level(const Geom& g, const Buffers& b, const LevelMaps& maps, int level, const ResizeTab& tab, int nImages, cudaStream_t s);
+int resize_encode_maps(const Geom& g, uint8_t* pyr, int nImages, LevelMaps* out);
 cudaError_t launch_octree(const Geom& g, const Buffers& b, int nImages, cudaStream_t s);
 void launch_assemble(const Geom& g, const Buffers& b, int nImages, cudaStream_t s);
 struct DescMaps {  // per level: 48x31 boxes of the pyramid (IC_Angle patch), 64x37 boxes of the blurred pyramid (rBRIEF window)
