@@ -238,33 +238,40 @@ constexpr int BLUR_SEG = 32;   // output rows per warp (6 extra rows of warm-up 
 constexpr int BLUR_WARPS = 4;
 
 constexpr int BLUR_BOXW = 144;                  // 4 halo bytes + 128 pixels + 4 halo bytes, rounded to a multiple of 16
-constexpr int BLUR_BOXH = BLUR_SEG + 6;         // 3 rows above and below the segment
+constexpr int BLUR_BOXH = 32;                   // input rows per TMA box
+constexpr int BLUR_BOX_BYTES = BLUR_BOXW * BLUR_BOXH;  // 4608 = 36 x 128
 
 template <bool SAT>
 __global__ void __launch_bounds__(32 * BLUR_WARPS) k_blur(const __grid_constant__ CUtensorMap srcMap, uint8_t* __restrict__ dst, int w, int h, int pitch,
-                                                         size_t plane, int imgBase, uint32_t cA, uint32_t cB, uint32_t c67, uint32_t c56, uint32_t c45,
-                                                         uint32_t c34, uint32_t c23, uint32_t c12, uint32_t c01, uint32_t c0x) {
-    // One TMA box per warp brings the warp's whole working set (144 bytes x 38 rows) into shared memory: 5.4 KB in flight per
-    // warp instead of three 128-byte loads, which is what it takes to keep HBM busy at ~40 warps per SM.
-    __shared__ __align__(128) unsigned char tile[BLUR_WARPS][(BLUR_BOXW * BLUR_BOXH + 127) / 128 * 128];
-    __shared__ __align__(8) uint64_t bars[BLUR_WARPS];
+                                                         size_t plane, int imgBase, int nStrips, int nWarps, uint32_t cA, uint32_t cB, uint32_t c67,
+                                                         uint32_t c56, uint32_t c45, uint32_t c34, uint32_t c23, uint32_t c12, uint32_t c01, uint32_t c0x) {
+    // A warp owns one 128-pixel column strip of one image and walks it top to bottom.  Its input arrives as TMA boxes of
+    // 144 bytes x 32 rows, double buffered: the next box is in flight while the current one is filtered, so ~9 KB per warp
+    // are outstanding (three 128-byte loads per warp would leave HBM two thirds idle at this occupancy), and the running
+    // column sums carry across boxes, so there is no per-segment warm-up.
+    __shared__ __align__(128) unsigned char tile[BLUR_WARPS][2][BLUR_BOX_BYTES];
+    __shared__ __align__(8) uint64_t bars[BLUR_WARPS][2];
     const int wy = threadIdx.y;
-    const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4;
-    const int ys = (blockIdx.y * BLUR_WARPS + wy) * BLUR_SEG;
-    if (threadIdx.x == 0) mbar_init(&bars[wy], 1);
+    if (threadIdx.x == 0) { mbar_init(&bars[wy][0], 1); mbar_init(&bars[wy][1], 1); }
     mbar_fence_init();
     __syncwarp();
-    if (blockIdx.x * 128 >= w || ys >= h) return;   // whole warp
+    const int gw = blockIdx.x * BLUR_WARPS + wy;
+    if (gw >= nWarps) return;   // whole warp
+    const int imgRel = gw / nStrips, strip = gw - imgRel * nStrips;
+    const int x0 = (strip * 32 + threadIdx.x) * 4;
+    const int nChunks = (h + 6 + BLUR_BOXH - 1) / BLUR_BOXH;
+    auto issue = [&](int c) {  // box origin: byte kMarginX + x - 4 = 128 * strip (16-byte aligned), plane row kMarginY + (32c - 3) = 32c
+        mbar_arrive_expect_tx(&bars[wy][c & 1], BLUR_BOX_BYTES);
+        tma_load_3d(tile[wy][c & 1], &srcMap, &bars[wy][c & 1], strip * 128, c * BLUR_BOXH, imgBase + imgRel);
+    };
     if (threadIdx.x == 0) {
-        mbar_arrive_expect_tx(&bars[wy], BLUR_BOXW * BLUR_BOXH);
-        // box origin: byte kMarginX + x - 4 = 128 * blockIdx.x (16-byte aligned), row kMarginY + ys - 3 = ys
-        tma_load_3d(tile[wy], &srcMap, &bars[wy], blockIdx.x * 128, ys, imgBase + blockIdx.z);
+        issue(0);
+        if (nChunks > 1) issue(1);
     }
-    if (x0 >= w) return;
-    const int ye = min(ys + BLUR_SEG, h);
-    uint8_t* D = dst + (size_t)blockIdx.z * plane + x0;
-    mbar_wait(&bars[wy], 0);
-    const uint32_t* T = reinterpret_cast<const uint32_t*>(tile[wy]) + threadIdx.x;  // word 0 = pixels x0-4..x0-1 of box row 0 (= image row ys-3)
+    const bool active = x0 < w;
+    uint8_t* D = dst + (size_t)imgRel * plane + x0;
+    uint32_t ph0 = 0, ph1 = 0;
+    const int ys = 0, ye = h;
     // Column pass two input rows at a time: P = (h[y], h[y+1]) as 16x2 lanes, and the pair's contribution to the eight output
     // rows y-3 .. y+4 is one IDP.2A each against the tap pairs (t6,0) (t5,t6) (t4,t5) (t3,t4) (t2,t3) (t1,t2) (t0,t1) (0,t0).
     // a[i][0..5] = running sums of output rows y-3 .. y+2 before the pair (y, y+1) is added.
@@ -304,11 +311,21 @@ __global__ void __launch_bounds__(32 * BLUR_WARPS) k_blur(const __grid_constant_
         if (y - 3 >= ys && y - 3 < ye) *reinterpret_cast<uint32_t*>(D + (size_t)(y - 3) * pitch) = out0;
         if (y - 2 >= ys && y - 2 < ye) *reinterpret_cast<uint32_t*>(D + (size_t)(y - 2) * pitch) = out1;
     };
-    for (int y = ys - 3; y <= ye + 2; y += 2) {
-        const uint32_t* r0 = T + (y - (ys - 3)) * (BLUR_BOXW / 4);
-        const uint32_t* r1 = r0 + (y + 1 - (ys - 3) < BLUR_BOXH ? BLUR_BOXW / 4 : 0);  // the row after the last box row is never needed
-        const uint32_t wa[3] = {r0[0], r0[1], r0[2]}, wb[3] = {r1[0], r1[1], r1[2]};
-        pair(y, wa, wb);
+    for (int c = 0; c < nChunks; ++c) {
+        if (c & 1) { mbar_wait(&bars[wy][1], ph1); ph1 ^= 1; }
+        else { mbar_wait(&bars[wy][0], ph0); ph0 ^= 1; }
+        if (active) {
+            const uint32_t* T = reinterpret_cast<const uint32_t*>(tile[wy][c & 1]) + threadIdx.x;  // word 0 = pixels x0-4..x0-1
+            const int yb = c * BLUR_BOXH - 3;  // image row of box row 0
+#pragma unroll 2
+            for (int k = 0; k < BLUR_BOXH; k += 2) {
+                const uint32_t* r0 = T + k * (BLUR_BOXW / 4);
+                const uint32_t wa[3] = {r0[0], r0[1], r0[2]}, wb[3] = {r0[BLUR_BOXW / 4], r0[BLUR_BOXW / 4 + 1], r0[BLUR_BOXW / 4 + 2]};
+                pair(yb + k, wa, wb);
+            }
+        }
+        __syncwarp();  // every lane is done with this buffer before lane 0 re-arms it
+        if (threadIdx.x == 0 && c + 2 < nChunks) issue(c + 2);
     }
 }
 
@@ -318,14 +335,15 @@ void launch_blur(const Geom& g, const Buffers& b, const LevelMaps& maps, int lev
     const uint32_t cB = (uint32_t)taps[4] | ((uint32_t)taps[5] << 8) | ((uint32_t)taps[6] << 16);
     int sum = 0;
     for (int i = 0; i < 7; ++i) sum += taps[i];
-    dim3 grid((L.w + 127) / 128, (L.h + BLUR_SEG * BLUR_WARPS - 1) / (BLUR_SEG * BLUR_WARPS), nImages), block(32, BLUR_WARPS);
+    const int nStrips = (L.w + 127) / 128, nWarps = nStrips * nImages;
+    dim3 grid((nWarps + BLUR_WARPS - 1) / BLUR_WARPS), block(32, BLUR_WARPS);
     const size_t o = (size_t)L.planeOff + (size_t)b.imgBase * L.planeBytes;
     auto pr = [&](int lo, int hi) { return (uint32_t)(lo < 0 || lo > 6 ? 0 : taps[lo]) | ((uint32_t)(hi < 0 || hi > 6 ? 0 : taps[hi]) << 8); };
     const uint32_t c67 = pr(6, 7), c56 = pr(5, 6), c45 = pr(4, 5), c34 = pr(3, 4), c23 = pr(2, 3), c12 = pr(1, 2), c01 = pr(0, 1), c0x = pr(-1, 0);
     if (sum > 256)
-        k_blur<true><<<grid, block, 0, s>>>(maps.m[level], b.blur + o, L.w, L.h, L.pitch, (size_t)L.planeBytes, b.imgBase, cA, cB, c67, c56, c45, c34, c23, c12, c01, c0x);
+        k_blur<true><<<grid, block, 0, s>>>(maps.m[level], b.blur + o, L.w, L.h, L.pitch, (size_t)L.planeBytes, b.imgBase, nStrips, nWarps, cA, cB, c67, c56, c45, c34, c23, c12, c01, c0x);
     else
-        k_blur<false><<<grid, block, 0, s>>>(maps.m[level], b.blur + o, L.w, L.h, L.pitch, (size_t)L.planeBytes, b.imgBase, cA, cB, c67, c56, c45, c34, c23, c12, c01, c0x);
+        k_blur<false><<<grid, block, 0, s>>>(maps.m[level], b.blur + o, L.w, L.h, L.pitch, (size_t)L.planeBytes, b.imgBase, nStrips, nWarps, cA, cB, c67, c56, c45, c34, c23, c12, c01, c0x);
 }
 
 int blur_encode_maps(const Geom& g, uint8_t* pyr, int nImages, LevelMaps* out) {
