@@ -107,13 +107,12 @@ __global__ void __launch_bounds__(32 * RS_WARPS) k_resize_s12(const __grid_const
         mbar_arrive_expect_tx(&bars[wy], RS_BOXW * RS_BOXH);
         tma_load_3d(tile[wy], &srcMap, &bars[wy], boxX, kMarginY + syMin, imgBase + blockIdx.z);
     }
-    if (x0 >= dw) return;
     uint32_t coef[4], sel[4];
     int base = 0;
     bool hi3 = false;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const int x = min(x0 + i, dw - 1);
+        const int x = min(x0 + i, dw - 1);  // (inactive lanes compute with the last column, harmlessly)
         const int sx = t.xofs[x];
         coef[i] = *reinterpret_cast<const uint32_t*>(t.xa + 2 * x);  // (1-fx)*2048 | fx*2048 << 16
         if (i == 0) base = sx & ~3;
@@ -121,44 +120,48 @@ __global__ void __launch_bounds__(32 * RS_WARPS) k_resize_s12(const __grid_const
         if (i == 3 && bi >= 7) { hi3 = true; bi -= 4; }
         sel[i] = (uint32_t)bi | ((uint32_t)(bi + 1) << 4);
     }
-    const unsigned char* S = tile[wy] + (kMarginX + base - boxX);  // word-aligned: the box origin is 16-byte aligned in the plane
-    uint8_t* D = dst + (size_t)blockIdx.z * dplane + x0;
-    int cachedRow = -1;
-    uint32_t hc[4] = {0, 0, 0, 0};
-    auto hrow = [&](int sy, uint32_t h[4]) {
-        const uint32_t* row = reinterpret_cast<const uint32_t*>(S + (sy - syMin) * RS_BOXW);
-        const uint32_t w0 = row[0], w1 = row[1], w2 = row[2];
+    // 32-bit shared-window address of the thread's first word (kept in a register; explicit ld.shared below)
+    const uint32_t sBase = smem_u32(tile[wy]) + (uint32_t)(kMarginX + base - boxX) - (uint32_t)(syMin * RS_BOXW);
+    uint8_t* D = dst + (size_t)blockIdx.z * dplane + x0 + (size_t)ys * dpitch;
+    // the row tables of the segment, one row per lane, broadcast with shuffles inside the loop
+    const int myRow = min(ys + (int)threadIdx.x, dh - 1);
+    const int myYo = t.yofs[myRow];
+    const uint32_t myBw = *reinterpret_cast<const uint32_t*>(t.yb + 2 * myRow);
+    auto hrow = [&](int sy, uint32_t h[4]) {  // horizontal interpolation of source row sy, >> 4 as cv::resize does
+        uint32_t w0, w1, w2;
+        asm volatile("ld.shared.u32 %0, [%3];\n\tld.shared.u32 %1, [%3+4];\n\tld.shared.u32 %2, [%3+8];" : "=r"(w0), "=r"(w1), "=r"(w2) : "r"(sBase + (uint32_t)(sy * RS_BOXW)));
         h[0] = __dp2a_lo(coef[0], __byte_perm(w0, w1, sel[0]), 0u) >> 4;
         h[1] = __dp2a_lo(coef[1], __byte_perm(w0, w1, sel[1]), 0u) >> 4;
         h[2] = __dp2a_lo(coef[2], __byte_perm(w0, w1, sel[2]), 0u) >> 4;
         h[3] = __dp2a_lo(coef[3], __byte_perm(hi3 ? w1 : w0, hi3 ? w2 : w1, sel[3]), 0u) >> 4;
     };
     mbar_wait(&bars[wy], 0);
-    for (int y = ys; y < ye; ++y) {
-        const int yo = t.yofs[y];
+    // hA / hB: interpolated source rows rA < rB, consumed as a stream (the lower row of one destination row is usually the
+    // upper row of the next)
+    int rA = -1, rB = -1;
+    uint32_t hA[4] = {0, 0, 0, 0}, hB[4] = {0, 0, 0, 0};
+    const int nrows = ye - ys;
+    for (int k = 0; k < nrows; ++k) {
+        const int yo = __shfl_sync(0xFFFFFFFFu, myYo, k);
+        const uint32_t bw = __shfl_sync(0xFFFFFFFFu, myBw, k);
         const int sy0 = min(max(yo, 0), sh - 1), sy1 = min(max(yo + 1, 0), sh - 1);
-        const uint32_t bw = *reinterpret_cast<const uint32_t*>(t.yb + 2 * y);
-        const uint32_t b0 = bw & 0xFFFFu, b1 = bw >> 16;
-        uint32_t h0[4], h1[4];
-        if (sy0 == cachedRow) {
+        if (sy0 != rA) {
+            if (sy0 == rB) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) h0[i] = hc[i];
-        } else
-            hrow(sy0, h0);
-        if (sy1 == sy0) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) h1[i] = h0[i];
-        } else
-            hrow(sy1, h1);
-        uint32_t out = 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            hc[i] = h1[i];
-            const uint32_t v = (((b0 * h0[i]) >> 16) + ((b1 * h1[i]) >> 16) + 2) >> 2;  // <= 255 by construction
-            out |= v << (8 * i);
+                for (int i = 0; i < 4; ++i) hA[i] = hB[i];
+            } else
+                hrow(sy0, hA);
+            rA = sy0;
         }
-        cachedRow = sy1;
-        *reinterpret_cast<uint32_t*>(D + (size_t)y * dpitch) = out;
+        if (sy1 != rA && sy1 != rB) { hrow(sy1, hB); rB = sy1; }
+        const bool same = sy1 == rA;  // only when the source row index was clamped at the bottom
+        const uint32_t b0 = bw & 0xFFFFu, b1 = bw >> 16;
+        uint32_t v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = (((b0 * hA[i]) >> 16) + ((b1 * (same ? hA[i] : hB[i])) >> 16) + 2u) >> 2;  // <= 255 by construction
+        const uint32_t out = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
+        // lanes past the last column store into the row's right padding (rewritten by k_margin / never read)
+        *reinterpret_cast<uint32_t*>(D + (size_t)k * dpitch) = out;
     }
 }
 
