@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(32 * FW) k_fast_cells(const __grid_constant__ 
                 const uint32_t maskLast = 0x80808080u >> (8 * (xb0 + 4 * nW - iw));
                 auto compass = [&](int itx, int& wofs) -> uint32_t {
                     if (itx >= items) return 0u;
-                    const int y = (int)__umulhi((uint32_t)itx, magicW), cc = itx - y * nW;
+                    const int y = nW == 1 ? itx : (int)__umulhi((uint32_t)itx, magicW), cc = itx - y * nW;  // (the magic of 1 does not fit 32 bits)
                     wofs = (y + 3) * (TS / 4) + wFirst + cc;
                     const uint32_t* row = tileW + wofs;
                     const uint32_t cur = row[0], prev = row[-1], next = row[1], up = row[3 * (TS / 4)], dn = row[-3 * (TS / 4)];

@@ -192,3 +192,81 @@ def test_sort_emulation_on_device():
         keys = ((nk << 12) | ux).astype(np.uint32)
         want = po.std_sort_perm(nk, ux)
         assert np.array_equal(orbx.debug_sort(keys, on_device=True), want), n
+
+
+def test_4k_single_frame():
+    """BASELINE.json configs[3]: 3840x2160, 4000 features (136 k candidates on level 0 go through the quadtree)."""
+    img = po.synth_v1(3840, 2160, 9)
+    m, k, d = stage_compare(img, (4000, 1.2, 8, 20, 7))
+    assert 4000 <= len(k) <= 4000 + 2 * 8
+
+
+def test_euroc_stereo_with_lapping_windows():
+    """BASELINE.json configs[2]: 752x480 stereo, 1200 features, KB8-style lapping windows left {250,751} / right {0,501}
+    (Frame.cc:1090-1091): the in-window keypoints are filled from the back, monoIndex = number outside the window."""
+    W, H = 752, 480
+    left = po.synth_v1(W, H, 21)
+    right = po.synth_v1(W, H, 21, xoff=16, noise_xor=0x5bd1e995)
+    st = T.StereoORBextractor(1200, 1.2, 8, 20, 7)
+    ora = po.OracleExtractor(1200, 1.2, 8, 20, 7)
+    (ml, kl, dl), (mr, kr, dr) = st(left, right, (250, 751), (0, 501))
+    for img, lap, (m, k, d) in ((left, (250, 751), (ml, kl, dl)), (right, (0, 501), (mr, kr, dr))):
+        om, ok, od = ora(img, lap)
+        assert m == om and 0 < m < len(k)
+        assert k.tobytes() == ok.tobytes() and np.array_equal(d, od)
+        assert np.all((k["x"][:m] < lap[0]) | (k["x"][:m] > lap[1])) and np.all((k["x"][m:] >= lap[0]) & (k["x"][m:] <= lap[1]))
+    st.close()
+
+
+def test_batch_sub_ranges_and_full_size_properties():
+    """run_range on sub-ranges of a resident batch equals one run over everything; size-independent properties at the
+    benchmark's scale: counts within [nfeatures, nfeatures + 2 * nlevels], coordinates inside the FAST region, octaves sorted."""
+    W, H, N = 1241, 376, 24
+    b = T.BatchExtractor(W, H, N, 2000, 1.2, 8, 20, 7)
+    b.synth(777, N, stereo=True)
+    b.run(N)
+    k1, d1, c1, m1 = b.download(N)
+    for first in range(0, N, 7):
+        b.run_range(first, min(7, N - first))
+    k2, d2, c2, m2 = b.download(N)
+    assert np.array_equal(c1, c2) and np.array_equal(m1, m2)
+    for i in range(N):
+        assert k1[i, :c1[i]].tobytes() == k2[i, :c2[i]].tobytes() and np.array_equal(d1[i, :c1[i]], d2[i, :c2[i]])
+        kk = k1[i, :c1[i]]
+        assert 2000 <= c1[i] <= 2016 and m1[i] == c1[i]
+        assert np.all(np.diff(kk["octave"]) >= 0) and kk["octave"].min() == 0 and kk["octave"].max() == 7
+        sf = T.tables()["scale_factors"][kk["octave"]]
+        assert np.all(kk["x"] >= 19 * sf - 1e-3) and np.all(kk["x"] <= (W - 19)) and np.all(kk["y"] >= 19 * sf - 1e-3) and np.all(kk["y"] <= H - 19)
+        assert np.all((kk["angle"] >= 0) & (kk["angle"] < 360)) and np.all(kk["class_id"] == -1)
+        assert np.all(kk["response"] >= 7) and np.all(kk["response"] <= 254)
+    b.close()
+
+
+def test_random_shapes_and_parameters():
+    """Geometry edge cases (narrow last cells, one-row grids, odd pitches): 48 random shapes / parameter sets, final outputs
+    compared bit for bit with the oracle (shapes the oracle rejects as too small must be rejected identically)."""
+    rng = np.random.default_rng(2024)
+    ex_cache = {}
+    n_ok = 0
+    for trial in range(48):
+        w, h = int(rng.integers(90, 900)), int(rng.integers(90, 500))
+        if w < 0.55 * h:
+            w = h  # portrait shapes have no quadtree root in the reference (nIni == 0)
+        args = (int(rng.integers(100, 1500)), float(rng.choice([1.2, 1.2, 1.15, 1.3, 1.5])), int(rng.integers(1, 7)), int(rng.choice([20, 12, 30])), int(rng.choice([7, 5, 12])))
+        if args[4] > args[3]:
+            args = args[:4] + (args[3],)
+        img = po.synth_v1(w, h, 5000 + trial)
+        lap = (int(rng.integers(0, w)), int(rng.integers(0, w))) if trial % 3 == 0 else (0, 0)
+        om, ok, od = po.OracleExtractor(*args)(img, lap)
+        ex = T.ORBextractor(*args)
+        if om == -2:
+            with pytest.raises(T.OrbxError) as e:
+                ex(img, None, lap)
+            assert e.value.code == orbx.ERR_TOO_SMALL
+        else:
+            m, k, d = ex(img, None, lap)
+            assert m == om and len(k) == len(ok), (trial, w, h, args)
+            assert k.tobytes() == ok.tobytes() and np.array_equal(d, od), (trial, w, h, args)
+            n_ok += 1
+        ex.close()
+    assert n_ok >= 24
