@@ -264,13 +264,14 @@ def main():
         gbs = ab[k] * n_img / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
         stages[k] = {"ms": ms, "bytes_per_image": ab[k], "GBps": gbs, "frac": gbs / peak}
     dom = max(stage_ms, key=stage_ms.get)
-    launches_of = {"pyramid": ORB_ARGS[2] - 1, "fast": 1, "blur": ORB_ARGS[2], "octree": 1, "assemble": 1, "orient_describe": 1}
+    launches_of = {"pyramid": ORB_ARGS[2], "fast": 1, "blur": ORB_ARGS[2], "octree": 2, "assemble": 1, "orient_describe": 1}
     n_sets = (n_img + group - 1) // group
     dom_launch_ms = stage_ms[dom] / (launches_of[dom] * n_sets)
     dom_bytes_launch = ab[dom] * n_img / (launches_of[dom] * n_sets)
-    traffic = None
+    traffic = None  # measured DRAM read+write bytes per launch of the dominant kernel (ncu --set full, profiles/traffic.json)
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj["bytes_per_image"][dom] * n_img / (launches_of[dom] * n_sets)
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": dom_bytes_launch / (dom_launch_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
