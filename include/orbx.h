@@ -126,6 +126,9 @@ int orbx_batch_sync(orbx_batch* b);
 /* the same on a sub-range [first, first+n) of the handle's images (lapping: n x 2 ints for that range): lets a caller keep
  * many frames resident and process them in groups small enough for the 126 MB L2 */
 int orbx_batch_run_range(orbx_batch* b, int first, int n, const int* lapping);
+/* images [0, n) in chunks of `chunk` images issued round-robin over the handle's internal streams: the latency-bound stages of
+ * one chunk overlap the issue-bound stages of another.  Asynchronous like orbx_batch_run; the handle's stream waits for all chunks. */
+int orbx_batch_run_pipelined(orbx_batch* b, int n, const int* lapping, int chunk);
 /* D2H of a sub-range without waiting (pinned destinations make it truly asynchronous); orbx_batch_check() synchronises the
  * stream and reports device-side capacity errors */
 int orbx_batch_download_async(orbx_batch* b, int first, int n, orbx_keypoint* keypoints, uint8_t* descriptors, int* counts, int* mono_index);

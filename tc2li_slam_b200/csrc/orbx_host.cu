@@ -126,6 +126,11 @@ struct orbx_batch {
     cudaStream_t own = nullptr, stream = nullptr;
     cudaStream_t side = nullptr;        // blur runs here, concurrently with FAST + quadtree (both only need the pyramid)
     cudaEvent_t evPyr = nullptr, evBlur = nullptr;
+    // extra lanes for orbx_batch_run_pipelined: chunks of a resident batch are issued round-robin over the lanes so that the
+    // latency-bound stages of one chunk (quadtree) overlap the issue-bound stages of another (FAST)
+    static const int kLanes = 3;
+    cudaStream_t laneMain[kLanes] = {}, laneSide[kLanes] = {};
+    cudaEvent_t lanePyr[kLanes] = {}, laneBlur[kLanes] = {}, laneDone[kLanes] = {}, evFork = nullptr;
     std::vector<void*> allocs;
     ResizeTab tabs[ORBX_MAX_LEVELS];
     size_t pyrBytes = 0, candElems = 0;
@@ -333,6 +338,16 @@ int orbx_batch_create(int nfeatures, float scale_factor, int nlevels, int ini_th
     if ((e = cudaStreamCreateWithFlags(&b->side, cudaStreamNonBlocking)) != cudaSuccess) return bail(cuda_fail(e, "cudaStreamCreate"));
     if ((e = cudaEventCreateWithFlags(&b->evPyr, cudaEventDisableTiming)) != cudaSuccess) return bail(cuda_fail(e, "cudaEventCreate"));
     if ((e = cudaEventCreateWithFlags(&b->evBlur, cudaEventDisableTiming)) != cudaSuccess) return bail(cuda_fail(e, "cudaEventCreate"));
+    if ((e = cudaEventCreateWithFlags(&b->evFork, cudaEventDisableTiming)) != cudaSuccess) return bail(cuda_fail(e, "cudaEventCreate"));
+    for (int k = 1; k < orbx_batch::kLanes; ++k) {
+        if ((e = cudaStreamCreateWithFlags(&b->laneMain[k], cudaStreamNonBlocking)) != cudaSuccess) return bail(cuda_fail(e, "cudaStreamCreate"));
+        if ((e = cudaStreamCreateWithFlags(&b->laneSide[k], cudaStreamNonBlocking)) != cudaSuccess) return bail(cuda_fail(e, "cudaStreamCreate"));
+    }
+    for (int k = 0; k < orbx_batch::kLanes; ++k) {
+        if ((e = cudaEventCreateWithFlags(&b->lanePyr[k], cudaEventDisableTiming)) != cudaSuccess) return bail(cuda_fail(e, "cudaEventCreate"));
+        if ((e = cudaEventCreateWithFlags(&b->laneBlur[k], cudaEventDisableTiming)) != cudaSuccess) return bail(cuda_fail(e, "cudaEventCreate"));
+        if ((e = cudaEventCreateWithFlags(&b->laneDone[k], cudaEventDisableTiming)) != cudaSuccess) return bail(cuda_fail(e, "cudaEventCreate"));
+    }
     if ((r = batch_alloc(b)) != ORBX_OK) return bail(r);
     if ((e = upload_describe_constants(kPatternHost, b->p.umax)) != cudaSuccess) return bail(cuda_fail(e, "constant upload"));
     int maxCap = 0;
@@ -355,6 +370,14 @@ void orbx_batch_destroy(orbx_batch* b) {
     if (b->side) { cudaStreamSynchronize(b->side); cudaStreamDestroy(b->side); }
     if (b->evPyr) cudaEventDestroy(b->evPyr);
     if (b->evBlur) cudaEventDestroy(b->evBlur);
+    if (b->evFork) cudaEventDestroy(b->evFork);
+    for (int k = 0; k < orbx_batch::kLanes; ++k) {
+        if (b->laneMain[k]) { cudaStreamSynchronize(b->laneMain[k]); cudaStreamDestroy(b->laneMain[k]); }
+        if (b->laneSide[k]) { cudaStreamSynchronize(b->laneSide[k]); cudaStreamDestroy(b->laneSide[k]); }
+        if (b->lanePyr[k]) cudaEventDestroy(b->lanePyr[k]);
+        if (b->laneBlur[k]) cudaEventDestroy(b->laneBlur[k]);
+        if (b->laneDone[k]) cudaEventDestroy(b->laneDone[k]);
+    }
     if (b->own) cudaStreamDestroy(b->own);
     delete b;
 }
@@ -460,13 +483,12 @@ int orbx_batch_synth(orbx_batch* b, uint32_t seed0, int first, int n, int stereo
     return ORBX_OK;
 }
 
-int orbx_batch_run_range(orbx_batch* b, int first, int n, const int* lapping) {
-    int r = check_images(b, first, n);
-    if (r) return r;
-    if (n == 0) return ORBX_OK;
-    DeviceGuard dg(b->device);
+// the whole launch sequence for images [first, first+n) on lane `lane` (lane 0 = the handle's own / caller's stream)
+static int run_range_lane(orbx_batch* b, int first, int n, const int* lapping, int lane) {
     const Geom& g = b->g;
-    cudaStream_t s = b->stream;
+    cudaStream_t s = lane == 0 ? b->stream : b->laneMain[lane];
+    cudaStream_t side = lane == 0 ? b->side : b->laneSide[lane];
+    cudaEvent_t evPyr = lane == 0 ? b->evPyr : b->lanePyr[lane], evBlur = lane == 0 ? b->evBlur : b->laneBlur[lane];
     Buffers buf = b->buf;
     buf.imgBase = first;
     int launches = 0;
@@ -479,19 +501,19 @@ int orbx_batch_run_range(orbx_batch* b, int first, int n, const int* lapping) {
         CU(cudaMemsetAsync(buf.lapping + 2 * (size_t)first, 0, (size_t)n * 2 * sizeof(int), s));
     CU(cudaMemsetAsync(buf.candCount + (size_t)first * ORBX_MAX_LEVELS, 0, (size_t)n * ORBX_MAX_LEVELS * sizeof(int), s));
     int evi = 0;
-    auto mark = [&]() { if (b->timing) cudaEventRecord(b->ev[evi++], s); };
+    auto mark = [&]() { if (b->timing && lane == 0) cudaEventRecord(b->ev[evi++], s); };
     mark();
     for (int l = 1; l < g.nlevels; ++l) { launch_pyramid_level(g, buf, b->resizeMaps, l, b->tabs[l], n, s); ++launches; }
     launch_margin(g, buf, n, s); ++launches;
     mark();
     // FAST -> quadtree and the blur both depend only on the pyramid: the blur goes to the side stream unless per-stage
     // timing was requested (then everything is serialised on one stream so that the events bracket single stages)
-    const bool overlap = !b->timing;
+    const bool overlap = !b->timing || lane != 0;
     if (overlap) {
-        CU(cudaEventRecord(b->evPyr, s));
-        CU(cudaStreamWaitEvent(b->side, b->evPyr, 0));
-        for (int l = 0; l < g.nlevels; ++l) { launch_blur(g, buf, b->blurMaps, l, n, b->taps, b->side); ++launches; }
-        CU(cudaEventRecord(b->evBlur, b->side));
+        CU(cudaEventRecord(evPyr, s));
+        CU(cudaStreamWaitEvent(side, evPyr, 0));
+        for (int l = 0; l < g.nlevels; ++l) { launch_blur(g, buf, b->blurMaps, l, n, b->taps, side); ++launches; }
+        CU(cudaEventRecord(evBlur, side));
     }
     launch_fast(g, buf, b->fastMaps, n, b->fastTileRows, b->fastTs, b->numSMs, s); ++launches;
     mark();
@@ -505,10 +527,44 @@ int orbx_batch_run_range(orbx_batch* b, int first, int n, const int* lapping) {
     mark();
     launch_assemble(g, buf, n, s); ++launches;
     mark();
-    if (overlap) CU(cudaStreamWaitEvent(s, b->evBlur, 0));
+    if (overlap) CU(cudaStreamWaitEvent(s, evBlur, 0));
     launch_describe(g, buf, b->descMaps, n, s); ++launches;
     mark();
     CU(cudaGetLastError());
+    b->launches = launches;
+    b->lastImages = n;
+    return ORBX_OK;
+}
+
+int orbx_batch_run_range(orbx_batch* b, int first, int n, const int* lapping) {
+    int r = check_images(b, first, n);
+    if (r) return r;
+    if (n == 0) return ORBX_OK;
+    DeviceGuard dg(b->device);
+    return run_range_lane(b, first, n, lapping, 0);
+}
+
+// images [0, n) in chunks of `chunk` images issued round-robin over the handle's lanes (streams); returns when everything is
+// ENQUEUED; the handle's stream is made to wait for all lanes, so orbx_batch_sync / download behave as after orbx_batch_run
+int orbx_batch_run_pipelined(orbx_batch* b, int n, const int* lapping, int chunk) {
+    int r = check_images(b, 0, n);
+    if (r) return r;
+    if (n == 0) return ORBX_OK;
+    if (chunk <= 0) return fail(ORBX_ERR_ARG, "chunk must be positive");
+    DeviceGuard dg(b->device);
+    if (b->timing || chunk >= n) return run_range_lane(b, 0, n, lapping, 0);
+    CU(cudaEventRecord(b->evFork, b->stream));
+    for (int k = 1; k < orbx_batch::kLanes; ++k) CU(cudaStreamWaitEvent(b->laneMain[k], b->evFork, 0));
+    int c = 0, launches = 0;
+    for (int first = 0; first < n; first += chunk, ++c) {
+        const int m = std::min(chunk, n - first);
+        if ((r = run_range_lane(b, first, m, lapping ? lapping + 2 * (size_t)first : nullptr, c % orbx_batch::kLanes))) return r;
+        launches += b->launches;
+    }
+    for (int k = 1; k < orbx_batch::kLanes; ++k) {
+        CU(cudaEventRecord(b->laneDone[k], b->laneMain[k]));
+        CU(cudaStreamWaitEvent(b->stream, b->laneDone[k], 0));
+    }
     b->launches = launches;
     b->lastImages = n;
     return ORBX_OK;

@@ -77,6 +77,7 @@ def lib():
         "orbx_batch_download": (i, [_vp, i, _vp, _vp, _vp, _vp]),
         "orbx_batch_sync": (i, [_vp]),
         "orbx_batch_run_range": (i, [_vp, i, i, _vp]),
+        "orbx_batch_run_pipelined": (i, [_vp, i, _vp, i]),
         "orbx_batch_download_async": (i, [_vp, i, i, _vp, _vp, _vp, _vp]),
         "orbx_batch_check": (i, [_vp]),
         "orbx_event_create": (_vp, []),
@@ -437,6 +438,13 @@ class BatchExtractor:
         if lapping is not None:
             lp = np.ascontiguousarray(lapping, np.int32).reshape(n, 2)
         _check(lib().orbx_batch_run_range(self._h, first, n, _p(lp) if lp is not None else None))
+
+    def run_pipelined(self, n, chunk, lapping=None):
+        """Like run(), in chunks of `chunk` images spread over the handle's internal streams."""
+        lp = None
+        if lapping is not None:
+            lp = np.ascontiguousarray(lapping, np.int32).reshape(n, 2)
+        _check(lib().orbx_batch_run_pipelined(self._h, n, _p(lp) if lp is not None else None, int(chunk)))
 
     def sync(self):
         _check(lib().orbx_batch_sync(self._h))
