@@ -205,26 +205,35 @@ __global__ void __launch_bounds__(256) k_margin(const __grid_constant__ Geom g, 
     const int level = blockIdx.y, img = b.imgBase + blockIdx.z;
     const LevelGeom& L = g.lv[level];
     const int t = blockIdx.x * 256 + threadIdx.x;
-    const int rowItems = 6 * (L.w + 6), colItems = 6 * L.h;
-    if (t >= rowItems + colItems) return;
-    int x, y;
-    if (t < rowItems) {
-        const int r = t / (L.w + 6);
-        x = t - r * (L.w + 6) - 3;
-        y = r < 3 ? r - 3 : L.h + (r - 3);
-    } else {
-        const int u = t - rowItems;
-        y = u / 6;
-        const int c = u - y * 6;
-        x = c < 3 ? c - 3 : L.w + (c - 3);
-    }
+    const int wWords = (L.w + 3) >> 2;
+    const int rowItems = 6 * wWords, colItems = L.h + 6;
     uint8_t* P = b.pyr + L.planeOff + (size_t)img * L.planeBytes;
-    P[(ptrdiff_t)y * L.pitch + x] = P[(size_t)reflect101(y, L.h) * L.pitch + reflect101(x, L.w)];
+    if (t < rowItems) {
+        // the three rows above and below: word copies of the mirrored interior rows (-k -> k, h-1+k -> h-1-k)
+        const int r = t / wWords, c = t - r * wWords;
+        const int y = r < 3 ? r - 3 : L.h + (r - 3);
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(P + (size_t)reflect101(y, L.h) * L.pitch);
+        if (4 * c + 4 <= L.w)
+            reinterpret_cast<uint32_t*>(P + (ptrdiff_t)y * L.pitch)[c] = src[c];
+        else  // the last, partial word: bytes >= w belong to the column part below (no two writers per byte)
+            for (int x = 4 * c; x < L.w; ++x) (P + (ptrdiff_t)y * L.pitch)[x] = reinterpret_cast<const uint8_t*>(src)[x];
+    } else if (t < rowItems + colItems) {
+        // the three columns left and right of every row (margin rows included: they read their mirrored source row directly,
+        // so this part does not depend on the copies above).  Left: one word [pad, p3, p2, p1] in front of pixel 0.
+        const int y = t - rowItems - 3;
+        const uint8_t* src = P + (size_t)reflect101(y, L.h) * L.pitch;
+        uint8_t* dst = P + (ptrdiff_t)y * L.pitch;
+        const uint32_t first = *reinterpret_cast<const uint32_t*>(src);
+        *reinterpret_cast<uint32_t*>(dst - 4) = __byte_perm(first, 0, 0x1230);  // bytes: pad(=p0), p3, p2, p1
+        dst[L.w] = src[reflect101(L.w, L.w)];
+        dst[L.w + 1] = src[reflect101(L.w + 1, L.w)];
+        dst[L.w + 2] = src[reflect101(L.w + 2, L.w)];
+    }
 }
 
 void launch_margin(const Geom& g, const Buffers& b, int nImages, cudaStream_t s) {
     int maxItems = 0;
-    for (int l = 0; l < g.nlevels; ++l) maxItems = max(maxItems, 6 * (g.lv[l].w + 6) + 6 * g.lv[l].h);
+    for (int l = 0; l < g.nlevels; ++l) maxItems = max(maxItems, 6 * ((g.lv[l].w + 3) / 4) + g.lv[l].h + 6);
     dim3 grid((maxItems + 255) / 256, g.nlevels, nImages);
     k_margin<<<grid, 256, 0, s>>>(g, b);
 }
