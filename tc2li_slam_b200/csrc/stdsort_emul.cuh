@@ -22,7 +22,11 @@ namespace orbx {
 template <int KeyShift>
 struct StdSortEmul {
     typedef unsigned long long E;
-    static __host__ __device__ inline bool lt(E a, E b) { return (a >> KeyShift) < (b >> KeyShift); }
+    // KeyShift == 32: the key is the upper word, one 32-bit compare; otherwise a shifted 64-bit compare
+    static __host__ __device__ inline bool lt(E a, E b) {
+        if (KeyShift == 32) return (uint32_t)(a >> 32) < (uint32_t)(b >> 32);
+        return (a >> KeyShift) < (b >> KeyShift);
+    }
     static __host__ __device__ inline void swp(E* a, int i, int j) { E t = a[i]; a[i] = a[j]; a[j] = t; }
 
     static __host__ __device__ void unguarded_linear_insert(E* a, int last) {

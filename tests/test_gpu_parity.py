@@ -192,6 +192,13 @@ def test_sort_emulation_on_device():
         keys = ((nk << 12) | ux).astype(np.uint32)
         want = po.std_sort_perm(nk, ux)
         assert np.array_equal(orbx.debug_sort(keys, on_device=True), want), n
+        assert np.array_equal(orbx.debug_sort(keys, force_depth=-2, on_device=True), want), ("CTA-parallel emulation", n)
+    for trial in range(60):  # the CTA-parallel emulation on tie-heavy and tie-free inputs of many sizes
+        n = int(rng.integers(1, 1200))
+        nk = rng.integers(2, 2 + int(rng.integers(1, 400)), n)
+        ux = rng.integers(0, int(rng.integers(1, 80)), n) * 25
+        keys = ((nk << 12) | ux).astype(np.uint32)
+        assert np.array_equal(orbx.debug_sort(keys, force_depth=-2, on_device=True), po.std_sort_perm(nk, ux)), (trial, n)
 
 
 def test_4k_single_frame():
