@@ -22,6 +22,7 @@ namespace orbx {
 namespace {
 
 constexpr int OT_THREADS = PS_THREADS;
+constexpr int OT_SMEM_CANDS = 2048;   // candidate lists up to this size are staged in shared memory (6 bytes each)
 typedef StdSortEmul<16> NodeSort;    // element = (nKeys << 12 | UL.x) << 16 | node index: any key size
 typedef StdSortEmul<32> NodeSort32;  // element = (nKeys << 12 | UL.x) << 32 | node index: keys below 2^32 (fewer than 2^20 candidates)
 
@@ -47,7 +48,7 @@ struct OctShared {
 
 __host__ __device__ inline size_t oct_smem_bytes(int cap) {
     size_t c = (size_t)((cap + 7) & ~7);
-    return c * (2 * sizeof(Box) + 2 * 4 + 16 + 8 + 8 + 2 * 8 + 1) + 128;
+    return c * (2 * sizeof(Box) + 2 * 4 + 16 + 8 + 8 + 2 * 8 + 1) + 128 + (size_t)OT_SMEM_CANDS * 6;
 }
 
 __device__ inline OctShared carve(unsigned char* base, int capIn) {
@@ -153,8 +154,17 @@ __global__ void __launch_bounds__(OT_THREADS) k_octree(const __grid_constant__ G
         return;
     }
     const OctShared s = carve(smemRaw, cap);
-    const uint32_t* __restrict__ cand = b.cand + L.candOff + (size_t)img * L.candCap;
-    uint16_t* __restrict__ pnode = b.pnode + L.candOff + (size_t)img * L.candCap;
+    // candidates and their node labels: staged in shared memory when they fit (every round walks them twice; from global
+    // memory the kernel is bound by L2 latency at two warps per CTA), otherwise in place in global memory
+    const uint32_t* cand = b.cand + L.candOff + (size_t)img * L.candCap;
+    uint16_t* pnode = b.pnode + L.candOff + (size_t)img * L.candCap;
+    if (n <= OT_SMEM_CANDS) {
+        unsigned char* extra = smemRaw + oct_smem_bytes(cap) - (size_t)OT_SMEM_CANDS * 6;
+        uint32_t* sc = reinterpret_cast<uint32_t*>(extra);
+        for (int c = tid; c < n; c += OT_THREADS) sc[c] = cand[c];
+        cand = sc;
+        pnode = reinterpret_cast<uint16_t*>(extra + (size_t)OT_SMEM_CANDS * 4);
+    }
 
     // ---- roots (ORBextractor.cc:533-575): nIni vertical strips; empty ones are dropped ----
     const int nIni = L.nIni;
