@@ -33,7 +33,7 @@ namespace orbx {
 
 namespace {
 
-constexpr int FW = 4;                    // warps per CTA
+constexpr int FW = 1;                    // warps per CTA (every warp is independent; small CTAs pack shared memory best)
 constexpr int CAP = 512;                 // entries per list
 constexpr unsigned FULL = 0xFFFFFFFFu;
 
@@ -395,7 +395,7 @@ int fast_encode_maps(const Geom& g, uint8_t* pyr, int nImages, int ts, FastMaps*
 
 void launch_fast(const Geom& g, const Buffers& b, const FastMaps& maps, int nImages, int tileRows, int ts, int numSMs, cudaStream_t s) {
     const size_t smem = FW * fast_warp_bytes(tileRows, ts);
-    const int ctasPerSM = std::max(1, std::min(8, (int)((220 * 1024) / (smem + 1024))));
+    const int ctasPerSM = std::max(1, std::min(32, (int)((227 * 1024) / (smem + 1024 + 64))));
     const int nWork = g.cellsPerImage * nImages;
     const int grid = std::min((nWork + FW - 1) / FW, numSMs * ctasPerSM);
     if (ts == 64)
