@@ -277,3 +277,26 @@ def test_random_shapes_and_parameters():
             n_ok += 1
         ex.close()
     assert n_ok >= 24
+
+
+def test_large_resident_batch_spot_checks():
+    """A resident batch at benchmark scale (1024 device-generated KITTI-shaped images, one launch set, then the pipelined
+    multi-stream variant): every image within the count bounds, 16 random images compared bit for bit with the oracle."""
+    W, H, N = 1241, 376, 1024
+    b = T.BatchExtractor(W, H, N, 2000, 1.2, 8, 20, 7)
+    b.synth(31337, N, stereo=True)
+    b.run(N)
+    kps, desc, cnt, mono = b.download(N)
+    assert cnt.min() >= 2000 and cnt.max() <= 2016 and np.array_equal(cnt, mono)
+    b.run_pipelined(N, 128)
+    kps2, desc2, cnt2, _ = b.download(N)
+    assert np.array_equal(cnt, cnt2)
+    ora = po.OracleExtractor(2000, 1.2, 8, 20, 7)
+    rng = np.random.default_rng(7)
+    for i in rng.choice(N, 16, replace=False):
+        seed = 31337 + i // 2
+        img = po.synth_v1(W, H, seed, 16, 0x5bd1e995) if i & 1 else po.synth_v1(W, H, seed)
+        om, ok, od = ora(img)
+        for kk, dd, cc in ((kps, desc, cnt), (kps2, desc2, cnt2)):
+            assert cc[i] == len(ok) and kk[i, :cc[i]].tobytes() == ok.tobytes() and np.array_equal(dd[i, :cc[i]], od), int(i)
+    b.close()
