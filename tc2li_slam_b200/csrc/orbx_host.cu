@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -141,6 +142,7 @@ struct orbx_batch {
     int launches = 0;
     int lastImages = 0;
     std::vector<int> hostLap;
+    bool lapStable = false;   // the `lapping` pointer given to run stays valid and pinned (single-image handle): copy from it directly
     int fastTileRows = 0, fastTs = 64, numSMs = 148;
     FastMaps fastMaps;
     LevelMaps blurMaps, resizeMaps;
@@ -492,7 +494,9 @@ static int run_range_lane(orbx_batch* b, int first, int n, const int* lapping, i
     Buffers buf = b->buf;
     buf.imgBase = first;
     int launches = 0;
-    if (lapping) {
+    if (lapping && b->lapStable) {
+        CU(cudaMemcpyAsync(buf.lapping + 2 * (size_t)first, lapping, (size_t)n * 2 * sizeof(int), cudaMemcpyHostToDevice, s));
+    } else if (lapping) {
         // (the staging vector must stay untouched until the copy has run: one slot per image of the handle)
         b->hostLap.resize(2 * (size_t)b->maxImages);
         std::memcpy(b->hostLap.data() + 2 * (size_t)first, lapping, 2 * (size_t)n * sizeof(int));
@@ -843,16 +847,25 @@ struct orbx_extractor {
     // pinned staging so that H2D / D2H are truly asynchronous with respect to the other handle of a stereo pair
     uint8_t* pinImg = nullptr; size_t pinImgBytes = 0;
     orbx_keypoint* pinKps = nullptr; uint8_t* pinDesc = nullptr; int* pinCnt = nullptr; size_t pinK = 0;
+    // The whole per-image sequence (H2D, 21 kernels on two streams, D2H) is launch-bound for one image: after a first eager
+    // call it is captured once into a CUDA graph and replayed; pinCnt[4..5] is the pinned lapping window the graph reads.
+    cudaGraphExec_t exec = nullptr;
+    int graphState = 0;  // 0: next call runs eagerly (lazy allocations), 1: capture on the next call, 2: replay `exec`, 3: capture failed, stay eager
 };
 
 namespace {
 
 int extractor_prepare(orbx_extractor* h, int w, int hgt) {
-    if (h->b && (h->b->width != w || h->b->height != hgt)) { orbx_batch_destroy(h->b); h->b = nullptr; }
+    if (h->b && (h->b->width != w || h->b->height != hgt)) {
+        if (h->exec) { cudaGraphExecDestroy(h->exec); h->exec = nullptr; }
+        h->graphState = 0;
+        orbx_batch_destroy(h->b); h->b = nullptr;
+    }
     if (!h->b) {
         int r = orbx_batch_create(h->p.nfeatures, h->p.scaleFactorF, h->p.nlevels, h->p.iniTh, h->p.minTh, h->device, w, hgt, 1, &h->b);
         if (r) return r;
         orbx_batch_set_blur_taps(h->b, h->taps);
+        h->b->lapStable = true;
     }
     DeviceGuard dg(h->device);
     const size_t need = (size_t)w * hgt;
@@ -870,21 +883,18 @@ int extractor_prepare(orbx_extractor* h, int w, int hgt) {
         h->pinKps = nullptr; h->pinDesc = nullptr; h->pinCnt = nullptr; h->pinK = 0;
         CU(cudaHostAlloc((void**)&h->pinKps, K * sizeof(orbx_keypoint), cudaHostAllocDefault));
         CU(cudaHostAlloc((void**)&h->pinDesc, K * 32, cudaHostAllocDefault));
-        CU(cudaHostAlloc((void**)&h->pinCnt, 4 * sizeof(int), cudaHostAllocDefault));
+        CU(cudaHostAlloc((void**)&h->pinCnt, 8 * sizeof(int), cudaHostAllocDefault));
         h->pinK = K;
     }
     return ORBX_OK;
 }
 
 // stage + enqueue everything for one image; nothing waits here
-int extractor_issue(orbx_extractor* h, const uint8_t* image, int w, int hgt, size_t stride, int lap0, int lap1) {
-    int r = extractor_prepare(h, w, hgt);
-    if (r) return r;
-    for (int y = 0; y < hgt; ++y) std::memcpy(h->pinImg + (size_t)y * w, image + (size_t)y * stride, (size_t)w);
+// everything one image needs, enqueued on the handle's streams (also the body of the captured graph)
+int extractor_enqueue(orbx_extractor* h, int w, int hgt) {
+    int r;
     if ((r = orbx_batch_upload(h->b, h->pinImg, (size_t)w, (size_t)w * hgt, 0, 1))) return r;
-    const int lap[2] = {lap0, lap1};
-    if ((r = orbx_batch_run(h->b, 1, lap))) return r;
-    DeviceGuard dg(h->device);
+    if ((r = orbx_batch_run(h->b, 1, h->pinCnt + 4))) return r;
     orbx_batch* b = h->b;
     cudaStream_t s = b->stream;
     const size_t K = (size_t)b->g.K;
@@ -893,6 +903,38 @@ int extractor_issue(orbx_extractor* h, const uint8_t* image, int w, int hgt, siz
     CU(cudaMemcpyAsync(h->pinCnt, b->buf.outCount, sizeof(int), cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(h->pinCnt + 1, b->buf.outMono, sizeof(int), cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(h->pinCnt + 2, b->buf.errFlag, sizeof(int), cudaMemcpyDeviceToHost, s));
+    return ORBX_OK;
+}
+
+// stage + enqueue everything for one image; nothing waits here
+int extractor_issue(orbx_extractor* h, const uint8_t* image, int w, int hgt, size_t stride, int lap0, int lap1) {
+    int r = extractor_prepare(h, w, hgt);
+    if (r) return r;
+    for (int y = 0; y < hgt; ++y) std::memcpy(h->pinImg + (size_t)y * w, image + (size_t)y * stride, (size_t)w);
+    h->pinCnt[4] = lap0; h->pinCnt[5] = lap1;
+    DeviceGuard dg(h->device);
+    orbx_batch* b = h->b;
+    static const bool noGraph = std::getenv("ORBX_NO_GRAPH") != nullptr;
+    if (noGraph || b->timing || b->stream != b->own) return extractor_enqueue(h, w, hgt);
+    if (h->graphState == 0) { h->graphState = 1; return extractor_enqueue(h, w, hgt); }  // first call eager: lazy allocations happen here
+    if (h->graphState == 3) return extractor_enqueue(h, w, hgt);
+    if (h->graphState == 1) {
+        cudaGraph_t graph = nullptr;
+        CU(cudaStreamBeginCapture(b->stream, cudaStreamCaptureModeThreadLocal));
+        r = extractor_enqueue(h, w, hgt);
+        const cudaError_t e = cudaStreamEndCapture(b->stream, &graph);
+        cudaError_t e2 = cudaErrorUnknown;
+        if (r == ORBX_OK && e == cudaSuccess && graph) e2 = cudaGraphInstantiate(&h->exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (e2 != cudaSuccess) {
+            h->exec = nullptr;
+            h->graphState = 3;
+            cudaGetLastError();
+            return extractor_enqueue(h, w, hgt);
+        }
+        h->graphState = 2;
+    }
+    CU(cudaGraphLaunch(h->exec, b->stream));
     return ORBX_OK;
 }
 
@@ -936,6 +978,7 @@ int orbx_create(int nfeatures, float scale_factor, int nlevels, int ini_th_fast,
 
 void orbx_destroy(orbx_extractor* h) {
     if (!h) return;
+    if (h->exec) cudaGraphExecDestroy(h->exec);
     if (h->b) orbx_batch_destroy(h->b);
     if (h->pinImg) cudaFreeHost(h->pinImg);
     if (h->pinKps) cudaFreeHost(h->pinKps);
@@ -971,6 +1014,8 @@ int orbx_max_keypoints(const orbx_extractor* h) {
 int orbx_set_blur_taps(orbx_extractor* h, const int taps[7]) {
     if (!h || !taps) return fail(ORBX_ERR_ARG, "null argument");
     std::memcpy(h->taps, taps, sizeof(h->taps));
+    if (h->exec) { cudaGraphExecDestroy(h->exec); h->exec = nullptr; }  // the taps are baked into the captured kernel arguments
+    if (h->graphState == 2) h->graphState = 1;
     if (h->b) return orbx_batch_set_blur_taps(h->b, taps);
     return ORBX_OK;
 }
