@@ -35,7 +35,7 @@ inline int cvCeil(double v) { int i = (int)v; return i + (i < v); }
 
 namespace cv {
 
-enum { BORDER_REFLECT_101 = 4, BORDER_ISOLATED = 16, INTER_LINEAR = 1 };
+enum { BORDER_REFLECT_101 = 4, BORDER_ISOLATED = 16, INTER_LINEAR = 1, NORM_L1 = 2 };
 
 template <typename T>
 struct Point_ {
@@ -109,6 +109,8 @@ public:
     template <typename T> const T& at(int y, int x) const { return *(const T*)(data + (size_t)y * step.v + x); }
     uchar* ptr(int y = 0) { return data + (size_t)y * step.v; }
     const uchar* ptr(int y = 0) const { return data + (size_t)y * step.v; }
+    template <typename T> T* ptr(int y = 0) { return (T*)(data + (size_t)y * step.v); }
+    template <typename T> const T* ptr(int y = 0) const { return (const T*)(data + (size_t)y * step.v); }
     bool sameBuffer(const Mat& o) const { return buf && buf == o.buf; }
 
 private:
@@ -182,6 +184,17 @@ inline void FAST(const Mat& img, std::vector<KeyPoint>& kps, int threshold, bool
     std::vector<int> xys((size_t)cap * 3);
     const int n = orbo_fast(img.data, img.cols, img.rows, (int)img.step.v, threshold, xys.data(), cap);
     for (int i = 0; i < n; ++i) kps.push_back(KeyPoint((float)xys[3 * i], (float)xys[3 * i + 1], 7.f, -1.f, (float)xys[3 * i + 2]));
+}
+
+// cv::norm(a, b, NORM_L1) on equally sized 8-bit matrices: sum of absolute differences (as double, like OpenCV)
+inline double norm(const Mat& a, const Mat& b, int type) {
+    assert(type == NORM_L1 && a.rows == b.rows && a.cols == b.cols);
+    long long s = 0;
+    for (int y = 0; y < a.rows; ++y) {
+        const uchar *pa = a.ptr(y), *pb = b.ptr(y);
+        for (int x = 0; x < a.cols; ++x) s += pa[x] > pb[x] ? pa[x] - pb[x] : pb[x] - pa[x];
+    }
+    return (double)s;
 }
 
 struct KeyPointsFilter {  // only referenced by the reference's dead ComputeKeyPointsOld

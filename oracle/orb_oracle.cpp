@@ -576,6 +576,107 @@ struct Extractor {
     }
 };
 
+// ---------------------------------------------------------------------------------------------
+// Frame::ComputeStereoMatches (slam_framework/src/Frame.cc:841-1011) restated: row-banded Hamming search of the right
+// keypoints (ORBmatcher::DescriptorDistance, ORBmatcher.cc:2067-2083; TH_HIGH 100, TH_LOW 50, ORBmatcher.cc:44-45), 11x11 SAD
+// refinement over 11 shifts on the pyramid level of the left keypoint, parabola fit, median-based outlier rejection.
+// uRight / depth = -1 where the left keypoint has no match.
+// ---------------------------------------------------------------------------------------------
+inline int hamming256(const uint8_t* a, const uint8_t* b) {
+    int d = 0;
+    for (int i = 0; i < 32; ++i) d += __builtin_popcount((unsigned)(a[i] ^ b[i]));
+    return d;
+}
+
+void stereo_match(const Extractor& L, const Extractor& R, float mb, float mbf, std::vector<float>& uRight, std::vector<float>& depth) {
+    const int N = (int)L.kps.size(), Nr = (int)R.kps.size();
+    uRight.assign(N, -1.0f);
+    depth.assign(N, -1.0f);
+    if (N == 0 || L.pyr.empty()) return;
+    const int thOrbDist = (100 + 50) / 2;
+    const int nRows = L.pyr[0].h;
+    std::vector<std::vector<int>> rows(nRows);
+    for (int iR = 0; iR < Nr; ++iR) {
+        const KeyPoint& kp = R.kps[iR];
+        const float r = 2.0f * R.sf[kp.octave];
+        const int maxr = (int)std::ceil(kp.y + r), minr = (int)std::floor(kp.y - r);
+        for (int yi = minr; yi <= maxr; ++yi)
+            if (yi >= 0 && yi < nRows) rows[yi].push_back(iR);  // (always inside for valid keypoints)
+    }
+    const float minZ = mb, minD = 0, maxD = mbf / minZ;
+    std::vector<std::pair<int, int>> distIdx;
+    for (int iL = 0; iL < N; ++iL) {
+        const KeyPoint& kpL = L.kps[iL];
+        const int levelL = kpL.octave;
+        const float vL = kpL.y, uL = kpL.x;
+        const std::vector<int>& cands = rows[(size_t)vL];
+        if (cands.empty()) continue;
+        const float minU = uL - maxD, maxU = uL - minD;
+        if (maxU < 0) continue;
+        int bestDist = 100;
+        int bestIdxR = 0;
+        const uint8_t* dL = &L.desc[(size_t)iL * 32];
+        for (int iR : cands) {
+            const KeyPoint& kpR = R.kps[iR];
+            if (kpR.octave < levelL - 1 || kpR.octave > levelL + 1) continue;
+            const float uR = kpR.x;
+            if (uR >= minU && uR <= maxU) {
+                const int dist = hamming256(dL, &R.desc[(size_t)iR * 32]);
+                if (dist < bestDist) { bestDist = dist; bestIdxR = iR; }
+            }
+        }
+        if (bestDist < thOrbDist) {
+            const float uR0 = R.kps[bestIdxR].x;
+            const float scaleFactor = L.isf[kpL.octave];
+            const float scaleduL = std::round(kpL.x * scaleFactor), scaledvL = std::round(kpL.y * scaleFactor), scaleduR0 = std::round(uR0 * scaleFactor);
+            const int w = 5, Lw = 5;
+            const Plane& PL = L.pyr[kpL.octave];
+            const Plane& PR = R.pyr[kpL.octave];
+            int best = 2147483647, bestincR = 0;
+            float vDists[11];
+            const float iniu = scaleduR0 + Lw - w, endu = scaleduR0 + Lw + w + 1;
+            if (iniu < 0 || endu >= PR.w) continue;
+            const int y0 = (int)(scaledvL - w), xl0 = (int)(scaleduL - w);
+            for (int incR = -Lw; incR <= Lw; ++incR) {
+                const int xr0 = (int)(scaleduR0 + incR - w);
+                int sad = 0;
+                for (int yy = 0; yy < 2 * w + 1; ++yy) {
+                    const uint8_t* a = PL.row(y0 + yy) + xl0;
+                    const uint8_t* b = PR.row(y0 + yy) + xr0;
+                    for (int xx = 0; xx < 2 * w + 1; ++xx) sad += std::abs((int)a[xx] - (int)b[xx]);
+                }
+                const float dist = (float)sad;  // cv::norm(IL, IR, NORM_L1) as float
+                if (dist < best) { best = (int)dist; bestincR = incR; }
+                vDists[Lw + incR] = dist;
+            }
+            if (bestincR == -Lw || bestincR == Lw) continue;
+            const float dist1 = vDists[Lw + bestincR - 1], dist2 = vDists[Lw + bestincR], dist3 = vDists[Lw + bestincR + 1];
+            const float deltaR = (dist1 - dist3) / (2.0f * (dist1 + dist3 - 2.0f * dist2));
+            if (deltaR < -1 || deltaR > 1) continue;
+            float bestuR = L.sf[kpL.octave] * ((float)scaleduR0 + (float)bestincR + deltaR);
+            float disparity = (uL - bestuR);
+            if (disparity >= minD && disparity < maxD) {
+                if (disparity <= 0) {
+                    disparity = 0.01;
+                    bestuR = uL - 0.01;
+                }
+                depth[iL] = mbf / disparity;
+                uRight[iL] = bestuR;
+                distIdx.push_back(std::pair<int, int>(best, iL));
+            }
+        }
+    }
+    if (distIdx.empty()) return;  // (the reference indexes an empty vector here)
+    std::sort(distIdx.begin(), distIdx.end());
+    const float median = distIdx[distIdx.size() / 2].first;
+    const float thDist = 1.5f * 1.4f * median;
+    for (int i = (int)distIdx.size() - 1; i >= 0; --i) {
+        if (distIdx[i].first < thDist) break;
+        uRight[distIdx[i].second] = -1;
+        depth[distIdx[i].second] = -1;
+    }
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -622,6 +723,12 @@ int orbo_num_selected(void* h, int l) { return (int)((Extractor*)h)->selected[l]
 void orbo_get_selected(void* h, int l, void* out) {
     Extractor* e = (Extractor*)h;
     if (!e->selected[l].empty()) std::memcpy(out, e->selected[l].data(), e->selected[l].size() * sizeof(KeyPoint));
+}
+int orbo_stereo_match(void* hl, void* hr, float mb, float mbf, float* uright, float* depth) {
+    std::vector<float> u, d;
+    stereo_match(*(Extractor*)hl, *(Extractor*)hr, mb, mbf, u, d);
+    if (!u.empty()) { std::memcpy(uright, u.data(), u.size() * 4); std::memcpy(depth, d.data(), d.size() * 4); }
+    return (int)u.size();
 }
 // primitives, for direct checks against cv2
 void orbo_synth_v1(uint8_t* out, int W, int H, uint32_t seed, int xoff, uint32_t noise_xor) { synth_v1(out, W, H, seed, xoff, noise_xor); }

@@ -47,6 +47,7 @@ def lib():
         L.orbo_num_fallback_cells.argtypes = [C.c_void_p, C.c_int]
         L.orbo_num_selected.argtypes = [C.c_void_p, C.c_int]
         L.orbo_get_selected.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.orbo_stereo_match.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
         L.orbo_synth_v1.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_uint32]
         L.orbo_resize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.orbo_blur.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
@@ -110,6 +111,15 @@ def std_sort_perm(nkeys, ulx):
     b = np.ascontiguousarray(ulx, np.int32).copy()
     lib().orbo_std_sort_pairs(_p(a), _p(b), len(a))
     return a
+
+
+def stereo_match(left, right, mb, mbf):
+    """Frame::ComputeStereoMatches (Frame.cc:841-1011) on the last images extracted by two OracleExtractors.
+    Returns (uRight, depth), float32 [N_left], -1 where unmatched."""
+    n = lib().orbo_num_keypoints(left._h)
+    u, d = np.empty(n, np.float32), np.empty(n, np.float32)
+    lib().orbo_stereo_match(left._h, right._h, float(mb), float(mbf), _p(u), _p(d))
+    return u, d
 
 
 class OracleExtractor:

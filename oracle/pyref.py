@@ -86,3 +86,36 @@ class RefExtractor:
         out = np.empty((h.value + 2 * border, w.value + 2 * border), np.uint8)
         lib().refo_get_level(self._h, l, border, _p(out))
         return out
+
+
+_LIB_STEREO = os.path.join(_HERE, "_ref", "libref_stereo.so")
+_slib = None
+
+
+def stereo_available():
+    return os.path.exists(_LIB_STEREO)
+
+
+def stereo_match(kps_l, desc_l, kps_r, desc_r, pyr_l, pyr_r, scale_factors, inv_scale_factors, mb, mbf):
+    """The reference's own Frame::ComputeStereoMatches (Frame.cc:841-1011, built by oracle/tools/gen_ref_stereo.py) on explicit
+    inputs: keypoints/descriptors of both images and both pyramids (lists of contiguous uint8 levels)."""
+    global _slib
+    if _slib is None:
+        C.CDLL(os.path.join(_HERE, "liborb_oracle.so"), mode=C.RTLD_GLOBAL)
+        _slib = C.CDLL(_LIB_STEREO)
+        _slib.refs_stereo_match.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    nl = len(pyr_l)
+    pl = [np.ascontiguousarray(p, np.uint8) for p in pyr_l]
+    pr = [np.ascontiguousarray(p, np.uint8) for p in pyr_r]
+    ptr_l = (C.c_void_p * nl)(*[p.ctypes.data for p in pl])
+    ptr_r = (C.c_void_p * nl)(*[p.ctypes.data for p in pr])
+    w = np.array([p.shape[1] for p in pl], np.int32)
+    h = np.array([p.shape[0] for p in pl], np.int32)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    isf = np.ascontiguousarray(inv_scale_factors, np.float32)
+    kl, kr = np.ascontiguousarray(kps_l), np.ascontiguousarray(kps_r)
+    dl, dr = np.ascontiguousarray(desc_l, np.uint8), np.ascontiguousarray(desc_r, np.uint8)
+    u, d = np.empty(len(kl), np.float32), np.empty(len(kl), np.float32)
+    _slib.refs_stereo_match(_p(kl), len(kl), _p(dl), _p(kr), len(kr), _p(dr), nl, ptr_l, ptr_r, _p(w), _p(h), _p(sf), _p(isf), float(mb), float(mbf), _p(u), _p(d))
+    return u, d

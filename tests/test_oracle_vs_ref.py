@@ -74,3 +74,22 @@ def test_many_seeds_kitti():
         rm, rk, rd = ref(img)
         om, ok, od = ora(img)
         assert rm == om and rk.tobytes() == ok.tobytes() and np.array_equal(rd, od), seed
+
+
+@pytest.mark.skipif(not pyref.stereo_available(), reason="oracle/_ref/libref_stereo.so not built")
+@pytest.mark.parametrize("w,h,seed,args,mb,mbf", [(1241, 376, 7, (2000, 1.2, 8, 20, 7), 0.5372, 387.5744), (1241, 376, 8, (2000, 1.2, 8, 12, 7), 0.5372, 387.5744),
+                                                    (752, 480, 9, (1200, 1.2, 8, 20, 7), 0.11, 47.9), (640, 200, 10, (500, 1.2, 6, 20, 7), 0.3, 120.0),
+                                                    (1241, 376, 11, (2000, 1.2, 8, 20, 7), 0.2, 60.0)])
+def test_stereo_match_restatement_equals_reference_function(w, h, seed, args, mb, mbf):
+    """oracle stereo_match vs the reference's own Frame::ComputeStereoMatches + ORBmatcher::DescriptorDistance (verbatim
+    function bodies compiled around a stand-in Frame): uRight and depth bit-identical, including the unmatched (-1) entries."""
+    left, right = po.OracleExtractor(*args), po.OracleExtractor(*args)
+    ml, kl, dl = left(po.synth_v1(w, h, seed))
+    mr, kr, dr = right(po.synth_v1(w, h, seed, 16, 0x5bd1e995))
+    ou, od = po.stereo_match(left, right, mb, mbf)
+    t = left.tables()
+    nl = args[2]
+    ru, rd = pyref.stereo_match(kl, dl, kr, dr, [left.level(l) for l in range(nl)], [right.level(l) for l in range(nl)],
+                                t["scale_factors"], t["inv_scale_factors"], mb, mbf)
+    assert (ou >= 0).sum() > 50
+    assert np.array_equal(ou.view(np.uint32), ru.view(np.uint32)) and np.array_equal(od.view(np.uint32), rd.view(np.uint32))
