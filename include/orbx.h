@@ -84,6 +84,15 @@ int orbx_extract_stereo(orbx_extractor* left, orbx_extractor* right, const uint8
                         orbx_keypoint* kps_left, uint8_t* desc_left, int cap_left, int* n_left, int* mono_left,
                         orbx_keypoint* kps_right, uint8_t* desc_right, int cap_right, int* n_right, int* mono_right);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Next step of the caller: replaces Frame::ComputeStereoMatches (Frame.cc:841-1011) and the
+ * ORBmatcher::DescriptorDistance calls inside it (ORBmatcher.cc:2067-2083) for the stereo pair last extracted by `left` and
+ * `right`; keypoints, descriptors and both pyramids stay on the device.  mb, mbf = Frame::mb / Frame::mbf (baseline in
+ * metres, baseline * fx).  uright[capacity] / depth[capacity] receive Frame::mvuRight / Frame::mvDepth for the *n_left
+ * left keypoints (-1 = no match).  Bit-identical to the reference.
+ * ---------------------------------------------------------------------------------------------------------------- */
+int orbx_stereo_match(orbx_extractor* left, orbx_extractor* right, float mb, float mbf, float* uright, float* depth, int capacity, int* n_left);
+
 /* replace the public member mvImagePyramid (ORBextractor.h:92), read by Frame::ComputeStereoMatches
  * (Frame.cc:848,938,948,953): size and (lazy) device->host copy of level `level` of the last extracted image.
  * border = 0 copies w x h pixels to dst; border = 19 writes the (w+38) x (h+38) BORDER_REFLECT_101 image the
@@ -122,6 +131,10 @@ int orbx_batch_run(orbx_batch* b, int n_images, const int* lapping);
 /* async D2H of the results + stream synchronisation.  keypoints [n_images][K], descriptors [n_images][K][32],
  * counts [n_images], mono_index [n_images]; any pointer may be NULL to skip that array. */
 int orbx_batch_download(orbx_batch* b, int n_images, orbx_keypoint* keypoints, uint8_t* descriptors, int* counts, int* mono_index);
+/* batched Frame::ComputeStereoMatches: image 2f = left, 2f+1 = right image of frame f (after orbx_batch_run of those images).
+ * orbx_batch_download_stereo: uright / depth [n_frames][K] floats (K = orbx_batch_max_keypoints), -1 = no match; synchronises. */
+int orbx_batch_stereo_match(orbx_batch* b, int n_frames, float mb, float mbf);
+int orbx_batch_download_stereo(orbx_batch* b, int n_frames, float* uright, float* depth);
 int orbx_batch_sync(orbx_batch* b);
 /* the same on a sub-range [first, first+n) of the handle's images (lapping: n x 2 ints for that range): lets a caller keep
  * many frames resident and process them in groups small enough for the 126 MB L2 */

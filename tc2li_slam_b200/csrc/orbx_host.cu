@@ -246,6 +246,8 @@ int batch_alloc(orbx_batch* b) {
     if ((r = dev_alloc(b, &B.work, (size_t)n * g.K))) return r;
     if ((r = dev_alloc(b, &B.outCount, (size_t)n))) return r;
     if ((r = dev_alloc(b, &B.outMono, (size_t)n))) return r;
+    if ((r = dev_alloc(b, &B.uRight, (size_t)n * g.K))) return r;
+    if ((r = dev_alloc(b, &B.depth, (size_t)n * g.K))) return r;
     if ((r = dev_alloc(b, &B.errFlag, 1))) return r;
     B.imgBase = 0;
     for (int l = 0; l < g.nlevels; ++l) {
@@ -272,6 +274,7 @@ int batch_alloc(orbx_batch* b) {
         CU(cudaGetDeviceProperties(&prop, b->device));
         b->numSMs = prop.multiProcessorCount;
         CU(describe_configure());
+        if (stereo_smem_bytes(g.K, g.lv[0].h) <= 220 * 1024) CU(stereo_configure(g.K, g.lv[0].h));
     }
     CU(cudaMemset(B.errFlag, 0, sizeof(int)));
     CU(cudaMemset(B.lapping, 0, (size_t)n * 2 * sizeof(int)));
@@ -575,6 +578,39 @@ int orbx_batch_run_pipelined(orbx_batch* b, int n, const int* lapping, int chunk
 }
 
 int orbx_batch_run(orbx_batch* b, int n, const int* lapping) { return orbx_batch_run_range(b, 0, n, lapping); }
+
+// Frame::ComputeStereoMatches (Frame.cc:841-1011) for frames [0, n_frames): image 2f is the left, 2f+1 the right image of frame f.
+// Asynchronous on the handle's stream, after orbx_batch_run of the same images.
+int orbx_batch_stereo_match(orbx_batch* b, int n_frames, float mb, float mbf) {
+    int r = check_images(b, 0, 2 * n_frames);
+    if (r) return r;
+    if (n_frames == 0) return ORBX_OK;
+    if (!(mb > 0.f) || !(mbf > 0.f)) return fail(ORBX_ERR_ARG, "mb and mbf must be positive");
+    if (stereo_smem_bytes(b->g.K, b->g.lv[0].h) > 220 * 1024) return fail(ORBX_ERR_TOO_LARGE, "keypoint capacity too large for the stereo matcher's shared memory");
+    DeviceGuard dg(b->device);
+    Buffers buf = b->buf;
+    buf.imgBase = 0;
+    launch_stereo_match(b->g, buf, buf, n_frames, 2, 0, 2, 1, mb, mbf, b->stream);
+    CU(cudaGetLastError());
+    return ORBX_OK;
+}
+
+// uright / depth: [n_frames][K] floats (row f = left image of frame f), -1 where the left keypoint has no match; synchronises
+int orbx_batch_download_stereo(orbx_batch* b, int n_frames, float* uright, float* depth) {
+    int r = check_images(b, 0, 2 * n_frames);
+    if (r) return r;
+    DeviceGuard dg(b->device);
+    const size_t K = (size_t)b->g.K;
+    if (n_frames) {
+        // left images are the even ones: a strided copy of every second row block
+        if (uright) CU(cudaMemcpy2DAsync(uright, K * 4, b->buf.uRight, 2 * K * 4, K * 4, n_frames, cudaMemcpyDeviceToHost, b->stream));
+        if (depth) CU(cudaMemcpy2DAsync(depth, K * 4, b->buf.depth, 2 * K * 4, K * 4, n_frames, cudaMemcpyDeviceToHost, b->stream));
+    }
+    CU(cudaStreamSynchronize(b->stream));
+    return ORBX_OK;
+}
+
+
 
 int orbx_batch_sync(orbx_batch* b) {
     if (!b) return fail(ORBX_ERR_ARG, "null batch");
@@ -1048,6 +1084,30 @@ int orbx_extract_stereo(orbx_extractor* left, orbx_extractor* right, const uint8
     r = extractor_collect(left, kps_left, desc_left, cap_left, n_left, mono_left);
     const int r2 = extractor_collect(right, kps_right, desc_right, cap_right, n_right, mono_right);
     return r ? r : r2;
+}
+
+// replaces Frame::ComputeStereoMatches (Frame.cc:841-1011) for the stereo pair last extracted by `left` and `right`
+// (mpORBextractorLeft / mpORBextractorRight): uright[N_left] / depth[N_left] = Frame::mvuRight / mvDepth, -1 = no match.
+int orbx_stereo_match(orbx_extractor* left, orbx_extractor* right, float mb, float mbf, float* uright, float* depth, int capacity, int* n_left) {
+    if (!left || !right || left == right || !left->b || !right->b) return fail(ORBX_ERR_ARG, "need two distinct handles that have extracted an image");
+    orbx_batch *bl = left->b, *br = right->b;
+    if (bl->device != br->device || bl->width != br->width || bl->height != br->height || bl->g.K != br->g.K || bl->g.nlevels != br->g.nlevels)
+        return fail(ORBX_ERR_ARG, "left and right extractors differ in image size, parameters or device");
+    if (!(mb > 0.f) || !(mbf > 0.f)) return fail(ORBX_ERR_ARG, "mb and mbf must be positive");
+    if (stereo_smem_bytes(bl->g.K, bl->g.lv[0].h) > 220 * 1024) return fail(ORBX_ERR_TOO_LARGE, "keypoint capacity too large for the stereo matcher's shared memory");
+    DeviceGuard dg(bl->device);
+    CU(cudaStreamSynchronize(br->stream));  // the right image's results must be complete (the left stream orders its own)
+    Buffers l = bl->buf, r = br->buf;
+    l.imgBase = 0; r.imgBase = 0;
+    launch_stereo_match(bl->g, l, r, 1, 0, 0, 0, 0, mb, mbf, bl->stream);
+    CU(cudaGetLastError());
+    const int N = left->pinCnt ? left->pinCnt[0] : 0;
+    if (n_left) *n_left = N;
+    if (N > capacity) return fail(ORBX_ERR_CAPACITY, "output capacity smaller than the number of left keypoints");
+    if (uright && N) CU(cudaMemcpyAsync(uright, l.uRight, (size_t)N * 4, cudaMemcpyDeviceToHost, bl->stream));
+    if (depth && N) CU(cudaMemcpyAsync(depth, l.depth, (size_t)N * 4, cudaMemcpyDeviceToHost, bl->stream));
+    CU(cudaStreamSynchronize(bl->stream));
+    return ORBX_OK;
 }
 
 int orbx_get_level_size(const orbx_extractor* h, int level, int* width, int* height) {

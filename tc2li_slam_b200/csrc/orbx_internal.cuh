@@ -87,6 +87,8 @@ struct Buffers {
     KpWork* work;           // [image][K]
     int* outCount;          // [image]
     int* outMono;           // [image]
+    float* uRight;          // [image][K] stereo matches of LEFT images: right-image x of the match, -1 = none (Frame::mvuRight)
+    float* depth;           // [image][K] depth of the match, -1 = none (Frame::mvDepth)
     int* errFlag;           // device-side error flag (capacity overflow etc.)
     const uint4* cellTab;   // [cellsPerImage] FAST cell descriptors (make_cell_table)
     int imgBase;            // first image of this launch set (kernels index images as imgBase + blockIdx)
@@ -122,6 +124,11 @@ void launch_margin(const Geom& g, const Buffers& b, int nImages, cudaStream_t s)
 void launch_border(const uint8_t* src, int w, int h, int pitch, uint8_t* dst, int dpitch, cudaStream_t s);
 size_t octree_smem_bytes(int nodeCap);
 cudaError_t upload_describe_constants(const signed char pattern[1024], const int umax[16]);
+
+size_t stereo_smem_bytes(int K, int H);
+cudaError_t stereo_configure(int K, int H);
+void launch_stereo_match(const Geom& g, const Buffers& bl, const Buffers& br, int nFrames, int lMul, int lAdd, int rMul, int rAdd, float mb, float mbf,
+                         cudaStream_t s);
 
 // debug / test hooks
 void launch_debug_sincos(const float* anglesDeg, float* outSin, float* outCos, int n, cudaStream_t s);

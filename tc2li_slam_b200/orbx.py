@@ -76,6 +76,9 @@ def lib():
         "orbx_batch_run": (i, [_vp, i, _vp]),
         "orbx_batch_download": (i, [_vp, i, _vp, _vp, _vp, _vp]),
         "orbx_batch_sync": (i, [_vp]),
+        "orbx_batch_stereo_match": (i, [_vp, i, f, f]),
+        "orbx_batch_download_stereo": (i, [_vp, i, _vp, _vp]),
+        "orbx_stereo_match": (i, [_vp, _vp, f, f, _vp, _vp, i, _vp]),
         "orbx_batch_run_range": (i, [_vp, i, i, _vp]),
         "orbx_batch_run_pipelined": (i, [_vp, i, _vp, i]),
         "orbx_batch_download_async": (i, [_vp, i, i, _vp, _vp, _vp, _vp]),
@@ -359,6 +362,14 @@ class StereoORBextractor:
         return ((ml.value, L._kps[:nl.value].copy(), L._desc[:nl.value].copy()),
                 (mr.value, R._kps[:nr.value].copy(), R._desc[:nr.value].copy()))
 
+    def stereo_match(self, mb, mbf):
+        """Frame::ComputeStereoMatches (Frame.cc:841-1011) for the pair last extracted: (mvuRight, mvDepth), -1 = no match."""
+        cap = lib().orbx_max_keypoints(self.left._h)
+        u, d = np.empty(cap, np.float32), np.empty(cap, np.float32)
+        n = C.c_int(0)
+        _check(lib().orbx_stereo_match(self.left._h, self.right._h, float(mb), float(mbf), _p(u), _p(d), cap, C.byref(n)))
+        return u[:n.value].copy(), d[:n.value].copy()
+
     def close(self):
         self.left.close()
         self.right.close()
@@ -445,6 +456,15 @@ class BatchExtractor:
         if lapping is not None:
             lp = np.ascontiguousarray(lapping, np.int32).reshape(n, 2)
         _check(lib().orbx_batch_run_pipelined(self._h, n, _p(lp) if lp is not None else None, int(chunk)))
+
+    def stereo_match(self, n_frames, mb, mbf):
+        """Batched Frame::ComputeStereoMatches: image 2f = left, 2f+1 = right (after run()); asynchronous."""
+        _check(lib().orbx_batch_stereo_match(self._h, int(n_frames), float(mb), float(mbf)))
+
+    def download_stereo(self, n_frames):
+        u, d = np.empty((n_frames, self.K), np.float32), np.empty((n_frames, self.K), np.float32)
+        _check(lib().orbx_batch_download_stereo(self._h, int(n_frames), _p(u), _p(d)))
+        return u, d
 
     def sync(self):
         _check(lib().orbx_batch_sync(self._h))
