@@ -175,6 +175,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--no-stereo", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing hygiene: at least three warm-up steps
@@ -279,6 +280,22 @@ def main():
                 "whole_step": {"bytes_per_frame": 2 * ab["total"], "GBps": 2 * ab["total"] * args.pairs / (ms_step * 1e-3) / 1e9,
                                "frac": 2 * ab["total"] * args.pairs / (ms_step * 1e-3) / 1e9 / peak}}
 
+    # ---- supplementary: the next step of the caller, Frame::ComputeStereoMatches, on the resident results (not part of `value`) ----
+    stereo = None
+    if not args.no_stereo:
+        mb, mbf = 0.5372, 387.5744  # KITTI 00-02: baseline 0.537 m, bf 387.57 (config/Camera-Lidar/KITTI00-02.yaml)
+        big.stereo_match(args.pairs, mb, mbf)
+        big.sync()
+        s0, s1 = Event(), Event()
+        s0.record(big)
+        for _ in range(args.steps):
+            big.stereo_match(args.pairs, mb, mbf)
+        s1.record(big)
+        ms_st = s0.elapsed_ms(s1) / args.steps
+        u, _ = big.download_stereo(min(args.pairs, 64))
+        stereo = {"what": "orbx_batch_stereo_match (Frame::ComputeStereoMatches, Frame.cc:841-1011) on the resident keypoints/descriptors/pyramids",
+                  "ms_per_step": ms_st, "frames_per_s": args.pairs / (ms_st * 1e-3), "matched_fraction_first_64": float((u >= 0).sum()) / float(max(1, (counts[:2 * min(args.pairs, 64):2]).sum()))}
+
     # ---- e2e: pinned host images in, keypoints/descriptors out, three pipelined handles ----
     e2e = None
     pinned_in = None
@@ -372,7 +389,7 @@ def main():
             "config": {"workload": "BASELINE.json configs[4]: batch of KITTI-shaped stereo frames 1241x376 (left+right), ORBextractor(2000,1.2,8,20,7), sharded by frame",
                        "pairs_per_gpu_per_step": args.pairs, "images_per_launch_set": group, "keypoints_per_image": kp_mean,
                        "l2": f"inputs {n_img * W * H / 1e9:.2f} GB per rank, larger than the {L2_BYTES / 1e6:.0f} MB L2; no flush needed"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step, "roofline": roofline, "cpu_baseline": cpu, "stages": stages, "latency": latency,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step, "roofline": roofline, "cpu_baseline": cpu, "stages": stages, "latency": latency, "stereo_match": stereo,
         }
         print(json.dumps(line))
     big.close()
