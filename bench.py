@@ -176,6 +176,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--no-stereo", action="store_true")
+    ap.add_argument("--no-large", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing hygiene: at least three warm-up steps
@@ -346,6 +347,31 @@ def main():
         for h in handles:
             h.close()
 
+    # ---- supplementary: BASELINE.json configs[3], large single frames (1920x1080 and 3840x2160, 4000 features) ----
+    large = None
+    if rank == 0 and not args.no_large:
+        large = {}
+        for (lw, lh, nimg) in ((1920, 1080, 64), (3840, 2160, 16)):
+            lb = T.BatchExtractor(lw, lh, nimg, 4000, 1.2, 8, 20, 7, device=local)
+            lb.synth(7, nimg, stereo=False)
+            for _ in range(3):
+                lb.run(nimg)
+            lb.check()
+            cl, _ = lb.download_counts(nimg)
+            l0, l1 = Event(), Event()
+            l0.record(lb)
+            for _ in range(args.steps):
+                lb.run(nimg)
+            l1.record(lb)
+            ms = l0.elapsed_ms(l1) / args.steps
+            px = [g_["w"] * g_["h"] for g_ in (T.level_geometry(lw, lh, l, 4000, 1.2, 8) for l in range(8))]
+            P_, K_ = sum(px), float(cl.mean())
+            bytes_img = 5 * P_ - px[0] - px[-1] + 1321 * K_
+            large[f"{lw}x{lh}"] = {"images_per_launch_set": nimg, "ms_per_image": ms / nimg, "images_per_s": nimg / (ms * 1e-3), "keypoints_per_image": K_,
+                                   "algorithmic_bytes_per_image": bytes_img, "GBps": bytes_img * nimg / (ms * 1e-3) / 1e9,
+                                   "frac_of_measured_hbm": bytes_img * nimg / (ms * 1e-3) / 1e9 / peak}
+            lb.close()
+
     # ---- stereo-pair latency through the reference-shaped API (BASELINE.json configs[1]) ----
     latency = None
     if rank == 0 and not args.no_latency:
@@ -389,7 +415,7 @@ def main():
             "config": {"workload": "BASELINE.json configs[4]: batch of KITTI-shaped stereo frames 1241x376 (left+right), ORBextractor(2000,1.2,8,20,7), sharded by frame",
                        "pairs_per_gpu_per_step": args.pairs, "images_per_launch_set": group, "keypoints_per_image": kp_mean,
                        "l2": f"inputs {n_img * W * H / 1e9:.2f} GB per rank, larger than the {L2_BYTES / 1e6:.0f} MB L2; no flush needed"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step, "roofline": roofline, "cpu_baseline": cpu, "stages": stages, "latency": latency, "stereo_match": stereo,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step, "roofline": roofline, "cpu_baseline": cpu, "stages": stages, "latency": latency, "stereo_match": stereo, "large_images": large,
         }
         print(json.dumps(line))
     big.close()

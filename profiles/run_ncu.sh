@@ -5,7 +5,7 @@
 set -u
 TAG=${1:-r01}
 NL=${2:-20}
-CMD="python bench.py --pairs 128 --steps 1 --warmup 3 --no-e2e --no-cpu --no-latency --no-stereo"
+CMD="python bench.py --pairs 128 --steps 1 --warmup 3 --no-e2e --no-cpu --no-latency --no-stereo --no-large"
 mkdir -p gpurun_out
 $CMD > gpurun_out/plain_$TAG.json 2> gpurun_out/plain_$TAG.err || { echo "plain run failed"; tail -5 gpurun_out/plain_$TAG.err; exit 1; }
 # launches: 1 synth + 3 warm-up steps + 1 timed step + 2 stage-timing steps, NL launches each
