@@ -33,6 +33,9 @@ UNIT = "frames/s"
 L2_BYTES = 126e6
 
 
+WORKLOAD = "BASELINE.json configs[4]: batch of KITTI-shaped stereo frames 1241x376 (left+right), ORBextractor(2000,1.2,8,20,7), sharded by frame"
+
+
 def level_sizes():
     import tc2li_slam_b200 as T
     return [(g["w"], g["h"]) for g in (T.level_geometry(W, H, l, *ORB_ARGS[:3]) for l in range(ORB_ARGS[2]))]
@@ -108,10 +111,10 @@ def reference_arm(args):
     sec = sum(times) / len(times)
     v = pairs / sec
     sample = f"{pairs} synthetic KITTI-shaped stereo frames per step on {cores} host threads ({kind} of ORBextractor.cc, -O3, no FMA contraction)"
-    print(json.dumps({
+    emit_line(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "KITTI-shaped stereo frames 1241x376, ORBextractor(2000,1.2,8,20,7), CPU reference path, bounded sample", "pairs_per_step": pairs},
+        "config": {"workload": WORKLOAD, "pairs_per_step": pairs, "sample": "bounded sample of the workload on the host cores (CPU reference path)"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -162,7 +165,25 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Everything any library writes to fd 1 from here on (NCCL prints its version there) goes to stderr; the one JSON
+    line of the contract is written to the real stdout by emit_line()."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit_line(text):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (text + "\n").encode())
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -412,12 +433,12 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "BASELINE.json configs[4]: batch of KITTI-shaped stereo frames 1241x376 (left+right), ORBextractor(2000,1.2,8,20,7), sharded by frame",
+            "config": {"workload": WORKLOAD,
                        "pairs_per_gpu_per_step": args.pairs, "images_per_launch_set": group, "keypoints_per_image": kp_mean,
                        "l2": f"inputs {n_img * W * H / 1e9:.2f} GB per rank, larger than the {L2_BYTES / 1e6:.0f} MB L2; no flush needed"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step, "roofline": roofline, "cpu_baseline": cpu, "stages": stages, "latency": latency, "stereo_match": stereo, "large_images": large,
         }
-        print(json.dumps(line))
+        emit_line(json.dumps(line))
     big.close()
     if dist is not None:
         dist.destroy_process_group()

@@ -17,9 +17,9 @@
 // ballot prefixes (no atomics):
 //   A  four pixels per lane, packed in one 32-bit word: |ring - centre| > t at the four compass points, combined as
 //      (N|S)&(E|W) — a necessary condition for a 9-arc of either polarity (VABSDIFF4 + carry tricks) -> list1;
-//   A2 dense over list1: exact bright/dark masks of the 16 ring pixels (both polarities at once in 16x2 lanes: the sign
-//      bits of hi - r and r - lo) and the contiguity test -> list2 (corners);
-//   B  dense over list2: arc score S into a score map that shares the tile's layout;
+//   A2 dense over list1: the exact score S of both polarities at once, ring pixels q and q + 8 paired in 16x2 lanes and
+//      the nine-windows built from three-input packed min / max (VIMNMX3.U16x2); S > t -> list2 (corners) and the score
+//      goes into a score map that shares the tile's layout;
 //   C  dense over list2: cell-local 3x3 NMS; survivors go straight to the global candidate list (one atomic per batch).
 // The threshold is iniThFAST first; only a cell without any survivor is redone at minThFAST (ORBextractor.cc:817-820).
 // The lists have a fixed capacity; a pass that would overflow flushes the downstream passes first, and a cell whose corner
@@ -37,17 +37,6 @@ constexpr int FW = 1;                    // warps per CTA (every warp is indepen
 constexpr int CAP = 512;                 // entries per list
 constexpr unsigned FULL = 0xFFFFFFFFu;
 
-// >= 9 contiguous set bits in each circular 16-bit half of m (low half: bright mask, high half: dark mask)
-__device__ __forceinline__ uint32_t arc9_halves(uint32_t m) {
-    const uint32_t lo = m & 0xFFFFu, hi = m >> 16;
-    uint32_t a = lo | (lo << 16), c = hi | (hi << 16);
-    a &= a >> 1; c &= c >> 1;
-    a &= a >> 2; c &= c >> 2;
-    a &= a >> 4; c &= c >> 4;
-    a &= a >> 1; c &= c >> 1;
-    return (a & 0xFFFFu) | (c << 16);
-}
-
 // per byte: 0x80 where the byte of d exceeds t (0 <= t <= 254); kAdd = (0x7f - (t & 0x7f)) * 0x01010101
 __device__ __forceinline__ uint32_t bytes_gt(uint32_t d, uint32_t kAdd, bool tHigh) {
     const uint32_t low = (d & 0x7f7f7f7fu) + kAdd;  // bit 7 of each byte: (d & 0x7f) > (t & 0x7f)
@@ -64,66 +53,67 @@ struct CellCtx {
     uint8_t* sc;           // score map, same layout
     uint16_t* listW;       // words with a compass survivor: tile word index | 4 pixel flags << 12
     uint16_t* list1;       // compass survivors (tile byte offsets); NMS survivors afterwards
-    uint16_t* list2;       // corners (tile offset | 0x8000 = dark)
+    uint16_t* list2;       // corners (tile byte offsets)
     int nw, n1, n2;        // warp-uniform fill levels
-    bool flushedB;         // list2 was flushed before the NMS: corners are no longer all listed
+    bool flushedB;         // list2 overflowed and restarted: corners are no longer all listed
     int lane;
 };
 
-template <int TS>
-__device__ __forceinline__ void flush_B(CellCtx& c) {  // arc score of the listed corners -> score map
-    for (int k = c.lane; k < c.n2; k += 32) {
-        const int e = c.list2[k], off = e & 0x7FFF;
-        const uint8_t* p = c.tile + off;
-        const int v = p[0];
-        const int sgn = (e & 0x8000) ? -1 : 1;
-        int d[16];
-#pragma unroll
-        for (int q = 0; q < 16; ++q) d[q] = sgn * ((int)p[RING(TS, q)] - v);
-        int m2[16], m4[16], m8[16];
-#pragma unroll
-        for (int q = 0; q < 16; ++q) m2[q] = min(d[q], d[(q + 1) & 15]);
-#pragma unroll
-        for (int q = 0; q < 16; ++q) m4[q] = min(m2[q], m2[(q + 2) & 15]);
-#pragma unroll
-        for (int q = 0; q < 16; ++q) m8[q] = min(m4[q], m4[(q + 4) & 15]);
-        int s = 0;
-#pragma unroll
-        for (int q = 0; q < 16; ++q) s = max(s, min(m8[q], d[(q + 8) & 15]));
-        c.sc[off] = (uint8_t)s;  // t < s <= 255
-    }
-    __syncwarp();
-}
+// half swap of a 16x2 word
+__device__ __forceinline__ uint32_t sw16(uint32_t x) { return __byte_perm(x, 0, 0x1032); }
 
+// list1 -> list2 with the exact score of every listed pixel (16x2 lanes, DPX three-input min / max):
+//   S = max( max_s min_{j<9} r[s+j] - v,  v - min_s max_{j<9} r[s+j] )        (at most one of the two terms is positive)
+// R[q] holds ring pixels q (low half) and q + 8 (high half), R[q + 8] is its half swap, so the nine-window starting at q
+// yields the windows starting at q and q + 8 at once: m3[q] = op3(R[q], R[q+1], R[q+2]), W[q] = op3(m3[q], m3[q+3], m3[q+6]).
+// A pixel is a corner at t iff S > t; only corners get their score written to the map.
 template <int TS>
-__device__ __forceinline__ void flush_A2(CellCtx& c, int t) {  // exact ring masks + contiguity: list1 -> list2
+__device__ __forceinline__ void flush_A2(CellCtx& c, int t) {
     for (int k0 = 0; k0 < c.n1; k0 += 32) {
         const int k = k0 + c.lane;
-        int off = 0;
-        uint32_t arcs = 0;
+        int off = 0, S = 0;
         if (k < c.n1) {
             off = c.list1[k];
             const uint8_t* p = c.tile + off;
-            const uint32_t v = p[0];
-            // 16x2 lanes: low = (v + t + 1) - (r + 1) = hi - r, high = r - lo; (r + 1) * 0xFFFF = (r << 16) | (-(r + 1) & 0xFFFF)
-            const uint32_t K = (v + t + 1) | (((uint32_t)(t - (int)v) & 0xFFFFu) << 16);
-            uint32_t m = 0;
+            const int v = p[0];
+            uint32_t R[10];
 #pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                const uint32_t r = p[RING(TS, q)];
-                const uint32_t sdiff = __vadd2(K, r * 0xFFFFu + 0xFFFFu);
-                m |= ((sdiff >> (15 - q)) & (0x00010001u << q));  // bit q: r > hi, bit 16 + q: r < lo
+            for (int q = 0; q < 8; ++q) R[q] = (uint32_t)p[RING(TS, q)] | ((uint32_t)p[RING(TS, q + 8)] << 16);
+            R[8] = sw16(R[0]);
+            R[9] = sw16(R[1]);
+            uint32_t mn[14], mx[14];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                mn[q] = __vimin3_u16x2(R[q], R[q + 1], R[q + 2]);
+                mx[q] = __vimax3_u16x2(R[q], R[q + 1], R[q + 2]);
             }
-            arcs = arc9_halves(m);
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+                mn[8 + q] = sw16(mn[q]);
+                mx[8 + q] = sw16(mx[q]);
+            }
+            uint32_t wn[8], wx[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                wn[q] = __vimin3_u16x2(mn[q], mn[q + 3], mn[q + 6]);
+                wx[q] = __vimax3_u16x2(mx[q], mx[q + 3], mx[q + 6]);
+            }
+            uint32_t bn = __vimax3_u16x2(__vimax3_u16x2(wn[0], wn[1], wn[2]), __vimax3_u16x2(wn[3], wn[4], wn[5]), __vmaxu2(wn[6], wn[7]));
+            uint32_t bx = __vimin3_u16x2(__vimin3_u16x2(wx[0], wx[1], wx[2]), __vimin3_u16x2(wx[3], wx[4], wx[5]), __vminu2(wx[6], wx[7]));
+            const int hiN = (int)max(bn & 0xFFFFu, bn >> 16), loX = (int)min(bx & 0xFFFFu, bx >> 16);
+            S = max(hiN - v, v - loX);
         }
-        const unsigned bal = __ballot_sync(FULL, arcs != 0);
+        const bool corner = S > t;
+        const unsigned bal = __ballot_sync(FULL, corner);
         if (bal) {
-            if (c.n2 + 32 > CAP) {  // warp-uniform
-                flush_B<TS>(c);
+            if (c.n2 + 32 > CAP) {  // warp-uniform: the scores stay in the map, the list restarts
                 c.n2 = 0;
                 c.flushedB = true;
             }
-            if (arcs) c.list2[c.n2 + __popc(bal & ((1u << c.lane) - 1))] = (uint16_t)(off | ((arcs >> 16) ? 0x8000 : 0));
+            if (corner) {
+                c.sc[off] = (uint8_t)S;  // t < S <= 255
+                c.list2[c.n2 + __popc(bal & ((1u << c.lane) - 1))] = (uint16_t)off;
+            }
             c.n2 += __popc(bal);
         }
     }
@@ -276,7 +266,6 @@ __global__ void __launch_bounds__(32 * FW) k_fast_cells(const __grid_constant__ 
             }
             flush_W<TS>(c, t);
             flush_A2<TS>(c, t);
-            flush_B<TS>(c);
 
             // ---- pass C: cell-local 3x3 non-maximum suppression (only interior pixels ever get a score: the rim reads 0) ----
             int ns = 0;                  // survivors waiting in list1
@@ -287,7 +276,7 @@ __global__ void __launch_bounds__(32 * FW) k_fast_cells(const __grid_constant__ 
                     bool keep = false;
                     int off = 0;
                     if (k < c.n2) {
-                        off = c.list2[k] & 0x7FFF;
+                        off = c.list2[k];
                         const uint8_t* q = c.sc + off;
                         const int s = q[0];
                         const int nmax = max(max(max((int)q[-1], (int)q[1]), max((int)q[-TS - 1], (int)q[-TS])), max(max((int)q[-TS + 1], (int)q[TS - 1]), max((int)q[TS], (int)q[TS + 1])));
@@ -301,7 +290,7 @@ __global__ void __launch_bounds__(32 * FW) k_fast_cells(const __grid_constant__ 
                 emit<TS>(c, surv, ns, shift, relX, relY, cand, L.candCap, candCount, b.errFlag);
                 nsTotal += ns;
                 __syncwarp();
-                for (int k = lane; k < c.n2; k += 32) c.sc[c.list2[k] & 0x7FFF] = 0;  // leave the score map clean
+                for (int k = lane; k < c.n2; k += 32) c.sc[c.list2[k]] = 0;  // leave the score map clean
             } else {
                 // the corner list was flushed early (very dense corners): find the scores by scanning the map
                 for (int p0 = 0; p0 < iw * ih; p0 += 32) {
