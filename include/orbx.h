@@ -93,6 +93,22 @@ int orbx_extract_stereo(orbx_extractor* left, orbx_extractor* right, const uint8
  * ---------------------------------------------------------------------------------------------------------------- */
 int orbx_stereo_match(orbx_extractor* left, orbx_extractor* right, float mb, float mbf, float* uright, float* depth, int capacity, int* n_left);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Next step of the fisheye (KannalaBrandt8) stereo caller: the descriptor stage of
+ * Frame::ComputeStereoFishEyeMatches (Frame.cc:1162-1187) — `BFmatcher.knnMatch(stereoDescLeft, stereoDescRight, matches, 2)`
+ * with BFmatcher = cv::BFMatcher(cv::NORM_HAMMING) (Frame.cc:52) over the lapping-area tails [monoLeft, Nleft) /
+ * [monoRight, Nright) that operator() leaves at the back of both outputs (ORBextractor.cc:1126-1135), and Lowe's gate
+ * `m[0].distance < m[1].distance * 0.7` (Frame.cc:1187).  For query q (left keypoint mono_left + q) knn[q] holds the two
+ * nearest train rows (right keypoint mono_right + train_idx) in cv::DMatch order, -1 where the right tail has fewer rows;
+ * ratio_ok[q] != 0 iff the reference would go on to KannalaBrandt8::TriangulateMatches for that pair (Frame.cc:1188-1192,
+ * which stays on the host).  Bit-identical to OpenCV's brute-force matcher, ties included.
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct orbx_knn2 {
+    int train_idx0, distance0; /* cv::DMatch{queryIdx = q, trainIdx, distance} of the nearest train row */
+    int train_idx1, distance1; /* ... of the second nearest */
+} orbx_knn2;
+int orbx_lapping_match(orbx_extractor* left, orbx_extractor* right, orbx_knn2* knn, uint8_t* ratio_ok, int capacity, int* n_query, int* n_train);
+
 /* replace the public member mvImagePyramid (ORBextractor.h:92), read by Frame::ComputeStereoMatches
  * (Frame.cc:848,938,948,953): size and (lazy) device->host copy of level `level` of the last extracted image.
  * border = 0 copies w x h pixels to dst; border = 19 writes the (w+38) x (h+38) BORDER_REFLECT_101 image the
@@ -135,6 +151,10 @@ int orbx_batch_download(orbx_batch* b, int n_images, orbx_keypoint* keypoints, u
  * orbx_batch_download_stereo: uright / depth [n_frames][K] floats (K = orbx_batch_max_keypoints), -1 = no match; synchronises. */
 int orbx_batch_stereo_match(orbx_batch* b, int n_frames, float mb, float mbf);
 int orbx_batch_download_stereo(orbx_batch* b, int n_frames, float* uright, float* depth);
+/* batched descriptor stage of Frame::ComputeStereoFishEyeMatches (see orbx_lapping_match): image 2f = left, 2f+1 = right.
+ * orbx_batch_download_lapping: knn / ratio_ok [n_frames][K]; row f holds the N_left - mono_left queries of frame f; synchronises. */
+int orbx_batch_lapping_match(orbx_batch* b, int n_frames);
+int orbx_batch_download_lapping(orbx_batch* b, int n_frames, orbx_knn2* knn, uint8_t* ratio_ok);
 int orbx_batch_sync(orbx_batch* b);
 /* the same on a sub-range [first, first+n) of the handle's images (lapping: n x 2 ints for that range): lets a caller keep
  * many frames resident and process them in groups small enough for the 126 MB L2 */

@@ -19,6 +19,7 @@
 // glibc sinf/cosf.
 
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -677,6 +678,37 @@ void stereo_match(const Extractor& L, const Extractor& R, float mb, float mbf, s
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Frame::ComputeStereoFishEyeMatches, descriptor stage (Frame.cc:1162-1187; BFmatcher = cv::BFMatcher(cv::NORM_HAMMING),
+// Frame.cc:52): knnMatch(k = 2) of the left lapping tail [monoLeft, Nleft) against the right tail [monoRight, Nright)
+// and Lowe's ratio gate `m[0].distance < m[1].distance * 0.7` (float * double -> double compare, Frame.cc:1187).
+// cv::BFMatcher::knnMatch -> cv::batchDistance(K = 2): the train rows are scanned in index order and a row enters the
+// K-best list only if its distance is STRICTLY smaller than the current K-th, sliding in behind equal distances; the
+// result is therefore the two smallest (distance, trainIdx) pairs in lexicographic order.  Fewer than two train rows
+// give fewer matches (the reference then skips the query: `size() >= 2`); no train rows give none.
+// out[q] = {trainIdx0, distance0, trainIdx1, distance1} (-1 where absent), ok[q] = passes the ratio gate.
+// Pinned against cv2.BFMatcher(NORM_HAMMING).knnMatch in tests/test_oracle_vs_cv2.py.
+// ---------------------------------------------------------------------------------------------
+void lapping_knn_match(const uint8_t* dl, int nq, const uint8_t* dr, int nt, int* out, uint8_t* ok) {
+    for (int q = 0; q < nq; ++q) {
+        int idx[2] = {-1, -1}, dist[2] = {INT_MAX, INT_MAX};
+        for (int j = 0; j < nt; ++j) {
+            const int d = hamming256(dl + (size_t)q * 32, dr + (size_t)j * 32);
+            if (d < dist[1]) {
+                int k = 0;
+                if (dist[0] > d) { idx[1] = idx[0]; dist[1] = dist[0]; k = -1; }
+                idx[k + 1] = j;
+                dist[k + 1] = d;
+            }
+        }
+        int* o = out + 4 * (size_t)q;
+        o[0] = idx[0]; o[1] = idx[0] >= 0 ? dist[0] : -1;
+        o[2] = idx[1]; o[3] = idx[1] >= 0 ? dist[1] : -1;
+        ok[q] = (idx[1] >= 0 && (float)dist[0] < (float)dist[1] * 0.7) ? 1 : 0;
+    }
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -730,6 +762,7 @@ int orbo_stereo_match(void* hl, void* hr, float mb, float mbf, float* uright, fl
     if (!u.empty()) { std::memcpy(uright, u.data(), u.size() * 4); std::memcpy(depth, d.data(), d.size() * 4); }
     return (int)u.size();
 }
+void orbo_lapping_match(const uint8_t* dl, int nq, const uint8_t* dr, int nt, int* out, uint8_t* ok) { lapping_knn_match(dl, nq, dr, nt, out, ok); }
 // primitives, for direct checks against cv2
 void orbo_synth_v1(uint8_t* out, int W, int H, uint32_t seed, int xoff, uint32_t noise_xor) { synth_v1(out, W, H, seed, xoff, noise_xor); }
 void orbo_resize(const uint8_t* src, int sw, int sh, int sstride, uint8_t* dst, int dw, int dh, int dstride) {

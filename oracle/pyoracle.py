@@ -48,6 +48,7 @@ def lib():
         L.orbo_num_selected.argtypes = [C.c_void_p, C.c_int]
         L.orbo_get_selected.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.orbo_stereo_match.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+        L.orbo_lapping_match.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.orbo_synth_v1.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_uint32]
         L.orbo_resize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.orbo_blur.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
@@ -120,6 +121,17 @@ def stereo_match(left, right, mb, mbf):
     u, d = np.empty(n, np.float32), np.empty(n, np.float32)
     lib().orbo_stereo_match(left._h, right._h, float(mb), float(mbf), _p(u), _p(d))
     return u, d
+
+
+def lapping_match(desc_left, desc_right):
+    """Descriptor stage of Frame::ComputeStereoFishEyeMatches (Frame.cc:1162-1187) on the two lapping tails:
+    returns (knn int32 [nq, 4] = trainIdx0, distance0, trainIdx1, distance1 with -1 where absent, ok uint8 [nq])."""
+    dl = np.ascontiguousarray(desc_left, np.uint8).reshape(-1, 32)
+    dr = np.ascontiguousarray(desc_right, np.uint8).reshape(-1, 32)
+    out = np.empty((len(dl), 4), np.int32)
+    ok = np.empty(len(dl), np.uint8)
+    lib().orbo_lapping_match(_p(dl), len(dl), _p(dr), len(dr), _p(out), _p(ok))
+    return out, ok
 
 
 class OracleExtractor:

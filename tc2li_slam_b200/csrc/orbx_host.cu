@@ -248,6 +248,8 @@ int batch_alloc(orbx_batch* b) {
     if ((r = dev_alloc(b, &B.outMono, (size_t)n))) return r;
     if ((r = dev_alloc(b, &B.uRight, (size_t)n * g.K))) return r;
     if ((r = dev_alloc(b, &B.depth, (size_t)n * g.K))) return r;
+    if ((r = dev_alloc(b, &B.lapKnn, (size_t)n * g.K))) return r;
+    if ((r = dev_alloc(b, &B.lapOk, (size_t)n * g.K))) return r;
     if ((r = dev_alloc(b, &B.errFlag, 1))) return r;
     B.imgBase = 0;
     for (int l = 0; l < g.nlevels; ++l) {
@@ -275,6 +277,7 @@ int batch_alloc(orbx_batch* b) {
         b->numSMs = prop.multiProcessorCount;
         CU(describe_configure());
         if (stereo_smem_bytes(g.K, g.lv[0].h) <= 220 * 1024) CU(stereo_configure(g.K, g.lv[0].h));
+        CU(lap_match_configure());
     }
     CU(cudaMemset(B.errFlag, 0, sizeof(int)));
     CU(cudaMemset(B.lapping, 0, (size_t)n * 2 * sizeof(int)));
@@ -611,6 +614,35 @@ int orbx_batch_download_stereo(orbx_batch* b, int n_frames, float* uright, float
 }
 
 
+
+// Descriptor stage of Frame::ComputeStereoFishEyeMatches (Frame.cc:1162-1187) for frames [0, n_frames): kNN (k = 2) of the left
+// lapping tail against the right lapping tail + Lowe's gate.  Asynchronous, after orbx_batch_run of the same images.
+int orbx_batch_lapping_match(orbx_batch* b, int n_frames) {
+    int r = check_images(b, 0, 2 * n_frames);
+    if (r) return r;
+    if (n_frames == 0) return ORBX_OK;
+    if (b->g.K > 65535) return fail(ORBX_ERR_TOO_LARGE, "keypoint capacity above 65535: train indices do not fit the matcher's 16-bit field");
+    DeviceGuard dg(b->device);
+    Buffers buf = b->buf;
+    buf.imgBase = 0;
+    launch_lap_match(b->g, buf, buf, n_frames, 2, 0, 2, 1, b->stream);
+    CU(cudaGetLastError());
+    return ORBX_OK;
+}
+
+// knn [n_frames][K], ratio_ok [n_frames][K] (row f = left image of frame f; entries [0, N_left - mono_left) are valid); synchronises
+int orbx_batch_download_lapping(orbx_batch* b, int n_frames, orbx_knn2* knn, uint8_t* ratio_ok) {
+    int r = check_images(b, 0, 2 * n_frames);
+    if (r) return r;
+    DeviceGuard dg(b->device);
+    const size_t K = (size_t)b->g.K;
+    if (n_frames) {
+        if (knn) CU(cudaMemcpy2DAsync(knn, K * 16, b->buf.lapKnn, 2 * K * 16, K * 16, n_frames, cudaMemcpyDeviceToHost, b->stream));
+        if (ratio_ok) CU(cudaMemcpy2DAsync(ratio_ok, K, b->buf.lapOk, 2 * K, K, n_frames, cudaMemcpyDeviceToHost, b->stream));
+    }
+    CU(cudaStreamSynchronize(b->stream));
+    return ORBX_OK;
+}
 
 int orbx_batch_sync(orbx_batch* b) {
     if (!b) return fail(ORBX_ERR_ARG, "null batch");
@@ -1106,6 +1138,30 @@ int orbx_stereo_match(orbx_extractor* left, orbx_extractor* right, float mb, flo
     if (N > capacity) return fail(ORBX_ERR_CAPACITY, "output capacity smaller than the number of left keypoints");
     if (uright && N) CU(cudaMemcpyAsync(uright, l.uRight, (size_t)N * 4, cudaMemcpyDeviceToHost, bl->stream));
     if (depth && N) CU(cudaMemcpyAsync(depth, l.depth, (size_t)N * 4, cudaMemcpyDeviceToHost, bl->stream));
+    CU(cudaStreamSynchronize(bl->stream));
+    return ORBX_OK;
+}
+
+// descriptor stage of Frame::ComputeStereoFishEyeMatches (Frame.cc:1162-1187) for the pair last extracted by `left` and `right`:
+// knn[q] / ratio_ok[q] for the *n_query rows of the left lapping tail (query q = left keypoint mono_left + q, train index t =
+// right keypoint mono_right + t), i.e. BFmatcher.knnMatch(stereoDescLeft, stereoDescRight, matches, 2) and Lowe's gate.
+int orbx_lapping_match(orbx_extractor* left, orbx_extractor* right, orbx_knn2* knn, uint8_t* ratio_ok, int capacity, int* n_query, int* n_train) {
+    if (!left || !right || left == right || !left->b || !right->b) return fail(ORBX_ERR_ARG, "need two distinct handles that have extracted an image");
+    orbx_batch *bl = left->b, *br = right->b;
+    if (bl->device != br->device || bl->g.K != br->g.K) return fail(ORBX_ERR_ARG, "left and right extractors differ in parameters or device");
+    if (bl->g.K > 65535) return fail(ORBX_ERR_TOO_LARGE, "keypoint capacity above 65535: train indices do not fit the matcher's 16-bit field");
+    DeviceGuard dg(bl->device);
+    CU(cudaStreamSynchronize(br->stream));  // the right image's results must be complete (the left stream orders its own)
+    Buffers l = bl->buf, r = br->buf;
+    l.imgBase = 0; r.imgBase = 0;
+    launch_lap_match(bl->g, l, r, 1, 0, 0, 0, 0, bl->stream);
+    CU(cudaGetLastError());
+    const int nq = left->pinCnt ? left->pinCnt[0] - left->pinCnt[1] : 0, nt = right->pinCnt ? right->pinCnt[0] - right->pinCnt[1] : 0;
+    if (n_query) *n_query = nq;
+    if (n_train) *n_train = nt;
+    if (nq > capacity) return fail(ORBX_ERR_CAPACITY, "output capacity smaller than the number of left lapping keypoints");
+    if (knn && nq) CU(cudaMemcpyAsync(knn, l.lapKnn, (size_t)nq * 16, cudaMemcpyDeviceToHost, bl->stream));
+    if (ratio_ok && nq) CU(cudaMemcpyAsync(ratio_ok, l.lapOk, (size_t)nq, cudaMemcpyDeviceToHost, bl->stream));
     CU(cudaStreamSynchronize(bl->stream));
     return ORBX_OK;
 }

@@ -89,6 +89,8 @@ struct Buffers {
     int* outMono;           // [image]
     float* uRight;          // [image][K] stereo matches of LEFT images: right-image x of the match, -1 = none (Frame::mvuRight)
     float* depth;           // [image][K] depth of the match, -1 = none (Frame::mvDepth)
+    int4* lapKnn;           // [image][K] lapping-tail kNN of LEFT images: {trainIdx0, distance0, trainIdx1, distance1}, -1 = absent
+    uint8_t* lapOk;         // [image][K] Lowe ratio gate of that pair (Frame.cc:1187)
     int* errFlag;           // device-side error flag (capacity overflow etc.)
     const uint4* cellTab;   // [cellsPerImage] FAST cell descriptors (make_cell_table)
     int imgBase;            // first image of this launch set (kernels index images as imgBase + blockIdx)
@@ -129,6 +131,10 @@ size_t stereo_smem_bytes(int K, int H);
 cudaError_t stereo_configure(int K, int H);
 void launch_stereo_match(const Geom& g, const Buffers& bl, const Buffers& br, int nFrames, int lMul, int lAdd, int rMul, int rAdd, float mb, float mbf,
                          cudaStream_t s);
+
+size_t lap_match_smem_bytes();
+cudaError_t lap_match_configure();
+void launch_lap_match(const Geom& g, const Buffers& bl, const Buffers& br, int nFrames, int lMul, int lAdd, int rMul, int rAdd, cudaStream_t s);
 
 // debug / test hooks
 void launch_debug_sincos(const float* anglesDeg, float* outSin, float* outCos, int n, cudaStream_t s);

@@ -79,6 +79,9 @@ def lib():
         "orbx_batch_stereo_match": (i, [_vp, i, f, f]),
         "orbx_batch_download_stereo": (i, [_vp, i, _vp, _vp]),
         "orbx_stereo_match": (i, [_vp, _vp, f, f, _vp, _vp, i, _vp]),
+        "orbx_lapping_match": (i, [_vp, _vp, _vp, _vp, i, _vp, _vp]),
+        "orbx_batch_lapping_match": (i, [_vp, i]),
+        "orbx_batch_download_lapping": (i, [_vp, i, _vp, _vp]),
         "orbx_batch_run_range": (i, [_vp, i, i, _vp]),
         "orbx_batch_run_pipelined": (i, [_vp, i, _vp, i]),
         "orbx_batch_download_async": (i, [_vp, i, i, _vp, _vp, _vp, _vp]),
@@ -370,6 +373,16 @@ class StereoORBextractor:
         _check(lib().orbx_stereo_match(self.left._h, self.right._h, float(mb), float(mbf), _p(u), _p(d), cap, C.byref(n)))
         return u[:n.value].copy(), d[:n.value].copy()
 
+    def lapping_match(self):
+        """Descriptor stage of Frame::ComputeStereoFishEyeMatches (Frame.cc:1162-1187) for the pair last extracted:
+        (knn int32 [nq, 4] = trainIdx0, distance0, trainIdx1, distance1 of BFmatcher.knnMatch(k=2) on the lapping tails, -1 where
+        absent; ratio_ok uint8 [nq] = Lowe's gate).  Query q is left keypoint monoLeft + q, train t right keypoint monoRight + t."""
+        cap = lib().orbx_max_keypoints(self.left._h)
+        knn, ok = np.empty((cap, 4), np.int32), np.empty(cap, np.uint8)
+        nq, nt = C.c_int(0), C.c_int(0)
+        _check(lib().orbx_lapping_match(self.left._h, self.right._h, _p(knn), _p(ok), cap, C.byref(nq), C.byref(nt)))
+        return knn[:nq.value].copy(), ok[:nq.value].copy()
+
     def close(self):
         self.left.close()
         self.right.close()
@@ -465,6 +478,16 @@ class BatchExtractor:
         u, d = np.empty((n_frames, self.K), np.float32), np.empty((n_frames, self.K), np.float32)
         _check(lib().orbx_batch_download_stereo(self._h, int(n_frames), _p(u), _p(d)))
         return u, d
+
+    def lapping_match(self, n_frames):
+        """Batched descriptor stage of Frame::ComputeStereoFishEyeMatches: image 2f = left, 2f+1 = right (after run()); asynchronous."""
+        _check(lib().orbx_batch_lapping_match(self._h, int(n_frames)))
+
+    def download_lapping(self, n_frames):
+        """(knn int32 [n_frames, K, 4], ratio_ok uint8 [n_frames, K]); row f: the N_left - mono_left queries of frame f are valid."""
+        knn, ok = np.empty((n_frames, self.K, 4), np.int32), np.empty((n_frames, self.K), np.uint8)
+        _check(lib().orbx_batch_download_lapping(self._h, int(n_frames), _p(knn), _p(ok)))
+        return knn, ok
 
     def sync(self):
         _check(lib().orbx_batch_sync(self._h))

@@ -77,3 +77,57 @@ def test_fast_atan2_matches_cv2():
     xs[25:75] = 0
     for y, x in zip(ys, xs):
         assert np.float32(po.fast_atan2(y, x)) == np.float32(cv2.fastAtan2(float(y), float(x))), (y, x)
+
+
+def _cv2_knn2(dl, dr):
+    """What Frame::ComputeStereoFishEyeMatches sees (Frame.cc:1178-1187): BFMatcher(NORM_HAMMING).knnMatch(k=2) + ratio gate."""
+    nq = len(dl)
+    out = np.full((nq, 4), -1, np.int32)
+    ok = np.zeros(nq, np.uint8)
+    if nq == 0 or len(dr) == 0:
+        return out, ok
+    matches = cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(dl, dr, 2)
+    assert len(matches) == nq
+    for q, m in enumerate(matches):
+        for k, dm in enumerate(m):
+            assert dm.queryIdx == q
+            out[q, 2 * k], out[q, 2 * k + 1] = dm.trainIdx, int(dm.distance)
+        ok[q] = len(m) >= 2 and m[0].distance < m[1].distance * 0.7
+    return out, ok
+
+
+@pytest.mark.parametrize("nq,nt,distinct", [(300, 280, 0), (257, 513, 0), (64, 1, 0), (5, 2, 0), (40, 0, 0), (0, 17, 0), (200, 200, 6), (150, 90, 2), (33, 700, 12)])
+def test_lapping_knn_match_matches_cv2(nq, nt, distinct):
+    """`distinct` > 0: descriptors drawn from a few prototypes with a few flipped bits -> many equal distances (tie order)."""
+    rng = np.random.default_rng(nq * 1000 + nt)
+    if distinct:
+        protos = rng.integers(0, 256, (distinct, 32), dtype=np.uint8)
+
+        def draw(n):
+            d = protos[rng.integers(0, distinct, n)].copy()
+            flip = rng.integers(0, 3, n)
+            for i in range(n):
+                for _ in range(flip[i]):
+                    d[i, rng.integers(0, 32)] ^= np.uint8(1 << rng.integers(0, 8))
+            return d
+        dl, dr = draw(nq), draw(nt)
+    else:
+        dl = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
+        dr = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+    want, want_ok = _cv2_knn2(dl, dr)
+    got, got_ok = po.lapping_match(dl, dr)
+    assert np.array_equal(got, want)
+    assert np.array_equal(got_ok, want_ok)
+
+
+def test_lapping_ratio_gate_boundary():
+    """d0 * 10 == d1 * 7 sits exactly on Lowe's boundary: the double product decides (7 < 10 * 0.7 is false in IEEE double)."""
+    dl = np.zeros((1, 32), np.uint8)
+    dr = np.zeros((2, 32), np.uint8)
+    dl[0, 0] = 0x7F                                   # 7 bits away from train 0 (all zero)
+    dr[1, 0], dr[1, 1], dr[1, 2] = 0x7F, 0xFF, 0x03   # train 1: 0 + 8 + 2 = 10 bits away
+    want, want_ok = _cv2_knn2(dl, dr)
+    got, got_ok = po.lapping_match(dl, dr)
+    assert want[0].tolist() == [0, 7, 1, 10]
+    assert np.array_equal(got, want) and np.array_equal(got_ok, want_ok)
+    assert bool(got_ok[0]) == (np.float32(7) < float(np.float32(10)) * 0.7)
