@@ -123,18 +123,26 @@ __global__ void __launch_bounds__(32 * RS_WARPS) k_resize_s12(const __grid_const
     // 32-bit shared-window address of the thread's first word (kept in a register; explicit ld.shared below)
     const uint32_t sBase = smem_u32(tile[wy]) + (uint32_t)(kMarginX + base - boxX) - (uint32_t)(syMin * RS_BOXW);
     uint8_t* D = dst + (size_t)blockIdx.z * dplane + x0 + (size_t)ys * dpitch;
-    // the row tables of the segment, one row per lane, broadcast with shuffles inside the loop
+    // the row tables of the segment, one row per lane (clamped source rows, vertical weights pre-scaled for mad.hi),
+    // broadcast with shuffles inside the loop
     const int myRow = min(ys + (int)threadIdx.x, dh - 1);
     const int myYo = t.yofs[myRow];
+    const uint32_t myRows = (uint32_t)min(max(myYo, 0), sh - 1) | ((uint32_t)min(max(myYo + 1, 0), sh - 1) << 16);
     const uint32_t myBw = *reinterpret_cast<const uint32_t*>(t.yb + 2 * myRow);
-    auto hrow = [&](int sy, uint32_t h[4]) {  // horizontal interpolation of source row sy, >> 4 as cv::resize does
+    const uint32_t myB0 = (myBw & 0xFFFFu) << 12, myB1 = (myBw >> 16) << 12;
+    // Issue balance: the ALU pipe (LOP3 / SHF / PRMT / IADD3) and the FMA pipe (IMAD / IDP) each take one warp instruction
+    // every other cycle per scheduler (profiles/tools/pipe_probe.cu), and cv::resize's vertical pass written with shifts is
+    // almost all ALU.  Here the horizontally interpolated value keeps its low four bits cleared, S' = S & ~15, instead of
+    // being shifted (S >> 4), so that  (b * (S >> 4)) >> 16  ==  mulhi(b << 12, S')  — one IMAD.HI — and the final  >> 2  becomes  * 64  (IMAD) followed by the byte-1 pick of the packing PRMT.
+    auto hrow = [&](int sy, uint32_t h[4]) {  // horizontal interpolation of source row sy
         uint32_t w0, w1, w2;
         asm volatile("ld.shared.u32 %0, [%3];\n\tld.shared.u32 %1, [%3+4];\n\tld.shared.u32 %2, [%3+8];" : "=r"(w0), "=r"(w1), "=r"(w2) : "r"(sBase + (uint32_t)(sy * RS_BOXW)));
-        h[0] = __dp2a_lo(coef[0], __byte_perm(w0, w1, sel[0]), 0u) >> 4;
-        h[1] = __dp2a_lo(coef[1], __byte_perm(w0, w1, sel[1]), 0u) >> 4;
-        h[2] = __dp2a_lo(coef[2], __byte_perm(w0, w1, sel[2]), 0u) >> 4;
-        h[3] = __dp2a_lo(coef[3], __byte_perm(hi3 ? w1 : w0, hi3 ? w2 : w1, sel[3]), 0u) >> 4;
+        h[0] = __dp2a_lo(coef[0], __byte_perm(w0, w1, sel[0]), 0u) & 0xFFFFFFF0u;
+        h[1] = __dp2a_lo(coef[1], __byte_perm(w0, w1, sel[1]), 0u) & 0xFFFFFFF0u;
+        h[2] = __dp2a_lo(coef[2], __byte_perm(w0, w1, sel[2]), 0u) & 0xFFFFFFF0u;
+        h[3] = __dp2a_lo(coef[3], __byte_perm(hi3 ? w1 : w0, hi3 ? w2 : w1, sel[3]), 0u) & 0xFFFFFFF0u;
     };
+    const uint32_t k64 = 64u + ((uint32_t)dw >> 30);  // 64, opaque to the compiler: keeps the multiply an IMAD (FMA pipe) instead of a LEA (ALU pipe)
     mbar_wait(&bars[wy], 0);
     // hA / hB: interpolated source rows rA < rB, consumed as a stream (the lower row of one destination row is usually the
     // upper row of the next)
@@ -142,9 +150,9 @@ __global__ void __launch_bounds__(32 * RS_WARPS) k_resize_s12(const __grid_const
     uint32_t hA[4] = {0, 0, 0, 0}, hB[4] = {0, 0, 0, 0};
     const int nrows = ye - ys;
     for (int k = 0; k < nrows; ++k) {
-        const int yo = __shfl_sync(0xFFFFFFFFu, myYo, k);
-        const uint32_t bw = __shfl_sync(0xFFFFFFFFu, myBw, k);
-        const int sy0 = min(max(yo, 0), sh - 1), sy1 = min(max(yo + 1, 0), sh - 1);
+        const uint32_t rows = __shfl_sync(0xFFFFFFFFu, myRows, k);
+        const uint32_t b0 = __shfl_sync(0xFFFFFFFFu, myB0, k), b1 = __shfl_sync(0xFFFFFFFFu, myB1, k);
+        const int sy0 = (int)(rows & 0xFFFFu), sy1 = (int)(rows >> 16);
         if (sy0 != rA) {
             if (sy0 == rB) {
 #pragma unroll
@@ -153,15 +161,21 @@ __global__ void __launch_bounds__(32 * RS_WARPS) k_resize_s12(const __grid_const
                 hrow(sy0, hA);
             rA = sy0;
         }
-        if (sy1 != rA && sy1 != rB) { hrow(sy1, hB); rB = sy1; }
-        const bool same = sy1 == rA;  // only when the source row index was clamped at the bottom
-        const uint32_t b0 = bw & 0xFFFFu, b1 = bw >> 16;
-        uint32_t v[4];
+        if (sy1 != rB) {
+            if (sy1 == rA) {  // only when the source row index was clamped at the bottom
 #pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = (((b0 * hA[i]) >> 16) + ((b1 * (same ? hA[i] : hB[i])) >> 16) + 2u) >> 2;  // <= 255 by construction
-        const uint32_t out = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
+                for (int i = 0; i < 4; ++i) hB[i] = hA[i];
+            } else
+                hrow(sy1, hB);
+            rB = sy1;
+        }
+        uint32_t u[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) u[i] = (__umulhi(b1, hB[i]) + __umulhi(b0, hA[i]) + 2u) * k64;  // byte 1 = the pixel (<= 255 by construction)
+        const uint32_t out = __byte_perm(__byte_perm(u[0], u[1], 0x0051), __byte_perm(u[2], u[3], 0x0051), 0x5410);
         // lanes past the last column store into the row's right padding (rewritten by k_margin / never read)
-        *reinterpret_cast<uint32_t*>(D + (size_t)k * dpitch) = out;
+        *reinterpret_cast<uint32_t*>(D) = out;
+        D += dpitch;
     }
 }
 
