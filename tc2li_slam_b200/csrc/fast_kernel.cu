@@ -34,13 +34,18 @@ namespace orbx {
 namespace {
 
 constexpr int FW = 1;                    // warps per CTA (every warp is independent; small CTAs pack shared memory best)
-constexpr int CAP = 512;                 // entries per list
+constexpr int CAP = 512;                 // entries of list1 / list2
+constexpr int CAPW = 256;                // entries of listW (32-bit)
 constexpr unsigned FULL = 0xFFFFFFFFu;
 
-// per byte: 0x80 where the byte of d exceeds t (0 <= t <= 254); kAdd = (0x7f - (t & 0x7f)) * 0x01010101
-__device__ __forceinline__ uint32_t bytes_gt(uint32_t d, uint32_t kAdd, bool tHigh) {
-    const uint32_t low = (d & 0x7f7f7f7fu) + kAdd;  // bit 7 of each byte: (d & 0x7f) > (t & 0x7f)
-    return tHigh ? (low & d) : (low | d);           // t >= 128: also needs d >= 128; t < 128: d >= 128 suffices
+// per byte: bit 7 set where the byte of d exceeds t (0 <= t <= 254); kAdd = (0x7f - (t & 0x7f)) * 0x01010101,
+// nh = t >= 128 ? 0 : ~0.  low = bit 7 of each byte: (d & 0x7f) > (t & 0x7f); t >= 128 also needs d >= 128 (low & d), below
+// that d >= 128 suffices (low | d): both are maj(low, d, nh), one LOP3
+__device__ __forceinline__ uint32_t bytes_gt(uint32_t d, uint32_t kAdd, uint32_t nh) {
+    const uint32_t low = (d & 0x7f7f7f7fu) + kAdd;
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(low), "r"(d), "r"(nh));
+    return r;
 }
 
 // byte offsets of the 16 ring pixels inside a tile with row stride TS
@@ -51,7 +56,7 @@ __device__ __forceinline__ uint32_t bytes_gt(uint32_t d, uint32_t kAdd, bool tHi
 struct CellCtx {
     const uint8_t* tile;   // crop byte (r, c) at tile[r * TS + shift + c]
     uint8_t* sc;           // score map, same layout
-    uint16_t* listW;       // words with a compass survivor: tile word index | 4 pixel flags << 12
+    uint32_t* listW;       // words with a compass survivor: tile word index | 4 pixel flags << 24
     uint16_t* list1;       // compass survivors (tile byte offsets); NMS survivors afterwards
     uint16_t* list2;       // corners (tile byte offsets)
     int nw, n1, n2;        // warp-uniform fill levels
@@ -126,8 +131,8 @@ template <int TS>
 __device__ __forceinline__ void flush_W(CellCtx& c, int t) {
     for (int k0 = 0; k0 < c.nw; k0 += 32) {
         const int k = k0 + c.lane;
-        const int e = k < c.nw ? c.listW[k] : 0;
-        const int f4 = e >> 12, off = (e & 0xFFF) * 4;
+        const uint32_t e = k < c.nw ? c.listW[k] : 0u;
+        const int f4 = (int)(e >> 24), off = (int)(e & 0xFFFu) * 4;
         const int cnt = __popc(f4);
         if (c.n1 + 128 > CAP) flush_A2<TS>(c, t);  // warp-uniform
         const unsigned q0 = __ballot_sync(FULL, cnt & 1), q1 = __ballot_sync(FULL, cnt & 2), q2 = __ballot_sync(FULL, cnt & 4);
@@ -170,12 +175,12 @@ __global__ void __launch_bounds__(32 * FW) k_fast_cells(const __grid_constant__ 
     extern __shared__ __align__(128) unsigned char fsm[];
     __shared__ __align__(8) uint64_t bars[FW][2];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int warpBytes = 3 * tileBytes + 3 * CAP * 2;
+    const int warpBytes = 3 * tileBytes + CAPW * 4 + 2 * CAP * 2;
     unsigned char* my = fsm + (size_t)wid * warpBytes;
     CellCtx c;
     c.sc = my + 2 * tileBytes;
-    c.listW = reinterpret_cast<uint16_t*>(my + 3 * tileBytes);
-    c.list1 = c.listW + CAP;
+    c.listW = reinterpret_cast<uint32_t*>(my + 3 * tileBytes);
+    c.list1 = reinterpret_cast<uint16_t*>(c.listW + CAPW);
     c.list2 = c.list1 + CAP;
     c.lane = lane;
     for (int k = lane; k < tileBytes / 16; k += 32) reinterpret_cast<uint4*>(c.sc)[k] = make_uint4(0, 0, 0, 0);  // stays all-zero between cells
@@ -228,39 +233,50 @@ __global__ void __launch_bounds__(32 * FW) k_fast_cells(const __grid_constant__ 
             // ---- pass A: compass test, 4 pixels per lane; words with a survivor are listed with their 4 pixel flags ----
             {
                 const uint32_t kAdd = (uint32_t)(0x7f - (t & 0x7f)) * 0x01010101u;
-                const bool tHigh = t >= 128;
+                const uint32_t nh = t >= 128 ? 0u : 0xFFFFFFFFu;
                 const int items = ih * nW;
                 // bytes outside the interior [0, iw) can only sit in the first / last word of a row
                 const int xb0 = 4 * wFirst - 3 - shift;  // interior x of byte 0 of the first word (<= 0)
                 const uint32_t maskFirst = 0x80808080u << (8 * (-xb0));
                 const uint32_t maskLast = 0x80808080u >> (8 * (xb0 + 4 * nW - iw));
-                auto compass = [&](int itx, int& wofs) -> uint32_t {
-                    if (itx >= items) return 0u;
-                    const int y = nW == 1 ? itx : (int)__umulhi((uint32_t)itx, magicW), cc = itx - y * nW;  // (the magic of 1 does not fit 32 bits)
-                    wofs = (y + 3) * (TS / 4) + wFirst + cc;
+                // item = (row y, word cc) in row-major order; two items per lane per trip (32 apart), walked incrementally:
+                // 64 items further is dq rows and dr words on, with a carry into the next row
+                const int dq = nW == 1 ? 64 : (int)__umulhi(64u, magicW), dr = 64 - dq * nW;  // (the magic of 1 does not fit 32 bits)
+                const int dW = dq * (TS / 4) + dr, wrapW = TS / 4 - nW;
+                int it0 = lane, it1 = lane + 32;
+                int y0 = nW == 1 ? it0 : (int)__umulhi((uint32_t)it0, magicW), y1 = nW == 1 ? it1 : (int)__umulhi((uint32_t)it1, magicW);
+                int cc0 = it0 - y0 * nW, cc1 = it1 - y1 * nW;
+                int wo0 = (y0 + 3) * (TS / 4) + wFirst + cc0, wo1 = (y1 + 3) * (TS / 4) + wFirst + cc1;
+                auto compass = [&](bool live, int cc, int wofs) -> uint32_t {
+                    if (!live) return 0u;
                     const uint32_t* row = tileW + wofs;
                     const uint32_t cur = row[0], prev = row[-1], next = row[1], up = row[3 * (TS / 4)], dn = row[-3 * (TS / 4)];
                     const uint32_t e = __funnelshift_r(cur, next, 24);  // pixels at x + 3
                     const uint32_t wv = __funnelshift_r(prev, cur, 8);  // pixels at x - 3
-                    const uint32_t ns = bytes_gt(__vabsdiffu4(up, cur), kAdd, tHigh) | bytes_gt(__vabsdiffu4(dn, cur), kAdd, tHigh);
-                    const uint32_t ew = bytes_gt(__vabsdiffu4(e, cur), kAdd, tHigh) | bytes_gt(__vabsdiffu4(wv, cur), kAdd, tHigh);
-                    return ns & ew & (cc == 0 ? maskFirst : 0x80808080u) & (cc == nW - 1 ? maskLast : 0x80808080u);
+                    const uint32_t ns = bytes_gt(__vabsdiffu4(up, cur), kAdd, nh) | bytes_gt(__vabsdiffu4(dn, cur), kAdd, nh);
+                    const uint32_t ew = bytes_gt(__vabsdiffu4(e, cur), kAdd, nh) | bytes_gt(__vabsdiffu4(wv, cur), kAdd, nh);
+                    const uint32_t m = (cc == 0 ? maskFirst : 0x80808080u) & (cc == nW - 1 ? maskLast : 0x80808080u);
+                    return ns & ew & m;
                 };
                 auto append = [&](uint32_t F, int wofs) {
                     const unsigned bal = __ballot_sync(FULL, F != 0);
                     if (bal) {
-                        if (c.nw + 32 > CAP) flush_W<TS>(c, t);  // warp-uniform
-                        // bits 7/15/23/31 -> 4 contiguous flag bits
-                        if (F) c.listW[c.nw + __popc(bal & ((1u << lane) - 1))] = (uint16_t)(wofs | ((((F >> 7) * 0x01020408u) >> 24) << 12));
+                        if (c.nw + 32 > CAPW) flush_W<TS>(c, t);  // warp-uniform
+                        // bits 7/15/23/31 -> 4 contiguous flag bits 24..27
+                        if (F) c.listW[c.nw + __popc(bal & ((1u << lane) - 1))] = (((F >> 7) * 0x01020408u) & 0x0F000000u) | (uint32_t)wofs;
                         c.nw += __popc(bal);
                     }
                 };
-                for (int it0 = 0; it0 < items; it0 += 64) {  // two independent items per lane per trip (ILP: 16 warps per SM)
-                    int w0 = 0, w1 = 0;
-                    const uint32_t F0 = compass(it0 + lane, w0);
-                    const uint32_t F1 = compass(it0 + 32 + lane, w1);
-                    append(F0, w0);
-                    append(F1, w1);
+                for (int base = 0; base < items; base += 64) {
+                    const uint32_t F0 = compass(it0 < items, cc0, wo0);
+                    const uint32_t F1 = compass(it1 < items, cc1, wo1);
+                    append(F0, wo0);
+                    append(F1, wo1);
+                    it0 += 64; it1 += 64;
+                    cc0 += dr; wo0 += dW;
+                    cc1 += dr; wo1 += dW;
+                    if (cc0 >= nW) { cc0 -= nW; wo0 += wrapW; }
+                    if (cc1 >= nW) { cc1 -= nW; wo1 += wrapW; }
                 }
                 __syncwarp();
             }
@@ -364,7 +380,7 @@ void make_cell_table(const Geom& g, uint4* tab, int* tileRows, int* maxCw) {
 
 // box rows of 64 bytes hold crops up to 49 columns (15 alignment bytes + crop), 96 bytes up to 81 (the largest possible: 78)
 int fast_tile_stride(int maxCw) { return maxCw <= 49 ? 64 : 96; }
-static size_t fast_warp_bytes(int tileRows, int ts) { return (size_t)3 * tileRows * ts + 3 * CAP * 2; }
+static size_t fast_warp_bytes(int tileRows, int ts) { return (size_t)3 * tileRows * ts + CAPW * 4 + 2 * CAP * 2; }
 
 cudaError_t fast_configure(int tileRows, int ts) {
     const int smem = (int)(FW * fast_warp_bytes(tileRows, ts));
