@@ -22,7 +22,7 @@ namespace orbx {
 namespace {
 
 constexpr int OT_THREADS = PS_THREADS;
-constexpr int OT_SMEM_CANDS = 2048;   // candidate lists up to this size are staged in shared memory (6 bytes each)
+constexpr int OT_STAGE_MAX = 2048;    // node labels of candidate lists up to the launch's stage capacity live in shared memory (2 bytes each)
 typedef StdSortEmul<16> NodeSort;    // element = (nKeys << 12 | UL.x) << 16 | node index: any key size
 typedef StdSortEmul<32> NodeSort32;  // element = (nKeys << 12 | UL.x) << 32 | node index: keys below 2^32 (fewer than 2^20 candidates)
 
@@ -46,10 +46,14 @@ struct OctShared {
     uint8_t* split;            // [cap]   node is split in this phase-2 round
 };
 
-__host__ __device__ inline size_t oct_smem_bytes(int cap) {
+__host__ __device__ inline size_t oct_node_bytes(int cap) {
     size_t c = (size_t)((cap + 7) & ~7);
-    return c * (2 * sizeof(Box) + 2 * 4 + 16 + 8 + 8 + 2 * 8 + 1) + 128 + (size_t)OT_SMEM_CANDS * 6;
+    return c * (2 * sizeof(Box) + 2 * 4 + 16 + 8 + 8 + 2 * 8 + 1) + 128;
 }
+__host__ __device__ inline size_t oct_smem_bytes(int cap, int stageCap) { return oct_node_bytes(cap) + (size_t)stageCap * 2; }
+// labels staged for lists up to four times the level's quota (at least 512, at most OT_STAGE_MAX entries); longer lists
+// keep their labels in global memory
+static int oct_stage_cap(int quota) { return std::min(OT_STAGE_MAX, std::max(512, (4 * quota + 63) & ~63)); }
 
 __device__ inline OctShared carve(unsigned char* base, int capIn) {
     const size_t cap = (size_t)((capIn + 7) & ~7);
@@ -138,7 +142,7 @@ __device__ __forceinline__ void emit_children(const OctShared& s, int cur, int i
 //            at  sum_{r<r'<t} nch_r',  t = number of nodes processed before the reference's `break`;
 //   nodes that are not split follow all child blocks in their old relative order.
 // Only the libstdc++-exact sort of phase 2 (ties decide results) runs on a single thread.
-__global__ void __launch_bounds__(OT_THREADS) k_octree(const __grid_constant__ Geom g, const Buffers b, int levelBase) {
+__global__ void __launch_bounds__(OT_THREADS) k_octree(const __grid_constant__ Geom g, const Buffers b, int levelBase, int stageCap) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     __shared__ int part[3][OT_THREADS + 1];
     __shared__ int sh_t;
@@ -154,17 +158,12 @@ __global__ void __launch_bounds__(OT_THREADS) k_octree(const __grid_constant__ G
         return;
     }
     const OctShared s = carve(smemRaw, cap);
-    // candidates and their node labels: staged in shared memory when they fit (every round walks them twice; from global
-    // memory the kernel is bound by L2 latency at two warps per CTA), otherwise in place in global memory
-    const uint32_t* cand = b.cand + L.candOff + (size_t)img * L.candCap;
+    // The CTA is latency bound (two warps, a barrier every few instructions): what matters is how many CTAs an SM holds, i.e.
+    // shared memory per CTA.  The candidates are read-only and come through L1 (ld.global.nc: every round walks them twice and
+    // they stay resident); their node labels, rewritten every round, are staged in shared memory when the list fits.
+    const uint32_t* __restrict__ cand = b.cand + L.candOff + (size_t)img * L.candCap;
     uint16_t* pnode = b.pnode + L.candOff + (size_t)img * L.candCap;
-    if (n <= OT_SMEM_CANDS) {
-        unsigned char* extra = smemRaw + oct_smem_bytes(cap) - (size_t)OT_SMEM_CANDS * 6;
-        uint32_t* sc = reinterpret_cast<uint32_t*>(extra);
-        for (int c = tid; c < n; c += OT_THREADS) sc[c] = cand[c];
-        cand = sc;
-        pnode = reinterpret_cast<uint16_t*>(extra + (size_t)OT_SMEM_CANDS * 4);
-    }
+    if (n <= stageCap) pnode = reinterpret_cast<uint16_t*>(smemRaw + oct_node_bytes(cap));
 
     // ---- roots (ORBextractor.cc:533-575): nIni vertical strips; empty ones are dropped ----
     const int nIni = L.nIni;
@@ -172,7 +171,7 @@ __global__ void __launch_bounds__(OT_THREADS) k_octree(const __grid_constant__ G
     for (int k = tid; k < nIni; k += OT_THREADS) rootCnt[k] = 0;
     __syncthreads();
     for (int c = tid; c < n; c += OT_THREADS) {
-        int r = (int)__fdiv_rn((float)cand_x(cand[c]), L.hX);  // vpIniNodes[kp.pt.x/hX]
+        int r = (int)__fdiv_rn((float)cand_x(__ldg(cand + c)), L.hX);  // vpIniNodes[kp.pt.x/hX]
         r = min(r, nIni - 1);
         pnode[c] = (uint16_t)r;
         atomicAdd(&rootCnt[r], 1);
@@ -209,7 +208,7 @@ __global__ void __launch_bounds__(OT_THREADS) k_octree(const __grid_constant__ G
         for (int c = tid; c < n; c += OT_THREADS) {
             const int node = pnode[c] & 0x3FFF;
             if (s.cnt[cur][node] > 1) {
-                const uint32_t pc = cand[c];
+                const uint32_t pc = __ldg(cand + c);
                 const Box bx = s.box[cur][node];
                 const int mx = bx.x0 + ((bx.x1 - bx.x0 + 1) >> 1), my = bx.y0 + ((bx.y1 - bx.y0 + 1) >> 1);
                 const int q = (cand_x(pc) < mx ? 0 : 1) | (cand_y(pc) < my ? 0 : 2);
@@ -334,7 +333,7 @@ __global__ void __launch_bounds__(OT_THREADS) k_octree(const __grid_constant__ G
     __syncthreads();
     const unsigned long long mask40 = (1ull << 40) - 1;
     for (int c = tid; c < n; c += OT_THREADS) {
-        const uint32_t pc = cand[c];
+        const uint32_t pc = __ldg(cand + c);
         const unsigned long long v = ((unsigned long long)cand_r(pc) << 40) | (~cand_order_key(pc, L.wCell, L.hCell) & mask40);
         atomicMax(&s.srt[pnode[c] & 0x3FFF], v);
     }
@@ -348,38 +347,34 @@ __global__ void __launch_bounds__(OT_THREADS) k_octree(const __grid_constant__ G
     if (tid == 0) *selCount = size;
 }
 
-size_t octree_smem_bytes(int nodeCap) { return oct_smem_bytes(nodeCap); }
+size_t octree_smem_bytes(int nodeCap) { return oct_smem_bytes(nodeCap, OT_STAGE_MAX); }
 
 // opt in to > 48 KB of dynamic shared memory (quotas above ~700 nodes per level); per device, called at handle creation
 cudaError_t octree_configure(int maxNodeCap) {
-    const size_t smem = oct_smem_bytes(maxNodeCap);
+    const size_t smem = oct_smem_bytes(maxNodeCap, OT_STAGE_MAX);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     return cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024));
 }
 
-// Levels are launched in two groups (large / small quotas) so that the small levels do not reserve the shared memory of the
-// largest one: the serial controller of a CTA is latency bound, what matters is how many CTAs are resident per SM.
-cudaError_t launch_octree(const Geom& g, const Buffers& b, int nImages, cudaStream_t s) {
-    int maxCap = 0;
-    for (int l = 0; l < g.nlevels; ++l) maxCap = std::max(maxCap, g.lv[l].nodeCap);
-    // node capacities shrink with the level (quota decay): split where the capacity first drops below half of the largest
-    int split = g.nlevels;
-    for (int l = 0; l < g.nlevels; ++l)
-        if (2 * g.lv[l].nodeCap <= maxCap) { split = l; break; }
-    for (int l = split; l < g.nlevels; ++l)
-        if (2 * g.lv[l].nodeCap > maxCap) { split = g.nlevels; break; }  // not monotone: one group
-    if (split > 0) {
-        dim3 grid(split, nImages);
-        k_octree<<<grid, OT_THREADS, oct_smem_bytes(maxCap), s>>>(g, b, 0);
+// Many images: one launch per level, each with exactly the shared memory its node capacity needs — the small levels then fit
+// three to four times as many CTAs per SM as the largest one.  Few images (large single frames): one launch over all levels,
+// so that the levels of an image run side by side instead of one after the other.
+cudaError_t launch_octree(const Geom& g, const Buffers& b, int nImages, int numSMs, cudaStream_t s) {
+    if (nImages * g.nlevels <= 8 * numSMs) {
+        int maxCap = 0;
+        for (int l = 0; l < g.nlevels; ++l) maxCap = std::max(maxCap, g.lv[l].nodeCap);
+        dim3 grid(g.nlevels, nImages);
+        k_octree<<<grid, OT_THREADS, oct_smem_bytes(maxCap, OT_STAGE_MAX), s>>>(g, b, 0, OT_STAGE_MAX);
+        return cudaGetLastError();
     }
-    if (split < g.nlevels) {
-        int cap2 = 0;
-        for (int l = split; l < g.nlevels; ++l) cap2 = std::max(cap2, g.lv[l].nodeCap);
-        dim3 grid(g.nlevels - split, nImages);
-        k_octree<<<grid, OT_THREADS, oct_smem_bytes(cap2), s>>>(g, b, split);
+    for (int l = 0; l < g.nlevels; ++l) {
+        const int stageCap = oct_stage_cap(g.lv[l].quota);
+        dim3 grid(1, nImages);
+        k_octree<<<grid, OT_THREADS, oct_smem_bytes(g.lv[l].nodeCap, stageCap), s>>>(g, b, l, stageCap);
     }
     return cudaGetLastError();
 }
+int octree_launch_count(const Geom& g, int nImages, int numSMs) { return nImages * g.nlevels <= 8 * numSMs ? 1 : g.nlevels; }
 
 // test hooks: the sort emulation in one device thread, and the CTA-parallel version k_octree runs
 __global__ void k_debug_sort(unsigned long long* buf, int n, int forceDepth) {

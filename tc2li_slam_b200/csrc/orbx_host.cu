@@ -531,7 +531,7 @@ static int run_range_lane(orbx_batch* b, int first, int n, const int* lapping, i
         for (int l = 0; l < g.nlevels; ++l) { launch_blur(g, buf, b->blurMaps, l, n, b->taps, s); ++launches; }
     mark();
     {
-        cudaError_t e = launch_octree(g, buf, n, s); launches += 2;  // two level groups
+        cudaError_t e = launch_octree(g, buf, n, b->numSMs, s); launches += octree_launch_count(g, n, b->numSMs);
         if (e != cudaSuccess) return cuda_fail(e, "octree launch");
     }
     mark();

@@ -114,7 +114,8 @@ void launch_blur(const Geom& g, const Buffers& b, const LevelMaps& maps, int lev
 int blur_encode_maps(const Geom& g, uint8_t* pyr, int nImages, LevelMaps* out);
 void launch_pyramid_level(const Geom& g, const Buffers& b, const LevelMaps& maps, int level, const ResizeTab& tab, int nImages, cudaStream_t s);
 int resize_encode_maps(const Geom& g, uint8_t* pyr, int nImages, LevelMaps* out);
-cudaError_t launch_octree(const Geom& g, const Buffers& b, int nImages, cudaStream_t s);
+cudaError_t launch_octree(const Geom& g, const Buffers& b, int nImages, int numSMs, cudaStream_t s);
+int octree_launch_count(const Geom& g, int nImages, int numSMs);
 void launch_assemble(const Geom& g, const Buffers& b, int nImages, cudaStream_t s);
 struct DescMaps {  // per level: 48x31 boxes of the pyramid (IC_Angle patch), 64x37 boxes of the blurred pyramid (rBRIEF window)
     CUtensorMap ic[ORBX_MAX_LEVELS];
