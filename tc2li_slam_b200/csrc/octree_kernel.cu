@@ -21,7 +21,9 @@ namespace orbx {
 
 namespace {
 
-constexpr int OT_THREADS = PS_THREADS;
+constexpr int OT_MAX_WARPS = PS_MAX_WARPS;
+constexpr int OT_T_BATCH = 128;       // threads per CTA when many images are in flight (shared memory bounds the CTAs per SM)
+constexpr int OT_T_FEW = 256;         // threads per CTA for a few large frames (long candidate lists, few CTAs)
 constexpr int OT_STAGE_MAX = 2048;    // node labels of candidate lists up to the launch's stage capacity live in shared memory (2 bytes each)
 typedef StdSortEmul<16> NodeSort;    // element = (nKeys << 12 | UL.x) << 16 | node index: any key size
 typedef StdSortEmul<32> NodeSort32;  // element = (nKeys << 12 | UL.x) << 32 | node index: keys below 2^32 (fewer than 2^20 candidates)
@@ -78,29 +80,39 @@ __device__ inline OctShared carve(unsigned char* base, int capIn) {
     return s;
 }
 
-// In-place exclusive scan of three uint16 arrays of length n by the whole CTA (chunk per thread, serial over the chunk
-// sums).  Returns the three totals to every thread.  `part` is a [3][OT_THREADS + 1] int scratch in shared memory.
-__device__ inline void scan3(uint16_t* a0, uint16_t* a1, uint16_t* a2, int n, int (*part)[OT_THREADS + 1], int& t0, int& t1, int& t2) {
-    const int tid = threadIdx.x;
+// In-place exclusive scan of three uint16 arrays of length n by the whole CTA (chunk per thread, warp-shuffle scan of the
+// chunk sums, then the warp totals).  Returns the three totals to every thread.  `part` is a [3][OT_MAX_WARPS] int scratch in
+// shared memory.
+template <int OT_THREADS>
+__device__ inline void scan3(uint16_t* a0, uint16_t* a1, uint16_t* a2, int n, int (*part)[OT_MAX_WARPS], int& t0, int& t1, int& t2) {
+    constexpr int NW = OT_THREADS / 32;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int per = (n + OT_THREADS - 1) / OT_THREADS;
     const int lo = min(tid * per, n), hi = min(lo + per, n);
     int s0 = 0, s1 = 0, s2 = 0;
     for (int i = lo; i < hi; ++i) { s0 += a0[i]; s1 += a1[i]; s2 += a2[i]; }
-    part[0][tid] = s0; part[1][tid] = s1; part[2][tid] = s2;
-    __syncthreads();
-    if (tid < 3) {
-        int run = 0;
-        for (int k = 0; k < OT_THREADS; ++k) { const int v = part[tid][k]; part[tid][k] = run; run += v; }
-        part[tid][OT_THREADS] = run;
+    int i0 = s0, i1 = s1, i2 = s2;  // inclusive warp scans of the chunk sums
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u0 = __shfl_up_sync(0xFFFFFFFFu, i0, o), u1 = __shfl_up_sync(0xFFFFFFFFu, i1, o), u2 = __shfl_up_sync(0xFFFFFFFFu, i2, o);
+        if (lane >= o) { i0 += u0; i1 += u1; i2 += u2; }
     }
+    if (lane == 31) { part[0][wid] = i0; part[1][wid] = i1; part[2][wid] = i2; }
     __syncthreads();
-    s0 = part[0][tid]; s1 = part[1][tid]; s2 = part[2][tid];
+    int b0 = 0, b1 = 0, b2 = 0;
+    t0 = 0; t1 = 0; t2 = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        const int p0 = part[0][w], p1 = part[1][w], p2 = part[2][w];
+        if (w < wid) { b0 += p0; b1 += p1; b2 += p2; }
+        t0 += p0; t1 += p1; t2 += p2;
+    }
+    s0 = b0 + i0 - s0; s1 = b1 + i1 - s1; s2 = b2 + i2 - s2;  // exclusive prefix of this thread's chunk
     for (int i = lo; i < hi; ++i) {
         const int x0 = a0[i], x1 = a1[i], x2 = a2[i];
         a0[i] = (uint16_t)s0; a1[i] = (uint16_t)s1; a2[i] = (uint16_t)s2;
         s0 += x0; s1 += x1; s2 += x2;
     }
-    t0 = part[0][OT_THREADS]; t1 = part[1][OT_THREADS]; t2 = part[2][OT_THREADS];
     __syncthreads();
 }
 
@@ -142,9 +154,10 @@ __device__ __forceinline__ void emit_children(const OctShared& s, int cur, int i
 //            at  sum_{r<r'<t} nch_r',  t = number of nodes processed before the reference's `break`;
 //   nodes that are not split follow all child blocks in their old relative order.
 // Only the libstdc++-exact sort of phase 2 (ties decide results) runs on a single thread.
+template <int OT_THREADS>
 __global__ void __launch_bounds__(OT_THREADS) k_octree(const __grid_constant__ Geom g, const Buffers b, int levelBase, int stageCap) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
-    __shared__ int part[3][OT_THREADS + 1];
+    __shared__ int part[3][OT_MAX_WARPS];
     __shared__ int sh_t;
     __shared__ ParSortShared psh;
 
@@ -180,7 +193,7 @@ __global__ void __launch_bounds__(OT_THREADS) k_octree(const __grid_constant__ G
     for (int k = tid; k < nIni; k += OT_THREADS) { s.v0[k] = rootCnt[k] > 0; s.v1[k] = 0; s.v2[k] = 0; }
     __syncthreads();
     int cur = 0, size, d1, d2;
-    scan3(s.v0, s.v1, s.v2, nIni, part, size, d1, d2);
+    scan3<OT_THREADS>(s.v0, s.v1, s.v2, nIni, part, size, d1, d2);
     for (int k = tid; k < nIni; k += OT_THREADS) {
         s.tailIdx[k] = s.v0[k];
         if (rootCnt[k] > 0) {
@@ -235,7 +248,7 @@ __global__ void __launch_bounds__(OT_THREADS) k_octree(const __grid_constant__ G
             }
             __syncthreads();
             int C, T, R;
-            scan3(s.v0, s.v1, s.v2, size, part, C, T, R);
+            scan3<OT_THREADS>(s.v0, s.v1, s.v2, size, part, C, T, R);
             newSize = C + T; nNew = R;
             if (newSize > cap) { err = true; break; }
             for (int i = tid; i < size; i += OT_THREADS) {
@@ -260,8 +273,8 @@ __global__ void __launch_bounds__(OT_THREADS) k_octree(const __grid_constant__ G
             __syncthreads();
             // scratch: the next node table's boxes (not written yet) and two of the scan arrays
             unsigned long long* tmp = reinterpret_cast<unsigned long long*>(s.box[cur ^ 1]);
-            if (small) par_std_sort<32>(s.srt, nRec, tmp, s.v0, s.v1, psh);
-            else par_std_sort<16>(s.srt, nRec, tmp, s.v0, s.v1, psh);
+            if (small) par_std_sort<32, OT_THREADS>(s.srt, nRec, tmp, s.v0, s.v1, psh);
+            else par_std_sort<16, OT_THREADS>(s.srt, nRec, tmp, s.v0, s.v1, psh);
             for (int i = tid; i < size; i += OT_THREADS) s.split[i] = 0;
             __syncthreads();
             // rank r = 0 .. nRec-1 <-> node srt[nRec-1-r]; growth of the list when it is split = non-empty children - 1
@@ -275,7 +288,7 @@ __global__ void __launch_bounds__(OT_THREADS) k_octree(const __grid_constant__ G
             }
             __syncthreads();
             int C, G, R;
-            scan3(s.v0, s.v1, s.v2, nRec, part, C, G, R);
+            scan3<OT_THREADS>(s.v0, s.v1, s.v2, nRec, part, C, G, R);
             // the reference breaks after the first split that brings the list to >= N nodes
             for (int r = tid; r < nRec; r += OT_THREADS) {
                 const int after = size + s.v1[r] + (int)s.tailIdx[r] - 1;  // list size after the r-th split
@@ -295,7 +308,7 @@ __global__ void __launch_bounds__(OT_THREADS) k_octree(const __grid_constant__ G
             for (int i = tid; i < size; i += OT_THREADS) { s.v0[i] = (uint16_t)(s.split[i] ? 0 : 1); s.v1[i] = 0; s.v2[i] = 0; }
             __syncthreads();
             int T, u1, u2;
-            scan3(s.v0, s.v1, s.v2, size, part, T, u1, u2);
+            scan3<OT_THREADS>(s.v0, s.v1, s.v2, size, part, T, u1, u2);
             newSize = Ct + T;
             if (newSize > cap) { err = true; break; }
             for (int i = tid; i < size; i += OT_THREADS) {
@@ -353,7 +366,9 @@ size_t octree_smem_bytes(int nodeCap) { return oct_smem_bytes(nodeCap, OT_STAGE_
 cudaError_t octree_configure(int maxNodeCap) {
     const size_t smem = oct_smem_bytes(maxNodeCap, OT_STAGE_MAX);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    return cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024));
+    cudaError_t e = cudaFuncSetAttribute(k_octree<OT_T_BATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_octree<OT_T_FEW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024));
 }
 
 // Many images: one launch per level, each with exactly the shared memory its node capacity needs — the small levels then fit
@@ -364,13 +379,13 @@ cudaError_t launch_octree(const Geom& g, const Buffers& b, int nImages, int numS
         int maxCap = 0;
         for (int l = 0; l < g.nlevels; ++l) maxCap = std::max(maxCap, g.lv[l].nodeCap);
         dim3 grid(g.nlevels, nImages);
-        k_octree<<<grid, OT_THREADS, oct_smem_bytes(maxCap, OT_STAGE_MAX), s>>>(g, b, 0, OT_STAGE_MAX);
+        k_octree<OT_T_FEW><<<grid, OT_T_FEW, oct_smem_bytes(maxCap, OT_STAGE_MAX), s>>>(g, b, 0, OT_STAGE_MAX);
         return cudaGetLastError();
     }
     for (int l = 0; l < g.nlevels; ++l) {
         const int stageCap = oct_stage_cap(g.lv[l].quota);
         dim3 grid(1, nImages);
-        k_octree<<<grid, OT_THREADS, oct_smem_bytes(g.lv[l].nodeCap, stageCap), s>>>(g, b, l, stageCap);
+        k_octree<OT_T_BATCH><<<grid, OT_T_BATCH, oct_smem_bytes(g.lv[l].nodeCap, stageCap), s>>>(g, b, l, stageCap);
     }
     return cudaGetLastError();
 }

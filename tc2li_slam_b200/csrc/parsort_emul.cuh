@@ -17,16 +17,19 @@
 
 namespace orbx {
 
-constexpr int PS_THREADS = 64;
+constexpr int PS_THREADS = 64;      // default CTA size of the callers
+constexpr int PS_MAX_WARPS = 8;
 
 struct ParSortShared {
     int stF[48], stL[48], stD[48];
-    int sp, first, last, depth, done, K, totGe, totLe, warpGe[2], warpLe[2];
+    int sp, first, last, depth, done, K, totGe, totLe, warpGe[PS_MAX_WARPS], warpLe[PS_MAX_WARPS];
 };
 
-template <int KeyShift>
+template <int KeyShift, int THREADS = PS_THREADS>
 __device__ inline void par_std_sort(unsigned long long* a, int n, unsigned long long* tmp, uint16_t* posL, uint16_t* posR, ParSortShared& sh) {
     typedef StdSortEmul<KeyShift> S;
+    constexpr int PS_THREADS = THREADS, NW = THREADS / 32;
+    static_assert(NW >= 1 && NW <= PS_MAX_WARPS, "CTA size");
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (n <= 16) {
         if (tid == 0) S::insertion_sort(a, 0, n);
@@ -75,9 +78,15 @@ __device__ inline void par_std_sort(unsigned long long* a, int n, unsigned long 
         }
         if (lane == 31) { sh.warpGe[wid] = ige; sh.warpLe[wid] = ile; }
         __syncthreads();
-        const int totGe = sh.warpGe[0] + sh.warpGe[1], totLe = sh.warpLe[0] + sh.warpLe[1];
-        int rg = ige - ge + (wid ? sh.warpGe[0] : 0);   // # >= pivot before this chunk
-        int rl = ile - le + (wid ? sh.warpLe[0] : 0);   // # <= pivot before this chunk
+        int totGe = 0, totLe = 0, befGe = 0, befLe = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            const int g2 = sh.warpGe[w], l2 = sh.warpLe[w];
+            if (w < wid) { befGe += g2; befLe += l2; }
+            totGe += g2; totLe += l2;
+        }
+        int rg = ige - ge + befGe;   // # >= pivot before this chunk
+        int rl = ile - le + befLe;   // # <= pivot before this chunk
         for (int x = c0; x < c1; ++x) {
             const unsigned long long e = a[x];
             if (!S::lt(e, pv)) posL[rg++] = (uint16_t)x;                 // L_k, k counted from the left
