@@ -200,10 +200,14 @@ __global__ void __launch_bounds__(32 * FW) k_fast_cells(const __grid_constant__ 
     };
     int w = blockIdx.x * FW + wid;
     if (lane == 0 && w < nWork) issue(w, 0);
-    for (int it = 0; w < nWork; w += stride, ++it) {
+    // (image, cell) of the work item, walked incrementally: `stride` items further is dImg images and dCell cells on
+    const int dImg = stride / nCells, dCell = stride - dImg * nCells;
+    int imgRel = w / nCells, cellIdx = w - imgRel * nCells;
+    for (int it = 0; w < nWork; w += stride, ++it, imgRel += dImg, cellIdx += dCell) {
         const int buf = it & 1;
+        if (cellIdx >= nCells) { cellIdx -= nCells; ++imgRel; }
         if (lane == 0 && w + stride < nWork) issue(w + stride, buf ^ 1);
-        const int imgRel = w / nCells, cellIdx = w - imgRel * nCells, img = b.imgBase + imgRel;
+        const int img = b.imgBase + imgRel;
         const uint4 cd = __ldg(b.cellTab + cellIdx);
         const int iniX = cd.x & 0xFFFF, iniY = cd.x >> 16;
         const int cw = cd.y & 0xFF, ch = (cd.y >> 8) & 0xFF, level = (cd.y >> 16) & 0xFF, kind = cd.y >> 24;
@@ -239,14 +243,19 @@ __global__ void __launch_bounds__(32 * FW) k_fast_cells(const __grid_constant__ 
                 const int xb0 = 4 * wFirst - 3 - shift;  // interior x of byte 0 of the first word (<= 0)
                 const uint32_t maskFirst = 0x80808080u << (8 * (-xb0));
                 const uint32_t maskLast = 0x80808080u >> (8 * (xb0 + 4 * nW - iw));
-                // item = (row y, word cc) in row-major order; two items per lane per trip (32 apart), walked incrementally:
-                // 64 items further is dq rows and dr words on, with a carry into the next row
-                const int dq = nW == 1 ? 64 : (int)__umulhi(64u, magicW), dr = 64 - dq * nW;  // (the magic of 1 does not fit 32 bits)
+                // item = (row y, word cc) in row-major order; NI items per lane per trip (32 apart), walked incrementally:
+                // 32 * NI items further is dq rows and dr words on, with a carry into the next row
+                constexpr int NI = 2;
+                const int dq = nW == 1 ? 32 * NI : (int)__umulhi(32u * NI, magicW), dr = 32 * NI - dq * nW;  // (the magic of 1 does not fit 32 bits)
                 const int dW = dq * (TS / 4) + dr, wrapW = TS / 4 - nW;
-                int it0 = lane, it1 = lane + 32;
-                int y0 = nW == 1 ? it0 : (int)__umulhi((uint32_t)it0, magicW), y1 = nW == 1 ? it1 : (int)__umulhi((uint32_t)it1, magicW);
-                int cc0 = it0 - y0 * nW, cc1 = it1 - y1 * nW;
-                int wo0 = (y0 + 3) * (TS / 4) + wFirst + cc0, wo1 = (y1 + 3) * (TS / 4) + wFirst + cc1;
+                int itx[NI], ccs[NI], wos[NI];
+#pragma unroll
+                for (int j = 0; j < NI; ++j) {
+                    itx[j] = lane + 32 * j;
+                    const int y = nW == 1 ? itx[j] : (int)__umulhi((uint32_t)itx[j], magicW);
+                    ccs[j] = itx[j] - y * nW;
+                    wos[j] = (y + 3) * (TS / 4) + wFirst + ccs[j];
+                }
                 auto compass = [&](bool live, int cc, int wofs) -> uint32_t {
                     if (!live) return 0u;
                     const uint32_t* row = tileW + wofs;
@@ -267,16 +276,17 @@ __global__ void __launch_bounds__(32 * FW) k_fast_cells(const __grid_constant__ 
                         c.nw += __popc(bal);
                     }
                 };
-                for (int base = 0; base < items; base += 64) {
-                    const uint32_t F0 = compass(it0 < items, cc0, wo0);
-                    const uint32_t F1 = compass(it1 < items, cc1, wo1);
-                    append(F0, wo0);
-                    append(F1, wo1);
-                    it0 += 64; it1 += 64;
-                    cc0 += dr; wo0 += dW;
-                    cc1 += dr; wo1 += dW;
-                    if (cc0 >= nW) { cc0 -= nW; wo0 += wrapW; }
-                    if (cc1 >= nW) { cc1 -= nW; wo1 += wrapW; }
+                for (int base = 0; base < items; base += 32 * NI) {
+                    uint32_t F[NI];
+#pragma unroll
+                    for (int j = 0; j < NI; ++j) F[j] = compass(itx[j] < items, ccs[j], wos[j]);
+#pragma unroll
+                    for (int j = 0; j < NI; ++j) {
+                        append(F[j], wos[j]);
+                        itx[j] += 32 * NI;
+                        ccs[j] += dr; wos[j] += dW;
+                        if (ccs[j] >= nW) { ccs[j] -= nW; wos[j] += wrapW; }
+                    }
                 }
                 __syncwarp();
             }
