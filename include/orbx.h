@@ -85,6 +85,21 @@ int orbx_extract_stereo(orbx_extractor* left, orbx_extractor* right, const uint8
                         orbx_keypoint* kps_right, uint8_t* desc_right, int cap_right, int* n_right, int* mono_right);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * The step BEFORE the extractor in the caller: Tracking::GrabImageStereoLidar (Tracking.cc:1646-1671, and the same block in
+ * the other Grab* entry points) converts 3- and 4-channel inputs with cvtColor(COLOR_RGB2GRAY | COLOR_BGR2GRAY |
+ * COLOR_RGBA2GRAY | COLOR_BGRA2GRAY), chosen by Camera.RGB (mbRGB), before it constructs the Frame.  These entry points take
+ * the interleaved 8-bit colour image as it is (channels = 3 or 4, rgb != 0 <=> mbRGB: the first channel is red), convert on
+ * the device with OpenCV 4's arithmetic, gray = (R*9798 + G*19235 + B*3735 + 2^14) >> 15, bit-identical to cv::cvtColor, and
+ * extract.  The grey image the reference keeps (Tracking::mImGray) is level 0: orbx_get_level(h, 0, dst, stride, 0).
+ * ---------------------------------------------------------------------------------------------------------------- */
+int orbx_extract_color(orbx_extractor* h, const uint8_t* image, int width, int height, size_t stride, int channels, int rgb, int lap0, int lap1,
+                       orbx_keypoint* keypoints, uint8_t* descriptors, int capacity, int* n_keypoints, int* mono_index);
+int orbx_extract_stereo_color(orbx_extractor* left, orbx_extractor* right, const uint8_t* image_left, const uint8_t* image_right, int width, int height,
+                              size_t stride_left, size_t stride_right, int channels, int rgb, const int lapping_left[2], const int lapping_right[2],
+                              orbx_keypoint* kps_left, uint8_t* desc_left, int cap_left, int* n_left, int* mono_left,
+                              orbx_keypoint* kps_right, uint8_t* desc_right, int cap_right, int* n_right, int* mono_right);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Next step of the caller: replaces Frame::ComputeStereoMatches (Frame.cc:841-1011) and the
  * ORBmatcher::DescriptorDistance calls inside it (ORBmatcher.cc:2067-2083) for the stereo pair last extracted by `left` and
  * `right`; keypoints, descriptors and both pyramids stay on the device.  mb, mbf = Frame::mb / Frame::mbf (baseline in
@@ -136,6 +151,8 @@ void* orbx_batch_get_stream(const orbx_batch* b);
  * generator orbx-synth-v1.  Image i of a stereo batch: frame = i/2, right image when i is odd
  * (sampled at x+16, noise seed ^ 0x5bd1e995); seed = seed0 + frame. */
 int orbx_batch_upload(orbx_batch* b, const uint8_t* host_images, size_t row_stride, size_t image_stride, int first_image, int n_images);
+/* colour variant (see orbx_extract_color): interleaved 8-bit images, row_stride >= width * channels; grey conversion on the device */
+int orbx_batch_upload_color(orbx_batch* b, const uint8_t* host_images, size_t row_stride, size_t image_stride, int channels, int rgb, int first_image, int n_images);
 int orbx_batch_upload_device(orbx_batch* b, const uint8_t* dev_images, size_t row_stride, size_t image_stride, int first_image, int n_images);
 int orbx_batch_synth(orbx_batch* b, uint32_t seed0, int first_image, int n_images, int stereo);
 /* level-0 images [first, first+n) back to a dense host array (synchronous) */

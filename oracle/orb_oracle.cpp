@@ -680,6 +680,23 @@ void stereo_match(const Extractor& L, const Extractor& R, float mb, float mbf, s
 
 
 // ---------------------------------------------------------------------------------------------
+// The caller's grayscale conversion, Tracking::GrabImageStereoLidar (Tracking.cc:1646-1671; the other Grab* entry points
+// repeat it): cvtColor(im, im, COLOR_RGB2GRAY | COLOR_BGR2GRAY | COLOR_RGBA2GRAY | COLOR_BGRA2GRAY) on 8-bit images.
+// OpenCV 4.x (imgproc/src/color_rgb.simd.hpp, RGB2Gray<uchar>): 15-bit fixed point,
+//     gray = (R * 9798 + G * 19235 + B * 3735 + (1 << 14)) >> 15        (RY15, GY15, BY15; alpha ignored).
+// Pinned against cv2.cvtColor for all four codes, IPP on and off, over all 2^24 colours (tests/test_oracle_vs_cv2.py).
+// ---------------------------------------------------------------------------------------------
+void cvt_gray_8u(const uint8_t* src, int w, int h, size_t sstride, int channels, int rgb, uint8_t* dst, size_t dstride) {
+    const int RY = 9798, GY = 19235, BY = 3735;
+    const int k0 = rgb ? RY : BY, k2 = rgb ? BY : RY;
+    for (int y = 0; y < h; ++y) {
+        const uint8_t* s = src + (size_t)y * sstride;
+        uint8_t* d = dst + (size_t)y * dstride;
+        for (int x = 0; x < w; ++x, s += channels) d[x] = (uint8_t)((s[0] * k0 + s[1] * GY + s[2] * k2 + (1 << 14)) >> 15);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Frame::ComputeStereoFishEyeMatches, descriptor stage (Frame.cc:1162-1187; BFmatcher = cv::BFMatcher(cv::NORM_HAMMING),
 // Frame.cc:52): knnMatch(k = 2) of the left lapping tail [monoLeft, Nleft) against the right tail [monoRight, Nright)
 // and Lowe's ratio gate `m[0].distance < m[1].distance * 0.7` (float * double -> double compare, Frame.cc:1187).
@@ -763,6 +780,9 @@ int orbo_stereo_match(void* hl, void* hr, float mb, float mbf, float* uright, fl
     return (int)u.size();
 }
 void orbo_lapping_match(const uint8_t* dl, int nq, const uint8_t* dr, int nt, int* out, uint8_t* ok) { lapping_knn_match(dl, nq, dr, nt, out, ok); }
+void orbo_cvt_gray(const uint8_t* src, int w, int h, int sstride, int channels, int rgb, uint8_t* dst, int dstride) {
+    cvt_gray_8u(src, w, h, (size_t)sstride, channels, rgb, dst, (size_t)dstride);
+}
 // primitives, for direct checks against cv2
 void orbo_synth_v1(uint8_t* out, int W, int H, uint32_t seed, int xoff, uint32_t noise_xor) { synth_v1(out, W, H, seed, xoff, noise_xor); }
 void orbo_resize(const uint8_t* src, int sw, int sh, int sstride, uint8_t* dst, int dw, int dh, int dstride) {

@@ -49,6 +49,7 @@ def lib():
         L.orbo_get_selected.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.orbo_stereo_match.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
         L.orbo_lapping_match.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.orbo_cvt_gray.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.orbo_synth_v1.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_uint32]
         L.orbo_resize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.orbo_blur.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
@@ -121,6 +122,16 @@ def stereo_match(left, right, mb, mbf):
     u, d = np.empty(n, np.float32), np.empty(n, np.float32)
     lib().orbo_stereo_match(left._h, right._h, float(mb), float(mbf), _p(u), _p(d))
     return u, d
+
+
+def cvt_gray(image, rgb):
+    """cv::cvtColor(image, COLOR_{RGB,BGR}[A]2GRAY) on an 8-bit [h, w, 3|4] image, as the reference's Grab* entry points do
+    (Tracking.cc:1646-1671); rgb=True: the first channel is red."""
+    image = np.ascontiguousarray(image, np.uint8)
+    h, w, c = image.shape
+    out = np.empty((h, w), np.uint8)
+    lib().orbo_cvt_gray(_p(image), w, h, image.strides[0], c, int(bool(rgb)), _p(out), out.strides[0])
+    return out
 
 
 def lapping_match(desc_left, desc_right):

@@ -205,6 +205,48 @@ void launch_pyramid_level(const Geom& g, const Buffers& b, const LevelMaps& maps
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Grayscale conversion of the caller: Tracking::GrabImageStereoLidar (Tracking.cc:1646-1671, repeated in the other Grab*
+// entry points) runs cvtColor(COLOR_{RGB,BGR}[A]2GRAY) on both images before it builds the Frame.  OpenCV 4.x, 8-bit:
+// gray = (R * 9798 + G * 19235 + B * 3735 + 2^14) >> 15.  Here the interleaved colour image is uploaded as it is and converted
+// straight into level 0 of the pyramid: four pixels per thread (four aligned words; for three channels the 12 bytes are cut out
+// of them with funnel shifts), two IDP.2A per pixel, one 32-bit store.  src: dense [image][h][w * C].
+// ---------------------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(128) k_gray(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int w, int h, int pitch, size_t plane, uint32_t k01,
+                                              uint32_t k2) {
+    const int x0 = 4 * (blockIdx.x * 128 + threadIdx.x);
+    if (x0 >= w) return;
+    const int y = blockIdx.y, img = blockIdx.z;
+    const size_t off = (((size_t)img * h + y) * (size_t)w + (size_t)x0) * C;
+    uint32_t p[4];  // p[i]: bytes c0, c1, c2 of pixel x0 + i in bytes 0..2
+    if (C == 4) {
+        const uint32_t* a = reinterpret_cast<const uint32_t*>(src + off);  // rows of odd widths are only 4-byte aligned
+        p[0] = a[0]; p[1] = a[1]; p[2] = a[2]; p[3] = a[3];
+    } else {
+        const uint32_t* a = reinterpret_cast<const uint32_t*>(src + (off & ~(size_t)3));  // (the staging buffer has 64 spare bytes at its end)
+        const int sh = (int)(off & 3) * 8;
+        const uint32_t w0 = a[0], w1 = a[1], w2 = a[2], w3 = a[3];
+        const uint32_t q0 = __funnelshift_r(w0, w1, sh), q1 = __funnelshift_r(w1, w2, sh), q2 = __funnelshift_r(w2, w3, sh);
+        p[0] = q0; p[1] = __funnelshift_r(q0, q1, 24); p[2] = __funnelshift_r(q1, q2, 16); p[3] = q2 >> 8;
+    }
+    uint32_t g4[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) g4[i] = __dp2a_hi(k2, p[i], __dp2a_lo(k01, p[i], 1u << 14)) >> 15;  // <= 255: the weights sum to 2^15
+    // pixels past the last column land in the row's right padding (rewritten by k_margin / never read)
+    *reinterpret_cast<uint32_t*>(dst + (size_t)img * plane + (size_t)y * pitch + x0) = g4[0] | (g4[1] << 8) | (g4[2] << 16) | (g4[3] << 24);
+}
+
+void launch_gray(const uint8_t* src, int channels, int rgb, uint8_t* l0, int w, int h, int pitch, size_t planeBytes, int nImages, cudaStream_t s) {
+    const uint32_t RY = 9798, GY = 19235, BY = 3735;
+    const uint32_t k01 = (rgb ? RY : BY) | (GY << 16), k2 = rgb ? BY : RY;  // 16x2 weights of bytes (0, 1) and (2, 3): alpha gets 0
+    dim3 grid((w + 511) / 512, h, nImages);
+    if (channels == 4)
+        k_gray<4><<<grid, 128, 0, s>>>(src, l0, w, h, pitch, planeBytes, k01, k2);
+    else
+        k_gray<3><<<grid, 128, 0, s>>>(src, l0, w, h, pitch, planeBytes, k01, k2);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Reflect-101 margin of every pyramid plane (3 rows / 3 columns around the interior): what GaussianBlur(...,
 // BORDER_REFLECT_101) reads beyond the edge of its (cloned, hence border-less) input (ORBextractor.cc:1105-1106).  With the
 // margin in place the blur kernel below has no edge cases.  One launch covers all levels of all images.

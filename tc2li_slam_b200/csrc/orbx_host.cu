@@ -451,6 +451,37 @@ int orbx_batch_upload(orbx_batch* b, const uint8_t* host_images, size_t row_stri
     return copy_images_in(b, host_images, row_stride, image_stride, first, n, cudaMemcpyHostToDevice);
 }
 
+// Tracking::GrabImageStereoLidar's cvtColor (Tracking.cc:1646-1671) fused into the upload: interleaved 8-bit colour images
+// (channels 3 or 4; rgb != 0: red first = COLOR_RGB[A]2GRAY, else COLOR_BGR[A]2GRAY) -> device staging -> level 0 as grey
+int orbx_batch_upload_color(orbx_batch* b, const uint8_t* host_images, size_t row_stride, size_t image_stride, int channels, int rgb, int first, int n) {
+    int r = check_images(b, first, n);
+    if (r) return r;
+    if (!host_images) return fail(ORBX_ERR_EMPTY, "null image");
+    if (channels != 3 && channels != 4) return fail(ORBX_ERR_ARG, "colour images have 3 or 4 interleaved channels");
+    const size_t rowBytes = (size_t)b->width * channels;
+    if (row_stride < rowBytes) return fail(ORBX_ERR_ARG, "row stride smaller than width * channels");
+    if (n == 0) return ORBX_OK;
+    DeviceGuard dg(b->device);
+    const size_t imgBytes = rowBytes * b->height, bytes = (size_t)n * imgBytes + 64;
+    if (bytes > b->stageBytes) {
+        CU(cudaStreamSynchronize(b->stream));
+        if (b->stageIn) cudaFree(b->stageIn);
+        b->stageIn = nullptr; b->stageBytes = 0;
+        CU(cudaMalloc((void**)&b->stageIn, bytes));
+        b->stageBytes = bytes;
+    }
+    if (row_stride == rowBytes && (n == 1 || image_stride == imgBytes))
+        CU(cudaMemcpyAsync(b->stageIn, host_images, (size_t)n * imgBytes, cudaMemcpyHostToDevice, b->stream));
+    else
+        for (int i = 0; i < n; ++i)
+            CU(cudaMemcpy2DAsync(b->stageIn + (size_t)i * imgBytes, rowBytes, host_images + (size_t)i * image_stride, row_stride, rowBytes, b->height,
+                                 cudaMemcpyHostToDevice, b->stream));
+    const LevelGeom& L0 = b->g.lv[0];
+    launch_gray(b->stageIn, channels, rgb, b->buf.pyr + L0.planeOff + (size_t)first * L0.planeBytes, L0.w, L0.h, L0.pitch, (size_t)L0.planeBytes, n, b->stream);
+    CU(cudaGetLastError());
+    return ORBX_OK;
+}
+
 int orbx_batch_upload_device(orbx_batch* b, const uint8_t* dev_images, size_t row_stride, size_t image_stride, int first, int n) {
     int r = check_images(b, first, n);
     if (r) return r;
@@ -918,16 +949,22 @@ struct orbx_extractor {
     // The whole per-image sequence (H2D, 21 kernels on two streams, D2H) is launch-bound for one image: after a first eager
     // call it is captured once into a CUDA graph and replayed; pinCnt[4..5] is the pinned lapping window the graph reads.
     cudaGraphExec_t exec = nullptr;
+    int channels = 1, rgb = 0;  // input format of the last call (1 = grey); a change re-captures the graph
     int graphState = 0;  // 0: next call runs eagerly (lazy allocations), 1: capture on the next call, 2: replay `exec`, 3: capture failed, stay eager
 };
 
 namespace {
 
-int extractor_prepare(orbx_extractor* h, int w, int hgt) {
+int extractor_prepare(orbx_extractor* h, int w, int hgt, int channels, int rgb) {
     if (h->b && (h->b->width != w || h->b->height != hgt)) {
         if (h->exec) { cudaGraphExecDestroy(h->exec); h->exec = nullptr; }
         h->graphState = 0;
         orbx_batch_destroy(h->b); h->b = nullptr;
+    }
+    if (h->channels != channels || h->rgb != rgb) {  // another input format: other copies and kernels, start over with an eager call
+        if (h->exec) { cudaGraphExecDestroy(h->exec); h->exec = nullptr; }
+        h->graphState = 0;
+        h->channels = channels; h->rgb = rgb;
     }
     if (!h->b) {
         int r = orbx_batch_create(h->p.nfeatures, h->p.scaleFactorF, h->p.nlevels, h->p.iniTh, h->p.minTh, h->device, w, hgt, 1, &h->b);
@@ -936,7 +973,7 @@ int extractor_prepare(orbx_extractor* h, int w, int hgt) {
         h->b->lapStable = true;
     }
     DeviceGuard dg(h->device);
-    const size_t need = (size_t)w * hgt;
+    const size_t need = (size_t)w * hgt * channels;
     if (need > h->pinImgBytes) {
         if (h->pinImg) cudaFreeHost(h->pinImg);
         h->pinImg = nullptr; h->pinImgBytes = 0;
@@ -961,7 +998,9 @@ int extractor_prepare(orbx_extractor* h, int w, int hgt) {
 // everything one image needs, enqueued on the handle's streams (also the body of the captured graph)
 int extractor_enqueue(orbx_extractor* h, int w, int hgt) {
     int r;
-    if ((r = orbx_batch_upload(h->b, h->pinImg, (size_t)w, (size_t)w * hgt, 0, 1))) return r;
+    if (h->channels == 1) r = orbx_batch_upload(h->b, h->pinImg, (size_t)w, (size_t)w * hgt, 0, 1);
+    else r = orbx_batch_upload_color(h->b, h->pinImg, (size_t)w * h->channels, (size_t)w * h->channels * hgt, h->channels, h->rgb, 0, 1);
+    if (r) return r;
     if ((r = orbx_batch_run(h->b, 1, h->pinCnt + 4))) return r;
     orbx_batch* b = h->b;
     cudaStream_t s = b->stream;
@@ -975,10 +1014,11 @@ int extractor_enqueue(orbx_extractor* h, int w, int hgt) {
 }
 
 // stage + enqueue everything for one image; nothing waits here
-int extractor_issue(orbx_extractor* h, const uint8_t* image, int w, int hgt, size_t stride, int lap0, int lap1) {
-    int r = extractor_prepare(h, w, hgt);
+int extractor_issue(orbx_extractor* h, const uint8_t* image, int w, int hgt, size_t stride, int lap0, int lap1, int channels = 1, int rgb = 0) {
+    int r = extractor_prepare(h, w, hgt, channels, rgb);
     if (r) return r;
-    for (int y = 0; y < hgt; ++y) std::memcpy(h->pinImg + (size_t)y * w, image + (size_t)y * stride, (size_t)w);
+    const size_t rowBytes = (size_t)w * channels;
+    for (int y = 0; y < hgt; ++y) std::memcpy(h->pinImg + (size_t)y * rowBytes, image + (size_t)y * stride, rowBytes);
     h->pinCnt[4] = lap0; h->pinCnt[5] = lap1;
     DeviceGuard dg(h->device);
     orbx_batch* b = h->b;
@@ -1113,6 +1153,39 @@ int orbx_extract_stereo(orbx_extractor* left, orbx_extractor* right, const uint8
     int r = extractor_issue(left, image_left, width, height, stride_left, lap_left[0], lap_left[1]);
     if (r) return r;
     if ((r = extractor_issue(right, image_right, width, height, stride_right, lap_right[0], lap_right[1]))) return r;
+    r = extractor_collect(left, kps_left, desc_left, cap_left, n_left, mono_left);
+    const int r2 = extractor_collect(right, kps_right, desc_right, cap_right, n_right, mono_right);
+    return r ? r : r2;
+}
+
+// the same with the caller's cvtColor (Tracking.cc:1646-1671) done on the device: interleaved 8-bit colour input
+int orbx_extract_color(orbx_extractor* h, const uint8_t* image, int width, int height, size_t stride, int channels, int rgb, int lap0, int lap1,
+                       orbx_keypoint* keypoints, uint8_t* descriptors, int capacity, int* n_keypoints, int* mono_index) {
+    if (!h) return fail(ORBX_ERR_ARG, "null handle");
+    if (n_keypoints) *n_keypoints = 0;
+    if (mono_index) *mono_index = 0;
+    if (!image || width <= 0 || height <= 0) return fail(ORBX_ERR_EMPTY, "empty image");
+    if (channels != 3 && channels != 4) return fail(ORBX_ERR_ARG, "colour images have 3 or 4 interleaved channels");
+    if (stride < (size_t)width * channels) return fail(ORBX_ERR_ARG, "row stride smaller than width * channels");
+    int r = extractor_issue(h, image, width, height, stride, lap0, lap1, channels, rgb != 0);
+    if (r) return r;
+    return extractor_collect(h, keypoints, descriptors, capacity, n_keypoints, mono_index);
+}
+
+int orbx_extract_stereo_color(orbx_extractor* left, orbx_extractor* right, const uint8_t* image_left, const uint8_t* image_right, int width, int height,
+                              size_t stride_left, size_t stride_right, int channels, int rgb, const int lap_left[2], const int lap_right[2],
+                              orbx_keypoint* kps_left, uint8_t* desc_left, int cap_left, int* n_left, int* mono_left, orbx_keypoint* kps_right,
+                              uint8_t* desc_right, int cap_right, int* n_right, int* mono_right) {
+    if (!left || !right || left == right) return fail(ORBX_ERR_ARG, "need two distinct handles");
+    if (!image_left || !image_right || width <= 0 || height <= 0) return fail(ORBX_ERR_EMPTY, "empty image");
+    if (channels != 3 && channels != 4) return fail(ORBX_ERR_ARG, "colour images have 3 or 4 interleaved channels");
+    if (stride_left < (size_t)width * channels || stride_right < (size_t)width * channels) return fail(ORBX_ERR_ARG, "row stride smaller than width * channels");
+    const int zero[2] = {0, 0};
+    if (!lap_left) lap_left = zero;
+    if (!lap_right) lap_right = zero;
+    int r = extractor_issue(left, image_left, width, height, stride_left, lap_left[0], lap_left[1], channels, rgb != 0);
+    if (r) return r;
+    if ((r = extractor_issue(right, image_right, width, height, stride_right, lap_right[0], lap_right[1], channels, rgb != 0))) return r;
     r = extractor_collect(left, kps_left, desc_left, cap_left, n_left, mono_left);
     const int r2 = extractor_collect(right, kps_right, desc_right, cap_right, n_right, mono_right);
     return r ? r : r2;

@@ -71,6 +71,9 @@ def lib():
         "orbx_batch_get_stream": (_vp, [_vp]),
         "orbx_batch_upload": (i, [_vp, _vp, sz, sz, i, i]),
         "orbx_batch_upload_device": (i, [_vp, _vp, sz, sz, i, i]),
+        "orbx_batch_upload_color": (i, [_vp, _vp, sz, sz, i, i, i, i]),
+        "orbx_extract_color": (i, [_vp, _vp, i, i, sz, i, i, i, i, _vp, _vp, i, _vp, _vp]),
+        "orbx_extract_stereo_color": (i, [_vp, _vp, _vp, _vp, i, i, sz, sz, i, i, _vp, _vp, _vp, _vp, i, _vp, _vp, _vp, _vp, i, _vp, _vp]),
         "orbx_batch_synth": (i, [_vp, u32, i, i, i]),
         "orbx_batch_download_images": (i, [_vp, i, i, _vp, sz, sz]),
         "orbx_batch_run": (i, [_vp, i, _vp]),
@@ -245,6 +248,18 @@ def _as_gray(image):
     return image
 
 
+def _as_color(image):
+    if image is None:
+        return None
+    image = np.asarray(image)
+    if image.size == 0:
+        return None
+    assert image.dtype == np.uint8 and image.ndim == 3 and image.shape[2] in (3, 4), "colour input is CV_8UC3 or CV_8UC4 (Tracking.cc:1646-1671)"
+    if image.strides[2] != 1 or image.strides[1] != image.shape[2]:
+        image = np.ascontiguousarray(image)
+    return image
+
+
 class ORBextractor:
     """Drop-in mirror of TC2LI_SLAM::ORBextractor (ORBextractor.h:52-118) over the CUDA path."""
 
@@ -320,6 +335,18 @@ class ORBextractor:
                                   _p(self._kps), _p(self._desc), cap, C.byref(n), C.byref(mono)))
         return mono.value, self._kps[:n.value].copy(), self._desc[:n.value].copy()
 
+    def extract_color(self, image, rgb, vLappingArea=(0, 0)):
+        """The caller's cvtColor (Tracking.cc:1646-1671: COLOR_RGB[A]2GRAY if rgb else COLOR_BGR[A]2GRAY) on the device, then
+        operator().  image: uint8 [H, W, 3|4].  The grey image the reference keeps (mImGray) is self.level(0)."""
+        image = _as_color(image)
+        if image is None:
+            return -1, np.empty(0, KP_DTYPE), np.empty((0, 32), np.uint8)
+        cap = self._outputs()
+        n, mono = C.c_int(0), C.c_int(0)
+        _check(lib().orbx_extract_color(self._h, _p(image), image.shape[1], image.shape[0], image.strides[0], image.shape[2], int(bool(rgb)),
+                                        int(vLappingArea[0]), int(vLappingArea[1]), _p(self._kps), _p(self._desc), cap, C.byref(n), C.byref(mono)))
+        return mono.value, self._kps[:n.value].copy(), self._desc[:n.value].copy()
+
     # ---- mvImagePyramid (ORBextractor.h:92): fetched lazily from the device ----
     def level(self, l, border=0):
         w, h = C.c_int(), C.c_int()
@@ -362,6 +389,24 @@ class StereoORBextractor:
         _check(lib().orbx_extract_stereo(L._h, R._h, _p(imLeft), _p(imRight), imLeft.shape[1], imLeft.shape[0], imLeft.strides[0], imRight.strides[0],
                                          _p(ll), _p(lr), _p(L._kps), _p(L._desc), capL, C.byref(nl), C.byref(ml),
                                          _p(R._kps), _p(R._desc), capR, C.byref(nr), C.byref(mr)))
+        return ((ml.value, L._kps[:nl.value].copy(), L._desc[:nl.value].copy()),
+                (mr.value, R._kps[:nr.value].copy(), R._desc[:nr.value].copy()))
+
+    def extract_color(self, imLeft, imRight, rgb, lapLeft=(0, 0), lapRight=(0, 0)):
+        """Tracking::GrabImageStereoLidar's two cvtColor calls (Tracking.cc:1646-1671) on the device, then both extractions."""
+        imLeft, imRight = _as_color(imLeft), _as_color(imRight)
+        if imLeft is None or imRight is None:
+            e = (-1, np.empty(0, KP_DTYPE), np.empty((0, 32), np.uint8))
+            return e, e
+        assert imLeft.shape == imRight.shape
+        L, R = self.left, self.right
+        capL, capR = L._outputs(), R._outputs()
+        nl, ml, nr, mr = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
+        ll = np.asarray(lapLeft, np.int32)
+        lr = np.asarray(lapRight, np.int32)
+        _check(lib().orbx_extract_stereo_color(L._h, R._h, _p(imLeft), _p(imRight), imLeft.shape[1], imLeft.shape[0], imLeft.strides[0], imRight.strides[0],
+                                               imLeft.shape[2], int(bool(rgb)), _p(ll), _p(lr), _p(L._kps), _p(L._desc), capL, C.byref(nl), C.byref(ml),
+                                               _p(R._kps), _p(R._desc), capR, C.byref(nr), C.byref(mr)))
         return ((ml.value, L._kps[:nl.value].copy(), L._desc[:nl.value].copy()),
                 (mr.value, R._kps[:nr.value].copy(), R._desc[:nr.value].copy()))
 
@@ -439,6 +484,12 @@ class BatchExtractor:
         images = np.asarray(images)
         assert images.dtype == np.uint8 and images.ndim == 3 and images.strides[2] == 1
         _check(lib().orbx_batch_upload(self._h, _p(images), images.strides[1], images.strides[0], first, images.shape[0]))
+
+    def upload_color(self, images, rgb, first=0):
+        """images: uint8 [n, H, W, 3|4] host array; converted to grey on the device as cv::cvtColor does (Tracking.cc:1646-1671)."""
+        images = np.asarray(images)
+        assert images.dtype == np.uint8 and images.ndim == 4 and images.shape[3] in (3, 4) and images.strides[3] == 1 and images.strides[2] == images.shape[3]
+        _check(lib().orbx_batch_upload_color(self._h, _p(images), images.strides[1], images.strides[0], images.shape[3], int(bool(rgb)), first, images.shape[0]))
 
     def upload_device(self, dev_ptr, row_stride, image_stride, first, n):
         _check(lib().orbx_batch_upload_device(self._h, _vp(dev_ptr), row_stride, image_stride, first, n))

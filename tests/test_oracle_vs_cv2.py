@@ -131,3 +131,21 @@ def test_lapping_ratio_gate_boundary():
     assert want[0].tolist() == [0, 7, 1, 10]
     assert np.array_equal(got, want) and np.array_equal(got_ok, want_ok)
     assert bool(got_ok[0]) == (np.float32(7) < float(np.float32(10)) * 0.7)
+
+
+@pytest.mark.parametrize("channels,rgb", [(3, True), (3, False), (4, True), (4, False)])
+def test_cvt_gray_matches_cv2(channels, rgb):
+    """Tracking::GrabImageStereoLidar's cvtColor (Tracking.cc:1646-1671), all four codes."""
+    code = {(3, True): cv2.COLOR_RGB2GRAY, (3, False): cv2.COLOR_BGR2GRAY, (4, True): cv2.COLOR_RGBA2GRAY, (4, False): cv2.COLOR_BGRA2GRAY}[(channels, rgb)]
+    rng = np.random.default_rng(channels * 2 + rgb)
+    for h, w in [(376, 1241), (37, 53), (1, 1), (5, 1023)]:
+        img = rng.integers(0, 256, (h, w, channels), dtype=np.uint8)
+        assert np.array_equal(po.cvt_gray(img, rgb), cv2.cvtColor(img, code)), (h, w)
+
+
+def test_cvt_gray_all_colours():
+    """every one of the 2^24 (c0, c1, c2) triples, both channel orders"""
+    v = np.arange(1 << 24, dtype=np.uint32)
+    img = np.stack([(v & 255), (v >> 8) & 255, (v >> 16)], axis=-1).astype(np.uint8).reshape(4096, 4096, 3)
+    assert np.array_equal(po.cvt_gray(img, True), cv2.cvtColor(img, cv2.COLOR_RGB2GRAY))
+    assert np.array_equal(po.cvt_gray(img, False), cv2.cvtColor(img, cv2.COLOR_BGR2GRAY))
