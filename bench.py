@@ -393,6 +393,36 @@ def main():
                                    "frac_of_measured_hbm": bytes_img * nimg / (ms * 1e-3) / 1e9 / peak}
             lb.close()
 
+    # ---- supplementary: BASELINE.json configs[2], EuRoC-shaped 752x480 stereo with lapping windows, 1200 features, plus the
+    #      descriptor stage of Frame::ComputeStereoFishEyeMatches (kNN(2) + Lowe gate over the lapping tails) ----
+    euroc = None
+    if rank == 0 and not args.no_large:
+        ef = 1024
+        eb = T.BatchExtractor(752, 480, 2 * ef, 1200, 1.2, 8, 20, 7, device=local)
+        eb.synth(11, 2 * ef, stereo=True)
+        lap = np.tile(np.array([[250, 751], [0, 501]], np.int32), (ef, 1))
+        for _ in range(3):
+            eb.run(2 * ef, lap)
+            eb.lapping_match(ef)
+        eb.check()
+        e0, e1, e2_ = Event(), Event(), Event()
+        e0.record(eb)
+        for _ in range(args.steps):
+            eb.run(2 * ef, lap)
+        e1.record(eb)
+        for _ in range(args.steps):
+            eb.lapping_match(ef)
+        e2_.record(eb)
+        ce, me = eb.download_counts(2 * ef)
+        knn, okf = eb.download_lapping(8)
+        nq = (ce[0:16:2] - me[0:16:2])
+        euroc = {"workload": "1024 EuRoC-shaped stereo frames 752x480, ORBextractor(1200,1.2,8,20,7), lapping windows {250,751} / {0,501}",
+                 "extract_frames_per_s": ef / (e0.elapsed_ms(e1) / args.steps * 1e-3), "keypoints_per_image": float(ce.mean()),
+                 "lapping_queries_per_frame": float((ce[0::2] - me[0::2]).mean()),
+                 "lapping_match_ms_per_1024_frames": e1.elapsed_ms(e2_) / args.steps,
+                 "ratio_pass_fraction_first_8": float(sum(int(okf[f, :nq[f]].sum()) for f in range(8))) / float(max(1, int(nq.sum())))}
+        eb.close()
+
     # ---- stereo-pair latency through the reference-shaped API (BASELINE.json configs[1]) ----
     latency = None
     if rank == 0 and not args.no_latency:
@@ -436,7 +466,7 @@ def main():
             "config": {"workload": WORKLOAD,
                        "pairs_per_gpu_per_step": args.pairs, "images_per_launch_set": group, "keypoints_per_image": kp_mean,
                        "l2": f"inputs {n_img * W * H / 1e9:.2f} GB per rank, larger than the {L2_BYTES / 1e6:.0f} MB L2; no flush needed"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step, "roofline": roofline, "cpu_baseline": cpu, "stages": stages, "latency": latency, "stereo_match": stereo, "large_images": large,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step, "roofline": roofline, "cpu_baseline": cpu, "stages": stages, "latency": latency, "stereo_match": stereo, "large_images": large, "euroc_lapping": euroc,
         }
         emit_line(json.dumps(line))
     big.close()

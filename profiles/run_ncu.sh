@@ -4,7 +4,7 @@
 # usage: profiles/run_ncu.sh [tag] [launches-per-step]
 set -u
 TAG=${1:-r01}
-NL=${2:-20}
+NL=${2:-27}
 CMD="python bench.py --pairs 128 --steps 1 --warmup 3 --no-e2e --no-cpu --no-latency --no-stereo --no-large"
 mkdir -p gpurun_out
 $CMD > gpurun_out/plain_$TAG.json 2> gpurun_out/plain_$TAG.err || { echo "plain run failed"; tail -5 gpurun_out/plain_$TAG.err; exit 1; }

@@ -14,8 +14,8 @@
 // fetches the cell crop with one TMA box load (tensor map per level, 16-byte aligned box origin, 64- or 96-byte box rows)
 // into the warp's own shared-memory tile.  The tile is single buffered (NB = 1): prefetching the next cell's box into a
 // second tile measured slower (18.3 vs 17.5 ms per 8192 KITTI images), because shared memory per warp sets the number of
-// resident warps (15 vs 20 per SM) and the other warps hide the box latency better than the prefetch did.  No block-level barrier exists; every pass is warp-synchronous and compacts its survivors in order with
-// ballot prefixes (no atomics):
+// resident warps (15 vs 20 per SM) and the other warps hide the box latency better than the prefetch did.  No block-level
+// barrier exists; every pass is warp-synchronous and compacts its survivors in order with ballot prefixes (no atomics):
 //   A  four pixels per lane, packed in one 32-bit word: |ring - centre| > t at the four compass points, combined as
 //      (N|S)&(E|W) — a necessary condition for a 9-arc of either polarity (VABSDIFF4 + carry tricks) -> list1;
 //   A2 dense over list1: the exact score S of both polarities at once, ring pixels q and q + 8 paired in 16x2 lanes and

@@ -946,7 +946,7 @@ struct orbx_extractor {
     // pinned staging so that H2D / D2H are truly asynchronous with respect to the other handle of a stereo pair
     uint8_t* pinImg = nullptr; size_t pinImgBytes = 0;
     orbx_keypoint* pinKps = nullptr; uint8_t* pinDesc = nullptr; int* pinCnt = nullptr; size_t pinK = 0;
-    // The whole per-image sequence (H2D, 21 kernels on two streams, D2H) is launch-bound for one image: after a first eager
+    // The whole per-image sequence (H2D, 20 kernels on two streams, D2H) is launch-bound for one image: after a first eager
     // call it is captured once into a CUDA graph and replayed; pinCnt[4..5] is the pinned lapping window the graph reads.
     cudaGraphExec_t exec = nullptr;
     int channels = 1, rgb = 0;  // input format of the last call (1 = grey); a change re-captures the graph
