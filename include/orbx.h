@@ -100,6 +100,19 @@ int orbx_extract_stereo_color(orbx_extractor* left, orbx_extractor* right, const
                               orbx_keypoint* kps_right, uint8_t* desc_right, int cap_right, int* n_right, int* mono_right);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * One step further up the caller: System::TrackStereoLidar (System.cc:238-248) rectifies both images with
+ * cv::remap(im, imToFeed, M1, M2, cv::INTER_LINEAR), M1/M2 = the CV_32FC1 maps Settings builds with
+ * cv::initUndistortRectifyMap (Settings.cc:523-526), when Settings::needToRectify().  orbx_set_rectification hands this
+ * extractor the maps of ITS camera (M1l/M2l for the left, M1r/M2r for the right instance): width x height floats each,
+ * sampling raw images of src_width x src_height.  From then on orbx_extract / orbx_extract_stereo / orbx_extract_color /
+ * orbx_extract_stereo_color take the RAW image (of the raw size); remap (per channel, constant-0 border, OpenCV's 5-bit
+ * fixed-point coordinates and 15-bit weights), the grey conversion and the extraction run on the device in the reference's
+ * order, bit-identical to cv::remap + cv::cvtColor.  NULL maps switch rectification off.
+ * ---------------------------------------------------------------------------------------------------------------- */
+int orbx_set_rectification(orbx_extractor* h, const float* map_x, const float* map_y, int width, int height, size_t map_stride_bytes, int src_width,
+                           int src_height);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Next step of the caller: replaces Frame::ComputeStereoMatches (Frame.cc:841-1011) and the
  * ORBmatcher::DescriptorDistance calls inside it (ORBmatcher.cc:2067-2083) for the stereo pair last extracted by `left` and
  * `right`; keypoints, descriptors and both pyramids stay on the device.  mb, mbf = Frame::mb / Frame::mbf (baseline in
@@ -153,6 +166,10 @@ void* orbx_batch_get_stream(const orbx_batch* b);
 int orbx_batch_upload(orbx_batch* b, const uint8_t* host_images, size_t row_stride, size_t image_stride, int first_image, int n_images);
 /* colour variant (see orbx_extract_color): interleaved 8-bit images, row_stride >= width * channels; grey conversion on the device */
 int orbx_batch_upload_color(orbx_batch* b, const uint8_t* host_images, size_t row_stride, size_t image_stride, int channels, int rgb, int first_image, int n_images);
+/* rectification variant (see orbx_set_rectification): maps of width x height floats for ALL images of the handle; then raw images of
+ * src_width x src_height with 1, 3 or 4 channels are remapped (+ converted to grey) into level 0 */
+int orbx_batch_set_rectification(orbx_batch* b, const float* map_x, const float* map_y, size_t map_stride_bytes, int src_width, int src_height);
+int orbx_batch_upload_raw(orbx_batch* b, const uint8_t* host_images, size_t row_stride, size_t image_stride, int channels, int rgb, int first_image, int n_images);
 int orbx_batch_upload_device(orbx_batch* b, const uint8_t* dev_images, size_t row_stride, size_t image_stride, int first_image, int n_images);
 int orbx_batch_synth(orbx_batch* b, uint32_t seed0, int first_image, int n_images, int stereo);
 /* level-0 images [first, first+n) back to a dense host array (synchronous) */

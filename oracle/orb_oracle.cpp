@@ -697,6 +697,34 @@ void cvt_gray_8u(const uint8_t* src, int w, int h, size_t sstride, int channels,
 }
 
 // ---------------------------------------------------------------------------------------------
+// The rectification in front of the Grab* call, System::TrackStereoLidar (System.cc:238-248):
+// cv::remap(im, imToFeed, M1, M2, cv::INTER_LINEAR) with the CV_32FC1 maps of cv::initUndistortRectifyMap (Settings.cc:523-526),
+// default border (BORDER_CONSTANT, value 0), 8-bit images of 1, 3 or 4 channels.  OpenCV's fixed-point path:
+//   sx = cvRound(mapx * 32), sy = cvRound(mapy * 32)  (float product, round half to even); integer parts sx >> 5, sy >> 5
+//   (saturated to short), fractions fx = sx & 31, fy = sy & 31; weights 32*(32-fx)*(32-fy), 32*fx*(32-fy), 32*(32-fx)*fy,
+//   32*fx*fy (the BilinearTab_i entries: products of multiples of 1/32 scaled by 2^15 are integers, so the table needs no
+//   correction step); dst = (sum of weight * tap + 2^14) >> 15, taps outside the source read as 0.
+// Pinned against cv2.remap (tests/test_oracle_vs_cv2.py).
+// ---------------------------------------------------------------------------------------------
+void remap_linear_8u(const uint8_t* src, int sw, int sh, size_t sstride, int channels, const float* mapx, const float* mapy, size_t mstride, uint8_t* dst,
+                     int dw, int dh, size_t dstride) {
+    for (int y = 0; y < dh; ++y)
+        for (int x = 0; x < dw; ++x) {
+            const int sxq = (int)lrintf(mapx[(size_t)y * mstride + x] * 32.0f), syq = (int)lrintf(mapy[(size_t)y * mstride + x] * 32.0f);
+            const int ix = std::min(std::max(sxq >> 5, -32768), 32767), iy = std::min(std::max(syq >> 5, -32768), 32767);
+            const int fx = sxq & 31, fy = syq & 31;
+            const int w00 = 32 * (32 - fx) * (32 - fy), w01 = 32 * fx * (32 - fy), w10 = 32 * (32 - fx) * fy, w11 = 32 * fx * fy;
+            for (int c = 0; c < channels; ++c) {
+                auto tap = [&](int yy, int xx) -> int {
+                    return (xx >= 0 && xx < sw && yy >= 0 && yy < sh) ? src[(size_t)yy * sstride + (size_t)xx * channels + c] : 0;
+                };
+                const int v = tap(iy, ix) * w00 + tap(iy, ix + 1) * w01 + tap(iy + 1, ix) * w10 + tap(iy + 1, ix + 1) * w11;
+                dst[(size_t)y * dstride + (size_t)x * channels + c] = (uint8_t)((v + (1 << 14)) >> 15);
+            }
+        }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Frame::ComputeStereoFishEyeMatches, descriptor stage (Frame.cc:1162-1187; BFmatcher = cv::BFMatcher(cv::NORM_HAMMING),
 // Frame.cc:52): knnMatch(k = 2) of the left lapping tail [monoLeft, Nleft) against the right tail [monoRight, Nright)
 // and Lowe's ratio gate `m[0].distance < m[1].distance * 0.7` (float * double -> double compare, Frame.cc:1187).
@@ -782,6 +810,10 @@ int orbo_stereo_match(void* hl, void* hr, float mb, float mbf, float* uright, fl
 void orbo_lapping_match(const uint8_t* dl, int nq, const uint8_t* dr, int nt, int* out, uint8_t* ok) { lapping_knn_match(dl, nq, dr, nt, out, ok); }
 void orbo_cvt_gray(const uint8_t* src, int w, int h, int sstride, int channels, int rgb, uint8_t* dst, int dstride) {
     cvt_gray_8u(src, w, h, (size_t)sstride, channels, rgb, dst, (size_t)dstride);
+}
+void orbo_remap(const uint8_t* src, int sw, int sh, int sstride, int channels, const float* mapx, const float* mapy, int mstride, uint8_t* dst, int dw, int dh,
+                int dstride) {
+    remap_linear_8u(src, sw, sh, (size_t)sstride, channels, mapx, mapy, (size_t)mstride, dst, dw, dh, (size_t)dstride);
 }
 // primitives, for direct checks against cv2
 void orbo_synth_v1(uint8_t* out, int W, int H, uint32_t seed, int xoff, uint32_t noise_xor) { synth_v1(out, W, H, seed, xoff, noise_xor); }

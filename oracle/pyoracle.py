@@ -50,6 +50,7 @@ def lib():
         L.orbo_stereo_match.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
         L.orbo_lapping_match.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.orbo_cvt_gray.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.orbo_remap.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.orbo_synth_v1.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_uint32]
         L.orbo_resize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.orbo_blur.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
@@ -131,6 +132,18 @@ def cvt_gray(image, rgb):
     h, w, c = image.shape
     out = np.empty((h, w), np.uint8)
     lib().orbo_cvt_gray(_p(image), w, h, image.strides[0], c, int(bool(rgb)), _p(out), out.strides[0])
+    return out
+
+
+def remap(image, map_x, map_y):
+    """cv::remap(image, map_x, map_y, INTER_LINEAR) with CV_32FC1 maps and the default constant-0 border, as System::TrackStereoLidar
+    rectifies its inputs (System.cc:238-248).  image: uint8 [h, w] or [h, w, 3|4]; maps: float32 [dh, dw]."""
+    image = np.ascontiguousarray(image, np.uint8)
+    map_x, map_y = np.ascontiguousarray(map_x, np.float32), np.ascontiguousarray(map_y, np.float32)
+    ch = 1 if image.ndim == 2 else image.shape[2]
+    dh, dw = map_x.shape
+    out = np.empty((dh, dw) if image.ndim == 2 else (dh, dw, ch), np.uint8)
+    lib().orbo_remap(_p(image), image.shape[1], image.shape[0], image.strides[0], ch, _p(map_x), _p(map_y), dw, _p(out), dw, dh, out.strides[0])
     return out
 
 

@@ -247,6 +247,60 @@ void launch_gray(const uint8_t* src, int channels, int rgb, uint8_t* l0, int w, 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Rectification of the caller: System::TrackStereoLidar (System.cc:238-248) runs cv::remap(im, imToFeed, M1, M2,
+// cv::INTER_LINEAR) with the CV_32FC1 maps of cv::initUndistortRectifyMap (Settings.cc:523-526) before Grab* converts to grey.
+// OpenCV's fixed-point path: sx = cvRound(mapx * 32), taps at (sx >> 5, sy >> 5) and its right / lower neighbours, weights
+// 32 * {(32-fx)(32-fy), fx(32-fy), (32-fx)fy, fx*fy}, dst = (sum + 2^14) >> 15, taps outside the source are 0.
+// Here: the raw image is uploaded as it is; the maps stay resident; one thread produces four destination pixels (gathers
+// through L1 / L2: the taps of neighbouring pixels share cache lines); colour images are remapped per channel and then
+// converted exactly as k_gray does, i.e. in the reference's order remap -> cvtColor.  src: dense [image][sh][sw * C].
+// ---------------------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(128) k_remap(const uint8_t* __restrict__ src, int sw, int sh, const float* __restrict__ mapx, const float* __restrict__ mapy,
+                                               uint8_t* __restrict__ dst, int dw, int dh, int pitch, size_t plane, uint32_t k01, uint32_t k2) {
+    const int x0 = 4 * (blockIdx.x * 128 + threadIdx.x);
+    if (x0 >= dw) return;
+    const int y = blockIdx.y, img = blockIdx.z;
+    const uint8_t* S = src + (size_t)img * sh * (size_t)sw * C;
+    uint32_t out = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int x = min(x0 + i, dw - 1);
+        const size_t m = (size_t)y * dw + x;
+        const int sxq = __float2int_rn(__fmul_rn(__ldg(mapx + m), 32.0f)), syq = __float2int_rn(__fmul_rn(__ldg(mapy + m), 32.0f));
+        const int ix = min(max(sxq >> 5, -32768), 32767), iy = min(max(syq >> 5, -32768), 32767);
+        const int fx = sxq & 31, fy = syq & 31;
+        const int w00 = 32 * (32 - fx) * (32 - fy), w01 = 32 * fx * (32 - fy), w10 = 32 * (32 - fx) * fy, w11 = 32 * fx * fy;
+        const bool inx0 = ix >= 0 && ix < sw, inx1 = ix + 1 >= 0 && ix + 1 < sw, iny0 = iy >= 0 && iy < sh, iny1 = iy + 1 >= 0 && iy + 1 < sh;
+        const uint8_t* p = S + ((ptrdiff_t)iy * sw + ix) * C;
+        uint32_t px = 0;  // the remapped channels in bytes 0..2
+#pragma unroll
+        for (int c = 0; c < (C == 1 ? 1 : 3); ++c) {
+            const int t00 = (iny0 && inx0) ? (int)__ldg(p + c) : 0, t01 = (iny0 && inx1) ? (int)__ldg(p + C + c) : 0;
+            const int t10 = (iny1 && inx0) ? (int)__ldg(p + (ptrdiff_t)sw * C + c) : 0, t11 = (iny1 && inx1) ? (int)__ldg(p + (ptrdiff_t)sw * C + C + c) : 0;
+            px |= (uint32_t)((t00 * w00 + t01 * w01 + t10 * w10 + t11 * w11 + (1 << 14)) >> 15) << (8 * c);
+        }
+        const uint32_t g = C == 1 ? px : (__dp2a_hi(k2, px, __dp2a_lo(k01, px, 1u << 14)) >> 15);
+        out |= g << (8 * i);
+    }
+    // pixels past the last column land in the row's right padding (rewritten by k_margin / never read)
+    *reinterpret_cast<uint32_t*>(dst + (size_t)img * plane + (size_t)y * pitch + x0) = out;
+}
+
+void launch_remap(const uint8_t* src, int sw, int sh, int channels, int rgb, const float* mapx, const float* mapy, uint8_t* l0, int w, int h, int pitch,
+                  size_t planeBytes, int nImages, cudaStream_t s) {
+    const uint32_t RY = 9798, GY = 19235, BY = 3735;
+    const uint32_t k01 = (rgb ? RY : BY) | (GY << 16), k2 = rgb ? BY : RY;
+    dim3 grid((w + 511) / 512, h, nImages);
+    if (channels == 1)
+        k_remap<1><<<grid, 128, 0, s>>>(src, sw, sh, mapx, mapy, l0, w, h, pitch, planeBytes, k01, k2);
+    else if (channels == 3)
+        k_remap<3><<<grid, 128, 0, s>>>(src, sw, sh, mapx, mapy, l0, w, h, pitch, planeBytes, k01, k2);
+    else
+        k_remap<4><<<grid, 128, 0, s>>>(src, sw, sh, mapx, mapy, l0, w, h, pitch, planeBytes, k01, k2);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Reflect-101 margin of every pyramid plane (3 rows / 3 columns around the interior): what GaussianBlur(...,
 // BORDER_REFLECT_101) reads beyond the edge of its (cloned, hence border-less) input (ORBextractor.cc:1105-1106).  With the
 // margin in place the blur kernel below has no edge cases.  One launch covers all levels of all images.

@@ -147,6 +147,8 @@ struct orbx_batch {
     FastMaps fastMaps;
     LevelMaps blurMaps, resizeMaps;
     DescMaps descMaps;
+    float *rectX = nullptr, *rectY = nullptr;  // resident rectification maps [height][width] (System.cc:238-248), null = none
+    int srcW = 0, srcH = 0;                    // size of the raw images the maps sample
     uint8_t* stageIn = nullptr;  // dense device staging of uploaded images (PCIe copies of odd-width rows are ~6x slower than one contiguous copy)
     size_t stageBytes = 0;
 };
@@ -478,6 +480,62 @@ int orbx_batch_upload_color(orbx_batch* b, const uint8_t* host_images, size_t ro
                                  cudaMemcpyHostToDevice, b->stream));
     const LevelGeom& L0 = b->g.lv[0];
     launch_gray(b->stageIn, channels, rgb, b->buf.pyr + L0.planeOff + (size_t)first * L0.planeBytes, L0.w, L0.h, L0.pitch, (size_t)L0.planeBytes, n, b->stream);
+    CU(cudaGetLastError());
+    return ORBX_OK;
+}
+
+// System::TrackStereoLidar's rectification (System.cc:238-248): the CV_32FC1 maps of Settings::M1l()/M2l() (or M1r()/M2r()), one
+// float per pixel of the handle's width x height, sampling raw images of src_width x src_height.  NULL maps clear it.  Synchronises.
+int orbx_batch_set_rectification(orbx_batch* b, const float* map_x, const float* map_y, size_t map_stride_bytes, int src_width, int src_height) {
+    if (!b) return fail(ORBX_ERR_ARG, "null batch");
+    DeviceGuard dg(b->device);
+    CU(cudaStreamSynchronize(b->stream));
+    if (!map_x || !map_y) {
+        b->srcW = b->srcH = 0;
+        return ORBX_OK;
+    }
+    if (src_width <= 0 || src_height <= 0 || src_width > ORBX_MAX_DIM || src_height > ORBX_MAX_DIM) return fail(ORBX_ERR_ARG, "raw image size out of range");
+    const size_t rowBytes = (size_t)b->width * sizeof(float);
+    if (map_stride_bytes < rowBytes) return fail(ORBX_ERR_ARG, "map stride smaller than width * sizeof(float)");
+    if (!b->rectX) {
+        int r;
+        if ((r = dev_alloc(b, &b->rectX, (size_t)b->width * b->height))) return r;
+        if ((r = dev_alloc(b, &b->rectY, (size_t)b->width * b->height))) return r;
+    }
+    CU(cudaMemcpy2D(b->rectX, rowBytes, map_x, map_stride_bytes, rowBytes, b->height, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy2D(b->rectY, rowBytes, map_y, map_stride_bytes, rowBytes, b->height, cudaMemcpyHostToDevice));
+    b->srcW = src_width; b->srcH = src_height;
+    return ORBX_OK;
+}
+
+// raw (unrectified) images of src_width x src_height, channels 1, 3 or 4 -> cv::remap -> [cvtColor] -> level 0, all on the device
+int orbx_batch_upload_raw(orbx_batch* b, const uint8_t* host_images, size_t row_stride, size_t image_stride, int channels, int rgb, int first, int n) {
+    int r = check_images(b, first, n);
+    if (r) return r;
+    if (!host_images) return fail(ORBX_ERR_EMPTY, "null image");
+    if (!b->srcW) return fail(ORBX_ERR_ARG, "no rectification maps set (orbx_batch_set_rectification)");
+    if (channels != 1 && channels != 3 && channels != 4) return fail(ORBX_ERR_ARG, "images have 1, 3 or 4 interleaved channels");
+    const size_t rowBytes = (size_t)b->srcW * channels;
+    if (row_stride < rowBytes) return fail(ORBX_ERR_ARG, "row stride smaller than width * channels");
+    if (n == 0) return ORBX_OK;
+    DeviceGuard dg(b->device);
+    const size_t imgBytes = rowBytes * b->srcH, bytes = (size_t)n * imgBytes + 64;
+    if (bytes > b->stageBytes) {
+        CU(cudaStreamSynchronize(b->stream));
+        if (b->stageIn) cudaFree(b->stageIn);
+        b->stageIn = nullptr; b->stageBytes = 0;
+        CU(cudaMalloc((void**)&b->stageIn, bytes));
+        b->stageBytes = bytes;
+    }
+    if (row_stride == rowBytes && (n == 1 || image_stride == imgBytes))
+        CU(cudaMemcpyAsync(b->stageIn, host_images, (size_t)n * imgBytes, cudaMemcpyHostToDevice, b->stream));
+    else
+        for (int i = 0; i < n; ++i)
+            CU(cudaMemcpy2DAsync(b->stageIn + (size_t)i * imgBytes, rowBytes, host_images + (size_t)i * image_stride, row_stride, rowBytes, b->srcH,
+                                 cudaMemcpyHostToDevice, b->stream));
+    const LevelGeom& L0 = b->g.lv[0];
+    launch_remap(b->stageIn, b->srcW, b->srcH, channels, rgb, b->rectX, b->rectY, b->buf.pyr + L0.planeOff + (size_t)first * L0.planeBytes, L0.w, L0.h, L0.pitch,
+                 (size_t)L0.planeBytes, n, b->stream);
     CU(cudaGetLastError());
     return ORBX_OK;
 }
@@ -950,6 +1008,10 @@ struct orbx_extractor {
     // call it is captured once into a CUDA graph and replayed; pinCnt[4..5] is the pinned lapping window the graph reads.
     cudaGraphExec_t exec = nullptr;
     int channels = 1, rgb = 0;  // input format of the last call (1 = grey); a change re-captures the graph
+    // rectification (orbx_set_rectification): host copies of the maps, applied to the batch-of-one when it is (re)created
+    std::vector<float> rectX, rectY;
+    int rectW = 0, rectH = 0, srcW = 0, srcH = 0;
+    bool rectDirty = false;
     int graphState = 0;  // 0: next call runs eagerly (lazy allocations), 1: capture on the next call, 2: replay `exec`, 3: capture failed, stay eager
 };
 
@@ -971,9 +1033,18 @@ int extractor_prepare(orbx_extractor* h, int w, int hgt, int channels, int rgb) 
         if (r) return r;
         orbx_batch_set_blur_taps(h->b, h->taps);
         h->b->lapStable = true;
+        h->rectDirty = h->rectW > 0;
+    }
+    if (h->rectDirty) {  // new maps (or a new batch-of-one): other kernels and pointers, start over with an eager call
+        if (h->exec) { cudaGraphExecDestroy(h->exec); h->exec = nullptr; }
+        h->graphState = 0;
+        int r = h->rectW > 0 ? orbx_batch_set_rectification(h->b, h->rectX.data(), h->rectY.data(), (size_t)h->rectW * sizeof(float), h->srcW, h->srcH)
+                             : orbx_batch_set_rectification(h->b, nullptr, nullptr, 0, 0, 0);
+        if (r) return r;
+        h->rectDirty = false;
     }
     DeviceGuard dg(h->device);
-    const size_t need = (size_t)w * hgt * channels;
+    const size_t need = h->rectW > 0 ? (size_t)h->srcW * h->srcH * channels : (size_t)w * hgt * channels;
     if (need > h->pinImgBytes) {
         if (h->pinImg) cudaFreeHost(h->pinImg);
         h->pinImg = nullptr; h->pinImgBytes = 0;
@@ -998,7 +1069,8 @@ int extractor_prepare(orbx_extractor* h, int w, int hgt, int channels, int rgb) 
 // everything one image needs, enqueued on the handle's streams (also the body of the captured graph)
 int extractor_enqueue(orbx_extractor* h, int w, int hgt) {
     int r;
-    if (h->channels == 1) r = orbx_batch_upload(h->b, h->pinImg, (size_t)w, (size_t)w * hgt, 0, 1);
+    if (h->rectW > 0) r = orbx_batch_upload_raw(h->b, h->pinImg, (size_t)h->srcW * h->channels, (size_t)h->srcW * h->channels * h->srcH, h->channels, h->rgb, 0, 1);
+    else if (h->channels == 1) r = orbx_batch_upload(h->b, h->pinImg, (size_t)w, (size_t)w * hgt, 0, 1);
     else r = orbx_batch_upload_color(h->b, h->pinImg, (size_t)w * h->channels, (size_t)w * h->channels * hgt, h->channels, h->rgb, 0, 1);
     if (r) return r;
     if ((r = orbx_batch_run(h->b, 1, h->pinCnt + 4))) return r;
@@ -1015,10 +1087,16 @@ int extractor_enqueue(orbx_extractor* h, int w, int hgt) {
 
 // stage + enqueue everything for one image; nothing waits here
 int extractor_issue(orbx_extractor* h, const uint8_t* image, int w, int hgt, size_t stride, int lap0, int lap1, int channels = 1, int rgb = 0) {
+    // with rectification maps the caller hands in the RAW image (System.cc:238-248); the extractor works on the maps' size
+    const int rawH = hgt;
+    if (h->rectW > 0) {
+        if (w != h->srcW || hgt != h->srcH) return fail(ORBX_ERR_ARG, "image size differs from the raw size given to orbx_set_rectification");
+        w = h->rectW; hgt = h->rectH;
+    }
     int r = extractor_prepare(h, w, hgt, channels, rgb);
     if (r) return r;
-    const size_t rowBytes = (size_t)w * channels;
-    for (int y = 0; y < hgt; ++y) std::memcpy(h->pinImg + (size_t)y * rowBytes, image + (size_t)y * stride, rowBytes);
+    const size_t rowBytes = (size_t)(h->rectW > 0 ? h->srcW : w) * channels;
+    for (int y = 0; y < rawH; ++y) std::memcpy(h->pinImg + (size_t)y * rowBytes, image + (size_t)y * stride, rowBytes);
     h->pinCnt[4] = lap0; h->pinCnt[5] = lap1;
     DeviceGuard dg(h->device);
     orbx_batch* b = h->b;
@@ -1156,6 +1234,33 @@ int orbx_extract_stereo(orbx_extractor* left, orbx_extractor* right, const uint8
     r = extractor_collect(left, kps_left, desc_left, cap_left, n_left, mono_left);
     const int r2 = extractor_collect(right, kps_right, desc_right, cap_right, n_right, mono_right);
     return r ? r : r2;
+}
+
+// System::TrackStereoLidar's cv::remap (System.cc:238-248) in front of this extractor: map_x / map_y are the CV_32FC1 maps of the
+// camera this extractor serves (Settings::M1l()/M2l() or M1r()/M2r()), width x height floats; the orbx_extract* calls then take
+// the RAW src_width x src_height image.  NULL maps switch rectification off.
+int orbx_set_rectification(orbx_extractor* h, const float* map_x, const float* map_y, int width, int height, size_t map_stride_bytes, int src_width,
+                           int src_height) {
+    if (!h) return fail(ORBX_ERR_ARG, "null handle");
+    if (!map_x || !map_y) {
+        h->rectW = h->rectH = h->srcW = h->srcH = 0;
+        h->rectX.clear(); h->rectY.clear();
+        h->rectDirty = true;
+        return ORBX_OK;
+    }
+    if (width <= 0 || height <= 0 || src_width <= 0 || src_height <= 0 || width > ORBX_MAX_DIM || height > ORBX_MAX_DIM || src_width > ORBX_MAX_DIM ||
+        src_height > ORBX_MAX_DIM)
+        return fail(ORBX_ERR_ARG, "image size out of range");
+    if (map_stride_bytes < (size_t)width * sizeof(float)) return fail(ORBX_ERR_ARG, "map stride smaller than width * sizeof(float)");
+    h->rectX.resize((size_t)width * height);
+    h->rectY.resize((size_t)width * height);
+    for (int y = 0; y < height; ++y) {
+        std::memcpy(h->rectX.data() + (size_t)y * width, (const char*)map_x + (size_t)y * map_stride_bytes, (size_t)width * sizeof(float));
+        std::memcpy(h->rectY.data() + (size_t)y * width, (const char*)map_y + (size_t)y * map_stride_bytes, (size_t)width * sizeof(float));
+    }
+    h->rectW = width; h->rectH = height; h->srcW = src_width; h->srcH = src_height;
+    h->rectDirty = true;
+    return ORBX_OK;
 }
 
 // the same with the caller's cvtColor (Tracking.cc:1646-1671) done on the device: interleaved 8-bit colour input

@@ -124,6 +124,8 @@ struct DescMaps {  // per level: 48x31 boxes of the pyramid (IC_Angle patch), 64
 void launch_describe(const Geom& g, const Buffers& b, const DescMaps& maps, int nImages, cudaStream_t s);
 cudaError_t describe_configure();
 void launch_margin(const Geom& g, const Buffers& b, int nImages, cudaStream_t s);
+void launch_remap(const uint8_t* src, int sw, int sh, int channels, int rgb, const float* mapx, const float* mapy, uint8_t* l0, int w, int h, int pitch,
+                  size_t planeBytes, int nImages, cudaStream_t s);
 void launch_gray(const uint8_t* src, int channels, int rgb, uint8_t* l0, int w, int h, int pitch, size_t planeBytes, int nImages, cudaStream_t s);
 void launch_border(const uint8_t* src, int w, int h, int pitch, uint8_t* dst, int dpitch, cudaStream_t s);
 size_t octree_smem_bytes(int nodeCap);

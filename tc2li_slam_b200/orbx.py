@@ -72,6 +72,9 @@ def lib():
         "orbx_batch_upload": (i, [_vp, _vp, sz, sz, i, i]),
         "orbx_batch_upload_device": (i, [_vp, _vp, sz, sz, i, i]),
         "orbx_batch_upload_color": (i, [_vp, _vp, sz, sz, i, i, i, i]),
+        "orbx_batch_upload_raw": (i, [_vp, _vp, sz, sz, i, i, i, i]),
+        "orbx_batch_set_rectification": (i, [_vp, _vp, _vp, sz, i, i]),
+        "orbx_set_rectification": (i, [_vp, _vp, _vp, i, i, sz, i, i]),
         "orbx_extract_color": (i, [_vp, _vp, i, i, sz, i, i, i, i, _vp, _vp, i, _vp, _vp]),
         "orbx_extract_stereo_color": (i, [_vp, _vp, _vp, _vp, i, i, sz, sz, i, i, _vp, _vp, _vp, _vp, i, _vp, _vp, _vp, _vp, i, _vp, _vp]),
         "orbx_batch_synth": (i, [_vp, u32, i, i, i]),
@@ -335,6 +338,17 @@ class ORBextractor:
                                   _p(self._kps), _p(self._desc), cap, C.byref(n), C.byref(mono)))
         return mono.value, self._kps[:n.value].copy(), self._desc[:n.value].copy()
 
+    def set_rectification(self, map_x, map_y, src_size):
+        """System::TrackStereoLidar's cv::remap (System.cc:238-248) in front of this extractor: float32 maps [H, W] (Settings::M1l/M2l or
+        M1r/M2r) sampling raw images of src_size = (src_width, src_height); afterwards __call__ / extract_color take the RAW image.
+        map_x=None switches it off."""
+        if map_x is None:
+            _check(lib().orbx_set_rectification(self._h, None, None, 0, 0, 0, 0, 0))
+            return
+        mx, my = np.ascontiguousarray(map_x, np.float32), np.ascontiguousarray(map_y, np.float32)
+        assert mx.shape == my.shape and mx.ndim == 2
+        _check(lib().orbx_set_rectification(self._h, _p(mx), _p(my), mx.shape[1], mx.shape[0], mx.strides[0], int(src_size[0]), int(src_size[1])))
+
     def extract_color(self, image, rgb, vLappingArea=(0, 0)):
         """The caller's cvtColor (Tracking.cc:1646-1671: COLOR_RGB[A]2GRAY if rgb else COLOR_BGR[A]2GRAY) on the device, then
         operator().  image: uint8 [H, W, 3|4].  The grey image the reference keeps (mImGray) is self.level(0)."""
@@ -490,6 +504,18 @@ class BatchExtractor:
         images = np.asarray(images)
         assert images.dtype == np.uint8 and images.ndim == 4 and images.shape[3] in (3, 4) and images.strides[3] == 1 and images.strides[2] == images.shape[3]
         _check(lib().orbx_batch_upload_color(self._h, _p(images), images.strides[1], images.strides[0], images.shape[3], int(bool(rgb)), first, images.shape[0]))
+
+    def set_rectification(self, map_x, map_y, src_size):
+        """float32 maps [H, W] for all images of the handle (System.cc:238-248); raw images are then uploaded with upload_raw()."""
+        mx, my = np.ascontiguousarray(map_x, np.float32), np.ascontiguousarray(map_y, np.float32)
+        assert mx.shape == my.shape == (self.height, self.width)
+        _check(lib().orbx_batch_set_rectification(self._h, _p(mx), _p(my), mx.strides[0], int(src_size[0]), int(src_size[1])))
+
+    def upload_raw(self, images, rgb=False, first=0):
+        """raw images uint8 [n, srcH, srcW] or [n, srcH, srcW, 3|4]: cv::remap (+ cvtColor) on the device into level 0."""
+        images = np.ascontiguousarray(images)
+        ch = 1 if images.ndim == 3 else images.shape[3]
+        _check(lib().orbx_batch_upload_raw(self._h, _p(images), images.strides[1], images.strides[0], ch, int(bool(rgb)), first, images.shape[0]))
 
     def upload_device(self, dev_ptr, row_stride, image_stride, first, n):
         _check(lib().orbx_batch_upload_device(self._h, _vp(dev_ptr), row_stride, image_stride, first, n))

@@ -149,3 +149,43 @@ def test_cvt_gray_all_colours():
     img = np.stack([(v & 255), (v >> 8) & 255, (v >> 16)], axis=-1).astype(np.uint8).reshape(4096, 4096, 3)
     assert np.array_equal(po.cvt_gray(img, True), cv2.cvtColor(img, cv2.COLOR_RGB2GRAY))
     assert np.array_equal(po.cvt_gray(img, False), cv2.cvtColor(img, cv2.COLOR_BGR2GRAY))
+
+
+def _rect_maps(dw, dh, sw, sh, seed):
+    """maps shaped like a rectification (smooth warp + rotation), reaching outside the source at the corners, with a sprinkling
+    of exact-grid and exact-half coordinates (the rounding boundaries of cvRound(v * 32))"""
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:dh, 0:dw].astype(np.float32)
+    cx, cy = np.float32(dw / 2), np.float32(dh / 2)
+    r2 = ((x - cx) ** 2 + (y - cy) ** 2) / np.float32(cx * cx + cy * cy)
+    mx = (cx + (x - cx) * (1 + 0.12 * r2) * np.float32(sw / dw) * 1.03 + 0.02 * (y - cy) - 3).astype(np.float32)
+    my = (cy + (y - cy) * (1 + 0.12 * r2) * np.float32(sh / dh) * 1.03 - 0.02 * (x - cx) + 2).astype(np.float32)
+    k = rng.integers(0, dw * dh, 4000)
+    mx.flat[k[:1000]] = np.round(mx.flat[k[:1000]])
+    my.flat[k[1000:2000]] = np.round(my.flat[k[1000:2000]]) + np.float32(0.5)
+    mx.flat[k[2000:3000]] = (np.round(mx.flat[k[2000:3000]] * 32) + np.float32(0.5)) / np.float32(32)   # ties of cvRound(v * 32)
+    my.flat[k[3000:]] = (np.round(my.flat[k[3000:]] * 32) - np.float32(0.5)) / np.float32(32)
+    return mx, my
+
+
+@pytest.mark.parametrize("channels", [1, 3, 4])
+def test_remap_matches_cv2(channels):
+    """System::TrackStereoLidar's cv::remap(im, out, M1, M2, cv::INTER_LINEAR) (System.cc:247-248), CV_32F maps (Settings.cc:523-526)."""
+    rng = np.random.default_rng(channels)
+    for (sw, sh, dw, dh) in [(752, 480, 752, 480), (640, 400, 600, 380), (97, 61, 131, 83)]:
+        shape = (sh, sw) if channels == 1 else (sh, sw, channels)
+        img = rng.integers(0, 256, shape, dtype=np.uint8)
+        mx, my = _rect_maps(dw, dh, sw, sh, sw + channels)
+        want = cv2.remap(img, mx, my, cv2.INTER_LINEAR)
+        got = po.remap(img, mx, my)
+        assert np.array_equal(got, want), (sw, sh, dw, dh, int((got != want).sum()))
+
+
+def test_remap_far_outside_and_borders():
+    img = np.full((50, 70), 200, np.uint8)
+    y, x = np.mgrid[0:64, 0:96].astype(np.float32)
+    mx = (x * 1.5 - 30).astype(np.float32)
+    my = (y * 1.7 - 25).astype(np.float32)
+    mx[0, 0], my[0, 0] = -1e6, 3.0
+    mx[1, 1], my[1, 1] = 5.0, 4e5
+    assert np.array_equal(po.remap(img, mx, my), cv2.remap(img, mx, my, cv2.INTER_LINEAR))
