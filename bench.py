@@ -182,6 +182,32 @@ def emit_line(text):
     os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (text + "\n").encode())
 
 
+def bind_to_gpu_numa_node(device):
+    """One process per GPU: run on the cores of the NUMA node the GPU hangs off, so that the pinned staging buffers (first
+    touch) and the copies that feed the GPU stay on its socket.  Returns a description, or None when the topology is not
+    exposed (single-socket hosts, containers without sysfs)."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(device).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(device), "pci_domain_id", 0)
+        devid = getattr(torch.cuda.get_device_properties(device), "pci_device_id", 0)
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{devid:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus": len(cpus)}
+    except Exception:
+        return None
+
+
 def main():
     claim_stdout()
     ap = argparse.ArgumentParser()
@@ -211,6 +237,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     import torch
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -466,7 +493,7 @@ def main():
             "config": {"workload": WORKLOAD,
                        "pairs_per_gpu_per_step": args.pairs, "images_per_launch_set": group, "keypoints_per_image": kp_mean,
                        "l2": f"inputs {n_img * W * H / 1e9:.2f} GB per rank, larger than the {L2_BYTES / 1e6:.0f} MB L2; no flush needed"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step, "roofline": roofline, "cpu_baseline": cpu, "stages": stages, "latency": latency, "stereo_match": stereo, "large_images": large, "euroc_lapping": euroc,
+            "clocks": clocks, "numa_binding": numa, "e2e": e2e, "gpu_launches": launches_per_step, "roofline": roofline, "cpu_baseline": cpu, "stages": stages, "latency": latency, "stereo_match": stereo, "large_images": large, "euroc_lapping": euroc,
         }
         emit_line(json.dumps(line))
     big.close()
