@@ -351,12 +351,13 @@ void launch_margin(const Geom& g, const Buffers& b, int nImages, cudaStream_t s)
 // ---------------------------------------------------------------------------------------------------------------
 // 7x7 sigma=2 Gaussian blur (GaussianBlur on a clone, ORBextractor.cc:1105-1106; arithmetic SURVEY.md A.3).
 // OpenCV's 8-bit path is a separable 8.8 fixed-point filter whose row pass cannot saturate (taps sum to 256 or 257), so the
-// result is the exact integer 2-D convolution followed by one rounding, (v + 32768) >> 16.  Here: each thread owns a column
-// strip 4 pixels wide and slides down the rows.  Row pass: the 7 taps of a pixel are two 4-byte dot products (IDP.4A) on
-// byte windows cut out of three aligned 32-bit loads with PRMT.  Column pass: a chain of 6 running sums per pixel (7 IMAD
-// per pixel and row), no shared memory, no inter-thread exchange; a warp reads and writes 128 contiguous bytes per row.
+// result is the exact integer 2-D convolution followed by one rounding, (v + 32768) >> 16.  Here: a warp owns a 128-pixel
+// column strip of one image (a thread 4 columns) and slides down the rows; its input arrives as double-buffered TMA boxes (see
+// k_blur).  Row pass: the 7 taps of a pixel are two 4-byte dot products (IDP.4A) on byte windows cut out of three aligned
+// 32-bit shared-memory loads with PRMT.  Column pass: two input rows at a time as 16x2 lanes, one IDP.2A per touched output
+// row against the tap pairs, six running sums per pixel carried across boxes; no inter-thread exchange; a warp writes 128
+// contiguous bytes per row.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int BLUR_SEG = 32;   // output rows per warp (6 extra rows of warm-up each)
 constexpr int BLUR_WARPS = 4;
 
 constexpr int BLUR_BOXW = 144;                  // 4 halo bytes + 128 pixels + 4 halo bytes, rounded to a multiple of 16
