@@ -90,6 +90,7 @@ constexpr int RS_BOXW = 192, RS_BOXH = 24;
 __global__ void __launch_bounds__(32 * RS_WARPS) k_resize_s12(const __grid_constant__ CUtensorMap srcMap, int sh, int imgBase, uint8_t* __restrict__ dst,
                                                              int dw, int dh, int dpitch, size_t dplane, ResizeTab t) {
     __shared__ __align__(128) unsigned char tile[RS_WARPS][RS_BOXW * RS_BOXH];
+    __shared__ __align__(16) uint4 rowTab[RS_WARPS][RS_SEG];   // per destination row of the segment: {sy0, sy1, b0 << 12, b1 << 12}
     __shared__ __align__(8) uint64_t bars[RS_WARPS];
     const int wy = threadIdx.y;
     const int xw = blockIdx.x * 128;                       // first destination column of the warp
@@ -123,13 +124,15 @@ __global__ void __launch_bounds__(32 * RS_WARPS) k_resize_s12(const __grid_const
     // 32-bit shared-window address of the thread's first word (kept in a register; explicit ld.shared below)
     const uint32_t sBase = smem_u32(tile[wy]) + (uint32_t)(kMarginX + base - boxX) - (uint32_t)(syMin * RS_BOXW);
     uint8_t* D = dst + (size_t)blockIdx.z * dplane + x0 + (size_t)ys * dpitch;
-    // the row tables of the segment, one row per lane (clamped source rows, vertical weights pre-scaled for mad.hi),
-    // broadcast with shuffles inside the loop
-    const int myRow = min(ys + (int)threadIdx.x, dh - 1);
-    const int myYo = t.yofs[myRow];
-    const uint32_t myRows = (uint32_t)min(max(myYo, 0), sh - 1) | ((uint32_t)min(max(myYo + 1, 0), sh - 1) << 16);
-    const uint32_t myBw = *reinterpret_cast<const uint32_t*>(t.yb + 2 * myRow);
-    const uint32_t myB0 = (myBw & 0xFFFFu) << 12, myB1 = (myBw >> 16) << 12;
+    // the row table of the segment (clamped source rows, vertical weights pre-scaled for mad.hi): one row per lane into shared
+    // memory, read back in the loop as one broadcast 128-bit load
+    if (threadIdx.x < RS_SEG) {
+        const int myRow = min(ys + (int)threadIdx.x, dh - 1);
+        const int myYo = t.yofs[myRow];
+        const uint32_t myBw = *reinterpret_cast<const uint32_t*>(t.yb + 2 * myRow);
+        rowTab[wy][threadIdx.x] = make_uint4((uint32_t)min(max(myYo, 0), sh - 1), (uint32_t)min(max(myYo + 1, 0), sh - 1), (myBw & 0xFFFFu) << 12, (myBw >> 16) << 12);
+    }
+    __syncwarp();
     // Issue balance: the ALU pipe (LOP3 / SHF / PRMT / IADD3) and the FMA pipe (IMAD / IDP) each take one warp instruction
     // every other cycle per scheduler (profiles/tools/pipe_probe.cu), and cv::resize's vertical pass written with shifts is
     // almost all ALU.  Here the horizontally interpolated value keeps its low four bits cleared, S' = S & ~15, instead of
@@ -150,9 +153,9 @@ __global__ void __launch_bounds__(32 * RS_WARPS) k_resize_s12(const __grid_const
     uint32_t hA[4] = {0, 0, 0, 0}, hB[4] = {0, 0, 0, 0};
     const int nrows = ye - ys;
     for (int k = 0; k < nrows; ++k) {
-        const uint32_t rows = __shfl_sync(0xFFFFFFFFu, myRows, k);
-        const uint32_t b0 = __shfl_sync(0xFFFFFFFFu, myB0, k), b1 = __shfl_sync(0xFFFFFFFFu, myB1, k);
-        const int sy0 = (int)(rows & 0xFFFFu), sy1 = (int)(rows >> 16);
+        const uint4 rt = rowTab[wy][k];
+        const int sy0 = (int)rt.x, sy1 = (int)rt.y;
+        const uint32_t b0 = rt.z, b1 = rt.w;
         if (sy0 != rA) {
             if (sy0 == rB) {
 #pragma unroll
@@ -161,17 +164,11 @@ __global__ void __launch_bounds__(32 * RS_WARPS) k_resize_s12(const __grid_const
                 hrow(sy0, hA);
             rA = sy0;
         }
-        if (sy1 != rB) {
-            if (sy1 == rA) {  // only when the source row index was clamped at the bottom
-#pragma unroll
-                for (int i = 0; i < 4; ++i) hB[i] = hA[i];
-            } else
-                hrow(sy1, hB);
-            rB = sy1;
-        }
+        // (sy1 == sy0 only where the source row index is clamped at the bottom: the row is then simply interpolated twice)
+        if (sy1 != rB) { hrow(sy1, hB); rB = sy1; }
         uint32_t u[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) u[i] = (__umulhi(b1, hB[i]) + __umulhi(b0, hA[i]) + 2u) * k64;  // byte 1 = the pixel (<= 255 by construction)
+        for (int i = 0; i < 4; ++i) u[i] = (__umulhi(b1, hB[i]) + __umulhi(b0, hA[i])) * k64 + 128u;  // (A + B + 2) * 64: byte 1 = the pixel (<= 255 by construction)
         const uint32_t out = __byte_perm(__byte_perm(u[0], u[1], 0x0051), __byte_perm(u[2], u[3], 0x0051), 0x5410);
         // lanes past the last column store into the row's right padding (rewritten by k_margin / never read)
         *reinterpret_cast<uint32_t*>(D) = out;
