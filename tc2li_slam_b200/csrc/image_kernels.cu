@@ -147,29 +147,30 @@ __global__ void __launch_bounds__(32 * RS_WARPS) k_resize_s12(const __grid_const
     };
     const uint32_t k64 = 64u + ((uint32_t)dw >> 30);  // 64, opaque to the compiler: keeps the multiply an IMAD (FMA pipe) instead of a LEA (ALU pipe)
     mbar_wait(&bars[wy], 0);
-    // hA / hB: interpolated source rows rA < rB, consumed as a stream (the lower row of one destination row is usually the
-    // upper row of the next)
-    int rA = -1, rB = -1;
-    uint32_t hA[4] = {0, 0, 0, 0}, hB[4] = {0, 0, 0, 0};
+    // hX / hY: the two most recent horizontally interpolated source rows (rows rX, rY).  A destination row needs rows sy0 and
+    // sy0 + 1; it usually finds sy0 in one of the two and loads sy0 + 1 over the other, so the roles alternate and no
+    // register-to-register copies are needed — the vertical pass exists in both orientations.
+    int rX = -1, rY = -1;
+    uint32_t hX[4] = {0, 0, 0, 0}, hY[4] = {0, 0, 0, 0};
     const int nrows = ye - ys;
-    for (int k = 0; k < nrows; ++k) {
-        const uint4 rt = rowTab[wy][k];
-        const int sy0 = (int)rt.x, sy1 = (int)rt.y;
-        const uint32_t b0 = rt.z, b1 = rt.w;
-        if (sy0 != rA) {
-            if (sy0 == rB) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) hA[i] = hB[i];
-            } else
-                hrow(sy0, hA);
-            rA = sy0;
-        }
-        // (sy1 == sy0 only where the source row index is clamped at the bottom: the row is then simply interpolated twice)
-        if (sy1 != rB) { hrow(sy1, hB); rB = sy1; }
+    auto vertical = [&](const uint32_t (&A)[4], const uint32_t (&B)[4], uint32_t b0, uint32_t b1) -> uint32_t {
         uint32_t u[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) u[i] = (__umulhi(b1, hB[i]) + __umulhi(b0, hA[i])) * k64 + 128u;  // (A + B + 2) * 64: byte 1 = the pixel (<= 255 by construction)
-        const uint32_t out = __byte_perm(__byte_perm(u[0], u[1], 0x0051), __byte_perm(u[2], u[3], 0x0051), 0x5410);
+        for (int i = 0; i < 4; ++i) u[i] = (__umulhi(b1, B[i]) + __umulhi(b0, A[i])) * k64 + 128u;  // (A + B + 2) * 64: byte 1 = the pixel (<= 255 by construction)
+        return __byte_perm(__byte_perm(u[0], u[1], 0x0051), __byte_perm(u[2], u[3], 0x0051), 0x5410);
+    };
+    for (int k = 0; k < nrows; ++k) {
+        const uint4 rt = rowTab[wy][k];
+        const int sy0 = (int)rt.x, sy1 = (int)rt.y;  // (sy1 == sy0 only where the source row index is clamped at the bottom: the row is then interpolated twice)
+        uint32_t out;
+        if (sy0 == rY) {
+            if (sy1 != rX) { hrow(sy1, hX); rX = sy1; }
+            out = vertical(hY, hX, rt.z, rt.w);
+        } else {
+            if (sy0 != rX) { hrow(sy0, hX); rX = sy0; }
+            if (sy1 != rY) { hrow(sy1, hY); rY = sy1; }
+            out = vertical(hX, hY, rt.z, rt.w);
+        }
         // lanes past the last column store into the row's right padding (rewritten by k_margin / never read)
         *reinterpret_cast<uint32_t*>(D) = out;
         D += dpitch;
