@@ -239,8 +239,11 @@ __global__ void __launch_bounds__(32 * FW) k_fast_cells(const __grid_constant__ 
 
             // ---- pass A: compass test, 4 pixels per lane; words with a survivor are listed with their 4 pixel flags ----
             {
-                const uint32_t kAdd = (uint32_t)(0x7f - (t & 0x7f)) * 0x01010101u;
+                // Both values go through a shuffle so that ptxas keeps them in registers: it otherwise re-derives kAdd with a move +
+                // IMAD at each of its four uses and the shared-window base with four uniform instructions per trip.
+                const uint32_t kAdd = __shfl_sync(FULL, (uint32_t)(0x7f - (t & 0x7f)) * 0x01010101u, 0);
                 const uint32_t nh = t >= 128 ? 0u : 0xFFFFFFFFu;
+                const uint32_t tileS = __shfl_sync(FULL, smem_u32(tileW), 0);  // shared-window address for the explicit ld.shared below
                 const int items = ih * nW;
                 // bytes outside the interior [0, iw) can only sit in the first / last word of a row
                 const int xb0 = 4 * wFirst - 3 - shift;  // interior x of byte 0 of the first word (<= 0)
@@ -261,8 +264,10 @@ __global__ void __launch_bounds__(32 * FW) k_fast_cells(const __grid_constant__ 
                 }
                 auto compass = [&](bool live, int cc, int wofs) -> uint32_t {
                     if (!live) return 0u;
-                    const uint32_t* row = tileW + wofs;
-                    const uint32_t cur = row[0], prev = row[-1], next = row[1], up = row[3 * (TS / 4)], dn = row[-3 * (TS / 4)];
+                    uint32_t cur, prev, next, up, dn;
+                    asm volatile("ld.shared.u32 %0, [%5];\n\tld.shared.u32 %1, [%5+-4];\n\tld.shared.u32 %2, [%5+4];\n\tld.shared.u32 %3, [%5+%6];\n\tld.shared.u32 %4, [%5+-%6];"
+                                 : "=r"(cur), "=r"(prev), "=r"(next), "=r"(up), "=r"(dn)
+                                 : "r"(tileS + 4u * (uint32_t)wofs), "n"(3 * TS));
                     const uint32_t e = __funnelshift_r(cur, next, 24);  // pixels at x + 3
                     const uint32_t wv = __funnelshift_r(prev, cur, 8);  // pixels at x - 3
                     const uint32_t ns = bytes_gt(__vabsdiffu4(up, cur), kAdd, nh) | bytes_gt(__vabsdiffu4(dn, cur), kAdd, nh);
