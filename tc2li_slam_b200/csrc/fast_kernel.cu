@@ -192,24 +192,28 @@ __global__ void __launch_bounds__(32 * FW) k_fast_cells(const __grid_constant__ 
     uint32_t ph0 = 0, ph1 = 0;
 
     const int stride = gridDim.x * FW;
-    auto issue = [&](int w, int buf) {  // lane 0: the crop of work item w into tile buffer `buf` (cells without FAST work load nothing)
-        const int img = w / nCells;
-        const uint4 cd = __ldg(b.cellTab + (w - img * nCells));
+    auto issue = [&](int img, int cell, int buf) {  // lane 0: the crop of work item (img, cell) into tile buffer `buf` (cells without FAST work load nothing)
+        const uint4 cd = __ldg(b.cellTab + cell);
         if ((cd.y >> 24) != 2) return;
         const int iniX = cd.x & 0xFFFF, iniY = cd.x >> 16, level = (cd.y >> 16) & 0xFF;
         mbar_arrive_expect_tx(&bars[wid][buf], TS * (g.lv[level].hCell + 6));
         tma_load_3d(my + buf * tileBytes, &maps.m[level], &bars[wid][buf], (kMarginX + iniX) & ~15, kMarginY + iniY, b.imgBase + img);
     };
     int w = blockIdx.x * FW + wid;
-    if (lane == 0 && w < nWork) issue(w, 0);
     // (image, cell) of the work item, walked incrementally: `stride` items further is dImg images and dCell cells on
     const int dImg = stride / nCells, dCell = stride - dImg * nCells;
     int imgRel = w / nCells, cellIdx = w - imgRel * nCells;
+    if (lane == 0 && w < nWork) issue(imgRel, cellIdx, 0);
     for (int it = 0; w < nWork; w += stride, ++it, imgRel += dImg, cellIdx += dCell) {
         const int buf = NB == 2 ? (it & 1) : 0;
         if (cellIdx >= nCells) { cellIdx -= nCells; ++imgRel; }
-        if (NB == 2) { if (lane == 0 && w + stride < nWork) issue(w + stride, buf ^ 1); }
-        else if (lane == 0 && it > 0) issue(w, 0);
+        if (NB == 2) {
+            if (lane == 0 && w + stride < nWork) {
+                const int c2 = cellIdx + dCell, wrap = c2 >= nCells;
+                issue(imgRel + dImg + wrap, c2 - (wrap ? nCells : 0), buf ^ 1);
+            }
+        } else if (lane == 0 && it > 0)
+            issue(imgRel, cellIdx, 0);
         const int img = b.imgBase + imgRel;
         const uint4 cd = __ldg(b.cellTab + cellIdx);
         const int iniX = cd.x & 0xFFFF, iniY = cd.x >> 16;
