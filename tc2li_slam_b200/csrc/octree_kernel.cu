@@ -153,7 +153,7 @@ __device__ __forceinline__ void emit_children(const OctShared& s, int cur, int i
 //   phase 2 (nodes split in descending sorted order until the list has N nodes): children of the r-th processed node start
 //            at  sum_{r<r'<t} nch_r',  t = number of nodes processed before the reference's `break`;
 //   nodes that are not split follow all child blocks in their old relative order.
-// Only the libstdc++-exact sort of phase 2 (ties decide results) runs on a single thread.
+// The libstdc++-exact sort of phase 2 (ties decide results) is CTA-parallel too (parsort_emul.cuh).
 template <int OT_THREADS>
 __global__ void __launch_bounds__(OT_THREADS) k_octree(const __grid_constant__ Geom g, const Buffers b, int levelBase, int stageCap) {
     extern __shared__ __align__(16) unsigned char smemRaw[];

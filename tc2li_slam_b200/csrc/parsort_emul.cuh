@@ -11,6 +11,9 @@
 //    is stable and moves an element only past strictly greater ones: the final position of x is
 //    x - #{p in [x-16, x) : key_p > key_x} + #{p in (x, x+16] : key_p < key_x}.
 // The control flow (range stack, depth limit, median-of-three, heap-sort fallback) is the serial one, run by thread 0.
+// Ranges of at most PS_SMALL elements are not partitioned by the CTA: they are parked and, at the end, each is finished by one
+// thread running the plain serial loop (StdSortEmul::introsort_range) — all parked ranges at the same time; ranges are
+// independent, so the result is the same, and the number of CTA-wide partition steps (four barriers each) drops several-fold.
 // Call with all threads of the CTA (blockDim.x == PS_THREADS); contains __syncthreads().
 #pragma once
 #include "stdsort_emul.cuh"
@@ -20,8 +23,12 @@ namespace orbx {
 constexpr int PS_THREADS = 64;      // default CTA size of the callers
 constexpr int PS_MAX_WARPS = 8;
 
+constexpr int PS_SMALL = 48;        // ranges up to this length are finished by ONE thread each (all of them concurrently)
+constexpr int PS_SMALL_MAX = 128;   // capacity of the small-range list; beyond it ranges are partitioned by the CTA as usual
+
 struct ParSortShared {
     int stF[48], stL[48], stD[48];
+    int smF[PS_SMALL_MAX], smL[PS_SMALL_MAX], smD[PS_SMALL_MAX], nSmall;
     int sp, first, last, depth, done, K, totGe, totLe, warpGe[PS_MAX_WARPS], warpLe[PS_MAX_WARPS];
 };
 
@@ -39,7 +46,7 @@ __device__ inline void par_std_sort(unsigned long long* a, int n, unsigned long 
     if (tid == 0) {
         int lg = 0;
         while ((1 << (lg + 1)) <= n) ++lg;
-        sh.sp = 0; sh.first = 0; sh.last = n; sh.depth = 2 * lg; sh.done = 0;
+        sh.sp = 0; sh.first = 0; sh.last = n; sh.depth = 2 * lg; sh.done = 0; sh.nSmall = 0;
     }
     __syncthreads();
     while (true) {
@@ -47,6 +54,13 @@ __device__ inline void par_std_sort(unsigned long long* a, int n, unsigned long 
             // next range that needs a partition (ranges of <= 16 elements are left to the final insertion sort)
             int first = sh.first, last = sh.last, depth = sh.depth, sp = sh.sp;
             while (true) {
+                if (last - first > 16 && last - first <= PS_SMALL && sh.nSmall < PS_SMALL_MAX) {
+                    // short range: parked, finished below by a single thread while other threads finish the other short ranges
+                    const int k = sh.nSmall++;
+                    sh.smF[k] = first; sh.smL[k] = last; sh.smD[k] = depth;
+                    last = first;
+                    continue;
+                }
                 if (last - first > 16) {
                     if (depth == 0) { S::heap_sort(a, first, last); last = first; continue; }
                     --depth;
@@ -122,6 +136,9 @@ __device__ inline void par_std_sort(unsigned long long* a, int n, unsigned long 
         }
         __syncthreads();
     }
+    // ---- the parked short ranges: the serial introsort loop, one range per thread (the ranges are disjoint) ----
+    for (int r = tid; r < sh.nSmall; r += PS_THREADS) S::template introsort_range<16>(a, sh.smF[r], sh.smL[r], sh.smD[r]);
+    __syncthreads();
     // ---- final insertion sort == stable placement inside windows of 16 ----
     for (int x = tid; x < n; x += PS_THREADS) {
         const unsigned long long e = a[x];

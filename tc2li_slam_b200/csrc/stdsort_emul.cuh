@@ -109,6 +109,31 @@ struct StdSortEmul {
             ++first;
         }
     }
+    // __introsort_loop on the sub-range [first0, last0) with `depth0` splits left: everything std::sort does to that range before
+    // the final insertion sort.  Ranges are independent, so different threads may run this on disjoint ranges concurrently.
+    template <int StackN>
+    static __host__ __device__ void introsort_range(E* a, int first0, int last0, int depth0) {
+        int stackFirst[StackN], stackLast[StackN], stackDepth[StackN], sp = 0;
+        stackFirst[0] = first0; stackLast[0] = last0; stackDepth[0] = depth0; sp = 1;
+        while (sp > 0) {
+            --sp;
+            int first = stackFirst[sp], last = stackLast[sp], depth = stackDepth[sp];
+            while (last - first > 16) {
+                if (depth == 0) { heap_sort(a, first, last); break; }
+                --depth;
+                const int mid = first + (last - first) / 2;
+                move_median_to_first(a, first, first + 1, mid, last - 1);
+                const int cut = unguarded_partition(a, first + 1, last, first);
+                if (cut - first < last - cut) {  // keep the larger one pending: the stack stays below log2 of the range length
+                    stackFirst[sp] = cut; stackLast[sp] = last; stackDepth[sp] = depth; ++sp;
+                    last = cut;
+                } else {
+                    stackFirst[sp] = first; stackLast[sp] = cut; stackDepth[sp] = depth; ++sp;
+                    first = cut;
+                }
+            }
+        }
+    }
     // forceHeapDepth >= 0 overrides the depth limit (tests only: exercises the heap fallback)
     static __host__ __device__ void sort(E* a, int n, int forceDepth = -1) {
         if (n <= 0) return;
