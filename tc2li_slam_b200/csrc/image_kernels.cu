@@ -392,7 +392,6 @@ __global__ void __launch_bounds__(32 * BLUR_WARPS) k_blur(const __grid_constant_
     const bool active = x0 < w;
     uint8_t* D = dst + (size_t)imgRel * plane + x0;
     uint32_t ph0 = 0, ph1 = 0;
-    const int ys = 0, ye = h;
     // Column pass two input rows at a time: P = (h[y], h[y+1]) as 16x2 lanes, and the pair's contribution to the eight output
     // rows y-3 .. y+4 is one IDP.2A each against the tap pairs (t6,0) (t5,t6) (t4,t5) (t3,t4) (t2,t3) (t1,t2) (t0,t1) (0,t0).
     // a[i][0..5] = running sums of output rows y-3 .. y+2 before the pair (y, y+1) is added.
@@ -400,7 +399,7 @@ __global__ void __launch_bounds__(32 * BLUR_WARPS) k_blur(const __grid_constant_
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int k = 0; k < 6; ++k) a[i][k] = 0;
+        for (int k = 0; k < 6; ++k) a[i][k] = 0;  // (the rows fed by these initial sums lie above the image and are not stored)
     auto hpass = [&](const uint32_t wd[3], uint32_t hr[4]) {  // row pass of one input row
         const uint32_t prev = wd[0], cur = wd[1], next = wd[2];
         hr[0] = __dp4a(__byte_perm(prev, cur, 0x4321), cA, __dp4a(__byte_perm(cur, next, 0x4321), cB, 0u));
@@ -408,29 +407,34 @@ __global__ void __launch_bounds__(32 * BLUR_WARPS) k_blur(const __grid_constant_
         hr[2] = __dp4a(__byte_perm(prev, cur, 0x6543), cA, __dp4a(__byte_perm(cur, next, 0x6543), cB, 0u));
         hr[3] = __dp4a(cur, cA, __dp4a(next, cB, 0u));
     };
+    // The rounding term of (v + 32768) >> 16 rides in the two accumulators a chain starts from; the result is then byte 2 of
+    // the sum (PRMT picks it; with taps summing to 257 the sum may exceed 255 << 16 and is clamped first).  Drow: the output
+    // row y - 3 of the pair being added, advanced by two rows per pair.
+    const uint32_t RND = 32768u;
+    uint8_t* Drow = D - (ptrdiff_t)6 * pitch;  // the first pair (box row 0 = image row -3) feeds output rows -6, -5
     auto pair = [&](int y, const uint32_t wa[3], const uint32_t wb[3]) {  // input rows y, y+1 -> output rows y-3, y-2
         uint32_t hA[4], hB[4];
         hpass(wa, hA);
         hpass(wb, hB);
-        uint32_t out0 = 0, out1 = 0;
+        uint32_t o0[4], o1[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const uint32_t P = __byte_perm(hA[i], hB[i], 0x5410);  // both <= 65535 (taps sum to <= 257)
-            const uint32_t o0 = __dp2a_lo(P, c67, a[i][0]);
-            const uint32_t o1 = __dp2a_lo(P, c56, a[i][1]);
+            o0[i] = __dp2a_lo(P, c67, a[i][0]);
+            o1[i] = __dp2a_lo(P, c56, a[i][1]);
             a[i][0] = __dp2a_lo(P, c45, a[i][2]);
             a[i][1] = __dp2a_lo(P, c34, a[i][3]);
             a[i][2] = __dp2a_lo(P, c23, a[i][4]);
             a[i][3] = __dp2a_lo(P, c12, a[i][5]);
-            a[i][4] = __dp2a_lo(P, c01, 0u);
-            a[i][5] = __dp2a_lo(P, c0x, 0u);
-            uint32_t r0 = (o0 + 32768u) >> 16, r1 = (o1 + 32768u) >> 16;
-            if (SAT) { r0 = min(r0, 255u); r1 = min(r1, 255u); }
-            out0 |= r0 << (8 * i);
-            out1 |= r1 << (8 * i);
+            a[i][4] = __dp2a_lo(P, c01, RND);
+            a[i][5] = __dp2a_lo(P, c0x, RND);
+            if (SAT) { o0[i] = min(o0[i], 0x00FFFFFFu); o1[i] = min(o1[i], 0x00FFFFFFu); }
         }
-        if (y - 3 >= ys && y - 3 < ye) *reinterpret_cast<uint32_t*>(D + (size_t)(y - 3) * pitch) = out0;
-        if (y - 2 >= ys && y - 2 < ye) *reinterpret_cast<uint32_t*>(D + (size_t)(y - 2) * pitch) = out1;
+        const uint32_t out0 = __byte_perm(__byte_perm(o0[0], o0[1], 0x0062), __byte_perm(o0[2], o0[3], 0x0062), 0x5410);
+        const uint32_t out1 = __byte_perm(__byte_perm(o1[0], o1[1], 0x0062), __byte_perm(o1[2], o1[3], 0x0062), 0x5410);
+        if ((unsigned)(y - 3) < (unsigned)h) *reinterpret_cast<uint32_t*>(Drow) = out0;
+        if ((unsigned)(y - 2) < (unsigned)h) *reinterpret_cast<uint32_t*>(Drow + pitch) = out1;
+        Drow += 2 * (ptrdiff_t)pitch;
     };
     for (int c = 0; c < nChunks; ++c) {
         if (c & 1) { mbar_wait(&bars[wy][1], ph1); ph1 ^= 1; }
