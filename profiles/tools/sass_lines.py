@@ -26,7 +26,7 @@ for f in os.listdir(tmp):
     for ln in dis.splitlines():
         m = re.match(r"\s*\.text\.(\S+):", ln)
         if m:
-            cur_fn = m.group(1); active = mangled_hint in cur_fn; 
+            cur_fn = m.group(1); active = mangled_hint in cur_fn and all(f"Li{a}E" in cur_fn for a in re.findall(r"\(int\)(\d+)", kname)); 
             if active: candidates.append(cur_fn)
             continue
         m = re.search(r'//## File "([^"]+)", line (\d+)', ln)

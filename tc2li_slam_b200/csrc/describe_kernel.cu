@@ -103,9 +103,18 @@ void launch_assemble(const Geom& g, const Buffers& b, int nImages, cudaStream_t 
 //      64-byte-row window; pattern as float4 {x0,y0,x1,y1} in shared memory; cvRound as add-magic (RNE, exact below 2^22).
 constexpr int DW = 8;            // warps per CTA
 constexpr int KPW = 8;           // consecutive keypoints per warp
-constexpr int PA_ROW = 48, PB_ROW = 64;
-constexpr int PA_BYTES = PA_ROW * 31, PB_BYTES = PB_ROW * 37;
-constexpr int ST_BYTES = 2432;   // one stage holds either box (PB_BYTES = 2368), 128-byte aligned
+constexpr int PA_ROW = 48, PB_ROW = kDescWindowRow;
+constexpr int PA_BYTES = PA_ROW * kDescARows, PB_BYTES = PB_ROW * kDescBRows;
+constexpr int ST_BYTES = (PB_ROW * 37 + 127) & ~127;   // one stage holds either box, 128-byte aligned
+#ifndef DESC_PAT_REGS
+#define DESC_PAT_REGS 1
+#endif
+#ifndef DESC_NA
+#define DESC_NA 2
+#endif
+constexpr int SA_BYTES = 1536;   // the moment phase cuts the same shared memory into NA stages of one 48 x 31 patch each
+constexpr int NA = DESC_NA;
+static_assert(NA >= 2 && NA <= 4 && NA * SA_BYTES <= 2 * ST_BYTES && PA_BYTES <= SA_BYTES, "moment stages");
 
 __device__ __forceinline__ int dp4a_us(uint32_t pix, uint32_t wgt, int acc) {  // unsigned pixels x signed weights
     int d;
@@ -116,26 +125,28 @@ __device__ __forceinline__ int dp4a_us(uint32_t pix, uint32_t wgt, int acc) {  /
 __global__ void __launch_bounds__(32 * DW) k_describe(const __grid_constant__ Geom g, const Buffers b, const __grid_constant__ DescMaps maps) {
     extern __shared__ __align__(128) unsigned char dsm[];
     __shared__ __align__(16) float4 pat4[256];
-    __shared__ __align__(8) uint64_t bars[DW][2];
+    __shared__ __align__(8) uint64_t bars[DW][4];
     __shared__ int mom[DW * KPW][2];
     __shared__ float2 rot[DW * KPW];  // (sin, cos)
+    __shared__ KpWork wks[DW * KPW];  // the CTA's work items (one coalesced read instead of a global load per use)
     const int img = b.imgBase + blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n = b.outCount[img];
+    const int kBase = blockIdx.x * DW * KPW;
+    if (kBase >= n) return;
+    if (tid < DW * KPW && kBase + tid < n) wks[tid] = b.work[(size_t)img * g.K + kBase + tid];
     {   // pair p = 8 * byte + bit is read by lane `byte` in iteration `bit`: store it at [bit][byte] so that a warp reads 32
         // consecutive float4 (a [byte][bit] layout makes every lane hit the same banks: 8-way conflicts)
         const signed char* q = c_pattern + 4 * tid;
         pat4[(tid & 7) * 32 + (tid >> 3)] = make_float4((float)q[0], (float)q[1], (float)q[2], (float)q[3]);
     }
-    if (lane == 0) { mbar_init(&bars[wid][0], 1); mbar_init(&bars[wid][1], 1); }
+    if (lane == 0) { mbar_init(&bars[wid][0], 1); mbar_init(&bars[wid][1], 1); mbar_init(&bars[wid][2], 1); mbar_init(&bars[wid][3], 1); }
     mbar_fence_init();
     __syncthreads();
-    const int n = b.outCount[img];
-    const int kBase = blockIdx.x * DW * KPW;
-    if (kBase >= n) return;
     const int k0 = kBase + wid * KPW;
     const int cnt = max(0, min(KPW, n - k0));
     unsigned char* stage = dsm + (size_t)wid * 2 * ST_BYTES;
-    const KpWork* work = b.work + (size_t)img * g.K + k0;
-    uint32_t ph0 = 0, ph1 = 0;  // parities of the two stage barriers (uniform per warp)
+    const KpWork* work = wks + wid * KPW;
+    uint32_t phbits = 0;  // bit s = parity of stage barrier s (uniform per warp)
 
     auto issueB = [&](int i) {
         const KpWork wk = work[i];
@@ -144,8 +155,8 @@ __global__ void __launch_bounds__(32 * DW) k_describe(const __grid_constant__ Ge
         tma_load_3d(stage + (i & 1) * ST_BYTES, &maps.bl[wk.level], bar, (kMarginX + wk.x - 18) & ~15, kMarginY + wk.y - 18, img);
     };
     auto wait_stage = [&](int st) {
-        if (st == 0) { mbar_wait(&bars[wid][0], ph0); ph0 ^= 1; }
-        else { mbar_wait(&bars[wid][1], ph1); ph1 ^= 1; }
+        mbar_wait(&bars[wid][st], (phbits >> st) & 1u);
+        phbits ^= 1u << st;
     };
 
     // ---- phase 1: moments ----
@@ -166,19 +177,21 @@ __global__ void __launch_bounds__(32 * DW) k_describe(const __grid_constant__ Ge
             }
             wu[c] = a; w1[c] = o;
         }
-        auto issueA = [&](int i) {
+        auto issueA = [&](int i, int st) {
             const KpWork wk = work[i];
-            uint64_t* bar = &bars[wid][i & 1];
+            uint64_t* bar = &bars[wid][st];
             mbar_arrive_expect_tx(bar, PA_BYTES);
-            tma_load_3d(stage + (i & 1) * ST_BYTES, &maps.ic[wk.level], bar, (kMarginX + wk.x - kHalfPatch) & ~15, kMarginY + wk.y - kHalfPatch, img);
+            tma_load_3d(stage + st * SA_BYTES, &maps.ic[wk.level], bar, (kMarginX + wk.x - kHalfPatch) & ~15, kMarginY + wk.y - kHalfPatch, img);
         };
-        if (lane == 0 && cnt > 0) issueA(0);
+        if (lane == 0)
+            for (int j = 0; j < NA - 1 && j < cnt; ++j) issueA(j, j);
+        int st = 0, stNext = NA - 1;  // stage of keypoint i, stage of keypoint i + NA - 1
         for (int i = 0; i < cnt; ++i) {
-            if (lane == 0 && i + 1 < cnt) issueA(i + 1);
+            if (lane == 0 && i + NA - 1 < cnt) issueA(i + NA - 1, stNext);
             const int sa = (kMarginX + work[i].x - kHalfPatch) & 15;  // patch column -15 sits at byte sa of the box row
-            wait_stage(i & 1);
+            wait_stage(st);
             // the whole 48-byte box row as three 128-bit loads (conflict-free at this stride), then a warp-uniform word offset
-            const uint4* rowp = reinterpret_cast<const uint4*>(stage + (i & 1) * ST_BYTES + (lane < 31 ? lane : 0) * PA_ROW);
+            const uint4* rowp = reinterpret_cast<const uint4*>(stage + st * SA_BYTES + (lane < 31 ? lane : 0) * PA_ROW);
             const uint4 q0 = rowp[0], q1 = rowp[1], q2 = rowp[2];
             const uint32_t rw[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
             const int bs = (sa & 3) * 8;
@@ -206,6 +219,8 @@ __global__ void __launch_bounds__(32 * DW) k_describe(const __grid_constant__ Ge
             }
             if (lane == 0) { mom[wid * KPW + i][0] = m01; mom[wid * KPW + i][1] = m10; }
             __syncwarp();  // every lane is done with this stage before lane 0 re-arms it
+            stNext = st;
+            st = st + 1 == NA ? 0 : st + 1;
         }
         // both stages are free: put the first two blurred windows in flight while phase 2 runs
         if (lane == 0) {
@@ -222,13 +237,17 @@ __global__ void __launch_bounds__(32 * DW) k_describe(const __grid_constant__ Ge
         float sn, cs;
         sinf_cosf_glibc(__fmul_rn(angle, factorPI), &sn, &cs);
         rot[tid] = make_float2(sn, cs);
-        const KpWork wk = b.work[(size_t)img * g.K + kBase + tid];
-        b.kps[(size_t)img * g.K + wk.dst].angle = angle;
+        b.kps[(size_t)img * g.K + wks[tid].dst].angle = angle;
     }
     __syncthreads();
 
     // ---- phase 3: steered BRIEF ----
     const float RND = 12582912.f;  // 1.5 * 2^23: (x + RND) has the round-half-even integer of x in its low mantissa bits
+#if DESC_PAT_REGS
+    float4 pq[8];  // this lane's eight pattern pairs stay in registers over the warp's keypoints
+#pragma unroll
+    for (int bit = 0; bit < 8; ++bit) pq[bit] = pat4[bit * 32 + lane];
+#endif
     for (int i = 0; i < cnt; ++i) {
         const KpWork wk = work[i];
         const float2 sc = rot[wid * KPW + i];
@@ -240,7 +259,11 @@ __global__ void __launch_bounds__(32 * DW) k_describe(const __grid_constant__ Ge
         int val = 0;
 #pragma unroll
         for (int bit = 0; bit < 8; ++bit) {
+#if DESC_PAT_REGS
+            const float4 q = pq[bit];
+#else
             const float4 q = pat4[bit * 32 + lane];
+#endif
             const int r0 = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(q.x, sn), __fmul_rn(q.y, cs)), RND));
             const int c0 = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(q.x, cs), __fmul_rn(q.y, sn)), RND));
             const int r1 = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(q.z, sn), __fmul_rn(q.w, cs)), RND));

@@ -37,6 +37,9 @@ namespace {
 constexpr int FW = 1;                    // warps per CTA (every warp is independent; small CTAs pack shared memory best)
 constexpr int CAP = 512;                 // entries of list1 / list2
 constexpr int CAPW = 256;                // entries of listW (32-bit)
+#ifndef FAST_NI
+#define FAST_NI 2
+#endif
 constexpr int NB = 1;                    // tile buffers per warp (2 = the next cell's crop is prefetched)
 constexpr unsigned FULL = 0xFFFFFFFFu;
 
@@ -248,57 +251,50 @@ __global__ void __launch_bounds__(32 * FW) k_fast_cells(const __grid_constant__ 
                 const uint32_t kAdd = __shfl_sync(FULL, (uint32_t)(0x7f - (t & 0x7f)) * 0x01010101u, 0);
                 const uint32_t nh = t >= 128 ? 0u : 0xFFFFFFFFu;
                 const uint32_t tileS = __shfl_sync(FULL, smem_u32(tileW), 0);  // shared-window address for the explicit ld.shared below
-                const int items = ih * nW;
                 // bytes outside the interior [0, iw) can only sit in the first / last word of a row
                 const int xb0 = 4 * wFirst - 3 - shift;  // interior x of byte 0 of the first word (<= 0)
                 const uint32_t maskFirst = 0x80808080u << (8 * (-xb0));
                 const uint32_t maskLast = 0x80808080u >> (8 * (xb0 + 4 * nW - iw));
-                // item = (row y, word cc) in row-major order; NI items per lane per trip (32 apart), walked incrementally:
-                // 32 * NI items further is dq rows and dr words on, with a carry into the next row
-                constexpr int NI = 2;
-                const int dq = nW == 1 ? 32 * NI : (int)__umulhi(32u * NI, magicW), dr = 32 * NI - dq * nW;  // (the magic of 1 does not fit 32 bits)
-                const int dW = dq * (TS / 4) + dr, wrapW = TS / 4 - nW;
-                int itx[NI], ccs[NI], wos[NI];
-#pragma unroll
-                for (int j = 0; j < NI; ++j) {
-                    itx[j] = lane + 32 * j;
-                    const int y = nW == 1 ? itx[j] : (int)__umulhi((uint32_t)itx[j], magicW);
-                    ccs[j] = itx[j] - y * nW;
-                    wos[j] = (y + 3) * (TS / 4) + wFirst + ccs[j];
-                }
-                auto compass = [&](bool live, int cc, int wofs) -> uint32_t {
-                    if (!live) return 0u;
+                // Lane = (row r of a group of RT = 32 / nW rows, word col): the word column, its edge mask and the row phase are
+                // per-lane constants of the cell, a trip advances every lane by RT rows (one add), and a row past the interior
+                // only zeroes the lane's mask (the reads stay inside the warp's own shared memory: the score map follows the tile).
+                // (RT <= 4 bounds the rows read past the interior; lanes beyond RT * nW idle on row 0 with an empty mask)
+                const int RT = nW == 1 ? 4 : min(4, (int)__umulhi(32u, magicW));
+                int r = nW == 1 ? lane : (int)__umulhi((uint32_t)lane, magicW), col = lane - r * nW;
+                const bool laneOn = r < RT;
+                if (!laneOn) { r = 0; col = 0; }
+                const uint32_t mLane = laneOn ? (col == 0 ? maskFirst : 0x80808080u) & (col == nW - 1 ? maskLast : 0x80808080u) : 0u;
+                constexpr int NI = FAST_NI;
+                const int dW = RT * (TS / 4);
+                int y = r, wofs = (r + 3) * (TS / 4) + wFirst + col;
+                auto compass = [&](uint32_t m, int wo) -> uint32_t {
                     uint32_t cur, prev, next, up, dn;
                     asm volatile("ld.shared.u32 %0, [%5];\n\tld.shared.u32 %1, [%5+-4];\n\tld.shared.u32 %2, [%5+4];\n\tld.shared.u32 %3, [%5+%6];\n\tld.shared.u32 %4, [%5+-%6];"
                                  : "=r"(cur), "=r"(prev), "=r"(next), "=r"(up), "=r"(dn)
-                                 : "r"(tileS + 4u * (uint32_t)wofs), "n"(3 * TS));
+                                 : "r"(tileS + 4u * (uint32_t)wo), "n"(3 * TS));
                     const uint32_t e = __funnelshift_r(cur, next, 24);  // pixels at x + 3
                     const uint32_t wv = __funnelshift_r(prev, cur, 8);  // pixels at x - 3
                     const uint32_t ns = bytes_gt(__vabsdiffu4(up, cur), kAdd, nh) | bytes_gt(__vabsdiffu4(dn, cur), kAdd, nh);
                     const uint32_t ew = bytes_gt(__vabsdiffu4(e, cur), kAdd, nh) | bytes_gt(__vabsdiffu4(wv, cur), kAdd, nh);
-                    const uint32_t m = (cc == 0 ? maskFirst : 0x80808080u) & (cc == nW - 1 ? maskLast : 0x80808080u);
                     return ns & ew & m;
                 };
-                auto append = [&](uint32_t F, int wofs) {
+                auto append = [&](uint32_t F, int wo) {
                     const unsigned bal = __ballot_sync(FULL, F != 0);
                     if (bal) {
                         if (c.nw + 32 > CAPW) flush_W<TS>(c, t);  // warp-uniform
                         // bits 7/15/23/31 -> 4 contiguous flag bits 24..27
-                        if (F) c.listW[c.nw + __popc(bal & ((1u << lane) - 1))] = (((F >> 7) * 0x01020408u) & 0x0F000000u) | (uint32_t)wofs;
+                        if (F) c.listW[c.nw + __popc(bal & ((1u << lane) - 1))] = (((F >> 7) * 0x01020408u) & 0x0F000000u) | (uint32_t)wo;
                         c.nw += __popc(bal);
                     }
                 };
-                for (int base = 0; base < items; base += 32 * NI) {
+                for (int base = 0; base < ih; base += RT * NI) {
                     uint32_t F[NI];
 #pragma unroll
-                    for (int j = 0; j < NI; ++j) F[j] = compass(itx[j] < items, ccs[j], wos[j]);
+                    for (int j = 0; j < NI; ++j) F[j] = compass(y + j * RT < ih ? mLane : 0u, wofs + j * dW);
 #pragma unroll
-                    for (int j = 0; j < NI; ++j) {
-                        append(F[j], wos[j]);
-                        itx[j] += 32 * NI;
-                        ccs[j] += dr; wos[j] += dW;
-                        if (ccs[j] >= nW) { ccs[j] -= nW; wos[j] += wrapW; }
-                    }
+                    for (int j = 0; j < NI; ++j) append(F[j], wofs + j * dW);
+                    y += NI * RT;
+                    wofs += NI * dW;
                 }
                 __syncwarp();
             }

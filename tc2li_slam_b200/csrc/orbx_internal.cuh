@@ -117,6 +117,17 @@ int resize_encode_maps(const Geom& g, uint8_t* pyr, int nImages, LevelMaps* out)
 cudaError_t launch_octree(const Geom& g, const Buffers& b, int nImages, int numSMs, cudaStream_t s);
 int octree_launch_count(const Geom& g, int nImages, int numSMs);
 void launch_assemble(const Geom& g, const Buffers& b, int nImages, cudaStream_t s);
+#ifndef DESC_WINDOW_ROW
+#define DESC_WINDOW_ROW 80
+#endif
+constexpr int kDescWindowRow = DESC_WINDOW_ROW;  // bytes per row of the staged rBRIEF window (TMA box width, multiple of 16, >= 52)
+#ifndef DESC_A_ROWS
+#define DESC_A_ROWS 31
+#endif
+#ifndef DESC_B_ROWS
+#define DESC_B_ROWS 37
+#endif
+constexpr int kDescARows = DESC_A_ROWS, kDescBRows = DESC_B_ROWS;  // (timing experiments only: fewer rows give wrong results)
 struct DescMaps {  // per level: 48x31 boxes of the pyramid (IC_Angle patch), 64x37 boxes of the blurred pyramid (rBRIEF window)
     CUtensorMap ic[ORBX_MAX_LEVELS];
     CUtensorMap bl[ORBX_MAX_LEVELS];
