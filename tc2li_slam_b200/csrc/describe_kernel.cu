@@ -109,6 +109,12 @@ constexpr int ST_BYTES = (PB_ROW * 37 + 127) & ~127;   // one stage holds either
 #ifndef DESC_PAT_REGS
 #define DESC_PAT_REGS 1
 #endif
+#ifndef DESC_LANE_ISSUE
+#define DESC_LANE_ISSUE 1
+#endif
+#ifndef DESC_ADDR_FOLD
+#define DESC_ADDR_FOLD 1
+#endif
 #ifndef DESC_NA
 #define DESC_NA 2
 #endif
@@ -148,12 +154,28 @@ __global__ void __launch_bounds__(32 * DW) k_describe(const __grid_constant__ Ge
     const KpWork* work = wks + wid * KPW;
     uint32_t phbits = 0;  // bit s = parity of stage barrier s (uniform per warp)
 
+#if DESC_LANE_ISSUE
+    // Lane j owns the box loads of the warp's keypoint j: the box coordinates and the tensor-map offset are computed once for
+    // all eight keypoints (SIMD) and stay in the lane's registers, the stage is the lane's parity, and an issue is a one-lane
+    // branch around expect_tx + UTMALDG (the operands go to uniform registers either way) instead of ~20 scalar setup instructions.
+    const KpWork myWk = wks[wid * KPW + (lane & (KPW - 1))];
+    const int myLvOff = (int)myWk.level * (int)sizeof(CUtensorMap);
+    const int myAx = (kMarginX + myWk.x - kHalfPatch) & ~15, myBx = (kMarginX + myWk.x - 18) & ~15, myAy = kMarginY + myWk.y - kHalfPatch;
+    uint64_t* const myBar = &bars[wid][lane & 1];
+    unsigned char* const myStageA = stage + (lane & 1) * SA_BYTES;
+    unsigned char* const myStageB = stage + (lane & 1) * ST_BYTES;
+    auto issueB = [&](int i) {  // executed by lane i only
+        mbar_arrive_expect_tx(myBar, PB_BYTES);
+        tma_load_3d(myStageB, reinterpret_cast<const CUtensorMap*>(reinterpret_cast<const char*>(&maps.bl[0]) + myLvOff), myBar, myBx, myAy - 3, img);
+    };
+#else
     auto issueB = [&](int i) {
         const KpWork wk = work[i];
         uint64_t* bar = &bars[wid][i & 1];
         mbar_arrive_expect_tx(bar, PB_BYTES);
         tma_load_3d(stage + (i & 1) * ST_BYTES, &maps.bl[wk.level], bar, (kMarginX + wk.x - 18) & ~15, kMarginY + wk.y - 18, img);
     };
+#endif
     auto wait_stage = [&](int st) {
         mbar_wait(&bars[wid][st], (phbits >> st) & 1u);
         phbits ^= 1u << st;
@@ -183,11 +205,24 @@ __global__ void __launch_bounds__(32 * DW) k_describe(const __grid_constant__ Ge
             mbar_arrive_expect_tx(bar, PA_BYTES);
             tma_load_3d(stage + st * SA_BYTES, &maps.ic[wk.level], bar, (kMarginX + wk.x - kHalfPatch) & ~15, kMarginY + wk.y - kHalfPatch, img);
         };
+#if DESC_LANE_ISSUE
+        static_assert(NA == 2, "lane-owned issue: the stage is the lane's parity");
+        auto issueMyA = [&]() {
+            mbar_arrive_expect_tx(myBar, PA_BYTES);
+            tma_load_3d(myStageA, reinterpret_cast<const CUtensorMap*>(reinterpret_cast<const char*>(&maps.ic[0]) + myLvOff), myBar, myAx, myAy, img);
+        };
+        if (lane == 0 && cnt > 0) issueMyA();
+#else
         if (lane == 0)
             for (int j = 0; j < NA - 1 && j < cnt; ++j) issueA(j, j);
+#endif
         int st = 0, stNext = NA - 1;  // stage of keypoint i, stage of keypoint i + NA - 1
         for (int i = 0; i < cnt; ++i) {
+#if DESC_LANE_ISSUE
+            if (lane == i + 1 && i + 1 < cnt) issueMyA();
+#else
             if (lane == 0 && i + NA - 1 < cnt) issueA(i + NA - 1, stNext);
+#endif
             const int sa = (kMarginX + work[i].x - kHalfPatch) & 15;  // patch column -15 sits at byte sa of the box row
             wait_stage(st);
             // the whole 48-byte box row as three 128-bit loads (conflict-free at this stride), then a warp-uniform word offset
@@ -223,10 +258,14 @@ __global__ void __launch_bounds__(32 * DW) k_describe(const __grid_constant__ Ge
             st = st + 1 == NA ? 0 : st + 1;
         }
         // both stages are free: put the first two blurred windows in flight while phase 2 runs
+#if DESC_LANE_ISSUE
+        if (lane < 2 && lane < cnt) issueB(lane);
+#else
         if (lane == 0) {
             if (cnt > 0) issueB(0);
             if (cnt > 1) issueB(1);
         }
+#endif
     }
     __syncthreads();
 
@@ -256,6 +295,7 @@ __global__ void __launch_bounds__(32 * DW) k_describe(const __grid_constant__ Ge
         // sample index r * 64 + c from the biased float bits (bias B = 0x4B400000 each), in wrap-around 32-bit arithmetic
         const unsigned char* cb = stage + (i & 1) * ST_BYTES + 18 * PB_ROW + 18 + ((kMarginX + wk.x - 18) & 15);
         const uint32_t BIAS = (uint32_t)(0x4B400000ull * (PB_ROW + 1));
+        const uint32_t cbK = smem_u32(cb) - BIAS;  // the window centre's shared address with both float biases taken off
         int val = 0;
 #pragma unroll
         for (int bit = 0; bit < 8; ++bit) {
@@ -268,13 +308,23 @@ __global__ void __launch_bounds__(32 * DW) k_describe(const __grid_constant__ Ge
             const int c0 = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(q.x, cs), __fmul_rn(q.y, sn)), RND));
             const int r1 = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(q.z, sn), __fmul_rn(q.w, cs)), RND));
             const int c1 = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(q.z, cs), __fmul_rn(q.w, sn)), RND));
+#if DESC_ADDR_FOLD
+            uint32_t t0, t1;  // address = r * PB_ROW + (c + cbK): one add + one IMAD per sample
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t0) : "r"((uint32_t)r0 * PB_ROW + ((uint32_t)c0 + cbK)));
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t1) : "r"((uint32_t)r1 * PB_ROW + ((uint32_t)c1 + cbK)));
+#else
             const int i0 = (int)((uint32_t)r0 * PB_ROW + (uint32_t)c0 - BIAS), i1 = (int)((uint32_t)r1 * PB_ROW + (uint32_t)c1 - BIAS);
             const int t0 = cb[i0], t1 = cb[i1];
+#endif
             val |= (t0 < t1) << bit;
         }
         b.desc[((size_t)img * g.K + wk.dst) * 32 + lane] = (uint8_t)val;
         __syncwarp();
+#if DESC_LANE_ISSUE
+        if (lane == i + 2 && i + 2 < cnt) issueB(i + 2);
+#else
         if (lane == 0 && i + 2 < cnt) issueB(i + 2);
+#endif
     }
 }
 

@@ -35,8 +35,14 @@ namespace orbx {
 namespace {
 
 constexpr int FW = 1;                    // warps per CTA (every warp is independent; small CTAs pack shared memory best)
-constexpr int CAP = 512;                 // entries of list1 / list2
-constexpr int CAPW = 256;                // entries of listW (32-bit)
+#ifndef FAST_CAP
+#define FAST_CAP 512
+#endif
+#ifndef FAST_CAPW
+#define FAST_CAPW 256
+#endif
+constexpr int CAP = FAST_CAP;                 // entries of list1 / list2
+constexpr int CAPW = FAST_CAPW;                // entries of listW (32-bit)
 #ifndef FAST_NI
 #define FAST_NI 2
 #endif
