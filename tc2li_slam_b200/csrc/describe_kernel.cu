@@ -95,32 +95,25 @@ void launch_assemble(const Geom& g, const Buffers& b, int nImages, cudaStream_t 
 //   1  moments: per keypoint ONE lane issues a TMA box load of the 31x31 patch of the unblurred level (box rows of 48 bytes:
 //      box origins must be 16-byte aligned in global memory, so the box starts at the aligned byte at or before column
 //      -15) into the warp's double-buffered shared memory; the next box is in flight while the current one is reduced.
+//      Lane j issues for the warp's keypoint j with operands it computed once (SIMD over the eight keypoints).
 //      Lane v+15 owns patch row v: 9 words are funnel-shifted into 8 patch-aligned words, sum u*I and sum I are 2 x 8
 //      IDP.4A against per-lane constant weight words (circular mask folded in), then two warp-shuffle reductions.
 //   2  64 threads turn the 64 moment pairs into angle (cv::fastAtan2), cosf, sinf: the scalar float/double chain runs once
 //      per keypoint instead of once per lane.  Meanwhile the first two 37x37 windows of the blurred level are in flight.
 //   3  rBRIEF: lane i builds descriptor byte i from 16 rotated samples (|offset| <= 18: pattern radius 18.38) of the staged
-//      64-byte-row window; pattern as float4 {x0,y0,x1,y1} in shared memory; cvRound as add-magic (RNE, exact below 2^22).
+//      window; its eight pattern pairs {x0,y0,x1,y1} stay in registers; cvRound as add-magic (RNE, exact below 2^22).  The
+//      window rows are 80 bytes apart (TMA box width): with 64 the random byte gathers of a warp fall into 20 of the 32 banks
+//      (5.1 wavefronts per load, ncu), with 80 the row offsets cycle through all of them.
+// Timing experiment (boxes cut to 2 rows, wrong results): 9.17 instead of 9.55 ms, i.e. the kernel is not bound by the box loads
+// or by L2 / HBM but by instruction issue and dependency latency (~470 warp instructions per keypoint).
 constexpr int DW = 8;            // warps per CTA
 constexpr int KPW = 8;           // consecutive keypoints per warp
 constexpr int PA_ROW = 48, PB_ROW = kDescWindowRow;
-constexpr int PA_BYTES = PA_ROW * kDescARows, PB_BYTES = PB_ROW * kDescBRows;
+constexpr int PA_BYTES = PA_ROW * 31, PB_BYTES = PB_ROW * 37;
 constexpr int ST_BYTES = (PB_ROW * 37 + 127) & ~127;   // one stage holds either box, 128-byte aligned
-#ifndef DESC_PAT_REGS
-#define DESC_PAT_REGS 1
-#endif
-#ifndef DESC_LANE_ISSUE
-#define DESC_LANE_ISSUE 1
-#endif
-#ifndef DESC_ADDR_FOLD
-#define DESC_ADDR_FOLD 1
-#endif
-#ifndef DESC_NA
-#define DESC_NA 2
-#endif
-constexpr int SA_BYTES = 1536;   // the moment phase cuts the same shared memory into NA stages of one 48 x 31 patch each
-constexpr int NA = DESC_NA;
-static_assert(NA >= 2 && NA <= 4 && NA * SA_BYTES <= 2 * ST_BYTES && PA_BYTES <= SA_BYTES, "moment stages");
+constexpr int SA_BYTES = 1536;   // stage stride of the moment phase (one 48 x 31 patch)
+constexpr int NA = 2;            // patch stages = the lane parity of the issuing lane (three or four stages in the same memory measured slower: 10.3 vs 9.6 ms)
+static_assert(NA * SA_BYTES <= 2 * ST_BYTES && PA_BYTES <= SA_BYTES, "moment stages");
 
 __device__ __forceinline__ int dp4a_us(uint32_t pix, uint32_t wgt, int acc) {  // unsigned pixels x signed weights
     int d;
@@ -131,7 +124,7 @@ __device__ __forceinline__ int dp4a_us(uint32_t pix, uint32_t wgt, int acc) {  /
 __global__ void __launch_bounds__(32 * DW) k_describe(const __grid_constant__ Geom g, const Buffers b, const __grid_constant__ DescMaps maps) {
     extern __shared__ __align__(128) unsigned char dsm[];
     __shared__ __align__(16) float4 pat4[256];
-    __shared__ __align__(8) uint64_t bars[DW][4];
+    __shared__ __align__(8) uint64_t bars[DW][2];
     __shared__ int mom[DW * KPW][2];
     __shared__ float2 rot[DW * KPW];  // (sin, cos)
     __shared__ KpWork wks[DW * KPW];  // the CTA's work items (one coalesced read instead of a global load per use)
@@ -145,7 +138,7 @@ __global__ void __launch_bounds__(32 * DW) k_describe(const __grid_constant__ Ge
         const signed char* q = c_pattern + 4 * tid;
         pat4[(tid & 7) * 32 + (tid >> 3)] = make_float4((float)q[0], (float)q[1], (float)q[2], (float)q[3]);
     }
-    if (lane == 0) { mbar_init(&bars[wid][0], 1); mbar_init(&bars[wid][1], 1); mbar_init(&bars[wid][2], 1); mbar_init(&bars[wid][3], 1); }
+    if (lane == 0) { mbar_init(&bars[wid][0], 1); mbar_init(&bars[wid][1], 1); }
     mbar_fence_init();
     __syncthreads();
     const int k0 = kBase + wid * KPW;
@@ -154,7 +147,6 @@ __global__ void __launch_bounds__(32 * DW) k_describe(const __grid_constant__ Ge
     const KpWork* work = wks + wid * KPW;
     uint32_t phbits = 0;  // bit s = parity of stage barrier s (uniform per warp)
 
-#if DESC_LANE_ISSUE
     // Lane j owns the box loads of the warp's keypoint j: the box coordinates and the tensor-map offset are computed once for
     // all eight keypoints (SIMD) and stay in the lane's registers, the stage is the lane's parity, and an issue is a one-lane
     // branch around expect_tx + UTMALDG (the operands go to uniform registers either way) instead of ~20 scalar setup instructions.
@@ -168,14 +160,6 @@ __global__ void __launch_bounds__(32 * DW) k_describe(const __grid_constant__ Ge
         mbar_arrive_expect_tx(myBar, PB_BYTES);
         tma_load_3d(myStageB, reinterpret_cast<const CUtensorMap*>(reinterpret_cast<const char*>(&maps.bl[0]) + myLvOff), myBar, myBx, myAy - 3, img);
     };
-#else
-    auto issueB = [&](int i) {
-        const KpWork wk = work[i];
-        uint64_t* bar = &bars[wid][i & 1];
-        mbar_arrive_expect_tx(bar, PB_BYTES);
-        tma_load_3d(stage + (i & 1) * ST_BYTES, &maps.bl[wk.level], bar, (kMarginX + wk.x - 18) & ~15, kMarginY + wk.y - 18, img);
-    };
-#endif
     auto wait_stage = [&](int st) {
         mbar_wait(&bars[wid][st], (phbits >> st) & 1u);
         phbits ^= 1u << st;
@@ -199,30 +183,14 @@ __global__ void __launch_bounds__(32 * DW) k_describe(const __grid_constant__ Ge
             }
             wu[c] = a; w1[c] = o;
         }
-        auto issueA = [&](int i, int st) {
-            const KpWork wk = work[i];
-            uint64_t* bar = &bars[wid][st];
-            mbar_arrive_expect_tx(bar, PA_BYTES);
-            tma_load_3d(stage + st * SA_BYTES, &maps.ic[wk.level], bar, (kMarginX + wk.x - kHalfPatch) & ~15, kMarginY + wk.y - kHalfPatch, img);
-        };
-#if DESC_LANE_ISSUE
-        static_assert(NA == 2, "lane-owned issue: the stage is the lane's parity");
         auto issueMyA = [&]() {
             mbar_arrive_expect_tx(myBar, PA_BYTES);
             tma_load_3d(myStageA, reinterpret_cast<const CUtensorMap*>(reinterpret_cast<const char*>(&maps.ic[0]) + myLvOff), myBar, myAx, myAy, img);
         };
         if (lane == 0 && cnt > 0) issueMyA();
-#else
-        if (lane == 0)
-            for (int j = 0; j < NA - 1 && j < cnt; ++j) issueA(j, j);
-#endif
-        int st = 0, stNext = NA - 1;  // stage of keypoint i, stage of keypoint i + NA - 1
+        int st = 0;  // stage of keypoint i
         for (int i = 0; i < cnt; ++i) {
-#if DESC_LANE_ISSUE
             if (lane == i + 1 && i + 1 < cnt) issueMyA();
-#else
-            if (lane == 0 && i + NA - 1 < cnt) issueA(i + NA - 1, stNext);
-#endif
             const int sa = (kMarginX + work[i].x - kHalfPatch) & 15;  // patch column -15 sits at byte sa of the box row
             wait_stage(st);
             // the whole 48-byte box row as three 128-bit loads (conflict-free at this stride), then a warp-uniform word offset
@@ -254,18 +222,10 @@ __global__ void __launch_bounds__(32 * DW) k_describe(const __grid_constant__ Ge
             }
             if (lane == 0) { mom[wid * KPW + i][0] = m01; mom[wid * KPW + i][1] = m10; }
             __syncwarp();  // every lane is done with this stage before lane 0 re-arms it
-            stNext = st;
             st = st + 1 == NA ? 0 : st + 1;
         }
         // both stages are free: put the first two blurred windows in flight while phase 2 runs
-#if DESC_LANE_ISSUE
         if (lane < 2 && lane < cnt) issueB(lane);
-#else
-        if (lane == 0) {
-            if (cnt > 0) issueB(0);
-            if (cnt > 1) issueB(1);
-        }
-#endif
     }
     __syncthreads();
 
@@ -282,11 +242,9 @@ __global__ void __launch_bounds__(32 * DW) k_describe(const __grid_constant__ Ge
 
     // ---- phase 3: steered BRIEF ----
     const float RND = 12582912.f;  // 1.5 * 2^23: (x + RND) has the round-half-even integer of x in its low mantissa bits
-#if DESC_PAT_REGS
     float4 pq[8];  // this lane's eight pattern pairs stay in registers over the warp's keypoints
 #pragma unroll
     for (int bit = 0; bit < 8; ++bit) pq[bit] = pat4[bit * 32 + lane];
-#endif
     for (int i = 0; i < cnt; ++i) {
         const KpWork wk = work[i];
         const float2 sc = rot[wid * KPW + i];
@@ -299,32 +257,19 @@ __global__ void __launch_bounds__(32 * DW) k_describe(const __grid_constant__ Ge
         int val = 0;
 #pragma unroll
         for (int bit = 0; bit < 8; ++bit) {
-#if DESC_PAT_REGS
             const float4 q = pq[bit];
-#else
-            const float4 q = pat4[bit * 32 + lane];
-#endif
             const int r0 = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(q.x, sn), __fmul_rn(q.y, cs)), RND));
             const int c0 = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(q.x, cs), __fmul_rn(q.y, sn)), RND));
             const int r1 = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(q.z, sn), __fmul_rn(q.w, cs)), RND));
             const int c1 = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(q.z, cs), __fmul_rn(q.w, sn)), RND));
-#if DESC_ADDR_FOLD
             uint32_t t0, t1;  // address = r * PB_ROW + (c + cbK): one add + one IMAD per sample
             asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t0) : "r"((uint32_t)r0 * PB_ROW + ((uint32_t)c0 + cbK)));
             asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t1) : "r"((uint32_t)r1 * PB_ROW + ((uint32_t)c1 + cbK)));
-#else
-            const int i0 = (int)((uint32_t)r0 * PB_ROW + (uint32_t)c0 - BIAS), i1 = (int)((uint32_t)r1 * PB_ROW + (uint32_t)c1 - BIAS);
-            const int t0 = cb[i0], t1 = cb[i1];
-#endif
             val |= (t0 < t1) << bit;
         }
         b.desc[((size_t)img * g.K + wk.dst) * 32 + lane] = (uint8_t)val;
         __syncwarp();
-#if DESC_LANE_ISSUE
         if (lane == i + 2 && i + 2 < cnt) issueB(i + 2);
-#else
-        if (lane == 0 && i + 2 < cnt) issueB(i + 2);
-#endif
     }
 }
 

@@ -257,8 +257,8 @@ int batch_alloc(orbx_batch* b) {
     for (int l = 0; l < g.nlevels; ++l) {
         const LevelGeom& L = g.lv[l];
         const size_t blockOff = (size_t)L.planeOff - (size_t)kMarginY * L.pitch - kMarginX;  // first byte of this level's block
-        if (tma_encode_3d(&b->descMaps.ic[l], B.pyr + blockOff, L.pitch, L.h + 2 * kMarginY, n, L.planeBytes, 48, kDescARows) ||
-            tma_encode_3d(&b->descMaps.bl[l], B.blur + blockOff, L.pitch, L.h + 2 * kMarginY, n, L.planeBytes, kDescWindowRow, kDescBRows))
+        if (tma_encode_3d(&b->descMaps.ic[l], B.pyr + blockOff, L.pitch, L.h + 2 * kMarginY, n, L.planeBytes, 48, 31) ||
+            tma_encode_3d(&b->descMaps.bl[l], B.blur + blockOff, L.pitch, L.h + 2 * kMarginY, n, L.planeBytes, kDescWindowRow, 37))
             return fail(ORBX_ERR_CUDA, "cuTensorMapEncodeTiled failed");
     }
     {

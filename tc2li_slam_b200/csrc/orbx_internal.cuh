@@ -121,14 +121,7 @@ void launch_assemble(const Geom& g, const Buffers& b, int nImages, cudaStream_t 
 #define DESC_WINDOW_ROW 80
 #endif
 constexpr int kDescWindowRow = DESC_WINDOW_ROW;  // bytes per row of the staged rBRIEF window (TMA box width, multiple of 16, >= 52)
-#ifndef DESC_A_ROWS
-#define DESC_A_ROWS 31
-#endif
-#ifndef DESC_B_ROWS
-#define DESC_B_ROWS 37
-#endif
-constexpr int kDescARows = DESC_A_ROWS, kDescBRows = DESC_B_ROWS;  // (timing experiments only: fewer rows give wrong results)
-struct DescMaps {  // per level: 48x31 boxes of the pyramid (IC_Angle patch), 64x37 boxes of the blurred pyramid (rBRIEF window)
+struct DescMaps {  // per level: 48x31 boxes of the pyramid (IC_Angle patch), kDescWindowRow x 37 boxes of the blurred pyramid (rBRIEF window)
     CUtensorMap ic[ORBX_MAX_LEVELS];
     CUtensorMap bl[ORBX_MAX_LEVELS];
 };
