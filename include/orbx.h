@@ -189,6 +189,26 @@ int orbx_batch_download_stereo(orbx_batch* b, int n_frames, float* uright, float
  * orbx_batch_download_lapping: knn / ratio_ok [n_frames][K]; row f holds the N_left - mono_left queries of frame f; synchronises. */
 int orbx_batch_lapping_match(orbx_batch* b, int n_frames);
 int orbx_batch_download_lapping(orbx_batch* b, int n_frames, orbx_knn2* knn, uint8_t* ratio_ok);
+/* The feature grid of a Frame on the resident keypoints (after orbx_batch_run): Frame::AssignFeaturesToGrid + Frame::PosInGrid
+ * (Frame.cc:412-443, 751-762) for the single-grid case (Nleft == -1; rectified input, so mvKeysUn == mvKeys, Frame.cc:777-782).
+ * Bounds = Frame::mnMinX / mnMaxX / mnMinY / mnMaxY (Frame::ComputeImageBounds, Frame.cc:812-839: 0, cols, 0, rows without
+ * distortion); the cell sizes follow Frame.cc:179-180.  Frame::mGrid[i][j] comes back as CSR: cell c = i * ORBX_GRID_ROWS + j
+ * holds items[cell_start[c] .. cell_start[c + 1]) = keypoint indices in the reference's push_back order.  Asynchronous.
+ * orbx_batch_download_grid: cell_start [n_images][ORBX_GRID_CELLS + 1], items [n_images][K]; either may be NULL; synchronises. */
+#define ORBX_GRID_COLS 64 /* FRAME_GRID_COLS, Frame.h:60 */
+#define ORBX_GRID_ROWS 48 /* FRAME_GRID_ROWS, Frame.h:59 */
+#define ORBX_GRID_CELLS (ORBX_GRID_COLS * ORBX_GRID_ROWS)
+int orbx_batch_assign_grid(orbx_batch* b, int n_images, float min_x, float max_x, float min_y, float max_y);
+int orbx_batch_download_grid(orbx_batch* b, int n_images, int* cell_start, int* items);
+/* Frame::GetFeaturesInArea(x, y, r, minLevel, maxLevel) (Frame.cc:687-749) for n_queries windows against the grids of
+ * orbx_batch_assign_grid (host arrays in, host arrays out; synchronises): counts[q] = the size of the vector the reference returns,
+ * indices[q * capacity ..] = its first min(counts[q], capacity) entries in the reference's order. */
+typedef struct orbx_area_query {
+    int image;
+    float x, y, r;
+    int min_level, max_level; /* the reference's defaults are -1, -1 */
+} orbx_area_query;
+int orbx_batch_features_in_area(orbx_batch* b, const orbx_area_query* queries, int n_queries, int capacity, int* counts, int* indices);
 int orbx_batch_sync(orbx_batch* b);
 /* the same on a sub-range [first, first+n) of the handle's images (lapping: n x 2 ints for that range): lets a caller keep
  * many frames resident and process them in groups small enough for the 126 MB L2 */

@@ -759,6 +759,70 @@ void lapping_knn_match(const uint8_t* dl, int nq, const uint8_t* dr, int nt, int
 // ---------------------------------------------------------------------------------------------
 // C API (ctypes) — used by tests/, smoke() and bench.py's CPU-baseline legs only.
 // ---------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------------------------------
+// Feature grid of a Frame (widening).  Restates Frame::PosInGrid (Frame.cc:751-762),
+// Frame::AssignFeaturesToGrid (Frame.cc:412-443) for the single-grid case (Nleft == -1, mvKeysUn == mvKeys: rectified input,
+// zero distortion, Frame::UndistortKeyPoints returns the keys unchanged) and Frame::GetFeaturesInArea (Frame.cc:687-749).
+// mGrid[i][j] (FRAME_GRID_COLS = 64 columns, FRAME_GRID_ROWS = 48 rows, Frame.h:59-60) is laid out as CSR: cell c = i * 48 + j
+// holds items[cellStart[c] .. cellStart[c + 1]) = the keypoint indices in push_back order (ascending).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int GRID_COLS = 64, GRID_ROWS = 48;
+
+static inline bool pos_in_grid(float x, float y, float minX, float minY, float invW, float invH, int& px, int& py) {
+    px = (int)std::round((x - minX) * invW);  // round half away from zero, as ::round / std::round do (Frame.cc:753-754)
+    py = (int)std::round((y - minY) * invH);
+    return !(px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS);
+}
+
+void assign_features_to_grid(const KeyPoint* kps, int n, float minX, float maxX, float minY, float maxY, int* cellStart, int* items) {
+    const float invW = (float)GRID_COLS / (maxX - minX), invH = (float)GRID_ROWS / (maxY - minY);  // Frame.cc:179-180
+    std::vector<std::vector<int>> grid(GRID_COLS * GRID_ROWS);
+    for (int i = 0; i < n; ++i) {
+        int px, py;
+        if (pos_in_grid(kps[i].x, kps[i].y, minX, minY, invW, invH, px, py)) grid[px * GRID_ROWS + py].push_back(i);
+    }
+    int pos = 0;
+    for (int c = 0; c < GRID_COLS * GRID_ROWS; ++c) {
+        cellStart[c] = pos;
+        for (int i : grid[c]) items[pos++] = i;
+    }
+    cellStart[GRID_COLS * GRID_ROWS] = pos;
+}
+
+// returns the number of indices the reference would return; the first min(count, cap) are written to out, in the reference's order
+int features_in_area(const KeyPoint* kps, const int* cellStart, const int* items, float minX, float maxX, float minY, float maxY, float x, float y, float r,
+                     int minLevel, int maxLevel, int* out, int cap) {
+    const float invW = (float)GRID_COLS / (maxX - minX), invH = (float)GRID_ROWS / (maxY - minY);
+    const int nMinCellX = std::max(0, (int)std::floor((x - minX - r) * invW));
+    if (nMinCellX >= GRID_COLS) return 0;
+    const int nMaxCellX = std::min(GRID_COLS - 1, (int)std::ceil((x - minX + r) * invW));
+    if (nMaxCellX < 0) return 0;
+    const int nMinCellY = std::max(0, (int)std::floor((y - minY - r) * invH));
+    if (nMinCellY >= GRID_ROWS) return 0;
+    const int nMaxCellY = std::min(GRID_ROWS - 1, (int)std::ceil((y - minY + r) * invH));
+    if (nMaxCellY < 0) return 0;
+    const bool checkLevels = minLevel > 0 || maxLevel >= 0;
+    int n = 0;
+    for (int ix = nMinCellX; ix <= nMaxCellX; ++ix)
+        for (int iy = nMinCellY; iy <= nMaxCellY; ++iy) {
+            const int c = ix * GRID_ROWS + iy;
+            for (int j = cellStart[c]; j < cellStart[c + 1]; ++j) {
+                const KeyPoint& kp = kps[items[j]];
+                if (checkLevels) {
+                    if (kp.octave < minLevel) continue;
+                    if (maxLevel >= 0 && kp.octave > maxLevel) continue;
+                }
+                const float dx = kp.x - x, dy = kp.y - y;
+                if (std::fabs(dx) < r && std::fabs(dy) < r) {
+                    if (n < cap) out[n] = items[j];
+                    ++n;
+                }
+            }
+        }
+    return n;
+}
+
+
 extern "C" {
 void* orbo_create(int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh) {
     return new Extractor(nfeatures, scaleFactor, nlevels, iniTh, minTh);
@@ -806,6 +870,13 @@ int orbo_stereo_match(void* hl, void* hr, float mb, float mbf, float* uright, fl
     stereo_match(*(Extractor*)hl, *(Extractor*)hr, mb, mbf, u, d);
     if (!u.empty()) { std::memcpy(uright, u.data(), u.size() * 4); std::memcpy(depth, d.data(), d.size() * 4); }
     return (int)u.size();
+}
+void orbo_assign_grid(const void* kps, int n, float minX, float maxX, float minY, float maxY, int* cellStart, int* items) {
+    assign_features_to_grid((const KeyPoint*)kps, n, minX, maxX, minY, maxY, cellStart, items);
+}
+int orbo_features_in_area(const void* kps, const int* cellStart, const int* items, float minX, float maxX, float minY, float maxY, float x, float y, float r,
+                          int minLevel, int maxLevel, int* out, int cap) {
+    return features_in_area((const KeyPoint*)kps, cellStart, items, minX, maxX, minY, maxY, x, y, r, minLevel, maxLevel, out, cap);
 }
 void orbo_lapping_match(const uint8_t* dl, int nq, const uint8_t* dr, int nt, int* out, uint8_t* ok) { lapping_knn_match(dl, nq, dr, nt, out, ok); }
 void orbo_cvt_gray(const uint8_t* src, int w, int h, int sstride, int channels, int rgb, uint8_t* dst, int dstride) {

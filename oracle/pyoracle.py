@@ -48,6 +48,8 @@ def lib():
         L.orbo_num_selected.argtypes = [C.c_void_p, C.c_int]
         L.orbo_get_selected.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.orbo_stereo_match.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+        L.orbo_assign_grid.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+        L.orbo_features_in_area.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_float] * 7 + [C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.orbo_lapping_match.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.orbo_cvt_gray.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.orbo_remap.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
@@ -156,6 +158,29 @@ def lapping_match(desc_left, desc_right):
     ok = np.empty(len(dl), np.uint8)
     lib().orbo_lapping_match(_p(dl), len(dl), _p(dr), len(dr), _p(out), _p(ok))
     return out, ok
+
+
+GRID_COLS, GRID_ROWS = 64, 48  # FRAME_GRID_COLS / FRAME_GRID_ROWS (Frame.h:59-60)
+
+
+def assign_grid(kps, bounds):
+    """Frame::AssignFeaturesToGrid (Frame.cc:412-443) for the single-grid, zero-distortion case as CSR: (cell_start int32 [3073],
+    items int32 [n_assigned]); cell c = column * 48 + row.  bounds = (mnMinX, mnMaxX, mnMinY, mnMaxY) (Frame::ComputeImageBounds)."""
+    kps = np.ascontiguousarray(kps)
+    start = np.empty(GRID_COLS * GRID_ROWS + 1, np.int32)
+    items = np.empty(max(len(kps), 1), np.int32)
+    lib().orbo_assign_grid(_p(kps), len(kps), *[float(v) for v in bounds], _p(start), _p(items))
+    return start, items[:start[-1]]
+
+
+def features_in_area(kps, grid, bounds, x, y, r, min_level=-1, max_level=-1):
+    """Frame::GetFeaturesInArea (Frame.cc:687-749): keypoint indices in the reference's order."""
+    kps = np.ascontiguousarray(kps)
+    start, items = np.ascontiguousarray(grid[0], np.int32), np.ascontiguousarray(grid[1], np.int32)
+    out = np.empty(max(len(kps), 1), np.int32)
+    n = lib().orbo_features_in_area(_p(kps), _p(start), _p(items), *[float(v) for v in bounds], float(x), float(y), float(r), int(min_level), int(max_level),
+                                    _p(out), len(out))
+    return out[:n]
 
 
 class OracleExtractor:

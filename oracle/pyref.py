@@ -119,3 +119,44 @@ def stereo_match(kps_l, desc_l, kps_r, desc_r, pyr_l, pyr_r, scale_factors, inv_
     u, d = np.empty(len(kl), np.float32), np.empty(len(kl), np.float32)
     _slib.refs_stereo_match(_p(kl), len(kl), _p(dl), _p(kr), len(kr), _p(dr), nl, ptr_l, ptr_r, _p(w), _p(h), _p(sf), _p(isf), float(mb), float(mbf), _p(u), _p(d))
     return u, d
+
+
+_LIB_GRID = os.path.join(_HERE, "_ref", "libref_grid.so")
+_glib = None
+
+
+def grid_available():
+    return os.path.exists(_LIB_GRID)
+
+
+class RefFrameGrid:
+    """The reference's own Frame::AssignFeaturesToGrid / PosInGrid / GetFeaturesInArea (Frame.cc:412-443, 687-762, built by
+    oracle/tools/gen_ref_grid.py) on explicit keypoints; single-grid case (Nleft == -1, zero distortion)."""
+
+    def __init__(self, kps, bounds):
+        global _glib
+        if _glib is None:
+            _glib = C.CDLL(_LIB_GRID)
+            _glib.refg_create.restype = C.c_void_p
+            _glib.refg_create.argtypes = [C.c_void_p, C.c_int] + [C.c_float] * 4
+            _glib.refg_destroy.argtypes = [C.c_void_p]
+            _glib.refg_grid.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+            _glib.refg_features_in_area.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        self._kps = np.ascontiguousarray(kps)
+        self._h = _glib.refg_create(_p(self._kps), len(self._kps), *[float(v) for v in bounds])
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            _glib.refg_destroy(self._h)
+            self._h = None
+
+    def grid(self):
+        start = np.empty(64 * 48 + 1, np.int32)
+        items = np.empty(max(len(self._kps), 1), np.int32)
+        _glib.refg_grid(self._h, _p(start), _p(items))
+        return start, items[:start[-1]]
+
+    def features_in_area(self, x, y, r, min_level=-1, max_level=-1):
+        out = np.empty(max(len(self._kps), 1), np.int32)
+        n = _glib.refg_features_in_area(self._h, float(x), float(y), float(r), int(min_level), int(max_level), _p(out), len(out))
+        return out[:n]

@@ -1,0 +1,151 @@
+// grid_kernel.cu — the feature grid of a Frame on the device (widening).
+//
+//   k_assign_grid      : Frame::AssignFeaturesToGrid (Frame.cc:412-443) + Frame::PosInGrid (Frame.cc:751-762) for the single-grid
+//                        case (Nleft == -1) on the keypoints the extractor just produced; with rectified input (zero
+//                        distortion) Frame::UndistortKeyPoints leaves mvKeysUn == mvKeys (Frame.cc:777-782).  mGrid[i][j]
+//                        (FRAME_GRID_COLS = 64 x FRAME_GRID_ROWS = 48 vectors, Frame.h:59-60, 278) becomes CSR: cell c = i * 48 + j
+//                        holds items[start[c] .. start[c + 1]) = keypoint indices in push_back order (ascending).
+//                        One CTA per image: shared-memory histogram, block scan, scatter through shared cursors, then every
+//                        cell list (0.65 entries on average) is put in ascending order by the thread that owns the cell.
+//   k_features_in_area : Frame::GetFeaturesInArea (Frame.cc:687-749), one warp per query.  The cells of one grid column that a
+//                        query touches are adjacent in the CSR, so the reference's (ix, iy, in-cell) visiting order is one
+//                        contiguous scan per column; hits are appended in order with ballot prefixes.
+// Float expressions follow the reference operation by operation (sub, sub/add, mul in float32; round half away from zero;
+// floor / ceil; strict |d| < r); no FMA contraction (--fmad=false) — although none of them has a multiply-add shape.
+#include <algorithm>
+
+#include "orbx_internal.cuh"
+
+namespace orbx {
+
+namespace {
+
+constexpr int GC = ORBX_GRID_COLS, GR = ORBX_GRID_ROWS, NC = GC * GR;
+constexpr int GT = 256;             // threads per CTA of k_assign_grid
+constexpr int CPT = NC / GT;        // cells per thread (12)
+static_assert(NC % GT == 0, "cells per thread");
+
+__device__ __forceinline__ int cell_of(float x, float y, const GridParams& p) {
+    const int px = (int)roundf(__fmul_rn(__fsub_rn(x, p.minX), p.invW));
+    const int py = (int)roundf(__fmul_rn(__fsub_rn(y, p.minY), p.invH));
+    return (px < 0 || px >= GC || py < 0 || py >= GR) ? -1 : px * GR + py;
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(GT) k_assign_grid(const Buffers b, int K, GridParams p) {
+    extern __shared__ int items[];       // [K]
+    __shared__ int cnt[NC];              // histogram, then the running cursor of every cell
+    __shared__ int start[NC + 1];
+    __shared__ int warpSum[GT / 32];
+    const int img = b.imgBase + blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n = b.outCount[img];
+    const orbx_keypoint* kps = b.kps + (size_t)img * K;
+    for (int c = tid; c < NC; c += GT) cnt[c] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += GT) {
+        const int c = cell_of(kps[i].x, kps[i].y, p);
+        if (c >= 0) atomicAdd(&cnt[c], 1);
+    }
+    __syncthreads();
+    // exclusive scan over the cells: thread t owns cells [t * CPT, (t + 1) * CPT)
+    int local[CPT], sum = 0;
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) { local[k] = sum; sum += cnt[tid * CPT + k]; }
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) warpSum[wid] = incl;
+    __syncthreads();
+    int base = incl - sum;
+    for (int w = 0; w < wid; ++w) base += warpSum[w];
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) start[tid * CPT + k] = base + local[k];
+    if (tid == GT - 1) start[NC] = base + sum;
+    __syncthreads();
+    for (int c = tid; c < NC; c += GT) cnt[c] = start[c];
+    __syncthreads();
+    for (int i = tid; i < n; i += GT) {
+        const int c = cell_of(kps[i].x, kps[i].y, p);
+        if (c >= 0) items[atomicAdd(&cnt[c], 1)] = i;
+    }
+    __syncthreads();
+    // push_back order = ascending keypoint index: insertion sort of every (short) cell list by its owner
+    for (int k = 0; k < CPT; ++k) {
+        const int c = tid * CPT + k, s = start[c], e = start[c + 1];
+        for (int a = s + 1; a < e; ++a) {
+            const int v = items[a];
+            int q = a - 1;
+            while (q >= s && items[q] > v) { items[q + 1] = items[q]; --q; }
+            items[q + 1] = v;
+        }
+    }
+    __syncthreads();
+    int* gs = b.gridStart + (size_t)img * (NC + 1);
+    int* gi = b.gridItems + (size_t)img * K;
+    for (int c = tid; c <= NC; c += GT) gs[c] = start[c];
+    const int total = start[NC];
+    for (int i = tid; i < total; i += GT) gi[i] = items[i];
+}
+
+// queries: {image, x, y, r, minLevel, maxLevel}; out: [nQueries][cap] indices, counts[nQueries] = what the reference would return
+__global__ void __launch_bounds__(128) k_features_in_area(const Buffers b, int K, GridParams p, const orbx_area_query* __restrict__ queries, int nQueries, int cap,
+                                                         int* __restrict__ counts, int* __restrict__ out) {
+    const int q = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (q >= nQueries) return;
+    const orbx_area_query Q = queries[q];
+    const float x = Q.x, y = Q.y, r = Q.r;
+    int n = 0;
+    // (x - mnMinX - factorX) * mfGridElementWidthInv etc. (Frame.cc:695-717), left to right in float32
+    const int minCX = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, p.minX), r), p.invW)));
+    const int maxCX = min(GC - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, p.minX), r), p.invW)));
+    const int minCY = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, p.minY), r), p.invH)));
+    const int maxCY = min(GR - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, p.minY), r), p.invH)));
+    if (!(minCX >= GC || maxCX < 0 || minCY >= GR || maxCY < 0)) {
+        const bool checkLevels = Q.min_level > 0 || Q.max_level >= 0;
+        const int* gs = b.gridStart + (size_t)Q.image * (NC + 1);
+        const int* gi = b.gridItems + (size_t)Q.image * K;
+        const orbx_keypoint* kps = b.kps + (size_t)Q.image * K;
+        int* o = out + (size_t)q * cap;
+        for (int ix = minCX; ix <= maxCX; ++ix) {
+            const int s = gs[ix * GR + minCY], e = gs[ix * GR + maxCY + 1];
+            for (int j0 = s; j0 < e; j0 += 32) {
+                const int j = j0 + lane;
+                bool hit = false;
+                int idx = 0;
+                if (j < e) {
+                    idx = gi[j];
+                    const orbx_keypoint kp = kps[idx];
+                    bool lv = true;
+                    if (checkLevels) lv = !(kp.octave < Q.min_level) && !(Q.max_level >= 0 && kp.octave > Q.max_level);
+                    hit = lv && fabsf(__fsub_rn(kp.x, x)) < r && fabsf(__fsub_rn(kp.y, y)) < r;
+                }
+                const unsigned bal = __ballot_sync(0xFFFFFFFFu, hit);
+                const int pos = n + __popc(bal & ((1u << lane) - 1));
+                if (hit && pos < cap) o[pos] = idx;
+                n += __popc(bal);
+            }
+        }
+    }
+    if (lane == 0) counts[q] = n;
+}
+
+size_t grid_smem_bytes(int K) { return (size_t)K * sizeof(int); }
+
+cudaError_t grid_configure(int K) {
+    return cudaFuncSetAttribute(k_assign_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(grid_smem_bytes(K), 1024));
+}
+
+void launch_assign_grid(const Buffers& b, int K, const GridParams& p, int nImages, cudaStream_t s) {
+    k_assign_grid<<<nImages, GT, grid_smem_bytes(K), s>>>(b, K, p);
+}
+
+void launch_features_in_area(const Buffers& b, int K, const GridParams& p, const orbx_area_query* queries, int nQueries, int cap, int* counts, int* out,
+                             cudaStream_t s) {
+    k_features_in_area<<<(nQueries + 3) / 4, 128, 0, s>>>(b, K, p, queries, nQueries, cap, counts, out);
+}
+
+}  // namespace orbx

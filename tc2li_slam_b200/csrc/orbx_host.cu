@@ -121,12 +121,18 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 struct orbx_batch {
     Params p;
     Geom g;
-    Buffers buf;
+    Buffers buf = {};
     int device = 0, width = 0, height = 0, maxImages = 0;
     int taps[7] = {18, 34, 48, 56, 48, 34, 18};
     cudaStream_t own = nullptr, stream = nullptr;
     cudaStream_t side = nullptr;        // blur runs here, concurrently with FAST + quadtree (both only need the pyramid)
     cudaEvent_t evPyr = nullptr, evBlur = nullptr;
+    int sched = 0;
+    // feature grid (orbx_batch_assign_grid): buffers are allocated on first use
+    GridParams gridParams = {0.f, 0.f, 0.f, 0.f};
+    int gridImages = 0;                 // images the grids were last built for (0 = never)
+    orbx_area_query* qDev = nullptr; int* qCounts = nullptr; int* qOut = nullptr;
+    size_t qCap = 0, qOutCap = 0;
     // extra lanes for orbx_batch_run_pipelined: chunks of a resident batch are issued round-robin over the lanes so that the
     // latency-bound stages of one chunk (quadtree) overlap the issue-bound stages of another (FAST)
     static const int kLanes = 3;
@@ -345,7 +351,14 @@ int orbx_batch_create(int nfeatures, float scale_factor, int nlevels, int ini_th
     auto bail = [&](int code) { orbx_batch_destroy(b); return code; };
     if ((e = cudaStreamCreateWithFlags(&b->own, cudaStreamNonBlocking)) != cudaSuccess) return bail(cuda_fail(e, "cudaStreamCreate"));
     b->stream = b->own;
-    if ((e = cudaStreamCreateWithFlags(&b->side, cudaStreamNonBlocking)) != cudaSuccess) return bail(cuda_fail(e, "cudaStreamCreate"));
+    {
+        const char* sv = std::getenv("ORBX_SCHED");  // experiment hook (profiles/tools): how the blur is scheduled against FAST -> quadtree
+        b->sched = sv ? std::atoi(sv) : 0;
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        const int prio = b->sched == 3 ? hi : b->sched == 4 ? lo : 0;
+        if ((e = cudaStreamCreateWithPriority(&b->side, cudaStreamNonBlocking, prio)) != cudaSuccess) return bail(cuda_fail(e, "cudaStreamCreate"));
+    }
     if ((e = cudaEventCreateWithFlags(&b->evPyr, cudaEventDisableTiming)) != cudaSuccess) return bail(cuda_fail(e, "cudaEventCreate"));
     if ((e = cudaEventCreateWithFlags(&b->evBlur, cudaEventDisableTiming)) != cudaSuccess) return bail(cuda_fail(e, "cudaEventCreate"));
     if ((e = cudaEventCreateWithFlags(&b->evFork, cudaEventDisableTiming)) != cudaSuccess) return bail(cuda_fail(e, "cudaEventCreate"));
@@ -374,6 +387,9 @@ void orbx_batch_destroy(orbx_batch* b) {
     DeviceGuard dg(b->device);
     if (b->own) cudaStreamSynchronize(b->own);
     for (void* p : b->allocs) cudaFree(p);
+    if (b->qDev) cudaFree(b->qDev);
+    if (b->qCounts) cudaFree(b->qCounts);
+    if (b->qOut) cudaFree(b->qOut);
     if (b->borderScratch) cudaFree(b->borderScratch);
     if (b->stageIn) cudaFree(b->stageIn);
     for (auto& ev : b->ev) if (ev) cudaEventDestroy(ev);
@@ -608,13 +624,23 @@ static int run_range_lane(orbx_batch* b, int first, int n, const int* lapping, i
     // FAST -> quadtree and the blur both depend only on the pyramid: the blur goes to the side stream unless per-stage
     // timing was requested (then everything is serialised on one stream so that the events bracket single stages)
     const bool overlap = !b->timing || lane != 0;
-    if (overlap) {
+    auto blur_on_side = [&]() -> int {
         CU(cudaEventRecord(evPyr, s));
         CU(cudaStreamWaitEvent(side, evPyr, 0));
         for (int l = 0; l < g.nlevels; ++l) { launch_blur(g, buf, b->blurMaps, l, n, b->taps, side); ++launches; }
         CU(cudaEventRecord(evBlur, side));
-    }
+        return ORBX_OK;
+    };
+    const bool blurFirst = b->sched == 0 || b->sched == 3 || b->sched == 4;
+    if (overlap && blurFirst) { int r = blur_on_side(); if (r) return r; }
+    if (overlap && b->sched == 1) CU(cudaEventRecord(evPyr, s));
     launch_fast(g, buf, b->fastMaps, n, b->fastTileRows, b->fastTs, b->numSMs, s); ++launches;
+    if (overlap && b->sched == 1) {  // the blur is enqueued after FAST but still only waits for the pyramid
+        CU(cudaStreamWaitEvent(side, evPyr, 0));
+        for (int l = 0; l < g.nlevels; ++l) { launch_blur(g, buf, b->blurMaps, l, n, b->taps, side); ++launches; }
+        CU(cudaEventRecord(evBlur, side));
+    }
+    if (overlap && b->sched == 2) { int r = blur_on_side(); if (r) return r; }  // the blur waits for FAST: it runs beside the quadtree only
     mark();
     if (!overlap)
         for (int l = 0; l < g.nlevels; ++l) { launch_blur(g, buf, b->blurMaps, l, n, b->taps, s); ++launches; }
@@ -703,6 +729,78 @@ int orbx_batch_download_stereo(orbx_batch* b, int n_frames, float* uright, float
 }
 
 
+
+// Frame::AssignFeaturesToGrid (Frame.cc:412-443) for images [0, n_images) on the resident keypoints; asynchronous on the handle's stream
+int orbx_batch_assign_grid(orbx_batch* b, int n_images, float min_x, float max_x, float min_y, float max_y) {
+    int r = check_images(b, 0, n_images);
+    if (r) return r;
+    if (!(max_x > min_x) || !(max_y > min_y)) return fail(ORBX_ERR_ARG, "grid bounds must satisfy max > min");
+    DeviceGuard dg(b->device);
+    if (!b->buf.gridStart) {
+        if (grid_smem_bytes(b->g.K) > 180 * 1024) return fail(ORBX_ERR_TOO_LARGE, "keypoint capacity too large for the grid kernel's shared memory");
+        if ((r = dev_alloc(b, &b->buf.gridStart, (size_t)b->maxImages * (ORBX_GRID_CELLS + 1)))) return r;
+        if ((r = dev_alloc(b, &b->buf.gridItems, (size_t)b->maxImages * b->g.K))) return r;
+        CU(grid_configure(b->g.K));
+    }
+    // mfGridElementWidthInv / HeightInv exactly as the Frame constructors compute them (Frame.cc:179-180): float / (float - float)
+    b->gridParams.minX = min_x; b->gridParams.minY = min_y;
+    b->gridParams.invW = static_cast<float>(ORBX_GRID_COLS) / (max_x - min_x);
+    b->gridParams.invH = static_cast<float>(ORBX_GRID_ROWS) / (max_y - min_y);
+    b->gridImages = n_images;
+    if (n_images == 0) return ORBX_OK;
+    Buffers buf = b->buf;
+    buf.imgBase = 0;
+    launch_assign_grid(buf, b->g.K, b->gridParams, n_images, b->stream);
+    CU(cudaGetLastError());
+    return ORBX_OK;
+}
+
+int orbx_batch_download_grid(orbx_batch* b, int n_images, int* cell_start, int* items) {
+    int r = check_images(b, 0, n_images);
+    if (r) return r;
+    if (n_images > b->gridImages) return fail(ORBX_ERR_ARG, "orbx_batch_assign_grid has not been run for these images");
+    DeviceGuard dg(b->device);
+    if (n_images) {
+        if (cell_start) CU(cudaMemcpyAsync(cell_start, b->buf.gridStart, (size_t)n_images * (ORBX_GRID_CELLS + 1) * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+        if (items) CU(cudaMemcpyAsync(items, b->buf.gridItems, (size_t)n_images * b->g.K * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+    }
+    CU(cudaStreamSynchronize(b->stream));
+    return ORBX_OK;
+}
+
+// Frame::GetFeaturesInArea (Frame.cc:687-749), batched: one warp per query
+int orbx_batch_features_in_area(orbx_batch* b, const orbx_area_query* queries, int n_queries, int capacity, int* counts, int* indices) {
+    if (!b) return fail(ORBX_ERR_ARG, "null handle");
+    if (n_queries < 0 || capacity < 0 || (n_queries && (!queries || !counts)) || (n_queries && capacity && !indices)) return fail(ORBX_ERR_ARG, "bad query arguments");
+    if (n_queries == 0) return ORBX_OK;
+    for (int q = 0; q < n_queries; ++q)
+        if (queries[q].image < 0 || queries[q].image >= b->gridImages) return fail(ORBX_ERR_ARG, "query refers to an image without a grid (run orbx_batch_assign_grid first)");
+    DeviceGuard dg(b->device);
+    const size_t outElems = std::max<size_t>((size_t)n_queries * (size_t)capacity, 1);
+    if ((size_t)n_queries > b->qCap) {
+        if (b->qDev) cudaFree(b->qDev);
+        if (b->qCounts) cudaFree(b->qCounts);
+        b->qDev = nullptr; b->qCounts = nullptr; b->qCap = 0;
+        CU(cudaMalloc(&b->qDev, (size_t)n_queries * sizeof(orbx_area_query)));
+        CU(cudaMalloc(&b->qCounts, (size_t)n_queries * sizeof(int)));
+        b->qCap = (size_t)n_queries;
+    }
+    if (outElems > b->qOutCap) {
+        if (b->qOut) cudaFree(b->qOut);
+        b->qOut = nullptr; b->qOutCap = 0;
+        CU(cudaMalloc(&b->qOut, outElems * sizeof(int)));
+        b->qOutCap = outElems;
+    }
+    CU(cudaMemcpyAsync(b->qDev, queries, (size_t)n_queries * sizeof(orbx_area_query), cudaMemcpyHostToDevice, b->stream));
+    Buffers buf = b->buf;
+    buf.imgBase = 0;
+    launch_features_in_area(buf, b->g.K, b->gridParams, b->qDev, n_queries, capacity, b->qCounts, b->qOut, b->stream);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(counts, b->qCounts, (size_t)n_queries * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+    if (capacity) CU(cudaMemcpyAsync(indices, b->qOut, (size_t)n_queries * capacity * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return ORBX_OK;
+}
 
 // Descriptor stage of Frame::ComputeStereoFishEyeMatches (Frame.cc:1162-1187) for frames [0, n_frames): kNN (k = 2) of the left
 // lapping tail against the right lapping tail + Lowe's gate.  Asynchronous, after orbx_batch_run of the same images.

@@ -91,6 +91,8 @@ struct Buffers {
     float* depth;           // [image][K] depth of the match, -1 = none (Frame::mvDepth)
     int4* lapKnn;           // [image][K] lapping-tail kNN of LEFT images: {trainIdx0, distance0, trainIdx1, distance1}, -1 = absent
     uint8_t* lapOk;         // [image][K] Lowe ratio gate of that pair (Frame.cc:1187)
+    int* gridStart;         // [image][64 * 48 + 1] CSR of Frame::mGrid (cell = column * 48 + row)
+    int* gridItems;         // [image][K] keypoint indices, cell by cell, ascending inside a cell
     int* errFlag;           // device-side error flag (capacity overflow etc.)
     const uint4* cellTab;   // [cellsPerImage] FAST cell descriptors (make_cell_table)
     int imgBase;            // first image of this launch set (kernels index images as imgBase + blockIdx)
@@ -143,6 +145,15 @@ void launch_stereo_match(const Geom& g, const Buffers& bl, const Buffers& br, in
 size_t lap_match_smem_bytes();
 cudaError_t lap_match_configure();
 void launch_lap_match(const Geom& g, const Buffers& bl, const Buffers& br, int nFrames, int lMul, int lAdd, int rMul, int rAdd, cudaStream_t s);
+
+struct GridParams {  // Frame::mnMinX / mnMinY and mfGridElementWidthInv / HeightInv (Frame.cc:179-180)
+    float minX, minY, invW, invH;
+};
+size_t grid_smem_bytes(int K);
+cudaError_t grid_configure(int K);
+void launch_assign_grid(const Buffers& b, int K, const GridParams& p, int nImages, cudaStream_t s);
+void launch_features_in_area(const Buffers& b, int K, const GridParams& p, const orbx_area_query* queries, int nQueries, int cap, int* counts, int* out,
+                             cudaStream_t s);
 
 // debug / test hooks
 void launch_debug_sincos(const float* anglesDeg, float* outSin, float* outCos, int n, cudaStream_t s);

@@ -88,6 +88,9 @@ def lib():
         "orbx_lapping_match": (i, [_vp, _vp, _vp, _vp, i, _vp, _vp]),
         "orbx_batch_lapping_match": (i, [_vp, i]),
         "orbx_batch_download_lapping": (i, [_vp, i, _vp, _vp]),
+        "orbx_batch_assign_grid": (i, [_vp, i, f, f, f, f]),
+        "orbx_batch_download_grid": (i, [_vp, i, _vp, _vp]),
+        "orbx_batch_features_in_area": (i, [_vp, _vp, i, i, _vp, _vp]),
         "orbx_batch_run_range": (i, [_vp, i, i, _vp]),
         "orbx_batch_run_pipelined": (i, [_vp, i, _vp, i]),
         "orbx_batch_download_async": (i, [_vp, i, i, _vp, _vp, _vp, _vp]),
@@ -447,6 +450,10 @@ class StereoORBextractor:
         self.right.close()
 
 
+GRID_COLS, GRID_ROWS = 64, 48  # ORBX_GRID_COLS / ORBX_GRID_ROWS = FRAME_GRID_COLS / FRAME_GRID_ROWS (Frame.h:59-60)
+AREA_QUERY_DTYPE = np.dtype([("image", "<i4"), ("x", "<f4"), ("y", "<f4"), ("r", "<f4"), ("min_level", "<i4"), ("max_level", "<i4")])  # orbx_area_query
+
+
 class BatchExtractor:
     """Many images of one shape per launch set (BASELINE.json configs[4]); frames x {left,right} are consecutive images."""
 
@@ -469,6 +476,9 @@ class BatchExtractor:
         self.nlevels = nlevels
         self.K = lib().orbx_batch_max_keypoints(self._h)
         self.max_images = lib().orbx_batch_max_images(self._h)
+        w, h = C.c_int(0), C.c_int(0)
+        lib().orbx_batch_get_level_size(self._h, 0, C.byref(w), C.byref(h))
+        self.width, self.height = w.value, h.value
         return self
 
     def close(self):
@@ -565,6 +575,28 @@ class BatchExtractor:
         knn, ok = np.empty((n_frames, self.K, 4), np.int32), np.empty((n_frames, self.K), np.uint8)
         _check(lib().orbx_batch_download_lapping(self._h, int(n_frames), _p(knn), _p(ok)))
         return knn, ok
+
+    def assign_grid(self, n_images, bounds=None):
+        """Batched Frame::AssignFeaturesToGrid (Frame.cc:412-443) on the resident keypoints (after run()); asynchronous.
+        bounds = (mnMinX, mnMaxX, mnMinY, mnMaxY); default: (0, width, 0, height) as Frame::ComputeImageBounds gives without distortion."""
+        if bounds is None:
+            bounds = (0.0, float(self.width), 0.0, float(self.height))
+        _check(lib().orbx_batch_assign_grid(self._h, int(n_images), *[float(v) for v in bounds]))
+
+    def download_grid(self, n_images):
+        """(cell_start int32 [n_images, 3073], items int32 [n_images, K]): Frame::mGrid[i][j] = items[cell_start[i * 48 + j] : cell_start[i * 48 + j + 1]]."""
+        start, items = np.empty((n_images, GRID_COLS * GRID_ROWS + 1), np.int32), np.empty((n_images, self.K), np.int32)
+        _check(lib().orbx_batch_download_grid(self._h, int(n_images), _p(start), _p(items)))
+        return start, items
+
+    def features_in_area(self, queries, capacity=256):
+        """Batched Frame::GetFeaturesInArea (Frame.cc:687-749).  queries: AREA_QUERY_DTYPE records (image, x, y, r, min_level, max_level)
+        or an iterable of such tuples; returns (counts int32 [nq], indices int32 [nq, capacity]) — row q holds the first
+        min(counts[q], capacity) indices in the reference's order."""
+        q = np.ascontiguousarray(np.asarray(queries, dtype=AREA_QUERY_DTYPE))
+        counts, idx = np.empty(len(q), np.int32), np.empty((len(q), int(capacity)), np.int32)
+        _check(lib().orbx_batch_features_in_area(self._h, _p(q), len(q), int(capacity), _p(counts), _p(idx)))
+        return counts, idx
 
     def sync(self):
         _check(lib().orbx_batch_sync(self._h))

@@ -93,3 +93,52 @@ def test_stereo_match_restatement_equals_reference_function(w, h, seed, args, mb
                                 t["scale_factors"], t["inv_scale_factors"], mb, mbf)
     assert (ou >= 0).sum() > 50
     assert np.array_equal(ou.view(np.uint32), ru.view(np.uint32)) and np.array_equal(od.view(np.uint32), rd.view(np.uint32))
+
+
+# ---- the feature grid (Frame::AssignFeaturesToGrid / GetFeaturesInArea) against the reference's own function bodies ----
+def _grid_keypoints(kind, seed):
+    rng = np.random.default_rng(seed)
+    if kind == "extracted":
+        _, k, _ = po.OracleExtractor(2000, 1.2, 8, 20, 7)(po.synth_v1(1241, 376, seed))
+        return k, (0.0, 1241.0, 0.0, 376.0)
+    n = 3000
+    k = np.zeros(n, po.KP_DTYPE)
+    if kind == "cell_edges":  # coordinates on and next to the .5 rounding boundaries of PosInGrid, and outside the image bounds
+        inv_w, inv_h = np.float32(64) / np.float32(1241), np.float32(48) / np.float32(376)
+        cx = (rng.integers(-2, 67, n).astype(np.float32) + np.float32(0.5)) / inv_w
+        cy = (rng.integers(-2, 51, n).astype(np.float32) + np.float32(0.5)) / inv_h
+        k["x"] = np.nextafter(cx, cx + rng.choice([-1, 0, 1], n).astype(np.float32) * 10).astype(np.float32)
+        k["y"] = np.nextafter(cy, cy + rng.choice([-1, 0, 1], n).astype(np.float32) * 10).astype(np.float32)
+        bounds = (0.0, 1241.0, 0.0, 376.0)
+    else:  # "offset_bounds": undistorted-style bounds that do not start at 0, clustered points (long cell lists)
+        k["x"] = (rng.normal(300, 40, n)).astype(np.float32)
+        k["y"] = (rng.normal(200, 25, n)).astype(np.float32)
+        bounds = (-13.25, 765.5, -9.75, 489.125)
+    k["octave"] = rng.integers(0, 8, n)
+    k["size"] = 31
+    k["class_id"] = -1
+    return k, bounds
+
+
+@pytest.mark.skipif(not pyref.grid_available(), reason="oracle/_ref/libref_grid.so not built (needs /root/reference once)")
+@pytest.mark.parametrize("kind,seed", [("extracted", 0), ("extracted", 7), ("cell_edges", 1), ("cell_edges", 2), ("offset_bounds", 3)])
+def test_feature_grid_matches_reference_bodies(kind, seed):
+    k, bounds = _grid_keypoints(kind, seed)
+    ref = pyref.RefFrameGrid(k, bounds)
+    rs, ri = ref.grid()
+    os_, oi = po.assign_grid(k, bounds)
+    assert np.array_equal(rs, os_) and np.array_equal(ri, oi)
+    rng = np.random.default_rng(seed + 100)
+    for q in range(400):
+        if q % 4 == 0:  # around an existing keypoint, radius such that |dx| == r happens (strict compare)
+            j = rng.integers(0, len(k))
+            x, y = float(k["x"][j]) + float(rng.integers(-3, 4)), float(k["y"][j]) + float(rng.integers(-3, 4))
+            r = float(rng.integers(1, 40))
+        else:
+            x = float(rng.uniform(bounds[0] - 60, bounds[1] + 60))
+            y = float(rng.uniform(bounds[2] - 60, bounds[3] + 60))
+            r = float(rng.choice([0.5, 3, 7.5, 15, 40, 100, 2000]))
+        lv = [(-1, -1), (0, 0), (2, 5), (3, -1), (0, 7), (-1, 2)][q % 6]
+        a = ref.features_in_area(x, y, r, *lv)
+        b = po.features_in_area(k, (os_, oi), bounds, x, y, r, *lv)
+        assert np.array_equal(a, b), (q, x, y, r, lv)
