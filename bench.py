@@ -345,6 +345,32 @@ def main():
         stereo = {"what": "orbx_batch_stereo_match (Frame::ComputeStereoMatches, Frame.cc:841-1011) on the resident keypoints/descriptors/pyramids",
                   "ms_per_step": ms_st, "frames_per_s": args.pairs / (ms_st * 1e-3), "matched_fraction_first_64": float((u >= 0).sum()) / float(max(1, (counts[:2 * min(args.pairs, 64):2]).sum()))}
 
+    # ---- supplementary: the feature grid every Frame constructor builds next (Frame::AssignFeaturesToGrid) + area queries ----
+    grid = None
+    if not args.no_stereo:
+        big.assign_grid(n_img)
+        big.sync()
+        s0, s1 = Event(), Event()
+        s0.record(big)
+        for _ in range(args.steps):
+            big.assign_grid(n_img)
+        s1.record(big)
+        ms_grid = s0.elapsed_ms(s1) / args.steps
+        nq = 1 << 16  # one 15-px window per query, spread over the first 64 images (a projection search issues ~1-2 k per frame)
+        rng = np.random.default_rng(11)
+        q = np.zeros(nq, T.AREA_QUERY_DTYPE)
+        q["image"] = rng.integers(0, min(n_img, 64), nq)
+        q["x"], q["y"], q["r"] = rng.uniform(0, W, nq), rng.uniform(0, H, nq), 15.0
+        q["min_level"], q["max_level"] = -1, -1
+        big.features_in_area(q, 64)
+        t0 = time.perf_counter()
+        qc, _ = big.features_in_area(q, 64)
+        dt_q = time.perf_counter() - t0
+        grid = {"what": "orbx_batch_assign_grid (Frame::AssignFeaturesToGrid, Frame.cc:412-443) on the resident keypoints; orbx_batch_features_in_area "
+                        "(Frame::GetFeaturesInArea, Frame.cc:687-749) host queries in, host index lists out",
+                "assign_ms_per_step": ms_grid, "assign_images_per_s": n_img / (ms_grid * 1e-3), "area_queries": nq,
+                "area_queries_per_s_host_to_host": nq / dt_q, "mean_hits_per_query": float(qc.mean())}
+
     # ---- e2e: pinned host images in, keypoints/descriptors out, three pipelined handles ----
     e2e = None
     pinned_in = None
@@ -493,7 +519,7 @@ def main():
             "config": {"workload": WORKLOAD,
                        "pairs_per_gpu_per_step": args.pairs, "images_per_launch_set": group, "keypoints_per_image": kp_mean,
                        "l2": f"inputs {n_img * W * H / 1e9:.2f} GB per rank, larger than the {L2_BYTES / 1e6:.0f} MB L2; no flush needed"},
-            "clocks": clocks, "numa_binding": numa, "e2e": e2e, "gpu_launches": launches_per_step, "roofline": roofline, "cpu_baseline": cpu, "stages": stages, "latency": latency, "stereo_match": stereo, "large_images": large, "euroc_lapping": euroc,
+            "clocks": clocks, "numa_binding": numa, "e2e": e2e, "gpu_launches": launches_per_step, "roofline": roofline, "cpu_baseline": cpu, "stages": stages, "latency": latency, "stereo_match": stereo, "feature_grid": grid, "large_images": large, "euroc_lapping": euroc,
         }
         emit_line(json.dumps(line))
     big.close()
