@@ -131,32 +131,37 @@ def grid_available():
 
 class RefFrameGrid:
     """The reference's own Frame::AssignFeaturesToGrid / PosInGrid / GetFeaturesInArea (Frame.cc:412-443, 687-762, built by
-    oracle/tools/gen_ref_grid.py) on explicit keypoints; single-grid case (Nleft == -1, zero distortion)."""
+    oracle/tools/gen_ref_grid.py) on explicit keypoints: the single-grid case (Nleft == -1, zero distortion) or, with kps_right, the
+    two-grid case of the fisheye stereo constructor (Nleft = len(kps), mGrid over mvKeys, mGridRight over mvKeysRight)."""
 
-    def __init__(self, kps, bounds):
+    def __init__(self, kps, bounds, kps_right=None):
         global _glib
         if _glib is None:
             _glib = C.CDLL(_LIB_GRID)
             _glib.refg_create.restype = C.c_void_p
-            _glib.refg_create.argtypes = [C.c_void_p, C.c_int] + [C.c_float] * 4
+            _glib.refg_create.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_float] * 4
             _glib.refg_destroy.argtypes = [C.c_void_p]
-            _glib.refg_grid.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
-            _glib.refg_features_in_area.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_int]
+            _glib.refg_grid.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+            _glib.refg_features_in_area.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_int]
         self._kps = np.ascontiguousarray(kps)
-        self._h = _glib.refg_create(_p(self._kps), len(self._kps), *[float(v) for v in bounds])
+        self._kr = None if kps_right is None else np.ascontiguousarray(kps_right)
+        self._h = _glib.refg_create(_p(self._kps), len(self._kps), None if self._kr is None else _p(self._kr), -1 if self._kr is None else len(self._kr),
+                                    *[float(v) for v in bounds])
 
     def __del__(self):
         if getattr(self, "_h", None):
             _glib.refg_destroy(self._h)
             self._h = None
 
-    def grid(self):
+    def grid(self, right=False):
+        n = len(self._kr) if right else len(self._kps)
         start = np.empty(64 * 48 + 1, np.int32)
-        items = np.empty(max(len(self._kps), 1), np.int32)
-        _glib.refg_grid(self._h, _p(start), _p(items))
+        items = np.empty(max(n, 1), np.int32)
+        _glib.refg_grid(self._h, int(right), _p(start), _p(items))
         return start, items[:start[-1]]
 
-    def features_in_area(self, x, y, r, min_level=-1, max_level=-1):
-        out = np.empty(max(len(self._kps), 1), np.int32)
-        n = _glib.refg_features_in_area(self._h, float(x), float(y), float(r), int(min_level), int(max_level), _p(out), len(out))
+    def features_in_area(self, x, y, r, min_level=-1, max_level=-1, right=False):
+        n = len(self._kr) if right else len(self._kps)
+        out = np.empty(max(n, 1), np.int32)
+        n = _glib.refg_features_in_area(self._h, int(right), float(x), float(y), float(r), int(min_level), int(max_level), _p(out), len(out))
         return out[:n]

@@ -48,11 +48,16 @@ float Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv, Frame::mnMinX
 }  // namespace TC2LI_SLAM
 
 using namespace TC2LI_SLAM;
-static Frame* make_frame(const void* kps, int n, float minX, float maxX, float minY, float maxY) {
+static Frame* make_frame(const void* kps, int n, const void* kpsRight, int nRight, float minX, float maxX, float minY, float maxY) {
     Frame* f = new Frame;
-    f->N = n; f->Nleft = -1;
     f->mvKeys.assign((const cv::KeyPoint*)kps, (const cv::KeyPoint*)kps + n);
-    f->mvKeysUn = f->mvKeys;   // Frame::UndistortKeyPoints with mDistCoef(0) == 0 (Frame.cc:777-782)
+    if (nRight < 0) {          // one grid: Nleft == -1, keys undistorted (Frame.cc:126-147, 217)
+        f->N = n; f->Nleft = -1;
+        f->mvKeysUn = f->mvKeys;   // Frame::UndistortKeyPoints with mDistCoef(0) == 0 (Frame.cc:777-782)
+    } else {                   // two grids: the fisheye stereo constructor (Frame.cc:1096-1104): N = Nleft + Nright, distorted keys
+        f->Nleft = n; f->N = n + nRight;
+        f->mvKeysRight.assign((const cv::KeyPoint*)kpsRight, (const cv::KeyPoint*)kpsRight + nRight);
+    }
     Frame::mnMinX = minX; Frame::mnMaxX = maxX; Frame::mnMinY = minY; Frame::mnMaxY = maxY;
     // the reference's constructors, Frame.cc:179-180
     Frame::mfGridElementWidthInv = static_cast<float>(FRAME_GRID_COLS) / (Frame::mnMaxX - Frame::mnMinX);
@@ -60,20 +65,22 @@ static Frame* make_frame(const void* kps, int n, float minX, float maxX, float m
     f->AssignFeaturesToGrid();
     return f;
 }
-extern "C" void* refg_create(const void* kps, int n, float minX, float maxX, float minY, float maxY) { return make_frame(kps, n, minX, maxX, minY, maxY); }
+extern "C" void* refg_create(const void* kps, int n, const void* kpsRight, int nRight, float minX, float maxX, float minY, float maxY) {
+    return make_frame(kps, n, kpsRight, nRight, minX, maxX, minY, maxY);
+}
 extern "C" void refg_destroy(void* h) { delete (Frame*)h; }
-extern "C" void refg_grid(void* h, int* cellStart, int* items) {   // mGrid[i][j] -> CSR, cell = i * FRAME_GRID_ROWS + j
+extern "C" void refg_grid(void* h, int right, int* cellStart, int* items) {   // mGrid[i][j] / mGridRight[i][j] -> CSR, cell = i * FRAME_GRID_ROWS + j
     Frame* f = (Frame*)h;
     int pos = 0;
     for (int i = 0; i < FRAME_GRID_COLS; ++i)
         for (int j = 0; j < FRAME_GRID_ROWS; ++j) {
             cellStart[i * FRAME_GRID_ROWS + j] = pos;
-            for (size_t v : f->mGrid[i][j]) items[pos++] = (int)v;
+            for (size_t v : (right ? f->mGridRight[i][j] : f->mGrid[i][j])) items[pos++] = (int)v;
         }
     cellStart[FRAME_GRID_COLS * FRAME_GRID_ROWS] = pos;
 }
-extern "C" int refg_features_in_area(void* h, float x, float y, float r, int minLevel, int maxLevel, int* out, int cap) {
-    const vector<size_t> v = ((Frame*)h)->GetFeaturesInArea(x, y, r, minLevel, maxLevel, false);
+extern "C" int refg_features_in_area(void* h, int right, float x, float y, float r, int minLevel, int maxLevel, int* out, int cap) {
+    const vector<size_t> v = ((Frame*)h)->GetFeaturesInArea(x, y, r, minLevel, maxLevel, right != 0);
     for (size_t i = 0; i < v.size() && (int)i < cap; ++i) out[i] = (int)v[i];
     return (int)v.size();
 }

@@ -299,9 +299,11 @@ void launch_remap(const uint8_t* src, int sw, int sh, int channels, int rgb, con
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Reflect-101 margin of every pyramid plane (3 rows / 3 columns around the interior): what GaussianBlur(...,
-// BORDER_REFLECT_101) reads beyond the edge of its (cloned, hence border-less) input (ORBextractor.cc:1105-1106).  With the
-// margin in place the blur kernel below has no edge cases.  One launch covers all levels of all images.
+// Reflect-101 margin ROWS of every pyramid plane (3 above, 3 below the interior): what GaussianBlur(..., BORDER_REFLECT_101)
+// reads beyond the top / bottom edge of its (cloned, hence border-less) input (ORBextractor.cc:1105-1106).  They are plain row
+// copies (contiguous, 6 x w bytes per plane).  The margin COLUMNS are not materialised in HBM: touching both ends of every
+// row costs two 64-byte DRAM accesses per row for 6 bytes (ncu: 0.47 MB per KITTI image, 1.1 ms per 8192 images); the blur
+// kernel writes the three mirrored bytes into its shared-memory box instead.  One launch covers all levels of all images.
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int reflect101(int i, int n) {
     if (i < 0) i = -i;
@@ -314,7 +316,7 @@ __global__ void __launch_bounds__(256) k_margin(const __grid_constant__ Geom g, 
     const LevelGeom& L = g.lv[level];
     const int t = blockIdx.x * 256 + threadIdx.x;
     const int wWords = (L.w + 3) >> 2;
-    const int rowItems = 6 * wWords, colItems = L.h + 6;
+    const int rowItems = 6 * wWords;
     uint8_t* P = b.pyr + L.planeOff + (size_t)img * L.planeBytes;
     if (t < rowItems) {
         // the three rows above and below: word copies of the mirrored interior rows (-k -> k, h-1+k -> h-1-k)
@@ -323,25 +325,14 @@ __global__ void __launch_bounds__(256) k_margin(const __grid_constant__ Geom g, 
         const uint32_t* src = reinterpret_cast<const uint32_t*>(P + (size_t)reflect101(y, L.h) * L.pitch);
         if (4 * c + 4 <= L.w)
             reinterpret_cast<uint32_t*>(P + (ptrdiff_t)y * L.pitch)[c] = src[c];
-        else  // the last, partial word: bytes >= w belong to the column part below (no two writers per byte)
+        else  // the last, partial word
             for (int x = 4 * c; x < L.w; ++x) (P + (ptrdiff_t)y * L.pitch)[x] = reinterpret_cast<const uint8_t*>(src)[x];
-    } else if (t < rowItems + colItems) {
-        // the three columns left and right of every row (margin rows included: they read their mirrored source row directly,
-        // so this part does not depend on the copies above).  Left: one word [pad, p3, p2, p1] in front of pixel 0.
-        const int y = t - rowItems - 3;
-        const uint8_t* src = P + (size_t)reflect101(y, L.h) * L.pitch;
-        uint8_t* dst = P + (ptrdiff_t)y * L.pitch;
-        const uint32_t first = *reinterpret_cast<const uint32_t*>(src);
-        *reinterpret_cast<uint32_t*>(dst - 4) = __byte_perm(first, 0, 0x1230);  // bytes: pad(=p0), p3, p2, p1
-        dst[L.w] = src[reflect101(L.w, L.w)];
-        dst[L.w + 1] = src[reflect101(L.w + 1, L.w)];
-        dst[L.w + 2] = src[reflect101(L.w + 2, L.w)];
     }
 }
 
 void launch_margin(const Geom& g, const Buffers& b, int nImages, cudaStream_t s) {
     int maxItems = 0;
-    for (int l = 0; l < g.nlevels; ++l) maxItems = max(maxItems, 6 * ((g.lv[l].w + 3) / 4) + g.lv[l].h + 6);
+    for (int l = 0; l < g.nlevels; ++l) maxItems = max(maxItems, 6 * ((g.lv[l].w + 3) / 4));
     dim3 grid((maxItems + 255) / 256, g.nlevels, nImages);
     k_margin<<<grid, 256, 0, s>>>(g, b);
 }
@@ -390,6 +381,11 @@ __global__ void __launch_bounds__(32 * BLUR_WARPS) k_blur(const __grid_constant_
         if (nChunks > 1) issue(1);
     }
     const bool active = x0 < w;
+    // BORDER_REFLECT_101 columns: pixels -3..-1 (first strip) and w..w+2 (every strip whose box reaches past column w - 1) are
+    // written into the box in shared memory; eR = box byte of pixel w (the box starts 4 bytes before the strip's first pixel)
+    const bool edgeL = strip == 0;
+    const int eR = 4 + w - strip * 128;
+    const bool edgeR = eR < BLUR_BOXW - 8;  // the filter reads box bytes 1 .. 134
     uint8_t* D = dst + (size_t)imgRel * plane + x0;
     uint32_t ph0 = 0, ph1 = 0;
     // Column pass two input rows at a time: P = (h[y], h[y+1]) as 16x2 lanes, and the pair's contribution to the eight output
@@ -439,6 +435,17 @@ __global__ void __launch_bounds__(32 * BLUR_WARPS) k_blur(const __grid_constant_
     for (int c = 0; c < nChunks; ++c) {
         if (c & 1) { mbar_wait(&bars[wy][1], ph1); ph1 ^= 1; }
         else { mbar_wait(&bars[wy][0], ph0); ph0 ^= 1; }
+        if (edgeL | edgeR) {  // warp-uniform: mirror the three pixels beyond the left / right image edge inside the box, lane = box row
+            unsigned char* row = tile[wy][c & 1] + threadIdx.x * BLUR_BOXW;
+            if (edgeL) reinterpret_cast<uint32_t*>(row)[0] = __byte_perm(reinterpret_cast<const uint32_t*>(row)[1], 0, 0x1230);  // [pad, p3, p2, p1] in front of p0
+            if (edgeR) {
+#pragma unroll
+                for (int m = 0; m < 3; ++m)
+                    if (eR + m < BLUR_BOXW) row[eR + m] = row[eR - 2 - m];  // pixel w + m <- pixel w - 2 - m
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes before the next TMA box lands in this buffer
+            __syncwarp();
+        }
         if (active) {
             const uint32_t* T = reinterpret_cast<const uint32_t*>(tile[wy][c & 1]) + threadIdx.x;  // word 0 = pixels x0-4..x0-1
             const int yb = c * BLUR_BOXH - 3;  // image row of box row 0

@@ -300,3 +300,13 @@ def test_large_resident_batch_spot_checks():
         for kk, dd, cc in ((kps, desc, cnt), (kps2, desc2, cnt2)):
             assert cc[i] == len(ok) and kk[i, :cc[i]].tobytes() == ok.tobytes() and np.array_equal(dd[i, :cc[i]], od), int(i)
     b.close()
+
+
+@pytest.mark.parametrize("w", [257, 258, 259, 384, 385, 386, 387, 640, 770, 895, 896])
+def test_blur_edges_at_strip_boundaries(w):
+    """The blur mirrors the three columns beyond the image edge inside its shared-memory boxes (no margin columns in HBM): widths
+    whose last 128-pixel strip holds 1, 2, 3 or all 128 pixels, and widths that make lower levels end at such boundaries; every
+    blurred level is compared in full."""
+    img = po.synth_v1(w, 150, 900 + w)
+    stage_compare(img, (400, 1.2, 4, 20, 7))
+    stage_compare(img, (400, 1.2, 2, 20, 7), taps=(18, 34, 49, 55, 49, 34, 18))

@@ -142,3 +142,23 @@ def test_feature_grid_matches_reference_bodies(kind, seed):
         a = ref.features_in_area(x, y, r, *lv)
         b = po.features_in_area(k, (os_, oi), bounds, x, y, r, *lv)
         assert np.array_equal(a, b), (q, x, y, r, lv)
+
+
+@pytest.mark.skipif(not pyref.grid_available(), reason="oracle/_ref/libref_grid.so not built (needs /root/reference once)")
+def test_feature_grid_two_grid_case_is_one_grid_per_image():
+    """Fisheye stereo (Nleft != -1): mGrid bins mvKeys, mGridRight bins mvKeysRight with indices i - Nleft (Frame.cc:428-441), and
+    GetFeaturesInArea(..., bRight) reads the matching pair — i.e. exactly one single-grid per image, which is what the batch API builds."""
+    bounds = (0.0, 752.0, 0.0, 480.0)
+    ex = po.OracleExtractor(1200, 1.2, 8, 20, 7)
+    _, kl, _ = ex(po.synth_v1(752, 480, 21), (250, 751))
+    _, kr, _ = ex(po.synth_v1(752, 480, 21, 16, 0x5bd1e995), (0, 501))
+    ref = pyref.RefFrameGrid(kl, bounds, kr)
+    rng = np.random.default_rng(9)
+    for right, k in ((False, kl), (True, kr)):
+        rs, ri = ref.grid(right)
+        os_, oi = po.assign_grid(k, bounds)
+        assert np.array_equal(rs, os_) and np.array_equal(ri, oi), right
+        for q in range(200):
+            x, y, r = float(rng.uniform(-30, 780)), float(rng.uniform(-30, 510)), float(rng.choice([3, 10, 25, 80]))
+            lv = [(-1, -1), (1, 4), (0, 2), (5, -1)][q % 4]
+            assert np.array_equal(ref.features_in_area(x, y, r, *lv, right=right), po.features_in_area(k, (os_, oi), bounds, x, y, r, *lv)), (right, q)
