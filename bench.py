@@ -366,7 +366,25 @@ def main():
         t0 = time.perf_counter()
         qc, _ = big.features_in_area(q, 64)
         dt_q = time.perf_counter() - t0
-        grid = {"what": "orbx_batch_assign_grid (Frame::AssignFeaturesToGrid, Frame.cc:412-443) on the resident keypoints; orbx_batch_features_in_area "
+        # projection search of one frame: the keypoints of image 0 re-projected onto themselves (th = 15, default level window)
+        kp0, de0, cn0, _ = big.download(1)
+        n0 = int(cn0[0])
+        sfs = T.tables(2000, 1.2, 8, 20, 7)["scale_factors"]
+        pq = np.zeros(n0, T.PROJ_QUERY_DTYPE)
+        pq["u"], pq["v"], pq["angle"] = kp0[0, :n0]["x"], kp0[0, :n0]["y"], kp0[0, :n0]["angle"]
+        pq["radius"] = np.float32(15.0) * sfs[kp0[0, :n0]["octave"]]
+        pq["ur"], pq["blocks"] = -1.0, 1
+        pq["min_level"], pq["max_level"] = kp0[0, :n0]["octave"] - 1, kp0[0, :n0]["octave"] + 1
+        pq["desc"] = de0[0, :n0]
+        big.search_by_projection(0, pq, False, True)
+        t0 = time.perf_counter()
+        for _ in range(10):
+            _, nm_sp = big.search_by_projection(0, pq, False, True)
+        dt_sp = (time.perf_counter() - t0) / 10
+        grid = {"projection_search": {"what": "orbx_batch_search_by_projection (ORBmatcher::SearchByProjection from ORBmatcher.cc:1729 on): the keypoints of one frame "
+                                              "re-projected onto themselves, th = 15, host queries in, host matches out", "map_points": n0, "matches": int(nm_sp),
+                                      "ms_per_frame_host_to_host": dt_sp * 1e3},
+                "what": "orbx_batch_assign_grid (Frame::AssignFeaturesToGrid, Frame.cc:412-443) on the resident keypoints; orbx_batch_features_in_area "
                         "(Frame::GetFeaturesInArea, Frame.cc:687-749) host queries in, host index lists out",
                 "assign_ms_per_step": ms_grid, "assign_images_per_s": n_img / (ms_grid * 1e-3), "area_queries": nq,
                 "area_queries_per_s_host_to_host": nq / dt_q, "mean_hits_per_query": float(qc.mean())}

@@ -209,6 +209,26 @@ typedef struct orbx_area_query {
     int min_level, max_level; /* the reference's defaults are -1, -1 */
 } orbx_area_query;
 int orbx_batch_features_in_area(orbx_batch* b, const orbx_area_query* queries, int n_queries, int capacity, int* counts, int* indices);
+/* The search of ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono) (ORBmatcher.cc:1685-1895) from the
+ * point where a map point has been projected (ORBmatcher.cc:1729 on), single-grid case, against image `image` of the handle (after
+ * orbx_batch_run and orbx_batch_assign_grid; use_uright = 1 also needs orbx_batch_stereo_match, whose mvuRight the gate of
+ * ORBmatcher.cc:1760-1766 reads).  The caller keeps the pose algebra (Tcw * x3Dw, project, the bounds test, the bForward / bBackward decision)
+ * and sends one query per surviving map point, in LastFrame order:
+ *   u, v = uv(0), uv(1);  radius = th * mvScaleFactors[nLastOctave];  ur = uv(0) - mbf * invzc;
+ *   min_level / max_level = the GetFeaturesInArea level window of its branch: (o, -1) forward, (0, o) backward, (o - 1, o + 1) otherwise;
+ *   angle = kpLF.angle;  blocks = pMP->Observations() > 0;  desc = pMP->GetDescriptor().
+ * match[k] (k < K = orbx_batch_max_keypoints) = index of the query whose map point CurrentFrame.mvpMapPoints[k] ends up with, -1 = NULL
+ * (CurrentFrame.mvpMapPoints starts all-NULL, as Tracking::TrackWithMotionModel fills it before the call); *n_matches = the value the
+ * reference returns.  th_high = ORBmatcher::TH_HIGH (100); check_orientation = ORBmatcher::mbCheckOrientation.  Host arrays; synchronises. */
+typedef struct orbx_proj_query {
+    float u, v, radius, ur;
+    int min_level, max_level;
+    float angle;
+    int blocks;
+    uint8_t desc[32];
+} orbx_proj_query;
+int orbx_batch_search_by_projection(orbx_batch* b, int image, const orbx_proj_query* queries, int n_queries, int use_uright, int check_orientation, int th_high,
+                                    int* match, int* n_matches);
 int orbx_batch_sync(orbx_batch* b);
 /* the same on a sub-range [first, first+n) of the handle's images (lapping: n x 2 ints for that range): lets a caller keep
  * many frames resident and process them in groups small enough for the 126 MB L2 */

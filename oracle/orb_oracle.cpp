@@ -823,6 +823,83 @@ int features_in_area(const KeyPoint* kps, const int* cellStart, const int* items
 }
 
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The search of ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono) (ORBmatcher.cc:1685-1895)
+// from the point where a map point has been projected (ORBmatcher.cc:1729 on) — single-grid case (CurrentFrame.Nleft == -1).
+// What precedes that line is pose algebra on Sophus / Eigen types and stays with the caller; a query carries its outcome:
+//   u, v = uv(0), uv(1);  radius = th * mvScaleFactors[nLastOctave];  ur = uv(0) - mbf * invzc;
+//   [minLevel, maxLevel] = the GetFeaturesInArea level window of the bForward / bBackward / default branch (:1737-1742);
+//   angle = kpLF.angle;  blocks = pMP->Observations() > 0;  desc = pMP->GetDescriptor().
+// Restated: the candidate walk (GetFeaturesInArea order), the skip of keypoints already taken by a point with observations
+// (:1756-1758; CurrentFrame.mvpMapPoints starts all-NULL as in Tracking::TrackWithMotionModel), the right-coordinate gate
+// (:1760-1766), first-minimum Hamming distance (:1768-1776), acceptance at bestDist <= TH_HIGH (:1779-1783), the rotation
+// histogram (:1784-1801, bin = round(rot / HISTO_LENGTH)), ComputeThreeMaxima (ORBmatcher.cc:2021-2062) and the removal of the
+// matches outside the three dominant bins (:1872-1892).  match[k] = index of the query whose point keypoint k ends up with, -1 = none.
+// ---------------------------------------------------------------------------------------------------------------------
+struct ProjQuery {
+    float u, v, radius, ur;
+    int32_t minLevel, maxLevel;
+    float angle;
+    int32_t blocks;
+    uint8_t desc[32];
+};
+static_assert(sizeof(ProjQuery) == 64, "orbx_proj_query layout");
+
+int search_by_projection_tail(const KeyPoint* kps, int nKps, const uint8_t* desc, const float* uRight, const int* cellStart, const int* items, float minX,
+                              float maxX, float minY, float maxY, const ProjQuery* q, int nq, int checkOrientation, int thHigh, int* match) {
+    constexpr int HISTO_LENGTH = 30;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = 1.0f / HISTO_LENGTH;
+    std::vector<int> cand((size_t)std::max(nKps, 1));
+    std::vector<char> taken((size_t)std::max(nKps, 1), 0);  // mvpMapPoints[i2] && mvpMapPoints[i2]->Observations() > 0
+    for (int k = 0; k < nKps; ++k) match[k] = -1;
+    int nmatches = 0;
+    for (int i = 0; i < nq; ++i) {
+        const ProjQuery& Q = q[i];
+        const int nc = features_in_area(kps, cellStart, items, minX, maxX, minY, maxY, Q.u, Q.v, Q.radius, Q.minLevel, Q.maxLevel, cand.data(), nKps);
+        if (nc == 0) continue;
+        int bestDist = 256, bestIdx2 = -1;
+        for (int c = 0; c < nc; ++c) {
+            const int i2 = cand[c];
+            if (match[i2] >= 0 && taken[i2]) continue;
+            if (uRight && uRight[i2] > 0) {
+                const float er = std::fabs(Q.ur - uRight[i2]);
+                if (er > Q.radius) continue;
+            }
+            const int dist = hamming256(Q.desc, desc + (size_t)i2 * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+        }
+        if (bestDist <= thHigh) {
+            match[bestIdx2] = i;
+            taken[bestIdx2] = Q.blocks != 0;
+            ++nmatches;
+            if (checkOrientation) {
+                float rot = Q.angle - kps[bestIdx2].angle;
+                if (rot < 0.0) rot += 360.0f;
+                int bin = (int)std::round(rot * factor);
+                if (bin == HISTO_LENGTH) bin = 0;
+                rotHist[bin].push_back(bestIdx2);
+            }
+        }
+    }
+    if (checkOrientation) {
+        int ind1 = -1, ind2 = -1, ind3 = -1, max1 = 0, max2 = 0, max3 = 0;
+        for (int i = 0; i < HISTO_LENGTH; ++i) {  // ORBmatcher::ComputeThreeMaxima
+            const int sz = (int)rotHist[i].size();
+            if (sz > max1) { max3 = max2; max2 = max1; max1 = sz; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (sz > max2) { max3 = max2; max2 = sz; ind3 = ind2; ind2 = i; }
+            else if (sz > max3) { max3 = sz; ind3 = i; }
+        }
+        if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+        else if (max3 < 0.1f * (float)max1) ind3 = -1;
+        for (int i = 0; i < HISTO_LENGTH; ++i)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (int k : rotHist[i]) { match[k] = -1; --nmatches; }
+    }
+    return nmatches;
+}
+
+
 extern "C" {
 void* orbo_create(int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh) {
     return new Extractor(nfeatures, scaleFactor, nlevels, iniTh, minTh);
@@ -877,6 +954,11 @@ void orbo_assign_grid(const void* kps, int n, float minX, float maxX, float minY
 int orbo_features_in_area(const void* kps, const int* cellStart, const int* items, float minX, float maxX, float minY, float maxY, float x, float y, float r,
                           int minLevel, int maxLevel, int* out, int cap) {
     return features_in_area((const KeyPoint*)kps, cellStart, items, minX, maxX, minY, maxY, x, y, r, minLevel, maxLevel, out, cap);
+}
+int orbo_search_by_projection(const void* kps, int nKps, const uint8_t* desc, const float* uRight, const int* cellStart, const int* items, float minX,
+                              float maxX, float minY, float maxY, const void* q, int nq, int checkOrientation, int thHigh, int* match) {
+    return search_by_projection_tail((const KeyPoint*)kps, nKps, desc, uRight, cellStart, items, minX, maxX, minY, maxY, (const ProjQuery*)q, nq, checkOrientation,
+                                     thHigh, match);
 }
 void orbo_lapping_match(const uint8_t* dl, int nq, const uint8_t* dr, int nt, int* out, uint8_t* ok) { lapping_knn_match(dl, nq, dr, nt, out, ok); }
 void orbo_cvt_gray(const uint8_t* src, int w, int h, int sstride, int channels, int rgb, uint8_t* dst, int dstride) {

@@ -50,6 +50,7 @@ def lib():
         L.orbo_stereo_match.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
         L.orbo_assign_grid.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
         L.orbo_features_in_area.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_float] * 7 + [C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.orbo_search_by_projection.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_float] * 4 + [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.orbo_lapping_match.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.orbo_cvt_gray.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.orbo_remap.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
@@ -181,6 +182,43 @@ def features_in_area(kps, grid, bounds, x, y, r, min_level=-1, max_level=-1):
     n = lib().orbo_features_in_area(_p(kps), _p(start), _p(items), *[float(v) for v in bounds], float(x), float(y), float(r), int(min_level), int(max_level),
                                     _p(out), len(out))
     return out[:n]
+
+
+PROJ_QUERY_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("radius", "<f4"), ("ur", "<f4"), ("min_level", "<i4"), ("max_level", "<i4"), ("angle", "<f4"),
+                             ("blocks", "<i4"), ("desc", "u1", (32,))])  # orbx_proj_query (64 bytes)
+
+
+def make_proj_queries(points, octaves, nobs, point_desc, scale_factors, th, mbf, mode):
+    """What ORBmatcher::SearchByProjection (ORBmatcher.cc:1712-1742) knows about a map point when it starts searching, in the
+    reference's float arithmetic.  points: float32 [nq, 4] = (uv(0), uv(1), x3Dc(2), kpLF.angle); mode 0 = default window
+    [o-1, o+1], 1 = bForward (o, -1), 2 = bBackward (0, o).  Points behind the camera or outside the image bounds are the caller's to drop."""
+    pts = np.ascontiguousarray(points, np.float32).reshape(-1, 4)
+    octv = np.ascontiguousarray(octaves, np.int32)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    q = np.zeros(len(pts), PROJ_QUERY_DTYPE)
+    q["u"], q["v"], q["angle"] = pts[:, 0], pts[:, 1], pts[:, 3]
+    q["radius"] = np.float32(th) * sf[octv]
+    invz = (1.0 / pts[:, 2].astype(np.float64)).astype(np.float32)  # const float invzc = 1.0/x3Dc(2)
+    q["ur"] = pts[:, 0] - np.float32(mbf) * invz
+    q["min_level"] = [octv - 1, octv, np.zeros_like(octv)][mode]
+    q["max_level"] = [octv + 1, np.full_like(octv, -1), octv][mode]
+    q["blocks"] = np.ascontiguousarray(nobs, np.int32) > 0
+    q["desc"] = np.ascontiguousarray(point_desc, np.uint8).reshape(-1, 32)
+    return q
+
+
+def search_by_projection(kps, desc, uright, grid, bounds, queries, check_orientation=True, th_high=100):
+    """The search of ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, ...) from ORBmatcher.cc:1729 on (see orb_oracle.cpp).
+    uright = None stands for a frame without right coordinates.  Returns (match int32 [n], nmatches)."""
+    kps = np.ascontiguousarray(kps)
+    desc = np.ascontiguousarray(desc, np.uint8)
+    start, items = np.ascontiguousarray(grid[0], np.int32), np.ascontiguousarray(grid[1], np.int32)
+    q = np.ascontiguousarray(queries, PROJ_QUERY_DTYPE)
+    ur = None if uright is None else np.ascontiguousarray(uright, np.float32)
+    match = np.empty(max(len(kps), 1), np.int32)
+    nm = lib().orbo_search_by_projection(_p(kps), len(kps), _p(desc), None if ur is None else _p(ur), _p(start), _p(items), *[float(v) for v in bounds], _p(q), len(q),
+                                         int(bool(check_orientation)), int(th_high), _p(match))
+    return match[:len(kps)], nm
 
 
 class OracleExtractor:

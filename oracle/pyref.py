@@ -165,3 +165,33 @@ class RefFrameGrid:
         out = np.empty(max(n, 1), np.int32)
         n = _glib.refg_features_in_area(self._h, int(right), float(x), float(y), float(r), int(min_level), int(max_level), _p(out), len(out))
         return out[:n]
+
+
+_LIB_SEARCH = os.path.join(_HERE, "_ref", "libref_search.so")
+_splib = None
+
+
+def search_available():
+    return os.path.exists(_LIB_SEARCH)
+
+
+def search_by_projection(kps, desc, uright, bounds, scale_factors, mb, mbf, points, octaves, nobs, point_desc, th, tlcz, mono=False, check_orientation=True):
+    """The reference's own ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) (ORBmatcher.cc:1685-1895, built by
+    oracle/tools/gen_ref_search.py) with identity pose algebra: points = float32 [nq, 4] (u, v, z, last-keypoint angle).
+    Returns (match int32 [n]: map-point index per current keypoint or -1, nmatches)."""
+    global _splib
+    if _splib is None:
+        _splib = C.CDLL(_LIB_SEARCH)
+        _splib.refsp_search.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p] + [C.c_float] * 4 + [C.c_void_p, C.c_int, C.c_float, C.c_float,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p]
+    kps = np.ascontiguousarray(kps)
+    desc = np.ascontiguousarray(desc, np.uint8)
+    ur = np.ascontiguousarray(uright, np.float32)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    pts = np.ascontiguousarray(points, np.float32).reshape(-1, 4)
+    octv, nob = np.ascontiguousarray(octaves, np.int32), np.ascontiguousarray(nobs, np.int32)
+    pd = np.ascontiguousarray(point_desc, np.uint8).reshape(-1, 32)
+    match = np.empty(max(len(kps), 1), np.int32)
+    nm = _splib.refsp_search(_p(kps), len(kps), _p(desc), _p(ur), *[float(v) for v in bounds], _p(sf), len(sf), float(mb), float(mbf), _p(pts), _p(octv), _p(nob),
+                             _p(pd), len(pts), float(th), float(tlcz), int(bool(mono)), int(bool(check_orientation)), _p(match))
+    return match[:len(kps)], nm

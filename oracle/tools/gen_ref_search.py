@@ -1,0 +1,151 @@
+#!/usr/bin/env python3
+"""Builds oracle/_ref/libref_search.so: the reference's OWN ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono),
+ORBmatcher::ComputeThreeMaxima, ORBmatcher::DescriptorDistance (slam_framework/src/ORBmatcher.cc) and Frame::GetFeaturesInArea /
+AssignFeaturesToGrid / PosInGrid (slam_framework/src/Frame.cc), compiled verbatim around stand-ins for the types they touch.
+Eigen is not in this image and Sophus needs it, so the pose algebra in front of the search is replaced by stand-ins that make it
+the identity: a map point's "world position" is (u, v, z), `Tcw * x` returns x, the camera's project() returns (x(0), x(1)); the
+last-frame pose stand-in returns a chosen tlc, which selects the bForward / bBackward / default branch.  Everything from
+ORBmatcher.cc:1729 on (windows, level filters, the taken-keypoint skip, the right-coordinate gate, best distance, rotation
+histogram, three maxima) runs as written.  As for the other generators the bodies are cut out of the mounted reference at BUILD
+time into a temporary file OUTSIDE the repository; only the shared object is kept (oracle/_ref is git-ignored).  TEST INFRASTRUCTURE ONLY.
+
+usage: gen_ref_search.py /root/reference OUT.so"""
+import os, re, subprocess, sys, tempfile
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from gen_ref_stereo import cut_function
+
+
+def main():
+    ref, out = sys.argv[1], sys.argv[2]
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    frame = open(os.path.join(ref, "slam_framework/src/Frame.cc")).read()
+    matcher = open(os.path.join(ref, "slam_framework/src/ORBmatcher.cc")).read()
+    header = open(os.path.join(ref, "slam_framework/include/Frame.h")).read()
+    defs = "\n".join(l for l in header.splitlines() if re.match(r"\s*#define FRAME_GRID_(ROWS|COLS)\s+\d+", l))
+    consts = "\n".join(l.strip() for l in matcher.splitlines() if re.match(r"\s*const int ORBmatcher::(TH_HIGH|TH_LOW|HISTO_LENGTH)\s*=", l))
+    assert "TH_HIGH" in consts and "HISTO_LENGTH" in consts
+    frame_bodies = [cut_function(frame, "void Frame::AssignFeaturesToGrid()"),
+                    cut_function(frame, "bool Frame::PosInGrid(const cv::KeyPoint &kp, int &posX, int &posY)"),
+                    cut_function(frame, "vector<size_t> Frame::GetFeaturesInArea(")]
+    matcher_bodies = [cut_function(matcher, "int ORBmatcher::DescriptorDistance(const cv::Mat &a, const cv::Mat &b)"),
+                      cut_function(matcher, "void ORBmatcher::ComputeThreeMaxima(vector<int>* histo, const int L, int &ind1, int &ind2, int &ind3)"),
+                      cut_function(matcher, "int ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono)")]
+    glue_top = r'''
+#include <algorithm>
+#include <cassert>
+#include <climits>
+#include <cmath>
+#include <cstring>
+#include <vector>
+#include "opencv2/cvstub.hpp"
+using namespace std;
+''' + defs + r'''
+namespace Eigen {   // stand-ins: plain containers, no arithmetic
+struct Vector3f { float d[3]; float operator()(int i) const { return d[i]; } };
+struct Vector2f { float d[2]; float operator()(int i) const { return d[i]; } };
+}
+namespace Sophus {  // stand-in: `T * x` is the identity, or a constant for the last-frame pose (-> tlc)
+struct SE3f {
+    bool constant = false;
+    Eigen::Vector3f t = {{0.f, 0.f, 0.f}};
+    SE3f inverse() const { return *this; }
+    Eigen::Vector3f translation() const { return t; }
+    Eigen::Vector3f operator*(const Eigen::Vector3f& p) const { return constant ? t : p; }
+};
+}
+namespace TC2LI_SLAM {
+struct MapPoint {
+    Eigen::Vector3f pos; cv::Mat desc; int nObs;
+    Eigen::Vector3f GetWorldPos() { return pos; }
+    cv::Mat GetDescriptor() { return desc; }
+    int Observations() { return nObs; }
+};
+struct GeometricCamera { Eigen::Vector2f project(const Eigen::Vector3f& p) { return Eigen::Vector2f{{p(0), p(1)}}; } };
+struct Frame {
+    int N, Nleft;
+    std::vector<cv::KeyPoint> mvKeys, mvKeysRight, mvKeysUn;
+    std::vector<MapPoint*> mvpMapPoints;
+    std::vector<bool> mvbOutlier;
+    std::vector<float> mvuRight, mvScaleFactors;
+    cv::Mat mDescriptors;
+    float mb, mbf;
+    GeometricCamera* mpCamera;
+    Sophus::SE3f mTcw;
+    Sophus::SE3f GetPose() const { return mTcw; }
+    Sophus::SE3f GetRelativePoseTrl() { return Sophus::SE3f(); }
+    static float mfGridElementWidthInv, mfGridElementHeightInv;
+    static float mnMinX, mnMaxX, mnMinY, mnMaxY;
+    std::vector<std::size_t> mGrid[FRAME_GRID_COLS][FRAME_GRID_ROWS];
+    std::vector<std::size_t> mGridRight[FRAME_GRID_COLS][FRAME_GRID_ROWS];
+    void AssignFeaturesToGrid();
+    bool PosInGrid(const cv::KeyPoint &kp, int &posX, int &posY);
+    vector<size_t> GetFeaturesInArea(const float &x, const float  &y, const float  &r, const int minLevel=-1, const int maxLevel=-1, const bool bRight = false) const;
+};
+float Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv, Frame::mnMinX, Frame::mnMaxX, Frame::mnMinY, Frame::mnMaxY;
+struct ORBmatcher {
+    static const int TH_LOW, TH_HIGH, HISTO_LENGTH;
+    float mfNNratio; bool mbCheckOrientation;
+    static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b);
+    void ComputeThreeMaxima(std::vector<int>* histo, const int L, int &ind1, int &ind2, int &ind3);
+    int SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono);
+};
+''' + consts + "\n"
+    glue_bottom = r'''
+}  // namespace TC2LI_SLAM
+
+using namespace TC2LI_SLAM;
+// points: nq x {u, v, z, angle} floats; octaves / nobs: nq ints; pdesc: nq x 32 bytes; tlcz selects the branch (vs mb)
+extern "C" int refsp_search(const void* kps, int n, const unsigned char* desc, const float* uright, float minX, float maxX, float minY, float maxY,
+                            const float* scaleFactors, int nlevels, float mb, float mbf, const float* points, const int* octaves, const int* nobs,
+                            const unsigned char* pdesc, int nq, float th, float tlcz, int bMono, int checkOrientation, int* match) {
+    Frame cur, last;
+    GeometricCamera cam;
+    cur.N = n; cur.Nleft = -1;
+    cur.mvKeys.assign((const cv::KeyPoint*)kps, (const cv::KeyPoint*)kps + n);
+    cur.mvKeysUn = cur.mvKeys;
+    cur.mvpMapPoints.assign(n, nullptr);                 // Tracking::TrackWithMotionModel: fill(..., NULL) before the search
+    cur.mvuRight.assign(uright, uright + n);
+    cur.mvScaleFactors.assign(scaleFactors, scaleFactors + nlevels);
+    cur.mDescriptors = cv::Mat(n, 32, CV_8U, (void*)desc, 32);
+    cur.mb = mb; cur.mbf = mbf; cur.mpCamera = &cam;
+    Frame::mnMinX = minX; Frame::mnMaxX = maxX; Frame::mnMinY = minY; Frame::mnMaxY = maxY;
+    Frame::mfGridElementWidthInv = static_cast<float>(FRAME_GRID_COLS) / (Frame::mnMaxX - Frame::mnMinX);
+    Frame::mfGridElementHeightInv = static_cast<float>(FRAME_GRID_ROWS) / (Frame::mnMaxY - Frame::mnMinY);
+    cur.AssignFeaturesToGrid();
+    std::vector<MapPoint> pts(nq);
+    last.N = nq; last.Nleft = -1;
+    last.mvKeys.resize(nq); last.mvKeysUn.resize(nq);
+    last.mvpMapPoints.resize(nq); last.mvbOutlier.assign(nq, false);
+    last.mTcw.constant = true; last.mTcw.t = Eigen::Vector3f{{0.f, 0.f, tlcz}};
+    for (int i = 0; i < nq; ++i) {
+        pts[i].pos = Eigen::Vector3f{{points[4 * i], points[4 * i + 1], points[4 * i + 2]}};
+        pts[i].desc = cv::Mat(1, 32, CV_8U, (void*)(pdesc + 32 * (size_t)i), 32);
+        pts[i].nObs = nobs[i];
+        last.mvpMapPoints[i] = &pts[i];
+        last.mvKeys[i].octave = octaves[i]; last.mvKeysUn[i].octave = octaves[i];
+        last.mvKeys[i].angle = points[4 * i + 3]; last.mvKeysUn[i].angle = points[4 * i + 3];
+    }
+    ORBmatcher m;
+    m.mfNNratio = 0.9f; m.mbCheckOrientation = checkOrientation != 0;
+    const int nm = m.SearchByProjection(cur, last, th, bMono != 0);
+    for (int k = 0; k < n; ++k) match[k] = cur.mvpMapPoints[k] ? (int)(cur.mvpMapPoints[k] - pts.data()) : -1;
+    return nm;
+}
+'''
+    tmp = tempfile.mkdtemp(prefix="orbx_ref_search_")
+    gen = os.path.join(tmp, "ref_search_gen.cpp")
+    with open(gen, "w") as f:
+        f.write(glue_top + "\n".join(frame_bodies + matcher_bodies) + "\n" + glue_bottom)
+    os.makedirs(os.path.dirname(os.path.abspath(out)), exist_ok=True)
+    cmd = ["g++", "-O3", "-march=x86-64-v3", "-ffp-contract=off", "-fPIC", "-std=c++14", "-w", "-shared", "-o", out, "-I" + os.path.join(here, "cvstub"), gen]
+    try:
+        subprocess.check_call(cmd)
+    finally:
+        os.remove(gen)
+        os.rmdir(tmp)
+    print("built", out)
+
+
+if __name__ == "__main__":
+    main()

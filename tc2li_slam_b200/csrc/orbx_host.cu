@@ -133,6 +133,9 @@ struct orbx_batch {
     int gridImages = 0;                 // images the grids were last built for (0 = never)
     orbx_area_query* qDev = nullptr; int* qCounts = nullptr; int* qOut = nullptr;
     size_t qCap = 0, qOutCap = 0;
+    orbx_proj_query* spDev = nullptr; int* spOut = nullptr;   // projection search: queries; match[K] + info[2]
+    size_t spCap = 0;
+    bool spConfigured = false;
     // extra lanes for orbx_batch_run_pipelined: chunks of a resident batch are issued round-robin over the lanes so that the
     // latency-bound stages of one chunk (quadtree) overlap the issue-bound stages of another (FAST)
     static const int kLanes = 3;
@@ -387,6 +390,8 @@ void orbx_batch_destroy(orbx_batch* b) {
     DeviceGuard dg(b->device);
     if (b->own) cudaStreamSynchronize(b->own);
     for (void* p : b->allocs) cudaFree(p);
+    if (b->spDev) cudaFree(b->spDev);
+    if (b->spOut) cudaFree(b->spOut);
     if (b->qDev) cudaFree(b->qDev);
     if (b->qCounts) cudaFree(b->qCounts);
     if (b->qOut) cudaFree(b->qOut);
@@ -799,6 +804,41 @@ int orbx_batch_features_in_area(orbx_batch* b, const orbx_area_query* queries, i
     CU(cudaMemcpyAsync(counts, b->qCounts, (size_t)n_queries * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
     if (capacity) CU(cudaMemcpyAsync(indices, b->qOut, (size_t)n_queries * capacity * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
     CU(cudaStreamSynchronize(b->stream));
+    return ORBX_OK;
+}
+
+// ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) from ORBmatcher.cc:1729 on (see search_kernel.cu); synchronous
+int orbx_batch_search_by_projection(orbx_batch* b, int image, const orbx_proj_query* queries, int n_queries, int use_uright, int check_orientation, int th_high,
+                                    int* match, int* n_matches) {
+    if (!b) return fail(ORBX_ERR_ARG, "null handle");
+    if (n_queries < 0 || (n_queries && !queries) || !match || !n_matches) return fail(ORBX_ERR_ARG, "bad search arguments");
+    if (image < 0 || image >= b->gridImages) return fail(ORBX_ERR_ARG, "image has no feature grid (run orbx_batch_assign_grid first)");
+    if (n_queries > 65535) return fail(ORBX_ERR_TOO_LARGE, "more than 65535 map points in one search");
+    DeviceGuard dg(b->device);
+    const int K = b->g.K;
+    const size_t budget = 200 * 1024, fixed = search_smem_bytes(K, n_queries, 0);
+    if (fixed + 4096 > budget) return fail(ORBX_ERR_TOO_LARGE, "keypoint capacity / number of map points too large for the search kernel's shared memory");
+    const int candCap = (int)((budget - fixed) / 4);
+    if (!b->spConfigured) { CU(search_configure()); b->spConfigured = true; }
+    if (!b->spOut) CU(cudaMalloc(&b->spOut, ((size_t)K + 2) * sizeof(int)));
+    if ((size_t)n_queries > b->spCap) {
+        if (b->spDev) cudaFree(b->spDev);
+        b->spDev = nullptr; b->spCap = 0;
+        CU(cudaMalloc(&b->spDev, (size_t)n_queries * sizeof(orbx_proj_query)));
+        b->spCap = (size_t)n_queries;
+    }
+    if (n_queries) CU(cudaMemcpyAsync(b->spDev, queries, (size_t)n_queries * sizeof(orbx_proj_query), cudaMemcpyHostToDevice, b->stream));
+    Buffers buf = b->buf;
+    buf.imgBase = 0;
+    launch_search_by_projection(buf, image, K, b->gridParams, b->spDev, n_queries, use_uright ? 1 : 0, check_orientation ? 1 : 0, th_high, candCap, b->spOut,
+                                b->spOut + K, b->stream);
+    CU(cudaGetLastError());
+    int info[2] = {0, 0};
+    CU(cudaMemcpyAsync(match, b->spOut, (size_t)K * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaMemcpyAsync(info, b->spOut + K, 2 * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    if (info[0] < 0) return fail(ORBX_ERR_CAPACITY, "the search windows hold more candidates than the kernel's shared memory (smaller th / fewer points)");
+    *n_matches = info[0];
     return ORBX_OK;
 }
 

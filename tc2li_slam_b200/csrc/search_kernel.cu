@@ -1,0 +1,234 @@
+// search_kernel.cu — the search of ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono)
+// (ORBmatcher.cc:1685-1895) on the device, from the point where a map point has been projected (ORBmatcher.cc:1729 on), for the
+// single-grid case (CurrentFrame.Nleft == -1).  The pose algebra in front of it (Sophus / Eigen: Tcw * x3Dw, project, the
+// bForward / bBackward decision) stays with the caller, who sends one orbx_proj_query per surviving map point; keypoints,
+// descriptors, right coordinates (orbx_batch_stereo_match) and the feature grid (orbx_batch_assign_grid) are already resident.
+//
+// One CTA per call (a frame).  Phase 1, a warp per query, twice over the same candidate walk (Frame::GetFeaturesInArea order,
+// see grid_kernel.cu): first the candidate counts, then — after a block scan gave every query its slice of a shared-memory
+// CSR — the candidates themselves as (Hamming distance << 16 | keypoint index), with the right-coordinate gate
+// (ORBmatcher.cc:1760-1766) applied.  Phase 2 is the reference's own sequential dependency: a keypoint taken by a point with
+// observations is skipped by every later point (ORBmatcher.cc:1756-1758), so one warp walks the queries in order, lanes over
+// the candidates of a query, first minimum by a (distance, position) key, acceptance at bestDist <= TH_HIGH; everything it
+// touches is in shared memory.  Phase 3: rotation histogram, ORBmatcher::ComputeThreeMaxima (ORBmatcher.cc:2021-2062), removal
+// of the matches outside the three dominant bins (ORBmatcher.cc:1872-1892).  Integer work except the window arithmetic, which
+// follows the reference operation by operation in float32.
+#include <algorithm>
+
+#include "orbx_internal.cuh"
+
+namespace orbx {
+
+namespace {
+
+constexpr int ST = 256;  // threads per CTA
+constexpr int GC = ORBX_GRID_COLS, GR = ORBX_GRID_ROWS, NC = GC * GR;
+constexpr int HISTO = 30;  // ORBmatcher::HISTO_LENGTH (ORBmatcher.cc:46)
+
+struct Window {
+    int minCX, maxCX, minCY, maxCY;
+    bool empty;
+};
+
+__device__ __forceinline__ Window window_of(float x, float y, float r, const GridParams& p) {  // Frame.cc:695-717
+    Window w;
+    w.minCX = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, p.minX), r), p.invW)));
+    w.maxCX = min(GC - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, p.minX), r), p.invW)));
+    w.minCY = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, p.minY), r), p.invH)));
+    w.maxCY = min(GR - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, p.minY), r), p.invH)));
+    w.empty = w.minCX >= GC || w.maxCX < 0 || w.minCY >= GR || w.maxCY < 0;
+    return w;
+}
+
+// the candidate walk of one query by one warp; EMIT = false: count only.  Returns the number of candidates (after the gate).
+template <bool EMIT>
+__device__ __forceinline__ int walk(const orbx_proj_query& Q, const Window& W, const int* __restrict__ gs, const int* __restrict__ gi,
+                                    const orbx_keypoint* __restrict__ kps, const uint8_t* __restrict__ desc, const float* __restrict__ uRight, uint32_t* out,
+                                    int lane) {
+    if (W.empty) return 0;
+    const bool checkLevels = Q.min_level > 0 || Q.max_level >= 0;
+    uint32_t qd[8];
+    if (EMIT) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) qd[k] = reinterpret_cast<const uint32_t*>(Q.desc)[k];
+    }
+    int n = 0;
+    for (int ix = W.minCX; ix <= W.maxCX; ++ix) {
+        const int s = gs[ix * GR + W.minCY], e = gs[ix * GR + W.maxCY + 1];
+        for (int j0 = s; j0 < e; j0 += 32) {
+            const int j = j0 + lane;
+            bool hit = false;
+            int idx = 0;
+            if (j < e) {
+                idx = gi[j];
+                const orbx_keypoint kp = kps[idx];
+                bool lv = true;
+                if (checkLevels) lv = !(kp.octave < Q.min_level) && !(Q.max_level >= 0 && kp.octave > Q.max_level);
+                hit = lv && fabsf(__fsub_rn(kp.x, Q.u)) < Q.radius && fabsf(__fsub_rn(kp.y, Q.v)) < Q.radius;
+                if (hit && uRight) {  // CurrentFrame.mvuRight[i2] > 0: the predicted right coordinate must fall inside the window too
+                    const float ur2 = uRight[idx];
+                    if (ur2 > 0.f && fabsf(__fsub_rn(Q.ur, ur2)) > Q.radius) hit = false;
+                }
+            }
+            const unsigned bal = __ballot_sync(0xFFFFFFFFu, hit);
+            if (EMIT && hit) {
+                const uint4* d = reinterpret_cast<const uint4*>(desc + (size_t)idx * 32);
+                const uint4 a = d[0], c = d[1];
+                const int dist = __popc(a.x ^ qd[0]) + __popc(a.y ^ qd[1]) + __popc(a.z ^ qd[2]) + __popc(a.w ^ qd[3]) + __popc(c.x ^ qd[4]) + __popc(c.y ^ qd[5]) +
+                                 __popc(c.z ^ qd[6]) + __popc(c.w ^ qd[7]);
+                out[n + __popc(bal & ((1u << lane) - 1))] = ((uint32_t)dist << 16) | (uint32_t)idx;
+            }
+            n += __popc(bal);
+        }
+    }
+    return n;
+}
+
+}  // namespace
+
+// shared memory: match[K] | candStart[nq + 1] | cand[candCap] | entIdx[nq] (u16) | entBin[nq] (u8) | taken[K] (u8)
+__global__ void __launch_bounds__(ST) k_search_by_projection(const Buffers b, int image, int K, GridParams p, const orbx_proj_query* __restrict__ queries, int nq,
+                                                            int useURight, int checkOrientation, int thHigh, int candCap, int* __restrict__ outMatch,
+                                                            int* __restrict__ outInfo) {
+    extern __shared__ __align__(16) unsigned char ssm[];
+    __shared__ int warpSum[ST / 32];
+    __shared__ int hist[HISTO];
+    __shared__ int sInfo[4];  // nmatches, entries, total candidates, keep-bin mask
+    int* match = reinterpret_cast<int*>(ssm);
+    int* candStart = match + K;
+    uint32_t* cand = reinterpret_cast<uint32_t*>(candStart + nq + 1);
+    uint16_t* entIdx = reinterpret_cast<uint16_t*>(cand + candCap);
+    uint8_t* entBin = reinterpret_cast<uint8_t*>(entIdx + nq);
+    uint8_t* taken = entBin + nq;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n = b.outCount[image];
+    const int* gs = b.gridStart + (size_t)image * (NC + 1);
+    const int* gi = b.gridItems + (size_t)image * K;
+    const orbx_keypoint* kps = b.kps + (size_t)image * K;
+    const uint8_t* desc = b.desc + (size_t)image * K * 32;
+    const float* uRight = useURight ? b.uRight + (size_t)image * K : nullptr;
+    for (int k = tid; k < K; k += ST) { match[k] = -1; taken[k] = 0; }
+    if (tid < HISTO) hist[tid] = 0;
+    if (tid < 4) sInfo[tid] = 0;
+    // ---- phase 1a: candidate counts ----
+    for (int i = wid; i < nq; i += ST / 32) {
+        const orbx_proj_query Q = queries[i];
+        const int c = walk<false>(Q, window_of(Q.u, Q.v, Q.radius, p), gs, gi, kps, desc, uRight, nullptr, lane);
+        if (lane == 0) candStart[i] = c;
+    }
+    __syncthreads();
+    // exclusive scan of the counts (chunks of ST with a running carry)
+    int carry = 0;
+    for (int base = 0; base < nq; base += ST) {
+        const int i = base + tid;
+        const int v = i < nq ? candStart[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warpSum[wid] = incl;
+        __syncthreads();
+        int off = carry;
+        for (int w = 0; w < wid; ++w) off += warpSum[w];
+        if (i < nq) candStart[i] = off + incl - v;
+        int tot = 0;
+        for (int w = 0; w < ST / 32; ++w) tot += warpSum[w];
+        carry += tot;
+        __syncthreads();
+    }
+    if (tid == 0) { candStart[nq] = carry; sInfo[2] = carry; }
+    __syncthreads();
+    const int total = carry;
+    if (total > candCap) {  // the caller sees the needed capacity and fails with ORBX_ERR_CAPACITY
+        if (tid == 0) { outInfo[0] = -1; outInfo[1] = total; }
+        return;
+    }
+    // ---- phase 1b: the candidates, in visiting order, with their distances ----
+    for (int i = wid; i < nq; i += ST / 32) {
+        const orbx_proj_query Q = queries[i];
+        walk<true>(Q, window_of(Q.u, Q.v, Q.radius, p), gs, gi, kps, desc, uRight, cand + candStart[i], lane);
+    }
+    __syncthreads();
+    // ---- phase 2: the reference's loop over the map points, in order (one warp) ----
+    if (wid == 0) {
+        int nm = 0, ne = 0;
+        for (int i = 0; i < nq; ++i) {
+            const int s = candStart[i], e = candStart[i + 1];
+            if (s == e) continue;
+            uint32_t best = 0xFFFFFFFFu;  // (distance << 16 | position): the first of the smallest distances
+            for (int c0 = s; c0 < e; c0 += 32) {
+                const int c = c0 + lane;
+                if (c < e) {
+                    const uint32_t en = cand[c];
+                    const int idx = (int)(en & 0xFFFFu);
+                    if (!(match[idx] >= 0 && taken[idx])) best = min(best, (en & 0xFFFF0000u) | (uint32_t)(c - s));
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xFFFFFFFFu, best, o));
+            if (best != 0xFFFFFFFFu && (int)(best >> 16) <= thHigh) {
+                const int idx = (int)(cand[s + (int)(best & 0xFFFFu)] & 0xFFFFu);
+                if (lane == 0) {
+                    match[idx] = i;
+                    taken[idx] = queries[i].blocks != 0;
+                    if (checkOrientation) {
+                        float rot = __fsub_rn(queries[i].angle, kps[idx].angle);  // ORBmatcher.cc:1793-1798
+                        if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+                        int bin = (int)roundf(__fmul_rn(rot, 1.0f / HISTO));
+                        if (bin == HISTO) bin = 0;
+                        entIdx[ne] = (uint16_t)idx;
+                        entBin[ne] = (uint8_t)bin;
+                        ++hist[bin];
+                    }
+                }
+                ++nm;
+                ++ne;
+                __syncwarp();
+            }
+        }
+        if (lane == 0) { sInfo[0] = nm; sInfo[1] = checkOrientation ? ne : 0; }
+    }
+    __syncthreads();
+    // ---- phase 3: rotation consistency ----
+    if (checkOrientation) {
+        if (tid == 0) {  // ORBmatcher::ComputeThreeMaxima
+            int ind1 = -1, ind2 = -1, ind3 = -1, max1 = 0, max2 = 0, max3 = 0;
+            for (int i = 0; i < HISTO; ++i) {
+                const int sz = hist[i];
+                if (sz > max1) { max3 = max2; max2 = max1; max1 = sz; ind3 = ind2; ind2 = ind1; ind1 = i; }
+                else if (sz > max2) { max3 = max2; max2 = sz; ind3 = ind2; ind2 = i; }
+                else if (sz > max3) { max3 = sz; ind3 = i; }
+            }
+            if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+            else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) ind3 = -1;
+            int keep = 0;
+            if (ind1 >= 0) keep |= 1 << ind1;
+            if (ind2 >= 0) keep |= 1 << ind2;
+            if (ind3 >= 0) keep |= 1 << ind3;
+            sInfo[3] = keep;
+        }
+        __syncthreads();
+        const int keep = sInfo[3], ne = sInfo[1];
+        for (int k = tid; k < ne; k += ST)
+            if (!((keep >> entBin[k]) & 1)) {
+                match[entIdx[k]] = -1;
+                atomicSub(&sInfo[0], 1);
+            }
+        __syncthreads();
+    }
+    for (int k = tid; k < K; k += ST) outMatch[k] = k < n ? match[k] : -1;
+    if (tid == 0) { outInfo[0] = sInfo[0]; outInfo[1] = total; }
+}
+
+size_t search_smem_bytes(int K, int nq, int candCap) { return (size_t)K * 4 + ((size_t)nq + 1) * 4 + (size_t)candCap * 4 + (size_t)nq * 2 + (size_t)nq + (size_t)K + 16; }
+
+cudaError_t search_configure() { return cudaFuncSetAttribute(k_search_by_projection, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); }
+
+void launch_search_by_projection(const Buffers& b, int image, int K, const GridParams& p, const orbx_proj_query* queries, int nq, int useURight, int checkOrientation,
+                                 int thHigh, int candCap, int* outMatch, int* outInfo, cudaStream_t s) {
+    k_search_by_projection<<<1, ST, search_smem_bytes(K, nq, candCap), s>>>(b, image, K, p, queries, nq, useURight, checkOrientation, thHigh, candCap, outMatch, outInfo);
+}
+
+}  // namespace orbx

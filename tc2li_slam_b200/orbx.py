@@ -91,6 +91,7 @@ def lib():
         "orbx_batch_assign_grid": (i, [_vp, i, f, f, f, f]),
         "orbx_batch_download_grid": (i, [_vp, i, _vp, _vp]),
         "orbx_batch_features_in_area": (i, [_vp, _vp, i, i, _vp, _vp]),
+        "orbx_batch_search_by_projection": (i, [_vp, i, _vp, i, i, i, i, _vp, _vp]),
         "orbx_batch_run_range": (i, [_vp, i, i, _vp]),
         "orbx_batch_run_pipelined": (i, [_vp, i, _vp, i]),
         "orbx_batch_download_async": (i, [_vp, i, i, _vp, _vp, _vp, _vp]),
@@ -454,6 +455,10 @@ GRID_COLS, GRID_ROWS = 64, 48  # ORBX_GRID_COLS / ORBX_GRID_ROWS = FRAME_GRID_CO
 AREA_QUERY_DTYPE = np.dtype([("image", "<i4"), ("x", "<f4"), ("y", "<f4"), ("r", "<f4"), ("min_level", "<i4"), ("max_level", "<i4")])  # orbx_area_query
 
 
+PROJ_QUERY_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("radius", "<f4"), ("ur", "<f4"), ("min_level", "<i4"), ("max_level", "<i4"), ("angle", "<f4"),
+                             ("blocks", "<i4"), ("desc", "u1", (32,))])  # orbx_proj_query
+
+
 class BatchExtractor:
     """Many images of one shape per launch set (BASELINE.json configs[4]); frames x {left,right} are consecutive images."""
 
@@ -597,6 +602,16 @@ class BatchExtractor:
         counts, idx = np.empty(len(q), np.int32), np.empty((len(q), int(capacity)), np.int32)
         _check(lib().orbx_batch_features_in_area(self._h, _p(q), len(q), int(capacity), _p(counts), _p(idx)))
         return counts, idx
+
+    def search_by_projection(self, image, queries, use_uright=True, check_orientation=True, th_high=100):
+        """The search of ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) from ORBmatcher.cc:1729 on, against the resident
+        image `image` (after run(), assign_grid() and — for use_uright — stereo_match()).  queries: PROJ_QUERY_DTYPE records, one per
+        projected map point in LastFrame order.  Returns (match int32 [K]: query index per keypoint or -1, nmatches)."""
+        q = np.ascontiguousarray(np.asarray(queries, dtype=PROJ_QUERY_DTYPE))
+        match, nm = np.empty(self.K, np.int32), C.c_int(0)
+        _check(lib().orbx_batch_search_by_projection(self._h, int(image), _p(q), len(q), int(bool(use_uright)), int(bool(check_orientation)), int(th_high),
+                                                     _p(match), C.byref(nm)))
+        return match, nm.value
 
     def sync(self):
         _check(lib().orbx_batch_sync(self._h))

@@ -1,0 +1,94 @@
+"""The search of ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) on the device against the
+CPU oracle, which is pinned against the reference's own function body (tests/test_oracle_vs_ref.py::test_search_by_projection_*).
+CurrentFrame.mvpMapPoints (as query indices) and the returned match count must be identical."""
+import numpy as np
+import pytest
+
+import tc2li_slam_b200 as T
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+MB, MBF = 0.5372, 387.5744
+
+
+def make_case(bx, w, h, seed, shift, rng):
+    """Two images resident in `bx`: 0 = current left, 1 = current right; the map points come from the same scene shifted by `shift`."""
+    cur_l, cur_r = po.synth_v1(w, h, seed), po.synth_v1(w, h, seed, 16, 0x5bd1e995)
+    bx.upload(np.stack([cur_l, cur_r]))
+    bx.run(2)
+    bx.stereo_match(1, MB, MBF)
+    bx.assign_grid(2)
+    kp, de, cnt, _ = bx.download(2)
+    u, _ = bx.download_stereo(1)
+    kc, dc, ur = kp[0, :cnt[0]], de[0, :cnt[0]], u[0, :cnt[0]]
+    return kc, dc, ur
+
+
+def points_from(args, w, h, seed, shift, rng):
+    ex = po.OracleExtractor(*args)
+    _, kl, dl = ex(po.synth_v1(w, h, seed, shift))
+    n = len(kl)
+    pts = np.zeros((n, 4), np.float32)
+    pts[:, 0] = kl["x"] - np.float32(shift) + rng.normal(0, 1.5, n).astype(np.float32)
+    pts[:, 1] = kl["y"] + rng.normal(0, 1.5, n).astype(np.float32)
+    pts[:, 2] = rng.uniform(2, 60, n).astype(np.float32)
+    pts[:, 3] = kl["angle"]
+    pts[::7, 3] = (kl["angle"][::7] + rng.uniform(0, 360, len(kl[::7])).astype(np.float32)) % np.float32(360)
+    nobs = rng.choice([0, 1, 3], n, p=[0.2, 0.3, 0.5]).astype(np.int32)
+    pd = dl.copy()
+    flip = rng.random((n, 32)) < 0.02
+    pd ^= (flip * rng.integers(1, 256, (n, 32))).astype(np.uint8)
+    return pts, kl["octave"].astype(np.int32), nobs, pd, ex.tables()["scale_factors"]
+
+
+@pytest.mark.parametrize("w,h,args,seed,th,mode,check,use_ur", [(1241, 376, (2000, 1.2, 8, 20, 7), 1, 15.0, 0, True, True), (1241, 376, (2000, 1.2, 8, 20, 7), 2, 7.0, 0, True, True),
+                                                                 (1241, 376, (2000, 1.2, 8, 20, 7), 3, 15.0, 1, True, True), (1241, 376, (2000, 1.2, 8, 20, 7), 4, 15.0, 2, True, False),
+                                                                 (752, 480, (1200, 1.2, 8, 20, 7), 5, 30.0, 0, False, True), (640, 200, (500, 1.2, 6, 20, 7), 6, 15.0, 0, True, True),
+                                                                 (1920, 1080, (4000, 1.2, 8, 20, 7), 7, 15.0, 0, True, True)])
+def test_projection_search_matches_oracle(w, h, args, seed, th, mode, check, use_ur):
+    rng = np.random.default_rng(seed)
+    bx = T.BatchExtractor(w, h, 2, *args)
+    kc, dc, ur = make_case(bx, w, h, seed, 5, rng)
+    pts, octv, nobs, pd, sf = points_from(args, w, h, seed, 5, rng)
+    bounds = (0.0, float(w), 0.0, float(h))
+    q = po.make_proj_queries(pts, octv, nobs, pd, sf, th, MBF, mode)
+    om, on = po.search_by_projection(kc, dc, ur if use_ur else None, po.assign_grid(kc, bounds), bounds, q, check)
+    for _ in range(2):
+        m, nm = bx.search_by_projection(0, q.view(T.PROJ_QUERY_DTYPE), use_ur, check)
+        assert nm == on and on > 0.1 * len(q), (nm, on)
+        assert np.array_equal(m[:len(kc)], om), int((m[:len(kc)] != om).sum())
+        assert (m[len(kc):] == -1).all()
+    bx.close()
+
+
+def test_projection_search_edge_cases():
+    w, h, args = 640, 200, (500, 1.2, 6, 20, 7)
+    rng = np.random.default_rng(0)
+    bx = T.BatchExtractor(w, h, 2, *args)
+    q1 = np.zeros(1, T.PROJ_QUERY_DTYPE)
+    q1["radius"], q1["min_level"], q1["max_level"] = 10.0, -1, -1
+    with pytest.raises(T.OrbxError):  # no grid yet
+        bx.search_by_projection(0, q1)
+    kc, dc, ur = make_case(bx, w, h, 11, 5, rng)
+    m, nm = bx.search_by_projection(0, np.zeros(0, T.PROJ_QUERY_DTYPE))
+    assert nm == 0 and (m == -1).all()
+    # all points on one keypoint: only the first blocking point may keep it; a non-blocking point in front is overwritten
+    j = len(kc) // 2
+    q = np.zeros(4, T.PROJ_QUERY_DTYPE)
+    q["u"], q["v"], q["radius"], q["ur"] = kc["x"][j], kc["y"][j], 0.75, -1000.0
+    q["min_level"], q["max_level"], q["angle"] = -1, -1, kc["angle"][j]
+    q["desc"] = dc[j]
+    q["blocks"] = [0, 1, 1, 0]
+    bounds = (0.0, float(w), 0.0, float(h))
+    om, on = po.search_by_projection(kc, dc, None, po.assign_grid(kc, bounds), bounds, q, False)
+    m, nm = bx.search_by_projection(0, q, False, False)
+    assert nm == on and np.array_equal(m[:len(kc)], om)
+    assert om[j] == 1 and on >= 2
+    # a window far outside the image and a point whose descriptor is too far from everything
+    q2 = q[:2].copy()
+    q2["u"][0] = 5000.0
+    q2["desc"][1] = ~dc[j]
+    m, nm = bx.search_by_projection(0, q2, False, True)
+    om, on = po.search_by_projection(kc, dc, None, po.assign_grid(kc, bounds), bounds, q2, True)
+    assert nm == on and np.array_equal(m[:len(kc)], om)
+    bx.close()

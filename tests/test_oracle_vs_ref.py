@@ -162,3 +162,41 @@ def test_feature_grid_two_grid_case_is_one_grid_per_image():
             x, y, r = float(rng.uniform(-30, 780)), float(rng.uniform(-30, 510)), float(rng.choice([3, 10, 25, 80]))
             lv = [(-1, -1), (1, 4), (0, 2), (5, -1)][q % 4]
             assert np.array_equal(ref.features_in_area(x, y, r, *lv, right=right), po.features_in_area(k, (os_, oi), bounds, x, y, r, *lv)), (right, q)
+
+
+# ---- the search of ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) against the reference's own function body ----
+def projection_case(seed, w=1241, h=376, args=(2000, 1.2, 8, 20, 7), shift=5):
+    """Current frame = a synthetic image; 'last frame' = the same scene `shift` px to the side: its keypoints become the map points
+    (position, octave, angle, descriptor), with random depth, observation counts (0 = temporal point that does not block) and noise."""
+    rng = np.random.default_rng(seed)
+    ex = po.OracleExtractor(*args)
+    _, kc, dc = ex(po.synth_v1(w, h, seed))
+    _, kl, dl = ex(po.synth_v1(w, h, seed, shift))
+    sf = ex.tables()["scale_factors"]
+    n = len(kl)
+    pts = np.zeros((n, 4), np.float32)
+    pts[:, 0] = kl["x"] - np.float32(shift) + rng.normal(0, 1.5, n).astype(np.float32)
+    pts[:, 1] = kl["y"] + rng.normal(0, 1.5, n).astype(np.float32)
+    pts[:, 2] = rng.uniform(2, 60, n).astype(np.float32)
+    pts[:, 3] = kl["angle"]
+    pts[::7, 3] = (kl["angle"][::7] + rng.uniform(0, 360, len(kl[::7])).astype(np.float32)) % np.float32(360)  # wrong orientation: rotation check
+    nobs = rng.choice([0, 1, 3], n, p=[0.2, 0.3, 0.5]).astype(np.int32)
+    pd = dl.copy()
+    flip = rng.random((n, 32)) < 0.02
+    pd ^= (flip * rng.integers(1, 256, (n, 32))).astype(np.uint8)
+    ur = np.where(rng.random(len(kc)) < 0.7, kc["x"] - rng.uniform(0.5, 40, len(kc)).astype(np.float32), np.float32(-1)).astype(np.float32)
+    return kc, dc, ur, (0.0, float(w), 0.0, float(h)), sf, pts, kl["octave"].astype(np.int32), nobs, pd
+
+
+@pytest.mark.skipif(not pyref.search_available(), reason="oracle/_ref/libref_search.so not built (needs /root/reference once)")
+@pytest.mark.parametrize("seed,th,mode,check", [(1, 15.0, 0, True), (2, 7.0, 0, True), (3, 15.0, 1, True), (4, 15.0, 2, True), (5, 30.0, 0, False), (6, 15.0, 0, True)])
+def test_search_by_projection_matches_reference_body(seed, th, mode, check):
+    kc, dc, ur, bounds, sf, pts, octv, nobs, pd = projection_case(seed)
+    mb, mbf = 0.5372, 387.5744
+    tlcz = {0: 0.0, 1: 2.0 * mb, 2: -2.0 * mb}[mode]
+    rm, rn = pyref.search_by_projection(kc, dc, ur, bounds, sf, mb, mbf, pts, octv, nobs, pd, th, tlcz, False, check)
+    grid = po.assign_grid(kc, bounds)
+    q = po.make_proj_queries(pts, octv, nobs, pd, sf, th, mbf, mode)
+    om, on = po.search_by_projection(kc, dc, ur, grid, bounds, q, check)
+    assert rn == on and rn > 300, (rn, on)
+    assert np.array_equal(rm, om), int((rm != om).sum())
