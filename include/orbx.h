@@ -229,6 +229,16 @@ typedef struct orbx_proj_query {
 } orbx_proj_query;
 int orbx_batch_search_by_projection(orbx_batch* b, int image, const orbx_proj_query* queries, int n_queries, int use_uright, int check_orientation, int th_high,
                                     int* match, int* n_matches);
+/* ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>& vpMapPoints, th, bFarPoints, thFarPoints) (ORBmatcher.cc:52-222), the
+ * local-map search of Tracking::SearchLocalPoints (Tracking.cc:3282), single-grid case.  One query per map point that passes the early tests
+ * (ORBmatcher.cc:61-70: mbTrackInView, the far-point test, isBad), in vpMapPoints order:
+ *   u, v = mTrackProjX, mTrackProjY;  radius = r * F.mvScaleFactors[nPredictedLevel], r = RadiusByViewingCos(mTrackViewCos) (* th if th != 1);
+ *   ur = mTrackProjXR;  min_level, max_level = nPredictedLevel - 1, nPredictedLevel;  blocks = Observations() > 0;  desc = GetDescriptor()  (angle unused).
+ * taken[k] != 0 (K host bytes, or NULL for none) where F.mvpMapPoints[k] holds a point with observations before the search.  nn_ratio =
+ * ORBmatcher::mfNNratio.  match[k] = index of the query this search writes into F.mvpMapPoints[k], -1 = left as it was; *n_matches = the
+ * reference's return value.  Same prerequisites as orbx_batch_search_by_projection; synchronises. */
+int orbx_batch_search_local_points(orbx_batch* b, int image, const orbx_proj_query* queries, int n_queries, int use_uright, float nn_ratio, int th_high,
+                                   const uint8_t* taken, int* match, int* n_matches);
 int orbx_batch_sync(orbx_batch* b);
 /* the same on a sub-range [first, first+n) of the handle's images (lapping: n x 2 ints for that range): lets a caller keep
  * many frames resident and process them in groups small enough for the 126 MB L2 */

@@ -900,6 +900,56 @@ int search_by_projection_tail(const KeyPoint* kps, int nKps, const uint8_t* desc
 }
 
 
+// ---------------------------------------------------------------------------------------------------------------------
+// ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>& vpMapPoints, th, bFarPoints, thFarPoints) (ORBmatcher.cc:52-222),
+// the local-map search of Tracking::SearchLocalPoints (Tracking.cc:3282), single-grid case (F.Nleft == -1).  Its body has no pose
+// algebra: the projections were stored in the map points by Frame::isInFrustum.  A query = one map point that passes the early
+// tests (:61-68, mbTrackInView): u, v = mTrackProjX / mTrackProjY; radius = r * F.mvScaleFactors[nPredictedLevel] with
+// r = RadiusByViewingCos(mTrackViewCos) (* th if th != 1) (:75-81); ur = mTrackProjXR; [minLevel, maxLevel] = [nPredictedLevel - 1,
+// nPredictedLevel]; blocks = Observations() > 0; desc = GetDescriptor().  taken0[k] != 0 where F.mvpMapPoints[k] already holds a point
+// with observations when the search starts.  Restated: candidate walk, taken skip (:95-97), right-coordinate gate (:99-104), best /
+// second-best distance with their levels in the reference's update order (:110-127), acceptance at bestDist <= TH_HIGH unless both
+// are on one level and bestDist > mfNNratio * bestDist2 (:131-137).  match[k] = query index written to F.mvpMapPoints[k] by THIS
+// search, -1 = left as it was.
+// ---------------------------------------------------------------------------------------------------------------------
+int search_local_points(const KeyPoint* kps, int nKps, const uint8_t* desc, const float* uRight, const uint8_t* taken0, const int* cellStart, const int* items,
+                        float minX, float maxX, float minY, float maxY, const ProjQuery* q, int nq, float nnRatio, int thHigh, int* match) {
+    std::vector<int> cand((size_t)std::max(nKps, 1));
+    std::vector<char> taken((size_t)std::max(nKps, 1), 0);
+    for (int k = 0; k < nKps; ++k) { match[k] = -1; taken[k] = taken0 ? (taken0[k] != 0) : 0; }
+    int nmatches = 0;
+    for (int i = 0; i < nq; ++i) {
+        const ProjQuery& Q = q[i];
+        const int nc = features_in_area(kps, cellStart, items, minX, maxX, minY, maxY, Q.u, Q.v, Q.radius, Q.minLevel, Q.maxLevel, cand.data(), nKps);
+        if (nc == 0) continue;
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        for (int c = 0; c < nc; ++c) {
+            const int idx = cand[c];
+            if (taken[idx]) continue;
+            if (uRight && uRight[idx] > 0) {
+                const float er = std::fabs(Q.ur - uRight[idx]);
+                if (er > Q.radius) continue;
+            }
+            const int dist = hamming256(Q.desc, desc + (size_t)idx * 32);
+            if (dist < bestDist) {
+                bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = kps[idx].octave; bestIdx = idx;
+            } else if (dist < bestDist2) {
+                bestLevel2 = kps[idx].octave; bestDist2 = dist;
+            }
+        }
+        if (bestDist <= thHigh) {
+            if (bestLevel == bestLevel2 && (float)bestDist > nnRatio * (float)bestDist2) continue;
+            if (bestLevel != bestLevel2 || (float)bestDist <= nnRatio * (float)bestDist2) {
+                match[bestIdx] = i;
+                taken[bestIdx] = Q.blocks != 0;
+                ++nmatches;
+            }
+        }
+    }
+    return nmatches;
+}
+
+
 extern "C" {
 void* orbo_create(int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh) {
     return new Extractor(nfeatures, scaleFactor, nlevels, iniTh, minTh);
@@ -959,6 +1009,10 @@ int orbo_search_by_projection(const void* kps, int nKps, const uint8_t* desc, co
                               float maxX, float minY, float maxY, const void* q, int nq, int checkOrientation, int thHigh, int* match) {
     return search_by_projection_tail((const KeyPoint*)kps, nKps, desc, uRight, cellStart, items, minX, maxX, minY, maxY, (const ProjQuery*)q, nq, checkOrientation,
                                      thHigh, match);
+}
+int orbo_search_local_points(const void* kps, int nKps, const uint8_t* desc, const float* uRight, const uint8_t* taken0, const int* cellStart, const int* items,
+                             float minX, float maxX, float minY, float maxY, const void* q, int nq, float nnRatio, int thHigh, int* match) {
+    return search_local_points((const KeyPoint*)kps, nKps, desc, uRight, taken0, cellStart, items, minX, maxX, minY, maxY, (const ProjQuery*)q, nq, nnRatio, thHigh, match);
 }
 void orbo_lapping_match(const uint8_t* dl, int nq, const uint8_t* dr, int nt, int* out, uint8_t* ok) { lapping_knn_match(dl, nq, dr, nt, out, ok); }
 void orbo_cvt_gray(const uint8_t* src, int w, int h, int sstride, int channels, int rgb, uint8_t* dst, int dstride) {

@@ -51,6 +51,7 @@ def lib():
         L.orbo_assign_grid.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
         L.orbo_features_in_area.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_float] * 7 + [C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.orbo_search_by_projection.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_float] * 4 + [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.orbo_search_local_points.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_float] * 4 + [C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p]
         L.orbo_lapping_match.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.orbo_cvt_gray.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.orbo_remap.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
@@ -218,6 +219,43 @@ def search_by_projection(kps, desc, uright, grid, bounds, queries, check_orienta
     match = np.empty(max(len(kps), 1), np.int32)
     nm = lib().orbo_search_by_projection(_p(kps), len(kps), _p(desc), None if ur is None else _p(ur), _p(start), _p(items), *[float(v) for v in bounds], _p(q), len(q),
                                          int(bool(check_orientation)), int(th_high), _p(match))
+    return match[:len(kps)], nm
+
+
+def make_local_queries(points, levels, nobs, flags, point_desc, scale_factors, th, far_points=False, th_far=50.0):
+    """The map points ORBmatcher::SearchByProjection(F, vpMapPoints, th, ...) actually searches for (ORBmatcher.cc:58-81), as queries, in the
+    reference's float arithmetic.  Returns (queries, index of each query in the input list)."""
+    pts = np.ascontiguousarray(points, np.float32).reshape(-1, 5)
+    lv, fl = np.ascontiguousarray(levels, np.int32), np.ascontiguousarray(flags, np.int32)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    keep = ((fl & 1) != 0) & ((fl & 2) == 0)
+    if far_points:
+        keep &= ~(pts[:, 4] > np.float32(th_far))
+    sel = np.nonzero(keep)[0]
+    q = np.zeros(len(sel), PROJ_QUERY_DTYPE)
+    r = np.where(pts[sel, 3] > 0.998, np.float32(2.5), np.float32(4.0)).astype(np.float32)  # RadiusByViewingCos: float viewCos against the double 0.998
+    if th != 1.0:
+        r = r * np.float32(th)
+    q["u"], q["v"], q["ur"] = pts[sel, 0], pts[sel, 1], pts[sel, 2]
+    q["radius"] = r * sf[lv[sel]]
+    q["min_level"], q["max_level"] = lv[sel] - 1, lv[sel]
+    q["blocks"] = np.ascontiguousarray(nobs, np.int32)[sel] > 0
+    q["desc"] = np.ascontiguousarray(point_desc, np.uint8).reshape(-1, 32)[sel]
+    return q, sel
+
+
+def search_local_points(kps, desc, uright, taken0, grid, bounds, queries, nn_ratio=0.8, th_high=100):
+    """ORBmatcher::SearchByProjection(F, vpMapPoints, ...) (ORBmatcher.cc:52-222) on prepared queries (see orb_oracle.cpp).
+    Returns (match int32 [n]: query index assigned by this search or -1, nmatches)."""
+    kps = np.ascontiguousarray(kps)
+    desc = np.ascontiguousarray(desc, np.uint8)
+    start, items = np.ascontiguousarray(grid[0], np.int32), np.ascontiguousarray(grid[1], np.int32)
+    q = np.ascontiguousarray(queries, PROJ_QUERY_DTYPE)
+    ur = None if uright is None else np.ascontiguousarray(uright, np.float32)
+    t0 = None if taken0 is None else np.ascontiguousarray(taken0, np.uint8)
+    match = np.empty(max(len(kps), 1), np.int32)
+    nm = lib().orbo_search_local_points(_p(kps), len(kps), _p(desc), None if ur is None else _p(ur), None if t0 is None else _p(t0), _p(start), _p(items),
+                                        *[float(v) for v in bounds], _p(q), len(q), float(nn_ratio), int(th_high), _p(match))
     return match[:len(kps)], nm
 
 

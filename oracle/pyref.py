@@ -195,3 +195,29 @@ def search_by_projection(kps, desc, uright, bounds, scale_factors, mb, mbf, poin
     nm = _splib.refsp_search(_p(kps), len(kps), _p(desc), _p(ur), *[float(v) for v in bounds], _p(sf), len(sf), float(mb), float(mbf), _p(pts), _p(octv), _p(nob),
                              _p(pd), len(pts), float(th), float(tlcz), int(bool(mono)), int(bool(check_orientation)), _p(match))
     return match[:len(kps)], nm
+
+
+def search_local_points(kps, desc, uright, taken0, bounds, scale_factors, points, levels, nobs, flags, point_desc, th, nn_ratio, far_points=False, th_far=50.0):
+    """The reference's own ORBmatcher::SearchByProjection(F, vpMapPoints, th, bFarPoints, thFarPoints) (ORBmatcher.cc:52-222), single-grid case.
+    points: float32 [nq, 5] = (mTrackProjX, mTrackProjY, mTrackProjXR, mTrackViewCos, mTrackDepth); flags bit 0 = mbTrackInView, bit 1 = isBad();
+    taken0[k]: 0 = F.mvpMapPoints[k] is NULL, 1 = holds a point with observations, 2 = holds one without.  Returns (match int32 [n], nmatches)."""
+    search_by_projection.__doc__  # (loads nothing; the library handle is shared below)
+    global _splib
+    if _splib is None:
+        _splib = C.CDLL(_LIB_SEARCH)
+        _splib.refsp_search.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p] + [C.c_float] * 4 + [C.c_void_p, C.c_int, C.c_float, C.c_float,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p]
+    _splib.refsp_search_local.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_float] * 4 + [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float, C.c_void_p]
+    kps = np.ascontiguousarray(kps)
+    desc = np.ascontiguousarray(desc, np.uint8)
+    ur = np.ascontiguousarray(uright, np.float32)
+    t0 = np.ascontiguousarray(taken0, np.uint8)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    pts = np.ascontiguousarray(points, np.float32).reshape(-1, 5)
+    lv, nob, fl = np.ascontiguousarray(levels, np.int32), np.ascontiguousarray(nobs, np.int32), np.ascontiguousarray(flags, np.int32)
+    pd = np.ascontiguousarray(point_desc, np.uint8).reshape(-1, 32)
+    match = np.empty(max(len(kps), 1), np.int32)
+    nm = _splib.refsp_search_local(_p(kps), len(kps), _p(desc), _p(ur), _p(t0), *[float(v) for v in bounds], _p(sf), len(sf), _p(pts), _p(lv), _p(nob), _p(fl), _p(pd),
+                                   len(pts), float(th), float(nn_ratio), int(bool(far_points)), float(th_far), _p(match))
+    return match[:len(kps)], nm

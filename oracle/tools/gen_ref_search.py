@@ -30,7 +30,9 @@ def main():
                     cut_function(frame, "vector<size_t> Frame::GetFeaturesInArea(")]
     matcher_bodies = [cut_function(matcher, "int ORBmatcher::DescriptorDistance(const cv::Mat &a, const cv::Mat &b)"),
                       cut_function(matcher, "void ORBmatcher::ComputeThreeMaxima(vector<int>* histo, const int L, int &ind1, int &ind2, int &ind3)"),
-                      cut_function(matcher, "int ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono)")]
+                      cut_function(matcher, "int ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono)"),
+                      cut_function(matcher, "float ORBmatcher::RadiusByViewingCos(const float &viewCos)"),
+                      cut_function(matcher, "int ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, const float th, const bool bFarPoints, const float thFarPoints)")]
     glue_top = r'''
 #include <algorithm>
 #include <cassert>
@@ -57,6 +59,11 @@ struct SE3f {
 namespace TC2LI_SLAM {
 struct MapPoint {
     Eigen::Vector3f pos; cv::Mat desc; int nObs;
+    // what Frame::isInFrustum leaves in a map point for the local-map search (MapPoint.h)
+    bool mbTrackInView = false, mbTrackInViewR = false, bad = false;
+    float mTrackProjX = 0, mTrackProjY = 0, mTrackDepth = 0, mTrackDepthR = 0, mTrackProjXR = 0, mTrackProjYR = 0, mTrackViewCos = 0, mTrackViewCosR = 0;
+    int mnTrackScaleLevel = 0, mnTrackScaleLevelR = -1;
+    bool isBad() { return bad; }
     Eigen::Vector3f GetWorldPos() { return pos; }
     cv::Mat GetDescriptor() { return desc; }
     int Observations() { return nObs; }
@@ -68,6 +75,7 @@ struct Frame {
     std::vector<MapPoint*> mvpMapPoints;
     std::vector<bool> mvbOutlier;
     std::vector<float> mvuRight, mvScaleFactors;
+    std::vector<int> mvLeftToRightMatch, mvRightToLeftMatch;
     cv::Mat mDescriptors;
     float mb, mbf;
     GeometricCamera* mpCamera;
@@ -89,6 +97,8 @@ struct ORBmatcher {
     static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b);
     void ComputeThreeMaxima(std::vector<int>* histo, const int L, int &ind1, int &ind2, int &ind3);
     int SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono);
+    int SearchByProjection(Frame &F, const std::vector<MapPoint*> &vpMapPoints, const float th=3, const bool bFarPoints = false, const float thFarPoints = 50.0f);
+    float RadiusByViewingCos(const float &viewCos);
 };
 ''' + consts + "\n"
     glue_bottom = r'''
@@ -130,6 +140,48 @@ extern "C" int refsp_search(const void* kps, int n, const unsigned char* desc, c
     m.mfNNratio = 0.9f; m.mbCheckOrientation = checkOrientation != 0;
     const int nm = m.SearchByProjection(cur, last, th, bMono != 0);
     for (int k = 0; k < n; ++k) match[k] = cur.mvpMapPoints[k] ? (int)(cur.mvpMapPoints[k] - pts.data()) : -1;
+    return nm;
+}
+'''
+    glue_bottom += r'''
+// local-map overload: points: nq x {mTrackProjX, mTrackProjY, mTrackProjXR, mTrackViewCos, mTrackDepth} floats; levels / nobs / flags: nq ints
+// (flags: bit 0 = mbTrackInView, bit 1 = isBad()); taken0[k] != 0: F.mvpMapPoints[k] holds a point with observations before the search
+extern "C" int refsp_search_local(const void* kps, int n, const unsigned char* desc, const float* uright, const unsigned char* taken0, float minX, float maxX,
+                                  float minY, float maxY, const float* scaleFactors, int nlevels, const float* points, const int* levels, const int* nobs,
+                                  const int* flags, const unsigned char* pdesc, int nq, float th, float nnRatio, int bFarPoints, float thFarPoints, int* match) {
+    Frame F;
+    F.N = n; F.Nleft = -1;
+    F.mvKeys.assign((const cv::KeyPoint*)kps, (const cv::KeyPoint*)kps + n);
+    F.mvKeysUn = F.mvKeys;
+    F.mvuRight.assign(uright, uright + n);
+    F.mvScaleFactors.assign(scaleFactors, scaleFactors + nlevels);
+    F.mDescriptors = cv::Mat(n, 32, CV_8U, (void*)desc, 32);
+    Frame::mnMinX = minX; Frame::mnMaxX = maxX; Frame::mnMinY = minY; Frame::mnMaxY = maxY;
+    Frame::mfGridElementWidthInv = static_cast<float>(FRAME_GRID_COLS) / (Frame::mnMaxX - Frame::mnMinX);
+    Frame::mfGridElementHeightInv = static_cast<float>(FRAME_GRID_ROWS) / (Frame::mnMaxY - Frame::mnMinY);
+    F.AssignFeaturesToGrid();
+    MapPoint held, heldFree;       // earlier matches of the frame: with / without observations
+    held.nObs = 1; heldFree.nObs = 0;
+    F.mvpMapPoints.assign(n, nullptr);
+    for (int k = 0; k < n; ++k) if (taken0[k]) F.mvpMapPoints[k] = taken0[k] == 1 ? &held : &heldFree;
+    std::vector<MapPoint> pts(nq);
+    std::vector<MapPoint*> vp(nq);
+    for (int i = 0; i < nq; ++i) {
+        MapPoint& P = pts[i];
+        P.mTrackProjX = points[5 * i]; P.mTrackProjY = points[5 * i + 1]; P.mTrackProjXR = points[5 * i + 2]; P.mTrackViewCos = points[5 * i + 3];
+        P.mTrackDepth = points[5 * i + 4];
+        P.mnTrackScaleLevel = levels[i]; P.nObs = nobs[i];
+        P.mbTrackInView = (flags[i] & 1) != 0; P.bad = (flags[i] & 2) != 0;
+        P.desc = cv::Mat(1, 32, CV_8U, (void*)(pdesc + 32 * (size_t)i), 32);
+        vp[i] = &P;
+    }
+    ORBmatcher m;
+    m.mfNNratio = nnRatio; m.mbCheckOrientation = true;
+    const int nm = m.SearchByProjection(F, vp, th, bFarPoints != 0, thFarPoints);
+    for (int k = 0; k < n; ++k) {
+        MapPoint* p = F.mvpMapPoints[k];
+        match[k] = (p && p != &held && p != &heldFree) ? (int)(p - pts.data()) : -1;
+    }
     return nm;
 }
 '''

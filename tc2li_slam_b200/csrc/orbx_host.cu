@@ -807,9 +807,9 @@ int orbx_batch_features_in_area(orbx_batch* b, const orbx_area_query* queries, i
     return ORBX_OK;
 }
 
-// ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) from ORBmatcher.cc:1729 on (see search_kernel.cu); synchronous
-int orbx_batch_search_by_projection(orbx_batch* b, int image, const orbx_proj_query* queries, int n_queries, int use_uright, int check_orientation, int th_high,
-                                    int* match, int* n_matches) {
+// both projection searches (search_kernel.cu); local = the local-map overload (taken: host bytes [K] or NULL); synchronous
+static int search_common(orbx_batch* b, bool local, int image, const orbx_proj_query* queries, int n_queries, int use_uright, int check_orientation, int th_high,
+                         float nn_ratio, const uint8_t* taken, int* match, int* n_matches) {
     if (!b) return fail(ORBX_ERR_ARG, "null handle");
     if (n_queries < 0 || (n_queries && !queries) || !match || !n_matches) return fail(ORBX_ERR_ARG, "bad search arguments");
     if (image < 0 || image >= b->gridImages) return fail(ORBX_ERR_ARG, "image has no feature grid (run orbx_batch_assign_grid first)");
@@ -820,7 +820,7 @@ int orbx_batch_search_by_projection(orbx_batch* b, int image, const orbx_proj_qu
     if (fixed + 4096 > budget) return fail(ORBX_ERR_TOO_LARGE, "keypoint capacity / number of map points too large for the search kernel's shared memory");
     const int candCap = (int)((budget - fixed) / 4);
     if (!b->spConfigured) { CU(search_configure()); b->spConfigured = true; }
-    if (!b->spOut) CU(cudaMalloc(&b->spOut, ((size_t)K + 2) * sizeof(int)));
+    if (!b->spOut) CU(cudaMalloc(&b->spOut, ((size_t)K + 2) * sizeof(int) + (size_t)K));  // match[K], info[2], taken0[K]
     if ((size_t)n_queries > b->spCap) {
         if (b->spDev) cudaFree(b->spDev);
         b->spDev = nullptr; b->spCap = 0;
@@ -828,10 +828,16 @@ int orbx_batch_search_by_projection(orbx_batch* b, int image, const orbx_proj_qu
         b->spCap = (size_t)n_queries;
     }
     if (n_queries) CU(cudaMemcpyAsync(b->spDev, queries, (size_t)n_queries * sizeof(orbx_proj_query), cudaMemcpyHostToDevice, b->stream));
+    uint8_t* takenDev = reinterpret_cast<uint8_t*>(b->spOut + K + 2);
+    if (local && taken) CU(cudaMemcpyAsync(takenDev, taken, (size_t)K, cudaMemcpyHostToDevice, b->stream));
     Buffers buf = b->buf;
     buf.imgBase = 0;
-    launch_search_by_projection(buf, image, K, b->gridParams, b->spDev, n_queries, use_uright ? 1 : 0, check_orientation ? 1 : 0, th_high, candCap, b->spOut,
-                                b->spOut + K, b->stream);
+    if (local)
+        launch_search_local_points(buf, image, K, b->gridParams, b->spDev, n_queries, use_uright ? 1 : 0, th_high, nn_ratio, taken ? takenDev : nullptr, candCap, b->spOut,
+                                   b->spOut + K, b->stream);
+    else
+        launch_search_by_projection(buf, image, K, b->gridParams, b->spDev, n_queries, use_uright ? 1 : 0, check_orientation ? 1 : 0, th_high, candCap, b->spOut,
+                                    b->spOut + K, b->stream);
     CU(cudaGetLastError());
     int info[2] = {0, 0};
     CU(cudaMemcpyAsync(match, b->spOut, (size_t)K * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
@@ -840,6 +846,18 @@ int orbx_batch_search_by_projection(orbx_batch* b, int image, const orbx_proj_qu
     if (info[0] < 0) return fail(ORBX_ERR_CAPACITY, "the search windows hold more candidates than the kernel's shared memory (smaller th / fewer points)");
     *n_matches = info[0];
     return ORBX_OK;
+}
+
+// ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) from ORBmatcher.cc:1729 on
+int orbx_batch_search_by_projection(orbx_batch* b, int image, const orbx_proj_query* queries, int n_queries, int use_uright, int check_orientation, int th_high,
+                                    int* match, int* n_matches) {
+    return search_common(b, false, image, queries, n_queries, use_uright, check_orientation, th_high, 0.f, nullptr, match, n_matches);
+}
+
+// ORBmatcher::SearchByProjection(F, vpMapPoints, th, bFarPoints, thFarPoints) (ORBmatcher.cc:52-222), the local-map search
+int orbx_batch_search_local_points(orbx_batch* b, int image, const orbx_proj_query* queries, int n_queries, int use_uright, float nn_ratio, int th_high,
+                                   const uint8_t* taken, int* match, int* n_matches) {
+    return search_common(b, true, image, queries, n_queries, use_uright, 0, th_high, nn_ratio, taken, match, n_matches);
 }
 
 // Descriptor stage of Frame::ComputeStereoFishEyeMatches (Frame.cc:1162-1187) for frames [0, n_frames): kNN (k = 2) of the left

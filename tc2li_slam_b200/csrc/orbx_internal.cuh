@@ -160,6 +160,9 @@ cudaError_t search_configure();
 void launch_search_by_projection(const Buffers& b, int image, int K, const GridParams& p, const orbx_proj_query* queries, int nq, int useURight, int checkOrientation,
                                  int thHigh, int candCap, int* outMatch, int* outInfo, cudaStream_t s);
 
+void launch_search_local_points(const Buffers& b, int image, int K, const GridParams& p, const orbx_proj_query* queries, int nq, int useURight, int thHigh, float nnRatio,
+                                const uint8_t* taken0, int candCap, int* outMatch, int* outInfo, cudaStream_t s);
+
 // debug / test hooks
 void launch_debug_sincos(const float* anglesDeg, float* outSin, float* outCos, int n, cudaStream_t s);
 void launch_debug_atan2(const float* y, const float* x, float* out, int n, cudaStream_t s);

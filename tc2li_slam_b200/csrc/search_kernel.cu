@@ -58,10 +58,11 @@ __device__ __forceinline__ int walk(const orbx_proj_query& Q, const Window& W, c
         for (int j0 = s; j0 < e; j0 += 32) {
             const int j = j0 + lane;
             bool hit = false;
-            int idx = 0;
+            int idx = 0, kpOctave = 0;
             if (j < e) {
                 idx = gi[j];
                 const orbx_keypoint kp = kps[idx];
+                kpOctave = kp.octave & 15;
                 bool lv = true;
                 if (checkLevels) lv = !(kp.octave < Q.min_level) && !(Q.max_level >= 0 && kp.octave > Q.max_level);
                 hit = lv && fabsf(__fsub_rn(kp.x, Q.u)) < Q.radius && fabsf(__fsub_rn(kp.y, Q.v)) < Q.radius;
@@ -76,7 +77,7 @@ __device__ __forceinline__ int walk(const orbx_proj_query& Q, const Window& W, c
                 const uint4 a = d[0], c = d[1];
                 const int dist = __popc(a.x ^ qd[0]) + __popc(a.y ^ qd[1]) + __popc(a.z ^ qd[2]) + __popc(a.w ^ qd[3]) + __popc(c.x ^ qd[4]) + __popc(c.y ^ qd[5]) +
                                  __popc(c.z ^ qd[6]) + __popc(c.w ^ qd[7]);
-                out[n + __popc(bal & ((1u << lane) - 1))] = ((uint32_t)dist << 16) | (uint32_t)idx;
+                out[n + __popc(bal & ((1u << lane) - 1))] = ((uint32_t)dist << 20) | ((uint32_t)kpOctave << 16) | (uint32_t)idx;
             }
             n += __popc(bal);
         }
@@ -87,9 +88,12 @@ __device__ __forceinline__ int walk(const orbx_proj_query& Q, const Window& W, c
 }  // namespace
 
 // shared memory: match[K] | candStart[nq + 1] | cand[candCap] | entIdx[nq] (u16) | entBin[nq] (u8) | taken[K] (u8)
+// LOCAL = false: frame-to-frame search (best distance, rotation check); LOCAL = true: local-map search (best / second best with
+// their levels and the mfNNratio test, keypoints taken before the search in taken0, no rotation check)
+template <bool LOCAL>
 __global__ void __launch_bounds__(ST) k_search_by_projection(const Buffers b, int image, int K, GridParams p, const orbx_proj_query* __restrict__ queries, int nq,
-                                                            int useURight, int checkOrientation, int thHigh, int candCap, int* __restrict__ outMatch,
-                                                            int* __restrict__ outInfo) {
+                                                            int useURight, int checkOrientation, int thHigh, float nnRatio, const uint8_t* __restrict__ taken0,
+                                                            int candCap, int* __restrict__ outMatch, int* __restrict__ outInfo) {
     extern __shared__ __align__(16) unsigned char ssm[];
     __shared__ int warpSum[ST / 32];
     __shared__ int hist[HISTO];
@@ -107,7 +111,7 @@ __global__ void __launch_bounds__(ST) k_search_by_projection(const Buffers b, in
     const orbx_keypoint* kps = b.kps + (size_t)image * K;
     const uint8_t* desc = b.desc + (size_t)image * K * 32;
     const float* uRight = useURight ? b.uRight + (size_t)image * K : nullptr;
-    for (int k = tid; k < K; k += ST) { match[k] = -1; taken[k] = 0; }
+    for (int k = tid; k < K; k += ST) { match[k] = -1; taken[k] = (LOCAL && taken0 && k < n) ? (taken0[k] != 0) : 0; }
     if (tid < HISTO) hist[tid] = 0;
     if (tid < 4) sInfo[tid] = 0;
     // ---- phase 1a: candidate counts ----
@@ -157,13 +161,36 @@ __global__ void __launch_bounds__(ST) k_search_by_projection(const Buffers b, in
         for (int i = 0; i < nq; ++i) {
             const int s = candStart[i], e = candStart[i + 1];
             if (s == e) continue;
+            if (LOCAL) {
+                // ORBmatcher.cc:85-137: the reference's update order decides who is "second best", so every lane replays the short
+                // candidate list as written (warp-uniform, shared-memory broadcasts, no shuffles)
+                int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+                for (int c = s; c < e; ++c) {
+                    const uint32_t en = cand[c];
+                    const int idx = (int)(en & 0xFFFFu);
+                    if (taken[idx]) continue;
+                    const int dist = (int)(en >> 20), level = (int)((en >> 16) & 15u);
+                    if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = level; bestIdx = idx; }
+                    else if (dist < bestDist2) { bestLevel2 = level; bestDist2 = dist; }
+                }
+                if (bestDist <= thHigh) {
+                    const float lim = __fmul_rn(nnRatio, (float)bestDist2);
+                    const bool ratioFail = bestLevel == bestLevel2 && (float)bestDist > lim;
+                    if (!ratioFail && (bestLevel != bestLevel2 || (float)bestDist <= lim)) {
+                        if (lane == 0) { match[bestIdx] = i; taken[bestIdx] = queries[i].blocks != 0; }
+                        ++nm;
+                        __syncwarp();
+                    }
+                }
+                continue;
+            }
             uint32_t best = 0xFFFFFFFFu;  // (distance << 16 | position): the first of the smallest distances
             for (int c0 = s; c0 < e; c0 += 32) {
                 const int c = c0 + lane;
                 if (c < e) {
                     const uint32_t en = cand[c];
                     const int idx = (int)(en & 0xFFFFu);
-                    if (!(match[idx] >= 0 && taken[idx])) best = min(best, (en & 0xFFFF0000u) | (uint32_t)(c - s));
+                    if (!taken[idx]) best = min(best, ((en >> 20) << 16) | (uint32_t)(c - s));
                 }
             }
 #pragma unroll
@@ -192,7 +219,7 @@ __global__ void __launch_bounds__(ST) k_search_by_projection(const Buffers b, in
     }
     __syncthreads();
     // ---- phase 3: rotation consistency ----
-    if (checkOrientation) {
+    if (!LOCAL && checkOrientation) {
         if (tid == 0) {  // ORBmatcher::ComputeThreeMaxima
             int ind1 = -1, ind2 = -1, ind3 = -1, max1 = 0, max2 = 0, max3 = 0;
             for (int i = 0; i < HISTO; ++i) {
@@ -224,11 +251,22 @@ __global__ void __launch_bounds__(ST) k_search_by_projection(const Buffers b, in
 
 size_t search_smem_bytes(int K, int nq, int candCap) { return (size_t)K * 4 + ((size_t)nq + 1) * 4 + (size_t)candCap * 4 + (size_t)nq * 2 + (size_t)nq + (size_t)K + 16; }
 
-cudaError_t search_configure() { return cudaFuncSetAttribute(k_search_by_projection, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); }
+cudaError_t search_configure() {
+    cudaError_t e = cudaFuncSetAttribute(k_search_by_projection<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_search_by_projection<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+}
 
 void launch_search_by_projection(const Buffers& b, int image, int K, const GridParams& p, const orbx_proj_query* queries, int nq, int useURight, int checkOrientation,
                                  int thHigh, int candCap, int* outMatch, int* outInfo, cudaStream_t s) {
-    k_search_by_projection<<<1, ST, search_smem_bytes(K, nq, candCap), s>>>(b, image, K, p, queries, nq, useURight, checkOrientation, thHigh, candCap, outMatch, outInfo);
+    k_search_by_projection<false><<<1, ST, search_smem_bytes(K, nq, candCap), s>>>(b, image, K, p, queries, nq, useURight, checkOrientation, thHigh, 0.f, nullptr, candCap,
+                                                                                  outMatch, outInfo);
+}
+
+void launch_search_local_points(const Buffers& b, int image, int K, const GridParams& p, const orbx_proj_query* queries, int nq, int useURight, int thHigh, float nnRatio,
+                                const uint8_t* taken0, int candCap, int* outMatch, int* outInfo, cudaStream_t s) {
+    k_search_by_projection<true><<<1, ST, search_smem_bytes(K, nq, candCap), s>>>(b, image, K, p, queries, nq, useURight, 0, thHigh, nnRatio, taken0, candCap, outMatch,
+                                                                                 outInfo);
 }
 
 }  // namespace orbx

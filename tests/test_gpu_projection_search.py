@@ -92,3 +92,45 @@ def test_projection_search_edge_cases():
     om, on = po.search_by_projection(kc, dc, None, po.assign_grid(kc, bounds), bounds, q2, True)
     assert nm == on and np.array_equal(m[:len(kc)], om)
     bx.close()
+
+
+@pytest.mark.parametrize("w,h,args,seed,th,ratio,use_ur", [(1241, 376, (2000, 1.2, 8, 20, 7), 21, 1.0, 0.8, True), (1241, 376, (2000, 1.2, 8, 20, 7), 22, 3.0, 0.8, True),
+                                                            (1241, 376, (2000, 1.2, 8, 20, 7), 23, 5.0, 0.9, False), (752, 480, (1200, 1.2, 8, 20, 7), 24, 15.0, 0.6, True),
+                                                            (1920, 1080, (4000, 1.2, 8, 20, 7), 25, 3.0, 0.8, True)])
+def test_local_map_search_matches_oracle(w, h, args, seed, th, ratio, use_ur):
+    """ORBmatcher::SearchByProjection(F, vpMapPoints, ...): the map = keypoints of two shifted views (near-duplicate candidates make the
+    ratio test fire), predicted levels off by up to one, keypoints already taken before the search."""
+    rng = np.random.default_rng(seed)
+    bx = T.BatchExtractor(w, h, 2, *args)
+    kc, dc, ur = make_case(bx, w, h, seed, 0, rng)
+    ex = po.OracleExtractor(*args)
+    sf = ex.tables()["scale_factors"]
+    parts = [ex(po.synth_v1(w, h, seed, s))[1:] + (s,) for s in (3, 6)]
+    k = np.concatenate([p[0] for p in parts])
+    d = np.concatenate([p[1] for p in parts])
+    sh = np.concatenate([np.full(len(p[0]), p[2], np.float32) for p in parts])
+    n = len(k)
+    pts = np.zeros((n, 5), np.float32)
+    pts[:, 0] = k["x"] - sh + rng.normal(0, 1.0, n).astype(np.float32)
+    pts[:, 1] = k["y"] + rng.normal(0, 1.0, n).astype(np.float32)
+    pts[:, 2] = pts[:, 0] - rng.uniform(0.5, 40, n).astype(np.float32)
+    pts[:, 3] = rng.choice([0.9, 0.9985, 0.9999], n).astype(np.float32)
+    pts[:, 4] = rng.uniform(1, 80, n).astype(np.float32)
+    lv = np.clip(k["octave"] + rng.integers(0, 2, n), 0, args[2] - 1).astype(np.int32)
+    nobs = rng.choice([0, 1, 3], n, p=[0.15, 0.35, 0.5]).astype(np.int32)
+    flags = (rng.random(n) < 0.9).astype(np.int32)
+    order = rng.permutation(n)
+    q, _ = po.make_local_queries(pts[order], lv[order], nobs[order], flags[order], d[order], sf, th)
+    taken = rng.random(len(kc)) < 0.2
+    bounds = (0.0, float(w), 0.0, float(h))
+    om, on = po.search_local_points(kc, dc, ur if use_ur else None, taken, po.assign_grid(kc, bounds), bounds, q, ratio)
+    for _ in range(2):
+        m, nm = bx.search_local_points(0, q.view(T.PROJ_QUERY_DTYPE), taken, use_ur, ratio)
+        assert nm == on and on > 100, (nm, on)
+        assert np.array_equal(m[:len(kc)], om), int((m[:len(kc)] != om).sum())
+        assert not (m[:len(kc)][taken] >= 0).any() and (m[len(kc):] == -1).all()
+    # without earlier matches
+    om, on = po.search_local_points(kc, dc, None, None, po.assign_grid(kc, bounds), bounds, q, ratio)
+    m, nm = bx.search_local_points(0, q.view(T.PROJ_QUERY_DTYPE), None, False, ratio)
+    assert nm == on and np.array_equal(m[:len(kc)], om)
+    bx.close()

@@ -200,3 +200,44 @@ def test_search_by_projection_matches_reference_body(seed, th, mode, check):
     om, on = po.search_by_projection(kc, dc, ur, grid, bounds, q, check)
     assert rn == on and rn > 300, (rn, on)
     assert np.array_equal(rm, om), int((rm != om).sum())
+
+
+def local_map_case(seed, w=1241, h=376, args=(2000, 1.2, 8, 20, 7)):
+    """Local map = the keypoints of two shifted views of the scene (so most windows hold a right and a near-duplicate candidate: the
+    ratio test fires), with predicted levels off by up to one, mixed viewing cosines, depths, bad / out-of-view points."""
+    rng = np.random.default_rng(seed)
+    ex = po.OracleExtractor(*args)
+    _, kc, dc = ex(po.synth_v1(w, h, seed))
+    sf = ex.tables()["scale_factors"]
+    parts = [ex(po.synth_v1(w, h, seed, s))[1:] + (s,) for s in (3, 6)]
+    k = np.concatenate([p[0] for p in parts])
+    d = np.concatenate([p[1] for p in parts])
+    sh = np.concatenate([np.full(len(p[0]), p[2], np.float32) for p in parts])
+    n = len(k)
+    pts = np.zeros((n, 5), np.float32)
+    pts[:, 0] = k["x"] - sh + rng.normal(0, 1.0, n).astype(np.float32)
+    pts[:, 1] = k["y"] + rng.normal(0, 1.0, n).astype(np.float32)
+    pts[:, 2] = pts[:, 0] - rng.uniform(0.5, 40, n).astype(np.float32)
+    pts[:, 3] = rng.choice([0.9, 0.9985, 0.9999], n).astype(np.float32)
+    pts[:, 4] = rng.uniform(1, 80, n).astype(np.float32)
+    lv = np.clip(k["octave"] + rng.integers(0, 2, n), 0, args[2] - 1).astype(np.int32)
+    nobs = rng.choice([0, 1, 3], n, p=[0.15, 0.35, 0.5]).astype(np.int32)
+    flags = (rng.random(n) < 0.9).astype(np.int32) | ((rng.random(n) < 0.05).astype(np.int32) << 1)
+    pd = d.copy()
+    flip = rng.random((n, 32)) < 0.03
+    pd ^= (flip * rng.integers(1, 256, (n, 32))).astype(np.uint8)
+    order = rng.permutation(n)
+    ur = np.where(rng.random(len(kc)) < 0.7, kc["x"] - rng.uniform(0.5, 40, len(kc)).astype(np.float32), np.float32(-1)).astype(np.float32)
+    taken0 = rng.choice([0, 1, 2], len(kc), p=[0.7, 0.2, 0.1]).astype(np.uint8)
+    return kc, dc, ur, taken0, (0.0, float(w), 0.0, float(h)), sf, pts[order], lv[order], nobs[order], flags[order], pd[order]
+
+
+@pytest.mark.skipif(not pyref.search_available(), reason="oracle/_ref/libref_search.so not built (needs /root/reference once)")
+@pytest.mark.parametrize("seed,th,ratio,far", [(1, 1.0, 0.8, False), (2, 3.0, 0.8, False), (3, 5.0, 0.9, True), (4, 15.0, 0.6, False), (5, 1.0, 0.8, True)])
+def test_search_local_points_matches_reference_body(seed, th, ratio, far):
+    kc, dc, ur, taken0, bounds, sf, pts, lv, nobs, flags, pd = local_map_case(seed)
+    rm, rn = pyref.search_local_points(kc, dc, ur, taken0, bounds, sf, pts, lv, nobs, flags, pd, th, ratio, far, 40.0)
+    q, sel = po.make_local_queries(pts, lv, nobs, flags, pd, sf, th, far, 40.0)
+    om, on = po.search_local_points(kc, dc, ur, taken0 == 1, po.assign_grid(kc, bounds), bounds, q, ratio)
+    assert rn == on and rn > 100, (rn, on)
+    assert np.array_equal(rm, np.where(om >= 0, sel[np.maximum(om, 0)], -1)), int((rm != np.where(om >= 0, sel[np.maximum(om, 0)], -1)).sum())
