@@ -816,7 +816,10 @@ static int search_common(orbx_batch* b, bool local, int image, const orbx_proj_q
     if (n_queries > 65535) return fail(ORBX_ERR_TOO_LARGE, "more than 65535 map points in one search");
     DeviceGuard dg(b->device);
     const int K = b->g.K;
-    const size_t budget = 200 * 1024, fixed = search_smem_bytes(K, n_queries, 0);
+    const size_t budget = 200 * 1024;
+    // the frame's descriptors are staged in shared memory when at least 32 KB remain for the candidate list next to them
+    const int stageDesc = search_smem_bytes(K, n_queries, 0, 1) + 32 * 1024 <= budget ? 1 : 0;
+    const size_t fixed = search_smem_bytes(K, n_queries, 0, stageDesc);
     if (fixed + 4096 > budget) return fail(ORBX_ERR_TOO_LARGE, "keypoint capacity / number of map points too large for the search kernel's shared memory");
     const int candCap = (int)((budget - fixed) / 4);
     if (!b->spConfigured) { CU(search_configure()); b->spConfigured = true; }
@@ -833,10 +836,10 @@ static int search_common(orbx_batch* b, bool local, int image, const orbx_proj_q
     Buffers buf = b->buf;
     buf.imgBase = 0;
     if (local)
-        launch_search_local_points(buf, image, K, b->gridParams, b->spDev, n_queries, use_uright ? 1 : 0, th_high, nn_ratio, taken ? takenDev : nullptr, candCap, b->spOut,
+        launch_search_local_points(buf, image, K, b->gridParams, b->spDev, n_queries, use_uright ? 1 : 0, th_high, nn_ratio, taken ? takenDev : nullptr, candCap, stageDesc, b->spOut,
                                    b->spOut + K, b->stream);
     else
-        launch_search_by_projection(buf, image, K, b->gridParams, b->spDev, n_queries, use_uright ? 1 : 0, check_orientation ? 1 : 0, th_high, candCap, b->spOut,
+        launch_search_by_projection(buf, image, K, b->gridParams, b->spDev, n_queries, use_uright ? 1 : 0, check_orientation ? 1 : 0, th_high, candCap, stageDesc, b->spOut,
                                     b->spOut + K, b->stream);
     CU(cudaGetLastError());
     int info[2] = {0, 0};

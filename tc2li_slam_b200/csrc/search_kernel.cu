@@ -21,7 +21,7 @@ namespace orbx {
 
 namespace {
 
-constexpr int ST = 256;  // threads per CTA
+constexpr int ST = 1024;  // threads per CTA: the candidate walks are latency bound, one CTA serves a frame
 constexpr int GC = ORBX_GRID_COLS, GR = ORBX_GRID_ROWS, NC = GC * GR;
 constexpr int HISTO = 30;  // ORBmatcher::HISTO_LENGTH (ORBmatcher.cc:46)
 
@@ -42,9 +42,8 @@ __device__ __forceinline__ Window window_of(float x, float y, float r, const Gri
 
 // the candidate walk of one query by one warp; EMIT = false: count only.  Returns the number of candidates (after the gate).
 template <bool EMIT>
-__device__ __forceinline__ int walk(const orbx_proj_query& Q, const Window& W, const int* __restrict__ gs, const int* __restrict__ gi,
-                                    const orbx_keypoint* __restrict__ kps, const uint8_t* __restrict__ desc, const float* __restrict__ uRight, uint32_t* out,
-                                    int lane) {
+__device__ __forceinline__ int walk(const orbx_proj_query& Q, const Window& W, const int* gs, const uint16_t* gi, const float2* kxy, const uint8_t* koct,
+                                    const uint8_t* desc, const float* uRight, uint32_t* out, int lane) {
     if (W.empty) return 0;
     const bool checkLevels = Q.min_level > 0 || Q.max_level >= 0;
     uint32_t qd[8];
@@ -61,10 +60,10 @@ __device__ __forceinline__ int walk(const orbx_proj_query& Q, const Window& W, c
             int idx = 0, kpOctave = 0;
             if (j < e) {
                 idx = gi[j];
-                const orbx_keypoint kp = kps[idx];
-                kpOctave = kp.octave & 15;
+                const float2 kp = kxy[idx];
+                kpOctave = koct[idx];
                 bool lv = true;
-                if (checkLevels) lv = !(kp.octave < Q.min_level) && !(Q.max_level >= 0 && kp.octave > Q.max_level);
+                if (checkLevels) lv = !(kpOctave < Q.min_level) && !(Q.max_level >= 0 && kpOctave > Q.max_level);
                 hit = lv && fabsf(__fsub_rn(kp.x, Q.u)) < Q.radius && fabsf(__fsub_rn(kp.y, Q.v)) < Q.radius;
                 if (hit && uRight) {  // CurrentFrame.mvuRight[i2] > 0: the predicted right coordinate must fall inside the window too
                     const float ur2 = uRight[idx];
@@ -87,13 +86,13 @@ __device__ __forceinline__ int walk(const orbx_proj_query& Q, const Window& W, c
 
 }  // namespace
 
-// shared memory: match[K] | candStart[nq + 1] | cand[candCap] | entIdx[nq] (u16) | entBin[nq] (u8) | taken[K] (u8)
+// shared memory: match[K] | candStart[nq + 1] | cand[candCap] | gs[3073] | kxy[K] | ur[K] | kang[K] | qang[nq] | gi[K] (u16) | entIdx[nq] (u16) | entBin[nq] | taken[K] | koct[K] | qblk[nq]
 // LOCAL = false: frame-to-frame search (best distance, rotation check); LOCAL = true: local-map search (best / second best with
 // their levels and the mfNNratio test, keypoints taken before the search in taken0, no rotation check)
 template <bool LOCAL>
 __global__ void __launch_bounds__(ST) k_search_by_projection(const Buffers b, int image, int K, GridParams p, const orbx_proj_query* __restrict__ queries, int nq,
                                                             int useURight, int checkOrientation, int thHigh, float nnRatio, const uint8_t* __restrict__ taken0,
-                                                            int candCap, int* __restrict__ outMatch, int* __restrict__ outInfo) {
+                                                            int candCap, int stageDesc, int* __restrict__ outMatch, int* __restrict__ outInfo) {
     extern __shared__ __align__(16) unsigned char ssm[];
     __shared__ int warpSum[ST / 32];
     __shared__ int hist[HISTO];
@@ -101,23 +100,54 @@ __global__ void __launch_bounds__(ST) k_search_by_projection(const Buffers b, in
     int* match = reinterpret_cast<int*>(ssm);
     int* candStart = match + K;
     uint32_t* cand = reinterpret_cast<uint32_t*>(candStart + nq + 1);
-    uint16_t* entIdx = reinterpret_cast<uint16_t*>(cand + candCap);
+    int* gsS = reinterpret_cast<int*>(cand + candCap);
+    float2* kxy = reinterpret_cast<float2*>((reinterpret_cast<uintptr_t>(gsS + NC + 1) + 7) & ~(uintptr_t)7);
+    float* urS = reinterpret_cast<float*>(kxy + K);
+    float* kang = urS + K;      // keypoint angles (rotation histogram)
+    float* qang = kang + K;     // per query: kpLF.angle
+    uint16_t* giS = reinterpret_cast<uint16_t*>(qang + nq);
+    uint16_t* entIdx = giS + K;
     uint8_t* entBin = reinterpret_cast<uint8_t*>(entIdx + nq);
     uint8_t* taken = entBin + nq;
+    uint8_t* koct = taken + K;
+    uint8_t* qblk = koct + K;   // per query: Observations() > 0
+    // the frame's descriptors (32 bytes per keypoint) when they fit next to the rest: then nothing below touches global memory
+    uint4* descS = reinterpret_cast<uint4*>((reinterpret_cast<uintptr_t>(qblk + nq) + 15) & ~(uintptr_t)15);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n = b.outCount[image];
     const int* gs = b.gridStart + (size_t)image * (NC + 1);
     const int* gi = b.gridItems + (size_t)image * K;
     const orbx_keypoint* kps = b.kps + (size_t)image * K;
     const uint8_t* desc = b.desc + (size_t)image * K * 32;
+    if (stageDesc) {
+        const uint4* g = reinterpret_cast<const uint4*>(desc);
+        for (int k = tid; k < 2 * n; k += ST) descS[k] = g[k];
+        desc = reinterpret_cast<const uint8_t*>(descS);
+    }
     const float* uRight = useURight ? b.uRight + (size_t)image * K : nullptr;
-    for (int k = tid; k < K; k += ST) { match[k] = -1; taken[k] = (LOCAL && taken0 && k < n) ? (taken0[k] != 0) : 0; }
+    // the frame's grid, keypoint coordinates / levels and right coordinates move to shared memory once: the walks below touch global
+    // memory only for the 32-byte descriptors of their hits
+    for (int k = tid; k < K; k += ST) {
+        match[k] = -1;
+        taken[k] = (LOCAL && taken0 && k < n) ? (taken0[k] != 0) : 0;
+        if (k < n) {
+            const orbx_keypoint kp = kps[k];
+            kxy[k] = make_float2(kp.x, kp.y);
+            koct[k] = (uint8_t)(kp.octave & 15);
+            urS[k] = uRight ? uRight[k] : -1.f;
+            kang[k] = kp.angle;
+            giS[k] = (uint16_t)gi[k];
+        }
+    }
+    for (int c = tid; c <= NC; c += ST) gsS[c] = gs[c];
+    for (int i = tid; i < nq; i += ST) { qang[i] = queries[i].angle; qblk[i] = queries[i].blocks != 0; }
     if (tid < HISTO) hist[tid] = 0;
     if (tid < 4) sInfo[tid] = 0;
+    __syncthreads();
     // ---- phase 1a: candidate counts ----
     for (int i = wid; i < nq; i += ST / 32) {
         const orbx_proj_query Q = queries[i];
-        const int c = walk<false>(Q, window_of(Q.u, Q.v, Q.radius, p), gs, gi, kps, desc, uRight, nullptr, lane);
+        const int c = walk<false>(Q, window_of(Q.u, Q.v, Q.radius, p), gsS, giS, kxy, koct, desc, uRight ? urS : nullptr, nullptr, lane);
         if (lane == 0) candStart[i] = c;
     }
     __syncthreads();
@@ -145,21 +175,32 @@ __global__ void __launch_bounds__(ST) k_search_by_projection(const Buffers b, in
     if (tid == 0) { candStart[nq] = carry; sInfo[2] = carry; }
     __syncthreads();
     const int total = carry;
-    if (total > candCap) {  // the caller sees the needed capacity and fails with ORBX_ERR_CAPACITY
-        if (tid == 0) { outInfo[0] = -1; outInfo[1] = total; }
-        return;
-    }
+    // Queries are processed in chunks [i0, i1) whose candidates fit the shared-memory list (one chunk unless the windows are
+    // very wide, e.g. th = 15 after tracking was lost); the taken / match state carries over, so chunking does not change the result.
+    int nm = 0, ne = 0;  // (live in warp 0)
+    for (int i0 = 0; i0 < nq;) {
+        if (tid == 0) {
+            int i1 = i0;
+            const int base = candStart[i0];
+            while (i1 < nq && candStart[i1 + 1] - base <= candCap) ++i1;
+            sInfo[2] = i1;
+        }
+        __syncthreads();
+        const int i1 = sInfo[2], cbase = candStart[i0];
+        if (i1 == i0) {  // a single window holds more candidates than the list: the caller fails with ORBX_ERR_CAPACITY
+            if (tid == 0) { outInfo[0] = -1; outInfo[1] = candStart[i0 + 1] - cbase; }
+            return;
+        }
     // ---- phase 1b: the candidates, in visiting order, with their distances ----
-    for (int i = wid; i < nq; i += ST / 32) {
+    for (int i = i0 + wid; i < i1; i += ST / 32) {
         const orbx_proj_query Q = queries[i];
-        walk<true>(Q, window_of(Q.u, Q.v, Q.radius, p), gs, gi, kps, desc, uRight, cand + candStart[i], lane);
+        walk<true>(Q, window_of(Q.u, Q.v, Q.radius, p), gsS, giS, kxy, koct, desc, uRight ? urS : nullptr, cand + (candStart[i] - cbase), lane);
     }
     __syncthreads();
     // ---- phase 2: the reference's loop over the map points, in order (one warp) ----
     if (wid == 0) {
-        int nm = 0, ne = 0;
-        for (int i = 0; i < nq; ++i) {
-            const int s = candStart[i], e = candStart[i + 1];
+        for (int i = i0; i < i1; ++i) {
+            const int s = candStart[i] - cbase, e = candStart[i + 1] - cbase;
             if (s == e) continue;
             if (LOCAL) {
                 // ORBmatcher.cc:85-137: the reference's update order decides who is "second best", so every lane replays the short
@@ -177,7 +218,7 @@ __global__ void __launch_bounds__(ST) k_search_by_projection(const Buffers b, in
                     const float lim = __fmul_rn(nnRatio, (float)bestDist2);
                     const bool ratioFail = bestLevel == bestLevel2 && (float)bestDist > lim;
                     if (!ratioFail && (bestLevel != bestLevel2 || (float)bestDist <= lim)) {
-                        if (lane == 0) { match[bestIdx] = i; taken[bestIdx] = queries[i].blocks != 0; }
+                        if (lane == 0) { match[bestIdx] = i; taken[bestIdx] = qblk[i]; }
                         ++nm;
                         __syncwarp();
                     }
@@ -199,9 +240,9 @@ __global__ void __launch_bounds__(ST) k_search_by_projection(const Buffers b, in
                 const int idx = (int)(cand[s + (int)(best & 0xFFFFu)] & 0xFFFFu);
                 if (lane == 0) {
                     match[idx] = i;
-                    taken[idx] = queries[i].blocks != 0;
+                    taken[idx] = qblk[i];
                     if (checkOrientation) {
-                        float rot = __fsub_rn(queries[i].angle, kps[idx].angle);  // ORBmatcher.cc:1793-1798
+                        float rot = __fsub_rn(qang[i], kang[idx]);  // ORBmatcher.cc:1793-1798
                         if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
                         int bin = (int)roundf(__fmul_rn(rot, 1.0f / HISTO));
                         if (bin == HISTO) bin = 0;
@@ -215,8 +256,11 @@ __global__ void __launch_bounds__(ST) k_search_by_projection(const Buffers b, in
                 __syncwarp();
             }
         }
-        if (lane == 0) { sInfo[0] = nm; sInfo[1] = checkOrientation ? ne : 0; }
     }
+        __syncthreads();
+        i0 = i1;
+    }
+    if (wid == 0 && lane == 0) { sInfo[0] = nm; sInfo[1] = checkOrientation ? ne : 0; }
     __syncthreads();
     // ---- phase 3: rotation consistency ----
     if (!LOCAL && checkOrientation) {
@@ -249,7 +293,9 @@ __global__ void __launch_bounds__(ST) k_search_by_projection(const Buffers b, in
     if (tid == 0) { outInfo[0] = sInfo[0]; outInfo[1] = total; }
 }
 
-size_t search_smem_bytes(int K, int nq, int candCap) { return (size_t)K * 4 + ((size_t)nq + 1) * 4 + (size_t)candCap * 4 + (size_t)nq * 2 + (size_t)nq + (size_t)K + 16; }
+size_t search_smem_bytes(int K, int nq, int candCap, int stageDesc) {
+    return (stageDesc ? (size_t)K * 32 + 16 : 0) + (size_t)K * 4 + ((size_t)nq + 1) * 4 + (size_t)candCap * 4 + (size_t)(NC + 2) * 4 + (size_t)K * (8 + 4 + 4 + 2 + 1 + 1) + (size_t)nq * (4 + 3 + 1) + 32;
+}
 
 cudaError_t search_configure() {
     cudaError_t e = cudaFuncSetAttribute(k_search_by_projection<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -258,15 +304,15 @@ cudaError_t search_configure() {
 }
 
 void launch_search_by_projection(const Buffers& b, int image, int K, const GridParams& p, const orbx_proj_query* queries, int nq, int useURight, int checkOrientation,
-                                 int thHigh, int candCap, int* outMatch, int* outInfo, cudaStream_t s) {
-    k_search_by_projection<false><<<1, ST, search_smem_bytes(K, nq, candCap), s>>>(b, image, K, p, queries, nq, useURight, checkOrientation, thHigh, 0.f, nullptr, candCap,
-                                                                                  outMatch, outInfo);
+                                 int thHigh, int candCap, int stageDesc, int* outMatch, int* outInfo, cudaStream_t s) {
+    k_search_by_projection<false><<<1, ST, search_smem_bytes(K, nq, candCap, stageDesc), s>>>(b, image, K, p, queries, nq, useURight, checkOrientation, thHigh, 0.f,
+                                                                                             nullptr, candCap, stageDesc, outMatch, outInfo);
 }
 
 void launch_search_local_points(const Buffers& b, int image, int K, const GridParams& p, const orbx_proj_query* queries, int nq, int useURight, int thHigh, float nnRatio,
-                                const uint8_t* taken0, int candCap, int* outMatch, int* outInfo, cudaStream_t s) {
-    k_search_by_projection<true><<<1, ST, search_smem_bytes(K, nq, candCap), s>>>(b, image, K, p, queries, nq, useURight, 0, thHigh, nnRatio, taken0, candCap, outMatch,
-                                                                                 outInfo);
+                                const uint8_t* taken0, int candCap, int stageDesc, int* outMatch, int* outInfo, cudaStream_t s) {
+    k_search_by_projection<true><<<1, ST, search_smem_bytes(K, nq, candCap, stageDesc), s>>>(b, image, K, p, queries, nq, useURight, 0, thHigh, nnRatio, taken0, candCap,
+                                                                                            stageDesc, outMatch, outInfo);
 }
 
 }  // namespace orbx
