@@ -4,7 +4,9 @@
 // bForward / bBackward decision) stays with the caller, who sends one orbx_proj_query per surviving map point; keypoints,
 // descriptors, right coordinates (orbx_batch_stereo_match) and the feature grid (orbx_batch_assign_grid) are already resident.
 //
-// One CTA per call (a frame).  Phase 1, a warp per query, twice over the same candidate walk (Frame::GetFeaturesInArea order,
+// One CTA of 1024 threads per call (a frame).  The frame's grid, keypoint coordinates / levels / angles, right coordinates and — when
+// they fit — its descriptors are staged in shared memory first, so nothing below waits for global memory (the walks are chains of
+// dependent loads).  Phase 1, a warp per query, twice over the same candidate walk (Frame::GetFeaturesInArea order,
 // see grid_kernel.cu): first the candidate counts, then — after a block scan gave every query its slice of a shared-memory
 // CSR — the candidates themselves as (Hamming distance << 16 | keypoint index), with the right-coordinate gate
 // (ORBmatcher.cc:1760-1766) applied.  Phase 2 is the reference's own sequential dependency: a keypoint taken by a point with
@@ -12,7 +14,9 @@
 // the candidates of a query, first minimum by a (distance, position) key, acceptance at bestDist <= TH_HIGH; everything it
 // touches is in shared memory.  Phase 3: rotation histogram, ORBmatcher::ComputeThreeMaxima (ORBmatcher.cc:2021-2062), removal
 // of the matches outside the three dominant bins (ORBmatcher.cc:1872-1892).  Integer work except the window arithmetic, which
-// follows the reference operation by operation in float32.
+// follows the reference operation by operation in float32.  The template parameter switches to the local-map overload
+// ORBmatcher::SearchByProjection(F, vpMapPoints, th, bFarPoints, thFarPoints) (ORBmatcher.cc:52-222): best / second best with levels
+// and the mfNNratio test instead of the rotation check, keypoints taken before the search as an input.
 #include <algorithm>
 
 #include "orbx_internal.cuh"
@@ -191,72 +195,72 @@ __global__ void __launch_bounds__(ST) k_search_by_projection(const Buffers b, in
             if (tid == 0) { outInfo[0] = -1; outInfo[1] = candStart[i0 + 1] - cbase; }
             return;
         }
-    // ---- phase 1b: the candidates, in visiting order, with their distances ----
-    for (int i = i0 + wid; i < i1; i += ST / 32) {
-        const orbx_proj_query Q = queries[i];
-        walk<true>(Q, window_of(Q.u, Q.v, Q.radius, p), gsS, giS, kxy, koct, desc, uRight ? urS : nullptr, cand + (candStart[i] - cbase), lane);
-    }
-    __syncthreads();
-    // ---- phase 2: the reference's loop over the map points, in order (one warp) ----
-    if (wid == 0) {
-        for (int i = i0; i < i1; ++i) {
-            const int s = candStart[i] - cbase, e = candStart[i + 1] - cbase;
-            if (s == e) continue;
-            if (LOCAL) {
-                // ORBmatcher.cc:85-137: the reference's update order decides who is "second best", so every lane replays the short
-                // candidate list as written (warp-uniform, shared-memory broadcasts, no shuffles)
-                int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
-                for (int c = s; c < e; ++c) {
-                    const uint32_t en = cand[c];
-                    const int idx = (int)(en & 0xFFFFu);
-                    if (taken[idx]) continue;
-                    const int dist = (int)(en >> 20), level = (int)((en >> 16) & 15u);
-                    if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = level; bestIdx = idx; }
-                    else if (dist < bestDist2) { bestLevel2 = level; bestDist2 = dist; }
+        // ---- phase 1b: the candidates, in visiting order, with their distances ----
+        for (int i = i0 + wid; i < i1; i += ST / 32) {
+            const orbx_proj_query Q = queries[i];
+            walk<true>(Q, window_of(Q.u, Q.v, Q.radius, p), gsS, giS, kxy, koct, desc, uRight ? urS : nullptr, cand + (candStart[i] - cbase), lane);
+        }
+        __syncthreads();
+        // ---- phase 2: the reference's loop over the map points, in order (one warp) ----
+        if (wid == 0) {
+            for (int i = i0; i < i1; ++i) {
+                const int s = candStart[i] - cbase, e = candStart[i + 1] - cbase;
+                if (s == e) continue;
+                if (LOCAL) {
+                    // ORBmatcher.cc:85-137: the reference's update order decides who is "second best", so every lane replays the short
+                    // candidate list as written (warp-uniform, shared-memory broadcasts, no shuffles)
+                    int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+                    for (int c = s; c < e; ++c) {
+                        const uint32_t en = cand[c];
+                        const int idx = (int)(en & 0xFFFFu);
+                        if (taken[idx]) continue;
+                        const int dist = (int)(en >> 20), level = (int)((en >> 16) & 15u);
+                        if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = level; bestIdx = idx; }
+                        else if (dist < bestDist2) { bestLevel2 = level; bestDist2 = dist; }
+                    }
+                    if (bestDist <= thHigh) {
+                        const float lim = __fmul_rn(nnRatio, (float)bestDist2);
+                        const bool ratioFail = bestLevel == bestLevel2 && (float)bestDist > lim;
+                        if (!ratioFail && (bestLevel != bestLevel2 || (float)bestDist <= lim)) {
+                            if (lane == 0) { match[bestIdx] = i; taken[bestIdx] = qblk[i]; }
+                            ++nm;
+                            __syncwarp();
+                        }
+                    }
+                    continue;
                 }
-                if (bestDist <= thHigh) {
-                    const float lim = __fmul_rn(nnRatio, (float)bestDist2);
-                    const bool ratioFail = bestLevel == bestLevel2 && (float)bestDist > lim;
-                    if (!ratioFail && (bestLevel != bestLevel2 || (float)bestDist <= lim)) {
-                        if (lane == 0) { match[bestIdx] = i; taken[bestIdx] = qblk[i]; }
-                        ++nm;
-                        __syncwarp();
+                uint32_t best = 0xFFFFFFFFu;  // (distance << 16 | position): the first of the smallest distances
+                for (int c0 = s; c0 < e; c0 += 32) {
+                    const int c = c0 + lane;
+                    if (c < e) {
+                        const uint32_t en = cand[c];
+                        const int idx = (int)(en & 0xFFFFu);
+                        if (!taken[idx]) best = min(best, ((en >> 20) << 16) | (uint32_t)(c - s));
                     }
                 }
-                continue;
-            }
-            uint32_t best = 0xFFFFFFFFu;  // (distance << 16 | position): the first of the smallest distances
-            for (int c0 = s; c0 < e; c0 += 32) {
-                const int c = c0 + lane;
-                if (c < e) {
-                    const uint32_t en = cand[c];
-                    const int idx = (int)(en & 0xFFFFu);
-                    if (!taken[idx]) best = min(best, ((en >> 20) << 16) | (uint32_t)(c - s));
-                }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xFFFFFFFFu, best, o));
-            if (best != 0xFFFFFFFFu && (int)(best >> 16) <= thHigh) {
-                const int idx = (int)(cand[s + (int)(best & 0xFFFFu)] & 0xFFFFu);
-                if (lane == 0) {
-                    match[idx] = i;
-                    taken[idx] = qblk[i];
-                    if (checkOrientation) {
-                        float rot = __fsub_rn(qang[i], kang[idx]);  // ORBmatcher.cc:1793-1798
-                        if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
-                        int bin = (int)roundf(__fmul_rn(rot, 1.0f / HISTO));
-                        if (bin == HISTO) bin = 0;
-                        entIdx[ne] = (uint16_t)idx;
-                        entBin[ne] = (uint8_t)bin;
-                        ++hist[bin];
+    #pragma unroll
+                for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xFFFFFFFFu, best, o));
+                if (best != 0xFFFFFFFFu && (int)(best >> 16) <= thHigh) {
+                    const int idx = (int)(cand[s + (int)(best & 0xFFFFu)] & 0xFFFFu);
+                    if (lane == 0) {
+                        match[idx] = i;
+                        taken[idx] = qblk[i];
+                        if (checkOrientation) {
+                            float rot = __fsub_rn(qang[i], kang[idx]);  // ORBmatcher.cc:1793-1798
+                            if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+                            int bin = (int)roundf(__fmul_rn(rot, 1.0f / HISTO));
+                            if (bin == HISTO) bin = 0;
+                            entIdx[ne] = (uint16_t)idx;
+                            entBin[ne] = (uint8_t)bin;
+                            ++hist[bin];
+                        }
                     }
+                    ++nm;
+                    ++ne;
+                    __syncwarp();
                 }
-                ++nm;
-                ++ne;
-                __syncwarp();
             }
         }
-    }
         __syncthreads();
         i0 = i1;
     }
