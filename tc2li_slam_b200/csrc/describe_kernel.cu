@@ -91,7 +91,9 @@ __global__ void __launch_bounds__(256) k_assemble(const __grid_constant__ Geom g
 void launch_assemble(const Geom& g, const Buffers& b, int nImages, cudaStream_t s) { k_assemble<<<nImages, 256, 0, s>>>(g, b); }
 
 // ---------------------------------------------------------------------------------------------------------------
-// k_describe: a CTA of 8 warps handles 64 consecutive keypoints, 8 per warp, in three phases.
+// k_describe: a CTA of DW = 2 warps handles 64 consecutive keypoints, KPW = 32 per warp, in three phases (measured, ms per 8192 KITTI
+// images: DW x KPW = 8 x 8: 9.50, 4 x 16: 8.89, 8 x 32: 8.86, 2 x 32: 8.77 — long per-warp runs amortise the per-lane weight / pattern
+// setup and phase 2 then keeps every thread of the CTA busy).
 //   1  moments: per keypoint ONE lane issues a TMA box load of the 31x31 patch of the unblurred level (box rows of 48 bytes:
 //      box origins must be 16-byte aligned in global memory, so the box starts at the aligned byte at or before column
 //      -15) into the warp's double-buffered shared memory; the next box is in flight while the current one is reduced.
@@ -106,8 +108,14 @@ void launch_assemble(const Geom& g, const Buffers& b, int nImages, cudaStream_t 
 //      (5.1 wavefronts per load, ncu), with 80 the row offsets cycle through all of them.
 // Timing experiment (boxes cut to 2 rows, wrong results): 9.17 instead of 9.55 ms, i.e. the kernel is not bound by the box loads
 // or by L2 / HBM but by instruction issue and dependency latency (~470 warp instructions per keypoint).
-constexpr int DW = 8;            // warps per CTA
-constexpr int KPW = 8;           // consecutive keypoints per warp
+#ifndef DESC_DW
+#define DESC_DW 2
+#endif
+#ifndef DESC_KPW
+#define DESC_KPW 32
+#endif
+constexpr int DW = DESC_DW;      // warps per CTA
+constexpr int KPW = DESC_KPW;    // consecutive keypoints per warp
 constexpr int PA_ROW = 48, PB_ROW = kDescWindowRow;
 constexpr int PA_BYTES = PA_ROW * 31, PB_BYTES = PB_ROW * 37;
 constexpr int ST_BYTES = (PB_ROW * 37 + 127) & ~127;   // one stage holds either box, 128-byte aligned
@@ -135,8 +143,10 @@ __global__ void __launch_bounds__(32 * DW) k_describe(const __grid_constant__ Ge
     if (tid < DW * KPW && kBase + tid < n) wks[tid] = b.work[(size_t)img * g.K + kBase + tid];
     {   // pair p = 8 * byte + bit is read by lane `byte` in iteration `bit`: store it at [bit][byte] so that a warp reads 32
         // consecutive float4 (a [byte][bit] layout makes every lane hit the same banks: 8-way conflicts)
-        const signed char* q = c_pattern + 4 * tid;
-        pat4[(tid & 7) * 32 + (tid >> 3)] = make_float4((float)q[0], (float)q[1], (float)q[2], (float)q[3]);
+        for (int t = tid; t < 256; t += 32 * DW) {
+            const signed char* q = c_pattern + 4 * t;
+            pat4[(t & 7) * 32 + (t >> 3)] = make_float4((float)q[0], (float)q[1], (float)q[2], (float)q[3]);
+        }
     }
     if (lane == 0) { mbar_init(&bars[wid][0], 1); mbar_init(&bars[wid][1], 1); }
     mbar_fence_init();

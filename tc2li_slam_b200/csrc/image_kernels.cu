@@ -84,8 +84,14 @@ __global__ void __launch_bounds__(256) k_resize(const uint8_t* __restrict__ src,
 // coefficients and PRMT selectors live in registers, a source row is three aligned 32-bit shared-memory loads, the
 // horizontal interpolation of a pixel is one PRMT + one IDP.2A (coefficients as 16x2 against two source bytes), and the
 // horizontally interpolated upper row is reused as the next destination row's lower row whenever the source row repeats.
-constexpr int RS_SEG = 16, RS_WARPS = 4;
-constexpr int RS_BOXW = 192, RS_BOXH = 24;
+#ifndef RS_SEG_ROWS
+#define RS_SEG_ROWS 16
+#endif
+#ifndef RS_NWARPS
+#define RS_NWARPS 4
+#endif
+constexpr int RS_SEG = RS_SEG_ROWS, RS_WARPS = RS_NWARPS;
+constexpr int RS_BOXW = 192, RS_BOXH = (RS_SEG * 5 + 3) / 4 + 4;  // 1.25 source rows per destination row + the second row of the last one + rounding
 
 __global__ void __launch_bounds__(32 * RS_WARPS) k_resize_s12(const __grid_constant__ CUtensorMap srcMap, int sh, int imgBase, uint8_t* __restrict__ dst,
                                                              int dw, int dh, int dpitch, size_t dplane, ResizeTab t) {
@@ -347,7 +353,10 @@ void launch_margin(const Geom& g, const Buffers& b, int nImages, cudaStream_t s)
 // row against the tap pairs, six running sums per pixel carried across boxes; no inter-thread exchange; a warp writes 128
 // contiguous bytes per row.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int BLUR_WARPS = 4;
+#ifndef BLUR_NWARPS
+#define BLUR_NWARPS 4
+#endif
+constexpr int BLUR_WARPS = BLUR_NWARPS;
 
 constexpr int BLUR_BOXW = 144;                  // 4 halo bytes + 128 pixels + 4 halo bytes, rounded to a multiple of 16
 constexpr int BLUR_BOXH = 32;                   // input rows per TMA box
