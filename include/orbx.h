@@ -169,6 +169,11 @@ int orbx_batch_upload_color(orbx_batch* b, const uint8_t* host_images, size_t ro
 /* rectification variant (see orbx_set_rectification): maps of width x height floats for ALL images of the handle; then raw images of
  * src_width x src_height with 1, 3 or 4 channels are remapped (+ converted to grey) into level 0 */
 int orbx_batch_set_rectification(orbx_batch* b, const float* map_x, const float* map_y, size_t map_stride_bytes, int src_width, int src_height);
+/* resize variant: System::TrackStereoLidar's cv::resize(im, imToFeed, settings_->newImSize()) (System.cc:250-252, Settings::needToResize())
+ * on the device: after this call orbx_batch_upload_raw takes raw images of src_width x src_height (1, 3 or 4 channels) and resizes them
+ * (INTER_LINEAR, bit-identical to cv::resize; colour input is then converted as cv::cvtColor does) into level 0.  It replaces a
+ * rectification set earlier and vice versa; 0, 0 switches it off. */
+int orbx_batch_set_input_resize(orbx_batch* b, int src_width, int src_height);
 int orbx_batch_upload_raw(orbx_batch* b, const uint8_t* host_images, size_t row_stride, size_t image_stride, int channels, int rgb, int first_image, int n_images);
 int orbx_batch_upload_device(orbx_batch* b, const uint8_t* dev_images, size_t row_stride, size_t image_stride, int first_image, int n_images);
 int orbx_batch_synth(orbx_batch* b, uint32_t seed0, int first_image, int n_images, int stereo);

@@ -85,6 +85,16 @@ def resize(src, dw, dh):
     return dst
 
 
+def input_resize(image, dw, dh, rgb=None):
+    """cv::resize(image, (dw, dh)) as System::TrackStereoLidar feeds its inputs (System.cc:250-252; INTER_LINEAR, per channel), followed —
+    for colour input when `rgb` is given — by the cvtColor of Tracking::Grab* (Tracking.cc:1646-1671).  image: uint8 [h, w] or [h, w, 3|4]."""
+    image = np.ascontiguousarray(image, np.uint8)
+    if image.ndim == 2:
+        return resize(image, dw, dh)
+    out = np.stack([resize(np.ascontiguousarray(image[:, :, c]), dw, dh) for c in range(image.shape[2])], axis=2)
+    return out if rgb is None else cvt_gray(out, rgb)
+
+
 def blur(src, taps=(18, 34, 48, 56, 48, 34, 18)):
     src = np.ascontiguousarray(src, np.uint8)
     dst = np.empty_like(src)

@@ -305,6 +305,59 @@ void launch_remap(const uint8_t* src, int sw, int sh, int channels, int rgb, con
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Input resize of the caller: System::TrackStereoLidar (System.cc:250-252) runs cv::resize(im, imToFeed, settings_->newImSize())
+// — INTER_LINEAR, the same 8-bit fixed-point arithmetic as the pyramid's resize, per channel — when
+// Settings::needToResize(), before Grab* converts to grey.  Here the raw image is uploaded as it is and resized (+ converted exactly
+// as k_gray does, i.e. in the reference's order resize -> cvtColor) straight into level 0.  One thread = four destination pixels.
+// src: dense [image][sh][sw * C]; tables as for the pyramid (make_resize_tables for sw -> dw, sh -> dh).
+// ---------------------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(128) k_input_resize(const uint8_t* __restrict__ src, int sw, int sh, ResizeTab t, uint8_t* __restrict__ dst, int dw, int dh,
+                                                      int pitch, size_t plane, uint32_t k01, uint32_t k2) {
+    const int x0 = 4 * (blockIdx.x * 128 + threadIdx.x);
+    if (x0 >= dw) return;
+    const int y = blockIdx.y, img = blockIdx.z;
+    const uint8_t* S = src + (size_t)img * sh * (size_t)sw * C;
+    const int yo = t.yofs[y];
+    const int sy0 = min(max(yo, 0), sh - 1), sy1 = min(max(yo + 1, 0), sh - 1);
+    const int b0 = t.yb[2 * y], b1 = t.yb[2 * y + 1];
+    const uint8_t* __restrict__ r0 = S + (size_t)sy0 * sw * C;
+    const uint8_t* __restrict__ r1 = S + (size_t)sy1 * sw * C;
+    uint32_t out = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int x = min(x0 + i, dw - 1);
+        const int sx = t.xofs[x], sx1 = min(sx + 1, sw - 1);
+        const int a0 = t.xa[2 * x], a1 = t.xa[2 * x + 1];
+        uint32_t px = 0;  // the resized channels in bytes 0..2
+#pragma unroll
+        for (int c = 0; c < (C == 1 ? 1 : 3); ++c) {
+            const int h0 = (int)__ldg(r0 + sx * C + c) * a0 + (int)__ldg(r0 + sx1 * C + c) * a1;
+            const int h1 = (int)__ldg(r1 + sx * C + c) * a0 + (int)__ldg(r1 + sx1 * C + c) * a1;
+            const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+            px |= (uint32_t)min(max(v, 0), 255) << (8 * c);
+        }
+        const uint32_t g = C == 1 ? px : (__dp2a_hi(k2, px, __dp2a_lo(k01, px, 1u << 14)) >> 15);
+        out |= g << (8 * i);
+    }
+    // pixels past the last column land in the row's right padding (never read)
+    *reinterpret_cast<uint32_t*>(dst + (size_t)img * plane + (size_t)y * pitch + x0) = out;
+}
+
+void launch_input_resize(const uint8_t* src, int sw, int sh, int channels, int rgb, const ResizeTab& tab, uint8_t* l0, int w, int h, int pitch, size_t planeBytes,
+                         int nImages, cudaStream_t s) {
+    const uint32_t RY = 9798, GY = 19235, BY = 3735;
+    const uint32_t k01 = (rgb ? RY : BY) | (GY << 16), k2 = rgb ? BY : RY;
+    dim3 grid((w + 511) / 512, h, nImages);
+    if (channels == 1)
+        k_input_resize<1><<<grid, 128, 0, s>>>(src, sw, sh, tab, l0, w, h, pitch, planeBytes, k01, k2);
+    else if (channels == 3)
+        k_input_resize<3><<<grid, 128, 0, s>>>(src, sw, sh, tab, l0, w, h, pitch, planeBytes, k01, k2);
+    else
+        k_input_resize<4><<<grid, 128, 0, s>>>(src, sw, sh, tab, l0, w, h, pitch, planeBytes, k01, k2);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Reflect-101 margin ROWS of every pyramid plane (3 above, 3 below the interior): what GaussianBlur(..., BORDER_REFLECT_101)
 // reads beyond the top / bottom edge of its (cloned, hence border-less) input (ORBextractor.cc:1105-1106).  They are plain row
 // copies (contiguous, 6 x w bytes per plane).  The margin COLUMNS are not materialised in HBM: touching both ends of every

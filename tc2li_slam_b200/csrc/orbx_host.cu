@@ -158,6 +158,9 @@ struct orbx_batch {
     DescMaps descMaps;
     float *rectX = nullptr, *rectY = nullptr;  // resident rectification maps [height][width] (System.cc:238-248), null = none
     int srcW = 0, srcH = 0;                    // size of the raw images the maps sample
+    bool inResize = false;                     // orbx_batch_set_input_resize: raw images are resized (System.cc:250-252) instead of remapped
+    ResizeTab inTab = {nullptr, nullptr, nullptr, nullptr};
+    int inTabW = 0, inTabH = 0;                // raw size the tables were built for
     uint8_t* stageIn = nullptr;  // dense device staging of uploaded images (PCIe copies of odd-width rows are ~6x slower than one contiguous copy)
     size_t stageBytes = 0;
 };
@@ -511,6 +514,7 @@ int orbx_batch_set_rectification(orbx_batch* b, const float* map_x, const float*
     if (!b) return fail(ORBX_ERR_ARG, "null batch");
     DeviceGuard dg(b->device);
     CU(cudaStreamSynchronize(b->stream));
+    b->inResize = false;
     if (!map_x || !map_y) {
         b->srcW = b->srcH = 0;
         return ORBX_OK;
@@ -529,12 +533,46 @@ int orbx_batch_set_rectification(orbx_batch* b, const float* map_x, const float*
     return ORBX_OK;
 }
 
+// cv::resize(raw, newImSize) of System::TrackStereoLidar (System.cc:250-252) in front of the extractor: raw images of src_width x src_height
+// given to orbx_batch_upload_raw are resized on the device to the handle's width x height; 0 x 0 switches it off
+int orbx_batch_set_input_resize(orbx_batch* b, int src_width, int src_height) {
+    if (!b) return fail(ORBX_ERR_ARG, "null batch");
+    DeviceGuard dg(b->device);
+    CU(cudaStreamSynchronize(b->stream));
+    if (src_width == 0 && src_height == 0) {
+        if (b->inResize) b->srcW = b->srcH = 0;
+        b->inResize = false;
+        return ORBX_OK;
+    }
+    if (src_width <= 1 || src_height <= 1 || src_width > ORBX_MAX_DIM || src_height > ORBX_MAX_DIM) return fail(ORBX_ERR_ARG, "raw image size out of range");
+    if (b->inTabW != src_width || b->inTabH != src_height) {
+        std::vector<short> xo, xa, yo, yb;
+        make_resize_tables(src_width, b->width, true, xo, xa);
+        make_resize_tables(src_height, b->height, false, yo, yb);
+        int r;
+        short *dxo, *dxa, *dyo, *dyb;  // (a handle changes its raw size rarely: earlier tables stay allocated until the handle is destroyed)
+        if ((r = dev_alloc(b, &dxo, xo.size()))) return r;
+        if ((r = dev_alloc(b, &dxa, xa.size()))) return r;
+        if ((r = dev_alloc(b, &dyo, yo.size()))) return r;
+        if ((r = dev_alloc(b, &dyb, yb.size()))) return r;
+        CU(cudaMemcpy(dxo, xo.data(), xo.size() * 2, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(dxa, xa.data(), xa.size() * 2, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(dyo, yo.data(), yo.size() * 2, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(dyb, yb.data(), yb.size() * 2, cudaMemcpyHostToDevice));
+        b->inTab = ResizeTab{dxo, dxa, dyo, dyb};
+        b->inTabW = src_width; b->inTabH = src_height;
+    }
+    b->srcW = src_width; b->srcH = src_height;
+    b->inResize = true;
+    return ORBX_OK;
+}
+
 // raw (unrectified) images of src_width x src_height, channels 1, 3 or 4 -> cv::remap -> [cvtColor] -> level 0, all on the device
 int orbx_batch_upload_raw(orbx_batch* b, const uint8_t* host_images, size_t row_stride, size_t image_stride, int channels, int rgb, int first, int n) {
     int r = check_images(b, first, n);
     if (r) return r;
     if (!host_images) return fail(ORBX_ERR_EMPTY, "null image");
-    if (!b->srcW) return fail(ORBX_ERR_ARG, "no rectification maps set (orbx_batch_set_rectification)");
+    if (!b->srcW) return fail(ORBX_ERR_ARG, "no rectification maps (orbx_batch_set_rectification) or input resize (orbx_batch_set_input_resize) set");
     if (channels != 1 && channels != 3 && channels != 4) return fail(ORBX_ERR_ARG, "images have 1, 3 or 4 interleaved channels");
     const size_t rowBytes = (size_t)b->srcW * channels;
     if (row_stride < rowBytes) return fail(ORBX_ERR_ARG, "row stride smaller than width * channels");
@@ -555,8 +593,12 @@ int orbx_batch_upload_raw(orbx_batch* b, const uint8_t* host_images, size_t row_
             CU(cudaMemcpy2DAsync(b->stageIn + (size_t)i * imgBytes, rowBytes, host_images + (size_t)i * image_stride, row_stride, rowBytes, b->srcH,
                                  cudaMemcpyHostToDevice, b->stream));
     const LevelGeom& L0 = b->g.lv[0];
-    launch_remap(b->stageIn, b->srcW, b->srcH, channels, rgb, b->rectX, b->rectY, b->buf.pyr + L0.planeOff + (size_t)first * L0.planeBytes, L0.w, L0.h, L0.pitch,
-                 (size_t)L0.planeBytes, n, b->stream);
+    if (b->inResize)
+        launch_input_resize(b->stageIn, b->srcW, b->srcH, channels, rgb, b->inTab, b->buf.pyr + L0.planeOff + (size_t)first * L0.planeBytes, L0.w, L0.h, L0.pitch,
+                            (size_t)L0.planeBytes, n, b->stream);
+    else
+        launch_remap(b->stageIn, b->srcW, b->srcH, channels, rgb, b->rectX, b->rectY, b->buf.pyr + L0.planeOff + (size_t)first * L0.planeBytes, L0.w, L0.h, L0.pitch,
+                     (size_t)L0.planeBytes, n, b->stream);
     CU(cudaGetLastError());
     return ORBX_OK;
 }

@@ -132,6 +132,8 @@ cudaError_t describe_configure();
 void launch_margin(const Geom& g, const Buffers& b, int nImages, cudaStream_t s);
 void launch_remap(const uint8_t* src, int sw, int sh, int channels, int rgb, const float* mapx, const float* mapy, uint8_t* l0, int w, int h, int pitch,
                   size_t planeBytes, int nImages, cudaStream_t s);
+void launch_input_resize(const uint8_t* src, int sw, int sh, int channels, int rgb, const ResizeTab& tab, uint8_t* l0, int w, int h, int pitch, size_t planeBytes,
+                         int nImages, cudaStream_t s);
 void launch_gray(const uint8_t* src, int channels, int rgb, uint8_t* l0, int w, int h, int pitch, size_t planeBytes, int nImages, cudaStream_t s);
 void launch_border(const uint8_t* src, int w, int h, int pitch, uint8_t* dst, int dpitch, cudaStream_t s);
 size_t octree_smem_bytes(int nodeCap);

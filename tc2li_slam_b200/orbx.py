@@ -93,6 +93,7 @@ def lib():
         "orbx_batch_features_in_area": (i, [_vp, _vp, i, i, _vp, _vp]),
         "orbx_batch_search_by_projection": (i, [_vp, i, _vp, i, i, i, i, _vp, _vp]),
         "orbx_batch_search_local_points": (i, [_vp, i, _vp, i, i, f, i, _vp, _vp, _vp]),
+        "orbx_batch_set_input_resize": (i, [_vp, i, i]),
         "orbx_batch_run_range": (i, [_vp, i, i, _vp]),
         "orbx_batch_run_pipelined": (i, [_vp, i, _vp, i]),
         "orbx_batch_download_async": (i, [_vp, i, i, _vp, _vp, _vp, _vp]),
@@ -526,6 +527,12 @@ class BatchExtractor:
         mx, my = np.ascontiguousarray(map_x, np.float32), np.ascontiguousarray(map_y, np.float32)
         assert mx.shape == my.shape == (self.height, self.width)
         _check(lib().orbx_batch_set_rectification(self._h, _p(mx), _p(my), mx.strides[0], int(src_size[0]), int(src_size[1])))
+
+    def set_input_resize(self, src_size):
+        """System::TrackStereoLidar's cv::resize(im, newImSize) (System.cc:250-252) on the device: upload_raw() then takes raw images of
+        src_size = (width, height) and resizes them into level 0; None switches it off."""
+        sw, sh = (0, 0) if src_size is None else src_size
+        _check(lib().orbx_batch_set_input_resize(self._h, int(sw), int(sh)))
 
     def upload_raw(self, images, rgb=False, first=0):
         """raw images uint8 [n, srcH, srcW] or [n, srcH, srcW, 3|4]: cv::remap (+ cvtColor) on the device into level 0."""

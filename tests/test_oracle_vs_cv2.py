@@ -40,6 +40,20 @@ def test_resize_other_ratios():
         assert np.array_equal(po.resize(img, dw, dh), cv2.resize(img, (dw, dh), interpolation=cv2.INTER_LINEAR)), (dw, dh)
 
 
+@pytest.mark.parametrize("channels", [1, 3, 4])
+def test_input_resize_matches_cv2(channels):
+    """System::TrackStereoLidar's cv::resize(im, newImSize) (System.cc:250-252): down, up, exact 2x (OpenCV switches to its INTER_AREA
+    fast path there, which is the same arithmetic), anisotropic and identity sizes, 1 / 3 / 4 channels, followed by cvtColor."""
+    rng = np.random.default_rng(channels)
+    src = rng.integers(0, 256, (480, 752) if channels == 1 else (480, 752, channels), dtype=np.uint8)
+    for dw, dh in [(600, 350), (1241, 376), (376, 240), (752, 480), (1000, 700), (640, 480), (188, 120)]:
+        ref = cv2.resize(src, (dw, dh))
+        assert np.array_equal(po.input_resize(src, dw, dh), ref), (dw, dh)
+        if channels > 1:
+            code = cv2.COLOR_RGB2GRAY if channels == 3 else cv2.COLOR_RGBA2GRAY
+            assert np.array_equal(po.input_resize(src, dw, dh, rgb=True), cv2.cvtColor(ref, code)), (dw, dh)
+
+
 def test_border_reflect101():
     img = po.synth_v1(97, 53, 1)
     assert np.array_equal(np.pad(img, 19, mode="reflect"), cv2.copyMakeBorder(img, 19, 19, 19, 19, cv2.BORDER_REFLECT_101))
