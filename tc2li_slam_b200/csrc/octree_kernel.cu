@@ -22,7 +22,10 @@ namespace orbx {
 namespace {
 
 constexpr int OT_MAX_WARPS = PS_MAX_WARPS;
-constexpr int OT_T_BATCH = 128;       // threads per CTA when many images are in flight (shared memory bounds the CTAs per SM)
+#ifndef OT_BATCH_THREADS
+#define OT_BATCH_THREADS 128
+#endif
+constexpr int OT_T_BATCH = OT_BATCH_THREADS;       // threads per CTA when many images are in flight (shared memory bounds the CTAs per SM)
 constexpr int OT_T_FEW = 256;         // threads per CTA for a few large frames (long candidate lists, few CTAs)
 constexpr int OT_STAGE_MAX = 2048;    // node labels of candidate lists up to the launch's stage capacity live in shared memory (2 bytes each)
 typedef StdSortEmul<16> NodeSort;    // element = (nKeys << 12 | UL.x) << 16 | node index: any key size
