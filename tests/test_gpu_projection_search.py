@@ -134,3 +134,25 @@ def test_local_map_search_matches_oracle(w, h, args, seed, th, ratio, use_ur):
     m, nm = bx.search_local_points(0, q.view(T.PROJ_QUERY_DTYPE), None, False, ratio)
     assert nm == on and np.array_equal(m[:len(kc)], om)
     bx.close()
+
+
+def test_search_through_the_single_image_handles():
+    """The reference-shaped path of INTEGRATION.md 2d / 2e: two ORBextractor handles (left / right), orbx_stereo_match, then the grid and
+    the projection search on the batch-of-one behind the left handle (orbx_extractor_batch)."""
+    w, h, args = 1241, 376, (2000, 1.2, 8, 20, 7)
+    rng = np.random.default_rng(5)
+    st = T.StereoORBextractor(*args)
+    (ml, kl, dl), _ = st(po.synth_v1(w, h, 31), po.synth_v1(w, h, 31, 16, 0x5bd1e995))
+    ur, _ = st.stereo_match(MB, MBF)
+    hb = st.left.batch
+    hb.assign_grid(1)
+    pts, octv, nobs, pd, sf = points_from(args, w, h, 31, 5, rng)
+    bounds = (0.0, float(w), 0.0, float(h))
+    q = po.make_proj_queries(pts, octv, nobs, pd, sf, 15.0, MBF, 0)
+    om, on = po.search_by_projection(kl, dl, ur, po.assign_grid(kl, bounds), bounds, q, True)
+    m, nm = hb.search_by_projection(0, q.view(T.PROJ_QUERY_DTYPE), True, True)
+    assert nm == on and on > 300 and np.array_equal(m[:len(kl)], om)
+    start, items = hb.download_grid(1)
+    os_, oi = po.assign_grid(kl, bounds)
+    assert np.array_equal(start[0], os_) and np.array_equal(items[0, :os_[-1]], oi)
+    st.close()
