@@ -404,7 +404,8 @@ void launch_margin(const Geom& g, const Buffers& b, int nImages, cudaStream_t s)
 // k_blur).  Row pass: the 7 taps of a pixel are two 4-byte dot products (IDP.4A) on byte windows cut out of three aligned
 // 32-bit shared-memory loads with PRMT.  Column pass: two input rows at a time as 16x2 lanes, one IDP.2A per touched output
 // row against the tap pairs, six running sums per pixel carried across boxes; no inter-thread exchange; a warp writes 128
-// contiguous bytes per row.
+// contiguous bytes per row.  BORDER_REFLECT_101: the three rows above / below the image exist in memory (k_margin); the three
+// columns left / right of it are mirrored inside the shared-memory box by the warps that own an edge strip (lane = box row).
 // ---------------------------------------------------------------------------------------------------------------
 #ifndef BLUR_NWARPS
 #define BLUR_NWARPS 4
@@ -412,7 +413,7 @@ void launch_margin(const Geom& g, const Buffers& b, int nImages, cudaStream_t s)
 constexpr int BLUR_WARPS = BLUR_NWARPS;
 
 constexpr int BLUR_BOXW = 144;                  // 4 halo bytes + 128 pixels + 4 halo bytes, rounded to a multiple of 16
-constexpr int BLUR_BOXH = 32;                   // input rows per TMA box
+constexpr int BLUR_BOXH = 32;                   // input rows per TMA box (= lanes: the edge mirroring handles one box row per lane)
 constexpr int BLUR_BOX_BYTES = BLUR_BOXW * BLUR_BOXH;  // 4608 = 36 x 128
 
 template <bool SAT>

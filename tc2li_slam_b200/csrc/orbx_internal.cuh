@@ -11,7 +11,7 @@ namespace orbx {
 constexpr int kEdge = 19;      // EDGE_THRESHOLD (ORBextractor.cc:47)
 constexpr int kBorder = 16;    // minBorderX/Y = EDGE_THRESHOLD - 3 (ORBextractor.cc:763)
 constexpr int kHalfPatch = 15; // HALF_PATCH_SIZE (ORBextractor.cc:46)
-constexpr int kMarginX = 4;    // bytes of left margin of every plane row (3 used by the reflect-101 ring, 4 keeps rows word-aligned)
+constexpr int kMarginX = 4;    // padding bytes in front of every plane row (keeps rows word-aligned; the blur mirrors pixels 3..1 into its box copy of them)
 constexpr int kMarginY = 3;    // rows of margin above and below every plane
 constexpr int kMaxCell = 72;   // wCell/hCell < 70 for any level with >= 1 cell of 35 px (ORBextractor.cc:771-777)
 
