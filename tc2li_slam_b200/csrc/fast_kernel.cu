@@ -29,6 +29,7 @@
 // list was flushed early falls back to scanning the score map for the NMS (textures such as saturated noise).
 // Integer only; HBM traffic = one read of every level, the work is ALU/issue bound.
 #include <algorithm>
+#include <type_traits>
 
 #include "orbx_internal.cuh"
 
@@ -275,13 +276,21 @@ __global__ void __launch_bounds__(32 * FW) k_fast_cells(const __grid_constant__ 
                 constexpr int NI = FAST_NI;
                 const int dW = RT * (TS / 4);
                 int y = r, wofs = (r + 3) * (TS / 4) + wFirst + col;
-                auto compass = [&](uint32_t m, int wo) -> uint32_t {
+                // LOWT (t < 128, every configuration the reference ships): bytes_gt is low | d, so (N|S) & (E|W) & m folds into four
+                // three-input LOP3 instead of four majorities and two combines
+                auto compass = [&](auto LOWT, uint32_t m, int wo) -> uint32_t {
                     uint32_t cur, prev, next, up, dn;
                     asm volatile("ld.shared.u32 %0, [%5];\n\tld.shared.u32 %1, [%5+-4];\n\tld.shared.u32 %2, [%5+4];\n\tld.shared.u32 %3, [%5+%6];\n\tld.shared.u32 %4, [%5+-%6];"
                                  : "=r"(cur), "=r"(prev), "=r"(next), "=r"(up), "=r"(dn)
                                  : "r"(tileS + 4u * (uint32_t)wo), "n"(3 * TS));
                     const uint32_t e = __funnelshift_r(cur, next, 24);  // pixels at x + 3
                     const uint32_t wv = __funnelshift_r(prev, cur, 8);  // pixels at x - 3
+                    if (decltype(LOWT)::value) {
+                        const uint32_t dN = __vabsdiffu4(up, cur), dS = __vabsdiffu4(dn, cur), dE = __vabsdiffu4(e, cur), dW4 = __vabsdiffu4(wv, cur);
+                        const uint32_t lN = (dN & 0x7f7f7f7fu) + kAdd, lS = (dS & 0x7f7f7f7fu) + kAdd, lE = (dE & 0x7f7f7f7fu) + kAdd, lW = (dW4 & 0x7f7f7f7fu) + kAdd;
+                        const uint32_t a = lN | dN | lS, bq = lE | dE | lW;
+                        return ((a | dS) & m) & (bq | dW4);
+                    }
                     const uint32_t ns = bytes_gt(__vabsdiffu4(up, cur), kAdd, nh) | bytes_gt(__vabsdiffu4(dn, cur), kAdd, nh);
                     const uint32_t ew = bytes_gt(__vabsdiffu4(e, cur), kAdd, nh) | bytes_gt(__vabsdiffu4(wv, cur), kAdd, nh);
                     return ns & ew & m;
@@ -295,15 +304,19 @@ __global__ void __launch_bounds__(32 * FW) k_fast_cells(const __grid_constant__ 
                         c.nw += __popc(bal);
                     }
                 };
-                for (int base = 0; base < ih; base += RT * NI) {
-                    uint32_t F[NI];
+                auto passA = [&](auto LOWT) {
+                    for (int base = 0; base < ih; base += RT * NI) {
+                        uint32_t F[NI];
 #pragma unroll
-                    for (int j = 0; j < NI; ++j) F[j] = compass(y + j * RT < ih ? mLane : 0u, wofs + j * dW);
+                        for (int j = 0; j < NI; ++j) F[j] = compass(LOWT, y + j * RT < ih ? mLane : 0u, wofs + j * dW);
 #pragma unroll
-                    for (int j = 0; j < NI; ++j) append(F[j], wofs + j * dW);
-                    y += NI * RT;
-                    wofs += NI * dW;
-                }
+                        for (int j = 0; j < NI; ++j) append(F[j], wofs + j * dW);
+                        y += NI * RT;
+                        wofs += NI * dW;
+                    }
+                };
+                if (t < 128) passA(std::true_type());
+                else passA(std::false_type());
                 __syncwarp();
             }
             flush_W<TS>(c, t);

@@ -310,3 +310,12 @@ def test_blur_edges_at_strip_boundaries(w):
     img = po.synth_v1(w, 150, 900 + w)
     stage_compare(img, (400, 1.2, 4, 20, 7))
     stage_compare(img, (400, 1.2, 2, 20, 7), taps=(18, 34, 49, 55, 49, 34, 18))
+
+
+@pytest.mark.parametrize("ini,mn", [(150, 130), (128, 127), (200, 90), (127, 7)])
+def test_high_fast_thresholds(ini, mn):
+    """Thresholds on both sides of 128 (the packed byte compare has a separate path for t >= 128) on a high-contrast image."""
+    rng = np.random.default_rng(ini)
+    img = (rng.integers(0, 2, (200, 640)) * 255).astype(np.uint8)
+    img[:, 320:] = po.synth_v1(640, 200, 5)[:, 320:]
+    stage_compare(img, (500, 1.2, 4, ini, mn))
