@@ -295,17 +295,30 @@ __global__ void __launch_bounds__(32 * FW) k_fast_cells(const __grid_constant__ 
                     const uint32_t ew = bytes_gt(__vabsdiffu4(e, cur), kAdd, nh) | bytes_gt(__vabsdiffu4(wv, cur), kAdd, nh);
                     return ns & ew & m;
                 };
-                auto append = [&](uint32_t F, int wo) {
+                auto append = [&](uint32_t F, int wo) {  // (the caller has made room for 32 entries)
                     const unsigned bal = __ballot_sync(FULL, F != 0);
                     if (bal) {
-                        if (c.nw + 32 > CAPW) flush_W<TS>(c, t);  // warp-uniform
                         // bits 7/15/23/31 -> 4 contiguous flag bits 24..27
                         if (F) c.listW[c.nw + __popc(bal & ((1u << lane) - 1))] = (((F >> 7) * 0x01020408u) & 0x0F000000u) | (uint32_t)wo;
                         c.nw += __popc(bal);
                     }
                 };
+                // full trips (every lane's NI rows lie inside the interior) need no per-row mask select; the last one or two do
                 auto passA = [&](auto LOWT) {
-                    for (int base = 0; base < ih; base += RT * NI) {
+                    int base = 0;
+                    const int yFullMax = ih - NI * RT;  // largest trip base whose NI * RT rows all lie inside the interior (rows r = 0 .. RT - 1 are all in use)
+                    for (; base <= yFullMax; base += RT * NI) {
+                        if (c.nw + 32 * NI > CAPW) flush_W<TS>(c, t);  // warp-uniform, once per trip
+                        uint32_t F[NI];
+#pragma unroll
+                        for (int j = 0; j < NI; ++j) F[j] = compass(LOWT, mLane, wofs + j * dW);
+#pragma unroll
+                        for (int j = 0; j < NI; ++j) append(F[j], wofs + j * dW);
+                        y += NI * RT;
+                        wofs += NI * dW;
+                    }
+                    for (; base < ih; base += RT * NI) {
+                        if (c.nw + 32 * NI > CAPW) flush_W<TS>(c, t);
                         uint32_t F[NI];
 #pragma unroll
                         for (int j = 0; j < NI; ++j) F[j] = compass(LOWT, y + j * RT < ih ? mLane : 0u, wofs + j * dW);
