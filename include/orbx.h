@@ -111,6 +111,10 @@ int orbx_extract_stereo_color(orbx_extractor* left, orbx_extractor* right, const
  * ---------------------------------------------------------------------------------------------------------------- */
 int orbx_set_rectification(orbx_extractor* h, const float* map_x, const float* map_y, int width, int height, size_t map_stride_bytes, int src_width,
                            int src_height);
+/* the other branch of the same `if`: cv::resize(im, imToFeed, settings_->newImSize()) (System.cc:250-252, Settings::needToResize()).  After this call the
+ * orbx_extract* entry points take the RAW src_width x src_height image and extract from its width x height resize (INTER_LINEAR, bit-identical to
+ * cv::resize; colour input is converted afterwards as cv::cvtColor does).  It replaces a rectification and vice versa; width = height = 0 switches it off. */
+int orbx_set_input_resize(orbx_extractor* h, int width, int height, int src_width, int src_height);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Next step of the caller: replaces Frame::ComputeStereoMatches (Frame.cc:841-1011) and the

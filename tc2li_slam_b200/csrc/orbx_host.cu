@@ -1211,7 +1211,8 @@ struct orbx_extractor {
     int channels = 1, rgb = 0;  // input format of the last call (1 = grey); a change re-captures the graph
     // rectification (orbx_set_rectification): host copies of the maps, applied to the batch-of-one when it is (re)created
     std::vector<float> rectX, rectY;
-    int rectW = 0, rectH = 0, srcW = 0, srcH = 0;
+    int rectW = 0, rectH = 0, srcW = 0, srcH = 0;   // fed (rectified / resized) size and raw size; rectW > 0: the extract calls take RAW images
+    bool inResize = false;                          // raw images are resized (orbx_set_input_resize) instead of remapped
     bool rectDirty = false;
     int graphState = 0;  // 0: next call runs eagerly (lazy allocations), 1: capture on the next call, 2: replay `exec`, 3: capture failed, stay eager
 };
@@ -1239,7 +1240,8 @@ int extractor_prepare(orbx_extractor* h, int w, int hgt, int channels, int rgb) 
     if (h->rectDirty) {  // new maps (or a new batch-of-one): other kernels and pointers, start over with an eager call
         if (h->exec) { cudaGraphExecDestroy(h->exec); h->exec = nullptr; }
         h->graphState = 0;
-        int r = h->rectW > 0 ? orbx_batch_set_rectification(h->b, h->rectX.data(), h->rectY.data(), (size_t)h->rectW * sizeof(float), h->srcW, h->srcH)
+        int r = h->rectW > 0 ? (h->inResize ? orbx_batch_set_input_resize(h->b, h->srcW, h->srcH)
+                                            : orbx_batch_set_rectification(h->b, h->rectX.data(), h->rectY.data(), (size_t)h->rectW * sizeof(float), h->srcW, h->srcH))
                              : orbx_batch_set_rectification(h->b, nullptr, nullptr, 0, 0, 0);
         if (r) return r;
         h->rectDirty = false;
@@ -1443,6 +1445,7 @@ int orbx_extract_stereo(orbx_extractor* left, orbx_extractor* right, const uint8
 int orbx_set_rectification(orbx_extractor* h, const float* map_x, const float* map_y, int width, int height, size_t map_stride_bytes, int src_width,
                            int src_height) {
     if (!h) return fail(ORBX_ERR_ARG, "null handle");
+    h->inResize = false;
     if (!map_x || !map_y) {
         h->rectW = h->rectH = h->srcW = h->srcH = 0;
         h->rectX.clear(); h->rectY.clear();
@@ -1460,6 +1463,26 @@ int orbx_set_rectification(orbx_extractor* h, const float* map_x, const float* m
         std::memcpy(h->rectY.data() + (size_t)y * width, (const char*)map_y + (size_t)y * map_stride_bytes, (size_t)width * sizeof(float));
     }
     h->rectW = width; h->rectH = height; h->srcW = src_width; h->srcH = src_height;
+    h->rectDirty = true;
+    return ORBX_OK;
+}
+
+// System::TrackStereoLidar's cv::resize(im, imToFeed, settings_->newImSize()) (System.cc:250-252) in front of this extractor: the orbx_extract*
+// calls then take the RAW src_width x src_height image and feed width x height.  width == 0 switches it off.  Replaces a rectification.
+int orbx_set_input_resize(orbx_extractor* h, int width, int height, int src_width, int src_height) {
+    if (!h) return fail(ORBX_ERR_ARG, "null handle");
+    h->rectX.clear(); h->rectY.clear();
+    if (width == 0 && height == 0) {
+        h->rectW = h->rectH = h->srcW = h->srcH = 0;
+        h->inResize = false;
+        h->rectDirty = true;
+        return ORBX_OK;
+    }
+    if (width <= 0 || height <= 0 || src_width <= 1 || src_height <= 1 || width > ORBX_MAX_DIM || height > ORBX_MAX_DIM || src_width > ORBX_MAX_DIM ||
+        src_height > ORBX_MAX_DIM)
+        return fail(ORBX_ERR_ARG, "image size out of range");
+    h->rectW = width; h->rectH = height; h->srcW = src_width; h->srcH = src_height;
+    h->inResize = true;
     h->rectDirty = true;
     return ORBX_OK;
 }

@@ -75,6 +75,7 @@ def lib():
         "orbx_batch_upload_raw": (i, [_vp, _vp, sz, sz, i, i, i, i]),
         "orbx_batch_set_rectification": (i, [_vp, _vp, _vp, sz, i, i]),
         "orbx_set_rectification": (i, [_vp, _vp, _vp, i, i, sz, i, i]),
+        "orbx_set_input_resize": (i, [_vp, i, i, i, i]),
         "orbx_extract_color": (i, [_vp, _vp, i, i, sz, i, i, i, i, _vp, _vp, i, _vp, _vp]),
         "orbx_extract_stereo_color": (i, [_vp, _vp, _vp, _vp, i, i, sz, sz, i, i, _vp, _vp, _vp, _vp, i, _vp, _vp, _vp, _vp, i, _vp, _vp]),
         "orbx_batch_synth": (i, [_vp, u32, i, i, i]),
@@ -354,6 +355,14 @@ class ORBextractor:
         mx, my = np.ascontiguousarray(map_x, np.float32), np.ascontiguousarray(map_y, np.float32)
         assert mx.shape == my.shape and mx.ndim == 2
         _check(lib().orbx_set_rectification(self._h, _p(mx), _p(my), mx.shape[1], mx.shape[0], mx.strides[0], int(src_size[0]), int(src_size[1])))
+
+    def set_input_resize(self, size, src_size):
+        """System::TrackStereoLidar's cv::resize(im, newImSize) (System.cc:250-252) in front of this extractor: afterwards __call__ /
+        extract_color take the RAW image of src_size = (width, height) and extract from its resize to size; size=None switches it off."""
+        if size is None:
+            _check(lib().orbx_set_input_resize(self._h, 0, 0, 0, 0))
+            return
+        _check(lib().orbx_set_input_resize(self._h, int(size[0]), int(size[1]), int(src_size[0]), int(src_size[1])))
 
     def extract_color(self, image, rgb, vLappingArea=(0, 0)):
         """The caller's cvtColor (Tracking.cc:1646-1671: COLOR_RGB[A]2GRAY if rgb else COLOR_BGR[A]2GRAY) on the device, then

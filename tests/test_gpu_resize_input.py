@@ -57,3 +57,31 @@ def test_resized_input_matches_oracle(sw, sh, dw, dh, channels, rgb):
     with pytest.raises(T.OrbxError):
         bx.upload_raw(raws, rgb)
     bx.close()
+
+
+def test_single_image_handles_resize_then_extract():
+    """orbx_set_input_resize on the reference-shaped handles: grey and colour raw images, eager call and CUDA-graph replays, a change of the
+    fed size, switching back to plain input and on to a rectification."""
+    ex = T.ORBextractor(*ARGS)
+    ora = po.OracleExtractor(*ARGS)
+    for (sw, sh, dw, dh, ch) in ((752, 480, 600, 350, 1), (752, 480, 600, 350, 3), (1241, 376, 1000, 303, 1)):
+        ex.set_input_resize((dw, dh), (sw, sh))
+        for rep in range(3):
+            raw = raw_image(sw, sh, 90 + rep, ch)
+            if ch == 1:
+                m, k, d = ex(raw, None, (0, 0))
+                exp = po.input_resize(raw, dw, dh)
+            else:
+                m, k, d = ex.extract_color(raw, True, (0, 0))
+                exp = po.input_resize(raw, dw, dh, rgb=True)
+            assert np.array_equal(ex.level(0), exp), (sw, sh, dw, dh, ch, rep)
+            om, ok, od = ora(exp)
+            assert m == om and k.tobytes() == ok.tobytes() and np.array_equal(d, od)
+        with pytest.raises(T.OrbxError):  # an image that is not of the raw size
+            ex(np.zeros((dh, dw), np.uint8), None, (0, 0))
+    ex.set_input_resize(None, None)
+    img = po.synth_v1(752, 480, 3)
+    m, k, d = ex(img, None, (0, 0))
+    om, ok, od = ora(img)
+    assert m == om and k.tobytes() == ok.tobytes() and np.array_equal(d, od)
+    ex.close()
