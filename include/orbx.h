@@ -248,6 +248,14 @@ int orbx_batch_search_by_projection(orbx_batch* b, int image, const orbx_proj_qu
  * reference's return value.  Same prerequisites as orbx_batch_search_by_projection; synchronises. */
 int orbx_batch_search_local_points(orbx_batch* b, int image, const orbx_proj_query* queries, int n_queries, int use_uright, float nn_ratio, int th_high,
                                    const uint8_t* taken, int* match, int* n_matches);
+/* ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const set<MapPoint*>& sAlreadyFound, th, ORBdist) (ORBmatcher.cc:1898-2019),
+ * the search of Tracking::Relocalization, from the point where a map point of the keyframe has been projected and its level predicted
+ * (ORBmatcher.cc:1947 on).  One query per surviving point, in pKF->GetMapPointMatches() order: u, v = uv; radius = th * mvScaleFactors[nPredictedLevel];
+ * min_level, max_level = nPredictedLevel - 1, nPredictedLevel + 1; angle = pKF->mvKeysUn[i].angle; blocks = 1 (here every assigned keypoint is
+ * skipped, ORBmatcher.cc:1962-1963); desc = GetDescriptor(); ur unused.  taken[k] != 0 (K host bytes or NULL) where CurrentFrame.mvpMapPoints[k]
+ * is non-NULL before the search.  orb_dist = ORBdist.  match / n_matches as for orbx_batch_search_by_projection; synchronises. */
+int orbx_batch_search_keyframe_points(orbx_batch* b, int image, const orbx_proj_query* queries, int n_queries, int check_orientation, int orb_dist,
+                                      const uint8_t* taken, int* match, int* n_matches);
 int orbx_batch_sync(orbx_batch* b);
 /* the same on a sub-range [first, first+n) of the handle's images (lapping: n x 2 ints for that range): lets a caller keep
  * many frames resident and process them in groups small enough for the 126 MB L2 */

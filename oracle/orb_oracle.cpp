@@ -845,14 +845,17 @@ struct ProjQuery {
 };
 static_assert(sizeof(ProjQuery) == 64, "orbx_proj_query layout");
 
-int search_by_projection_tail(const KeyPoint* kps, int nKps, const uint8_t* desc, const float* uRight, const int* cellStart, const int* items, float minX,
-                              float maxX, float minY, float maxY, const ProjQuery* q, int nq, int checkOrientation, int thHigh, int* match) {
+// The same loop serves ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (ORBmatcher.cc:1898-2019, relocalisation) from
+// :1947 on: no right-coordinate gate (uRight = nullptr), every assigned keypoint is skipped (:1962-1963: blocks = 1 in every query and taken0 marks the
+// keypoints that hold a point before the search), thHigh = ORBdist, angle = pKF->mvKeysUn[i].angle.
+int search_by_projection_tail(const KeyPoint* kps, int nKps, const uint8_t* desc, const float* uRight, const uint8_t* taken0, const int* cellStart, const int* items,
+                              float minX, float maxX, float minY, float maxY, const ProjQuery* q, int nq, int checkOrientation, int thHigh, int* match) {
     constexpr int HISTO_LENGTH = 30;
     std::vector<int> rotHist[HISTO_LENGTH];
     const float factor = 1.0f / HISTO_LENGTH;
     std::vector<int> cand((size_t)std::max(nKps, 1));
     std::vector<char> taken((size_t)std::max(nKps, 1), 0);  // mvpMapPoints[i2] && mvpMapPoints[i2]->Observations() > 0
-    for (int k = 0; k < nKps; ++k) match[k] = -1;
+    for (int k = 0; k < nKps; ++k) { match[k] = -1; taken[k] = taken0 ? (taken0[k] != 0) : 0; }
     int nmatches = 0;
     for (int i = 0; i < nq; ++i) {
         const ProjQuery& Q = q[i];
@@ -861,7 +864,7 @@ int search_by_projection_tail(const KeyPoint* kps, int nKps, const uint8_t* desc
         int bestDist = 256, bestIdx2 = -1;
         for (int c = 0; c < nc; ++c) {
             const int i2 = cand[c];
-            if (match[i2] >= 0 && taken[i2]) continue;
+            if (taken[i2]) continue;
             if (uRight && uRight[i2] > 0) {
                 const float er = std::fabs(Q.ur - uRight[i2]);
                 if (er > Q.radius) continue;
@@ -1005,10 +1008,10 @@ int orbo_features_in_area(const void* kps, const int* cellStart, const int* item
                           int minLevel, int maxLevel, int* out, int cap) {
     return features_in_area((const KeyPoint*)kps, cellStart, items, minX, maxX, minY, maxY, x, y, r, minLevel, maxLevel, out, cap);
 }
-int orbo_search_by_projection(const void* kps, int nKps, const uint8_t* desc, const float* uRight, const int* cellStart, const int* items, float minX,
-                              float maxX, float minY, float maxY, const void* q, int nq, int checkOrientation, int thHigh, int* match) {
-    return search_by_projection_tail((const KeyPoint*)kps, nKps, desc, uRight, cellStart, items, minX, maxX, minY, maxY, (const ProjQuery*)q, nq, checkOrientation,
-                                     thHigh, match);
+int orbo_search_by_projection(const void* kps, int nKps, const uint8_t* desc, const float* uRight, const uint8_t* taken0, const int* cellStart, const int* items,
+                              float minX, float maxX, float minY, float maxY, const void* q, int nq, int checkOrientation, int thHigh, int* match) {
+    return search_by_projection_tail((const KeyPoint*)kps, nKps, desc, uRight, taken0, cellStart, items, minX, maxX, minY, maxY, (const ProjQuery*)q, nq,
+                                     checkOrientation, thHigh, match);
 }
 int orbo_search_local_points(const void* kps, int nKps, const uint8_t* desc, const float* uRight, const uint8_t* taken0, const int* cellStart, const int* items,
                              float minX, float maxX, float minY, float maxY, const void* q, int nq, float nnRatio, int thHigh, int* match) {

@@ -50,7 +50,7 @@ def lib():
         L.orbo_stereo_match.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
         L.orbo_assign_grid.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
         L.orbo_features_in_area.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_float] * 7 + [C.c_int, C.c_int, C.c_void_p, C.c_int]
-        L.orbo_search_by_projection.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_float] * 4 + [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.orbo_search_by_projection.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_float] * 4 + [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.orbo_search_local_points.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_float] * 4 + [C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p]
         L.orbo_lapping_match.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.orbo_cvt_gray.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
@@ -218,17 +218,19 @@ def make_proj_queries(points, octaves, nobs, point_desc, scale_factors, th, mbf,
     return q
 
 
-def search_by_projection(kps, desc, uright, grid, bounds, queries, check_orientation=True, th_high=100):
+def search_by_projection(kps, desc, uright, grid, bounds, queries, check_orientation=True, th_high=100, taken=None):
     """The search of ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, ...) from ORBmatcher.cc:1729 on (see orb_oracle.cpp).
-    uright = None stands for a frame without right coordinates.  Returns (match int32 [n], nmatches)."""
+    uright = None stands for a frame without right coordinates; with uright = None, `taken` (keypoints that hold a point before the search),
+    blocks = 1 in every query and th_high = ORBdist it is the relocalisation overload (ORBmatcher.cc:1898-2019).  Returns (match int32 [n], nmatches)."""
     kps = np.ascontiguousarray(kps)
     desc = np.ascontiguousarray(desc, np.uint8)
     start, items = np.ascontiguousarray(grid[0], np.int32), np.ascontiguousarray(grid[1], np.int32)
     q = np.ascontiguousarray(queries, PROJ_QUERY_DTYPE)
     ur = None if uright is None else np.ascontiguousarray(uright, np.float32)
+    t0 = None if taken is None else np.ascontiguousarray(np.asarray(taken) != 0, np.uint8)
     match = np.empty(max(len(kps), 1), np.int32)
-    nm = lib().orbo_search_by_projection(_p(kps), len(kps), _p(desc), None if ur is None else _p(ur), _p(start), _p(items), *[float(v) for v in bounds], _p(q), len(q),
-                                         int(bool(check_orientation)), int(th_high), _p(match))
+    nm = lib().orbo_search_by_projection(_p(kps), len(kps), _p(desc), None if ur is None else _p(ur), None if t0 is None else _p(t0), _p(start), _p(items),
+                                         *[float(v) for v in bounds], _p(q), len(q), int(bool(check_orientation)), int(th_high), _p(match))
     return match[:len(kps)], nm
 
 

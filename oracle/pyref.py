@@ -221,3 +221,27 @@ def search_local_points(kps, desc, uright, taken0, bounds, scale_factors, points
     nm = _splib.refsp_search_local(_p(kps), len(kps), _p(desc), _p(ur), _p(t0), *[float(v) for v in bounds], _p(sf), len(sf), _p(pts), _p(lv), _p(nob), _p(fl), _p(pd),
                                    len(pts), float(th), float(nn_ratio), int(bool(far_points)), float(th_far), _p(match))
     return match[:len(kps)], nm
+
+
+def search_keyframe_points(kps, desc, taken0, bounds, scale_factors, points, levels, flags, point_desc, th, orb_dist, check_orientation=True):
+    """The reference's own ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (ORBmatcher.cc:1898-2019) with identity pose
+    algebra.  points: float32 [nq, 4] = (u, v, z, keyframe keypoint angle); flags bit 0 = NULL entry, bit 1 = isBad(), bit 2 = in sAlreadyFound;
+    taken0[k] != 0: CurrentFrame.mvpMapPoints[k] is non-NULL before the search.  Returns (match int32 [n], nmatches)."""
+    global _splib
+    if _splib is None:
+        _splib = C.CDLL(_LIB_SEARCH)
+        _splib.refsp_search.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p] + [C.c_float] * 4 + [C.c_void_p, C.c_int, C.c_float, C.c_float,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p]
+    _splib.refsp_search_kf.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p] + [C.c_float] * 4 + [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_void_p]
+    kps = np.ascontiguousarray(kps)
+    desc = np.ascontiguousarray(desc, np.uint8)
+    t0 = np.ascontiguousarray(taken0, np.uint8)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    pts = np.ascontiguousarray(points, np.float32).reshape(-1, 4)
+    lv, fl = np.ascontiguousarray(levels, np.int32), np.ascontiguousarray(flags, np.int32)
+    pd = np.ascontiguousarray(point_desc, np.uint8).reshape(-1, 32)
+    match = np.empty(max(len(kps), 1), np.int32)
+    nm = _splib.refsp_search_kf(_p(kps), len(kps), _p(desc), _p(t0), *[float(v) for v in bounds], _p(sf), len(sf), _p(pts), _p(lv), _p(fl), _p(pd), len(pts), float(th),
+                                int(orb_dist), int(bool(check_orientation)), _p(match))
+    return match[:len(kps)], nm

@@ -32,6 +32,7 @@ def main():
                       cut_function(matcher, "void ORBmatcher::ComputeThreeMaxima(vector<int>* histo, const int L, int &ind1, int &ind2, int &ind3)"),
                       cut_function(matcher, "int ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono)"),
                       cut_function(matcher, "float ORBmatcher::RadiusByViewingCos(const float &viewCos)"),
+                      cut_function(matcher, "int ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const set<MapPoint*> &sAlreadyFound, const float th , const int ORBdist)"),
                       cut_function(matcher, "int ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, const float th, const bool bFarPoints, const float thFarPoints)")]
     glue_top = r'''
 #include <algorithm>
@@ -39,12 +40,18 @@ def main():
 #include <climits>
 #include <cmath>
 #include <cstring>
+#include <set>
 #include <vector>
 #include "opencv2/cvstub.hpp"
 using namespace std;
 ''' + defs + r'''
-namespace Eigen {   // stand-ins: plain containers, no arithmetic
-struct Vector3f { float d[3]; float operator()(int i) const { return d[i]; } };
+namespace Eigen {   // stand-ins: plain containers; the only arithmetic is the distance the relocalisation search range-checks
+struct Vector3f {
+    float d[3];
+    float operator()(int i) const { return d[i]; }
+    Vector3f operator-(const Vector3f& o) const { return Vector3f{{d[0] - o.d[0], d[1] - o.d[1], d[2] - o.d[2]}}; }
+    float norm() const { return std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]); }
+};
 struct Vector2f { float d[2]; float operator()(int i) const { return d[i]; } };
 }
 namespace Sophus {  // stand-in: `T * x` is the identity, or a constant for the last-frame pose (-> tlc)
@@ -64,6 +71,10 @@ struct MapPoint {
     float mTrackProjX = 0, mTrackProjY = 0, mTrackDepth = 0, mTrackDepthR = 0, mTrackProjXR = 0, mTrackProjYR = 0, mTrackViewCos = 0, mTrackViewCosR = 0;
     int mnTrackScaleLevel = 0, mnTrackScaleLevelR = -1;
     bool isBad() { return bad; }
+    int predictedLevel = 0;     // relocalisation search: what PredictScale returns
+    float GetMaxDistanceInvariance() { return 1e30f; }
+    float GetMinDistanceInvariance() { return 0.f; }
+    template <class F> int PredictScale(const float&, F*) { return predictedLevel; }
     Eigen::Vector3f GetWorldPos() { return pos; }
     cv::Mat GetDescriptor() { return desc; }
     int Observations() { return nObs; }
@@ -91,6 +102,11 @@ struct Frame {
     vector<size_t> GetFeaturesInArea(const float &x, const float  &y, const float  &r, const int minLevel=-1, const int maxLevel=-1, const bool bRight = false) const;
 };
 float Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv, Frame::mnMinX, Frame::mnMaxX, Frame::mnMinY, Frame::mnMaxY;
+struct KeyFrame {
+    std::vector<MapPoint*> mps;
+    std::vector<cv::KeyPoint> mvKeysUn;
+    std::vector<MapPoint*> GetMapPointMatches() { return mps; }
+};
 struct ORBmatcher {
     static const int TH_LOW, TH_HIGH, HISTO_LENGTH;
     float mfNNratio; bool mbCheckOrientation;
@@ -98,6 +114,7 @@ struct ORBmatcher {
     void ComputeThreeMaxima(std::vector<int>* histo, const int L, int &ind1, int &ind2, int &ind3);
     int SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono);
     int SearchByProjection(Frame &F, const std::vector<MapPoint*> &vpMapPoints, const float th=3, const bool bFarPoints = false, const float thFarPoints = 50.0f);
+    int SearchByProjection(Frame &CurrentFrame, KeyFrame* pKF, const std::set<MapPoint*> &sAlreadyFound, const float th, const int ORBdist);
     float RadiusByViewingCos(const float &viewCos);
 };
 ''' + consts + "\n"
@@ -181,6 +198,50 @@ extern "C" int refsp_search_local(const void* kps, int n, const unsigned char* d
     for (int k = 0; k < n; ++k) {
         MapPoint* p = F.mvpMapPoints[k];
         match[k] = (p && p != &held && p != &heldFree) ? (int)(p - pts.data()) : -1;
+    }
+    return nm;
+}
+'''
+    glue_bottom += r'''
+// relocalisation overload: points: nq x {u, v, z, keyframe keypoint angle} floats; levels: predicted levels; flags: bit 0 = NULL entry of the keyframe,
+// bit 1 = isBad(), bit 2 = in sAlreadyFound; taken0[k] != 0: CurrentFrame.mvpMapPoints[k] is non-NULL before the search
+extern "C" int refsp_search_kf(const void* kps, int n, const unsigned char* desc, const unsigned char* taken0, float minX, float maxX, float minY, float maxY,
+                               const float* scaleFactors, int nlevels, const float* points, const int* levels, const int* flags, const unsigned char* pdesc, int nq,
+                               float th, int orbDist, int checkOrientation, int* match) {
+    Frame cur;
+    GeometricCamera cam;
+    cur.N = n; cur.Nleft = -1;
+    cur.mvKeys.assign((const cv::KeyPoint*)kps, (const cv::KeyPoint*)kps + n);
+    cur.mvKeysUn = cur.mvKeys;
+    cur.mvScaleFactors.assign(scaleFactors, scaleFactors + nlevels);
+    cur.mDescriptors = cv::Mat(n, 32, CV_8U, (void*)desc, 32);
+    cur.mpCamera = &cam;
+    Frame::mnMinX = minX; Frame::mnMaxX = maxX; Frame::mnMinY = minY; Frame::mnMaxY = maxY;
+    Frame::mfGridElementWidthInv = static_cast<float>(FRAME_GRID_COLS) / (Frame::mnMaxX - Frame::mnMinX);
+    Frame::mfGridElementHeightInv = static_cast<float>(FRAME_GRID_ROWS) / (Frame::mnMaxY - Frame::mnMinY);
+    cur.AssignFeaturesToGrid();
+    MapPoint held;
+    cur.mvpMapPoints.assign(n, nullptr);
+    for (int k = 0; k < n; ++k) if (taken0[k]) cur.mvpMapPoints[k] = &held;
+    std::vector<MapPoint> pts(nq);
+    KeyFrame kf;
+    kf.mps.resize(nq); kf.mvKeysUn.resize(nq);
+    std::set<MapPoint*> found;
+    for (int i = 0; i < nq; ++i) {
+        MapPoint& P = pts[i];
+        P.pos = Eigen::Vector3f{{points[4 * i], points[4 * i + 1], points[4 * i + 2]}};
+        P.desc = cv::Mat(1, 32, CV_8U, (void*)(pdesc + 32 * (size_t)i), 32);
+        P.predictedLevel = levels[i]; P.bad = (flags[i] & 2) != 0; P.nObs = 1;
+        kf.mps[i] = (flags[i] & 1) ? nullptr : &P;
+        if (flags[i] & 4) found.insert(&P);
+        kf.mvKeysUn[i].angle = points[4 * i + 3];
+    }
+    ORBmatcher m;
+    m.mfNNratio = 0.9f; m.mbCheckOrientation = checkOrientation != 0;
+    const int nm = m.SearchByProjection(cur, &kf, found, th, orbDist);
+    for (int k = 0; k < n; ++k) {
+        MapPoint* p = cur.mvpMapPoints[k];
+        match[k] = (p && p != &held) ? (int)(p - pts.data()) : -1;
     }
     return nm;
 }

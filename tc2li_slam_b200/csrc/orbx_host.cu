@@ -874,14 +874,14 @@ static int search_common(orbx_batch* b, bool local, int image, const orbx_proj_q
     }
     if (n_queries) CU(cudaMemcpyAsync(b->spDev, queries, (size_t)n_queries * sizeof(orbx_proj_query), cudaMemcpyHostToDevice, b->stream));
     uint8_t* takenDev = reinterpret_cast<uint8_t*>(b->spOut + K + 2);
-    if (local && taken) CU(cudaMemcpyAsync(takenDev, taken, (size_t)K, cudaMemcpyHostToDevice, b->stream));
+    if (taken) CU(cudaMemcpyAsync(takenDev, taken, (size_t)K, cudaMemcpyHostToDevice, b->stream));
     Buffers buf = b->buf;
     buf.imgBase = 0;
     if (local)
         launch_search_local_points(buf, image, K, b->gridParams, b->spDev, n_queries, use_uright ? 1 : 0, th_high, nn_ratio, taken ? takenDev : nullptr, candCap, stageDesc, b->spOut,
                                    b->spOut + K, b->stream);
     else
-        launch_search_by_projection(buf, image, K, b->gridParams, b->spDev, n_queries, use_uright ? 1 : 0, check_orientation ? 1 : 0, th_high, candCap, stageDesc, b->spOut,
+        launch_search_by_projection(buf, image, K, b->gridParams, b->spDev, n_queries, use_uright ? 1 : 0, check_orientation ? 1 : 0, th_high, taken ? takenDev : nullptr, candCap, stageDesc, b->spOut,
                                     b->spOut + K, b->stream);
     CU(cudaGetLastError());
     int info[2] = {0, 0};
@@ -897,6 +897,12 @@ static int search_common(orbx_batch* b, bool local, int image, const orbx_proj_q
 int orbx_batch_search_by_projection(orbx_batch* b, int image, const orbx_proj_query* queries, int n_queries, int use_uright, int check_orientation, int th_high,
                                     int* match, int* n_matches) {
     return search_common(b, false, image, queries, n_queries, use_uright, check_orientation, th_high, 0.f, nullptr, match, n_matches);
+}
+
+// ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (ORBmatcher.cc:1898-2019), the relocalisation search, behind its projection
+int orbx_batch_search_keyframe_points(orbx_batch* b, int image, const orbx_proj_query* queries, int n_queries, int check_orientation, int orb_dist,
+                                      const uint8_t* taken, int* match, int* n_matches) {
+    return search_common(b, false, image, queries, n_queries, 0, check_orientation, orb_dist, 0.f, taken, match, n_matches);
 }
 
 // ORBmatcher::SearchByProjection(F, vpMapPoints, th, bFarPoints, thFarPoints) (ORBmatcher.cc:52-222), the local-map search

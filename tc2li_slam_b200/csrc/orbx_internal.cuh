@@ -160,7 +160,7 @@ void launch_features_in_area(const Buffers& b, int K, const GridParams& p, const
 size_t search_smem_bytes(int K, int nq, int candCap, int stageDesc);
 cudaError_t search_configure();
 void launch_search_by_projection(const Buffers& b, int image, int K, const GridParams& p, const orbx_proj_query* queries, int nq, int useURight, int checkOrientation,
-                                 int thHigh, int candCap, int stageDesc, int* outMatch, int* outInfo, cudaStream_t s);
+                                 int thHigh, const uint8_t* taken0, int candCap, int stageDesc, int* outMatch, int* outInfo, cudaStream_t s);
 
 void launch_search_local_points(const Buffers& b, int image, int K, const GridParams& p, const orbx_proj_query* queries, int nq, int useURight, int thHigh, float nnRatio,
                                 const uint8_t* taken0, int candCap, int stageDesc, int* outMatch, int* outInfo, cudaStream_t s);

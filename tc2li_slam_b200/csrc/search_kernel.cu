@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(ST) k_search_by_projection(const Buffers b, in
     // memory only for the 32-byte descriptors of their hits
     for (int k = tid; k < K; k += ST) {
         match[k] = -1;
-        taken[k] = (LOCAL && taken0 && k < n) ? (taken0[k] != 0) : 0;
+        taken[k] = (taken0 && k < n) ? (taken0[k] != 0) : 0;
         if (k < n) {
             const orbx_keypoint kp = kps[k];
             kxy[k] = make_float2(kp.x, kp.y);
@@ -308,9 +308,9 @@ cudaError_t search_configure() {
 }
 
 void launch_search_by_projection(const Buffers& b, int image, int K, const GridParams& p, const orbx_proj_query* queries, int nq, int useURight, int checkOrientation,
-                                 int thHigh, int candCap, int stageDesc, int* outMatch, int* outInfo, cudaStream_t s) {
+                                 int thHigh, const uint8_t* taken0, int candCap, int stageDesc, int* outMatch, int* outInfo, cudaStream_t s) {
     k_search_by_projection<false><<<1, ST, search_smem_bytes(K, nq, candCap, stageDesc), s>>>(b, image, K, p, queries, nq, useURight, checkOrientation, thHigh, 0.f,
-                                                                                             nullptr, candCap, stageDesc, outMatch, outInfo);
+                                                                                             taken0, candCap, stageDesc, outMatch, outInfo);
 }
 
 void launch_search_local_points(const Buffers& b, int image, int K, const GridParams& p, const orbx_proj_query* queries, int nq, int useURight, int thHigh, float nnRatio,

@@ -95,6 +95,7 @@ def lib():
         "orbx_batch_search_by_projection": (i, [_vp, i, _vp, i, i, i, i, _vp, _vp]),
         "orbx_batch_search_local_points": (i, [_vp, i, _vp, i, i, f, i, _vp, _vp, _vp]),
         "orbx_batch_set_input_resize": (i, [_vp, i, i]),
+        "orbx_batch_search_keyframe_points": (i, [_vp, i, _vp, i, i, i, _vp, _vp, _vp]),
         "orbx_batch_run_range": (i, [_vp, i, i, _vp]),
         "orbx_batch_run_pipelined": (i, [_vp, i, _vp, i]),
         "orbx_batch_download_async": (i, [_vp, i, i, _vp, _vp, _vp, _vp]),
@@ -628,6 +629,19 @@ class BatchExtractor:
         match, nm = np.empty(self.K, np.int32), C.c_int(0)
         _check(lib().orbx_batch_search_by_projection(self._h, int(image), _p(q), len(q), int(bool(use_uright)), int(bool(check_orientation)), int(th_high),
                                                      _p(match), C.byref(nm)))
+        return match, nm.value
+
+    def search_keyframe_points(self, image, queries, taken=None, check_orientation=True, orb_dist=100):
+        """ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (ORBmatcher.cc:1898-2019, Tracking::Relocalization) behind its
+        projection; taken: per-keypoint flags (CurrentFrame.mvpMapPoints[k] non-NULL).  Returns (match int32 [K], nmatches)."""
+        q = np.ascontiguousarray(np.asarray(queries, dtype=PROJ_QUERY_DTYPE))
+        t = None
+        if taken is not None:
+            t = np.zeros(self.K, np.uint8)
+            t[:len(taken)] = np.asarray(taken) != 0
+        match, nm = np.empty(self.K, np.int32), C.c_int(0)
+        _check(lib().orbx_batch_search_keyframe_points(self._h, int(image), _p(q), len(q), int(bool(check_orientation)), int(orb_dist),
+                                                       _p(t) if t is not None else None, _p(match), C.byref(nm)))
         return match, nm.value
 
     def search_local_points(self, image, queries, taken=None, use_uright=True, nn_ratio=0.8, th_high=100):

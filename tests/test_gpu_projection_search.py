@@ -156,3 +156,26 @@ def test_search_through_the_single_image_handles():
     os_, oi = po.assign_grid(kl, bounds)
     assert np.array_equal(start[0], os_) and np.array_equal(items[0, :os_[-1]], oi)
     st.close()
+
+
+@pytest.mark.parametrize("seed,th,dist,check", [(41, 10.0, 100, True), (42, 3.0, 64, True), (43, 10.0, 100, False)])
+def test_relocalisation_search_matches_oracle(seed, th, dist, check):
+    """ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) behind its projection: every assigned keypoint blocks, keypoints
+    that already hold a point are an input, no right-coordinate gate."""
+    w, h, args = 1241, 376, (2000, 1.2, 8, 20, 7)
+    rng = np.random.default_rng(seed)
+    bx = T.BatchExtractor(w, h, 2, *args)
+    kc, dc, _ = make_case(bx, w, h, seed, 5, rng)
+    pts, octv, nobs, pd, sf = points_from(args, w, h, seed, 5, rng)
+    q = np.zeros(len(pts), T.PROJ_QUERY_DTYPE)
+    q["u"], q["v"], q["angle"] = pts[:, 0], pts[:, 1], pts[:, 3]
+    q["radius"] = np.float32(th) * sf[octv]
+    q["min_level"], q["max_level"], q["blocks"] = octv - 1, octv + 1, 1
+    q["desc"] = pd
+    taken = rng.random(len(kc)) < 0.3
+    bounds = (0.0, float(w), 0.0, float(h))
+    om, on = po.search_by_projection(kc, dc, None, po.assign_grid(kc, bounds), bounds, q.view(po.PROJ_QUERY_DTYPE), check, dist, taken)
+    m, nm = bx.search_keyframe_points(0, q, taken, check, dist)
+    assert nm == on and on > 20 and np.array_equal(m[:len(kc)], om)
+    assert not (m[:len(kc)][taken] >= 0).any()
+    bx.close()

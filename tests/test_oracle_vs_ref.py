@@ -241,3 +241,29 @@ def test_search_local_points_matches_reference_body(seed, th, ratio, far):
     om, on = po.search_local_points(kc, dc, ur, taken0 == 1, po.assign_grid(kc, bounds), bounds, q, ratio)
     assert rn == on and rn > 100, (rn, on)
     assert np.array_equal(rm, np.where(om >= 0, sel[np.maximum(om, 0)], -1)), int((rm != np.where(om >= 0, sel[np.maximum(om, 0)], -1)).sum())
+
+
+def keyframe_queries(pts, lv, flags, pd, sf, th):
+    """The map points the relocalisation search actually looks for (ORBmatcher.cc:1915-1947: non-NULL, not bad, not already found; the bounds and
+    distance tests pass here), as queries."""
+    sel = np.nonzero((flags & 7) == 0)[0]
+    q = np.zeros(len(sel), po.PROJ_QUERY_DTYPE)
+    q["u"], q["v"], q["angle"] = pts[sel, 0], pts[sel, 1], pts[sel, 3]
+    q["radius"] = np.float32(th) * np.ascontiguousarray(sf, np.float32)[lv[sel]]
+    q["min_level"], q["max_level"], q["blocks"] = lv[sel] - 1, lv[sel] + 1, 1
+    q["desc"] = pd[sel]
+    return q, sel
+
+
+@pytest.mark.skipif(not pyref.search_available(), reason="oracle/_ref/libref_search.so not built (needs /root/reference once)")
+@pytest.mark.parametrize("seed,th,dist,check", [(11, 10.0, 100, True), (12, 3.0, 64, True), (13, 10.0, 100, False)])
+def test_search_keyframe_points_matches_reference_body(seed, th, dist, check):
+    kc, dc, _, bounds, sf, pts, octv, nobs, pd = projection_case(seed)
+    rng = np.random.default_rng(seed)
+    flags = (rng.random(len(pts)) < 0.05).astype(np.int32) | ((rng.random(len(pts)) < 0.05).astype(np.int32) << 1) | ((rng.random(len(pts)) < 0.2).astype(np.int32) << 2)
+    taken0 = (rng.random(len(kc)) < 0.3).astype(np.uint8)
+    rm, rn = pyref.search_keyframe_points(kc, dc, taken0, bounds, sf, pts, octv, flags, pd, th, dist, check)
+    q, sel = keyframe_queries(pts, octv, flags, pd, sf, th)
+    om, on = po.search_by_projection(kc, dc, None, po.assign_grid(kc, bounds), bounds, q, check, dist, taken0)
+    assert rn == on and rn > 20, (rn, on)
+    assert np.array_equal(rm, np.where(om >= 0, sel[np.maximum(om, 0)], -1))
