@@ -93,3 +93,15 @@ def test_no_gpu_means_loud_failure():
     rc = T.lib().orbx_create(2000, 1.2, 8, 20, 7, 99, ctypes.byref(h))  # device 99 never exists
     assert rc == orbx.ERR_CUDA and not h.value
     assert b"CUDA" in T.lib().orbx_last_error()
+
+
+def test_query_record_layouts_match_the_c_structs():
+    """orbx_area_query (6 x 4 bytes) and orbx_proj_query (8 x 4 + 32 bytes) as numpy records, and the oracle's copy of the latter."""
+    import tc2li_slam_b200 as T
+    from oracle import pyoracle as po
+    assert T.AREA_QUERY_DTYPE.itemsize == 24 and T.PROJ_QUERY_DTYPE.itemsize == 64 and po.PROJ_QUERY_DTYPE == T.PROJ_QUERY_DTYPE
+    assert [T.PROJ_QUERY_DTYPE.fields[n][1] for n in ("u", "v", "radius", "ur", "min_level", "max_level", "angle", "blocks", "desc")] == [0, 4, 8, 12, 16, 20, 24, 28, 32]
+    hdr = open(os.path.join(ROOT, "include", "orbx.h")).read()
+    for name in ("orbx_batch_assign_grid", "orbx_batch_features_in_area", "orbx_batch_search_by_projection", "orbx_batch_search_local_points",
+                 "orbx_batch_search_keyframe_points", "orbx_batch_set_input_resize", "orbx_set_input_resize"):
+        assert name in hdr
