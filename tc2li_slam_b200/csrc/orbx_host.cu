@@ -154,6 +154,10 @@ struct orbx_batch {
     bool lapStable = false;   // the `lapping` pointer given to run stays valid and pinned (single-image handle): copy from it directly
     int fastTileRows = 0, fastTs = 64, numSMs = 148;
     FastMaps fastMaps;
+    // dense band pass (fast_band_kernel.cu), the default FAST stage; ORBX_FAST=cells selects the warp-per-cell kernel instead
+    bool fastBand = true;
+    FastBand* bandTab = nullptr; uint8_t* bandAux = nullptr; int* bandCtr = nullptr;   // bandCtr: one dynamic work counter per lane
+    int nBands = 0, bandRows = 0, bandTp = 0;
     LevelMaps blurMaps, resizeMaps;
     DescMaps descMaps;
     float *rectX = nullptr, *rectY = nullptr;  // resident rectification maps [height][width] (System.cc:238-248), null = none
@@ -283,6 +287,25 @@ int batch_alloc(orbx_batch* b) {
         CU(cudaMemcpy(dtab, tab.data(), tab.size() * sizeof(uint4), cudaMemcpyHostToDevice));
         B.cellTab = dtab;
         CU(fast_configure(b->fastTileRows, b->fastTs));
+        {
+            const char* fv = std::getenv("ORBX_FAST");
+            b->fastBand = !(fv && std::string(fv) == "cells");
+            std::vector<FastBand> bands;
+            std::vector<uint8_t> aux, flags;
+            b->bandTp = fast_band_pick_tp(g);
+            if (make_fast_bands(g, b->bandTp, bands, aux, flags, &b->bandRows)) return fail(ORBX_ERR_TOO_LARGE, "FAST band table: a cell does not fit the shared-memory tile");
+            b->nBands = (int)bands.size();
+            if ((r = dev_alloc(b, &b->bandTab, bands.size()))) return r;
+            if ((r = dev_alloc(b, &b->bandAux, aux.size() + 16))) return r;
+            if ((r = dev_alloc(b, &b->bandCtr, (size_t)orbx_batch::kLanes))) return r;
+            CU(cudaMemcpy(b->bandTab, bands.data(), bands.size() * sizeof(FastBand), cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(b->bandAux, aux.data(), aux.size(), cudaMemcpyHostToDevice));
+            CU(fast_band_configure());
+            // flags of the cells without FAST work never change: written once for every image (the kernel overwrites the others)
+            std::vector<uint8_t> all((size_t)n * g.cellsPerImage);
+            for (int i = 0; i < n; ++i) std::memcpy(all.data() + (size_t)i * g.cellsPerImage, flags.data(), flags.size());
+            CU(cudaMemcpy(B.cellFlags, all.data(), all.size(), cudaMemcpyHostToDevice));
+        }
         if (fast_encode_maps(g, B.pyr, n, b->fastTs, &b->fastMaps)) return fail(ORBX_ERR_CUDA, "cuTensorMapEncodeTiled failed (FAST tiles)");
         if (blur_encode_maps(g, B.pyr, n, &b->blurMaps)) return fail(ORBX_ERR_CUDA, "cuTensorMapEncodeTiled failed (blur tiles)");
         if (resize_encode_maps(g, B.pyr, n, &b->resizeMaps)) return fail(ORBX_ERR_CUDA, "cuTensorMapEncodeTiled failed (resize tiles)");
@@ -681,7 +704,9 @@ static int run_range_lane(orbx_batch* b, int first, int n, const int* lapping, i
     const bool blurFirst = b->sched == 0 || b->sched == 3 || b->sched == 4;
     if (overlap && blurFirst) { int r = blur_on_side(); if (r) return r; }
     if (overlap && b->sched == 1) CU(cudaEventRecord(evPyr, s));
-    launch_fast(g, buf, b->fastMaps, n, b->fastTileRows, b->fastTs, b->numSMs, s); ++launches;
+    if (b->fastBand) launch_fast_band(g, buf, b->bandTab, b->bandAux, b->nBands, b->bandRows, b->bandTp, n, b->numSMs, b->bandCtr + lane, s);
+    else launch_fast(g, buf, b->fastMaps, n, b->fastTileRows, b->fastTs, b->numSMs, s);
+    ++launches;
     if (overlap && b->sched == 1) {  // the blur is enqueued after FAST but still only waits for the pyramid
         CU(cudaStreamWaitEvent(side, evPyr, 0));
         for (int l = 0; l < g.nlevels; ++l) { launch_blur(g, buf, b->blurMaps, l, n, b->taps, side); ++launches; }
