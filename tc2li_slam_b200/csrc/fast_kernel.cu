@@ -179,9 +179,7 @@ __device__ __forceinline__ void emit(const CellCtx& c, const uint16_t* surv, int
 
 }  // namespace
 
-// REDO = false: every cell, iniThFAST first and minThFAST for the cells that kept nothing (the warp-per-cell FAST stage, ORBX_FAST=cells).
-// REDO = true : only the cells the streaming strip pass (fast_strip_kernel.cu) left marked "kept nothing" (flag 2), at minThFAST only.
-template <int TS, bool REDO>
+template <int TS>
 __global__ void __launch_bounds__(32 * FW) k_fast_cells(const __grid_constant__ Geom g, const Buffers b, const __grid_constant__ FastMaps maps,
                                                        int nCells, int nWork, int tileBytes) {
     extern __shared__ __align__(128) unsigned char fsm[];
@@ -210,7 +208,7 @@ __global__ void __launch_bounds__(32 * FW) k_fast_cells(const __grid_constant__ 
         tma_load_3d(my + buf * tileBytes, &maps.m[level], &bars[wid][buf], (kMarginX + iniX) & ~15, kMarginY + iniY, b.imgBase + img);
     };
     // one cell: wait for its crop, FAST + NMS at iniThFAST (attempt 0) and / or minThFAST (attempt 1), candidates and the cell's flag
-    auto run_cell = [&](int imgRel, int cellIdx, int buf, int attempt0) {
+    auto run_cell = [&](int imgRel, int cellIdx, int buf) {
         const int img = b.imgBase + imgRel;
         const uint4 cd = __ldg(b.cellTab + cellIdx);
         const int iniX = cd.x & 0xFFFF, iniY = cd.x >> 16;
@@ -233,7 +231,7 @@ __global__ void __launch_bounds__(32 * FW) k_fast_cells(const __grid_constant__ 
         int* candCount = b.candCount + img * ORBX_MAX_LEVELS + level;
         const int relX = iniX - kBorder, relY = iniY - kBorder;
         int nsTotal = 0;
-        int attempt = attempt0;
+        int attempt = 0;
         for (;; ++attempt) {
             const int t = attempt == 0 ? g.iniTh : g.minTh;
             c.nw = 0; c.n1 = 0; c.n2 = 0; c.flushedB = false;
@@ -244,8 +242,6 @@ __global__ void __launch_bounds__(32 * FW) k_fast_cells(const __grid_constant__ 
                 // IMAD at each of its four uses and the shared-window base with four uniform instructions per trip.
                 const uint32_t kAdd = __shfl_sync(FULL, (uint32_t)(0x7f - (t & 0x7f)) * 0x01010101u, 0);
                 const uint32_t nh = t >= 128 ? 0u : 0xFFFFFFFFu;
-                const uint32_t one = __shfl_sync(FULL, 1u, 0);
-                (void)one;
                 const uint32_t tileS = __shfl_sync(FULL, smem_u32(tileW), 0);  // shared-window address for the explicit ld.shared below
                 // bytes outside the interior [0, iw) can only sit in the first / last word of a row
                 const int xb0 = 4 * wFirst - 3 - shift;  // interior x of byte 0 of the first word (<= 0)
@@ -270,27 +266,12 @@ __global__ void __launch_bounds__(32 * FW) k_fast_cells(const __grid_constant__ 
                     asm volatile("ld.shared.u32 %0, [%5];\n\tld.shared.u32 %1, [%5+-4];\n\tld.shared.u32 %2, [%5+4];\n\tld.shared.u32 %3, [%5+%6];\n\tld.shared.u32 %4, [%5+-%6];"
                                  : "=r"(cur), "=r"(prev), "=r"(next), "=r"(up), "=r"(dn)
                                  : "r"(tileS + 4u * (uint32_t)wo), "n"(3 * TS));
-#ifdef FAST_IMAD_FUNNEL
-                    // funnel shifts on the FMA pipe: (hi : lo) >> s = hi * 2^(32 - s) + (lo >> s), the latter as the high half of lo * 2^(32 - s)
-                    uint32_t e, wv;
-                    asm("{\n\t.reg .u32 t;\n\tmul.hi.u32 t, %1, 256;\n\tmad.lo.u32 %0, %2, 256, t;\n\t}" : "=r"(e) : "r"(cur), "r"(next));
-                    asm("{\n\t.reg .u32 t;\n\tmul.hi.u32 t, %1, 16777216;\n\tmad.lo.u32 %0, %2, 16777216, t;\n\t}" : "=r"(wv) : "r"(prev), "r"(cur));
-#else
                     const uint32_t e = __funnelshift_r(cur, next, 24);  // pixels at x + 3
                     const uint32_t wv = __funnelshift_r(prev, cur, 8);  // pixels at x - 3
-#endif
                     if (decltype(LOWT)::value) {
                         const uint32_t dN = __vabsdiffu4(up, cur), dS = __vabsdiffu4(dn, cur), dE = __vabsdiffu4(e, cur), dW4 = __vabsdiffu4(wv, cur);
                         // (a carry out of a byte >= 128 can only ADD a survivor one byte up, at d == t there: the exact score of pass A2 decides)
-#ifdef FAST_IMAD_ADD
-                        uint32_t lN, lS, lE, lW;   // x * one + kAdd: an IMAD (FMA pipe) as long as ptxas cannot see that one == 1
-                        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(lN) : "r"(dN), "r"(one), "r"(kAdd));
-                        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(lS) : "r"(dS), "r"(one), "r"(kAdd));
-                        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(lE) : "r"(dE), "r"(one), "r"(kAdd));
-                        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(lW) : "r"(dW4), "r"(one), "r"(kAdd));
-#else
                         const uint32_t lN = dN + kAdd, lS = dS + kAdd, lE = dE + kAdd, lW = dW4 + kAdd;
-#endif
                         const uint32_t a = lN | dN | lS, bq = lE | dE | lW;
                         return ((a | dS) & m) & (bq | dW4);
                     }
@@ -400,28 +381,7 @@ __global__ void __launch_bounds__(32 * FW) k_fast_cells(const __grid_constant__ 
         if (lane == 0) *flag = (attempt == 0) ? 1 : 2;
         __syncwarp();  // every lane is done with this tile buffer before lane 0 re-arms it
     };
-    const int w0 = blockIdx.x * FW + wid;
-    if (REDO) {
-        // 32 work items per trip: a lane looks at one cell's flag, the warp then redoes the marked ones one after the other
-        for (int chunk = w0; chunk * 32 < nWork; chunk += stride) {
-            const int it = chunk * 32 + lane;
-            bool need = false;
-            if (it < nWork) {
-                const int ir = it / nCells, ce = it - ir * nCells;
-                need = (__ldg(&b.cellTab[ce].y) >> 24) == 2 && b.cellFlags[(size_t)(b.imgBase + ir) * g.cellsPerImage + ce] == 2;
-            }
-            unsigned todo = __ballot_sync(FULL, need);
-            while (todo) {
-                const int j = __ffs(todo) - 1;
-                todo &= todo - 1;
-                const int itj = chunk * 32 + j, ir = itj / nCells, ce = itj - ir * nCells;
-                if (lane == 0) issue(ir, ce, 0);
-                run_cell(ir, ce, 0, 1);
-            }
-        }
-        return;
-    }
-    int w = w0;
+    int w = blockIdx.x * FW + wid;
     // (image, cell) of the work item, walked incrementally: `stride` items further is dImg images and dCell cells on
     const int dImg = stride / nCells, dCell = stride - dImg * nCells;
     int imgRel = w / nCells, cellIdx = w - imgRel * nCells;
@@ -436,7 +396,7 @@ __global__ void __launch_bounds__(32 * FW) k_fast_cells(const __grid_constant__ 
             }
         } else if (lane == 0 && it > 0)
             issue(imgRel, cellIdx, 0);
-        run_cell(imgRel, cellIdx, buf, 0);
+        run_cell(imgRel, cellIdx, buf);
     }
 }
 
@@ -481,10 +441,8 @@ cudaError_t fast_configure(int tileRows, int ts) {
     static int configured = 0;
     const int want = std::max(smem, 48 * 1024);
     if (want <= configured) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(k_fast_cells<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fast_cells<96, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fast_cells<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fast_cells<96, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+    cudaError_t e = cudaFuncSetAttribute(k_fast_cells<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fast_cells<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
     if (e == cudaSuccess) configured = want;
     return e;
 }
@@ -504,22 +462,9 @@ void launch_fast(const Geom& g, const Buffers& b, const FastMaps& maps, int nIma
     const int nWork = g.cellsPerImage * nImages;
     const int grid = std::min((nWork + FW - 1) / FW, numSMs * ctasPerSM);
     if (ts == 64)
-        k_fast_cells<64, false><<<grid, 32 * FW, smem, s>>>(g, b, maps, g.cellsPerImage, nWork, tileRows * ts);
+        k_fast_cells<64><<<grid, 32 * FW, smem, s>>>(g, b, maps, g.cellsPerImage, nWork, tileRows * ts);
     else
-        k_fast_cells<96, false><<<grid, 32 * FW, smem, s>>>(g, b, maps, g.cellsPerImage, nWork, tileRows * ts);
-}
-
-// the cells the strip pass marked "kept nothing at iniThFAST" again, at minThFAST (ORBextractor.cc:817-820)
-void launch_fast_redo(const Geom& g, const Buffers& b, const FastMaps& maps, int nImages, int tileRows, int ts, int numSMs, cudaStream_t s) {
-    if (g.iniTh == g.minTh) return;  // the redo would find the same nothing
-    const size_t smem = FW * fast_warp_bytes(tileRows, ts);
-    const int ctasPerSM = std::max(1, std::min(32, (int)((227 * 1024) / (smem + 1024 + 64))));
-    const int nWork = g.cellsPerImage * nImages;
-    const int grid = std::min(((nWork + 31) / 32 + FW - 1) / FW, numSMs * ctasPerSM);
-    if (ts == 64)
-        k_fast_cells<64, true><<<grid, 32 * FW, smem, s>>>(g, b, maps, g.cellsPerImage, nWork, tileRows * ts);
-    else
-        k_fast_cells<96, true><<<grid, 32 * FW, smem, s>>>(g, b, maps, g.cellsPerImage, nWork, tileRows * ts);
+        k_fast_cells<96><<<grid, 32 * FW, smem, s>>>(g, b, maps, g.cellsPerImage, nWork, tileRows * ts);
 }
 
 }  // namespace orbx

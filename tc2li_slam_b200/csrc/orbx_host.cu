@@ -154,12 +154,6 @@ struct orbx_batch {
     bool lapStable = false;   // the `lapping` pointer given to run stays valid and pinned (single-image handle): copy from it directly
     int fastTileRows = 0, fastTs = 64, numSMs = 148;
     FastMaps fastMaps;
-    // FAST stage: 0 = streaming strip pass + redo of the marked cells (default), 1 = dense band pass (ORBX_FAST=band), 2 = warp per cell (ORBX_FAST=cells)
-    int fastImpl = 0;
-    FastStrip* stripTab = nullptr; uint8_t* stripAux = nullptr; int nStrips = 0;
-    StripMaps stripMaps;
-    FastBand* bandTab = nullptr; uint8_t* bandAux = nullptr; int* bandCtr = nullptr;   // bandCtr: one dynamic work counter per lane
-    int nBands = 0, bandRows = 0, bandTp = 0;
     LevelMaps blurMaps, resizeMaps;
     DescMaps descMaps;
     float *rectX = nullptr, *rectY = nullptr;  // resident rectification maps [height][width] (System.cc:238-248), null = none
@@ -289,38 +283,6 @@ int batch_alloc(orbx_batch* b) {
         CU(cudaMemcpy(dtab, tab.data(), tab.size() * sizeof(uint4), cudaMemcpyHostToDevice));
         B.cellTab = dtab;
         CU(fast_configure(b->fastTileRows, b->fastTs));
-        {
-            const char* fv = std::getenv("ORBX_FAST");
-            b->fastImpl = fv && std::string(fv) == "cells" ? 2 : fv && std::string(fv) == "band" ? 1 : 0;
-            std::vector<FastBand> bands;
-            std::vector<uint8_t> aux, flags;
-            b->bandTp = fast_band_pick_tp(g);
-            if (make_fast_bands(g, b->bandTp, bands, aux, flags, &b->bandRows)) return fail(ORBX_ERR_TOO_LARGE, "FAST band table: a cell does not fit the shared-memory tile");
-            b->nBands = (int)bands.size();
-            if ((r = dev_alloc(b, &b->bandTab, bands.size()))) return r;
-            if ((r = dev_alloc(b, &b->bandAux, aux.size() + 16))) return r;
-            if ((r = dev_alloc(b, &b->bandCtr, (size_t)orbx_batch::kLanes))) return r;
-            CU(cudaMemcpy(b->bandTab, bands.data(), bands.size() * sizeof(FastBand), cudaMemcpyHostToDevice));
-            CU(cudaMemcpy(b->bandAux, aux.data(), aux.size(), cudaMemcpyHostToDevice));
-            CU(fast_band_configure());
-            {
-                // strips: whole columns for batches (long streams per warp), single cell rows for a few frames (many short items)
-                std::vector<FastStrip> strips;
-                std::vector<uint8_t> saux;
-                if (make_fast_strips(g, n >= 16, strips, saux, flags)) return fail(ORBX_ERR_TOO_LARGE, "FAST strip table: a cell does not fit the 128-byte window");
-                b->nStrips = (int)strips.size();
-                if ((r = dev_alloc(b, &b->stripTab, strips.size()))) return r;
-                if ((r = dev_alloc(b, &b->stripAux, saux.size() + 16))) return r;
-                CU(cudaMemcpy(b->stripTab, strips.data(), strips.size() * sizeof(FastStrip), cudaMemcpyHostToDevice));
-                CU(cudaMemcpy(b->stripAux, saux.data(), saux.size(), cudaMemcpyHostToDevice));
-                if (fast_strip_encode_maps(g, B.pyr, n, &b->stripMaps)) return fail(ORBX_ERR_CUDA, "cuTensorMapEncodeTiled failed (FAST strips)");
-                CU(fast_strip_configure());
-            }
-            // flags of the cells without FAST work never change: written once for every image (the kernel overwrites the others)
-            std::vector<uint8_t> all((size_t)n * g.cellsPerImage);
-            for (int i = 0; i < n; ++i) std::memcpy(all.data() + (size_t)i * g.cellsPerImage, flags.data(), flags.size());
-            CU(cudaMemcpy(B.cellFlags, all.data(), all.size(), cudaMemcpyHostToDevice));
-        }
         if (fast_encode_maps(g, B.pyr, n, b->fastTs, &b->fastMaps)) return fail(ORBX_ERR_CUDA, "cuTensorMapEncodeTiled failed (FAST tiles)");
         if (blur_encode_maps(g, B.pyr, n, &b->blurMaps)) return fail(ORBX_ERR_CUDA, "cuTensorMapEncodeTiled failed (blur tiles)");
         if (resize_encode_maps(g, B.pyr, n, &b->resizeMaps)) return fail(ORBX_ERR_CUDA, "cuTensorMapEncodeTiled failed (resize tiles)");
@@ -719,15 +681,7 @@ static int run_range_lane(orbx_batch* b, int first, int n, const int* lapping, i
     const bool blurFirst = b->sched == 0 || b->sched == 3 || b->sched == 4;
     if (overlap && blurFirst) { int r = blur_on_side(); if (r) return r; }
     if (overlap && b->sched == 1) CU(cudaEventRecord(evPyr, s));
-    if (b->fastImpl == 0) {
-        launch_fast_strip(g, buf, b->stripMaps, b->stripTab, b->stripAux, b->nStrips, n, b->numSMs, b->bandCtr + lane, s);
-        launch_fast_redo(g, buf, b->fastMaps, n, b->fastTileRows, b->fastTs, b->numSMs, s);
-        launches += g.iniTh != g.minTh ? 2 : 1;
-    } else {
-        if (b->fastImpl == 1) launch_fast_band(g, buf, b->bandTab, b->bandAux, b->nBands, b->bandRows, b->bandTp, n, b->numSMs, b->bandCtr + lane, s);
-        else launch_fast(g, buf, b->fastMaps, n, b->fastTileRows, b->fastTs, b->numSMs, s);
-        ++launches;
-    }
+    launch_fast(g, buf, b->fastMaps, n, b->fastTileRows, b->fastTs, b->numSMs, s); ++launches;
     if (overlap && b->sched == 1) {  // the blur is enqueued after FAST but still only waits for the pyramid
         CU(cudaStreamWaitEvent(side, evPyr, 0));
         for (int l = 0; l < g.nlevels; ++l) { launch_blur(g, buf, b->blurMaps, l, n, b->taps, side); ++launches; }

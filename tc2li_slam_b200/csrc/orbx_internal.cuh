@@ -109,56 +109,6 @@ void make_cell_table(const Geom& g, uint4* tab, int* tileRows, int* maxCw);
 int fast_tile_stride(int maxCw);
 cudaError_t fast_configure(int tileRows, int ts);
 int fast_encode_maps(const Geom& g, uint8_t* pyr, int nImages, int ts, FastMaps* out);
-// the dense band pass (fast_band_kernel.cu): one band = the crops of cells [c0, c0 + nCells) of one cell row of one level
-struct __align__(16) FastBand {
-    uint16_t iniX, iniY;     // crop origin of the first cell (level coordinates)
-    uint16_t cw, ch;         // columns and rows of the union of the crops (3-px rims included)
-    uint16_t cell0;          // first cell: index inside the per-image cell array
-    uint16_t nDr;            // groups of four words (16 pixels) per interior row
-    uint8_t level, nCells, shift, wFirstP;   // shift: byte of crop column 0 inside its 16-byte aligned tile row; wFirstP: word index of the first pair (even)
-    uint32_t magicD;         // exact i / nDr for i < 2^16
-    uint32_t aux;            // byte offset of this band's tables in the aux buffer: uint32 masks[4 * nDr + 4], uint8 colInfo[cw]
-    uint16_t wCell, nwc;     // cell pitch; word slots per cell row in the redo pass
-    uint32_t magicWc;        // / nwc
-    uint32_t magicCell;      // / (nwc * (ch - 6))
-    uint32_t rowBytes;       // bytes copied per tile row (multiple of 16)
-    uint32_t pad0, pad1;
-};
-static_assert(sizeof(FastBand) == 48, "FastBand layout");
-}  // namespace orbx
-#include <vector>
-namespace orbx {
-int make_fast_bands(const Geom& g, int tp, std::vector<FastBand>& bands, std::vector<uint8_t>& aux, std::vector<uint8_t>& flagTemplate, int* tileRows);
-int fast_band_pick_tp(const Geom& g);
-size_t fast_band_smem(int tileRows, int tp);
-cudaError_t fast_band_configure();
-void launch_fast_band(const Geom& g, const Buffers& b, const FastBand* bands, const uint8_t* aux, int nBands, int tileRows, int tp, int nImages, int numSMs,
-                      int* workCtr, cudaStream_t s);
-// the streaming strip pass (fast_strip_kernel.cu): one item = a column strip of cells [c0, c0 + nCells) over cell rows [cellRow0, cellRow0 + nCellRows)
-struct __align__(16) FastStrip {
-    uint16_t iniX;           // crop origin of the first cell (level coordinates)
-    uint16_t cw;             // columns of the union of the crops (3-px rims included)
-    uint16_t rowBase;        // row of the level's FAST region (level row - 16) that is local row 0 = first output row - 3
-    uint16_t rowEnd;         // output rows are the local rows [3, rowEnd)
-    uint16_t cell0;          // cell (cellRow0, c0): index inside the per-image cell array
-    uint16_t nCols;          // cells per cell row of the level
-    uint8_t level, nCells, shift, win8;   // shift: byte of crop column 0 inside its 16-byte aligned ring row; the 128-byte window starts at byte 8 * win8
-    uint8_t nCellRows, cellRow0, pad[2];
-    uint32_t aux;            // byte offset of this strip's column table (uint8 colInfo[cw]) in the aux buffer
-    uint32_t hCell;          // cell pitch in rows
-    uint32_t magicH;         // exact i / hCell for i < 2^16
-};
-static_assert(sizeof(FastStrip) == 32, "FastStrip layout");
-struct StripMaps {  // per level: {160 x 8} boxes (ring slots) and {160 x 4} boxes (mirror rows) of the pyramid
-    CUtensorMap b8[ORBX_MAX_LEVELS];
-    CUtensorMap b4[ORBX_MAX_LEVELS];
-};
-int make_fast_strips(const Geom& g, bool wholeStrips, std::vector<FastStrip>& strips, std::vector<uint8_t>& aux, std::vector<uint8_t>& flagTemplate);
-int fast_strip_encode_maps(const Geom& g, uint8_t* pyr, int nImages, StripMaps* out);
-cudaError_t fast_strip_configure();
-void launch_fast_strip(const Geom& g, const Buffers& b, const StripMaps& maps, const FastStrip* strips, const uint8_t* aux, int nStrips, int nImages, int numSMs,
-                       int* workCtr, cudaStream_t s);
-void launch_fast_redo(const Geom& g, const Buffers& b, const FastMaps& maps, int nImages, int tileRows, int ts, int numSMs, cudaStream_t s);
 struct LevelMaps {  // one tensor map per pyramid level
     CUtensorMap m[ORBX_MAX_LEVELS];
 };
