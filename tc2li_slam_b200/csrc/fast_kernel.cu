@@ -208,14 +208,17 @@ __global__ void __launch_bounds__(32 * FW) k_fast_cells(const __grid_constant__ 
         tma_load_3d(my + buf * tileBytes, &maps.m[level], &bars[wid][buf], (kMarginX + iniX) & ~15, kMarginY + iniY, b.imgBase + img);
     };
     // one cell: wait for its crop, FAST + NMS at iniThFAST (attempt 0) and / or minThFAST (attempt 1), candidates and the cell's flag
-    auto run_cell = [&](int imgRel, int cellIdx, int buf) {
+    auto run_cell = [&](int imgRel, int cellIdx, int buf, int nextImg, int nextCell) {   // nextImg < 0: no next item
         const int img = b.imgBase + imgRel;
         const uint4 cd = __ldg(b.cellTab + cellIdx);
         const int iniX = cd.x & 0xFFFF, iniY = cd.x >> 16;
         const int cw = cd.y & 0xFF, ch = (cd.y >> 8) & 0xFF, level = (cd.y >> 16) & 0xFF, kind = cd.y >> 24;
         uint8_t* flag = b.cellFlags + (size_t)img * g.cellsPerImage + cellIdx;
         if (kind != 2) {  // 0: a cell the reference skips (ORBextractor.cc:785-796); 1: crop thinner than the ring, cv::FAST yields nothing
-            if (lane == 0) *flag = kind == 0 ? 0 : 2;
+            if (lane == 0) {
+                *flag = kind == 0 ? 0 : 2;
+                if (NB == 1 && nextImg >= 0) issue(nextImg, nextCell, 0);
+            }
             return;
         }
         const LevelGeom& L = g.lv[level];
@@ -231,6 +234,7 @@ __global__ void __launch_bounds__(32 * FW) k_fast_cells(const __grid_constant__ 
         int* candCount = b.candCount + img * ORBX_MAX_LEVELS + level;
         const int relX = iniX - kBorder, relY = iniY - kBorder;
         int nsTotal = 0;
+        bool issuedNext = false;
         int attempt = 0;
         for (;; ++attempt) {
             const int t = attempt == 0 ? g.iniTh : g.minTh;
@@ -339,10 +343,32 @@ __global__ void __launch_bounds__(32 * FW) k_fast_cells(const __grid_constant__ 
                     ns += __popc(bal);
                 }
                 __syncwarp();
-                emit<TS>(c, surv, ns, shift, relX, relY, cand, L.candCap, candCount, b.errFlag);
+                // the tile is free once no second attempt can follow: the next cell's crop starts to load under the rest of this cell
+                const bool last = ns > 0 || attempt == 1 || g.iniTh == g.minTh;
+                if (NB == 1 && last && lane == 0 && nextImg >= 0) { issue(nextImg, nextCell, 0); issuedNext = true; }
+                if (ns > 0 && ns <= 32) {
+                    // one group of survivors (the usual case): the counter's round trip hides behind the wipe of the score map
+                    uint32_t packed = 0u;
+                    if (lane < ns) {
+                        const int off = surv[lane];
+                        const int r = off / TS, cx = off - r * TS - shift;
+                        packed = pack_cand(cx + relX, r + relY, (int)c.sc[off] - 1);
+                    }
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(candCount, ns);
+                    __syncwarp();
+                    for (int k = lane; k < c.n2; k += 32) c.sc[c.list2[k]] = 0;  // leave the score map clean
+                    base = __shfl_sync(FULL, base, 0);
+                    if (base + ns > L.candCap) {
+                        if (lane == 0) atomicExch(b.errFlag, 1);
+                    } else if (lane < ns)
+                        cand[base + lane] = packed;
+                } else {
+                    emit<TS>(c, surv, ns, shift, relX, relY, cand, L.candCap, candCount, b.errFlag);
+                    __syncwarp();
+                    for (int k = lane; k < c.n2; k += 32) c.sc[c.list2[k]] = 0;  // leave the score map clean
+                }
                 nsTotal += ns;
-                __syncwarp();
-                for (int k = lane; k < c.n2; k += 32) c.sc[c.list2[k]] = 0;  // leave the score map clean
             } else {
                 // the corner list was flushed early (very dense corners): find the scores by scanning the map
                 for (int p0 = 0; p0 < iw * ih; p0 += 32) {
@@ -378,8 +404,11 @@ __global__ void __launch_bounds__(32 * FW) k_fast_cells(const __grid_constant__ 
             __syncwarp();
             if (nsTotal > 0 || attempt == 1 || g.iniTh == g.minTh) break;
         }
-        if (lane == 0) *flag = (attempt == 0) ? 1 : 2;
-        __syncwarp();  // every lane is done with this tile buffer before lane 0 re-arms it
+        if (lane == 0) {
+            *flag = (attempt == 0) ? 1 : 2;
+            if (NB == 1 && !issuedNext && nextImg >= 0) issue(nextImg, nextCell, 0);   // (the dense-corner path: every lane is past the tile here)
+        }
+        __syncwarp();
     };
     int w = blockIdx.x * FW + wid;
     // (image, cell) of the work item, walked incrementally: `stride` items further is dImg images and dCell cells on
@@ -394,9 +423,15 @@ __global__ void __launch_bounds__(32 * FW) k_fast_cells(const __grid_constant__ 
                 const int c2 = cellIdx + dCell, wrap = c2 >= nCells;
                 issue(imgRel + dImg + wrap, c2 - (wrap ? nCells : 0), buf ^ 1);
             }
-        } else if (lane == 0 && it > 0)
-            issue(imgRel, cellIdx, 0);
-        run_cell(imgRel, cellIdx, buf);
+        }
+        if (cellIdx >= nCells) { cellIdx -= nCells; ++imgRel; }
+        int ni = -1, nc = 0;
+        if (w + stride < nWork) {
+            nc = cellIdx + dCell;
+            ni = imgRel + dImg + (nc >= nCells ? 1 : 0);
+            if (nc >= nCells) nc -= nCells;
+        }
+        run_cell(imgRel, cellIdx, buf, ni, nc);
     }
 }
 
