@@ -74,16 +74,19 @@ def cpu_images(n_pairs, seed0):
     return out
 
 
-def cpu_run(images, cores, make_extractor):
-    """Extract every image, sharded over `cores` host threads (the C library releases the GIL).  Returns seconds."""
+def cpu_run(images, cores, make_extractor, keep=None):
+    """Extract every image, sharded over `cores` host threads (the C library releases the GIL).  Returns (seconds, keypoints);
+    keep: a list of len(images) that receives (mono, keypoints, descriptors) per image (the parity check of the bench line)."""
     n = len(images)
     exs = [make_extractor(*ORB_ARGS) for _ in range(cores)]
     nk = [0] * cores
 
     def work(t):
         for i in range(t, n, cores):
-            _, k, _ = exs[t](images[i])
+            m, k, d = exs[t](images[i])
             nk[t] += len(k)
+            if keep is not None:
+                keep[i] = (m, k.copy(), d.copy())
 
     t0 = time.perf_counter()
     th = [threading.Thread(target=work, args=(t,)) for t in range(cores)]
@@ -114,7 +117,7 @@ def reference_arm(args):
     emit_line(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "pairs_per_step": pairs, "sample": "bounded sample of the workload on the host cores (CPU reference path)"},
+        "config": {"workload": WORKLOAD},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -208,6 +211,32 @@ def bind_to_gpu_numa_node(device):
         return None
 
 
+def feed_ceiling(n_gpus, h2d_bytes, d2h_bytes, frames):
+    """The host <-> device copy ceiling for this step's traffic: profiles/tools/feed_probe run live (duplex, pinned buffers of the
+    benchmark's chunk sizes, one host thread per GPU), else the committed measurement profiles/r02/feed_ceiling.json."""
+    run, src = None, None
+    exe = os.path.join(ROOT, "profiles", "tools", "feed_probe")
+    try:
+        if os.access(exe, os.X_OK):
+            out = subprocess.run([exe, "0.3", str(n_gpus)], capture_output=True, text=True, timeout=120).stdout
+            run, src = json.loads(out)["runs"][0], "live: profiles/tools/feed_probe"
+    except Exception:
+        run = None
+    if run is None:
+        try:
+            for r_ in json.load(open(os.path.join(ROOT, "profiles", "r02", "feed_ceiling.json")))["runs"]:
+                if r_["n"] == n_gpus and r_["gpus"] == list(range(n_gpus)):
+                    run, src = r_, "profiles/r02/feed_ceiling.json"
+        except Exception:
+            pass
+    if run is None:
+        return None
+    # (in the duplex run the two directions are rate-matched by the probe's loop: its D2H figure is not a ceiling, the D2H-only one is)
+    t = max(h2d_bytes / (run["duplex_h2d_GBps"] * 1e9), d2h_bytes / (run["d2h_only_GBps"] * 1e9))
+    return {"source": src, "duplex_h2d_GBps": run["duplex_h2d_GBps"], "d2h_only_GBps": run["d2h_only_GBps"], "h2d_only_GBps": run["h2d_only_GBps"],
+            "ceiling_frames_per_s": frames / t, "what": "frames/s if the step's copies ran at the measured duplex rates and nothing else took time"}
+
+
 def main():
     claim_stdout()
     ap = argparse.ArgumentParser()
@@ -235,25 +264,32 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    import torch
-    torch.cuda.set_device(local)
     numa = bind_to_gpu_numa_node(local) if world > 1 else None
     dist = None
     if world > 1:
+        # the data path has no collective (frames are independent): the ranks only meet at start barriers and for the max / sum of
+        # a few floats, on the host (gloo); NCCL is not initialised
+        import torch
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("gloo")
 
     def barrier():
         if dist is not None:
             dist.barrier()
-        torch.cuda.synchronize()
 
-    def max_over_ranks(v):
+    def _reduce(v, op):
         if dist is None:
             return v
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        import torch
+        t = torch.tensor([v], dtype=torch.float64)
+        dist.all_reduce(t, op=op)
         return float(t.item())
+
+    def max_over_ranks(v):
+        return _reduce(v, dist.ReduceOp.MAX) if dist is not None else v
+
+    def sum_over_ranks(v):
+        return _reduce(v, dist.ReduceOp.SUM) if dist is not None else v
 
     import tc2li_slam_b200 as T
     from tc2li_slam_b200.orbx import Event
@@ -276,14 +312,15 @@ def main():
     big.check()
     counts, _ = big.download_counts(n_img)
     kp_mean = float(counts.mean())
-    ev0, ev1 = Event(), Event()
+    ev0, ev1 = Event(big), Event(big)
+    big.sync()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     ev0.record(big)
     for _ in range(args.steps):
         resident_step()
     ev1.record(big)
-    ms_total = ev0.elapsed_ms(ev1)
+    ms_total = ev0.elapsed_ms(ev1)   # (waits for the stop event: the device is idle again)
     barrier()
     clocks = sampler.stop() if sampler else None
     ms_step = max_over_ranks(ms_total / args.steps)
@@ -335,7 +372,7 @@ def main():
         mb, mbf = 0.5372, 387.5744  # KITTI 00-02: baseline 0.537 m, bf 387.57 (config/Camera-Lidar/KITTI00-02.yaml)
         big.stereo_match(args.pairs, mb, mbf)
         big.sync()
-        s0, s1 = Event(), Event()
+        s0, s1 = Event(big), Event(big)
         s0.record(big)
         for _ in range(args.steps):
             big.stereo_match(args.pairs, mb, mbf)
@@ -350,7 +387,7 @@ def main():
     if not args.no_stereo:
         big.assign_grid(n_img)
         big.sync()
-        s0, s1 = Event(), Event()
+        s0, s1 = Event(big), Event(big)
         s0.record(big)
         for _ in range(args.steps):
             big.assign_grid(n_img)
@@ -389,9 +426,14 @@ def main():
                 "assign_ms_per_step": ms_grid, "assign_images_per_s": n_img / (ms_grid * 1e-3), "area_queries": nq,
                 "area_queries_per_s_host_to_host": nq / dt_q, "mean_hits_per_query": float(qc.mean())}
 
-    # ---- e2e: pinned host images in, keypoints/descriptors out, three pipelined handles ----
+    # ---- e2e: the product call.  Pinned host images -> orbx_pool_extract -> host keypoints / descriptors / counts, frame order.
+    #      N = 1: a pool of this GPU.  N > 1: every rank first drives its own GPU at the same time (supplementary), then rank 0
+    #      alone drives ALL N GPUs through ONE pool from one process — the multi-GPU product API — while the other ranks wait ----
     e2e = None
+    e2e_ranks = None
     pinned_in = None
+    out_kps = out_desc = out_cnt = out_mono = None
+    feed = None
     if not args.no_e2e:
         chunk = min(args.chunk, n_img)
         K = big.K
@@ -403,41 +445,56 @@ def main():
         out_desc = T.PinnedArray((n_img, K, 32), np.uint8)
         out_cnt = T.PinnedArray((n_img,), np.int32)
         out_mono = T.PinnedArray((n_img,), np.int32)
-        handles = [T.BatchExtractor(W, H, chunk, *ORB_ARGS, device=local) for _ in range(3)]
-        ends = [Event() for _ in handles]
-        start = Event()
-
-        def e2e_step():
-            for ci, first in enumerate(range(0, n_img, chunk)):
-                n = min(chunk, n_img - first)
-                h = handles[ci % len(handles)]
-                h.upload(pinned_in.array[first:first + n])
-                h.run(n)
-                h.download_async(0, n, out_kps.array[first:first + n], out_desc.array[first:first + n], out_cnt.array[first:first + n], out_mono.array[first:first + n])
-
-        for _ in range(args.warmup):
-            e2e_step()
-        for h in handles:
-            h.check()
-        assert np.array_equal(out_cnt.array, counts), "e2e keypoint counts differ from the resident run"
-        barrier()
-        start.record(handles[0])
-        for _ in range(args.steps):
-            e2e_step()
-        for h, e in zip(handles, ends):
-            e.record(h)
-        ms_e2e = max(start.elapsed_ms(e) for e in ends) / args.steps
-        for h in handles:
-            h.check()
-        barrier()
-        ms_e2e = max_over_ranks(ms_e2e)
         h2d = n_img * H * W
         d2h = n_img * (K * 28 + K * 32 + 8)
-        e2e = {"value": args.pairs * world / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "ms_per_step": ms_e2e, "pipeline": f"3 handles x {chunk} images, pinned host buffers",
-               "gpu_launches": handles[0].kernel_launches * ((n_img + chunk - 1) // chunk)}
-        for h in handles:
-            h.close()
+
+        def pool_run(pool, src, dst):
+            for _ in range(args.warmup):
+                pool.extract(src, None, *dst)
+            ms = 0.0
+            for _ in range(args.steps):
+                pool.extract(src, None, *dst)
+                ms += float(pool.last_ms().max())   # device time of the call: first upload enqueued -> last download done, slowest GPU
+            return ms / args.steps
+
+        pool = T.ExtractorPool(W, H, [local], *ORB_ARGS, chunk_images=chunk, handles_per_device=3)
+        barrier()
+        ms_mine = pool_run(pool, pinned_in.array, (out_kps.array, out_desc.array, out_cnt.array, out_mono.array))
+        assert np.array_equal(out_cnt.array, counts), "e2e keypoint counts differ from the resident run"
+        launches_e2e = pool.kernel_launches
+        pool.close()
+        barrier()
+        ms_ranks = max_over_ranks(ms_mine)
+        e2e = {"value": args.pairs * world / (ms_ranks * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+               "ms_per_step": ms_ranks, "api": "orbx_pool_extract (include/orbx.h)",
+               "pipeline": f"per GPU: one host thread, 3 handles x {chunk} images, pinned host buffers", "gpu_launches": launches_e2e * world}
+        if world > 1:
+            e2e_ranks = dict(e2e, what=f"{world} processes, each driving its own GPU through a pool of one at the same time")
+            e2e = None
+            if rank == 0:
+                # one process, one pool over all N GPUs; the frames of GPU d's share are rank 0's frames again (throughput does not depend on the texture)
+                all_in = T.PinnedArray((world * n_img, H, W), np.uint8)
+                for r_ in range(world):
+                    all_in.array[r_ * n_img:(r_ + 1) * n_img] = pinned_in.array
+                all_out = (T.PinnedArray((world * n_img, K), T.KP_DTYPE), T.PinnedArray((world * n_img, K, 32), np.uint8),
+                           T.PinnedArray((world * n_img,), np.int32), T.PinnedArray((world * n_img,), np.int32))
+                feed = feed_ceiling(world, h2d * world, d2h * world, args.pairs * world)
+                pool = T.ExtractorPool(W, H, list(range(world)), *ORB_ARGS, chunk_images=chunk, handles_per_device=3)
+                ms_pool = pool_run(pool, all_in.array, tuple(a.array for a in all_out))
+                assert np.array_equal(all_out[2].array, np.tile(counts, world)), "pool keypoint counts differ from the resident run"
+                e2e = {"value": args.pairs * world / (ms_pool * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+                       "ms_per_step": ms_pool, "api": "orbx_pool_extract (include/orbx.h), ONE process driving all GPUs",
+                       "pipeline": f"per GPU: one host thread, 3 handles x {chunk} images, pinned host buffers; chunk c -> GPU c mod {world}",
+                       "gpu_launches": pool.kernel_launches, "per_gpu_ms": [float(x) for x in pool.last_ms()]}
+                pool.close()
+                for a in (all_in,) + all_out:
+                    a.free()
+            barrier()
+        elif rank == 0:
+            feed = feed_ceiling(1, h2d, d2h, args.pairs)
+        if e2e is not None and feed is not None and feed.get("ceiling_frames_per_s"):
+            e2e["frac_of_feed_ceiling"] = e2e["value"] / feed["ceiling_frames_per_s"]
+            e2e["feed_ceiling"] = feed
 
     # ---- supplementary: BASELINE.json configs[3], large single frames (1920x1080 and 3840x2160, 4000 features) ----
     large = None
@@ -450,7 +507,7 @@ def main():
                 lb.run(nimg)
             lb.check()
             cl, _ = lb.download_counts(nimg)
-            l0, l1 = Event(), Event()
+            l0, l1 = Event(lb), Event(lb)
             l0.record(lb)
             for _ in range(args.steps):
                 lb.run(nimg)
@@ -476,7 +533,7 @@ def main():
             eb.run(2 * ef, lap)
             eb.lapping_match(ef)
         eb.check()
-        e0, e1, e2_ = Event(), Event(), Event()
+        e0, e1, e2_ = Event(eb), Event(eb), Event(eb)
         e0.record(eb)
         for _ in range(args.steps):
             eb.run(2 * ef, lap)
@@ -514,6 +571,7 @@ def main():
 
     # ---- CPU baseline on this box's host cores (rank 0, N == 1 only) ----
     cpu = None
+    parity = None
     if rank == 0 and world == 1 and not args.no_cpu:
         kind, make = cpu_backend()
         cores = os.cpu_count() or 1
@@ -525,10 +583,34 @@ def main():
         dt1, _ = cpu_run(src[:2], 1, make)
         per_img = dt1 / 2
         n_s = int(min(len(src), max(2 * cores, (15.0 * cores / per_img) // 2 * 2)))
-        dt, nk = cpu_run(src[:n_s], cores, make)
+        kept = [None] * n_s
+        dt, nk = cpu_run(src[:n_s], cores, make, kept)
         cpu = {"value": (n_s / 2) / dt, "unit": UNIT, "cores": cores, "kind": kind,
-               "sample": f"first {n_s // 2} stereo frames of this workload, sharded over {cores} host threads, {dt:.1f} s wall",
+               "sample": f"first {n_s // 2} stereo frames of this workload, sharded over {cores} host threads, {dt:.1f} s wall; pixel primitives are the "
+                         f"oracle's scalar restatements of OpenCV's (a SIMD OpenCV build would be faster per core)",
                "single_thread_ms_per_image": per_img * 1e3}
+        if out_kps is not None:
+            # parity at benchmark scale: the CPU leg's keypoints / descriptors against what the timed e2e call left in the pinned outputs
+            bad = 0
+            for i_, (m_, k_, d_) in enumerate(kept):
+                c_ = int(out_cnt.array[i_])
+                if c_ != len(k_) or int(out_mono.array[i_]) != m_ or out_kps.array[i_, :c_].tobytes() != k_.tobytes() or not np.array_equal(out_desc.array[i_, :c_], d_):
+                    bad += 1
+            parity = {"frames_checked": n_s, "mismatches": bad, "against": f"CPU {kind} of ORBextractor.cc, every field of every keypoint and every descriptor byte"}
+
+    if world > 1 and out_kps is not None:
+        # every rank checks four of its own frames against the CPU path (outside every timed region)
+        kind, make = cpu_backend()
+        ex_ = make(*ORB_ARGS)
+        bad = 0
+        picks = [0, 1, n_img // 2, n_img - 1]
+        for i_ in picks:
+            m_, k_, d_ = ex_(pinned_in.array[i_])
+            c_ = int(out_cnt.array[i_])
+            if c_ != len(k_) or int(out_mono.array[i_]) != m_ or out_kps.array[i_, :c_].tobytes() != k_.tobytes() or not np.array_equal(out_desc.array[i_, :c_], d_):
+                bad += 1
+        parity = {"frames_checked": int(sum_over_ranks(len(picks))), "mismatches": int(sum_over_ranks(bad)),
+                  "against": f"CPU {kind} of ORBextractor.cc on four frames of every rank"}
 
     if rank == 0:
         line = {
@@ -537,11 +619,12 @@ def main():
             "config": {"workload": WORKLOAD,
                        "pairs_per_gpu_per_step": args.pairs, "images_per_launch_set": group, "keypoints_per_image": kp_mean,
                        "l2": f"inputs {n_img * W * H / 1e9:.2f} GB per rank, larger than the {L2_BYTES / 1e6:.0f} MB L2; no flush needed"},
-            "clocks": clocks, "numa_binding": numa, "e2e": e2e, "gpu_launches": launches_per_step, "roofline": roofline, "cpu_baseline": cpu, "stages": stages, "latency": latency, "stereo_match": stereo, "feature_grid": grid, "large_images": large, "euroc_lapping": euroc,
+            "clocks": clocks, "numa_binding": numa, "e2e": e2e, "e2e_one_process_per_gpu": e2e_ranks, "parity": parity, "gpu_launches": launches_per_step, "roofline": roofline, "cpu_baseline": cpu, "stages": stages, "latency": latency, "stereo_match": stereo, "feature_grid": grid, "large_images": large, "euroc_lapping": euroc,
         }
         emit_line(json.dumps(line))
     big.close()
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
 
 

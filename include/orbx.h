@@ -269,7 +269,7 @@ int orbx_batch_download_async(orbx_batch* b, int first, int n, orbx_keypoint* ke
 int orbx_batch_check(orbx_batch* b);
 
 /* CUDA events on the handles' streams (device-side timing, ordering between handles of a pipelined caller) */
-void* orbx_event_create(void);
+void* orbx_event_create(const orbx_batch* b);   /* on the batch's device */
 void orbx_event_destroy(void* ev);
 int orbx_event_record(void* ev, orbx_batch* b);
 int orbx_event_wait(orbx_batch* b, void* ev);
@@ -294,7 +294,33 @@ int orbx_batch_debug_selected(orbx_batch* b, int image, int level, float* xyr, i
 int orbx_batch_debug_fallback_cells(orbx_batch* b, int image, int level, int* n_fallback);
 orbx_batch* orbx_extractor_batch(orbx_extractor* h); /* the batch-of-one behind a single-image handle (NULL before the first call) */
 
-/* page-locked host memory, so that the uploads / downloads above overlap with kernels of other handles */
+/* ------------------------------------------------------------------------------------------------------------------
+ * Multi-GPU pool: the product form of "frames are independent, shard them by frame over the GPUs of one box, no collective"
+ * (SURVEY.md 8e).  It scales out what every Frame constructor does for one stereo pair — two extraction threads, one per
+ * image (Frame.cc:139-142, Frame::ExtractORB Frame.cc:445-455): here one host thread per GPU, each driving `handles_per_device`
+ * batch handles (own streams) over chunks of `chunk_images` images, so that the upload of one chunk, the kernels of the next
+ * and the download of a third overlap.  Chunk c of a call goes to device c mod n_devices; the results land in the caller's
+ * arrays at the images' own indices (frame order).  No torch, no NCCL, no device-to-device traffic.
+ *   images      : n_images x height rows of row_stride bytes, image_stride bytes apart (pinned memory from orbx_alloc_pinned
+ *                 keeps the copies asynchronous; pageable memory works, slower)
+ *   lapping     : n_images x 2 ints (vLappingArea of every image, ORBextractor.cc:1126-1135) or NULL
+ *   keypoints   : n_images x K (K = orbx_pool_max_keypoints), descriptors n_images x K x 32, counts / mono_index n_images;
+ *                 any of the four may be NULL
+ * orbx_pool_extract returns when everything is on the host (ORBX_ERR_CAPACITY etc. as for the batch handle). */
+typedef struct orbx_pool orbx_pool;
+int orbx_pool_create(int nfeatures, float scale_factor, int nlevels, int ini_th_fast, int min_th_fast, const int* devices, int n_devices, int width,
+                     int height, int chunk_images, int handles_per_device, orbx_pool** out);
+void orbx_pool_destroy(orbx_pool* p);
+int orbx_pool_max_keypoints(const orbx_pool* p);
+int orbx_pool_devices(const orbx_pool* p);
+int orbx_pool_extract(orbx_pool* p, const uint8_t* images, size_t row_stride, size_t image_stride, int n_images, const int* lapping,
+                      orbx_keypoint* keypoints, uint8_t* descriptors, int* counts, int* mono_index);
+/* device time of the last orbx_pool_extract: per device, first upload enqueued -> last download finished (CUDA events on the
+ * handles' streams), ms[n_devices]; the call's throughput is n_images / max(ms) */
+int orbx_pool_last_ms(const orbx_pool* p, float* ms);
+int orbx_pool_kernel_launches(const orbx_pool* p);   /* kernels launched by the last orbx_pool_extract, all devices */
+
+/* page-locked host memory (portable: pinned for every device), so that the uploads / downloads above overlap with kernels of other handles */
 void* orbx_alloc_pinned(size_t bytes);
 void orbx_free_pinned(void* p);
 

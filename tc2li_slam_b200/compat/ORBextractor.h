@@ -17,6 +17,9 @@
 #ifndef ORBEXTRACTOR_H
 #define ORBEXTRACTOR_H
 
+#include <cstring>
+#include <stdexcept>
+#include <string>
 #include <cassert>
 #include <cstdlib>
 #include <list>
@@ -68,7 +71,9 @@ public:
         if (rc != ORBX_OK) {
             _keypoints.clear();
             _descriptors.release();
-            return -1;
+            // an empty / too small image is the reference's "-1"; a device fault or an exceeded capacity must not look like "no features"
+            if (rc == ORBX_ERR_EMPTY || rc == ORBX_ERR_TOO_SMALL) return -1;
+            throw std::runtime_error(std::string("orbx: ") + orbx_last_error());
         }
         _keypoints = std::vector<cv::KeyPoint>((size_t)n);
         if (n == 0)

@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(32 * DW) k_describe(const __grid_constant__ Ge
 }
 
 cudaError_t describe_configure() {
-    return cudaFuncSetAttribute(k_describe, cudaFuncAttributeMaxDynamicSharedMemorySize, DW * 2 * ST_BYTES);
+    return raise_dynamic_smem(k_describe, (size_t)DW * 2 * ST_BYTES);
 }
 
 void launch_describe(const Geom& g, const Buffers& b, const DescMaps& maps, int nImages, cudaStream_t s) {

@@ -78,9 +78,6 @@ struct CellCtx {
     int lane;
 };
 
-// half swap of a 16x2 word
-__device__ __forceinline__ uint32_t sw16(uint32_t x) { return __byte_perm(x, 0, 0x1032); }
-
 // list1 -> list2 with the exact score of every listed pixel (16x2 lanes, DPX three-input min / max):
 //   S = max( max_s min_{j<9} r[s+j] - v,  v - min_s max_{j<9} r[s+j] )        (at most one of the two terms is positive)
 // R[q] holds ring pixels q (low half) and q + 8 (high half), R[q + 8] is its half swap, so the nine-window starting at q
@@ -472,13 +469,8 @@ static size_t fast_warp_bytes(int tileRows, int ts) { return (size_t)(NB + 1) * 
 
 cudaError_t fast_configure(int tileRows, int ts) {
     const int smem = (int)(FW * fast_warp_bytes(tileRows, ts));
-    // (per-kernel, per-device attribute shared by every handle: only ever raised)
-    static int configured = 0;
-    const int want = std::max(smem, 48 * 1024);
-    if (want <= configured) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(k_fast_cells<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fast_cells<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
-    if (e == cudaSuccess) configured = want;
+    cudaError_t e = raise_dynamic_smem(k_fast_cells<64>, (size_t)smem);
+    if (e == cudaSuccess) e = raise_dynamic_smem(k_fast_cells<96>, (size_t)smem);
     return e;
 }
 

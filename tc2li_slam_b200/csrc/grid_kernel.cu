@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(128) k_features_in_area(const Buffers b, int K
 size_t grid_smem_bytes(int K) { return (size_t)K * sizeof(int); }
 
 cudaError_t grid_configure(int K) {
-    return cudaFuncSetAttribute(k_assign_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(grid_smem_bytes(K), 1024));
+    return raise_dynamic_smem(k_assign_grid, grid_smem_bytes(K));
 }
 
 void launch_assign_grid(const Buffers& b, int K, const GridParams& p, int nImages, cudaStream_t s) {

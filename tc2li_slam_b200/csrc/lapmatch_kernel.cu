@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(LM_THREADS) k_lap_match(const __grid_constant_
 
 size_t lap_match_smem_bytes() { return (size_t)8 * LM_TILE * 4; }
 
-cudaError_t lap_match_configure() { return cudaFuncSetAttribute(k_lap_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lap_match_smem_bytes()); }
+cudaError_t lap_match_configure() { return raise_dynamic_smem(k_lap_match, lap_match_smem_bytes()); }
 
 void launch_lap_match(const Geom& g, const Buffers& bl, const Buffers& br, int nFrames, int lMul, int lAdd, int rMul, int rAdd, cudaStream_t s) {
     k_lap_match<<<nFrames, LM_THREADS, lap_match_smem_bytes(), s>>>(g, bl, br, lMul, lAdd, rMul, rAdd);

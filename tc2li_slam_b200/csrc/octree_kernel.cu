@@ -369,9 +369,9 @@ size_t octree_smem_bytes(int nodeCap) { return oct_smem_bytes(nodeCap, OT_STAGE_
 cudaError_t octree_configure(int maxNodeCap) {
     const size_t smem = oct_smem_bytes(maxNodeCap, OT_STAGE_MAX);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(k_octree<OT_T_BATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024));
+    cudaError_t e = raise_dynamic_smem(k_octree<OT_T_BATCH>, smem);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_octree<OT_T_FEW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024));
+    return raise_dynamic_smem(k_octree<OT_T_FEW>, smem);
 }
 
 // Many images: one launch per level, each with exactly the shared memory its node capacity needs — the small levels then fit

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "orbx_internal.cuh"
@@ -124,6 +125,7 @@ struct orbx_batch {
     Buffers buf = {};
     int device = 0, width = 0, height = 0, maxImages = 0;
     int taps[7] = {18, 34, 48, 56, 48, 34, 18};
+    unsigned tapsGeneration = 0;        // bumped by every change of the taps (orbx_extractor re-captures its graph)
     cudaStream_t own = nullptr, stream = nullptr;
     cudaStream_t side = nullptr;        // blur runs here, concurrently with FAST + quadtree (both only need the pyramid)
     cudaEvent_t evPyr = nullptr, evBlur = nullptr;
@@ -421,8 +423,9 @@ int orbx_batch_max_images(const orbx_batch* b) { return b ? b->maxImages : ORBX_
 int orbx_batch_set_blur_taps(orbx_batch* b, const int taps[7]) {
     if (!b || !taps) return fail(ORBX_ERR_ARG, "null argument");
     int sum = 0;
-    for (int i = 0; i < 7; ++i) { if (taps[i] < 0 || taps[i] > 256) return fail(ORBX_ERR_ARG, "tap outside [0,256]"); sum += taps[i]; }
+    for (int i = 0; i < 7; ++i) { if (taps[i] < 0 || taps[i] > 255) return fail(ORBX_ERR_ARG, "tap outside [0,255] (the kernel packs taps into bytes)"); sum += taps[i]; }
     if (sum > 257) return fail(ORBX_ERR_ARG, "taps must sum to about 256 (8.8 fixed point)");
+    if (std::memcmp(b->taps, taps, sizeof(b->taps)) != 0) ++b->tapsGeneration;  // a captured graph has the old taps baked into its kernel arguments
     std::memcpy(b->taps, taps, sizeof(b->taps));
     return ORBX_OK;
 }
@@ -751,6 +754,7 @@ int orbx_batch_stereo_match(orbx_batch* b, int n_frames, float mb, float mbf) {
     if (r) return r;
     if (n_frames == 0) return ORBX_OK;
     if (!(mb > 0.f) || !(mbf > 0.f)) return fail(ORBX_ERR_ARG, "mb and mbf must be positive");
+    if (b->p.scaleFactorF > 1.9f) return fail(ORBX_ERR_ARG, "stereo matching needs scaleFactor <= 1.9 (beyond it the reference's SAD window, Frame.cc:950, leaves the image and cv::Mat::colRange asserts)");
     if (stereo_smem_bytes(b->g.K, b->g.lv[0].h) > 220 * 1024) return fail(ORBX_ERR_TOO_LARGE, "keypoint capacity too large for the stereo matcher's shared memory");
     DeviceGuard dg(b->device);
     Buffers buf = b->buf;
@@ -981,7 +985,9 @@ int orbx_batch_download(orbx_batch* b, int n, orbx_keypoint* keypoints, uint8_t*
 }
 
 // ---- CUDA events on the handles' streams: device-side timing and cross-handle ordering for pipelined callers ----
-void* orbx_event_create(void) {
+void* orbx_event_create(const orbx_batch* b) {
+    if (!b) { g_err = "null batch"; return nullptr; }
+    DeviceGuard dg(b->device);  // an event belongs to the device that is current when it is created
     cudaEvent_t e = nullptr;
     if (cudaEventCreate(&e) != cudaSuccess) { g_err = "cudaEventCreate failed"; return nullptr; }
     return (void*)e;
@@ -1120,7 +1126,7 @@ int orbx_batch_debug_fallback_cells(orbx_batch* b, int image, int level, int* n_
 // ---- pinned host memory for callers that want overlapped copies ----
 void* orbx_alloc_pinned(size_t bytes) {
     void* p = nullptr;
-    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { g_err = "cudaHostAlloc failed"; return nullptr; }
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) { g_err = "cudaHostAlloc failed"; return nullptr; }
     return p;
 }
 void orbx_free_pinned(void* p) { if (p) cudaFreeHost(p); }
@@ -1201,6 +1207,131 @@ int orbx_debug_atan2(const float* y, const float* x, float* out, int n) {
 }  // extern "C"
 
 // ------------------------------------------------------------------------------------------------------------------
+// Multi-GPU pool (include/orbx.h): one host thread per device, pipelined batch handles, frames sharded by chunk
+// ------------------------------------------------------------------------------------------------------------------
+struct orbx_pool {
+    std::vector<int> devices;
+    std::vector<std::vector<orbx_batch*>> handles;   // [device][handle]
+    std::vector<cudaEvent_t> evStart, evStop;        // per device, on its first handle's stream / after the join of all its handles
+    std::vector<float> lastMs;
+    int chunk = 0, K = 0, width = 0, height = 0, launches = 0;
+};
+
+extern "C" {
+
+int orbx_pool_create(int nfeatures, float scale_factor, int nlevels, int ini_th_fast, int min_th_fast, const int* devices, int n_devices, int width,
+                     int height, int chunk_images, int handles_per_device, orbx_pool** out) {
+    if (!out) return fail(ORBX_ERR_ARG, "null out pointer");
+    *out = nullptr;
+    if (!devices || n_devices < 1 || n_devices > 64) return fail(ORBX_ERR_ARG, "need 1..64 device ordinals");
+    if (chunk_images < 1 || handles_per_device < 1 || handles_per_device > 8) return fail(ORBX_ERR_ARG, "chunk_images >= 1 and 1 <= handles_per_device <= 8");
+    for (int i = 0; i < n_devices; ++i)
+        for (int j = 0; j < i; ++j)
+            if (devices[i] == devices[j]) return fail(ORBX_ERR_ARG, "a device appears twice");
+    orbx_pool* p = new orbx_pool();
+    p->devices.assign(devices, devices + n_devices);
+    p->handles.resize((size_t)n_devices);
+    p->evStart.assign((size_t)n_devices, nullptr);
+    p->evStop.assign((size_t)n_devices, nullptr);
+    p->lastMs.assign((size_t)n_devices, 0.f);
+    p->chunk = chunk_images; p->width = width; p->height = height;
+    for (int d = 0; d < n_devices; ++d) {
+        for (int k = 0; k < handles_per_device; ++k) {
+            orbx_batch* b = nullptr;
+            const int r = orbx_batch_create(nfeatures, scale_factor, nlevels, ini_th_fast, min_th_fast, devices[d], width, height, chunk_images, &b);
+            if (r != ORBX_OK) { const std::string msg = g_err; orbx_pool_destroy(p); return fail(r, msg); }
+            p->handles[(size_t)d].push_back(b);
+        }
+        DeviceGuard dg(devices[d]);
+        if (cudaEventCreate(&p->evStart[(size_t)d]) != cudaSuccess || cudaEventCreate(&p->evStop[(size_t)d]) != cudaSuccess) {
+            orbx_pool_destroy(p);
+            return fail(ORBX_ERR_CUDA, "cudaEventCreate failed");
+        }
+    }
+    p->K = p->handles[0][0]->g.K;
+    *out = p;
+    return ORBX_OK;
+}
+
+void orbx_pool_destroy(orbx_pool* p) {
+    if (!p) return;
+    for (size_t d = 0; d < p->handles.size(); ++d) {
+        for (orbx_batch* b : p->handles[d]) orbx_batch_destroy(b);
+        DeviceGuard dg(p->devices[d]);
+        if (p->evStart[d]) cudaEventDestroy(p->evStart[d]);
+        if (p->evStop[d]) cudaEventDestroy(p->evStop[d]);
+    }
+    delete p;
+}
+
+int orbx_pool_max_keypoints(const orbx_pool* p) { return p ? p->K : ORBX_ERR_ARG; }
+int orbx_pool_devices(const orbx_pool* p) { return p ? (int)p->devices.size() : ORBX_ERR_ARG; }
+int orbx_pool_kernel_launches(const orbx_pool* p) { return p ? p->launches : ORBX_ERR_ARG; }
+int orbx_pool_last_ms(const orbx_pool* p, float* ms) {
+    if (!p || !ms) return fail(ORBX_ERR_ARG, "null argument");
+    for (size_t d = 0; d < p->lastMs.size(); ++d) ms[d] = p->lastMs[d];
+    return ORBX_OK;
+}
+
+int orbx_pool_extract(orbx_pool* p, const uint8_t* images, size_t row_stride, size_t image_stride, int n_images, const int* lapping,
+                      orbx_keypoint* keypoints, uint8_t* descriptors, int* counts, int* mono_index) {
+    if (!p) return fail(ORBX_ERR_ARG, "null pool");
+    if (n_images < 0) return fail(ORBX_ERR_ARG, "negative image count");
+    if (n_images == 0) return ORBX_OK;
+    if (!images) return fail(ORBX_ERR_EMPTY, "null image");
+    if (row_stride < (size_t)p->width || image_stride < row_stride * (size_t)p->height) return fail(ORBX_ERR_ARG, "strides smaller than the image");
+    const int G = (int)p->devices.size(), chunk = p->chunk, nChunks = (n_images + chunk - 1) / chunk;
+    const size_t K = (size_t)p->K;
+    std::vector<int> rc((size_t)G, ORBX_OK), nl((size_t)G, 0);
+    std::vector<std::string> err((size_t)G);
+    // one host thread per device (the scaled-out form of the two extraction threads of Frame.cc:139-142): it only enqueues,
+    // every copy and kernel is asynchronous on the handles' streams
+    auto worker = [&](int d) {
+        std::vector<orbx_batch*>& hs = p->handles[(size_t)d];
+        const int nh = (int)hs.size();
+        int r = ORBX_OK, mine = 0;
+        DeviceGuard dg(p->devices[(size_t)d]);
+        cudaEventRecord(p->evStart[(size_t)d], hs[0]->stream);
+        for (int k = 1; k < nh; ++k) cudaStreamWaitEvent(hs[(size_t)k]->stream, p->evStart[(size_t)d], 0);   // nobody starts before the clock does
+        for (int c = d; c < nChunks && r == ORBX_OK; c += G, ++mine) {
+            orbx_batch* b = hs[(size_t)(mine % nh)];
+            const int first = c * chunk, n = std::min(chunk, n_images - first);
+            r = orbx_batch_upload(b, images + (size_t)first * image_stride, row_stride, image_stride, 0, n);
+            if (r == ORBX_OK) r = orbx_batch_run(b, n, lapping ? lapping + 2 * (size_t)first : nullptr);
+            if (r == ORBX_OK)
+                r = orbx_batch_download_async(b, 0, n, keypoints ? keypoints + (size_t)first * K : nullptr, descriptors ? descriptors + (size_t)first * K * 32 : nullptr,
+                                              counts ? counts + first : nullptr, mono_index ? mono_index + first : nullptr);
+            nl[(size_t)d] += orbx_batch_kernel_launches(b);
+        }
+        // join the handles' streams on the first one, stop the clock there, wait
+        for (int k = 1; k < nh; ++k) {
+            cudaEventRecord(hs[(size_t)k]->evFork, hs[(size_t)k]->stream);
+            cudaStreamWaitEvent(hs[0]->stream, hs[(size_t)k]->evFork, 0);
+        }
+        cudaEventRecord(p->evStop[(size_t)d], hs[0]->stream);
+        for (int k = 0; k < nh; ++k) {
+            const int rk = orbx_batch_check(hs[(size_t)k]);   // synchronises the handle's stream, reports device-side capacity errors
+            if (r == ORBX_OK) r = rk;
+        }
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p->evStart[(size_t)d], p->evStop[(size_t)d]) == cudaSuccess) p->lastMs[(size_t)d] = ms;
+        rc[(size_t)d] = r;
+        if (r != ORBX_OK) err[(size_t)d] = g_err;   // (g_err is thread local)
+    };
+    std::vector<std::thread> th;
+    for (int d = 1; d < G; ++d) th.emplace_back(worker, d);
+    worker(0);
+    for (std::thread& t : th) t.join();
+    p->launches = 0;
+    for (int d = 0; d < G; ++d) p->launches += nl[(size_t)d];
+    for (int d = 0; d < G; ++d)
+        if (rc[(size_t)d] != ORBX_OK) return fail(rc[(size_t)d], "device " + std::to_string(p->devices[(size_t)d]) + ": " + err[(size_t)d]);
+    return ORBX_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------------
 // Single-image handle == one TC2LI_SLAM::ORBextractor instance: a batch of one, created lazily for the image size
 // ------------------------------------------------------------------------------------------------------------------
 struct orbx_extractor {
@@ -1220,6 +1351,7 @@ struct orbx_extractor {
     int rectW = 0, rectH = 0, srcW = 0, srcH = 0;   // fed (rectified / resized) size and raw size; rectW > 0: the extract calls take RAW images
     bool inResize = false;                          // raw images are resized (orbx_set_input_resize) instead of remapped
     bool rectDirty = false;
+    unsigned tapsGeneration = 0;  // generation of the batch's taps the graph was captured with
     int graphState = 0;  // 0: next call runs eagerly (lazy allocations), 1: capture on the next call, 2: replay `exec`, 3: capture failed, stay eager
 };
 
@@ -1311,6 +1443,11 @@ int extractor_issue(orbx_extractor* h, const uint8_t* image, int w, int hgt, siz
     orbx_batch* b = h->b;
     static const bool noGraph = std::getenv("ORBX_NO_GRAPH") != nullptr;
     if (noGraph || b->timing || b->stream != b->own) return extractor_enqueue(h, w, hgt);
+    if (h->graphState == 2 && h->tapsGeneration != b->tapsGeneration) {  // taps changed through the batch handle: the graph is stale
+        if (h->exec) { cudaGraphExecDestroy(h->exec); h->exec = nullptr; }
+        h->graphState = 1;
+    }
+    h->tapsGeneration = b->tapsGeneration;
     if (h->graphState == 0) { h->graphState = 1; return extractor_enqueue(h, w, hgt); }  // first call eager: lazy allocations happen here
     if (h->graphState == 3) return extractor_enqueue(h, w, hgt);
     if (h->graphState == 1) {
@@ -1408,6 +1545,11 @@ int orbx_max_keypoints(const orbx_extractor* h) {
 }
 int orbx_set_blur_taps(orbx_extractor* h, const int taps[7]) {
     if (!h || !taps) return fail(ORBX_ERR_ARG, "null argument");
+    {
+        int sum = 0;
+        for (int i = 0; i < 7; ++i) { if (taps[i] < 0 || taps[i] > 255) return fail(ORBX_ERR_ARG, "tap outside [0,255] (the kernel packs taps into bytes)"); sum += taps[i]; }
+        if (sum > 257) return fail(ORBX_ERR_ARG, "taps must sum to about 256 (8.8 fixed point)");
+    }
     std::memcpy(h->taps, taps, sizeof(h->taps));
     if (h->exec) { cudaGraphExecDestroy(h->exec); h->exec = nullptr; }  // the taps are baked into the captured kernel arguments
     if (h->graphState == 2) h->graphState = 1;
@@ -1534,6 +1676,7 @@ int orbx_stereo_match(orbx_extractor* left, orbx_extractor* right, float mb, flo
     if (bl->device != br->device || bl->width != br->width || bl->height != br->height || bl->g.K != br->g.K || bl->g.nlevels != br->g.nlevels)
         return fail(ORBX_ERR_ARG, "left and right extractors differ in image size, parameters or device");
     if (!(mb > 0.f) || !(mbf > 0.f)) return fail(ORBX_ERR_ARG, "mb and mbf must be positive");
+    if (bl->p.scaleFactorF > 1.9f) return fail(ORBX_ERR_ARG, "stereo matching needs scaleFactor <= 1.9 (beyond it the reference's SAD window, Frame.cc:950, leaves the image and cv::Mat::colRange asserts)");
     if (stereo_smem_bytes(bl->g.K, bl->g.lv[0].h) > 220 * 1024) return fail(ORBX_ERR_TOO_LARGE, "keypoint capacity too large for the stereo matcher's shared memory");
     DeviceGuard dg(bl->device);
     CU(cudaStreamSynchronize(br->stream));  // the right image's results must be complete (the left stream orders its own)

@@ -3,6 +3,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "../../include/orbx.h"
 #include "tma.cuh"
 
@@ -97,6 +102,24 @@ struct Buffers {
     const uint4* cellTab;   // [cellsPerImage] FAST cell descriptors (make_cell_table)
     int imgBase;            // first image of this launch set (kernels index images as imgBase + blockIdx)
 };
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to (kernel, device), not to a handle: a second handle with smaller parameters must
+// not lower the limit a live, larger handle launches with.  Every *_configure goes through this: the limit is only ever raised.
+template <typename Kernel>
+inline cudaError_t raise_dynamic_smem(Kernel kernel, size_t bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, size_t> limit;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& cur = limit[std::make_pair(reinterpret_cast<const void*>(kernel), dev)];
+    const size_t want = std::max<size_t>(bytes, 48 * 1024);
+    if (want <= cur) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
+    if (e == cudaSuccess) cur = want;
+    return e;
+}
 
 // kernel launchers (one translation unit per stage)
 void launch_synth(uint8_t* l0, int w, int h, int pitch, size_t planeBytes, uint32_t seed0, int firstImage, int nImages, int stereo, cudaStream_t s);

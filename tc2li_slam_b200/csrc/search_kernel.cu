@@ -302,9 +302,9 @@ size_t search_smem_bytes(int K, int nq, int candCap, int stageDesc) {
 }
 
 cudaError_t search_configure() {
-    cudaError_t e = cudaFuncSetAttribute(k_search_by_projection<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = raise_dynamic_smem(k_search_by_projection<false>, 200 * 1024);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_search_by_projection<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    return raise_dynamic_smem(k_search_by_projection<true>, 200 * 1024);
 }
 
 void launch_search_by_projection(const Buffers& b, int image, int K, const GridParams& p, const orbx_proj_query* queries, int nq, int useURight, int checkOrientation,

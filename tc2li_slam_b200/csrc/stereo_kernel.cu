@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(SM_THREADS) k_stereo_match(const __grid_consta
 }
 
 cudaError_t stereo_configure(int K, int H) {
-    return cudaFuncSetAttribute(k_stereo_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(stereo_smem_bytes(K, H), 48 * 1024));
+    return raise_dynamic_smem(k_stereo_match, stereo_smem_bytes(K, H));
 }
 
 void launch_stereo_match(const Geom& g, const Buffers& bl, const Buffers& br, int nFrames, int lMul, int lAdd, int rMul, int rAdd, float mb, float mbf,

@@ -100,7 +100,7 @@ def lib():
         "orbx_batch_run_pipelined": (i, [_vp, i, _vp, i]),
         "orbx_batch_download_async": (i, [_vp, i, i, _vp, _vp, _vp, _vp]),
         "orbx_batch_check": (i, [_vp]),
-        "orbx_event_create": (_vp, []),
+        "orbx_event_create": (_vp, [_vp]),
         "orbx_event_destroy": (None, [_vp]),
         "orbx_event_record": (i, [_vp, _vp]),
         "orbx_event_wait": (i, [_vp, _vp]),
@@ -115,6 +115,13 @@ def lib():
         "orbx_batch_debug_candidates": (i, [_vp, i, i, _vp, i, _vp]),
         "orbx_batch_debug_selected": (i, [_vp, i, i, _vp, i, _vp]),
         "orbx_batch_debug_fallback_cells": (i, [_vp, i, i, _vp]),
+        "orbx_pool_create": (i, [i, f, i, i, i, _vp, i, i, i, i, i, C.POINTER(_vp)]),
+        "orbx_pool_destroy": (None, [_vp]),
+        "orbx_pool_max_keypoints": (i, [_vp]),
+        "orbx_pool_devices": (i, [_vp]),
+        "orbx_pool_extract": (i, [_vp, _vp, sz, sz, i, _vp, _vp, _vp, _vp, _vp]),
+        "orbx_pool_last_ms": (i, [_vp, _vp]),
+        "orbx_pool_kernel_launches": (i, [_vp]),
         "orbx_alloc_pinned": (_vp, [sz]),
         "orbx_free_pinned": (None, [_vp]),
         "orbx_tables": (i, [i, f, i, i, i, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -189,8 +196,8 @@ def debug_atan2(y, x):
 class Event:
     """CUDA event recorded on a BatchExtractor's stream (device-side timing / ordering between handles)."""
 
-    def __init__(self):
-        self._e = lib().orbx_event_create()
+    def __init__(self, batch):
+        self._e = lib().orbx_event_create(batch._h)   # (an event lives on the batch's device)
         if not self._e:
             raise OrbxError(ERR_CUDA, lib().orbx_last_error().decode())
 
@@ -737,3 +744,50 @@ class BatchExtractor:
     @property
     def kernel_launches(self):
         return lib().orbx_batch_kernel_launches(self._h)
+
+
+class ExtractorPool:
+    """orbx_pool: every GPU of the box behind one call.  Frames are sharded by chunk over the devices, one host
+    thread and `handles_per_device` pipelined batch handles per device; host images in, frame-ordered host results out."""
+
+    def __init__(self, width, height, devices, nfeatures=2000, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7, chunk_images=128, handles_per_device=3):
+        devs = np.ascontiguousarray(np.asarray(devices, np.int32))
+        self._h = _vp()
+        _check(lib().orbx_pool_create(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, _p(devs), len(devs), width, height, chunk_images,
+                                      handles_per_device, C.byref(self._h)))
+        self.width, self.height, self.n_devices = width, height, len(devs)
+        self.K = lib().orbx_pool_max_keypoints(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().orbx_pool_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def extract(self, images, lapping=None, keypoints=None, descriptors=None, counts=None, mono=None):
+        """images: [n, H, W] uint8 (pinned for speed).  Returns (keypoints [n, K], descriptors [n, K, 32], counts [n], mono [n]);
+        pass preallocated (pinned) outputs to keep the downloads asynchronous."""
+        n = len(images)
+        assert images.dtype == np.uint8 and images.shape[1:] == (self.height, self.width) and images.strides[2] == 1
+        keypoints = np.empty((n, self.K), KP_DTYPE) if keypoints is None else keypoints
+        descriptors = np.empty((n, self.K, 32), np.uint8) if descriptors is None else descriptors
+        counts = np.empty(n, np.int32) if counts is None else counts
+        mono = np.empty(n, np.int32) if mono is None else mono
+        lap = None if lapping is None else np.ascontiguousarray(lapping, np.int32)
+        _check(lib().orbx_pool_extract(self._h, _p(images), images.strides[1], images.strides[0], n, None if lap is None else _p(lap), _p(keypoints),
+                                       _p(descriptors), _p(counts), _p(mono)))
+        return keypoints, descriptors, counts, mono
+
+    def last_ms(self):
+        ms = np.zeros(self.n_devices, np.float32)
+        _check(lib().orbx_pool_last_ms(self._h, _p(ms)))
+        return ms
+
+    @property
+    def kernel_launches(self):
+        return lib().orbx_pool_kernel_launches(self._h)

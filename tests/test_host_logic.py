@@ -95,6 +95,15 @@ def test_no_gpu_means_loud_failure():
     assert b"CUDA" in T.lib().orbx_last_error()
 
 
+def test_pool_without_gpu_fails_loudly():
+    import ctypes
+    h = ctypes.c_void_p()
+    devs = (ctypes.c_int * 1)(99)
+    rc = T.lib().orbx_pool_create(2000, 1.2, 8, 20, 7, devs, 1, 1241, 376, 16, 2, ctypes.byref(h))
+    assert rc == orbx.ERR_CUDA and not h.value
+    assert T.lib().orbx_pool_extract(None, None, 0, 0, 1, None, None, None, None, None) == orbx.ERR_ARG
+
+
 def test_query_record_layouts_match_the_c_structs():
     """orbx_area_query (6 x 4 bytes) and orbx_proj_query (8 x 4 + 32 bytes) as numpy records, and the oracle's copy of the latter."""
     import tc2li_slam_b200 as T
