@@ -211,21 +211,23 @@ def bind_to_gpu_numa_node(device):
         return None
 
 
-def feed_ceiling(n_gpus, h2d_bytes, d2h_bytes, frames):
-    """The host <-> device copy ceiling for this step's traffic: profiles/tools/feed_probe run live (duplex, pinned buffers of the
-    benchmark's chunk sizes, one host thread per GPU), else the committed measurement profiles/r02/feed_ceiling.json."""
+def feed_ceiling(devices, h2d_bytes, d2h_bytes, frames):
+    """The host <-> device copy ceiling for this step's traffic on these GPUs: profiles/tools/feed_probe run live (pinned buffers of
+    the benchmark's chunk sizes, one host process per GPU), else the committed measurement profiles/r02/feed_ceiling.json."""
     run, src = None, None
     exe = os.path.join(ROOT, "profiles", "tools", "feed_probe")
     try:
         if os.access(exe, os.X_OK):
-            out = subprocess.run([exe, "0.3", str(n_gpus)], capture_output=True, text=True, timeout=120).stdout
-            run, src = json.loads(out)["runs"][0], "live: profiles/tools/feed_probe"
+            out = subprocess.run([exe, "0.3", ",".join(str(d) for d in devices)], capture_output=True, text=True, timeout=120).stdout
+            run, src = json.loads(out)["runs"][0], "live: profiles/tools/feed_probe (one process per GPU)"
+            if not run.get("ok", True):
+                run = None
     except Exception:
         run = None
     if run is None:
         try:
             for r_ in json.load(open(os.path.join(ROOT, "profiles", "r02", "feed_ceiling.json")))["runs"]:
-                if r_["n"] == n_gpus and r_["gpus"] == list(range(n_gpus)):
+                if r_["gpus"] == list(devices):
                     run, src = r_, "profiles/r02/feed_ceiling.json"
         except Exception:
             pass
@@ -264,6 +266,16 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # rank -> GPU: spread over the box (N = 2 -> GPUs 0, 4; N = 4 -> 0, 2, 4, 6 on an 8-GPU box).  Neighbouring GPUs share an upstream PCIe
+    # port here: GPUs 0-3 together get what GPUs 0 and 4 get as a pair (profiles/r02/feed_ceiling.json)
+    ndev = 0
+    try:
+        ndev = len([l_ for l_ in subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True, timeout=30).stdout.splitlines() if l_.startswith("GPU ")])
+    except Exception:
+        pass
+    spread = ndev // world if ndev >= world and world > 1 and ndev % world == 0 else 1
+    devices = [r_ * spread for r_ in range(world)]
+    local = devices[local] if world > 1 else local
     numa = bind_to_gpu_numa_node(local) if world > 1 else None
     dist = None
     if world > 1:
@@ -300,7 +312,7 @@ def main():
     group = min(args.group, n_img) if args.group > 0 else n_img
 
     # ---- resident run: all level-0 images live in the handle's pyramid buffer ----
-    big = T.BatchExtractor(W, H, n_img, *ORB_ARGS, device=local)
+    big = T.BatchExtractor(W, H, n_img, *ORB_ARGS, device=local)   # (local = this rank's GPU)
     big.synth(seed0, n_img, stereo=True)
     big.sync()
 
@@ -355,13 +367,22 @@ def main():
     dom_launch_ms = stage_ms[dom] / (launches_of[dom] * n_sets)
     dom_bytes_launch = ab[dom] * n_img / (launches_of[dom] * n_sets)
     traffic = None  # measured DRAM read+write bytes per launch of the dominant kernel (ncu --set full, profiles/traffic.json)
+    issue = None    # the bound the dominant kernel actually runs against when it is not HBM: instruction issue (4 warp instructions per clock and SM)
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         traffic = tj["bytes_per_image"][dom] * n_img / (launches_of[dom] * n_sets)
+        wi = tj["warp_instructions_per_image"][dom]
+        px = sum(w_ * h_ for w_, h_ in level_sizes())
+        sm_mhz = (clocks or {}).get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
+        issue = {"lane_instr_per_pixel": wi * 32.0 / px, "warp_instr_per_image": wi, "issue_pct": tj["issue_pct"][dom],
+                 "achieved_occupancy_pct": tj["achieved_occupancy_pct"][dom],
+                 "frac_of_issue_peak": wi * n_img / (stage_ms[dom] * 1e-3 * 148 * 4 * sm_mhz * 1e6),
+                 "what": "warp instructions (smsp__inst_executed, ncu capture: " + tj["source"] + ") per image x images of this run / (stage time measured in this run "
+                         "x 148 SMs x 4 schedulers x the SM clock sampled in this run); issue_pct is ncu's own smsp__issue_active of that capture"}
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": dom_bytes_launch / (dom_launch_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": dom_bytes_launch / (dom_launch_ms * 1e-3) / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
+                "frac": dom_bytes_launch / (dom_launch_ms * 1e-3) / 1e9 / peak, "traffic": traffic, "issue": issue, "peak_source": peak_src,
                 "bytes_per_launch": dom_bytes_launch, "ms_per_launch": dom_launch_ms,
                 "whole_step": {"bytes_per_frame": 2 * ab["total"], "GBps": 2 * ab["total"] * args.pairs / (ms_step * 1e-3) / 1e9,
                                "frac": 2 * ab["total"] * args.pairs / (ms_step * 1e-3) / 1e9 / peak}}
@@ -430,7 +451,7 @@ def main():
     #      N = 1: a pool of this GPU.  N > 1: every rank first drives its own GPU at the same time (supplementary), then rank 0
     #      alone drives ALL N GPUs through ONE pool from one process — the multi-GPU product API — while the other ranks wait ----
     e2e = None
-    e2e_ranks = None
+    e2e_one = None
     pinned_in = None
     out_kps = out_desc = out_cnt = out_mono = None
     feed = None
@@ -466,33 +487,33 @@ def main():
         barrier()
         ms_ranks = max_over_ranks(ms_mine)
         e2e = {"value": args.pairs * world / (ms_ranks * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
-               "ms_per_step": ms_ranks, "api": "orbx_pool_extract (include/orbx.h)",
-               "pipeline": f"per GPU: one host thread, 3 handles x {chunk} images, pinned host buffers", "gpu_launches": launches_e2e * world}
+               "ms_per_step": ms_ranks, "api": "orbx_pool_extract (include/orbx.h), one rank per GPU" if world > 1 else "orbx_pool_extract (include/orbx.h)",
+               "pipeline": f"per GPU: one host thread, 3 handles x {chunk} images, pinned host buffers", "gpu_launches": launches_e2e * world,
+               "gpus": devices if world > 1 else [local]}
         if world > 1:
-            e2e_ranks = dict(e2e, what=f"{world} processes, each driving its own GPU through a pool of one at the same time")
-            e2e = None
             if rank == 0:
-                # one process, one pool over all N GPUs; the frames of GPU d's share are rank 0's frames again (throughput does not depend on the texture)
+                feed = feed_ceiling(devices, h2d * world, d2h * world, args.pairs * world)   # (the other ranks wait at the barrier below)
+                # supplementary: ONE process driving all N GPUs through one pool; GPU d's share are rank 0's frames again
+                # (throughput does not depend on the texture)
                 all_in = T.PinnedArray((world * n_img, H, W), np.uint8)
                 for r_ in range(world):
                     all_in.array[r_ * n_img:(r_ + 1) * n_img] = pinned_in.array
                 all_out = (T.PinnedArray((world * n_img, K), T.KP_DTYPE), T.PinnedArray((world * n_img, K, 32), np.uint8),
                            T.PinnedArray((world * n_img,), np.int32), T.PinnedArray((world * n_img,), np.int32))
-                feed = feed_ceiling(world, h2d * world, d2h * world, args.pairs * world)
-                pool = T.ExtractorPool(W, H, list(range(world)), *ORB_ARGS, chunk_images=chunk, handles_per_device=3)
+                pool = T.ExtractorPool(W, H, devices, *ORB_ARGS, chunk_images=chunk, handles_per_device=3)
                 ms_pool = pool_run(pool, all_in.array, tuple(a.array for a in all_out))
                 assert np.array_equal(all_out[2].array, np.tile(counts, world)), "pool keypoint counts differ from the resident run"
-                e2e = {"value": args.pairs * world / (ms_pool * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
-                       "ms_per_step": ms_pool, "api": "orbx_pool_extract (include/orbx.h), ONE process driving all GPUs",
-                       "pipeline": f"per GPU: one host thread, 3 handles x {chunk} images, pinned host buffers; chunk c -> GPU c mod {world}",
-                       "gpu_launches": pool.kernel_launches, "per_gpu_ms": [float(x) for x in pool.last_ms()]}
+                e2e_one = {"value": args.pairs * world / (ms_pool * 1e-3), "unit": UNIT, "ms_per_step": ms_pool,
+                           "what": f"orbx_pool_extract from ONE process over all {world} GPUs (chunk c -> GPU c mod {world}); the driver serialises part of the "
+                                   "copy submission inside a process: see profiles/r02/feed_ceiling_one_process.json against feed_ceiling.json",
+                           "per_gpu_ms": [float(x) for x in pool.last_ms()]}
                 pool.close()
                 for a in (all_in,) + all_out:
                     a.free()
             barrier()
         elif rank == 0:
-            feed = feed_ceiling(1, h2d, d2h, args.pairs)
-        if e2e is not None and feed is not None and feed.get("ceiling_frames_per_s"):
+            feed = feed_ceiling([local], h2d, d2h, args.pairs)
+        if feed is not None and feed.get("ceiling_frames_per_s"):
             e2e["frac_of_feed_ceiling"] = e2e["value"] / feed["ceiling_frames_per_s"]
             e2e["feed_ceiling"] = feed
 
@@ -619,7 +640,7 @@ def main():
             "config": {"workload": WORKLOAD,
                        "pairs_per_gpu_per_step": args.pairs, "images_per_launch_set": group, "keypoints_per_image": kp_mean,
                        "l2": f"inputs {n_img * W * H / 1e9:.2f} GB per rank, larger than the {L2_BYTES / 1e6:.0f} MB L2; no flush needed"},
-            "clocks": clocks, "numa_binding": numa, "e2e": e2e, "e2e_one_process_per_gpu": e2e_ranks, "parity": parity, "gpu_launches": launches_per_step, "roofline": roofline, "cpu_baseline": cpu, "stages": stages, "latency": latency, "stereo_match": stereo, "feature_grid": grid, "large_images": large, "euroc_lapping": euroc,
+            "clocks": clocks, "numa_binding": numa, "e2e": e2e, "e2e_one_process_all_gpus": e2e_one, "parity": parity, "gpu_launches": launches_per_step, "roofline": roofline, "cpu_baseline": cpu, "stages": stages, "latency": latency, "stereo_match": stereo, "feature_grid": grid, "large_images": large, "euroc_lapping": euroc,
         }
         emit_line(json.dumps(line))
     big.close()

@@ -28,11 +28,16 @@ for n in range(1, len(rows)):
         per_step = n
         break
 rows = rows[-per_step:]
-per_stage, us = {}, {}
+per_stage, us, winst, issue_w, occ_w = {}, {}, {}, {}, {}
 for r in rows:
     st = stage_of(r["kernel"])
     per_stage[st] = per_stage.get(st, 0.0) + (r.get("dram_rd_MB", 0) + r.get("dram_wr_MB", 0)) * 1e6 / nimg
     us[st] = us.get(st, 0.0) + r.get("us", 0)
-out = {"launches_per_step": per_step, "source": f"ncu --set full, {tag}, {nimg} KITTI-shaped images per launch set", "bytes_per_image": per_stage, "us_per_launch_set": us}
+    winst[st] = winst.get(st, 0.0) + r.get("warp_inst", 0)
+    issue_w[st] = issue_w.get(st, 0.0) + r.get("issue_pct", 0) * r.get("us", 0)   # time-weighted over the stage's launches
+    occ_w[st] = occ_w.get(st, 0.0) + r.get("occ_pct", 0) * r.get("us", 0)
+out = {"launches_per_step": per_step, "source": f"ncu --set full, {tag}, {nimg} KITTI-shaped images per launch set", "images": nimg, "bytes_per_image": per_stage,
+       "us_per_launch_set": us, "warp_instructions_per_image": {k: v / nimg for k, v in winst.items()},
+       "issue_pct": {k: issue_w[k] / us[k] for k in us if us[k]}, "achieved_occupancy_pct": {k: occ_w[k] / us[k] for k in us if us[k]}}
 json.dump(out, open(os.path.join(root, "profiles", "traffic.json"), "w"), indent=1)
 print(json.dumps(out, indent=1))
