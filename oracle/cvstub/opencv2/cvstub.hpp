@@ -79,8 +79,8 @@ public:
     uchar* data;
     MatStep step;
     Mat() : rows(0), cols(0), data(nullptr), step{0} {}
-    Mat(int r, int c, int) { create(r, c, 0); }
-    Mat(Size s, int) { create(s.height, s.width, 0); }
+    Mat(int r, int c, int) : rows(0), cols(0), data(nullptr), step{0} { create(r, c, 0); }
+    Mat(Size s, int) : rows(0), cols(0), data(nullptr), step{0} { create(s.height, s.width, 0); }
     Mat(int r, int c, int, void* ext, size_t st) : rows(r), cols(c), data((uchar*)ext), step{st} {}  // non-owning
     void create(int r, int c, int) {
         if (data && r == rows && c == cols) return;

@@ -24,6 +24,8 @@
 #include <cstdint>
 #include <cstring>
 #include <list>
+#include <cstdio>
+#include <map>
 #include <vector>
 
 namespace {
@@ -953,6 +955,104 @@ int search_local_points(const KeyPoint* kps, int nKps, const uint8_t* desc, cons
 }
 
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// DBoW2 vocabulary: what Frame::ComputeBoW (Frame.cc:768-775) runs on the descriptors the extractor produced.  Restated from the
+// vendored library (slam_framework/Thirdparty/DBoW2/DBoW2): the text loader the reference uses for ORBvoc.txt
+// (TemplatedVocabulary.h:1350-1433), the tree descent (:1230-1276) with FORB::distance (FORB.cpp:81-100), the vector assembly
+// (:1139-1214), BowVector::addWeight / addIfNotExist / normalize (BowVector.cpp:34-84), mustNormalize (ScoringObject.h:74-89).
+// Pinned against that code compiled here (oracle/_ref/libref_bow.so, tests/test_oracle_vs_ref.py).
+// One deliberate difference: the reference's `while(!f.eof())` turns a trailing empty line into one more child of the root with an
+// UNINITIALISED descriptor (FORB::fromString sets no byte when the string is empty); here empty lines are skipped.  The results
+// are the same for files that do not end in a blank line (the tests write such files).
+// ------------------------------------------------------------------------------------------------------------------
+struct Vocabulary {
+    int k = 0, L = 0, scoring = 0, weighting = 0;
+    std::vector<int> parent;                 // node 0 is the root
+    std::vector<std::vector<int>> children;  // in file order (= ascending node id)
+    std::vector<uint8_t> desc;               // [node][32]
+    std::vector<double> weight;
+    std::vector<int> wordId;                 // -1 for inner nodes
+    int nWords = 0;
+};
+
+static bool vocabulary_load_text(const char* path, Vocabulary& v) {
+    FILE* f = std::fopen(path, "r");
+    if (!f) return false;
+    std::vector<char> line(1 << 12);
+    if (!std::fgets(line.data(), (int)line.size(), f)) { std::fclose(f); return false; }
+    if (std::sscanf(line.data(), "%d %d %d %d", &v.k, &v.L, &v.scoring, &v.weighting) != 4 || v.k < 0 || v.k > 20 || v.L < 1 || v.L > 10 || v.scoring < 0 ||
+        v.scoring > 5 || v.weighting < 0 || v.weighting > 3) { std::fclose(f); return false; }
+    v.parent.assign(1, 0); v.children.assign(1, {}); v.desc.assign(32, 0); v.weight.assign(1, 0.0); v.wordId.assign(1, -1);
+    while (std::fgets(line.data(), (int)line.size(), f)) {
+        char* p = line.data();
+        char* e = nullptr;
+        const long pid = std::strtol(p, &e, 10);
+        if (e == p) continue;  // blank line
+        p = e;
+        const long leaf = std::strtol(p, &e, 10); p = e;
+        const int nid = (int)v.parent.size();
+        v.parent.push_back((int)pid);
+        v.children.emplace_back();
+        v.children[(size_t)pid].push_back(nid);
+        for (int i = 0; i < 32; ++i) { const long b = std::strtol(p, &e, 10); p = e; v.desc.push_back((uint8_t)b); }
+        v.weight.push_back(std::strtod(p, &e));
+        v.wordId.push_back(leaf > 0 ? v.nWords++ : -1);
+    }
+    std::fclose(f);
+    return true;
+}
+
+
+// one descriptor down the tree: the child with the smallest distance, the FIRST of equals (strict <); nid = the node at level L - levelsup
+static void vocabulary_descend(const Vocabulary& v, const uint8_t* d, int levelsup, int* word, double* w, int* nid) {
+    const int nidLevel = v.L - levelsup;
+    *nid = 0;  // (the reference sets it only when nidLevel <= 0 or the descent passes that level: complete trees always do)
+    int node = 0, level = 0;
+    do {
+        ++level;
+        const std::vector<int>& ch = v.children[(size_t)node];
+        node = ch[0];
+        int best = hamming256(d, &v.desc[(size_t)node * 32]);
+        for (size_t c = 1; c < ch.size(); ++c) {
+            const int dist = hamming256(d, &v.desc[(size_t)ch[c] * 32]);
+            if (dist < best) { best = dist; node = ch[c]; }
+        }
+        if (level == nidLevel) *nid = node;
+    } while (!v.children[(size_t)node].empty());
+    *word = v.wordId[(size_t)node] < 0 ? 0 : v.wordId[(size_t)node];   // (Node::word_id defaults to 0)
+    *w = v.weight[(size_t)node];
+}
+
+static void vocabulary_transform(const Vocabulary& v, const uint8_t* desc, int n, int levelsup, std::map<unsigned, double>& bow,
+                                 std::map<unsigned, std::vector<unsigned>>& fv) {
+    bow.clear(); fv.clear();
+    if (v.parent.size() <= 1) return;
+    const bool must = v.scoring != 5;             // DotProductScoring is the one that does not normalise
+    const bool l2 = v.scoring == 1;
+    const bool tf = v.weighting == 0 || v.weighting == 1;   // TF_IDF, TF: weights add up; IDF, BINARY: a word counts once
+    for (int i = 0; i < n; ++i) {
+        int word, nid; double w;
+        vocabulary_descend(v, desc + (size_t)i * 32, levelsup, &word, &w, &nid);
+        if (w > 0) {
+            auto it = bow.lower_bound((unsigned)word);
+            if (it != bow.end() && it->first == (unsigned)word) { if (tf) it->second += w; }
+            else bow.insert(it, std::make_pair((unsigned)word, w));
+            fv[(unsigned)nid].push_back((unsigned)i);
+        }
+    }
+    if (tf && !bow.empty() && !must) {
+        const double nd = (double)bow.size();
+        for (auto& e : bow) e.second /= nd;
+    }
+    if (must) {
+        double norm = 0.0;
+        if (l2) { for (auto& e : bow) norm += e.second * e.second; norm = std::sqrt(norm); }
+        else for (auto& e : bow) norm += std::fabs(e.second);
+        if (norm > 0.0) for (auto& e : bow) e.second /= norm;
+    }
+}
+
 extern "C" {
 void* orbo_create(int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh) {
     return new Extractor(nfeatures, scaleFactor, nlevels, iniTh, minTh);
@@ -1026,6 +1126,42 @@ void orbo_remap(const uint8_t* src, int sw, int sh, int sstride, int channels, c
     remap_linear_8u(src, sw, sh, (size_t)sstride, channels, mapx, mapy, (size_t)mstride, dst, dw, dh, (size_t)dstride);
 }
 // primitives, for direct checks against cv2
+// vocabulary (DBoW2) -------------------------------------------------------------------------------------------------
+void* orbo_voc_load_text(const char* path) {
+    Vocabulary* v = new Vocabulary();
+    if (!vocabulary_load_text(path, *v)) { delete v; return nullptr; }
+    return v;
+}
+void orbo_voc_destroy(void* h) { delete (Vocabulary*)h; }
+void orbo_voc_info(void* h, int out[6]) {
+    Vocabulary* v = (Vocabulary*)h;
+    out[0] = v->k; out[1] = v->L; out[2] = v->scoring; out[3] = v->weighting; out[4] = (int)v->parent.size(); out[5] = v->nWords;
+}
+// the tree as flat arrays (node 0 = root): parent[n], is_word[n], descriptors[n][32], weights[n]
+void orbo_voc_export(void* h, int* parent, uint8_t* isWord, uint8_t* desc, double* weight) {
+    Vocabulary* v = (Vocabulary*)h;
+    const size_t n = v->parent.size();
+    for (size_t i = 0; i < n; ++i) { parent[i] = v->parent[i]; isWord[i] = v->wordId[i] >= 0; weight[i] = v->weight[i]; }
+    std::memcpy(desc, v->desc.data(), n * 32);
+}
+int orbo_bow_transform(void* h, const uint8_t* desc, int n, int levelsup, uint32_t* words, double* values, int* nWords, uint32_t* nodes, int* nodeStart,
+                       uint32_t* features, int* nNodes) {
+    std::map<unsigned, double> bow;
+    std::map<unsigned, std::vector<unsigned>> fv;
+    vocabulary_transform(*(Vocabulary*)h, desc, n, levelsup, bow, fv);
+    int k = 0;
+    for (auto& e : bow) { words[k] = e.first; values[k] = e.second; ++k; }
+    *nWords = k;
+    int m = 0, pos = 0;
+    for (auto& e : fv) {
+        nodes[m] = e.first; nodeStart[m] = pos;
+        for (unsigned f : e.second) features[pos++] = f;
+        ++m;
+    }
+    nodeStart[m] = pos;
+    *nNodes = m;
+    return 0;
+}
 void orbo_synth_v1(uint8_t* out, int W, int H, uint32_t seed, int xoff, uint32_t noise_xor) { synth_v1(out, W, H, seed, xoff, noise_xor); }
 void orbo_resize(const uint8_t* src, int sw, int sh, int sstride, uint8_t* dst, int dw, int dh, int dstride) {
     resize_linear_8u(src, sw, sh, (size_t)sstride, dst, dw, dh, (size_t)dstride);

@@ -344,3 +344,79 @@ class OracleExtractor:
         out = np.empty(n, KP_DTYPE)
         lib().orbo_get_selected(self._h, l, _p(out))
         return out
+
+
+# ---- DBoW2 vocabulary transform (Frame::ComputeBoW) ----
+def write_vocabulary_text(path, k, L, scoring, weighting, seed=1, stop_fraction=0.05, trailing_newline=False):
+    """A complete k-ary tree of depth L with random 256-bit node descriptors and idf-like weights in the text format the reference loads
+    ORBvoc.txt from (TemplatedVocabulary::loadFromTextFile): header 'k L scoring weighting', then per node in creation order
+    'parent is_leaf d0 .. d31 weight'.  Nodes are numbered breadth-first like DBoW2's own files; a fraction of the words is
+    stopped (weight 0).  Returns the number of nodes written (without the root)."""
+    rng = np.random.default_rng(seed)
+    lines = [f"{k} {L} {scoring} {weighting}"]
+    level, nid, n = [0], 0, 0
+    for depth in range(1, L + 1):
+        nxt = []
+        for parent in level:
+            for _ in range(k):
+                nid += 1
+                d = rng.integers(0, 256, 32)
+                leaf = depth == L
+                wgt = 0.0
+                if leaf:
+                    wgt = 0.0 if rng.random() < stop_fraction else float(np.round(rng.uniform(0.5, 12.0), 6))
+                    if weighting in (1, 3):   # TF, BINARY: the stored weight of a word is 1
+                        wgt = 0.0 if wgt == 0.0 else 1.0
+                lines.append(f"{parent} {1 if leaf else 0} " + " ".join(str(int(x)) for x in d) + f" {wgt!r}")
+                nxt.append(nid)
+                n += 1
+        level = nxt
+    with open(path, "w") as f:
+        f.write("\n".join(lines) + ("\n" if trailing_newline else ""))
+    return n
+
+
+class _BowBase:
+    def transform(self, desc, levelsup=4):
+        """desc [n, 32] uint8 -> (word ids ascending, values, node ids ascending, node_start [nodes + 1], feature indices)"""
+        desc = np.ascontiguousarray(desc, np.uint8)
+        n = len(desc)
+        words, values = np.zeros(max(n, 1), np.uint32), np.zeros(max(n, 1), np.float64)
+        nodes, start, feats = np.zeros(max(n, 1), np.uint32), np.zeros(n + 2, np.int32), np.zeros(max(n, 1), np.uint32)
+        nw, nn = C.c_int(), C.c_int()
+        self._fn(self._h, _p(desc), n, levelsup, _p(words), _p(values), C.byref(nw), _p(nodes), _p(start), _p(feats), C.byref(nn))
+        return words[:nw.value], values[:nw.value], nodes[:nn.value], start[:nn.value + 1], feats[:start[nn.value]]
+
+
+class OracleVocabulary(_BowBase):
+    """The oracle's restatement of the vendored DBoW2 (orb_oracle.cpp: vocabulary_*)."""
+
+    def __init__(self, path):
+        L = lib()
+        L.orbo_voc_load_text.restype = C.c_void_p
+        L.orbo_voc_load_text.argtypes = [C.c_char_p]
+        L.orbo_voc_destroy.argtypes = [C.c_void_p]
+        L.orbo_voc_info.argtypes = [C.c_void_p, C.c_void_p]
+        L.orbo_voc_export.argtypes = [C.c_void_p] + [C.c_void_p] * 4
+        L.orbo_bow_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 7
+        self._h = L.orbo_voc_load_text(os.fsencode(path))
+        if not self._h:
+            raise RuntimeError("cannot load the vocabulary text file")
+        self._fn = L.orbo_bow_transform
+        info = np.zeros(6, np.int32)
+        L.orbo_voc_info(self._h, _p(info))
+        self.k, self.L, self.scoring, self.weighting, self.n_nodes, self.n_words = (int(x) for x in info)
+
+    def export(self):
+        """(parent, is_word, descriptors, weights) with node 0 = root: the arrays orbx_vocabulary_create takes."""
+        n = self.n_nodes
+        parent, isw, desc, w = np.zeros(n, np.int32), np.zeros(n, np.uint8), np.zeros((n, 32), np.uint8), np.zeros(n, np.float64)
+        lib().orbo_voc_export(self._h, _p(parent), _p(isw), _p(desc), _p(w))
+        return parent, isw, desc, w
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().orbo_voc_destroy(self._h)
+        except Exception:
+            pass

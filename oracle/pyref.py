@@ -245,3 +245,42 @@ def search_keyframe_points(kps, desc, taken0, bounds, scale_factors, points, lev
     nm = _splib.refsp_search_kf(_p(kps), len(kps), _p(desc), _p(t0), *[float(v) for v in bounds], _p(sf), len(sf), _p(pts), _p(lv), _p(fl), _p(pd), len(pts), float(th),
                                 int(orb_dist), int(bool(check_orientation)), _p(match))
     return match[:len(kps)], nm
+
+
+class RefVocabulary:
+    """The reference's OWN DBoW2 (oracle/_ref/libref_bow.so, oracle/ref_bow_capi.cpp): loadFromTextFile + transform."""
+    _LIB = os.path.join(_HERE, "_ref", "libref_bow.so")
+
+    @classmethod
+    def available(cls):
+        return os.path.exists(cls._LIB)
+
+    def __init__(self, path):
+        L = C.CDLL(self._LIB)
+        L.refb_load_text.restype = C.c_void_p
+        L.refb_load_text.argtypes = [C.c_char_p]
+        L.refb_destroy.argtypes = [C.c_void_p]
+        L.refb_words.argtypes = [C.c_void_p]
+        L.refb_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 7
+        self._L = L
+        self._h = L.refb_load_text(os.fsencode(path))
+        if not self._h:
+            raise RuntimeError("the reference could not load the vocabulary text file")
+        self.n_words = L.refb_words(self._h)
+
+    def transform(self, desc, levelsup=4):
+        desc = np.ascontiguousarray(desc, np.uint8)
+        n = len(desc)
+        words, values = np.zeros(max(n, 1), np.uint32), np.zeros(max(n, 1), np.float64)
+        nodes, start, feats = np.zeros(max(n, 1), np.uint32), np.zeros(n + 2, np.int32), np.zeros(max(n, 1), np.uint32)
+        nw, nn = C.c_int(), C.c_int()
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        self._L.refb_transform(self._h, p(desc), n, levelsup, p(words), p(values), C.byref(nw), p(nodes), p(start), p(feats), C.byref(nn))
+        return words[:nw.value], values[:nw.value], nodes[:nn.value], start[:nn.value + 1], feats[:start[nn.value]]
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._L.refb_destroy(self._h)
+        except Exception:
+            pass

@@ -267,3 +267,30 @@ def test_search_keyframe_points_matches_reference_body(seed, th, dist, check):
     om, on = po.search_by_projection(kc, dc, None, po.assign_grid(kc, bounds), bounds, q, check, dist, taken0)
     assert rn == on and rn > 20, (rn, on)
     assert np.array_equal(rm, np.where(om >= 0, sel[np.maximum(om, 0)], -1))
+
+
+# ---- DBoW2 vocabulary transform (Frame::ComputeBoW, Frame.cc:768-775) ----
+BOW_CASES = [  # (k, L, scoring, weighting): L1 / L2 / chi-square / KL / Bhattacharyya / dot-product x TF-IDF / TF / IDF / binary
+    (10, 6, 0, 0), (10, 4, 1, 0), (6, 3, 0, 1), (4, 5, 5, 2), (3, 4, 2, 3), (10, 3, 4, 0), (10, 3, 3, 0), (9, 3, 5, 0), (2, 8, 0, 0),
+]
+
+
+@pytest.mark.skipif(not pyref.RefVocabulary.available(), reason="oracle/_ref/libref_bow.so not built")
+@pytest.mark.parametrize("k,L,scoring,weighting", BOW_CASES)
+def test_bow_transform_restatement_equals_vendored_dbow2(tmp_path, k, L, scoring, weighting):
+    """oracle vocabulary_* == the reference's vendored DBoW2 (TemplatedVocabulary::loadFromTextFile + transform, FORB::distance,
+    BowVector::addWeight / addIfNotExist / normalize) on synthetic vocabularies in ORBvoc.txt's format (the real file is absent from
+    the reference checkout): word ids, values (as float64 bits), FeatureVector node ids and their feature lists."""
+    path = str(tmp_path / "voc.txt")
+    po.write_vocabulary_text(path, k, L, scoring, weighting, seed=100 * k + L)
+    ora, ref = po.OracleVocabulary(path), pyref.RefVocabulary(path)
+    assert ora.n_words == ref.n_words == k ** L
+    rng = np.random.default_rng(k + L)
+    ext = po.OracleExtractor(500, 1.2, 4, 20, 7)
+    _, _, real = ext(po.synth_v1(640, 200, 7))
+    sets = [rng.integers(0, 256, (n, 32), dtype=np.uint8) for n in (0, 1, 7, 500, 2000)] + [real, np.repeat(real[:5], 40, axis=0)]
+    for d in sets:
+        for levelsup in (0, 2, 4, L - 1, L, L + 2):
+            a, b = ora.transform(d, levelsup), ref.transform(d, levelsup)
+            for x, y, what in zip(a, b, ("words", "values", "nodes", "node_start", "features")):
+                assert x.tobytes() == y.tobytes(), (what, len(d), levelsup)
