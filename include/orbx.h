@@ -256,6 +256,36 @@ int orbx_batch_search_local_points(orbx_batch* b, int image, const orbx_proj_que
  * is non-NULL before the search.  orb_dist = ORBdist.  match / n_matches as for orbx_batch_search_by_projection; synchronises. */
 int orbx_batch_search_keyframe_points(orbx_batch* b, int image, const orbx_proj_query* queries, int n_queries, int check_orientation, int orb_dist,
                                       const uint8_t* taken, int* match, int* n_matches);
+/* ------------------------------------------------------------------------------------------------------------------
+ * Bag of words: Frame::ComputeBoW (Frame.cc:768-775; KeyFrame::ComputeBoW is the same call on stored descriptors)
+ *     mpORBvocabulary->transform(vCurrentDesc, mBowVec, mFeatVec, 4);
+ * = DBoW2 TemplatedVocabulary<FORB::TDescriptor, FORB>::transform(features, v, fv, levelsup)
+ * (slam_framework/Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1139-1276, FORB::distance FORB.cpp:81-100, BowVector.cpp:34-84).
+ * orbx_vocabulary = the resident ORBVocabulary (the tree, ~35 MB for ORBvoc.txt): orbx_vocabulary_load_text reads the text format
+ * of ORBvoc.txt like ORBVocabulary::loadFromTextFile (TemplatedVocabulary.h:1350-1433, called once by System's constructor);
+ * orbx_vocabulary_create takes the same tree as flat arrays (node 0 = root; parent[n] < n; is_word[n] marks the words; descriptors
+ * [n][32]; weights[n]).  Results, per image / call, bit-identical to DBoW2's containers:
+ *   BowVector     : words[0..n_words) ascending WordIds, values[] their WordValues (doubles, normalised as the scoring type asks)
+ *   FeatureVector : nodes[0..n_nodes) ascending NodeIds at level L - levelsup, features[node_start[j] .. node_start[j + 1]) the
+ *                   feature indices of nodes[j] in ascending order
+ * Per-image capacity of every array = K (orbx_batch_max_keypoints), node_start K + 1.  At most ORBX_BOW_MAX_FEATURES features per image.
+ * ---------------------------------------------------------------------------------------------------------------- */
+#define ORBX_BOW_MAX_FEATURES 8192
+typedef struct orbx_vocabulary orbx_vocabulary;
+int orbx_vocabulary_load_text(int device, const char* path, orbx_vocabulary** out);
+int orbx_vocabulary_create(int device, int k, int L, int scoring, int weighting, int n_nodes, const int* parent, const uint8_t* is_word,
+                           const uint8_t* descriptors, const double* weights, orbx_vocabulary** out);
+void orbx_vocabulary_destroy(orbx_vocabulary* v);
+int orbx_vocabulary_info(const orbx_vocabulary* v, int out[6]); /* {k, L, scoring, weighting, nodes incl. root, words} */
+/* transform() of n host descriptors [n][32] (capacity of every output array: n, node_start n + 1); synchronous */
+int orbx_vocabulary_transform(orbx_vocabulary* v, const uint8_t* descriptors, int n, int levelsup, uint32_t* words, double* values, int* n_words,
+                              uint32_t* nodes, int* node_start, uint32_t* features, int* n_nodes);
+/* transform() of the descriptors resident after orbx_batch_run, images [0, n_images); asynchronous on the handle's stream.
+ * orbx_batch_download_bow: words / nodes / features [n_images][K], values [n_images][K] doubles, node_start [n_images][K + 1],
+ * n_words / n_nodes [n_images]; any pointer may be NULL; synchronises. */
+int orbx_batch_compute_bow(orbx_batch* b, const orbx_vocabulary* v, int n_images, int levelsup);
+int orbx_batch_download_bow(orbx_batch* b, int n_images, uint32_t* words, double* values, int* n_words, uint32_t* nodes, int* node_start,
+                            uint32_t* features, int* n_nodes);
 int orbx_batch_sync(orbx_batch* b);
 /* the same on a sub-range [first, first+n) of the handle's images (lapping: n x 2 ints for that range): lets a caller keep
  * many frames resident and process them in groups small enough for the 126 MB L2 */

@@ -58,6 +58,12 @@ int cuda_fail(cudaError_t e, const char* what) {
     return ORBX_ERR_CUDA;
 }
 #define CU(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) return cuda_fail(e__, #x); } while (0)
+}  // namespace
+namespace orbx {
+int set_error(int code, const std::string& msg) { return fail(code, msg); }
+int set_cuda_error(cudaError_t e, const char* what) { return cuda_fail(e, what); }
+}  // namespace orbx
+namespace {
 
 static const signed char kPatternHost[1024] = {
 #include "orb_pattern.inc"
@@ -138,6 +144,10 @@ struct orbx_batch {
     orbx_proj_query* spDev = nullptr; int* spOut = nullptr;   // projection search: queries; match[K] + info[2]
     size_t spCap = 0;
     bool spConfigured = false;
+    // bag of words (orbx_batch_compute_bow): buffers are allocated on first use
+    uint32_t *bowLeaf = nullptr, *bowNid = nullptr;
+    BowOut bow = {};
+    int bowImages = 0;
     // extra lanes for orbx_batch_run_pipelined: chunks of a resident batch are issued round-robin over the lanes so that the
     // latency-bound stages of one chunk (quadtree) overlap the issue-bound stages of another (FAST)
     static const int kLanes = 3;
@@ -939,6 +949,55 @@ int orbx_batch_download_lapping(orbx_batch* b, int n_frames, orbx_knn2* knn, uin
     if (n_frames) {
         if (knn) CU(cudaMemcpy2DAsync(knn, K * 16, b->buf.lapKnn, 2 * K * 16, K * 16, n_frames, cudaMemcpyDeviceToHost, b->stream));
         if (ratio_ok) CU(cudaMemcpy2DAsync(ratio_ok, K, b->buf.lapOk, 2 * K, K, n_frames, cudaMemcpyDeviceToHost, b->stream));
+    }
+    CU(cudaStreamSynchronize(b->stream));
+    return ORBX_OK;
+}
+
+// Frame::ComputeBoW (Frame.cc:768-775) for images [0, n_images) on the resident descriptors; asynchronous on the handle's stream
+int orbx_batch_compute_bow(orbx_batch* b, const orbx_vocabulary* v, int n_images, int levelsup) {
+    int r = check_images(b, 0, n_images);
+    if (r) return r;
+    if (!v) return fail(ORBX_ERR_ARG, "null vocabulary");
+    if (vocabulary_device_ordinal(v) != b->device) return fail(ORBX_ERR_ARG, "the vocabulary lives on another device than the handle");
+    const int K = b->g.K;
+    if (K > ORBX_BOW_MAX_FEATURES) return fail(ORBX_ERR_TOO_LARGE, "keypoint capacity above ORBX_BOW_MAX_FEATURES");
+    DeviceGuard dg(b->device);
+    if (!b->bowLeaf) {
+        const size_t n = (size_t)b->maxImages;
+        if ((r = dev_alloc(b, &b->bow.values, n * K))) return r;
+        if ((r = dev_alloc(b, &b->bowLeaf, n * K))) return r;
+        if ((r = dev_alloc(b, &b->bowNid, n * K))) return r;
+        if ((r = dev_alloc(b, &b->bow.words, n * K))) return r;
+        if ((r = dev_alloc(b, &b->bow.nodes, n * K))) return r;
+        if ((r = dev_alloc(b, &b->bow.features, n * K))) return r;
+        if ((r = dev_alloc(b, &b->bow.nodeStart, n * ((size_t)K + 1)))) return r;
+        if ((r = dev_alloc(b, &b->bow.nWords, n))) return r;
+        if ((r = dev_alloc(b, &b->bow.nNodes, n))) return r;
+        CU(bow_configure(K));
+    }
+    b->bowImages = n_images;
+    if (n_images == 0) return ORBX_OK;
+    launch_bow(vocabulary_device(v), b->buf.desc, b->buf.outCount, 0, K, n_images, levelsup, b->bowLeaf, b->bowNid, b->bow, b->stream);
+    CU(cudaGetLastError());
+    return ORBX_OK;
+}
+
+int orbx_batch_download_bow(orbx_batch* b, int n_images, uint32_t* words, double* values, int* n_words, uint32_t* nodes, int* node_start, uint32_t* features,
+                            int* n_nodes) {
+    int r = check_images(b, 0, n_images);
+    if (r) return r;
+    if (n_images > b->bowImages) return fail(ORBX_ERR_ARG, "orbx_batch_compute_bow has not been run for these images");
+    DeviceGuard dg(b->device);
+    const size_t n = (size_t)n_images, K = (size_t)b->g.K;
+    if (n_images) {
+        if (words) CU(cudaMemcpyAsync(words, b->bow.words, n * K * 4, cudaMemcpyDeviceToHost, b->stream));
+        if (values) CU(cudaMemcpyAsync(values, b->bow.values, n * K * 8, cudaMemcpyDeviceToHost, b->stream));
+        if (n_words) CU(cudaMemcpyAsync(n_words, b->bow.nWords, n * 4, cudaMemcpyDeviceToHost, b->stream));
+        if (nodes) CU(cudaMemcpyAsync(nodes, b->bow.nodes, n * K * 4, cudaMemcpyDeviceToHost, b->stream));
+        if (node_start) CU(cudaMemcpyAsync(node_start, b->bow.nodeStart, n * (K + 1) * 4, cudaMemcpyDeviceToHost, b->stream));
+        if (features) CU(cudaMemcpyAsync(features, b->bow.features, n * K * 4, cudaMemcpyDeviceToHost, b->stream));
+        if (n_nodes) CU(cudaMemcpyAsync(n_nodes, b->bow.nNodes, n * 4, cudaMemcpyDeviceToHost, b->stream));
     }
     CU(cudaStreamSynchronize(b->stream));
     return ORBX_OK;

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <map>
 #include <mutex>
+#include <string>
 #include <utility>
 
 #include "../../include/orbx.h"
@@ -187,6 +188,29 @@ void launch_search_by_projection(const Buffers& b, int image, int K, const GridP
 
 void launch_search_local_points(const Buffers& b, int image, int K, const GridParams& p, const orbx_proj_query* queries, int nq, int useURight, int thHigh, float nnRatio,
                                 const uint8_t* taken0, int candCap, int stageDesc, int* outMatch, int* outInfo, cudaStream_t s);
+
+// DBoW2 vocabulary transform (bow_kernel.cu): the tree by node id (0 = root); children of node n = childList[childStart[n] .. childStart[n + 1])
+struct BowVocDev {
+    int k, L, scoring, weighting;
+    const uint4* desc;        // [nodes][2]
+    const int* childStart;    // [nodes + 1]
+    const int* childList;     // [nodes - 1]
+    const double* weight;     // [nodes]
+    const int* wordId;        // [nodes]
+};
+struct BowOut {               // per image: capacity K entries each (nodeStart: K + 1)
+    uint32_t* words; double* values; int* nWords;
+    uint32_t* nodes; int* nodeStart; uint32_t* features; int* nNodes;
+};
+int bow_sort_size(int K);
+cudaError_t bow_configure(int K);
+void launch_bow(const BowVocDev& v, const uint8_t* desc, const int* counts, int fixedCount, int K, int nImages, int levelsup, uint32_t* leaf, uint32_t* nid,
+                const BowOut& out, cudaStream_t s);
+const BowVocDev& vocabulary_device(const orbx_vocabulary* v);
+int vocabulary_device_ordinal(const orbx_vocabulary* v);
+// error reporting shared by the translation units that hold C-ABI entry points (thread-local message behind orbx_last_error)
+int set_error(int code, const std::string& msg);
+int set_cuda_error(cudaError_t e, const char* what);
 
 // debug / test hooks
 void launch_debug_sincos(const float* anglesDeg, float* outSin, float* outCos, int n, cudaStream_t s);

@@ -115,6 +115,13 @@ def lib():
         "orbx_batch_debug_candidates": (i, [_vp, i, i, _vp, i, _vp]),
         "orbx_batch_debug_selected": (i, [_vp, i, i, _vp, i, _vp]),
         "orbx_batch_debug_fallback_cells": (i, [_vp, i, i, _vp]),
+        "orbx_vocabulary_load_text": (i, [i, C.c_char_p, C.POINTER(_vp)]),
+        "orbx_vocabulary_create": (i, [i, i, i, i, i, i, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
+        "orbx_vocabulary_destroy": (None, [_vp]),
+        "orbx_vocabulary_info": (i, [_vp, _vp]),
+        "orbx_vocabulary_transform": (i, [_vp, _vp, i, i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+        "orbx_batch_compute_bow": (i, [_vp, _vp, i, i]),
+        "orbx_batch_download_bow": (i, [_vp, i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
         "orbx_pool_create": (i, [i, f, i, i, i, _vp, i, i, i, i, i, C.POINTER(_vp)]),
         "orbx_pool_destroy": (None, [_vp]),
         "orbx_pool_max_keypoints": (i, [_vp]),
@@ -665,6 +672,18 @@ class BatchExtractor:
                                                     _p(t) if t is not None else None, _p(match), C.byref(nm)))
         return match, nm.value
 
+    def compute_bow(self, vocabulary, n_images, levelsup=4):
+        """Batched Frame::ComputeBoW (Frame.cc:768-775) on the resident descriptors (after run()); asynchronous."""
+        _check(lib().orbx_batch_compute_bow(self._h, vocabulary._h, int(n_images), int(levelsup)))
+
+    def download_bow(self, n_images):
+        """Per image i: (words[:nw], values[:nw], nodes[:nn], node_start[:nn + 1], features[:node_start[nn]]) as ORBVocabulary.transform returns them."""
+        n, K = int(n_images), self.K
+        words, values, nw = np.empty((n, K), np.uint32), np.empty((n, K), np.float64), np.empty(n, np.int32)
+        nodes, start, feats, nn = np.empty((n, K), np.uint32), np.empty((n, K + 1), np.int32), np.empty((n, K), np.uint32), np.empty(n, np.int32)
+        _check(lib().orbx_batch_download_bow(self._h, n, _p(words), _p(values), _p(nw), _p(nodes), _p(start), _p(feats), _p(nn)))
+        return [(words[i, :nw[i]], values[i, :nw[i]], nodes[i, :nn[i]], start[i, :nn[i] + 1], feats[i, :start[i, nn[i]]]) for i in range(n)]
+
     def sync(self):
         _check(lib().orbx_batch_sync(self._h))
 
@@ -744,6 +763,62 @@ class BatchExtractor:
     @property
     def kernel_launches(self):
         return lib().orbx_batch_kernel_launches(self._h)
+
+
+class ORBVocabulary:
+    """The resident DBoW2 vocabulary (ORBVocabulary = TemplatedVocabulary<FORB::TDescriptor, FORB>, slam_framework/include/ORBVocabulary.h):
+    `loadFromTextFile` reads ORBvoc.txt's format (TemplatedVocabulary.h:1350-1433), `transform` is
+    transform(features, BowVector, FeatureVector, levelsup) (TemplatedVocabulary.h:1139-1214) for host descriptors; resident
+    descriptors go through BatchExtractor.compute_bow."""
+
+    def __init__(self, device=0):
+        self.device, self._h = int(device), None
+
+    def _adopt(self, h):
+        self.close()
+        self._h = h
+        info = np.zeros(6, np.int32)
+        _check(lib().orbx_vocabulary_info(self._h, _p(info)))
+        self.k, self.L, self.scoring, self.weighting, self.n_nodes, self.n_words = (int(v) for v in info)
+
+    def loadFromTextFile(self, path):
+        h = _vp()
+        _check(lib().orbx_vocabulary_load_text(self.device, os.fsencode(path), C.byref(h)))
+        self._adopt(h)
+        return True
+
+    def from_arrays(self, k, L, scoring, weighting, parent, is_word, descriptors, weights):
+        parent, is_word = np.ascontiguousarray(parent, np.int32), np.ascontiguousarray(is_word, np.uint8)
+        descriptors, weights = np.ascontiguousarray(descriptors, np.uint8), np.ascontiguousarray(weights, np.float64)
+        h = _vp()
+        _check(lib().orbx_vocabulary_create(self.device, int(k), int(L), int(scoring), int(weighting), len(parent), _p(parent), _p(is_word), _p(descriptors),
+                                            _p(weights), C.byref(h)))
+        self._adopt(h)
+        return self
+
+    def size(self):
+        return self.n_words
+
+    def transform(self, descriptors, levelsup=4):
+        """descriptors [n, 32] uint8 -> (words ascending, values, nodes ascending, node_start [nodes + 1], features)"""
+        d = np.ascontiguousarray(descriptors, np.uint8).reshape(-1, 32)
+        n = len(d)
+        words, values = np.empty(max(n, 1), np.uint32), np.empty(max(n, 1), np.float64)
+        nodes, start, feats = np.empty(max(n, 1), np.uint32), np.zeros(n + 1, np.int32), np.empty(max(n, 1), np.uint32)
+        nw, nn = C.c_int(), C.c_int()
+        _check(lib().orbx_vocabulary_transform(self._h, _p(d), n, int(levelsup), _p(words), _p(values), C.byref(nw), _p(nodes), _p(start), _p(feats), C.byref(nn)))
+        return words[:nw.value], values[:nw.value], nodes[:nn.value], start[:nn.value + 1], feats[:start[nn.value]]
+
+    def close(self):
+        if self._h:
+            lib().orbx_vocabulary_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class ExtractorPool:
