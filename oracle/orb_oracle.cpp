@@ -956,6 +956,120 @@ int search_local_points(const KeyPoint* kps, int nKps, const uint8_t* desc, cons
 
 
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The two-grid (fisheye stereo, Frame::Nleft != -1) branches of both searches.  The frame is a left and a right image with one grid
+// each (Frame::mGrid / mGridRight, Frame.cc:428-441), mvpMapPoints holds N = Nleft + Nright entries (left keypoints first), the
+// right-coordinate gate does not apply (Nleft == -1 is false, ORBmatcher.cc:99, :1760).  A map point becomes up to two sub-queries in
+// a row, told apart by side[i]: 0 = its search in the left image, 1 = its search in the right image after a left one ("paired"),
+// 2 = a right-image search of a point that has no left part (local map: mbTrackInViewR without mbTrackInView).
+// Frame to frame (ORBmatcher.cc:1729-1868): the left part as in the single-grid case; `if(vIndices2.empty()) continue;` (:1744-1745)
+// also skips the right part of that point; the right part (:1803-1866) walks mGridRight with (u, v) of the point re-projected into the
+// right camera (the caller's pose algebra), writes mvpMapPoints[bestIdx2 + Nleft] and votes in the same rotation histogram with
+// mvKeysRight[bestIdx2].angle.
+// Local map (ORBmatcher.cc:72-219): the ratio-test `continue` of the left part (:133-134) skips the right part too; an accepted left
+// match also takes the right keypoint mvLeftToRightMatch[bestIdx] (+1 match, :139-143), an accepted right match the left keypoint
+// mvRightToLeftMatch[bestIdx] (:205-209).
+// matchL / matchR[k] = index of the SUB-QUERY whose point the keypoint ends up with (-1 = none / untouched).
+// ---------------------------------------------------------------------------------------------------------------------
+struct StereoSide {
+    const KeyPoint* kps; int n; const uint8_t* desc; const int* cellStart; const int* items; int* match; std::vector<char> taken;
+};
+
+int search_by_projection_tail_stereo(StereoSide& L, StereoSide& R, float minX, float maxX, float minY, float maxY, const ProjQuery* q, const uint8_t* side, int nq,
+                                     int checkOrientation, int thHigh) {
+    constexpr int HISTO_LENGTH = 30;
+    std::vector<std::pair<int, int>> rotHist[HISTO_LENGTH];   // (side, keypoint)
+    const float factor = 1.0f / HISTO_LENGTH;
+    std::vector<int> cand((size_t)std::max(std::max(L.n, R.n), 1));
+    for (StereoSide* S : {&L, &R}) { S->taken.assign((size_t)std::max(S->n, 1), 0); for (int k = 0; k < S->n; ++k) S->match[k] = -1; }
+    int nmatches = 0;
+    bool skipRight = false;
+    for (int i = 0; i < nq; ++i) {
+        const ProjQuery& Q = q[i];
+        const int sd = side[i];
+        if (sd == 0) skipRight = false;
+        else if (sd == 1 && skipRight) continue;
+        StereoSide& S = sd == 0 ? L : R;
+        const int nc = features_in_area(S.kps, S.cellStart, S.items, minX, maxX, minY, maxY, Q.u, Q.v, Q.radius, Q.minLevel, Q.maxLevel, cand.data(), S.n);
+        if (nc == 0) { if (sd == 0) skipRight = true; continue; }
+        int bestDist = 256, bestIdx2 = -1;
+        for (int c = 0; c < nc; ++c) {
+            const int i2 = cand[c];
+            if (S.taken[i2]) continue;
+            const int dist = hamming256(Q.desc, S.desc + (size_t)i2 * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+        }
+        if (bestDist <= thHigh) {
+            S.match[bestIdx2] = i;
+            S.taken[bestIdx2] = Q.blocks != 0;
+            ++nmatches;
+            if (checkOrientation) {
+                float rot = Q.angle - S.kps[bestIdx2].angle;
+                if (rot < 0.0) rot += 360.0f;
+                int bin = (int)std::round(rot * factor);
+                if (bin == HISTO_LENGTH) bin = 0;
+                rotHist[bin].push_back(std::make_pair(sd == 0 ? 0 : 1, bestIdx2));
+            }
+        }
+    }
+    if (checkOrientation) {
+        int ind1 = -1, ind2 = -1, ind3 = -1, max1 = 0, max2 = 0, max3 = 0;
+        for (int i = 0; i < HISTO_LENGTH; ++i) {  // ORBmatcher::ComputeThreeMaxima
+            const int sz = (int)rotHist[i].size();
+            if (sz > max1) { max3 = max2; max2 = max1; max1 = sz; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (sz > max2) { max3 = max2; max2 = sz; ind3 = ind2; ind2 = i; }
+            else if (sz > max3) { max3 = sz; ind3 = i; }
+        }
+        if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+        else if (max3 < 0.1f * (float)max1) ind3 = -1;
+        for (int i = 0; i < HISTO_LENGTH; ++i)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (auto& e : rotHist[i]) { (e.first ? R : L).match[e.second] = -1; --nmatches; }
+    }
+    return nmatches;
+}
+
+int search_local_points_stereo(StereoSide& L, StereoSide& R, const uint8_t* takenL0, const uint8_t* takenR0, const int* leftToRight, const int* rightToLeft, float minX,
+                               float maxX, float minY, float maxY, const ProjQuery* q, const uint8_t* side, int nq, float nnRatio, int thHigh) {
+    std::vector<int> cand((size_t)std::max(std::max(L.n, R.n), 1));
+    L.taken.assign((size_t)std::max(L.n, 1), 0); R.taken.assign((size_t)std::max(R.n, 1), 0);
+    for (int k = 0; k < L.n; ++k) { L.match[k] = -1; L.taken[k] = takenL0 ? (takenL0[k] != 0) : 0; }
+    for (int k = 0; k < R.n; ++k) { R.match[k] = -1; R.taken[k] = takenR0 ? (takenR0[k] != 0) : 0; }
+    int nmatches = 0;
+    bool skipRight = false;
+    for (int i = 0; i < nq; ++i) {
+        const ProjQuery& Q = q[i];
+        const int sd = side[i];
+        if (sd == 0) skipRight = false;
+        else if (sd == 1 && skipRight) continue;
+        StereoSide& S = sd == 0 ? L : R;
+        StereoSide& O = sd == 0 ? R : L;
+        const int nc = features_in_area(S.kps, S.cellStart, S.items, minX, maxX, minY, maxY, Q.u, Q.v, Q.radius, Q.minLevel, Q.maxLevel, cand.data(), S.n);
+        if (nc == 0) continue;
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        for (int c = 0; c < nc; ++c) {
+            const int idx = cand[c];
+            if (S.taken[idx]) continue;
+            const int dist = hamming256(Q.desc, S.desc + (size_t)idx * 32);
+            if (dist < bestDist) {
+                bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = S.kps[idx].octave; bestIdx = idx;
+            } else if (dist < bestDist2) {
+                bestLevel2 = S.kps[idx].octave; bestDist2 = dist;
+            }
+        }
+        if (bestDist <= thHigh) {
+            if (bestLevel == bestLevel2 && (float)bestDist > nnRatio * (float)bestDist2) { if (sd == 0) skipRight = true; continue; }
+            const int partner = (sd == 0 ? leftToRight : rightToLeft) ? (sd == 0 ? leftToRight : rightToLeft)[bestIdx] : -1;
+            if (partner != -1) { O.match[partner] = i; O.taken[partner] = Q.blocks != 0; ++nmatches; }
+            S.match[bestIdx] = i;
+            S.taken[bestIdx] = Q.blocks != 0;
+            ++nmatches;
+        }
+    }
+    return nmatches;
+}
+
+
 // ------------------------------------------------------------------------------------------------------------------
 // DBoW2 vocabulary: what Frame::ComputeBoW (Frame.cc:768-775) runs on the descriptors the extractor produced.  Restated from the
 // vendored library (slam_framework/Thirdparty/DBoW2/DBoW2): the text loader the reference uses for ORBvoc.txt
@@ -1126,6 +1240,19 @@ void orbo_remap(const uint8_t* src, int sw, int sh, int sstride, int channels, c
     remap_linear_8u(src, sw, sh, (size_t)sstride, channels, mapx, mapy, (size_t)mstride, dst, dw, dh, (size_t)dstride);
 }
 // primitives, for direct checks against cv2
+int orbo_search_by_projection_stereo(const void* kpsL, int nL, const uint8_t* descL, const int* startL, const int* itemsL, const void* kpsR, int nR, const uint8_t* descR,
+                                     const int* startR, const int* itemsR, float minX, float maxX, float minY, float maxY, const void* q, const uint8_t* side, int nq,
+                                     int checkOrientation, int thHigh, int* matchL, int* matchR) {
+    StereoSide L{(const KeyPoint*)kpsL, nL, descL, startL, itemsL, matchL, {}}, R{(const KeyPoint*)kpsR, nR, descR, startR, itemsR, matchR, {}};
+    return search_by_projection_tail_stereo(L, R, minX, maxX, minY, maxY, (const ProjQuery*)q, side, nq, checkOrientation, thHigh);
+}
+int orbo_search_local_points_stereo(const void* kpsL, int nL, const uint8_t* descL, const uint8_t* takenL0, const int* startL, const int* itemsL, const int* leftToRight,
+                                    const void* kpsR, int nR, const uint8_t* descR, const uint8_t* takenR0, const int* startR, const int* itemsR, const int* rightToLeft,
+                                    float minX, float maxX, float minY, float maxY, const void* q, const uint8_t* side, int nq, float nnRatio, int thHigh, int* matchL,
+                                    int* matchR) {
+    StereoSide L{(const KeyPoint*)kpsL, nL, descL, startL, itemsL, matchL, {}}, R{(const KeyPoint*)kpsR, nR, descR, startR, itemsR, matchR, {}};
+    return search_local_points_stereo(L, R, takenL0, takenR0, leftToRight, rightToLeft, minX, maxX, minY, maxY, (const ProjQuery*)q, side, nq, nnRatio, thHigh);
+}
 // vocabulary (DBoW2) -------------------------------------------------------------------------------------------------
 void* orbo_voc_load_text(const char* path) {
     Vocabulary* v = new Vocabulary();

@@ -50,6 +50,9 @@ def lib():
         L.orbo_stereo_match.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
         L.orbo_assign_grid.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
         L.orbo_features_in_area.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_float] * 7 + [C.c_int, C.c_int, C.c_void_p, C.c_int]
+        vp, ci, cf = C.c_void_p, C.c_int, C.c_float
+        L.orbo_search_by_projection_stereo.argtypes = [vp, ci, vp, vp, vp, vp, ci, vp, vp, vp, cf, cf, cf, cf, vp, vp, ci, ci, ci, vp, vp]
+        L.orbo_search_local_points_stereo.argtypes = [vp, ci, vp, vp, vp, vp, vp, vp, ci, vp, vp, vp, vp, vp, cf, cf, cf, cf, vp, vp, ci, cf, ci, vp, vp]
         L.orbo_search_by_projection.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_float] * 4 + [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.orbo_search_local_points.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_float] * 4 + [C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p]
         L.orbo_lapping_match.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -269,6 +272,91 @@ def search_local_points(kps, desc, uright, taken0, grid, bounds, queries, nn_rat
     nm = lib().orbo_search_local_points(_p(kps), len(kps), _p(desc), None if ur is None else _p(ur), None if t0 is None else _p(t0), _p(start), _p(items),
                                         *[float(v) for v in bounds], _p(q), len(q), float(nn_ratio), int(th_high), _p(match))
     return match[:len(kps)], nm
+
+
+def make_proj_queries_stereo(points, octaves, nobs, point_desc, scale_factors, th, mode, dx_r, dy_r):
+    """Two sub-queries per projected map point for a two-grid current frame (ORBmatcher.cc:1729-1868): its window in the left image (side 0) and,
+    paired with it (side 1), the window around its projection into the right camera, here (u + dx_r, v + dy_r) in float32.  Returns (queries, side, owner)."""
+    pts = np.ascontiguousarray(points, np.float32).reshape(-1, 4)
+    n = len(pts)
+    base = make_proj_queries(pts, octaves, nobs, point_desc, scale_factors, th, 0.0, mode)
+    q = np.zeros(2 * n, PROJ_QUERY_DTYPE)
+    q[0::2] = base
+    q[1::2] = base
+    q["u"][1::2] = pts[:, 0] + np.float32(dx_r)
+    q["v"][1::2] = pts[:, 1] + np.float32(dy_r)
+    q["ur"] = 0
+    side = np.zeros(2 * n, np.uint8)
+    side[1::2] = 1
+    return q, side, np.repeat(np.arange(n, dtype=np.int32), 2)
+
+
+def make_local_queries_stereo(points, levels, levels_r, nobs, flags, point_desc, scale_factors, th, far_points=False, th_far=50.0):
+    """Sub-queries of the two-grid local-map search (ORBmatcher.cc:58-81, :154-163).  points: float32 [nq, 7] = (mTrackProjX, mTrackProjY, mTrackViewCos,
+    mTrackDepth, mTrackProjXR, mTrackProjYR, mTrackViewCosR); flags bit 0 = mbTrackInView, bit 1 = isBad(), bit 2 = mbTrackInViewR.  Returns (queries, side, owner)."""
+    pts = np.ascontiguousarray(points, np.float32).reshape(-1, 7)
+    lv, lvr, fl = np.ascontiguousarray(levels, np.int32), np.ascontiguousarray(levels_r, np.int32), np.ascontiguousarray(flags, np.int32)
+    nob = np.ascontiguousarray(nobs, np.int32)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    pd = np.ascontiguousarray(point_desc, np.uint8).reshape(-1, 32)
+    rows, side, owner = [], [], []
+    for i in range(len(pts)):
+        in_l, in_r = bool(fl[i] & 1), bool(fl[i] & 4)
+        if not in_l and not in_r:
+            continue
+        if far_points and pts[i, 3] > np.float32(th_far):
+            continue
+        if fl[i] & 2:
+            continue
+        if in_l:
+            r = np.float32(2.5) if pts[i, 2] > 0.998 else np.float32(4.0)
+            if th != 1.0:
+                r = r * np.float32(th)
+            rows.append((pts[i, 0], pts[i, 1], r * sf[lv[i]], 0.0, lv[i] - 1, lv[i], 0.0, int(nob[i] > 0), pd[i]))
+            side.append(0)
+            owner.append(i)
+        if in_r and lvr[i] != -1:
+            r = np.float32(2.5) if pts[i, 6] > 0.998 else np.float32(4.0)
+            rows.append((pts[i, 4], pts[i, 5], r * sf[lvr[i]], 0.0, lvr[i] - 1, lvr[i], 0.0, int(nob[i] > 0), pd[i]))
+            side.append(1 if in_l else 2)
+            owner.append(i)
+    q = np.zeros(len(rows), PROJ_QUERY_DTYPE)
+    for j, row in enumerate(rows):
+        q[j] = row
+    return q, np.array(side, np.uint8), np.array(owner, np.int32)
+
+
+def _side_args(kps, desc, grid):
+    kps = np.ascontiguousarray(kps)
+    return kps, np.ascontiguousarray(desc, np.uint8), np.ascontiguousarray(grid[0], np.int32), np.ascontiguousarray(grid[1], np.int32)
+
+
+def search_by_projection_stereo(left, right, bounds, queries, side, check_orientation=True, th_high=100):
+    """Two-grid frame-to-frame search (see orb_oracle.cpp).  left / right = (kps, desc, grid).  Returns (match_left, match_right, nmatches): sub-query indices."""
+    kl, dl, sl, il = _side_args(*left)
+    kr, dr, sr, ir = _side_args(*right)
+    q, sd = np.ascontiguousarray(queries, PROJ_QUERY_DTYPE), np.ascontiguousarray(side, np.uint8)
+    ml, mr = np.empty(max(len(kl), 1), np.int32), np.empty(max(len(kr), 1), np.int32)
+    nm = lib().orbo_search_by_projection_stereo(_p(kl), len(kl), _p(dl), _p(sl), _p(il), _p(kr), len(kr), _p(dr), _p(sr), _p(ir), *[float(v) for v in bounds], _p(q), _p(sd),
+                                                len(q), int(bool(check_orientation)), int(th_high), _p(ml), _p(mr))
+    return ml[:len(kl)], mr[:len(kr)], nm
+
+
+def search_local_points_stereo(left, right, taken_l, taken_r, l2r, r2l, bounds, queries, side, nn_ratio=0.8, th_high=100):
+    """Two-grid local-map search (see orb_oracle.cpp).  left / right = (kps, desc, grid); taken_* = keypoints holding a point WITH observations before the
+    search (or None); l2r / r2l = Frame::mvLeftToRightMatch / mvRightToLeftMatch (or None)."""
+    kl, dl, sl, il = _side_args(*left)
+    kr, dr, sr, ir = _side_args(*right)
+    q, sd = np.ascontiguousarray(queries, PROJ_QUERY_DTYPE), np.ascontiguousarray(side, np.uint8)
+    tl = None if taken_l is None else np.ascontiguousarray(np.asarray(taken_l) != 0, np.uint8)
+    tr = None if taken_r is None else np.ascontiguousarray(np.asarray(taken_r) != 0, np.uint8)
+    a = None if l2r is None else np.ascontiguousarray(l2r, np.int32)
+    b = None if r2l is None else np.ascontiguousarray(r2l, np.int32)
+    o = lambda x: None if x is None else _p(x)
+    ml, mr = np.empty(max(len(kl), 1), np.int32), np.empty(max(len(kr), 1), np.int32)
+    nm = lib().orbo_search_local_points_stereo(_p(kl), len(kl), _p(dl), o(tl), _p(sl), _p(il), o(a), _p(kr), len(kr), _p(dr), o(tr), _p(sr), _p(ir), o(b),
+                                               *[float(v) for v in bounds], _p(q), _p(sd), len(q), float(nn_ratio), int(th_high), _p(ml), _p(mr))
+    return ml[:len(kl)], mr[:len(kr)], nm
 
 
 class OracleExtractor:

@@ -247,6 +247,56 @@ def search_keyframe_points(kps, desc, taken0, bounds, scale_factors, points, lev
     return match[:len(kps)], nm
 
 
+def _search_lib():
+    global _splib
+    if _splib is None:
+        _splib = C.CDLL(_LIB_SEARCH)
+        _splib.refsp_search.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p] + [C.c_float] * 4 + [C.c_void_p, C.c_int, C.c_float, C.c_float,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p]
+    return _splib
+
+
+def search_by_projection_stereo(kps_l, kps_r, desc_lr, bounds, scale_factors, mb, mbf, points, octaves, nobs, point_desc, th, tlcz, dx_r, dy_r, check_orientation=True):
+    """The reference's own ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, false) with a TWO-GRID current frame (Nleft = len(kps_l)): the
+    right camera sees a point at (u + dx_r, v + dy_r).  Returns (match int32 [nL + nR]: map-point index or -1, nmatches)."""
+    L = _search_lib()
+    L.refsp_search_stereo.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p] + [C.c_float] * 4 + [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_void_p]
+    kl, kr = np.ascontiguousarray(kps_l), np.ascontiguousarray(kps_r)
+    d = np.ascontiguousarray(desc_lr, np.uint8)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    pts = np.ascontiguousarray(points, np.float32).reshape(-1, 4)
+    octv, nob = np.ascontiguousarray(octaves, np.int32), np.ascontiguousarray(nobs, np.int32)
+    pd = np.ascontiguousarray(point_desc, np.uint8).reshape(-1, 32)
+    match = np.empty(max(len(kl) + len(kr), 1), np.int32)
+    nm = L.refsp_search_stereo(_p(kl), len(kl), _p(kr), len(kr), _p(d), *[float(v) for v in bounds], _p(sf), len(sf), float(mb), float(mbf), _p(pts), _p(octv), _p(nob),
+                               _p(pd), len(pts), float(th), float(tlcz), float(dx_r), float(dy_r), int(bool(check_orientation)), _p(match))
+    return match[:len(kl) + len(kr)], nm
+
+
+def search_local_points_stereo(kps_l, kps_r, desc_lr, taken0, l2r, r2l, bounds, scale_factors, points, levels, levels_r, nobs, flags, point_desc, th, nn_ratio,
+                               far_points=False, th_far=50.0):
+    """The reference's own ORBmatcher::SearchByProjection(F, vpMapPoints, ...) with a TWO-GRID frame.  points: float32 [nq, 7] = (mTrackProjX, mTrackProjY,
+    mTrackViewCos, mTrackDepth, mTrackProjXR, mTrackProjYR, mTrackViewCosR); flags bit 0 = mbTrackInView, bit 1 = isBad(), bit 2 = mbTrackInViewR."""
+    L = _search_lib()
+    L.refsp_search_local_stereo.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_float] * 4 + [C.c_void_p,
+                                           C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int,
+                                           C.c_float, C.c_void_p]
+    kl, kr = np.ascontiguousarray(kps_l), np.ascontiguousarray(kps_r)
+    d = np.ascontiguousarray(desc_lr, np.uint8)
+    t0 = np.ascontiguousarray(taken0, np.uint8)
+    a, b = np.ascontiguousarray(l2r, np.int32), np.ascontiguousarray(r2l, np.int32)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    pts = np.ascontiguousarray(points, np.float32).reshape(-1, 7)
+    lv, lvr = np.ascontiguousarray(levels, np.int32), np.ascontiguousarray(levels_r, np.int32)
+    nob, fl = np.ascontiguousarray(nobs, np.int32), np.ascontiguousarray(flags, np.int32)
+    pd = np.ascontiguousarray(point_desc, np.uint8).reshape(-1, 32)
+    match = np.empty(max(len(kl) + len(kr), 1), np.int32)
+    nm = L.refsp_search_local_stereo(_p(kl), len(kl), _p(kr), len(kr), _p(d), _p(t0), _p(a), _p(b), *[float(v) for v in bounds], _p(sf), len(sf), _p(pts), _p(lv), _p(lvr),
+                                     _p(nob), _p(fl), _p(pd), len(pts), float(th), float(nn_ratio), int(bool(far_points)), float(th_far), _p(match))
+    return match[:len(kl) + len(kr)], nm
+
+
 class RefVocabulary:
     """The reference's OWN DBoW2 (oracle/_ref/libref_bow.so, oracle/ref_bow_capi.cpp): loadFromTextFile + transform."""
     _LIB = os.path.join(_HERE, "_ref", "libref_bow.so")

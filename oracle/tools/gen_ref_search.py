@@ -56,11 +56,11 @@ struct Vector2f { float d[2]; float operator()(int i) const { return d[i]; } };
 }
 namespace Sophus {  // stand-in: `T * x` is the identity, or a constant for the last-frame pose (-> tlc)
 struct SE3f {
-    bool constant = false;
+    bool constant = false, offset = false;   // offset: T * p = p + t (the right camera's view of a point in the two-grid tests)
     Eigen::Vector3f t = {{0.f, 0.f, 0.f}};
     SE3f inverse() const { return *this; }
     Eigen::Vector3f translation() const { return t; }
-    Eigen::Vector3f operator*(const Eigen::Vector3f& p) const { return constant ? t : p; }
+    Eigen::Vector3f operator*(const Eigen::Vector3f& p) const { return constant ? t : offset ? Eigen::Vector3f{{p(0) + t(0), p(1) + t(1), p(2) + t(2)}} : p; }
 };
 }
 namespace TC2LI_SLAM {
@@ -92,7 +92,8 @@ struct Frame {
     GeometricCamera* mpCamera;
     Sophus::SE3f mTcw;
     Sophus::SE3f GetPose() const { return mTcw; }
-    Sophus::SE3f GetRelativePoseTrl() { return Sophus::SE3f(); }
+    Sophus::SE3f mTrl;
+    Sophus::SE3f GetRelativePoseTrl() { return mTrl; }
     static float mfGridElementWidthInv, mfGridElementHeightInv;
     static float mnMinX, mnMaxX, mnMinY, mnMaxY;
     std::vector<std::size_t> mGrid[FRAME_GRID_COLS][FRAME_GRID_ROWS];
@@ -242,6 +243,85 @@ extern "C" int refsp_search_kf(const void* kps, int n, const unsigned char* desc
     for (int k = 0; k < n; ++k) {
         MapPoint* p = cur.mvpMapPoints[k];
         match[k] = (p && p != &held) ? (int)(p - pts.data()) : -1;
+    }
+    return nm;
+}
+'''
+    glue_bottom += r'''
+// ---- two-grid (Nleft != -1) variants: left keypoints [nL], right keypoints [nR], descLR = the vconcat of both descriptor matrices ----
+static void two_grid_frame(Frame& F, const void* kpsL, int nL, const void* kpsR, int nR, const unsigned char* descLR, float minX, float maxX, float minY, float maxY,
+                           const float* scaleFactors, int nlevels) {
+    F.Nleft = nL; F.N = nL + nR;
+    F.mvKeys.assign((const cv::KeyPoint*)kpsL, (const cv::KeyPoint*)kpsL + nL);
+    F.mvKeysRight.assign((const cv::KeyPoint*)kpsR, (const cv::KeyPoint*)kpsR + nR);
+    F.mvuRight.assign(F.N, -1.f);
+    F.mvScaleFactors.assign(scaleFactors, scaleFactors + nlevels);
+    F.mDescriptors = cv::Mat(F.N, 32, CV_8U, (void*)descLR, 32);
+    Frame::mnMinX = minX; Frame::mnMaxX = maxX; Frame::mnMinY = minY; Frame::mnMaxY = maxY;
+    Frame::mfGridElementWidthInv = static_cast<float>(FRAME_GRID_COLS) / (Frame::mnMaxX - Frame::mnMinX);
+    Frame::mfGridElementHeightInv = static_cast<float>(FRAME_GRID_ROWS) / (Frame::mnMaxY - Frame::mnMinY);
+    F.AssignFeaturesToGrid();
+}
+// frame to frame: the right camera sees a point at (u + dxR, v + dyR) (GetRelativePoseTrl stand-in = that offset); match[N]: left entries first
+extern "C" int refsp_search_stereo(const void* kpsL, int nL, const void* kpsR, int nR, const unsigned char* descLR, float minX, float maxX, float minY, float maxY,
+                                   const float* scaleFactors, int nlevels, float mb, float mbf, const float* points, const int* octaves, const int* nobs,
+                                   const unsigned char* pdesc, int nq, float th, float tlcz, float dxR, float dyR, int checkOrientation, int* match) {
+    Frame cur, last;
+    GeometricCamera cam;
+    two_grid_frame(cur, kpsL, nL, kpsR, nR, descLR, minX, maxX, minY, maxY, scaleFactors, nlevels);
+    cur.mvpMapPoints.assign(cur.N, nullptr);
+    cur.mb = mb; cur.mbf = mbf; cur.mpCamera = &cam;
+    cur.mTrl.offset = true; cur.mTrl.t = Eigen::Vector3f{{dxR, dyR, 0.f}};
+    std::vector<MapPoint> pts(nq);
+    last.N = nq; last.Nleft = -1;
+    last.mvKeys.resize(nq); last.mvKeysUn.resize(nq);
+    last.mvpMapPoints.resize(nq); last.mvbOutlier.assign(nq, false);
+    last.mTcw.constant = true; last.mTcw.t = Eigen::Vector3f{{0.f, 0.f, tlcz}};
+    for (int i = 0; i < nq; ++i) {
+        pts[i].pos = Eigen::Vector3f{{points[4 * i], points[4 * i + 1], points[4 * i + 2]}};
+        pts[i].desc = cv::Mat(1, 32, CV_8U, (void*)(pdesc + 32 * (size_t)i), 32);
+        pts[i].nObs = nobs[i];
+        last.mvpMapPoints[i] = &pts[i];
+        last.mvKeys[i].octave = octaves[i]; last.mvKeysUn[i].octave = octaves[i];
+        last.mvKeys[i].angle = points[4 * i + 3]; last.mvKeysUn[i].angle = points[4 * i + 3];
+    }
+    ORBmatcher m;
+    m.mfNNratio = 0.9f; m.mbCheckOrientation = checkOrientation != 0;
+    const int nm = m.SearchByProjection(cur, last, th, false);
+    for (int k = 0; k < cur.N; ++k) match[k] = cur.mvpMapPoints[k] ? (int)(cur.mvpMapPoints[k] - pts.data()) : -1;
+    return nm;
+}
+// local map: points nq x {mTrackProjX, mTrackProjY, mTrackViewCos, mTrackDepth, mTrackProjXR, mTrackProjYR, mTrackViewCosR}; levels / levelsR (-1 = none);
+// flags bit 0 = mbTrackInView, bit 1 = isBad(), bit 2 = mbTrackInViewR; taken0[N] as in refsp_search_local; l2r[nL] / r2l[nR] = mvLeftToRightMatch / mvRightToLeftMatch
+extern "C" int refsp_search_local_stereo(const void* kpsL, int nL, const void* kpsR, int nR, const unsigned char* descLR, const unsigned char* taken0, const int* l2r,
+                                         const int* r2l, float minX, float maxX, float minY, float maxY, const float* scaleFactors, int nlevels, const float* points,
+                                         const int* levels, const int* levelsR, const int* nobs, const int* flags, const unsigned char* pdesc, int nq, float th,
+                                         float nnRatio, int bFarPoints, float thFarPoints, int* match) {
+    Frame F;
+    two_grid_frame(F, kpsL, nL, kpsR, nR, descLR, minX, maxX, minY, maxY, scaleFactors, nlevels);
+    F.mvLeftToRightMatch.assign(l2r, l2r + nL);
+    F.mvRightToLeftMatch.assign(r2l, r2l + nR);
+    MapPoint held, heldFree;
+    held.nObs = 1; heldFree.nObs = 0;
+    F.mvpMapPoints.assign(F.N, nullptr);
+    for (int k = 0; k < F.N; ++k) if (taken0[k]) F.mvpMapPoints[k] = taken0[k] == 1 ? &held : &heldFree;
+    std::vector<MapPoint> pts(nq);
+    std::vector<MapPoint*> vp(nq);
+    for (int i = 0; i < nq; ++i) {
+        MapPoint& P = pts[i];
+        const float* p = points + 7 * (size_t)i;
+        P.mTrackProjX = p[0]; P.mTrackProjY = p[1]; P.mTrackViewCos = p[2]; P.mTrackDepth = p[3]; P.mTrackProjXR = p[4]; P.mTrackProjYR = p[5]; P.mTrackViewCosR = p[6];
+        P.mnTrackScaleLevel = levels[i]; P.mnTrackScaleLevelR = levelsR[i]; P.nObs = nobs[i];
+        P.mbTrackInView = (flags[i] & 1) != 0; P.bad = (flags[i] & 2) != 0; P.mbTrackInViewR = (flags[i] & 4) != 0;
+        P.desc = cv::Mat(1, 32, CV_8U, (void*)(pdesc + 32 * (size_t)i), 32);
+        vp[i] = &P;
+    }
+    ORBmatcher m;
+    m.mfNNratio = nnRatio; m.mbCheckOrientation = true;
+    const int nm = m.SearchByProjection(F, vp, th, bFarPoints != 0, thFarPoints);
+    for (int k = 0; k < F.N; ++k) {
+        MapPoint* p = F.mvpMapPoints[k];
+        match[k] = (p && p != &held && p != &heldFree) ? (int)(p - pts.data()) : -1;
     }
     return nm;
 }

@@ -294,3 +294,59 @@ def test_bow_transform_restatement_equals_vendored_dbow2(tmp_path, k, L, scoring
             a, b = ora.transform(d, levelsup), ref.transform(d, levelsup)
             for x, y, what in zip(a, b, ("words", "values", "nodes", "node_start", "features")):
                 assert x.tobytes() == y.tobytes(), (what, len(d), levelsup)
+
+
+# ---- two-grid (fisheye stereo, Nleft != -1) branches of both searches: ORBmatcher.cc:1803-1868 and :153-218 ----
+import two_grid_cases as tg  # noqa: E402
+
+
+def oracle_stereo_frame(seed, kind):
+    ex = po.OracleExtractor(*tg.ARGS)
+    il, ir = tg.stereo_images(seed, kind)
+    (_, kl, dl), (_, kr, dr) = ex(il), ex(ir)
+    return ex.tables()["scale_factors"], (kl, dl), (kr, dr)
+
+
+@pytest.mark.skipif(not pyref.search_available(), reason="oracle/_ref/libref_search.so not built (needs /root/reference once)")
+@pytest.mark.parametrize("seed,th,mode,check,kind", [(21, 15.0, 0, True, "plain"), (22, 7.0, 0, True, "plain"), (23, 15.0, 1, True, "plain"), (24, 15.0, 2, False, "plain"),
+                                                    (25, 30.0, 0, True, "plain"), (26, 7.0, 0, True, "band"), (27, 15.0, 0, False, "band")])
+def test_two_grid_search_by_projection_matches_reference_body(seed, th, mode, check, kind):
+    sf, (kl, dl), (kr, dr) = oracle_stereo_frame(seed, kind)
+    pts, octv, nobs, pd = tg.frame_to_frame_points(seed, sf, *tg.last_frame(seed))
+    mb = 0.11
+    tlcz = {0: 0.0, 1: 2.0 * mb, 2: -2.0 * mb}[mode]
+    rm, rn = pyref.search_by_projection_stereo(kl, kr, np.concatenate([dl, dr]), tg.BOUNDS, sf, mb, 47.9, pts, octv, nobs, pd, th, tlcz, tg.DX_R, tg.DY_R, check)
+    q, side, owner = po.make_proj_queries_stereo(pts, octv, nobs, pd, sf, th, mode, tg.DX_R, tg.DY_R)
+    left, right = (kl, dl, po.assign_grid(kl, tg.BOUNDS)), (kr, dr, po.assign_grid(kr, tg.BOUNDS))
+    ml, mr, on = po.search_by_projection_stereo(left, right, tg.BOUNDS, q, side, check)
+    om = np.concatenate([ml, mr])
+    om = np.where(om >= 0, owner[np.maximum(om, 0)], -1)
+    assert rn == on and rn > 300, (rn, on)
+    assert np.array_equal(rm, om), int((rm != om).sum())
+    assert (rm[:len(kl)] >= 0).sum() > 100 and (rm[len(kl):] >= 0).sum() > 100
+    if kind == "band":   # the case is sensitive to the cancelled right search: treating the right parts as independent gives another answer
+        _, mr2, on2 = po.search_by_projection_stereo(left, right, tg.BOUNDS, q, np.where(side == 1, 2, side).astype(np.uint8), check)
+        assert on2 != on or not np.array_equal(mr, mr2)
+
+
+@pytest.mark.skipif(not pyref.search_available(), reason="oracle/_ref/libref_search.so not built (needs /root/reference once)")
+@pytest.mark.parametrize("seed,th,ratio,far,kind", [(31, 1.0, 0.8, False, "plain"), (32, 3.0, 0.8, False, "plain"), (33, 5.0, 0.9, True, "plain"), (34, 15.0, 0.6, False, "plain"),
+                                                   (35, 15.0, 0.8, False, "periodic"), (36, 15.0, 0.9, True, "periodic")])
+def test_two_grid_search_local_points_matches_reference_body(seed, th, ratio, far, kind):
+    sf, (kl, dl), (kr, dr) = oracle_stereo_frame(seed, kind)
+    taken0, l2r, r2l, pts, lv, lvr, nobs, flags, pd = tg.local_map_points(seed, len(kl), len(kr), kind)
+    rm, rn = pyref.search_local_points_stereo(kl, kr, np.concatenate([dl, dr]), taken0, l2r, r2l, tg.BOUNDS, sf, pts, lv, lvr, nobs, flags, pd, th, ratio, far, 40.0)
+    q, side, owner = po.make_local_queries_stereo(pts, lv, lvr, nobs, flags, pd, sf, th, far, 40.0)
+    assert (side == 0).sum() > 100 and (side == 1).sum() > 100 and (side == 2).sum() > 20
+    left, right = (kl, dl, po.assign_grid(kl, tg.BOUNDS)), (kr, dr, po.assign_grid(kr, tg.BOUNDS))
+    tl, tr = taken0[:len(kl)] == 1, taken0[len(kl):] == 1
+    ml, mr, on = po.search_local_points_stereo(left, right, tl, tr, l2r, r2l, tg.BOUNDS, q, side, ratio)
+    om = np.concatenate([ml, mr])
+    om = np.where(om >= 0, owner[np.maximum(om, 0)], -1)
+    assert rn == on and rn > 100, (rn, on)
+    assert np.array_equal(rm, om), int((rm != om).sum())
+    if kind == "periodic":   # sensitive to the ratio-test `continue` that also cancels the right search, and to the left/right links
+        ml2, mr2, on2 = po.search_local_points_stereo(left, right, tl, tr, l2r, r2l, tg.BOUNDS, q, np.where(side == 1, 2, side).astype(np.uint8), ratio)
+        assert on2 != on
+        ml3, mr3, on3 = po.search_local_points_stereo(left, right, tl, tr, None, None, tg.BOUNDS, q, side, ratio)
+        assert on3 != on
