@@ -256,6 +256,21 @@ int orbx_batch_search_local_points(orbx_batch* b, int image, const orbx_proj_que
  * is non-NULL before the search.  orb_dist = ORBdist.  match / n_matches as for orbx_batch_search_by_projection; synchronises. */
 int orbx_batch_search_keyframe_points(orbx_batch* b, int image, const orbx_proj_query* queries, int n_queries, int check_orientation, int orb_dist,
                                       const uint8_t* taken, int* match, int* n_matches);
+/* The same two searches for a TWO-GRID frame (fisheye stereo, Frame::Nleft != -1): ORBmatcher.cc:1803-1868 (frame to frame) and :153-218 (local map).
+ * The frame is image_left + image_right of the handle (each with its own grid from orbx_batch_assign_grid = Frame::mGrid / mGridRight, Frame.cc:428-441);
+ * mvpMapPoints[0 .. Nleft) is match_left, mvpMapPoints[Nleft ..) is match_right (K entries each).  A map point is sent as up to two queries IN A ROW,
+ * told apart by side[i]:  0 = its search in the left image (u, v = its projection there);  1 = its search in the right image, directly after its
+ * side-0 query (u, v = the projection into the right camera: GetRelativePoseTrl() * x3Dc resp. mTrackProjXR / mTrackProjYR, radius from mTrackViewCosR
+ * without the th factor, levels from mnTrackScaleLevelR);  2 = a right-image search of a point without a left part (local map: mbTrackInViewR only).
+ * The device replays what the reference's `continue`s do: an empty left window cancels the right search of that point in the frame-to-frame search
+ * (:1744-1745), a failed ratio test in the local-map search (:133-134).  The right-coordinate gate does not exist for such frames (ur unused).
+ * left_to_right / right_to_left = Frame::mvLeftToRightMatch / mvRightToLeftMatch (K host ints each, -1 = none, or NULL): an accepted local-map match also
+ * takes the partner keypoint and counts twice (:139-143, :205-209).  match values are indices into `queries`.  Synchronise. */
+int orbx_batch_search_by_projection_stereo(orbx_batch* b, int image_left, int image_right, const orbx_proj_query* queries, const uint8_t* side, int n_queries,
+                                           int check_orientation, int th_high, int* match_left, int* match_right, int* n_matches);
+int orbx_batch_search_local_points_stereo(orbx_batch* b, int image_left, int image_right, const orbx_proj_query* queries, const uint8_t* side, int n_queries,
+                                          float nn_ratio, int th_high, const uint8_t* taken_left, const uint8_t* taken_right, const int* left_to_right,
+                                          const int* right_to_left, int* match_left, int* match_right, int* n_matches);
 /* ------------------------------------------------------------------------------------------------------------------
  * Bag of words: Frame::ComputeBoW (Frame.cc:768-775; KeyFrame::ComputeBoW is the same call on stored descriptors)
  *     mpORBvocabulary->transform(vCurrentDesc, mBowVec, mFeatVec, 4);

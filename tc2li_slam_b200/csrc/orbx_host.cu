@@ -863,66 +863,129 @@ int orbx_batch_features_in_area(orbx_batch* b, const orbx_area_query* queries, i
     return ORBX_OK;
 }
 
-// both projection searches (search_kernel.cu); local = the local-map overload (taken: host bytes [K] or NULL); synchronous
-static int search_common(orbx_batch* b, bool local, int image, const orbx_proj_query* queries, int n_queries, int use_uright, int check_orientation, int th_high,
-                         float nn_ratio, const uint8_t* taken, int* match, int* n_matches) {
+// both projection searches (search_kernel.cu); local = the local-map overload; image2 >= 0 = a two-grid frame (side: n_queries host bytes; taken / taken2: host
+// bytes [K] per image or NULL; l2r / r2l: host ints [K] or NULL; match / match2: host ints [K] per image); synchronous
+struct SearchArgs {
+    bool local = false;
+    int image = 0, image2 = -1;
+    const orbx_proj_query* queries = nullptr;
+    const uint8_t* side = nullptr;
+    int n_queries = 0, use_uright = 0, check_orientation = 0, th_high = 100;
+    float nn_ratio = 0.f;
+    const uint8_t *taken = nullptr, *taken2 = nullptr;
+    const int *l2r = nullptr, *r2l = nullptr;
+    int *match = nullptr, *match2 = nullptr, *n_matches = nullptr;
+};
+
+static int search_common(orbx_batch* b, const SearchArgs& a) {
     if (!b) return fail(ORBX_ERR_ARG, "null handle");
-    if (n_queries < 0 || (n_queries && !queries) || !match || !n_matches) return fail(ORBX_ERR_ARG, "bad search arguments");
-    if (image < 0 || image >= b->gridImages) return fail(ORBX_ERR_ARG, "image has no feature grid (run orbx_batch_assign_grid first)");
+    const int n_queries = a.n_queries;
+    const bool two = a.image2 >= 0;
+    if (n_queries < 0 || (n_queries && !a.queries) || !a.match || !a.n_matches || (two && (!a.match2 || (n_queries && !a.side)))) return fail(ORBX_ERR_ARG, "bad search arguments");
+    if (a.image < 0 || a.image >= b->gridImages || (two && a.image2 >= b->gridImages)) return fail(ORBX_ERR_ARG, "image has no feature grid (run orbx_batch_assign_grid first)");
+    if (two && a.image2 == a.image) return fail(ORBX_ERR_ARG, "a two-grid frame needs two different images");
     if (n_queries > 65535) return fail(ORBX_ERR_TOO_LARGE, "more than 65535 map points in one search");
+    if (two)
+        for (int i = 0; i < n_queries; ++i)
+            if (a.side[i] > 2 || (a.side[i] == 1 && (i == 0 || a.side[i - 1] != 0))) return fail(ORBX_ERR_ARG, "side[i] must be 0, 2, or 1 right after a 0");
     DeviceGuard dg(b->device);
-    const int K = b->g.K;
+    const int K = b->g.K, sides = two ? 2 : 1, KK = K * sides;
+    if (KK > 32767) return fail(ORBX_ERR_TOO_LARGE, "keypoint capacity too large for the search kernel's 16-bit indices");
     const size_t budget = 200 * 1024;
     // the frame's descriptors are staged in shared memory when at least 32 KB remain for the candidate list next to them
-    const int stageDesc = search_smem_bytes(K, n_queries, 0, 1) + 32 * 1024 <= budget ? 1 : 0;
-    const size_t fixed = search_smem_bytes(K, n_queries, 0, stageDesc);
+    const int stageDesc = search_smem_bytes(K, n_queries, 0, 1, sides) + 32 * 1024 <= budget ? 1 : 0;
+    const size_t fixed = search_smem_bytes(K, n_queries, 0, stageDesc, sides);
     if (fixed + 4096 > budget) return fail(ORBX_ERR_TOO_LARGE, "keypoint capacity / number of map points too large for the search kernel's shared memory");
     const int candCap = (int)((budget - fixed) / 4);
     if (!b->spConfigured) { CU(search_configure()); b->spConfigured = true; }
-    if (!b->spOut) CU(cudaMalloc(&b->spOut, ((size_t)K + 2) * sizeof(int) + (size_t)K));  // match[K], info[2], taken0[K]
+    // per-call scratch: match[2K], info[2], links[2K] (ints) | taken0[2K] (bytes); side[] rides behind the queries
+    if (!b->spOut) CU(cudaMalloc(&b->spOut, ((size_t)4 * K + 2) * sizeof(int) + (size_t)2 * K));
     if ((size_t)n_queries > b->spCap) {
         if (b->spDev) cudaFree(b->spDev);
         b->spDev = nullptr; b->spCap = 0;
-        CU(cudaMalloc(&b->spDev, (size_t)n_queries * sizeof(orbx_proj_query)));
+        CU(cudaMalloc(&b->spDev, (size_t)n_queries * (sizeof(orbx_proj_query) + 1)));
         b->spCap = (size_t)n_queries;
     }
-    if (n_queries) CU(cudaMemcpyAsync(b->spDev, queries, (size_t)n_queries * sizeof(orbx_proj_query), cudaMemcpyHostToDevice, b->stream));
-    uint8_t* takenDev = reinterpret_cast<uint8_t*>(b->spOut + K + 2);
-    if (taken) CU(cudaMemcpyAsync(takenDev, taken, (size_t)K, cudaMemcpyHostToDevice, b->stream));
+    uint8_t* sideDev = reinterpret_cast<uint8_t*>(b->spDev + b->spCap);
+    if (n_queries) CU(cudaMemcpyAsync(b->spDev, a.queries, (size_t)n_queries * sizeof(orbx_proj_query), cudaMemcpyHostToDevice, b->stream));
+    if (n_queries && two) CU(cudaMemcpyAsync(sideDev, a.side, (size_t)n_queries, cudaMemcpyHostToDevice, b->stream));
+    int* infoDev = b->spOut + 2 * K;
+    int* linksDev = infoDev + 2;
+    uint8_t* takenDev = reinterpret_cast<uint8_t*>(linksDev + 2 * K);
+    const bool anyTaken = a.taken || a.taken2, anyLinks = two && (a.l2r || a.r2l);
+    if (anyTaken) {
+        if (a.taken) CU(cudaMemcpyAsync(takenDev, a.taken, (size_t)K, cudaMemcpyHostToDevice, b->stream)); else CU(cudaMemsetAsync(takenDev, 0, (size_t)K, b->stream));
+        if (two) { if (a.taken2) CU(cudaMemcpyAsync(takenDev + K, a.taken2, (size_t)K, cudaMemcpyHostToDevice, b->stream)); else CU(cudaMemsetAsync(takenDev + K, 0, (size_t)K, b->stream)); }
+    }
+    if (anyLinks) {
+        if (a.l2r) CU(cudaMemcpyAsync(linksDev, a.l2r, (size_t)K * sizeof(int), cudaMemcpyHostToDevice, b->stream)); else CU(cudaMemsetAsync(linksDev, 0xFF, (size_t)K * sizeof(int), b->stream));
+        if (a.r2l) CU(cudaMemcpyAsync(linksDev + K, a.r2l, (size_t)K * sizeof(int), cudaMemcpyHostToDevice, b->stream)); else CU(cudaMemsetAsync(linksDev + K, 0xFF, (size_t)K * sizeof(int), b->stream));
+    }
     Buffers buf = b->buf;
     buf.imgBase = 0;
-    if (local)
-        launch_search_local_points(buf, image, K, b->gridParams, b->spDev, n_queries, use_uright ? 1 : 0, th_high, nn_ratio, taken ? takenDev : nullptr, candCap, stageDesc, b->spOut,
-                                   b->spOut + K, b->stream);
+    if (a.local)
+        launch_search_local_points(buf, a.image, K, b->gridParams, b->spDev, n_queries, (a.use_uright && !two) ? 1 : 0, a.th_high, a.nn_ratio, anyTaken ? takenDev : nullptr, candCap,
+                                   stageDesc, b->spOut, infoDev, b->stream, a.image2, two ? sideDev : nullptr, anyLinks ? linksDev : nullptr);
     else
-        launch_search_by_projection(buf, image, K, b->gridParams, b->spDev, n_queries, use_uright ? 1 : 0, check_orientation ? 1 : 0, th_high, taken ? takenDev : nullptr, candCap, stageDesc, b->spOut,
-                                    b->spOut + K, b->stream);
+        launch_search_by_projection(buf, a.image, K, b->gridParams, b->spDev, n_queries, (a.use_uright && !two) ? 1 : 0, a.check_orientation ? 1 : 0, a.th_high,
+                                    anyTaken ? takenDev : nullptr, candCap, stageDesc, b->spOut, infoDev, b->stream, a.image2, two ? sideDev : nullptr);
     CU(cudaGetLastError());
     int info[2] = {0, 0};
-    CU(cudaMemcpyAsync(match, b->spOut, (size_t)K * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
-    CU(cudaMemcpyAsync(info, b->spOut + K, 2 * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaMemcpyAsync(a.match, b->spOut, (size_t)K * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+    if (two) CU(cudaMemcpyAsync(a.match2, b->spOut + K, (size_t)K * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaMemcpyAsync(info, infoDev, 2 * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
     CU(cudaStreamSynchronize(b->stream));
     if (info[0] < 0) return fail(ORBX_ERR_CAPACITY, "the search windows hold more candidates than the kernel's shared memory (smaller th / fewer points)");
-    *n_matches = info[0];
+    *a.n_matches = info[0];
     return ORBX_OK;
 }
 
 // ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) from ORBmatcher.cc:1729 on
 int orbx_batch_search_by_projection(orbx_batch* b, int image, const orbx_proj_query* queries, int n_queries, int use_uright, int check_orientation, int th_high,
                                     int* match, int* n_matches) {
-    return search_common(b, false, image, queries, n_queries, use_uright, check_orientation, th_high, 0.f, nullptr, match, n_matches);
+    SearchArgs a;
+    a.image = image; a.queries = queries; a.n_queries = n_queries; a.use_uright = use_uright; a.check_orientation = check_orientation; a.th_high = th_high;
+    a.match = match; a.n_matches = n_matches;
+    return search_common(b, a);
 }
 
 // ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (ORBmatcher.cc:1898-2019), the relocalisation search, behind its projection
 int orbx_batch_search_keyframe_points(orbx_batch* b, int image, const orbx_proj_query* queries, int n_queries, int check_orientation, int orb_dist,
                                       const uint8_t* taken, int* match, int* n_matches) {
-    return search_common(b, false, image, queries, n_queries, 0, check_orientation, orb_dist, 0.f, taken, match, n_matches);
+    SearchArgs a;
+    a.image = image; a.queries = queries; a.n_queries = n_queries; a.check_orientation = check_orientation; a.th_high = orb_dist; a.taken = taken;
+    a.match = match; a.n_matches = n_matches;
+    return search_common(b, a);
 }
 
 // ORBmatcher::SearchByProjection(F, vpMapPoints, th, bFarPoints, thFarPoints) (ORBmatcher.cc:52-222), the local-map search
 int orbx_batch_search_local_points(orbx_batch* b, int image, const orbx_proj_query* queries, int n_queries, int use_uright, float nn_ratio, int th_high,
                                    const uint8_t* taken, int* match, int* n_matches) {
-    return search_common(b, true, image, queries, n_queries, use_uright, 0, th_high, nn_ratio, taken, match, n_matches);
+    SearchArgs a;
+    a.local = true; a.image = image; a.queries = queries; a.n_queries = n_queries; a.use_uright = use_uright; a.nn_ratio = nn_ratio; a.th_high = th_high; a.taken = taken;
+    a.match = match; a.n_matches = n_matches;
+    return search_common(b, a);
+}
+
+// the two-grid (Frame::Nleft != -1) branches: ORBmatcher.cc:1803-1868 and :153-218
+int orbx_batch_search_by_projection_stereo(orbx_batch* b, int image_left, int image_right, const orbx_proj_query* queries, const uint8_t* side, int n_queries,
+                                           int check_orientation, int th_high, int* match_left, int* match_right, int* n_matches) {
+    if (image_right < 0) return fail(ORBX_ERR_ARG, "bad right image");
+    SearchArgs a;
+    a.image = image_left; a.image2 = image_right; a.queries = queries; a.side = side; a.n_queries = n_queries; a.check_orientation = check_orientation; a.th_high = th_high;
+    a.match = match_left; a.match2 = match_right; a.n_matches = n_matches;
+    return search_common(b, a);
+}
+
+int orbx_batch_search_local_points_stereo(orbx_batch* b, int image_left, int image_right, const orbx_proj_query* queries, const uint8_t* side, int n_queries,
+                                          float nn_ratio, int th_high, const uint8_t* taken_left, const uint8_t* taken_right, const int* left_to_right,
+                                          const int* right_to_left, int* match_left, int* match_right, int* n_matches) {
+    if (image_right < 0) return fail(ORBX_ERR_ARG, "bad right image");
+    SearchArgs a;
+    a.local = true; a.image = image_left; a.image2 = image_right; a.queries = queries; a.side = side; a.n_queries = n_queries; a.nn_ratio = nn_ratio; a.th_high = th_high;
+    a.taken = taken_left; a.taken2 = taken_right; a.l2r = left_to_right; a.r2l = right_to_left;
+    a.match = match_left; a.match2 = match_right; a.n_matches = n_matches;
+    return search_common(b, a);
 }
 
 // Descriptor stage of Frame::ComputeStereoFishEyeMatches (Frame.cc:1162-1187) for frames [0, n_frames): kNN (k = 2) of the left

@@ -181,13 +181,17 @@ void launch_assign_grid(const Buffers& b, int K, const GridParams& p, int nImage
 void launch_features_in_area(const Buffers& b, int K, const GridParams& p, const orbx_area_query* queries, int nQueries, int cap, int* counts, int* out,
                              cudaStream_t s);
 
-size_t search_smem_bytes(int K, int nq, int candCap, int stageDesc);
+size_t search_smem_bytes(int K, int nq, int candCap, int stageDesc, int sides);
 cudaError_t search_configure();
+// image2 >= 0: a two-grid frame (left image `image`, right image `image2`); side[nq] (device) tells the sub-queries apart; taken0 / links / outMatch then hold
+// 2 * K entries (left image first); links = partner keypoint in the other image (mvLeftToRightMatch | mvRightToLeftMatch), local-map search only
 void launch_search_by_projection(const Buffers& b, int image, int K, const GridParams& p, const orbx_proj_query* queries, int nq, int useURight, int checkOrientation,
-                                 int thHigh, const uint8_t* taken0, int candCap, int stageDesc, int* outMatch, int* outInfo, cudaStream_t s);
+                                 int thHigh, const uint8_t* taken0, int candCap, int stageDesc, int* outMatch, int* outInfo, cudaStream_t s, int image2 = -1,
+                                 const uint8_t* side = nullptr);
 
 void launch_search_local_points(const Buffers& b, int image, int K, const GridParams& p, const orbx_proj_query* queries, int nq, int useURight, int thHigh, float nnRatio,
-                                const uint8_t* taken0, int candCap, int stageDesc, int* outMatch, int* outInfo, cudaStream_t s);
+                                const uint8_t* taken0, int candCap, int stageDesc, int* outMatch, int* outInfo, cudaStream_t s, int image2 = -1,
+                                const uint8_t* side = nullptr, const int* links = nullptr);
 
 // DBoW2 vocabulary transform (bow_kernel.cu): the tree by node id (0 = root); children of node n = childList[childStart[n] .. childStart[n + 1])
 struct BowVocDev {

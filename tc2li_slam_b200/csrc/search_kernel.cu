@@ -17,6 +17,13 @@
 // follows the reference operation by operation in float32.  The template parameter switches to the local-map overload
 // ORBmatcher::SearchByProjection(F, vpMapPoints, th, bFarPoints, thFarPoints) (ORBmatcher.cc:52-222): best / second best with levels
 // and the mfNNratio test instead of the rotation check, keypoints taken before the search as an input.
+//
+// Two-grid frames (fisheye stereo, Frame::Nleft != -1; ORBmatcher.cc:153-218 and :1803-1868): image2 >= 0 names the right image of the
+// frame.  Both images' grids / keypoints / descriptors are staged (the right ones behind the left ones, keypoint k of the right image
+// is entry K + k), a map point arrives as up to two sub-queries in a row told apart by side[i] (0 = left image, 1 = right image after
+// its left part, 2 = right image alone), and the sequential pass replays what the reference's `continue`s do to the right part: an EMPTY
+// left window cancels it in the frame-to-frame search (:1744-1745), a failed ratio test in the local-map search (:133-134).  An accepted
+// local-map match also takes the partner keypoint of mvLeftToRightMatch / mvRightToLeftMatch (:139-143, :205-209).  No right-coordinate gate.
 #include <algorithm>
 
 #include "orbx_internal.cuh"
@@ -47,7 +54,7 @@ __device__ __forceinline__ Window window_of(float x, float y, float r, const Gri
 // the candidate walk of one query by one warp; EMIT = false: count only.  Returns the number of candidates (after the gate).
 template <bool EMIT>
 __device__ __forceinline__ int walk(const orbx_proj_query& Q, const Window& W, const int* gs, const uint16_t* gi, const float2* kxy, const uint8_t* koct,
-                                    const uint8_t* desc, const float* uRight, uint32_t* out, int lane) {
+                                    const uint8_t* desc, const float* uRight, uint32_t* out, int lane, int base) {
     if (W.empty) return 0;
     const bool checkLevels = Q.min_level > 0 || Q.max_level >= 0;
     uint32_t qd[8];
@@ -63,7 +70,7 @@ __device__ __forceinline__ int walk(const orbx_proj_query& Q, const Window& W, c
             bool hit = false;
             int idx = 0, kpOctave = 0;
             if (j < e) {
-                idx = gi[j];
+                idx = base + gi[j];
                 const float2 kp = kxy[idx];
                 kpOctave = koct[idx];
                 bool lv = true;
@@ -76,7 +83,7 @@ __device__ __forceinline__ int walk(const orbx_proj_query& Q, const Window& W, c
             }
             const unsigned bal = __ballot_sync(0xFFFFFFFFu, hit);
             if (EMIT && hit) {
-                const uint4* d = reinterpret_cast<const uint4*>(desc + (size_t)idx * 32);
+                const uint4* d = reinterpret_cast<const uint4*>(desc + (size_t)(idx - base) * 32);   // desc: this image's rows
                 const uint4 a = d[0], c = d[1];
                 const int dist = __popc(a.x ^ qd[0]) + __popc(a.y ^ qd[1]) + __popc(a.z ^ qd[2]) + __popc(a.w ^ qd[3]) + __popc(c.x ^ qd[4]) + __popc(c.y ^ qd[5]) +
                                  __popc(c.z ^ qd[6]) + __popc(c.w ^ qd[7]);
@@ -90,68 +97,83 @@ __device__ __forceinline__ int walk(const orbx_proj_query& Q, const Window& W, c
 
 }  // namespace
 
-// shared memory: match[K] | candStart[nq + 1] | cand[candCap] | gs[3073] | kxy[K] | ur[K] | kang[K] | qang[nq] | gi[K] (u16) | entIdx[nq] (u16) | entBin[nq] | taken[K] | koct[K] | qblk[nq]
+// shared memory (KK = K per image of the frame): match[KK] | candStart[nq + 1] | cand[candCap] | gs[sides][3073] | kxy[KK] | ur[KK] | kang[KK] | qang[nq] | gi[KK] (u16) |
+// entIdx[nq] (u16) | link[KK] (i16) | entBin[nq] | taken[KK] | koct[KK] | qblk[nq] | qside[nq]
 // LOCAL = false: frame-to-frame search (best distance, rotation check); LOCAL = true: local-map search (best / second best with
 // their levels and the mfNNratio test, keypoints taken before the search in taken0, no rotation check)
 template <bool LOCAL>
 __global__ void __launch_bounds__(ST) k_search_by_projection(const Buffers b, int image, int K, GridParams p, const orbx_proj_query* __restrict__ queries, int nq,
                                                             int useURight, int checkOrientation, int thHigh, float nnRatio, const uint8_t* __restrict__ taken0,
-                                                            int candCap, int stageDesc, int* __restrict__ outMatch, int* __restrict__ outInfo) {
+                                                            int candCap, int stageDesc, int* __restrict__ outMatch, int* __restrict__ outInfo, int image2,
+                                                            const uint8_t* __restrict__ side, const int* __restrict__ links) {
     extern __shared__ __align__(16) unsigned char ssm[];
     __shared__ int warpSum[ST / 32];
     __shared__ int hist[HISTO];
     __shared__ int sInfo[4];  // nmatches, entries, total candidates, keep-bin mask
+    const int sides = image2 >= 0 ? 2 : 1, KK = K * sides;
     int* match = reinterpret_cast<int*>(ssm);
-    int* candStart = match + K;
+    int* candStart = match + KK;
     uint32_t* cand = reinterpret_cast<uint32_t*>(candStart + nq + 1);
     int* gsS = reinterpret_cast<int*>(cand + candCap);
-    float2* kxy = reinterpret_cast<float2*>((reinterpret_cast<uintptr_t>(gsS + NC + 1) + 7) & ~(uintptr_t)7);
-    float* urS = reinterpret_cast<float*>(kxy + K);
-    float* kang = urS + K;      // keypoint angles (rotation histogram)
-    float* qang = kang + K;     // per query: kpLF.angle
+    float2* kxy = reinterpret_cast<float2*>((reinterpret_cast<uintptr_t>(gsS + sides * (NC + 1)) + 7) & ~(uintptr_t)7);
+    float* urS = reinterpret_cast<float*>(kxy + KK);
+    float* kang = urS + KK;     // keypoint angles (rotation histogram)
+    float* qang = kang + KK;    // per query: kpLF.angle
     uint16_t* giS = reinterpret_cast<uint16_t*>(qang + nq);
-    uint16_t* entIdx = giS + K;
-    uint8_t* entBin = reinterpret_cast<uint8_t*>(entIdx + nq);
+    uint16_t* entIdx = giS + KK;
+    int16_t* link = reinterpret_cast<int16_t*>(entIdx + nq);   // two-grid local map: partner keypoint in the other image, -1 = none
+    uint8_t* entBin = reinterpret_cast<uint8_t*>(link + KK);
     uint8_t* taken = entBin + nq;
-    uint8_t* koct = taken + K;
-    uint8_t* qblk = koct + K;   // per query: Observations() > 0
+    uint8_t* koct = taken + KK;
+    uint8_t* qblk = koct + KK;  // per query: Observations() > 0
+    uint8_t* qside = qblk + nq; // per query: 0 left image, 1 right image after its left part, 2 right image alone
     // the frame's descriptors (32 bytes per keypoint) when they fit next to the rest: then nothing below touches global memory
-    uint4* descS = reinterpret_cast<uint4*>((reinterpret_cast<uintptr_t>(qblk + nq) + 15) & ~(uintptr_t)15);
+    uint4* descS = reinterpret_cast<uint4*>((reinterpret_cast<uintptr_t>(qside + nq) + 15) & ~(uintptr_t)15);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n = b.outCount[image];
-    const int* gs = b.gridStart + (size_t)image * (NC + 1);
-    const int* gi = b.gridItems + (size_t)image * K;
-    const orbx_keypoint* kps = b.kps + (size_t)image * K;
+    const int n2 = sides == 2 ? b.outCount[image2] : 0;
     const uint8_t* desc = b.desc + (size_t)image * K * 32;
+    const uint8_t* desc2 = sides == 2 ? b.desc + (size_t)image2 * K * 32 : nullptr;
     if (stageDesc) {
         const uint4* g = reinterpret_cast<const uint4*>(desc);
         for (int k = tid; k < 2 * n; k += ST) descS[k] = g[k];
+        if (sides == 2) {
+            const uint4* g2 = reinterpret_cast<const uint4*>(desc2);
+            for (int k = tid; k < 2 * n2; k += ST) descS[2 * K + k] = g2[k];
+        }
         desc = reinterpret_cast<const uint8_t*>(descS);
+        desc2 = desc + (size_t)K * 32;
     }
     const float* uRight = useURight ? b.uRight + (size_t)image * K : nullptr;
     // the frame's grid, keypoint coordinates / levels and right coordinates move to shared memory once: the walks below touch global
     // memory only for the 32-byte descriptors of their hits
-    for (int k = tid; k < K; k += ST) {
-        match[k] = -1;
-        taken[k] = (taken0 && k < n) ? (taken0[k] != 0) : 0;
-        if (k < n) {
-            const orbx_keypoint kp = kps[k];
-            kxy[k] = make_float2(kp.x, kp.y);
-            koct[k] = (uint8_t)(kp.octave & 15);
-            urS[k] = uRight ? uRight[k] : -1.f;
-            kang[k] = kp.angle;
-            giS[k] = (uint16_t)gi[k];
+    for (int kk = tid; kk < KK; kk += ST) {
+        const int sd = kk >= K ? 1 : 0, k = kk - sd * K, img = sd ? image2 : image, cnt = sd ? n2 : n;
+        match[kk] = -1;
+        taken[kk] = (taken0 && k < cnt) ? (taken0[kk] != 0) : 0;
+        link[kk] = (links && k < cnt) ? (int16_t)links[kk] : (int16_t)-1;
+        if (k < cnt) {
+            const orbx_keypoint kp = b.kps[(size_t)img * K + k];
+            kxy[kk] = make_float2(kp.x, kp.y);
+            koct[kk] = (uint8_t)(kp.octave & 15);
+            urS[kk] = uRight ? uRight[k] : -1.f;
+            kang[kk] = kp.angle;
+            giS[kk] = (uint16_t)b.gridItems[(size_t)img * K + k];
         }
     }
-    for (int c = tid; c <= NC; c += ST) gsS[c] = gs[c];
-    for (int i = tid; i < nq; i += ST) { qang[i] = queries[i].angle; qblk[i] = queries[i].blocks != 0; }
+    for (int c = tid; c < sides * (NC + 1); c += ST) {
+        const int sd = c > NC ? 1 : 0;
+        gsS[c] = b.gridStart[(size_t)(sd ? image2 : image) * (NC + 1) + (c - sd * (NC + 1))];
+    }
+    for (int i = tid; i < nq; i += ST) { qang[i] = queries[i].angle; qblk[i] = queries[i].blocks != 0; qside[i] = (sides == 2 && side) ? side[i] : 0; }
     if (tid < HISTO) hist[tid] = 0;
     if (tid < 4) sInfo[tid] = 0;
     __syncthreads();
     // ---- phase 1a: candidate counts ----
     for (int i = wid; i < nq; i += ST / 32) {
         const orbx_proj_query Q = queries[i];
-        const int c = walk<false>(Q, window_of(Q.u, Q.v, Q.radius, p), gsS, giS, kxy, koct, desc, uRight ? urS : nullptr, nullptr, lane);
+        const int sd = qside[i] ? 1 : 0;
+        const int c = walk<false>(Q, window_of(Q.u, Q.v, Q.radius, p), gsS + sd * (NC + 1), giS + sd * K, kxy, koct, sd ? desc2 : desc, uRight ? urS : nullptr, nullptr, lane, sd * K);
         if (lane == 0) candStart[i] = c;
     }
     __syncthreads();
@@ -182,6 +204,7 @@ __global__ void __launch_bounds__(ST) k_search_by_projection(const Buffers b, in
     // Queries are processed in chunks [i0, i1) whose candidates fit the shared-memory list (one chunk unless the windows are
     // very wide, e.g. th = 15 after tracking was lost); the taken / match state carries over, so chunking does not change the result.
     int nm = 0, ne = 0;  // (live in warp 0)
+    bool skipRight = false;  // (warp 0) the left part of this map point hit a `continue` that also skips its right part
     for (int i0 = 0; i0 < nq;) {
         if (tid == 0) {
             int i1 = i0;
@@ -198,14 +221,21 @@ __global__ void __launch_bounds__(ST) k_search_by_projection(const Buffers b, in
         // ---- phase 1b: the candidates, in visiting order, with their distances ----
         for (int i = i0 + wid; i < i1; i += ST / 32) {
             const orbx_proj_query Q = queries[i];
-            walk<true>(Q, window_of(Q.u, Q.v, Q.radius, p), gsS, giS, kxy, koct, desc, uRight ? urS : nullptr, cand + (candStart[i] - cbase), lane);
+            const int sd = qside[i] ? 1 : 0;
+            walk<true>(Q, window_of(Q.u, Q.v, Q.radius, p), gsS + sd * (NC + 1), giS + sd * K, kxy, koct, sd ? desc2 : desc, uRight ? urS : nullptr, cand + (candStart[i] - cbase), lane, sd * K);
         }
         __syncthreads();
         // ---- phase 2: the reference's loop over the map points, in order (one warp) ----
         if (wid == 0) {
             for (int i = i0; i < i1; ++i) {
+                const int sd = qside[i];
+                if (sd == 0) skipRight = false;
+                else if (sd == 1 && skipRight) continue;
                 const int s = candStart[i] - cbase, e = candStart[i + 1] - cbase;
-                if (s == e) continue;
+                if (s == e) {
+                    if (!LOCAL && sd == 0) skipRight = true;   // if(vIndices2.empty()) continue;  (ORBmatcher.cc:1744-1745)
+                    continue;
+                }
                 if (LOCAL) {
                     // ORBmatcher.cc:85-137: the reference's update order decides who is "second best", so every lane replays the short
                     // candidate list as written (warp-uniform, shared-memory broadcasts, no shuffles)
@@ -221,9 +251,15 @@ __global__ void __launch_bounds__(ST) k_search_by_projection(const Buffers b, in
                     if (bestDist <= thHigh) {
                         const float lim = __fmul_rn(nnRatio, (float)bestDist2);
                         const bool ratioFail = bestLevel == bestLevel2 && (float)bestDist > lim;
-                        if (!ratioFail && (bestLevel != bestLevel2 || (float)bestDist <= lim)) {
-                            if (lane == 0) { match[bestIdx] = i; taken[bestIdx] = qblk[i]; }
-                            ++nm;
+                        if (ratioFail) {
+                            if (sd == 0) skipRight = true;       // the `continue` of ORBmatcher.cc:133-134 leaves the loop body
+                        } else if (bestLevel != bestLevel2 || (float)bestDist <= lim) {
+                            const int partner = link[bestIdx];   // mvLeftToRightMatch / mvRightToLeftMatch (two-grid frames), -1 = none
+                            if (lane == 0) {
+                                match[bestIdx] = i; taken[bestIdx] = qblk[i];
+                                if (partner >= 0) { const int pk = (sd == 0 ? K : 0) + partner; match[pk] = i; taken[pk] = qblk[i]; }
+                            }
+                            nm += partner >= 0 ? 2 : 1;
                             __syncwarp();
                         }
                     }
@@ -293,12 +329,14 @@ __global__ void __launch_bounds__(ST) k_search_by_projection(const Buffers b, in
             }
         __syncthreads();
     }
-    for (int k = tid; k < K; k += ST) outMatch[k] = k < n ? match[k] : -1;
+    for (int kk = tid; kk < KK; kk += ST) outMatch[kk] = (kk < K ? kk < n : kk - K < n2) ? match[kk] : -1;
     if (tid == 0) { outInfo[0] = sInfo[0]; outInfo[1] = total; }
 }
 
-size_t search_smem_bytes(int K, int nq, int candCap, int stageDesc) {
-    return (stageDesc ? (size_t)K * 32 + 16 : 0) + (size_t)K * 4 + ((size_t)nq + 1) * 4 + (size_t)candCap * 4 + (size_t)(NC + 2) * 4 + (size_t)K * (8 + 4 + 4 + 2 + 1 + 1) + (size_t)nq * (4 + 3 + 1) + 32;
+size_t search_smem_bytes(int K, int nq, int candCap, int stageDesc, int sides) {
+    const size_t KK = (size_t)K * sides;
+    return (stageDesc ? KK * 32 + 16 : 0) + KK * 4 + ((size_t)nq + 1) * 4 + (size_t)candCap * 4 + (size_t)sides * (NC + 1) * 4 + 8 + KK * (8 + 4 + 4 + 2 + 2 + 1 + 1) +
+           (size_t)nq * (4 + 2 + 1 + 1 + 1) + 32;
 }
 
 cudaError_t search_configure() {
@@ -308,15 +346,18 @@ cudaError_t search_configure() {
 }
 
 void launch_search_by_projection(const Buffers& b, int image, int K, const GridParams& p, const orbx_proj_query* queries, int nq, int useURight, int checkOrientation,
-                                 int thHigh, const uint8_t* taken0, int candCap, int stageDesc, int* outMatch, int* outInfo, cudaStream_t s) {
-    k_search_by_projection<false><<<1, ST, search_smem_bytes(K, nq, candCap, stageDesc), s>>>(b, image, K, p, queries, nq, useURight, checkOrientation, thHigh, 0.f,
-                                                                                             taken0, candCap, stageDesc, outMatch, outInfo);
+                                 int thHigh, const uint8_t* taken0, int candCap, int stageDesc, int* outMatch, int* outInfo, cudaStream_t s, int image2, const uint8_t* side) {
+    k_search_by_projection<false><<<1, ST, search_smem_bytes(K, nq, candCap, stageDesc, image2 >= 0 ? 2 : 1), s>>>(b, image, K, p, queries, nq, useURight, checkOrientation,
+                                                                                                                  thHigh, 0.f, taken0, candCap, stageDesc, outMatch, outInfo,
+                                                                                                                  image2, side, nullptr);
 }
 
 void launch_search_local_points(const Buffers& b, int image, int K, const GridParams& p, const orbx_proj_query* queries, int nq, int useURight, int thHigh, float nnRatio,
-                                const uint8_t* taken0, int candCap, int stageDesc, int* outMatch, int* outInfo, cudaStream_t s) {
-    k_search_by_projection<true><<<1, ST, search_smem_bytes(K, nq, candCap, stageDesc), s>>>(b, image, K, p, queries, nq, useURight, 0, thHigh, nnRatio, taken0, candCap,
-                                                                                            stageDesc, outMatch, outInfo);
+                                const uint8_t* taken0, int candCap, int stageDesc, int* outMatch, int* outInfo, cudaStream_t s, int image2, const uint8_t* side,
+                                const int* links) {
+    k_search_by_projection<true><<<1, ST, search_smem_bytes(K, nq, candCap, stageDesc, image2 >= 0 ? 2 : 1), s>>>(b, image, K, p, queries, nq, useURight, 0, thHigh, nnRatio,
+                                                                                                                 taken0, candCap, stageDesc, outMatch, outInfo, image2, side,
+                                                                                                                 links);
 }
 
 }  // namespace orbx

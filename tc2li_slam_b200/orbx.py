@@ -115,6 +115,8 @@ def lib():
         "orbx_batch_debug_candidates": (i, [_vp, i, i, _vp, i, _vp]),
         "orbx_batch_debug_selected": (i, [_vp, i, i, _vp, i, _vp]),
         "orbx_batch_debug_fallback_cells": (i, [_vp, i, i, _vp]),
+        "orbx_batch_search_by_projection_stereo": (i, [_vp, i, i, _vp, _vp, i, i, i, _vp, _vp, _vp]),
+        "orbx_batch_search_local_points_stereo": (i, [_vp, i, i, _vp, _vp, i, f, i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
         "orbx_vocabulary_load_text": (i, [i, C.c_char_p, C.POINTER(_vp)]),
         "orbx_vocabulary_create": (i, [i, i, i, i, i, i, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
         "orbx_vocabulary_destroy": (None, [_vp]),
@@ -671,6 +673,38 @@ class BatchExtractor:
         _check(lib().orbx_batch_search_local_points(self._h, int(image), _p(q), len(q), int(bool(use_uright)), float(nn_ratio), int(th_high),
                                                     _p(t) if t is not None else None, _p(match), C.byref(nm)))
         return match, nm.value
+
+    def _padded(self, a, dtype, fill):
+        if a is None:
+            return None
+        out = np.full(self.K, fill, dtype)
+        out[:len(a)] = a
+        return out
+
+    def search_by_projection_stereo(self, image_left, image_right, queries, side, check_orientation=True, th_high=100):
+        """Two-grid frame (fisheye stereo, Nleft != -1) variant of search_by_projection (ORBmatcher.cc:1729-1868): sub-queries with side[i] = 0 (left image),
+        1 (right image, directly after its left part) — see include/orbx.h.  Returns (match_left [K], match_right [K], nmatches)."""
+        q = np.ascontiguousarray(np.asarray(queries, dtype=PROJ_QUERY_DTYPE))
+        sd = np.ascontiguousarray(side, np.uint8)
+        ml, mr, nm = np.empty(self.K, np.int32), np.empty(self.K, np.int32), C.c_int(0)
+        _check(lib().orbx_batch_search_by_projection_stereo(self._h, int(image_left), int(image_right), _p(q), _p(sd), len(q), int(bool(check_orientation)), int(th_high),
+                                                            _p(ml), _p(mr), C.byref(nm)))
+        return ml, mr, nm.value
+
+    def search_local_points_stereo(self, image_left, image_right, queries, side, taken_left=None, taken_right=None, left_to_right=None, right_to_left=None,
+                                   nn_ratio=0.8, th_high=100):
+        """Two-grid variant of search_local_points (ORBmatcher.cc:52-222 with F.Nleft != -1); left_to_right / right_to_left = Frame::mvLeftToRightMatch /
+        mvRightToLeftMatch.  Returns (match_left [K], match_right [K], nmatches)."""
+        q = np.ascontiguousarray(np.asarray(queries, dtype=PROJ_QUERY_DTYPE))
+        sd = np.ascontiguousarray(side, np.uint8)
+        tl = self._padded(None if taken_left is None else np.asarray(taken_left) != 0, np.uint8, 0)
+        tr = self._padded(None if taken_right is None else np.asarray(taken_right) != 0, np.uint8, 0)
+        a, b = self._padded(left_to_right, np.int32, -1), self._padded(right_to_left, np.int32, -1)
+        o = lambda x: None if x is None else _p(x)
+        ml, mr, nm = np.empty(self.K, np.int32), np.empty(self.K, np.int32), C.c_int(0)
+        _check(lib().orbx_batch_search_local_points_stereo(self._h, int(image_left), int(image_right), _p(q), _p(sd), len(q), float(nn_ratio), int(th_high), o(tl), o(tr),
+                                                           o(a), o(b), _p(ml), _p(mr), C.byref(nm)))
+        return ml, mr, nm.value
 
     def compute_bow(self, vocabulary, n_images, levelsup=4):
         """Batched Frame::ComputeBoW (Frame.cc:768-775) on the resident descriptors (after run()); asynchronous."""
