@@ -891,10 +891,11 @@ static int search_common(orbx_batch* b, const SearchArgs& a) {
     DeviceGuard dg(b->device);
     const int K = b->g.K, sides = two ? 2 : 1, KK = K * sides;
     if (KK > 32767) return fail(ORBX_ERR_TOO_LARGE, "keypoint capacity too large for the search kernel's 16-bit indices");
-    const size_t budget = 200 * 1024;
+    const size_t budget = kSearchSmemBudget;
+    const bool anyTaken = a.taken || a.taken2, anyLinks = two && a.local && (a.l2r || a.r2l);
     // the frame's descriptors are staged in shared memory when at least 32 KB remain for the candidate list next to them
-    const int stageDesc = search_smem_bytes(K, n_queries, 0, 1, sides) + 32 * 1024 <= budget ? 1 : 0;
-    const size_t fixed = search_smem_bytes(K, n_queries, 0, stageDesc, sides);
+    const int stageDesc = search_smem_bytes(K, n_queries, 0, 1, sides, anyLinks) + 32 * 1024 <= budget ? 1 : 0;
+    const size_t fixed = search_smem_bytes(K, n_queries, 0, stageDesc, sides, anyLinks);
     if (fixed + 4096 > budget) return fail(ORBX_ERR_TOO_LARGE, "keypoint capacity / number of map points too large for the search kernel's shared memory");
     const int candCap = (int)((budget - fixed) / 4);
     if (!b->spConfigured) { CU(search_configure()); b->spConfigured = true; }
@@ -912,7 +913,6 @@ static int search_common(orbx_batch* b, const SearchArgs& a) {
     int* infoDev = b->spOut + 2 * K;
     int* linksDev = infoDev + 2;
     uint8_t* takenDev = reinterpret_cast<uint8_t*>(linksDev + 2 * K);
-    const bool anyTaken = a.taken || a.taken2, anyLinks = two && (a.l2r || a.r2l);
     if (anyTaken) {
         if (a.taken) CU(cudaMemcpyAsync(takenDev, a.taken, (size_t)K, cudaMemcpyHostToDevice, b->stream)); else CU(cudaMemsetAsync(takenDev, 0, (size_t)K, b->stream));
         if (two) { if (a.taken2) CU(cudaMemcpyAsync(takenDev + K, a.taken2, (size_t)K, cudaMemcpyHostToDevice, b->stream)); else CU(cudaMemsetAsync(takenDev + K, 0, (size_t)K, b->stream)); }

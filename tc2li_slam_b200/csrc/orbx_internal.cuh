@@ -181,7 +181,8 @@ void launch_assign_grid(const Buffers& b, int K, const GridParams& p, int nImage
 void launch_features_in_area(const Buffers& b, int K, const GridParams& p, const orbx_area_query* queries, int nQueries, int cap, int* counts, int* out,
                              cudaStream_t s);
 
-size_t search_smem_bytes(int K, int nq, int candCap, int stageDesc, int sides);
+constexpr size_t kSearchSmemBudget = 224 * 1024;   // dynamic shared memory of the search kernel (B200: 227 KB per CTA minus its static arrays)
+size_t search_smem_bytes(int K, int nq, int candCap, int stageDesc, int sides, int hasLinks);
 cudaError_t search_configure();
 // image2 >= 0: a two-grid frame (left image `image`, right image `image2`); side[nq] (device) tells the sub-queries apart; taken0 / links / outMatch then hold
 // 2 * K entries (left image first); links = partner keypoint in the other image (mvLeftToRightMatch | mvRightToLeftMatch), local-map search only

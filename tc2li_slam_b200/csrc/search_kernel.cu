@@ -122,13 +122,13 @@ __global__ void __launch_bounds__(ST) k_search_by_projection(const Buffers b, in
     uint16_t* giS = reinterpret_cast<uint16_t*>(qang + nq);
     uint16_t* entIdx = giS + KK;
     int16_t* link = reinterpret_cast<int16_t*>(entIdx + nq);   // two-grid local map: partner keypoint in the other image, -1 = none
-    uint8_t* entBin = reinterpret_cast<uint8_t*>(link + KK);
+    uint8_t* entBin = reinterpret_cast<uint8_t*>(link + (links ? KK : 0));   // (no link / side arrays for single-grid frames)
     uint8_t* taken = entBin + nq;
     uint8_t* koct = taken + KK;
     uint8_t* qblk = koct + KK;  // per query: Observations() > 0
     uint8_t* qside = qblk + nq; // per query: 0 left image, 1 right image after its left part, 2 right image alone
     // the frame's descriptors (32 bytes per keypoint) when they fit next to the rest: then nothing below touches global memory
-    uint4* descS = reinterpret_cast<uint4*>((reinterpret_cast<uintptr_t>(qside + nq) + 15) & ~(uintptr_t)15);
+    uint4* descS = reinterpret_cast<uint4*>((reinterpret_cast<uintptr_t>(qside + (side ? nq : 0)) + 15) & ~(uintptr_t)15);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n = b.outCount[image];
     const int n2 = sides == 2 ? b.outCount[image2] : 0;
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(ST) k_search_by_projection(const Buffers b, in
         const int sd = kk >= K ? 1 : 0, k = kk - sd * K, img = sd ? image2 : image, cnt = sd ? n2 : n;
         match[kk] = -1;
         taken[kk] = (taken0 && k < cnt) ? (taken0[kk] != 0) : 0;
-        link[kk] = (links && k < cnt) ? (int16_t)links[kk] : (int16_t)-1;
+        if (links) link[kk] = k < cnt ? (int16_t)links[kk] : (int16_t)-1;
         if (k < cnt) {
             const orbx_keypoint kp = b.kps[(size_t)img * K + k];
             kxy[kk] = make_float2(kp.x, kp.y);
@@ -165,14 +165,14 @@ __global__ void __launch_bounds__(ST) k_search_by_projection(const Buffers b, in
         const int sd = c > NC ? 1 : 0;
         gsS[c] = b.gridStart[(size_t)(sd ? image2 : image) * (NC + 1) + (c - sd * (NC + 1))];
     }
-    for (int i = tid; i < nq; i += ST) { qang[i] = queries[i].angle; qblk[i] = queries[i].blocks != 0; qside[i] = (sides == 2 && side) ? side[i] : 0; }
+    for (int i = tid; i < nq; i += ST) { qang[i] = queries[i].angle; qblk[i] = queries[i].blocks != 0; if (side) qside[i] = side[i]; }
     if (tid < HISTO) hist[tid] = 0;
     if (tid < 4) sInfo[tid] = 0;
     __syncthreads();
     // ---- phase 1a: candidate counts ----
     for (int i = wid; i < nq; i += ST / 32) {
         const orbx_proj_query Q = queries[i];
-        const int sd = qside[i] ? 1 : 0;
+        const int sd = (side && qside[i]) ? 1 : 0;
         const int c = walk<false>(Q, window_of(Q.u, Q.v, Q.radius, p), gsS + sd * (NC + 1), giS + sd * K, kxy, koct, sd ? desc2 : desc, uRight ? urS : nullptr, nullptr, lane, sd * K);
         if (lane == 0) candStart[i] = c;
     }
@@ -221,14 +221,14 @@ __global__ void __launch_bounds__(ST) k_search_by_projection(const Buffers b, in
         // ---- phase 1b: the candidates, in visiting order, with their distances ----
         for (int i = i0 + wid; i < i1; i += ST / 32) {
             const orbx_proj_query Q = queries[i];
-            const int sd = qside[i] ? 1 : 0;
+            const int sd = (side && qside[i]) ? 1 : 0;
             walk<true>(Q, window_of(Q.u, Q.v, Q.radius, p), gsS + sd * (NC + 1), giS + sd * K, kxy, koct, sd ? desc2 : desc, uRight ? urS : nullptr, cand + (candStart[i] - cbase), lane, sd * K);
         }
         __syncthreads();
         // ---- phase 2: the reference's loop over the map points, in order (one warp) ----
         if (wid == 0) {
             for (int i = i0; i < i1; ++i) {
-                const int sd = qside[i];
+                const int sd = side ? qside[i] : 0;
                 if (sd == 0) skipRight = false;
                 else if (sd == 1 && skipRight) continue;
                 const int s = candStart[i] - cbase, e = candStart[i + 1] - cbase;
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(ST) k_search_by_projection(const Buffers b, in
                         if (ratioFail) {
                             if (sd == 0) skipRight = true;       // the `continue` of ORBmatcher.cc:133-134 leaves the loop body
                         } else if (bestLevel != bestLevel2 || (float)bestDist <= lim) {
-                            const int partner = link[bestIdx];   // mvLeftToRightMatch / mvRightToLeftMatch (two-grid frames), -1 = none
+                            const int partner = links ? link[bestIdx] : -1;   // mvLeftToRightMatch / mvRightToLeftMatch (two-grid frames), -1 = none
                             if (lane == 0) {
                                 match[bestIdx] = i; taken[bestIdx] = qblk[i];
                                 if (partner >= 0) { const int pk = (sd == 0 ? K : 0) + partner; match[pk] = i; taken[pk] = qblk[i]; }
@@ -333,21 +333,21 @@ __global__ void __launch_bounds__(ST) k_search_by_projection(const Buffers b, in
     if (tid == 0) { outInfo[0] = sInfo[0]; outInfo[1] = total; }
 }
 
-size_t search_smem_bytes(int K, int nq, int candCap, int stageDesc, int sides) {
+size_t search_smem_bytes(int K, int nq, int candCap, int stageDesc, int sides, int hasLinks) {
     const size_t KK = (size_t)K * sides;
-    return (stageDesc ? KK * 32 + 16 : 0) + KK * 4 + ((size_t)nq + 1) * 4 + (size_t)candCap * 4 + (size_t)sides * (NC + 1) * 4 + 8 + KK * (8 + 4 + 4 + 2 + 2 + 1 + 1) +
-           (size_t)nq * (4 + 2 + 1 + 1 + 1) + 32;
+    return (stageDesc ? KK * 32 + 16 : 0) + KK * 4 + ((size_t)nq + 1) * 4 + (size_t)candCap * 4 + (size_t)sides * (NC + 1) * 4 + 8 + KK * (8 + 4 + 4 + 2 + 1 + 1) +
+           (hasLinks ? KK * 2 : 0) + (size_t)nq * (4 + 2 + 1 + 1 + (sides == 2 ? 1 : 0)) + 32;
 }
 
 cudaError_t search_configure() {
-    cudaError_t e = raise_dynamic_smem(k_search_by_projection<false>, 200 * 1024);
+    cudaError_t e = raise_dynamic_smem(k_search_by_projection<false>, kSearchSmemBudget);
     if (e != cudaSuccess) return e;
-    return raise_dynamic_smem(k_search_by_projection<true>, 200 * 1024);
+    return raise_dynamic_smem(k_search_by_projection<true>, kSearchSmemBudget);
 }
 
 void launch_search_by_projection(const Buffers& b, int image, int K, const GridParams& p, const orbx_proj_query* queries, int nq, int useURight, int checkOrientation,
                                  int thHigh, const uint8_t* taken0, int candCap, int stageDesc, int* outMatch, int* outInfo, cudaStream_t s, int image2, const uint8_t* side) {
-    k_search_by_projection<false><<<1, ST, search_smem_bytes(K, nq, candCap, stageDesc, image2 >= 0 ? 2 : 1), s>>>(b, image, K, p, queries, nq, useURight, checkOrientation,
+    k_search_by_projection<false><<<1, ST, search_smem_bytes(K, nq, candCap, stageDesc, image2 >= 0 ? 2 : 1, 0), s>>>(b, image, K, p, queries, nq, useURight, checkOrientation,
                                                                                                                   thHigh, 0.f, taken0, candCap, stageDesc, outMatch, outInfo,
                                                                                                                   image2, side, nullptr);
 }
@@ -355,7 +355,7 @@ void launch_search_by_projection(const Buffers& b, int image, int K, const GridP
 void launch_search_local_points(const Buffers& b, int image, int K, const GridParams& p, const orbx_proj_query* queries, int nq, int useURight, int thHigh, float nnRatio,
                                 const uint8_t* taken0, int candCap, int stageDesc, int* outMatch, int* outInfo, cudaStream_t s, int image2, const uint8_t* side,
                                 const int* links) {
-    k_search_by_projection<true><<<1, ST, search_smem_bytes(K, nq, candCap, stageDesc, image2 >= 0 ? 2 : 1), s>>>(b, image, K, p, queries, nq, useURight, 0, thHigh, nnRatio,
+    k_search_by_projection<true><<<1, ST, search_smem_bytes(K, nq, candCap, stageDesc, image2 >= 0 ? 2 : 1, links ? 1 : 0), s>>>(b, image, K, p, queries, nq, useURight, 0, thHigh, nnRatio,
                                                                                                                  taken0, candCap, stageDesc, outMatch, outInfo, image2, side,
                                                                                                                  links);
 }
