@@ -124,7 +124,7 @@ def test_single_image_handle_frame_compute_bow(tmp_path):
     voc.loadFromTextFile(path)
     ex = T.ORBextractor(1000, 1.2, 8, 20, 7)
     _, kps, desc = ex(po.synth_v1(752, 480, 9))
-    b = ex.batch()
+    b = ex.batch
     b.compute_bow(voc, 1, 4)
     same(b.download_bow(1)[0], ora.transform(desc, 4), ("single",))
     same(voc.transform(desc, 4), ora.transform(desc, 4), ("host",))
