@@ -123,6 +123,32 @@ constexpr int SA_BYTES = 1536;   // stage stride of the moment phase (one 48 x 3
 constexpr int NA = 2;            // patch stages = the lane parity of the issuing lane (three or four stages in the same memory measured slower: 10.3 vs 9.6 ms)
 static_assert(NA * SA_BYTES <= 2 * ST_BYTES && PA_BYTES <= SA_BYTES, "moment stages");
 
+// barrier waits on a 32-bit shared-window address (kept in a register; through generic pointers ptxas re-derives the window base, S2UR + ULEA,
+// at every use: 7 % of the kernel's stall samples in the r02h profile)
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+    for (int spin = 0;; ++spin) {
+        uint32_t ok;
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return;
+        if (spin > (1 << 22)) __trap();
+    }
+}
+
+// the same for the box issue and the small per-keypoint records: everything in the loops addresses shared memory by register
+__device__ __forceinline__ void tma_issue_a(uint32_t dst, const CUtensorMap* map, uint32_t bar, uint32_t bytes, int c0, int c1, int c2) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst), "l"(map), "r"(bar),
+                 "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ KpWork lds_work(uint32_t a) {
+    uint32_t lo, hi;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(a));
+    KpWork w;
+    w.x = (short)(lo & 0xFFFFu); w.y = (short)(lo >> 16); w.level = (short)(hi & 0xFFFFu); w.dst = (short)(hi >> 16);
+    return w;
+}
+
 __device__ __forceinline__ int dp4a_us(uint32_t pix, uint32_t wgt, int acc) {  // unsigned pixels x signed weights
     int d;
     asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(pix), "r"(wgt), "r"(acc));
@@ -154,8 +180,14 @@ __global__ void __launch_bounds__(32 * DW) k_describe(const __grid_constant__ Ge
     const int k0 = kBase + wid * KPW;
     const int cnt = max(0, min(KPW, n - k0));
     unsigned char* stage = dsm + (size_t)wid * 2 * ST_BYTES;
-    const KpWork* work = wks + wid * KPW;
+    const int wk0 = wid * KPW;   // this warp's work items: wks[wk0 + i] (indexed, not through a pointer: the address stays a shared-window constant)
     uint32_t phbits = 0;  // bit s = parity of stage barrier s (uniform per warp)
+    // shared-window addresses of the warp's stages and barriers, through a shuffle so that ptxas keeps them in registers
+    const uint32_t stageS = __shfl_sync(0xFFFFFFFFu, smem_u32(stage), 0);
+    const uint32_t barS = __shfl_sync(0xFFFFFFFFu, smem_u32(&bars[wid][0]), 0);
+    const uint32_t wksS = __shfl_sync(0xFFFFFFFFu, smem_u32(&wks[wk0]), 0);
+    const uint32_t rotS = __shfl_sync(0xFFFFFFFFu, smem_u32(&rot[wk0]), 0);
+    const uint32_t momS = __shfl_sync(0xFFFFFFFFu, smem_u32(&mom[wk0][0]), 0);
 
     // Lane j owns the box loads of the warp's keypoint j: the box coordinates and the tensor-map offset are computed once for
     // all eight keypoints (SIMD) and stay in the lane's registers, the stage is the lane's parity, and an issue is a one-lane
@@ -163,15 +195,13 @@ __global__ void __launch_bounds__(32 * DW) k_describe(const __grid_constant__ Ge
     const KpWork myWk = wks[wid * KPW + (lane & (KPW - 1))];
     const int myLvOff = (int)myWk.level * (int)sizeof(CUtensorMap);
     const int myAx = (kMarginX + myWk.x - kHalfPatch) & ~15, myBx = (kMarginX + myWk.x - 18) & ~15, myAy = kMarginY + myWk.y - kHalfPatch;
-    uint64_t* const myBar = &bars[wid][lane & 1];
-    unsigned char* const myStageA = stage + (lane & 1) * SA_BYTES;
-    unsigned char* const myStageB = stage + (lane & 1) * ST_BYTES;
+    const uint32_t myBar = barS + 8u * (lane & 1);
+    const uint32_t myStageA = stageS + (lane & 1) * SA_BYTES, myStageB = stageS + (lane & 1) * ST_BYTES;
     auto issueB = [&](int i) {  // executed by lane i only
-        mbar_arrive_expect_tx(myBar, PB_BYTES);
-        tma_load_3d(myStageB, reinterpret_cast<const CUtensorMap*>(reinterpret_cast<const char*>(&maps.bl[0]) + myLvOff), myBar, myBx, myAy - 3, img);
+        tma_issue_a(myStageB, reinterpret_cast<const CUtensorMap*>(reinterpret_cast<const char*>(&maps.bl[0]) + myLvOff), myBar, PB_BYTES, myBx, myAy - 3, img);
     };
     auto wait_stage = [&](int st) {
-        mbar_wait(&bars[wid][st], (phbits >> st) & 1u);
+        mbar_wait_a(barS + 8u * (uint32_t)st, (phbits >> st) & 1u);
         phbits ^= 1u << st;
     };
 
@@ -194,19 +224,23 @@ __global__ void __launch_bounds__(32 * DW) k_describe(const __grid_constant__ Ge
             wu[c] = a; w1[c] = o;
         }
         auto issueMyA = [&]() {
-            mbar_arrive_expect_tx(myBar, PA_BYTES);
-            tma_load_3d(myStageA, reinterpret_cast<const CUtensorMap*>(reinterpret_cast<const char*>(&maps.ic[0]) + myLvOff), myBar, myAx, myAy, img);
+            tma_issue_a(myStageA, reinterpret_cast<const CUtensorMap*>(reinterpret_cast<const char*>(&maps.ic[0]) + myLvOff), myBar, PA_BYTES, myAx, myAy, img);
         };
         if (lane == 0 && cnt > 0) issueMyA();
+        const uint32_t rowOff = (uint32_t)(lane < 31 ? lane : 0) * PA_ROW;
         int st = 0;  // stage of keypoint i
         for (int i = 0; i < cnt; ++i) {
             if (lane == i + 1 && i + 1 < cnt) issueMyA();
-            const int sa = (kMarginX + work[i].x - kHalfPatch) & 15;  // patch column -15 sits at byte sa of the box row
+            const int sa = (kMarginX + lds_work(wksS + 8u * (uint32_t)i).x - kHalfPatch) & 15;  // patch column -15 sits at byte sa of the box row
             wait_stage(st);
             // the whole 48-byte box row as three 128-bit loads (conflict-free at this stride), then a warp-uniform word offset
-            const uint4* rowp = reinterpret_cast<const uint4*>(stage + st * SA_BYTES + (lane < 31 ? lane : 0) * PA_ROW);
-            const uint4 q0 = rowp[0], q1 = rowp[1], q2 = rowp[2];
-            const uint32_t rw[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+            uint32_t rw[12];
+            {
+                const uint32_t a = stageS + (uint32_t)st * SA_BYTES + rowOff;
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(rw[0]), "=r"(rw[1]), "=r"(rw[2]), "=r"(rw[3]) : "r"(a));
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+16];" : "=r"(rw[4]), "=r"(rw[5]), "=r"(rw[6]), "=r"(rw[7]) : "r"(a));
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+32];" : "=r"(rw[8]), "=r"(rw[9]), "=r"(rw[10]), "=r"(rw[11]) : "r"(a));
+            }
             const int bs = (sa & 3) * 8;
             int m10 = 0, s1 = 0;
             auto reduce_row = [&](auto W0) {
@@ -230,7 +264,7 @@ __global__ void __launch_bounds__(32 * DW) k_describe(const __grid_constant__ Ge
                 m10 += __shfl_xor_sync(0xFFFFFFFFu, m10, o);
                 m01 += __shfl_xor_sync(0xFFFFFFFFu, m01, o);
             }
-            if (lane == 0) { mom[wid * KPW + i][0] = m01; mom[wid * KPW + i][1] = m10; }
+            if (lane == 0) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(momS + 8u * (uint32_t)i), "r"(m01), "r"(m10) : "memory");
             __syncwarp();  // every lane is done with this stage before lane 0 re-arms it
             st = st + 1 == NA ? 0 : st + 1;
         }
@@ -256,14 +290,14 @@ __global__ void __launch_bounds__(32 * DW) k_describe(const __grid_constant__ Ge
 #pragma unroll
     for (int bit = 0; bit < 8; ++bit) pq[bit] = pat4[bit * 32 + lane];
     for (int i = 0; i < cnt; ++i) {
-        const KpWork wk = work[i];
-        const float2 sc = rot[wid * KPW + i];
-        const float sn = sc.x, cs = sc.y;
+        const KpWork wk = lds_work(wksS + 8u * (uint32_t)i);
+        float sn, cs;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(sn), "=f"(cs) : "r"(rotS + 8u * (uint32_t)i));
         wait_stage(i & 1);
-        // sample index r * 64 + c from the biased float bits (bias B = 0x4B400000 each), in wrap-around 32-bit arithmetic
-        const unsigned char* cb = stage + (i & 1) * ST_BYTES + 18 * PB_ROW + 18 + ((kMarginX + wk.x - 18) & 15);
+        // sample index r * PB_ROW + c from the biased float bits (bias B = 0x4B400000 each), in wrap-around 32-bit arithmetic
         const uint32_t BIAS = (uint32_t)(0x4B400000ull * (PB_ROW + 1));
-        const uint32_t cbK = smem_u32(cb) - BIAS;  // the window centre's shared address with both float biases taken off
+        // the window centre's shared address with both float biases taken off
+        const uint32_t cbK = stageS + (uint32_t)(i & 1) * ST_BYTES + (18 * PB_ROW + 18) + (uint32_t)((kMarginX + wk.x - 18) & 15) - BIAS;
         int val = 0;
 #pragma unroll
         for (int bit = 0; bit < 8; ++bit) {

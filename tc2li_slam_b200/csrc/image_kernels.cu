@@ -416,28 +416,22 @@ constexpr int BLUR_BOXW = 144;                  // 4 halo bytes + 128 pixels + 4
 constexpr int BLUR_BOXH = 32;                   // input rows per TMA box (= lanes: the edge mirroring handles one box row per lane)
 constexpr int BLUR_BOX_BYTES = BLUR_BOXW * BLUR_BOXH;  // 4608 = 36 x 128
 
+struct BlurTaps { uint32_t cA, cB, c67, c56, c45, c34, c23, c12, c01, c0x; };
+
+// one warp: output rows [rowBeg, rowBeg + nRows) of the 128-pixel column strip `strip` of image `imgAbs` (dst = that image's pixel (0, 0) of the blurred level)
 template <bool SAT>
-__global__ void __launch_bounds__(32 * BLUR_WARPS) k_blur(const __grid_constant__ CUtensorMap srcMap, uint8_t* __restrict__ dst, int w, int h, int pitch,
-                                                         size_t plane, int imgBase, int nStrips, int nWarps, uint32_t cA, uint32_t cB, uint32_t c67,
-                                                         uint32_t c56, uint32_t c45, uint32_t c34, uint32_t c23, uint32_t c12, uint32_t c01, uint32_t c0x) {
+__device__ __forceinline__ void blur_strip(const CUtensorMap* srcMap, uint8_t* __restrict__ dst, int w, int pitch, int strip, int imgAbs, int rowBeg, int nRows,
+                                           unsigned char (*tileW)[BLUR_BOX_BYTES], uint64_t* barW, uint32_t cA, uint32_t cB, uint32_t c67, uint32_t c56, uint32_t c45,
+                                           uint32_t c34, uint32_t c23, uint32_t c12, uint32_t c01, uint32_t c0x) {
     // A warp owns one 128-pixel column strip of one image and walks it top to bottom.  Its input arrives as TMA boxes of
     // 144 bytes x 32 rows, double buffered: the next box is in flight while the current one is filtered, so ~9 KB per warp
     // are outstanding (three 128-byte loads per warp would leave HBM two thirds idle at this occupancy), and the running
     // column sums carry across boxes, so there is no per-segment warm-up.
-    __shared__ __align__(128) unsigned char tile[BLUR_WARPS][2][BLUR_BOX_BYTES];
-    __shared__ __align__(8) uint64_t bars[BLUR_WARPS][2];
-    const int wy = threadIdx.y;
-    if (threadIdx.x == 0) { mbar_init(&bars[wy][0], 1); mbar_init(&bars[wy][1], 1); }
-    mbar_fence_init();
-    __syncwarp();
-    const int gw = blockIdx.x * BLUR_WARPS + wy;
-    if (gw >= nWarps) return;   // whole warp
-    const int imgRel = gw / nStrips, strip = gw - imgRel * nStrips;
     const int x0 = (strip * 32 + threadIdx.x) * 4;
-    const int nChunks = (h + 6 + BLUR_BOXH - 1) / BLUR_BOXH;
-    auto issue = [&](int c) {  // box origin: byte kMarginX + x - 4 = 128 * strip (16-byte aligned), plane row kMarginY + (32c - 3) = 32c
-        mbar_arrive_expect_tx(&bars[wy][c & 1], BLUR_BOX_BYTES);
-        tma_load_3d(tile[wy][c & 1], &srcMap, &bars[wy][c & 1], strip * 128, c * BLUR_BOXH, imgBase + imgRel);
+    const int nChunks = (nRows + 6 + BLUR_BOXH - 1) / BLUR_BOXH;
+    auto issue = [&](int c) {  // box origin: byte kMarginX + x - 4 = 128 * strip (16-byte aligned), plane row kMarginY + (rowBeg + 32c - 3) = rowBeg + 32c
+        mbar_arrive_expect_tx(&barW[c & 1], BLUR_BOX_BYTES);
+        tma_load_3d(tileW[c & 1], srcMap, &barW[c & 1], strip * 128, rowBeg + c * BLUR_BOXH, imgAbs);
     };
     if (threadIdx.x == 0) {
         issue(0);
@@ -449,7 +443,7 @@ __global__ void __launch_bounds__(32 * BLUR_WARPS) k_blur(const __grid_constant_
     const bool edgeL = strip == 0;
     const int eR = 4 + w - strip * 128;
     const bool edgeR = eR < BLUR_BOXW - 8;  // the filter reads box bytes 1 .. 134
-    uint8_t* D = dst + (size_t)imgRel * plane + x0;
+    uint8_t* D = dst + (ptrdiff_t)rowBeg * pitch + x0;
     uint32_t ph0 = 0, ph1 = 0;
     // Column pass two input rows at a time: P = (h[y], h[y+1]) as 16x2 lanes, and the pair's contribution to the eight output
     // rows y-3 .. y+4 is one IDP.2A each against the tap pairs (t6,0) (t5,t6) (t4,t5) (t3,t4) (t2,t3) (t1,t2) (t0,t1) (0,t0).
@@ -491,15 +485,15 @@ __global__ void __launch_bounds__(32 * BLUR_WARPS) k_blur(const __grid_constant_
         }
         const uint32_t out0 = __byte_perm(__byte_perm(o0[0], o0[1], 0x0062), __byte_perm(o0[2], o0[3], 0x0062), 0x5410);
         const uint32_t out1 = __byte_perm(__byte_perm(o1[0], o1[1], 0x0062), __byte_perm(o1[2], o1[3], 0x0062), 0x5410);
-        if ((unsigned)(y - 3) < (unsigned)h) *reinterpret_cast<uint32_t*>(Drow) = out0;
-        if ((unsigned)(y - 2) < (unsigned)h) *reinterpret_cast<uint32_t*>(Drow + pitch) = out1;
+        if ((unsigned)(y - 3) < (unsigned)nRows) *reinterpret_cast<uint32_t*>(Drow) = out0;   // y: input row relative to rowBeg
+        if ((unsigned)(y - 2) < (unsigned)nRows) *reinterpret_cast<uint32_t*>(Drow + pitch) = out1;
         Drow += 2 * (ptrdiff_t)pitch;
     };
     for (int c = 0; c < nChunks; ++c) {
-        if (c & 1) { mbar_wait(&bars[wy][1], ph1); ph1 ^= 1; }
-        else { mbar_wait(&bars[wy][0], ph0); ph0 ^= 1; }
+        if (c & 1) { mbar_wait(&barW[1], ph1); ph1 ^= 1; }
+        else { mbar_wait(&barW[0], ph0); ph0 ^= 1; }
         if (edgeL | edgeR) {  // warp-uniform: mirror the three pixels beyond the left / right image edge inside the box, lane = box row
-            unsigned char* row = tile[wy][c & 1] + threadIdx.x * BLUR_BOXW;
+            unsigned char* row = tileW[c & 1] + threadIdx.x * BLUR_BOXW;
             if (edgeL) reinterpret_cast<uint32_t*>(row)[0] = __byte_perm(reinterpret_cast<const uint32_t*>(row)[1], 0, 0x1230);  // [pad, p3, p2, p1] in front of p0
             if (edgeR) {
 #pragma unroll
@@ -510,8 +504,8 @@ __global__ void __launch_bounds__(32 * BLUR_WARPS) k_blur(const __grid_constant_
             __syncwarp();
         }
         if (active) {
-            const uint32_t* T = reinterpret_cast<const uint32_t*>(tile[wy][c & 1]) + threadIdx.x;  // word 0 = pixels x0-4..x0-1
-            const int yb = c * BLUR_BOXH - 3;  // image row of box row 0
+            const uint32_t* T = reinterpret_cast<const uint32_t*>(tileW[c & 1]) + threadIdx.x;  // word 0 = pixels x0-4..x0-1
+            const int yb = c * BLUR_BOXH - 3;  // row of box row 0, relative to rowBeg
 #pragma unroll 2
             for (int k = 0; k < BLUR_BOXH; k += 2) {
                 const uint32_t* r0 = T + k * (BLUR_BOXW / 4);
@@ -524,21 +518,102 @@ __global__ void __launch_bounds__(32 * BLUR_WARPS) k_blur(const __grid_constant_
     }
 }
 
+
+template <bool SAT>
+__global__ void __launch_bounds__(32 * BLUR_WARPS) k_blur(const __grid_constant__ CUtensorMap srcMap, uint8_t* __restrict__ dst, int w, int h, int pitch,
+                                                         size_t plane, int imgBase, int nStrips, int nWarps, const __grid_constant__ BlurTaps t) {
+    __shared__ __align__(128) unsigned char tile[BLUR_WARPS][2][BLUR_BOX_BYTES];
+    __shared__ __align__(8) uint64_t bars[BLUR_WARPS][2];
+    const int wy = threadIdx.y;
+    if (threadIdx.x == 0) { mbar_init(&bars[wy][0], 1); mbar_init(&bars[wy][1], 1); }
+    mbar_fence_init();
+    __syncwarp();
+    const int gw = blockIdx.x * BLUR_WARPS + wy;
+    if (gw >= nWarps) return;   // whole warp
+    const int imgRel = gw / nStrips, strip = gw - imgRel * nStrips;
+    blur_strip<SAT>(&srcMap, dst + (size_t)imgRel * plane, w, pitch, strip, imgBase + imgRel, 0, h, tile[wy], bars[wy], t.cA, t.cB, t.c67, t.c56, t.c45, t.c34, t.c23,
+                    t.c12, t.c01, t.c0x);
+}
+
+// All levels of a FEW images in one launch (the single-image handle: Frame's two extractor calls): eight dependent launches of a handful of
+// warps each are pure launch latency, and a warp walking a whole strip top to bottom is serial.  Here a warp = (level, image, strip, row segment);
+// a segment re-reads the six rows of filter support above / below it, nothing else changes.
+struct BlurAllLevels {
+    CUtensorMap m[ORBX_MAX_LEVELS];
+    unsigned long long dstOff[ORBX_MAX_LEVELS], plane[ORBX_MAX_LEVELS];
+    int w[ORBX_MAX_LEVELS], h[ORBX_MAX_LEVELS], pitch[ORBX_MAX_LEVELS], nStrips[ORBX_MAX_LEVELS], nSegs[ORBX_MAX_LEVELS], segRows[ORBX_MAX_LEVELS];
+    int warpEnd[ORBX_MAX_LEVELS];   // running total of warps up to and including the level
+    int nlevels, imgBase;
+};
+
+template <bool SAT>
+__global__ void __launch_bounds__(32 * BLUR_WARPS) k_blur_all(const __grid_constant__ BlurAllLevels lv, uint8_t* __restrict__ blur, const __grid_constant__ BlurTaps t) {
+    __shared__ __align__(128) unsigned char tile[BLUR_WARPS][2][BLUR_BOX_BYTES];
+    __shared__ __align__(8) uint64_t bars[BLUR_WARPS][2];
+    const int wy = threadIdx.y;
+    if (threadIdx.x == 0) { mbar_init(&bars[wy][0], 1); mbar_init(&bars[wy][1], 1); }
+    mbar_fence_init();
+    __syncwarp();
+    int gw = blockIdx.x * BLUR_WARPS + wy;
+    if (gw >= lv.warpEnd[lv.nlevels - 1]) return;   // whole warp
+    int level = 0;
+    while (gw >= lv.warpEnd[level]) ++level;
+    if (level) gw -= lv.warpEnd[level - 1];
+    const int perImage = lv.nStrips[level] * lv.nSegs[level];
+    const int imgRel = gw / perImage, rem = gw - imgRel * perImage;
+    const int seg = rem / lv.nStrips[level], strip = rem - seg * lv.nStrips[level];
+    const int rowBeg = seg * lv.segRows[level], nRows = min(lv.segRows[level], lv.h[level] - rowBeg);
+    blur_strip<SAT>(&lv.m[level], blur + lv.dstOff[level] + (size_t)imgRel * lv.plane[level], lv.w[level], lv.pitch[level], strip, lv.imgBase + imgRel, rowBeg, nRows,
+                    tile[wy], bars[wy], t.cA, t.cB, t.c67, t.c56, t.c45, t.c34, t.c23, t.c12, t.c01, t.c0x);
+}
+
+static BlurTaps make_blur_taps(const int taps[7], int* sum) {
+    BlurTaps t;
+    t.cA = (uint32_t)taps[0] | ((uint32_t)taps[1] << 8) | ((uint32_t)taps[2] << 16) | ((uint32_t)taps[3] << 24);
+    t.cB = (uint32_t)taps[4] | ((uint32_t)taps[5] << 8) | ((uint32_t)taps[6] << 16);
+    *sum = 0;
+    for (int i = 0; i < 7; ++i) *sum += taps[i];
+    auto pr = [&](int lo, int hi) { return (uint32_t)(lo < 0 || lo > 6 ? 0 : taps[lo]) | ((uint32_t)(hi < 0 || hi > 6 ? 0 : taps[hi]) << 8); };
+    t.c67 = pr(6, 7); t.c56 = pr(5, 6); t.c45 = pr(4, 5); t.c34 = pr(3, 4); t.c23 = pr(2, 3); t.c12 = pr(1, 2); t.c01 = pr(0, 1); t.c0x = pr(-1, 0);
+    return t;
+}
+
 void launch_blur(const Geom& g, const Buffers& b, const LevelMaps& maps, int level, int nImages, const int taps[7], cudaStream_t s) {
     const LevelGeom& L = g.lv[level];
-    const uint32_t cA = (uint32_t)taps[0] | ((uint32_t)taps[1] << 8) | ((uint32_t)taps[2] << 16) | ((uint32_t)taps[3] << 24);
-    const uint32_t cB = (uint32_t)taps[4] | ((uint32_t)taps[5] << 8) | ((uint32_t)taps[6] << 16);
-    int sum = 0;
-    for (int i = 0; i < 7; ++i) sum += taps[i];
+    int sum;
+    const BlurTaps t = make_blur_taps(taps, &sum);
     const int nStrips = (L.w + 127) / 128, nWarps = nStrips * nImages;
     dim3 grid((nWarps + BLUR_WARPS - 1) / BLUR_WARPS), block(32, BLUR_WARPS);
     const size_t o = (size_t)L.planeOff + (size_t)b.imgBase * L.planeBytes;
-    auto pr = [&](int lo, int hi) { return (uint32_t)(lo < 0 || lo > 6 ? 0 : taps[lo]) | ((uint32_t)(hi < 0 || hi > 6 ? 0 : taps[hi]) << 8); };
-    const uint32_t c67 = pr(6, 7), c56 = pr(5, 6), c45 = pr(4, 5), c34 = pr(3, 4), c23 = pr(2, 3), c12 = pr(1, 2), c01 = pr(0, 1), c0x = pr(-1, 0);
     if (sum > 256)
-        k_blur<true><<<grid, block, 0, s>>>(maps.m[level], b.blur + o, L.w, L.h, L.pitch, (size_t)L.planeBytes, b.imgBase, nStrips, nWarps, cA, cB, c67, c56, c45, c34, c23, c12, c01, c0x);
+        k_blur<true><<<grid, block, 0, s>>>(maps.m[level], b.blur + o, L.w, L.h, L.pitch, (size_t)L.planeBytes, b.imgBase, nStrips, nWarps, t);
     else
-        k_blur<false><<<grid, block, 0, s>>>(maps.m[level], b.blur + o, L.w, L.h, L.pitch, (size_t)L.planeBytes, b.imgBase, nStrips, nWarps, cA, cB, c67, c56, c45, c34, c23, c12, c01, c0x);
+        k_blur<false><<<grid, block, 0, s>>>(maps.m[level], b.blur + o, L.w, L.h, L.pitch, (size_t)L.planeBytes, b.imgBase, nStrips, nWarps, t);
+}
+
+// every level of images [imgBase, imgBase + nImages) in ONE launch; segRows = output rows per warp (a multiple of 2)
+void launch_blur_all(const Geom& g, const Buffers& b, const LevelMaps& maps, int nImages, const int taps[7], int segRows, cudaStream_t s) {
+    int sum;
+    const BlurTaps t = make_blur_taps(taps, &sum);
+    BlurAllLevels lv;
+    int total = 0;
+    for (int l = 0; l < g.nlevels; ++l) {
+        const LevelGeom& L = g.lv[l];
+        lv.m[l] = maps.m[l];
+        lv.dstOff[l] = L.planeOff + (unsigned long long)b.imgBase * L.planeBytes;
+        lv.plane[l] = L.planeBytes;
+        lv.w[l] = L.w; lv.h[l] = L.h; lv.pitch[l] = L.pitch;
+        lv.nStrips[l] = (L.w + 127) / 128;
+        lv.segRows[l] = segRows;
+        lv.nSegs[l] = (L.h + segRows - 1) / segRows;
+        total += lv.nStrips[l] * lv.nSegs[l] * nImages;
+        lv.warpEnd[l] = total;
+    }
+    for (int l = g.nlevels; l < ORBX_MAX_LEVELS; ++l) lv.warpEnd[l] = total;
+    lv.nlevels = g.nlevels; lv.imgBase = b.imgBase;
+    dim3 grid((total + BLUR_WARPS - 1) / BLUR_WARPS), block(32, BLUR_WARPS);
+    if (sum > 256) k_blur_all<true><<<grid, block, 0, s>>>(lv, b.blur, t);
+    else k_blur_all<false><<<grid, block, 0, s>>>(lv, b.blur, t);
 }
 
 int blur_encode_maps(const Geom& g, uint8_t* pyr, int nImages, LevelMaps* out) {

@@ -684,10 +684,19 @@ static int run_range_lane(orbx_batch* b, int first, int n, const int* lapping, i
     // FAST -> quadtree and the blur both depend only on the pyramid: the blur goes to the side stream unless per-stage
     // timing was requested (then everything is serialised on one stream so that the events bracket single stages)
     const bool overlap = !b->timing || lane != 0;
+    // a few images (the single-image handle): every level in ONE launch, strips cut into row segments so that the handful of warps becomes a
+    // few hundred; many images: one launch per level (each already fills the machine, and whole strips have no re-read rows)
+    int sumStrips = 0;
+    for (int l = 0; l < g.nlevels; ++l) sumStrips += (g.lv[l].w + 127) / 128;
+    const int blurSeg = (long long)n * sumStrips <= 256 ? 64 : (long long)n * sumStrips <= 512 ? 128 : 0;
+    auto issue_blur = [&](cudaStream_t st) {
+        if (blurSeg) { launch_blur_all(g, buf, b->blurMaps, n, b->taps, blurSeg, st); ++launches; }
+        else for (int l = 0; l < g.nlevels; ++l) { launch_blur(g, buf, b->blurMaps, l, n, b->taps, st); ++launches; }
+    };
     auto blur_on_side = [&]() -> int {
         CU(cudaEventRecord(evPyr, s));
         CU(cudaStreamWaitEvent(side, evPyr, 0));
-        for (int l = 0; l < g.nlevels; ++l) { launch_blur(g, buf, b->blurMaps, l, n, b->taps, side); ++launches; }
+        issue_blur(side);
         CU(cudaEventRecord(evBlur, side));
         return ORBX_OK;
     };
@@ -697,13 +706,12 @@ static int run_range_lane(orbx_batch* b, int first, int n, const int* lapping, i
     launch_fast(g, buf, b->fastMaps, n, b->fastTileRows, b->fastTs, b->numSMs, s); ++launches;
     if (overlap && b->sched == 1) {  // the blur is enqueued after FAST but still only waits for the pyramid
         CU(cudaStreamWaitEvent(side, evPyr, 0));
-        for (int l = 0; l < g.nlevels; ++l) { launch_blur(g, buf, b->blurMaps, l, n, b->taps, side); ++launches; }
+        issue_blur(side);
         CU(cudaEventRecord(evBlur, side));
     }
     if (overlap && b->sched == 2) { int r = blur_on_side(); if (r) return r; }  // the blur waits for FAST: it runs beside the quadtree only
     mark();
-    if (!overlap)
-        for (int l = 0; l < g.nlevels; ++l) { launch_blur(g, buf, b->blurMaps, l, n, b->taps, s); ++launches; }
+    if (!overlap) issue_blur(s);
     mark();
     {
         cudaError_t e = launch_octree(g, buf, n, b->numSMs, s); launches += octree_launch_count(g, n, b->numSMs);

@@ -137,6 +137,7 @@ struct LevelMaps {  // one tensor map per pyramid level
     CUtensorMap m[ORBX_MAX_LEVELS];
 };
 void launch_blur(const Geom& g, const Buffers& b, const LevelMaps& maps, int level, int nImages, const int taps[7], cudaStream_t s);
+void launch_blur_all(const Geom& g, const Buffers& b, const LevelMaps& maps, int nImages, const int taps[7], int segRows, cudaStream_t s);
 int blur_encode_maps(const Geom& g, uint8_t* pyr, int nImages, LevelMaps* out);
 void launch_pyramid_level(const Geom& g, const Buffers& b, const LevelMaps& maps, int level, const ResizeTab& tab, int nImages, cudaStream_t s);
 int resize_encode_maps(const Geom& g, uint8_t* pyr, int nImages, LevelMaps* out);
