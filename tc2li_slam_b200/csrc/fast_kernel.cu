@@ -465,7 +465,10 @@ void make_cell_table(const Geom& g, uint4* tab, int* tileRows, int* maxCw) {
 
 // box rows of 64 bytes hold crops up to 49 columns (15 alignment bytes + crop), 96 bytes up to 81 (the largest possible: 78)
 int fast_tile_stride(int maxCw) { return maxCw <= 49 ? 64 : 96; }
-static size_t fast_warp_bytes(int tileRows, int ts) { return (size_t)(NB + 1) * tileRows * ts + CAPW * 4 + 2 * CAP * 2; }
+#ifndef FAST_PAD
+#define FAST_PAD 0   // residency experiment: unused bytes of shared memory per warp
+#endif
+static size_t fast_warp_bytes(int tileRows, int ts) { return (size_t)(NB + 1) * tileRows * ts + CAPW * 4 + 2 * CAP * 2 + FAST_PAD; }
 
 cudaError_t fast_configure(int tileRows, int ts) {
     const int smem = (int)(FW * fast_warp_bytes(tileRows, ts));
