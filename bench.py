@@ -447,6 +447,34 @@ def main():
                 "assign_ms_per_step": ms_grid, "assign_images_per_s": n_img / (ms_grid * 1e-3), "area_queries": nq,
                 "area_queries_per_s_host_to_host": nq / dt_q, "mean_hits_per_query": float(qc.mean())}
 
+    # ---- supplementary: Frame::ComputeBoW on the resident descriptors (DBoW2 transform; synthetic vocabulary of ORBvoc.txt's shape: k = 10, L = 6) ----
+    bow = None
+    if not args.no_stereo:
+        k_voc, L_voc = 10, 6
+        n_nodes = (k_voc ** (L_voc + 1) - 1) // (k_voc - 1)
+        rng = np.random.default_rng(5)
+        parent = np.zeros(n_nodes, np.int32)
+        parent[1:] = (np.arange(1, n_nodes) - 1) // k_voc          # complete k-ary tree in breadth-first numbering
+        first_leaf = n_nodes - k_voc ** L_voc
+        is_word = (np.arange(n_nodes) >= first_leaf).astype(np.uint8)
+        vdesc = rng.integers(0, 256, (n_nodes, 32), dtype=np.uint8)
+        weight = np.where(is_word == 1, rng.uniform(0.5, 12.0, n_nodes), 0.0)
+        voc = T.ORBVocabulary(local).from_arrays(k_voc, L_voc, 0, 0, parent, is_word, vdesc, weight)
+        big.compute_bow(voc, n_img, 4)
+        big.sync()
+        s0, s1 = Event(big), Event(big)
+        s0.record(big)
+        for _ in range(args.steps):
+            big.compute_bow(voc, n_img, 4)
+        s1.record(big)
+        ms_bow = s0.elapsed_ms(s1) / args.steps
+        r0 = big.download_bow(1)[0]
+        bow = {"what": "orbx_batch_compute_bow (Frame::ComputeBoW, Frame.cc:768-775 = DBoW2 TemplatedVocabulary::transform, levelsup 4) on the resident descriptors; "
+                       "synthetic vocabulary k = 10, L = 6 (10^6 words, 35.6 MB of node descriptors: L2 resident); the real ORBvoc.txt is absent from the reference checkout",
+               "ms_per_step": ms_bow, "images_per_s": n_img / (ms_bow * 1e-3), "descriptors_per_s": float(counts.sum()) / (ms_bow * 1e-3),
+               "words_first_image": int(len(r0[0])), "nodes_first_image": int(len(r0[2]))}
+        voc.close()
+
     # ---- e2e: the product call.  Pinned host images -> orbx_pool_extract -> host keypoints / descriptors / counts, frame order.
     #      N = 1: a pool of this GPU.  N > 1: every rank first drives its own GPU at the same time (supplementary), then rank 0
     #      alone drives ALL N GPUs through ONE pool from one process — the multi-GPU product API — while the other ranks wait ----
@@ -640,7 +668,7 @@ def main():
             "config": {"workload": WORKLOAD,
                        "pairs_per_gpu_per_step": args.pairs, "images_per_launch_set": group, "keypoints_per_image": kp_mean,
                        "l2": f"inputs {n_img * W * H / 1e9:.2f} GB per rank, larger than the {L2_BYTES / 1e6:.0f} MB L2; no flush needed"},
-            "clocks": clocks, "numa_binding": numa, "e2e": e2e, "e2e_one_process_all_gpus": e2e_one, "parity": parity, "gpu_launches": launches_per_step, "roofline": roofline, "cpu_baseline": cpu, "stages": stages, "latency": latency, "stereo_match": stereo, "feature_grid": grid, "large_images": large, "euroc_lapping": euroc,
+            "clocks": clocks, "numa_binding": numa, "e2e": e2e, "e2e_one_process_all_gpus": e2e_one, "parity": parity, "gpu_launches": launches_per_step, "roofline": roofline, "cpu_baseline": cpu, "stages": stages, "latency": latency, "stereo_match": stereo, "feature_grid": grid, "bag_of_words": bow, "large_images": large, "euroc_lapping": euroc,
         }
         emit_line(json.dumps(line))
     big.close()
