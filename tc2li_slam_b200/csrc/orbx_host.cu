@@ -270,13 +270,19 @@ int batch_alloc(orbx_batch* b) {
     if ((r = dev_alloc(b, &B.kps, (size_t)n * g.K))) return r;
     if ((r = dev_alloc(b, &B.desc, (size_t)n * g.K * 32))) return r;
     if ((r = dev_alloc(b, &B.work, (size_t)n * g.K))) return r;
-    if ((r = dev_alloc(b, &B.outCount, (size_t)n))) return r;
-    if ((r = dev_alloc(b, &B.outMono, (size_t)n))) return r;
+    if (n == 1) {   // the single-image handle reads {count, monoIndex, error flag} back with ONE copy: keep them adjacent
+        if ((r = dev_alloc(b, &B.outCount, (size_t)4))) return r;
+        B.outMono = B.outCount + 1;
+        B.errFlag = B.outCount + 2;
+    } else {
+        if ((r = dev_alloc(b, &B.outCount, (size_t)n))) return r;
+        if ((r = dev_alloc(b, &B.outMono, (size_t)n))) return r;
+    }
     if ((r = dev_alloc(b, &B.uRight, (size_t)n * g.K))) return r;
     if ((r = dev_alloc(b, &B.depth, (size_t)n * g.K))) return r;
     if ((r = dev_alloc(b, &B.lapKnn, (size_t)n * g.K))) return r;
     if ((r = dev_alloc(b, &B.lapOk, (size_t)n * g.K))) return r;
-    if ((r = dev_alloc(b, &B.errFlag, 1))) return r;
+    if (n != 1 && (r = dev_alloc(b, &B.errFlag, 1))) return r;
     B.imgBase = 0;
     for (int l = 0; l < g.nlevels; ++l) {
         const LevelGeom& L = g.lv[l];
@@ -1550,9 +1556,7 @@ int extractor_enqueue(orbx_extractor* h, int w, int hgt) {
     const size_t K = (size_t)b->g.K;
     CU(cudaMemcpyAsync(h->pinKps, b->buf.kps, K * sizeof(orbx_keypoint), cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(h->pinDesc, b->buf.desc, K * 32, cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(h->pinCnt, b->buf.outCount, sizeof(int), cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(h->pinCnt + 1, b->buf.outMono, sizeof(int), cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(h->pinCnt + 2, b->buf.errFlag, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(h->pinCnt, b->buf.outCount, 3 * sizeof(int), cudaMemcpyDeviceToHost, s));   // count, monoIndex, error flag (adjacent in a batch of one)
     return ORBX_OK;
 }
 
