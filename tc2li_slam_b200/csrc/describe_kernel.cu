@@ -26,56 +26,61 @@ cudaError_t upload_describe_constants(const signed char pattern[1024], const int
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int AT = 1024;   // threads of k_assemble: the whole image (about 2000 keypoints) is two passes, i.e. a few microseconds of latency
-__global__ void __launch_bounds__(AT) k_assemble(const __grid_constant__ Geom g, const Buffers b) {
-    __shared__ int warpTot[AT / 32];
-    __shared__ int levelStart[ORBX_MAX_LEVELS + 1];   // encounter index of the first keypoint of every level (level-major order)
+__global__ void __launch_bounds__(256) k_assemble(const __grid_constant__ Geom g, const Buffers b) {
+    __shared__ int warpTot[8];
+    __shared__ int carry;  // keypoints outside the lapping window so far
     const int img = b.imgBase + blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int* selCount = b.selCount + img * ORBX_MAX_LEVELS;
-    if (tid == 0) {
-        int acc = 0;
-        for (int l = 0; l < g.nlevels; ++l) { levelStart[l] = acc; acc += selCount[l]; }
-        for (int l = g.nlevels; l <= ORBX_MAX_LEVELS; ++l) levelStart[l] = acc;
-    }
-    __syncthreads();
-    const int total = levelStart[g.nlevels];
+    int total = 0;
+    for (int l = 0; l < g.nlevels; ++l) total += selCount[l];
     const float lap0 = (float)b.lapping[2 * img], lap1 = (float)b.lapping[2 * img + 1];
     orbx_keypoint* kps = b.kps + (size_t)img * g.K;
     KpWork* work = b.work + (size_t)img * g.K;
-    int carry = 0;  // keypoints outside the lapping window so far (same value in every thread)
-    for (int base = 0; base < total; base += AT) {
-        const int ord = base + tid;  // encounter index
-        const bool valid = ord < total;
-        int X = 0, Y = 0, R = 0, l = 0;
-        float sx = 0.f, sy = 0.f;
-        bool inLap = false;
-        if (valid) {
-            while (ord >= levelStart[l + 1]) ++l;
-            const LevelGeom& L = g.lv[l];
-            const uint32_t pc = b.sel[(size_t)img * g.K + L.selOff + (ord - levelStart[l])];
-            X = cand_x(pc) + kBorder; Y = cand_y(pc) + kBorder; R = cand_r(pc);
-            sx = (float)X; sy = (float)Y;
-            if (l != 0) { sx = __fmul_rn(sx, L.sf); sy = __fmul_rn(sy, L.sf); }  // keypoint->pt *= scale (ORBextractor.cc:1122-1124)
-            inLap = sx >= lap0 && sx <= lap1;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    int seen = 0;  // keypoints of the previous levels
+    for (int l = 0; l < g.nlevels; ++l) {
+        const LevelGeom& L = g.lv[l];
+        const int nl = selCount[l];
+        const uint32_t* sel = b.sel + (size_t)img * g.K + L.selOff;
+        for (int base = 0; base < nl; base += 256) {
+            const int k = base + tid;
+            const bool valid = k < nl;
+            int X = 0, Y = 0, R = 0;
+            float sx = 0.f, sy = 0.f;
+            bool inLap = false;
+            if (valid) {
+                const uint32_t pc = sel[k];
+                X = cand_x(pc) + kBorder; Y = cand_y(pc) + kBorder; R = cand_r(pc);
+                sx = (float)X; sy = (float)Y;
+                if (l != 0) { sx = __fmul_rn(sx, L.sf); sy = __fmul_rn(sy, L.sf); }  // keypoint->pt *= scale (ORBextractor.cc:1122-1124)
+                inLap = sx >= lap0 && sx <= lap1;
+            }
+            const unsigned monoMask = __ballot_sync(0xFFFFFFFFu, valid && !inLap);
+            if (lane == 0) warpTot[wid] = __popc(monoMask);
+            __syncthreads();
+            int before = carry;
+            for (int w = 0; w < wid; ++w) before += warpTot[w];
+            const int monoBefore = before + __popc(monoMask & ((1u << lane) - 1));  // mono keypoints preceding this one
+            if (valid) {
+                const int ord = seen + k;  // encounter index
+                const int dst = inLap ? (total - 1 - (ord - monoBefore)) : monoBefore;
+                orbx_keypoint kp;
+                kp.x = sx; kp.y = sy; kp.size = L.kpSize; kp.angle = -1.f; kp.response = (float)R; kp.octave = l; kp.class_id = -1;
+                kps[dst] = kp;
+                KpWork wk;
+                wk.x = (short)X; wk.y = (short)Y; wk.level = (short)l; wk.dst = (short)dst;
+                work[ord] = wk;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int s = 0;
+                for (int w = 0; w < 8; ++w) s += warpTot[w];
+                carry += s;
+            }
+            __syncthreads();
         }
-        const unsigned monoMask = __ballot_sync(0xFFFFFFFFu, valid && !inLap);
-        if (lane == 0) warpTot[wid] = __popc(monoMask);
-        __syncthreads();
-        int before = carry, all = 0;
-#pragma unroll 8
-        for (int w = 0; w < AT / 32; ++w) { const int t = warpTot[w]; if (w < wid) before += t; all += t; }
-        const int monoBefore = before + __popc(monoMask & ((1u << lane) - 1));  // mono keypoints preceding this one
-        if (valid) {
-            const int dst = inLap ? (total - 1 - (ord - monoBefore)) : monoBefore;
-            orbx_keypoint kp;
-            kp.x = sx; kp.y = sy; kp.size = g.lv[l].kpSize; kp.angle = -1.f; kp.response = (float)R; kp.octave = l; kp.class_id = -1;
-            kps[dst] = kp;
-            KpWork wk;
-            wk.x = (short)X; wk.y = (short)Y; wk.level = (short)l; wk.dst = (short)dst;
-            work[ord] = wk;
-        }
-        carry += all;
-        __syncthreads();   // warpTot is rewritten by the next pass
+        seen += nl;
     }
     if (tid == 0) {
         b.outCount[img] = total;
@@ -83,7 +88,7 @@ __global__ void __launch_bounds__(AT) k_assemble(const __grid_constant__ Geom g,
     }
 }
 
-void launch_assemble(const Geom& g, const Buffers& b, int nImages, cudaStream_t s) { k_assemble<<<nImages, AT, 0, s>>>(g, b); }
+void launch_assemble(const Geom& g, const Buffers& b, int nImages, cudaStream_t s) { k_assemble<<<nImages, 256, 0, s>>>(g, b); }
 
 // ---------------------------------------------------------------------------------------------------------------
 // k_describe: a CTA of DW = 2 warps handles 64 consecutive keypoints, KPW = 32 per warp, in three phases (measured, ms per 8192 KITTI

@@ -685,17 +685,22 @@ static int run_range_lane(orbx_batch* b, int first, int n, const int* lapping, i
     auto mark = [&]() { if (b->timing && lane == 0) cudaEventRecord(b->ev[evi++], s); };
     mark();
     for (int l = 1; l < g.nlevels; ++l) { launch_pyramid_level(g, buf, b->resizeMaps, l, b->tabs[l], n, s); ++launches; }
-    launch_margin(g, buf, n, s); ++launches;
-    mark();
     // FAST -> quadtree and the blur both depend only on the pyramid: the blur goes to the side stream unless per-stage
-    // timing was requested (then everything is serialised on one stream so that the events bracket single stages)
+    // timing was requested (then everything is serialised on one stream so that the events bracket single stages).
+    // The reflect-101 margin rows are read by the blur alone (FAST and the descriptor stage stay 16 / 19 pixels inside the image),
+    // so k_margin travels with it and leaves the FAST -> quadtree -> descriptor chain.
+    // (only for a few images, where it takes a node out of the latency chain; with many images the margin kernel beside FAST cost 0.3 ms per 8192)
     const bool overlap = !b->timing || lane != 0;
+    const bool marginOnSide = overlap && n <= 16;
+    if (!marginOnSide) { launch_margin(g, buf, n, s); ++launches; }
+    mark();
     // a few images (the single-image handle): every level in ONE launch, strips cut into row segments so that the handful of warps becomes a
     // few hundred; many images: one launch per level (each already fills the machine, and whole strips have no re-read rows)
     int sumStrips = 0;
     for (int l = 0; l < g.nlevels; ++l) sumStrips += (g.lv[l].w + 127) / 128;
     const int blurSeg = (long long)n * sumStrips <= 256 ? 64 : (long long)n * sumStrips <= 512 ? 128 : 0;
     auto issue_blur = [&](cudaStream_t st) {
+        if (marginOnSide) { launch_margin(g, buf, n, st); ++launches; }
         if (blurSeg) { launch_blur_all(g, buf, b->blurMaps, n, b->taps, blurSeg, st); ++launches; }
         else for (int l = 0; l < g.nlevels; ++l) { launch_blur(g, buf, b->blurMaps, l, n, b->taps, st); ++launches; }
     };
