@@ -76,9 +76,11 @@ int orbx_set_blur_taps(orbx_extractor* h, const int taps[7]);
 int orbx_extract(orbx_extractor* h, const uint8_t* image, int width, int height, size_t stride, int lap0, int lap1,
                  orbx_keypoint* keypoints, uint8_t* descriptors, int capacity, int* n_keypoints, int* mono_index);
 
-/* replaces the two std::thread extractions of Frame::Frame (Frame.cc:139-142, 1090-1094): both images are issued on
- * the two handles' own CUDA streams before either is waited for.  lap_left / lap_right = {x0, x1} as Frame::ExtractORB
- * builds them (Frame.cc:445-455). */
+/* replaces the two std::thread extractions of Frame::Frame (Frame.cc:139-142, 1090-1094).  Handles with identical parameters (the
+ * reference builds mpORBextractorLeft / Right from the same settings) share ONE launch sequence over a batch of two images — the
+ * sequence is latency bound, so the pair costs what one image costs; otherwise both images are issued on the two handles' own CUDA
+ * streams before either is waited for.  lap_left / lap_right = {x0, x1} as Frame::ExtractORB builds them (Frame.cc:445-455).
+ * Either way orbx_get_level / orbx_stereo_match / orbx_lapping_match on the handles see this call's results. */
 int orbx_extract_stereo(orbx_extractor* left, orbx_extractor* right, const uint8_t* image_left, const uint8_t* image_right,
                         int width, int height, size_t stride_left, size_t stride_right, const int lap_left[2], const int lap_right[2],
                         orbx_keypoint* kps_left, uint8_t* desc_left, int cap_left, int* n_left, int* mono_left,
@@ -337,7 +339,10 @@ int orbx_batch_debug_candidates(orbx_batch* b, int image, int level, float* xyr,
 int orbx_batch_debug_selected(orbx_batch* b, int image, int level, float* xyr, int capacity, int* n);
 
 int orbx_batch_debug_fallback_cells(orbx_batch* b, int image, int level, int* n_fallback);
-orbx_batch* orbx_extractor_batch(orbx_extractor* h); /* the batch-of-one behind a single-image handle (NULL before the first call) */
+/* the batch that holds the results of the handle's last call (NULL before the first call): the batch-of-one of the handle after a single-image call; after
+ * orbx_extract_stereo on two handles with identical parameters the batch of TWO that served the pair (image 0 = left, image 1 = right: the layout the
+ * orbx_batch_* pair functions expect), returned for both handles */
+orbx_batch* orbx_extractor_batch(orbx_extractor* h);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Multi-GPU pool: the product form of "frames are independent, shard them by frame over the GPUs of one box, no collective"

@@ -274,6 +274,10 @@ int batch_alloc(orbx_batch* b) {
         if ((r = dev_alloc(b, &B.outCount, (size_t)4))) return r;
         B.outMono = B.outCount + 1;
         B.errFlag = B.outCount + 2;
+    } else if (n == 2) {   // the stereo-pair batch: {count[2], monoIndex[2], error flag}
+        if ((r = dev_alloc(b, &B.outCount, (size_t)8))) return r;
+        B.outMono = B.outCount + 2;
+        B.errFlag = B.outCount + 4;
     } else {
         if ((r = dev_alloc(b, &B.outCount, (size_t)n))) return r;
         if ((r = dev_alloc(b, &B.outMono, (size_t)n))) return r;
@@ -282,7 +286,7 @@ int batch_alloc(orbx_batch* b) {
     if ((r = dev_alloc(b, &B.depth, (size_t)n * g.K))) return r;
     if ((r = dev_alloc(b, &B.lapKnn, (size_t)n * g.K))) return r;
     if ((r = dev_alloc(b, &B.lapOk, (size_t)n * g.K))) return r;
-    if (n != 1 && (r = dev_alloc(b, &B.errFlag, 1))) return r;
+    if (n > 2 && (r = dev_alloc(b, &B.errFlag, 1))) return r;
     B.imgBase = 0;
     for (int l = 0; l < g.nlevels; ++l) {
         const LevelGeom& L = g.lv[l];
@@ -1494,6 +1498,21 @@ struct orbx_extractor {
     bool rectDirty = false;
     unsigned tapsGeneration = 0;  // generation of the batch's taps the graph was captured with
     int graphState = 0;  // 0: next call runs eagerly (lazy allocations), 1: capture on the next call, 2: replay `exec`, 3: capture failed, stay eager
+    // Where the results of the last call live: (vb, vi) = (b, 0) after a single-image call, (the pair batch of the left handle, 0 | 1) after
+    // orbx_extract_stereo took the pair path; vCount / vMono = N and monoIndex of that call.  Everything that reads results goes through the view.
+    orbx_batch* vb = nullptr;
+    int vi = 0, vCount = 0, vMono = 0;
+    // orbx_extract_stereo on two handles with identical parameters: ONE batch of two images, one graph, one launch sequence for the pair — the
+    // launch sequence is latency bound (a pair costs what one image costs: profiles/tools/latency_probe.py).  Owned by the LEFT handle.
+    struct Pair {
+        orbx_batch* b = nullptr;
+        uint8_t* pinImg = nullptr; size_t pinImgBytes = 0;
+        orbx_keypoint* pinKps = nullptr; uint8_t* pinDesc = nullptr; int* pinCnt = nullptr; size_t pinK = 0;  // pinCnt: count[2], mono[2], err | [8..11] lapping
+        cudaGraphExec_t exec = nullptr;
+        int graphState = 0;
+        int taps[7] = {0, 0, 0, 0, 0, 0, 0};
+    } pair;
+    orbx_extractor* peer = nullptr;   // the other handle of the pair whose view points into pair.b (cleared when either is destroyed)
 };
 
 namespace {
@@ -1617,11 +1636,145 @@ int extractor_collect(orbx_extractor* h, orbx_keypoint* kps, uint8_t* desc, int 
         return fail(ORBX_ERR_CAPACITY, "device capacity exceeded");
     }
     const int N = h->pinCnt[0];
+    h->vb = h->b; h->vi = 0; h->vCount = N; h->vMono = h->pinCnt[1];
     if (N > capacity) return fail(ORBX_ERR_CAPACITY, "output capacity smaller than the number of keypoints");
     if (kps) std::memcpy(kps, h->pinKps, (size_t)N * sizeof(orbx_keypoint));
     if (desc) std::memcpy(desc, h->pinDesc, (size_t)N * 32);
     if (n) *n = N;
     if (mono) *mono = h->pinCnt[1];
+    return ORBX_OK;
+}
+
+// ---- the pair path of orbx_extract_stereo ----
+bool pair_eligible(const orbx_extractor* l, const orbx_extractor* r) {
+    static const bool off = std::getenv("ORBX_NO_PAIR") != nullptr;
+    return !off && l->device == r->device && l->p.nfeatures == r->p.nfeatures && l->p.scaleFactorF == r->p.scaleFactorF && l->p.nlevels == r->p.nlevels &&
+           l->p.iniTh == r->p.iniTh && l->p.minTh == r->p.minTh && std::memcmp(l->taps, r->taps, sizeof(l->taps)) == 0 && l->rectW == 0 && r->rectW == 0;
+}
+
+void pair_release(orbx_extractor* h) {
+    orbx_extractor::Pair& P = h->pair;
+    if (P.exec) { cudaGraphExecDestroy(P.exec); P.exec = nullptr; }
+    if (P.b) { orbx_batch_destroy(P.b); P.b = nullptr; }
+    if (P.pinImg) cudaFreeHost(P.pinImg);
+    if (P.pinKps) cudaFreeHost(P.pinKps);
+    if (P.pinDesc) cudaFreeHost(P.pinDesc);
+    if (P.pinCnt) cudaFreeHost(P.pinCnt);
+    P = orbx_extractor::Pair();
+}
+
+int pair_enqueue(orbx_extractor* left, int w, int hgt) {
+    orbx_extractor::Pair& P = left->pair;
+    int r = orbx_batch_upload(P.b, P.pinImg, (size_t)w, (size_t)w * hgt, 0, 2);
+    if (r) return r;
+    if ((r = orbx_batch_run(P.b, 2, P.pinCnt + 8))) return r;
+    cudaStream_t s = P.b->stream;
+    const size_t K = (size_t)P.b->g.K;
+    CU(cudaMemcpyAsync(P.pinKps, P.b->buf.kps, 2 * K * sizeof(orbx_keypoint), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(P.pinDesc, P.b->buf.desc, 2 * K * 32, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(P.pinCnt, P.b->buf.outCount, 5 * sizeof(int), cudaMemcpyDeviceToHost, s));   // count[2], monoIndex[2], error flag (adjacent in a batch of two)
+    return ORBX_OK;
+}
+
+int pair_extract(orbx_extractor* left, orbx_extractor* right, const uint8_t* imL, const uint8_t* imR, int w, int hgt, size_t strideL, size_t strideR, const int lapL[2],
+                 const int lapR[2], orbx_keypoint* kpsL, uint8_t* descL, int capL, int* nL, int* monoL, orbx_keypoint* kpsR, uint8_t* descR, int capR, int* nR, int* monoR) {
+    orbx_extractor::Pair& P = left->pair;
+    DeviceGuard dg(left->device);
+    if (P.b && (P.b->width != w || P.b->height != hgt)) {
+        if (P.exec) { cudaGraphExecDestroy(P.exec); P.exec = nullptr; }
+        orbx_batch_destroy(P.b); P.b = nullptr; P.graphState = 0;
+        if (right->vb && right->peer == left) right->vb = nullptr;
+        left->vb = nullptr;
+    }
+    if (!P.b) {
+        int r = orbx_batch_create(left->p.nfeatures, left->p.scaleFactorF, left->p.nlevels, left->p.iniTh, left->p.minTh, left->device, w, hgt, 2, &P.b);
+        if (r) return r;
+        orbx_batch_set_blur_taps(P.b, left->taps);
+        std::memcpy(P.taps, left->taps, sizeof(P.taps));
+        P.b->lapStable = true;
+        P.graphState = 0;
+    }
+    if (std::memcmp(P.taps, left->taps, sizeof(P.taps)) != 0) {   // taps changed since the graph was captured (they are baked into kernel arguments)
+        orbx_batch_set_blur_taps(P.b, left->taps);
+        std::memcpy(P.taps, left->taps, sizeof(P.taps));
+        if (P.exec) { cudaGraphExecDestroy(P.exec); P.exec = nullptr; }
+        if (P.graphState == 2) P.graphState = 1;
+    }
+    const size_t need = 2 * (size_t)w * hgt, K = (size_t)P.b->g.K;
+    if (need > P.pinImgBytes) {
+        if (P.pinImg) cudaFreeHost(P.pinImg);
+        P.pinImg = nullptr; P.pinImgBytes = 0;
+        CU(cudaHostAlloc((void**)&P.pinImg, need, cudaHostAllocDefault));
+        P.pinImgBytes = need;
+        if (P.exec) { cudaGraphExecDestroy(P.exec); P.exec = nullptr; }
+        if (P.graphState == 2) P.graphState = 1;
+    }
+    if (K > P.pinK) {
+        if (P.pinKps) cudaFreeHost(P.pinKps);
+        if (P.pinDesc) cudaFreeHost(P.pinDesc);
+        if (P.pinCnt) cudaFreeHost(P.pinCnt);
+        P.pinKps = nullptr; P.pinDesc = nullptr; P.pinCnt = nullptr; P.pinK = 0;
+        CU(cudaHostAlloc((void**)&P.pinKps, 2 * K * sizeof(orbx_keypoint), cudaHostAllocDefault));
+        CU(cudaHostAlloc((void**)&P.pinDesc, 2 * K * 32, cudaHostAllocDefault));
+        CU(cudaHostAlloc((void**)&P.pinCnt, 16 * sizeof(int), cudaHostAllocDefault));
+        P.pinK = K;
+        if (P.exec) { cudaGraphExecDestroy(P.exec); P.exec = nullptr; }
+        if (P.graphState == 2) P.graphState = 1;
+    }
+    const size_t plane = (size_t)w * hgt;
+    if (strideL == (size_t)w) std::memcpy(P.pinImg, imL, plane);
+    else for (int y = 0; y < hgt; ++y) std::memcpy(P.pinImg + (size_t)y * w, imL + (size_t)y * strideL, (size_t)w);
+    if (strideR == (size_t)w) std::memcpy(P.pinImg + plane, imR, plane);
+    else for (int y = 0; y < hgt; ++y) std::memcpy(P.pinImg + plane + (size_t)y * w, imR + (size_t)y * strideR, (size_t)w);
+    P.pinCnt[8] = lapL[0]; P.pinCnt[9] = lapL[1]; P.pinCnt[10] = lapR[0]; P.pinCnt[11] = lapR[1];
+    orbx_batch* b = P.b;
+    static const bool noGraph = std::getenv("ORBX_NO_GRAPH") != nullptr;
+    int r = ORBX_OK;
+    if (noGraph || b->timing || b->stream != b->own || P.graphState == 0 || P.graphState == 3) {
+        if (P.graphState == 0) P.graphState = 1;   // first call eager: lazy allocations happen here
+        r = pair_enqueue(left, w, hgt);
+    } else {
+        if (P.graphState == 1) {
+            cudaGraph_t graph = nullptr;
+            CU(cudaStreamBeginCapture(b->stream, cudaStreamCaptureModeThreadLocal));
+            r = pair_enqueue(left, w, hgt);
+            const cudaError_t e = cudaStreamEndCapture(b->stream, &graph);
+            cudaError_t e2 = cudaErrorUnknown;
+            if (r == ORBX_OK && e == cudaSuccess && graph) e2 = cudaGraphInstantiate(&P.exec, graph, 0);
+            if (graph) cudaGraphDestroy(graph);
+            if (e2 != cudaSuccess) {
+                P.exec = nullptr;
+                P.graphState = 3;
+                cudaGetLastError();
+                r = pair_enqueue(left, w, hgt);
+            } else {
+                P.graphState = 2;
+                r = ORBX_OK;
+            }
+        }
+        if (P.graphState == 2) CU(cudaGraphLaunch(P.exec, b->stream));
+    }
+    if (r) return r;
+    CU(cudaStreamSynchronize(b->stream));
+    if (P.pinCnt[4]) {
+        cudaMemsetAsync(b->buf.errFlag, 0, sizeof(int), b->stream);
+        return fail(ORBX_ERR_CAPACITY, "device capacity exceeded");
+    }
+    // the views of both handles now point into the pair batch
+    if (left->peer && left->peer != right) { left->peer->peer = nullptr; if (left->peer->vb == b) left->peer->vb = nullptr; }
+    if (right->peer && right->peer != left) { right->peer->peer = nullptr; }
+    left->peer = right; right->peer = left;
+    left->vb = b; left->vi = 0; left->vCount = P.pinCnt[0]; left->vMono = P.pinCnt[2];
+    right->vb = b; right->vi = 1; right->vCount = P.pinCnt[1]; right->vMono = P.pinCnt[3];
+    if (nL) *nL = P.pinCnt[0];
+    if (monoL) *monoL = P.pinCnt[2];
+    if (nR) *nR = P.pinCnt[1];
+    if (monoR) *monoR = P.pinCnt[3];
+    if (P.pinCnt[0] > capL || P.pinCnt[1] > capR) return fail(ORBX_ERR_CAPACITY, "output capacity smaller than the number of keypoints");
+    if (kpsL) std::memcpy(kpsL, P.pinKps, (size_t)P.pinCnt[0] * sizeof(orbx_keypoint));
+    if (descL) std::memcpy(descL, P.pinDesc, (size_t)P.pinCnt[0] * 32);
+    if (kpsR) std::memcpy(kpsR, P.pinKps + K, (size_t)P.pinCnt[1] * sizeof(orbx_keypoint));
+    if (descR) std::memcpy(descR, P.pinDesc + K * 32, (size_t)P.pinCnt[1] * 32);
     return ORBX_OK;
 }
 
@@ -1649,6 +1802,11 @@ int orbx_create(int nfeatures, float scale_factor, int nlevels, int ini_th_fast,
 
 void orbx_destroy(orbx_extractor* h) {
     if (!h) return;
+    if (h->peer) {   // the other handle of a pair must not keep a view into a batch that goes away with this one
+        if (h->peer->vb == h->pair.b || h->peer->vb == h->vb) h->peer->vb = nullptr;
+        h->peer->peer = nullptr;
+    }
+    pair_release(h);
     if (h->exec) cudaGraphExecDestroy(h->exec);
     if (h->b) orbx_batch_destroy(h->b);
     if (h->pinImg) cudaFreeHost(h->pinImg);
@@ -1718,6 +1876,11 @@ int orbx_extract_stereo(orbx_extractor* left, orbx_extractor* right, const uint8
     const int zero[2] = {0, 0};
     if (!lap_left) lap_left = zero;
     if (!lap_right) lap_right = zero;
+    if (n_left) *n_left = 0;
+    if (n_right) *n_right = 0;
+    if (pair_eligible(left, right))
+        return pair_extract(left, right, image_left, image_right, width, height, stride_left, stride_right, lap_left, lap_right, kps_left, desc_left, cap_left, n_left,
+                            mono_left, kps_right, desc_right, cap_right, n_right, mono_right);
     int r = extractor_issue(left, image_left, width, height, stride_left, lap_left[0], lap_left[1]);
     if (r) return r;
     if ((r = extractor_issue(right, image_right, width, height, stride_right, lap_right[0], lap_right[1]))) return r;
@@ -1810,24 +1973,25 @@ int orbx_extract_stereo_color(orbx_extractor* left, orbx_extractor* right, const
 // replaces Frame::ComputeStereoMatches (Frame.cc:841-1011) for the stereo pair last extracted by `left` and `right`
 // (mpORBextractorLeft / mpORBextractorRight): uright[N_left] / depth[N_left] = Frame::mvuRight / mvDepth, -1 = no match.
 int orbx_stereo_match(orbx_extractor* left, orbx_extractor* right, float mb, float mbf, float* uright, float* depth, int capacity, int* n_left) {
-    if (!left || !right || left == right || !left->b || !right->b) return fail(ORBX_ERR_ARG, "need two distinct handles that have extracted an image");
-    orbx_batch *bl = left->b, *br = right->b;
+    if (!left || !right || left == right || !left->vb || !right->vb) return fail(ORBX_ERR_ARG, "need two distinct handles that have extracted an image");
+    orbx_batch *bl = left->vb, *br = right->vb;
     if (bl->device != br->device || bl->width != br->width || bl->height != br->height || bl->g.K != br->g.K || bl->g.nlevels != br->g.nlevels)
         return fail(ORBX_ERR_ARG, "left and right extractors differ in image size, parameters or device");
     if (!(mb > 0.f) || !(mbf > 0.f)) return fail(ORBX_ERR_ARG, "mb and mbf must be positive");
     if (bl->p.scaleFactorF > 1.9f) return fail(ORBX_ERR_ARG, "stereo matching needs scaleFactor <= 1.9 (beyond it the reference's SAD window, Frame.cc:950, leaves the image and cv::Mat::colRange asserts)");
     if (stereo_smem_bytes(bl->g.K, bl->g.lv[0].h) > 220 * 1024) return fail(ORBX_ERR_TOO_LARGE, "keypoint capacity too large for the stereo matcher's shared memory");
     DeviceGuard dg(bl->device);
-    CU(cudaStreamSynchronize(br->stream));  // the right image's results must be complete (the left stream orders its own)
+    if (br != bl) CU(cudaStreamSynchronize(br->stream));  // the right image's results must be complete (the left stream orders its own)
     Buffers l = bl->buf, r = br->buf;
     l.imgBase = 0; r.imgBase = 0;
-    launch_stereo_match(bl->g, l, r, 1, 0, 0, 0, 0, mb, mbf, bl->stream);
+    launch_stereo_match(bl->g, l, r, 1, 0, left->vi, 0, right->vi, mb, mbf, bl->stream);
     CU(cudaGetLastError());
-    const int N = left->pinCnt ? left->pinCnt[0] : 0;
+    const int N = left->vCount;
+    const size_t lo = (size_t)left->vi * bl->g.K;
     if (n_left) *n_left = N;
     if (N > capacity) return fail(ORBX_ERR_CAPACITY, "output capacity smaller than the number of left keypoints");
-    if (uright && N) CU(cudaMemcpyAsync(uright, l.uRight, (size_t)N * 4, cudaMemcpyDeviceToHost, bl->stream));
-    if (depth && N) CU(cudaMemcpyAsync(depth, l.depth, (size_t)N * 4, cudaMemcpyDeviceToHost, bl->stream));
+    if (uright && N) CU(cudaMemcpyAsync(uright, l.uRight + lo, (size_t)N * 4, cudaMemcpyDeviceToHost, bl->stream));
+    if (depth && N) CU(cudaMemcpyAsync(depth, l.depth + lo, (size_t)N * 4, cudaMemcpyDeviceToHost, bl->stream));
     CU(cudaStreamSynchronize(bl->stream));
     return ORBX_OK;
 }
@@ -1836,34 +2000,35 @@ int orbx_stereo_match(orbx_extractor* left, orbx_extractor* right, float mb, flo
 // knn[q] / ratio_ok[q] for the *n_query rows of the left lapping tail (query q = left keypoint mono_left + q, train index t =
 // right keypoint mono_right + t), i.e. BFmatcher.knnMatch(stereoDescLeft, stereoDescRight, matches, 2) and Lowe's gate.
 int orbx_lapping_match(orbx_extractor* left, orbx_extractor* right, orbx_knn2* knn, uint8_t* ratio_ok, int capacity, int* n_query, int* n_train) {
-    if (!left || !right || left == right || !left->b || !right->b) return fail(ORBX_ERR_ARG, "need two distinct handles that have extracted an image");
-    orbx_batch *bl = left->b, *br = right->b;
+    if (!left || !right || left == right || !left->vb || !right->vb) return fail(ORBX_ERR_ARG, "need two distinct handles that have extracted an image");
+    orbx_batch *bl = left->vb, *br = right->vb;
     if (bl->device != br->device || bl->g.K != br->g.K) return fail(ORBX_ERR_ARG, "left and right extractors differ in parameters or device");
     if (bl->g.K > 65535) return fail(ORBX_ERR_TOO_LARGE, "keypoint capacity above 65535: train indices do not fit the matcher's 16-bit field");
     DeviceGuard dg(bl->device);
-    CU(cudaStreamSynchronize(br->stream));  // the right image's results must be complete (the left stream orders its own)
+    if (br != bl) CU(cudaStreamSynchronize(br->stream));  // the right image's results must be complete (the left stream orders its own)
     Buffers l = bl->buf, r = br->buf;
     l.imgBase = 0; r.imgBase = 0;
-    launch_lap_match(bl->g, l, r, 1, 0, 0, 0, 0, bl->stream);
+    launch_lap_match(bl->g, l, r, 1, 0, left->vi, 0, right->vi, bl->stream);
     CU(cudaGetLastError());
-    const int nq = left->pinCnt ? left->pinCnt[0] - left->pinCnt[1] : 0, nt = right->pinCnt ? right->pinCnt[0] - right->pinCnt[1] : 0;
+    const int nq = left->vCount - left->vMono, nt = right->vCount - right->vMono;
+    const size_t lo = (size_t)left->vi * bl->g.K;
     if (n_query) *n_query = nq;
     if (n_train) *n_train = nt;
     if (nq > capacity) return fail(ORBX_ERR_CAPACITY, "output capacity smaller than the number of left lapping keypoints");
-    if (knn && nq) CU(cudaMemcpyAsync(knn, l.lapKnn, (size_t)nq * 16, cudaMemcpyDeviceToHost, bl->stream));
-    if (ratio_ok && nq) CU(cudaMemcpyAsync(ratio_ok, l.lapOk, (size_t)nq, cudaMemcpyDeviceToHost, bl->stream));
+    if (knn && nq) CU(cudaMemcpyAsync(knn, l.lapKnn + lo, (size_t)nq * 16, cudaMemcpyDeviceToHost, bl->stream));
+    if (ratio_ok && nq) CU(cudaMemcpyAsync(ratio_ok, l.lapOk + lo, (size_t)nq, cudaMemcpyDeviceToHost, bl->stream));
     CU(cudaStreamSynchronize(bl->stream));
     return ORBX_OK;
 }
 
 int orbx_get_level_size(const orbx_extractor* h, int level, int* width, int* height) {
-    if (!h || !h->b) return fail(ORBX_ERR_ARG, "no image has been extracted yet");
-    return orbx_batch_get_level_size(h->b, level, width, height);
+    if (!h || !h->vb) return fail(ORBX_ERR_ARG, "no image has been extracted yet");
+    return orbx_batch_get_level_size(h->vb, level, width, height);
 }
 int orbx_get_level(orbx_extractor* h, int level, uint8_t* dst, size_t dst_stride, int border) {
-    if (!h || !h->b) return fail(ORBX_ERR_ARG, "no image has been extracted yet");
-    return orbx_batch_get_level(h->b, 0, level, dst, dst_stride, border);
+    if (!h || !h->vb) return fail(ORBX_ERR_ARG, "no image has been extracted yet");
+    return orbx_batch_get_level(h->vb, h->vi, level, dst, dst_stride, border);
 }
-orbx_batch* orbx_extractor_batch(orbx_extractor* h) { return h ? h->b : nullptr; }
+orbx_batch* orbx_extractor_batch(orbx_extractor* h) { return h ? (h->vb ? h->vb : h->b) : nullptr; }
 
 }  // extern "C"
