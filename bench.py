@@ -97,6 +97,12 @@ def cpu_run(images, cores, make_extractor, keep=None):
     return time.perf_counter() - t0, sum(nk)
 
 
+def workload_config(pairs):
+    """`config` of both arms (identical dicts): the named workload, its size per GPU and step, and how the L2 is kept out of the timing."""
+    return {"workload": WORKLOAD, "pairs_per_gpu_per_step": pairs,
+            "l2": f"inputs {2 * pairs * W * H / 1e9:.2f} GB per rank and step, larger than the {L2_BYTES / 1e6:.0f} MB L2; no flush needed"}
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -117,7 +123,7 @@ def reference_arm(args):
     emit_line(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD},
+        "config": workload_config(args.pairs),   # the same dict as the GPU arm's: what was actually timed of it is under cpu_baseline.sample
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -674,9 +680,8 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD,
-                       "pairs_per_gpu_per_step": args.pairs, "images_per_launch_set": group, "keypoints_per_image": kp_mean,
-                       "l2": f"inputs {n_img * W * H / 1e9:.2f} GB per rank, larger than the {L2_BYTES / 1e6:.0f} MB L2; no flush needed"},
+            "config": workload_config(args.pairs),
+            "run": {"images_per_launch_set": group, "keypoints_per_image": kp_mean},
             "clocks": clocks, "numa_binding": numa, "e2e": e2e, "e2e_one_process_all_gpus": e2e_one, "parity": parity, "gpu_launches": launches_per_step, "roofline": roofline, "cpu_baseline": cpu, "stages": stages, "latency": latency, "stereo_match": stereo, "feature_grid": grid, "bag_of_words": bow, "large_images": large, "euroc_lapping": euroc,
         }
         emit_line(json.dumps(line))
