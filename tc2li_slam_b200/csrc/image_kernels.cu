@@ -127,6 +127,10 @@ __global__ void __launch_bounds__(32 * RS_WARPS) k_resize_s12(const __grid_const
         if (i == 3 && bi >= 7) { hi3 = true; bi -= 4; }
         sel[i] = (uint32_t)bi | ((uint32_t)(bi + 1) << 4);
     }
+    // sel[3], the third-word flag and the *64 factor are per-thread constants of the segment; ptxas otherwise rebuilds them from `bi` / `dw` inside every
+    // hrow (five + two instructions per source row, SASS listing profiles/r02/sass_k_resize_s12.txt): an identity shuffle makes them opaque
+    sel[3] = __shfl_sync(0xFFFFFFFFu, sel[3], threadIdx.x);
+    const uint32_t hi3w = __shfl_sync(0xFFFFFFFFu, hi3 ? 1u : 0u, threadIdx.x);
     // 32-bit shared-window address of the thread's first word (kept in a register; explicit ld.shared below)
     const uint32_t sBase = smem_u32(tile[wy]) + (uint32_t)(kMarginX + base - boxX) - (uint32_t)(syMin * RS_BOXW);
     uint8_t* D = dst + (size_t)blockIdx.z * dplane + x0 + (size_t)ys * dpitch;
@@ -149,9 +153,9 @@ __global__ void __launch_bounds__(32 * RS_WARPS) k_resize_s12(const __grid_const
         h[0] = __dp2a_lo(coef[0], __byte_perm(w0, w1, sel[0]), 0u) & 0xFFFFFFF0u;
         h[1] = __dp2a_lo(coef[1], __byte_perm(w0, w1, sel[1]), 0u) & 0xFFFFFFF0u;
         h[2] = __dp2a_lo(coef[2], __byte_perm(w0, w1, sel[2]), 0u) & 0xFFFFFFF0u;
-        h[3] = __dp2a_lo(coef[3], __byte_perm(hi3 ? w1 : w0, hi3 ? w2 : w1, sel[3]), 0u) & 0xFFFFFFF0u;
+        h[3] = __dp2a_lo(coef[3], __byte_perm(hi3w ? w1 : w0, hi3w ? w2 : w1, sel[3]), 0u) & 0xFFFFFFF0u;
     };
-    const uint32_t k64 = 64u + ((uint32_t)dw >> 30);  // 64, opaque to the compiler: keeps the multiply an IMAD (FMA pipe) instead of a LEA (ALU pipe)
+    const uint32_t k64 = __shfl_sync(0xFFFFFFFFu, 64u + ((uint32_t)dw >> 30), threadIdx.x);  // 64, opaque to the compiler: keeps the multiply an IMAD (FMA pipe) instead of a LEA (ALU pipe)
     mbar_wait(&bars[wy], 0);
     // hX / hY: the two most recent horizontally interpolated source rows (rows rX, rY).  A destination row needs rows sy0 and
     // sy0 + 1; it usually finds sy0 in one of the two and loads sy0 + 1 over the other, so the roles alternate and no
