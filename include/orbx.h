@@ -209,6 +209,14 @@ int orbx_batch_download_lapping(orbx_batch* b, int n_frames, orbx_knn2* knn, uin
 #define ORBX_GRID_COLS 64 /* FRAME_GRID_COLS, Frame.h:60 */
 #define ORBX_GRID_ROWS 48 /* FRAME_GRID_ROWS, Frame.h:59 */
 #define ORBX_GRID_CELLS (ORBX_GRID_COLS * ORBX_GRID_ROWS)
+/* Frame::UndistortKeyPoints (Frame.cc:777-810) on the resident keypoints of images [0, n_images): cv::undistortPoints(mat, mat, toK(), mDistCoef, cv::Mat(), mK),
+ * bit-identical to OpenCV (five fixed-point iterations in double).  camera / new_camera = {fx, fy, cx, cy} of Pinhole::toK() / Frame::mK; dist = mDistCoef
+ * (n_dist = 4, 5, 8 or 12).  dist == NULL or dist[0] == 0: mvKeysUn = mvKeys, as the reference's early return.  Asynchronous.  A grid built afterwards
+ * (orbx_batch_assign_grid) and the single-grid searches on it use the undistorted coordinates (the caller passes the bounds of Frame::ComputeImageBounds);
+ * two-grid (fisheye) frames use mvKeys / mvKeysRight as in the reference.  The next orbx_batch_run* resets it.
+ * orbx_batch_download_undistorted: xy [n_images][K][2] floats = mvKeysUn[i].pt; synchronises. */
+int orbx_batch_undistort_keypoints(orbx_batch* b, int n_images, const float camera[4], const float* dist, int n_dist, const float new_camera[4]);
+int orbx_batch_download_undistorted(orbx_batch* b, int n_images, float* xy);
 int orbx_batch_assign_grid(orbx_batch* b, int n_images, float min_x, float max_x, float min_y, float max_y);
 int orbx_batch_download_grid(orbx_batch* b, int n_images, int* cell_start, int* items);
 /* Frame::GetFeaturesInArea(x, y, r, minLevel, maxLevel) (Frame.cc:687-749) for n_queries windows against the grids of

@@ -1070,6 +1070,46 @@ int search_local_points_stereo(StereoSide& L, StereoSide& R, const uint8_t* take
 }
 
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Frame::UndistortKeyPoints (Frame.cc:777-810): cv::undistortPoints(mat, mat, toK(), mDistCoef, cv::Mat(), mK) on the keypoint coordinates, i.e.
+// OpenCV's cvUndistortPointsInternal with its default criteria (5 fixed-point iterations, no epsilon test), no tilt, R = identity, P = mK: all in
+// double, left to right, no FMA contraction; the result is rounded to float once.  cam / newCam = {fx, fy, cx, cy} (float, as the cv::Mat_<float>
+// matrices hold them); dist = k1, k2, p1, p2[, k3[, k4, k5, k6[, s1, s2, s3, s4]]] (nDist = 4, 5, 8 or 12).  Pinned against cv2.undistortPoints.
+// ---------------------------------------------------------------------------------------------------------------------
+void undistort_points(const float* xyIn, int n, const float cam[4], const float* dist, int nDist, const float newCam[4], float* xyOut) {
+    const double fx = cam[0], fy = cam[1], cx = cam[2], cy = cam[3];
+    const double ifx = 1. / fx, ify = 1. / fy;
+    double k[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < nDist && i < 12; ++i) k[i] = dist[i];
+    const double nfx = newCam[0], nfy = newCam[1], ncx = newCam[2], ncy = newCam[3];
+    for (int i = 0; i < n; ++i) {
+        double x = xyIn[2 * i], y = xyIn[2 * i + 1];
+        const double u = x, v = y;
+        x = (x - cx) * ifx;
+        y = (y - cy) * ify;
+        if (nDist > 0) {
+            const double x0 = x, y0 = y;
+            for (int j = 0; j < 5; ++j) {
+                const double r2 = x * x + y * y;
+                const double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+                if (icdist < 0) {   // (OpenCV: "test: undistortPoints.regression_14583")
+                    x = (u - cx) * ifx;
+                    y = (v - cy) * ify;
+                    break;
+                }
+                const double deltaX = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2;
+                const double deltaY = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2;
+                x = (x0 - deltaX) * icdist;
+                y = (y0 - deltaY) * icdist;
+            }
+        }
+        const double xx = nfx * x + 0.0 * y + ncx, yy = 0.0 * x + nfy * y + ncy, ww = 1. / (0.0 * x + 0.0 * y + 1.0);
+        xyOut[2 * i] = (float)(xx * ww);
+        xyOut[2 * i + 1] = (float)(yy * ww);
+    }
+}
+
+
 // ------------------------------------------------------------------------------------------------------------------
 // DBoW2 vocabulary: what Frame::ComputeBoW (Frame.cc:768-775) runs on the descriptors the extractor produced.  Restated from the
 // vendored library (slam_framework/Thirdparty/DBoW2/DBoW2): the text loader the reference uses for ORBvoc.txt
@@ -1252,6 +1292,9 @@ int orbo_search_local_points_stereo(const void* kpsL, int nL, const uint8_t* des
                                     int* matchR) {
     StereoSide L{(const KeyPoint*)kpsL, nL, descL, startL, itemsL, matchL, {}}, R{(const KeyPoint*)kpsR, nR, descR, startR, itemsR, matchR, {}};
     return search_local_points_stereo(L, R, takenL0, takenR0, leftToRight, rightToLeft, minX, maxX, minY, maxY, (const ProjQuery*)q, side, nq, nnRatio, thHigh);
+}
+void orbo_undistort_points(const float* xy, int n, const float* cam, const float* dist, int nDist, const float* newCam, float* out) {
+    undistort_points(xy, n, cam, dist, nDist, newCam, out);
 }
 // vocabulary (DBoW2) -------------------------------------------------------------------------------------------------
 void* orbo_voc_load_text(const char* path) {

@@ -359,6 +359,20 @@ def search_local_points_stereo(left, right, taken_l, taken_r, l2r, r2l, bounds, 
     return ml[:len(kl)], mr[:len(kr)], nm
 
 
+def undistort_points(xy, cam, dist, new_cam=None):
+    """Frame::UndistortKeyPoints' cv::undistortPoints(mat, mat, K, mDistCoef, cv::Mat(), mK) (Frame.cc:777-810) on float32 points [n, 2];
+    cam / new_cam = (fx, fy, cx, cy); dist = 4, 5, 8 or 12 coefficients."""
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+    c = np.ascontiguousarray(cam, np.float32)
+    nc = c if new_cam is None else np.ascontiguousarray(new_cam, np.float32)
+    d = np.ascontiguousarray(dist, np.float32)
+    out = np.empty_like(xy)
+    L = lib()
+    L.orbo_undistort_points.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.orbo_undistort_points(_p(xy), len(xy), _p(c), _p(d), len(d), _p(nc), _p(out))
+    return out
+
+
 class OracleExtractor:
     """Mirror of TC2LI_SLAM::ORBextractor (ORBextractor.h:52-118) on the CPU oracle."""
 

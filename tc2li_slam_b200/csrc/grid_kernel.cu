@@ -43,8 +43,9 @@ __global__ void __launch_bounds__(GT) k_assign_grid(const Buffers b, int K, Grid
     const orbx_keypoint* kps = b.kps + (size_t)img * K;
     for (int c = tid; c < NC; c += GT) cnt[c] = 0;
     __syncthreads();
+    const float2* un = b.kpsUn ? b.kpsUn + (size_t)img * K : nullptr;   // Frame::mvKeysUn when the caller undistorted the keypoints
     for (int i = tid; i < n; i += GT) {
-        const int c = cell_of(kps[i].x, kps[i].y, p);
+        const int c = un ? cell_of(un[i].x, un[i].y, p) : cell_of(kps[i].x, kps[i].y, p);
         if (c >= 0) atomicAdd(&cnt[c], 1);
     }
     __syncthreads();
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(GT) k_assign_grid(const Buffers b, int K, Grid
     for (int c = tid; c < NC; c += GT) cnt[c] = start[c];
     __syncthreads();
     for (int i = tid; i < n; i += GT) {
-        const int c = cell_of(kps[i].x, kps[i].y, p);
+        const int c = un ? cell_of(un[i].x, un[i].y, p) : cell_of(kps[i].x, kps[i].y, p);
         if (c >= 0) items[atomicAdd(&cnt[c], 1)] = i;
     }
     __syncthreads();
@@ -118,7 +119,8 @@ __global__ void __launch_bounds__(128) k_features_in_area(const Buffers b, int K
                 int idx = 0;
                 if (j < e) {
                     idx = gi[j];
-                    const orbx_keypoint kp = kps[idx];
+                    orbx_keypoint kp = kps[idx];
+                    if (b.kpsUn) { const float2 u = b.kpsUn[(size_t)Q.image * K + idx]; kp.x = u.x; kp.y = u.y; }
                     bool lv = true;
                     if (checkLevels) lv = !(kp.octave < Q.min_level) && !(Q.max_level >= 0 && kp.octave > Q.max_level);
                     hit = lv && fabsf(__fsub_rn(kp.x, x)) < r && fabsf(__fsub_rn(kp.y, y)) < r;
@@ -131,6 +133,48 @@ __global__ void __launch_bounds__(128) k_features_in_area(const Buffers b, int K
         }
     }
     if (lane == 0) counts[q] = n;
+}
+
+// Frame::UndistortKeyPoints (Frame.cc:777-810) = cv::undistortPoints(mat, mat, toK(), mDistCoef, cv::Mat(), mK): OpenCV's fixed-point inversion of the distortion
+// model, five iterations, in double, operation by operation (every product and sum an explicit round-to-nearest double op: no contraction), rounded to float once.
+__global__ void __launch_bounds__(128) k_undistort(const Buffers b, int K, const __grid_constant__ UndistortParams p, float2* __restrict__ out) {
+    const int img = b.imgBase + blockIdx.y, i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= b.outCount[img]) return;
+    const orbx_keypoint kp = b.kps[(size_t)img * K + i];
+    const double u = (double)kp.x, v = (double)kp.y;
+    double x = __dmul_rn(__dsub_rn(u, p.cx), p.ifx), y = __dmul_rn(__dsub_rn(v, p.cy), p.ify);
+    const double x0 = x, y0 = y;
+    const double* k = p.k;
+    for (int j = 0; j < 5; ++j) {
+        const double r2 = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y));
+        const double num = __dadd_rn(1.0, __dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(k[7], r2), k[6]), r2), k[5]), r2));
+        const double den = __dadd_rn(1.0, __dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(k[4], r2), k[1]), r2), k[0]), r2));
+        const double icdist = __ddiv_rn(num, den);
+        if (icdist < 0) {
+            x = __dmul_rn(__dsub_rn(u, p.cx), p.ifx);
+            y = __dmul_rn(__dsub_rn(v, p.cy), p.ify);
+            break;
+        }
+        // deltaX = 2*k[2]*x*y + k[3]*(r2 + 2*x*x) + k[8]*r2 + k[9]*r2*r2;  deltaY = k[2]*(r2 + 2*y*y) + 2*k[3]*x*y + k[10]*r2 + k[11]*r2*r2  (left to right)
+        const double dX = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(2.0, k[2]), x), y), __dmul_rn(k[3], __dadd_rn(r2, __dmul_rn(__dmul_rn(2.0, x), x)))),
+                                              __dmul_rn(k[8], r2)),
+                                    __dmul_rn(__dmul_rn(k[9], r2), r2));
+        const double dY = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(k[2], __dadd_rn(r2, __dmul_rn(__dmul_rn(2.0, y), y))), __dmul_rn(__dmul_rn(__dmul_rn(2.0, k[3]), x), y)),
+                                              __dmul_rn(k[10], r2)),
+                                    __dmul_rn(__dmul_rn(k[11], r2), r2));
+        x = __dmul_rn(__dsub_rn(x0, dX), icdist);
+        y = __dmul_rn(__dsub_rn(y0, dY), icdist);
+    }
+    // RR = P * I: xx = fx' x + 0 y + cx', yy = 0 x + fy' y + cy', ww = 1 / (0 x + 0 y + 1)
+    const double xx = __dadd_rn(__dadd_rn(__dmul_rn(p.nfx, x), __dmul_rn(0.0, y)), p.ncx);
+    const double yy = __dadd_rn(__dadd_rn(__dmul_rn(0.0, x), __dmul_rn(p.nfy, y)), p.ncy);
+    const double ww = __ddiv_rn(1.0, __dadd_rn(__dadd_rn(__dmul_rn(0.0, x), __dmul_rn(0.0, y)), 1.0));
+    out[(size_t)img * K + i] = make_float2((float)__dmul_rn(xx, ww), (float)__dmul_rn(yy, ww));
+}
+
+void launch_undistort(const Buffers& b, int K, const UndistortParams& p, float2* out, int nImages, cudaStream_t s) {
+    dim3 grid((unsigned)((K + 127) / 128), (unsigned)nImages);
+    k_undistort<<<grid, 128, 0, s>>>(b, K, p, out);
 }
 
 size_t grid_smem_bytes(int K) { return (size_t)K * sizeof(int); }

@@ -144,6 +144,10 @@ struct orbx_batch {
     orbx_proj_query* spDev = nullptr; int* spOut = nullptr;   // projection search: queries; match[K] + info[2]
     size_t spCap = 0;
     bool spConfigured = false;
+    // Frame::UndistortKeyPoints (orbx_batch_undistort_keypoints): undistorted coordinates of images [0, unImages); 0 = mvKeysUn == mvKeys
+    float2* kpsUnBuf = nullptr;
+    int unImages = 0;
+    bool gridUn = false;   // the feature grid was built from the undistorted coordinates: its readers use them too
     // bag of words (orbx_batch_compute_bow): buffers are allocated on first use
     uint32_t *bowLeaf = nullptr, *bowNid = nullptr;
     BowOut bow = {};
@@ -749,6 +753,7 @@ int orbx_batch_run_range(orbx_batch* b, int first, int n, const int* lapping) {
     if (r) return r;
     if (n == 0) return ORBX_OK;
     DeviceGuard dg(b->device);
+    b->unImages = 0;   // new keypoints: mvKeysUn is mvKeys again until the caller undistorts them
     return run_range_lane(b, first, n, lapping, 0);
 }
 
@@ -760,6 +765,7 @@ int orbx_batch_run_pipelined(orbx_batch* b, int n, const int* lapping, int chunk
     if (n == 0) return ORBX_OK;
     if (chunk <= 0) return fail(ORBX_ERR_ARG, "chunk must be positive");
     DeviceGuard dg(b->device);
+    b->unImages = 0;
     if (b->timing || chunk >= n) return run_range_lane(b, 0, n, lapping, 0);
     CU(cudaEventRecord(b->evFork, b->stream));
     for (int k = 1; k < orbx_batch::kLanes; ++k) CU(cudaStreamWaitEvent(b->laneMain[k], b->evFork, 0));
@@ -814,6 +820,43 @@ int orbx_batch_download_stereo(orbx_batch* b, int n_frames, float* uright, float
 
 
 
+// Frame::UndistortKeyPoints (Frame.cc:777-810) for images [0, n_images) on the resident keypoints: cv::undistortPoints(mat, mat, toK(), mDistCoef, cv::Mat(), mK).
+// camera / new_camera = {fx, fy, cx, cy} of toK() / mK; dist = mDistCoef (4, 5, 8 or 12 floats).  dist == NULL or dist[0] == 0 means mvKeysUn = mvKeys
+// (the reference's early return).  Asynchronous; the grid and the single-grid searches built afterwards read the undistorted coordinates.
+int orbx_batch_undistort_keypoints(orbx_batch* b, int n_images, const float camera[4], const float* dist, int n_dist, const float new_camera[4]) {
+    int r = check_images(b, 0, n_images);
+    if (r) return r;
+    if (!dist || n_dist <= 0 || dist[0] == 0.0f) { b->unImages = 0; return ORBX_OK; }
+    if (!camera || !new_camera || (n_dist != 4 && n_dist != 5 && n_dist != 8 && n_dist != 12)) return fail(ORBX_ERR_ARG, "camera matrices and 4, 5, 8 or 12 distortion coefficients are needed");
+    if (!(camera[0] != 0.f) || !(camera[1] != 0.f)) return fail(ORBX_ERR_ARG, "zero focal length");
+    DeviceGuard dg(b->device);
+    if (!b->kpsUnBuf && (r = dev_alloc(b, &b->kpsUnBuf, (size_t)b->maxImages * b->g.K))) return r;
+    UndistortParams p;
+    p.cx = camera[2]; p.cy = camera[3];
+    p.ifx = 1. / (double)camera[0]; p.ify = 1. / (double)camera[1];
+    for (int i = 0; i < 12; ++i) p.k[i] = i < n_dist ? (double)dist[i] : 0.0;
+    p.nfx = new_camera[0]; p.nfy = new_camera[1]; p.ncx = new_camera[2]; p.ncy = new_camera[3];
+    b->unImages = n_images;
+    if (n_images == 0) return ORBX_OK;
+    Buffers buf = b->buf;
+    buf.imgBase = 0;
+    launch_undistort(buf, b->g.K, p, b->kpsUnBuf, n_images, b->stream);
+    CU(cudaGetLastError());
+    return ORBX_OK;
+}
+
+// xy: [n_images][K][2] floats (Frame::mvKeysUn[i].pt); synchronises
+int orbx_batch_download_undistorted(orbx_batch* b, int n_images, float* xy) {
+    int r = check_images(b, 0, n_images);
+    if (r) return r;
+    if (!xy) return fail(ORBX_ERR_ARG, "null output");
+    if (n_images > b->unImages) return fail(ORBX_ERR_ARG, "orbx_batch_undistort_keypoints has not been run for these images (or the coefficients were zero: mvKeysUn = mvKeys)");
+    DeviceGuard dg(b->device);
+    if (n_images) CU(cudaMemcpyAsync(xy, b->kpsUnBuf, (size_t)n_images * b->g.K * sizeof(float2), cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return ORBX_OK;
+}
+
 // Frame::AssignFeaturesToGrid (Frame.cc:412-443) for images [0, n_images) on the resident keypoints; asynchronous on the handle's stream
 int orbx_batch_assign_grid(orbx_batch* b, int n_images, float min_x, float max_x, float min_y, float max_y) {
     int r = check_images(b, 0, n_images);
@@ -830,10 +873,13 @@ int orbx_batch_assign_grid(orbx_batch* b, int n_images, float min_x, float max_x
     b->gridParams.minX = min_x; b->gridParams.minY = min_y;
     b->gridParams.invW = static_cast<float>(ORBX_GRID_COLS) / (max_x - min_x);
     b->gridParams.invH = static_cast<float>(ORBX_GRID_ROWS) / (max_y - min_y);
+    if (b->unImages > 0 && n_images > b->unImages) return fail(ORBX_ERR_ARG, "orbx_batch_undistort_keypoints covered fewer images than this grid asks for");
     b->gridImages = n_images;
+    b->gridUn = b->unImages > 0;
     if (n_images == 0) return ORBX_OK;
     Buffers buf = b->buf;
     buf.imgBase = 0;
+    buf.kpsUn = b->gridUn ? b->kpsUnBuf : nullptr;
     launch_assign_grid(buf, b->g.K, b->gridParams, n_images, b->stream);
     CU(cudaGetLastError());
     return ORBX_OK;
@@ -878,6 +924,7 @@ int orbx_batch_features_in_area(orbx_batch* b, const orbx_area_query* queries, i
     CU(cudaMemcpyAsync(b->qDev, queries, (size_t)n_queries * sizeof(orbx_area_query), cudaMemcpyHostToDevice, b->stream));
     Buffers buf = b->buf;
     buf.imgBase = 0;
+    buf.kpsUn = b->gridUn ? b->kpsUnBuf : nullptr;
     launch_features_in_area(buf, b->g.K, b->gridParams, b->qDev, n_queries, capacity, b->qCounts, b->qOut, b->stream);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(counts, b->qCounts, (size_t)n_queries * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
@@ -946,6 +993,7 @@ static int search_common(orbx_batch* b, const SearchArgs& a) {
     }
     Buffers buf = b->buf;
     buf.imgBase = 0;
+    buf.kpsUn = (b->gridUn && !two) ? b->kpsUnBuf : nullptr;
     if (a.local)
         launch_search_local_points(buf, a.image, K, b->gridParams, b->spDev, n_queries, (a.use_uright && !two) ? 1 : 0, a.th_high, a.nn_ratio, anyTaken ? takenDev : nullptr, candCap,
                                    stageDesc, b->spOut, infoDev, b->stream, a.image2, two ? sideDev : nullptr, anyLinks ? linksDev : nullptr);

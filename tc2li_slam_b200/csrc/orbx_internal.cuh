@@ -99,6 +99,7 @@ struct Buffers {
     uint8_t* lapOk;         // [image][K] Lowe ratio gate of that pair (Frame.cc:1187)
     int* gridStart;         // [image][64 * 48 + 1] CSR of Frame::mGrid (cell = column * 48 + row)
     int* gridItems;         // [image][K] keypoint indices, cell by cell, ascending inside a cell
+    const float2* kpsUn;    // [image][K] undistorted keypoint coordinates (Frame::mvKeysUn), or NULL: the grid and the single-grid searches then read kps
     int* errFlag;           // device-side error flag (capacity overflow etc.)
     const uint4* cellTab;   // [cellsPerImage] FAST cell descriptors (make_cell_table)
     int imgBase;            // first image of this launch set (kernels index images as imgBase + blockIdx)
@@ -178,6 +179,10 @@ struct GridParams {  // Frame::mnMinX / mnMinY and mfGridElementWidthInv / Heigh
 };
 size_t grid_smem_bytes(int K);
 cudaError_t grid_configure(int K);
+struct UndistortParams {   // cv::undistortPoints(src, dst, K, distCoeffs, noArray(), P) as Frame::UndistortKeyPoints calls it (Frame.cc:777-810)
+    double cx, cy, ifx, ify, k[12], nfx, nfy, ncx, ncy;
+};
+void launch_undistort(const Buffers& b, int K, const UndistortParams& p, float2* out, int nImages, cudaStream_t s);
 void launch_assign_grid(const Buffers& b, int K, const GridParams& p, int nImages, cudaStream_t s);
 void launch_features_in_area(const Buffers& b, int K, const GridParams& p, const orbx_area_query* queries, int nQueries, int cap, int* counts, int* out,
                              cudaStream_t s);

@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(ST) k_search_by_projection(const Buffers b, in
         if (links) link[kk] = k < cnt ? (int16_t)links[kk] : (int16_t)-1;
         if (k < cnt) {
             const orbx_keypoint kp = b.kps[(size_t)img * K + k];
-            kxy[kk] = make_float2(kp.x, kp.y);
+            kxy[kk] = (b.kpsUn && sides == 1) ? b.kpsUn[(size_t)img * K + k] : make_float2(kp.x, kp.y);   // mvKeysUn for single-grid frames, mvKeys / mvKeysRight for two-grid ones
             koct[kk] = (uint8_t)(kp.octave & 15);
             urS[kk] = uRight ? uRight[k] : -1.f;
             kang[kk] = kp.angle;

@@ -89,6 +89,8 @@ def lib():
         "orbx_lapping_match": (i, [_vp, _vp, _vp, _vp, i, _vp, _vp]),
         "orbx_batch_lapping_match": (i, [_vp, i]),
         "orbx_batch_download_lapping": (i, [_vp, i, _vp, _vp]),
+        "orbx_batch_undistort_keypoints": (i, [_vp, i, _vp, _vp, i, _vp]),
+        "orbx_batch_download_undistorted": (i, [_vp, i, _vp]),
         "orbx_batch_assign_grid": (i, [_vp, i, f, f, f, f]),
         "orbx_batch_download_grid": (i, [_vp, i, _vp, _vp]),
         "orbx_batch_features_in_area": (i, [_vp, _vp, i, i, _vp, _vp]),
@@ -614,6 +616,19 @@ class BatchExtractor:
         knn, ok = np.empty((n_frames, self.K, 4), np.int32), np.empty((n_frames, self.K), np.uint8)
         _check(lib().orbx_batch_download_lapping(self._h, int(n_frames), _p(knn), _p(ok)))
         return knn, ok
+
+    def undistort_keypoints(self, n_images, camera, dist, new_camera=None):
+        """Batched Frame::UndistortKeyPoints (Frame.cc:777-810) on the resident keypoints; camera / new_camera = (fx, fy, cx, cy), dist = mDistCoef.  Asynchronous;
+        the grid / single-grid searches built afterwards use the undistorted coordinates."""
+        c = np.ascontiguousarray(camera, np.float32)
+        nc = c if new_camera is None else np.ascontiguousarray(new_camera, np.float32)
+        d = None if dist is None else np.ascontiguousarray(dist, np.float32)
+        _check(lib().orbx_batch_undistort_keypoints(self._h, int(n_images), _p(c), None if d is None else _p(d), 0 if d is None else len(d), _p(nc)))
+
+    def download_undistorted(self, n_images):
+        xy = np.empty((int(n_images), self.K, 2), np.float32)
+        _check(lib().orbx_batch_download_undistorted(self._h, int(n_images), _p(xy)))
+        return xy
 
     def assign_grid(self, n_images, bounds=None):
         """Batched Frame::AssignFeaturesToGrid (Frame.cc:412-443) on the resident keypoints (after run()); asynchronous.

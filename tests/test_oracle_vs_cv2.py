@@ -203,3 +203,40 @@ def test_remap_far_outside_and_borders():
     mx[0, 0], my[0, 0] = -1e6, 3.0
     mx[1, 1], my[1, 1] = 5.0, 4e5
     assert np.array_equal(po.remap(img, mx, my), cv2.remap(img, mx, my, cv2.INTER_LINEAR))
+
+
+def undistort_cases(rng, n_trials):
+    for trial in range(n_trials):
+        fx, fy = rng.uniform(300, 900, 2)
+        cam = np.array([fx, fy, rng.uniform(300, 700), rng.uniform(150, 300)], np.float32)
+        nd = int(rng.choice([4, 5, 8, 12]))
+        d = np.zeros(nd, np.float32)
+        d[0], d[1] = rng.uniform(-0.4, 0.4), rng.uniform(-0.2, 0.2)
+        d[2:4] = rng.uniform(-0.01, 0.01, 2)
+        if nd >= 5:
+            d[4] = rng.uniform(-0.05, 0.05)
+        if nd >= 8:
+            d[5:8] = rng.uniform(-0.05, 0.05, 3)
+        if nd >= 12:
+            d[8:12] = rng.uniform(-0.002, 0.002, 4)
+        new = cam if trial % 2 == 0 else np.array([fx * 0.9, fy * 1.1, cam[2] + 5, cam[3] - 3], np.float32)
+        yield cam, d, new
+
+
+def cv2_undistort(pts, cam, d, new):
+    K = np.array([[cam[0], 0, cam[2]], [0, cam[1], cam[3]], [0, 0, 1]], np.float32)
+    P = np.array([[new[0], 0, new[2]], [0, new[1], new[3]], [0, 0, 1]], np.float32)
+    return cv2.undistortPoints(pts.reshape(-1, 1, 2), K, d, None, P).reshape(-1, 2)
+
+
+def test_undistort_points_matches_cv2():
+    """Frame::UndistortKeyPoints' cv::undistortPoints(mat, mat, K, mDistCoef, cv::Mat(), mK) (Frame.cc:777-810): the restatement is bit-identical to OpenCV
+    for 4 / 5 / 8 / 12 coefficients, equal and different new camera matrices, points inside and far outside the image (strong distortion: the icdist < 0 exit)."""
+    rng = np.random.default_rng(1)
+    for cam, d, new in undistort_cases(rng, 120):
+        pts = np.stack([rng.uniform(-200, 1500, 1500), rng.uniform(-200, 600, 1500)], 1).astype(np.float32)
+        assert np.array_equal(cv2_undistort(pts, cam, d, new).view(np.uint32), po.undistort_points(pts, cam, d, new).view(np.uint32))
+    cam = np.array([400, 400, 620, 188], np.float32)   # extreme barrel distortion: the rational term turns negative for far points
+    pts = np.stack([rng.uniform(-3000, 4000, 4000), rng.uniform(-2000, 2500, 4000)], 1).astype(np.float32)
+    for d in (np.array([-0.9, 0.3, 0, 0], np.float32), np.array([0.5, -2.0, 0.001, 0.001, 3.0], np.float32)):
+        assert np.array_equal(cv2_undistort(pts, cam, d, cam).view(np.uint32), po.undistort_points(pts, cam, d, cam).view(np.uint32))
