@@ -302,7 +302,8 @@ int orbx_vocabulary_create(int device, int k, int L, int scoring, int weighting,
                            const uint8_t* descriptors, const double* weights, orbx_vocabulary** out);
 void orbx_vocabulary_destroy(orbx_vocabulary* v);
 int orbx_vocabulary_info(const orbx_vocabulary* v, int out[6]); /* {k, L, scoring, weighting, nodes incl. root, words} */
-/* transform() of n host descriptors [n][32] (capacity of every output array: n, node_start n + 1); synchronous */
+/* transform() of n host descriptors [n][32] (capacity of every output array: n, node_start n + 1); synchronous.  Uses a stream and scratch buffers of the
+ * vocabulary handle: one call at a time per handle (orbx_batch_compute_bow only reads the vocabulary and may run concurrently on many batches). */
 int orbx_vocabulary_transform(orbx_vocabulary* v, const uint8_t* descriptors, int n, int levelsup, uint32_t* words, double* values, int* n_words,
                               uint32_t* nodes, int* node_start, uint32_t* features, int* n_nodes);
 /* transform() of the descriptors resident after orbx_batch_run, images [0, n_images); asynchronous on the handle's stream.
