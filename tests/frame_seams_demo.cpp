@@ -5,6 +5,7 @@
 // prints checksums that the test compares with the CPU oracle.  With argument "compile-only" it does nothing.
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <vector>
 
 #include "ORBextractor.h"
@@ -76,5 +77,44 @@ int main(int argc, char** argv) {
     msum = 0;
     for (int k = 0; k < N; ++k) msum += (long long)(match[k] + 2) * (k + 1);
     std::printf("local %d %lld\n", nmatches, msum);
+
+    // Frame::ComputeBoW (Frame.cc:768-775): mpORBvocabulary->transform(vCurrentDesc, mBowVec, mFeatVec, 4) on the resident descriptors, here against a
+    // small synthetic vocabulary (k = 4, L = 3) handed over as arrays; the containers are rebuilt the way INTEGRATION.md 2f shows
+    {
+        const int kk = 4, LL = 3, nNodes = 1 + 4 + 16 + 64;
+        std::vector<int> parent(nNodes, 0);
+        std::vector<uint8_t> isWord(nNodes, 0), vdesc((size_t)nNodes * 32, 0);
+        std::vector<double> weight(nNodes, 0.0);
+        for (int i = 1; i < nNodes; ++i) {
+            parent[i] = (i - 1) / kk;
+            isWord[i] = i >= 21;
+            for (int j = 0; j < 32; ++j) vdesc[(size_t)i * 32 + j] = (uint8_t)((i * 131 + j * 29 + (i * j) % 7) & 255);
+            weight[i] = isWord[i] ? 0.5 + (i % 13) * 0.37 : 0.0;
+        }
+        orbx_vocabulary* voc = nullptr;
+        if (orbx_vocabulary_create(0, kk, LL, 0, 0, nNodes, parent.data(), isWord.data(), vdesc.data(), weight.data(), &voc) != ORBX_OK) return 7;
+        const int K = orbx_batch_max_keypoints(hb);
+        std::vector<uint32_t> words(K), nodes(K), feats(K);
+        std::vector<double> values(K);
+        std::vector<int> start(K + 1);
+        int nw = 0, nn = 0;
+        if (orbx_batch_compute_bow(hb, voc, 1, 2) != ORBX_OK) return 8;
+        if (orbx_batch_download_bow(hb, 1, words.data(), values.data(), &nw, nodes.data(), start.data(), feats.data(), &nn) != ORBX_OK) return 9;
+        std::map<unsigned, double> mBowVec;
+        std::map<unsigned, std::vector<unsigned> > mFeatVec;
+        for (int i = 0; i < nw; ++i) mBowVec.insert(mBowVec.end(), std::make_pair(words[i], values[i]));
+        for (int j = 0; j < nn; ++j) mFeatVec.insert(mFeatVec.end(), std::make_pair(nodes[j], std::vector<unsigned>(feats.begin() + start[j], feats.begin() + start[j + 1])));
+        unsigned long long wsum = 0, vsum = 0, fsum = 0;
+        for (std::map<unsigned, double>::const_iterator it = mBowVec.begin(); it != mBowVec.end(); ++it) {
+            unsigned long long bits;
+            std::memcpy(&bits, &it->second, 8);
+            wsum += (unsigned long long)(it->first + 1);
+            vsum += bits >> 20;   // (the sum of the top 44 bits of every value: any differing value changes it)
+        }
+        for (std::map<unsigned, std::vector<unsigned> >::const_iterator it = mFeatVec.begin(); it != mFeatVec.end(); ++it)
+            for (size_t j = 0; j < it->second.size(); ++j) fsum += (unsigned long long)(it->first + 1) * (it->second[j] + 1) * (j + 1);
+        std::printf("bow %d %d %llu %llu %llu\n", nw, nn, wsum, vsum, fsum);
+        orbx_vocabulary_destroy(voc);
+    }
     return 0;
 }

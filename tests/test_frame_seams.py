@@ -64,3 +64,22 @@ def test_frame_seams_match_oracle():
     m, nm = po.search_local_points(k, d, ur, taken, (start, items), bounds, q, 0.8)
     assert lines["local"] == [nm, int(((m.astype(np.int64) + 2) * w).sum())]
     assert nm > 500
+    # Frame::ComputeBoW against the same synthetic vocabulary (written in ORBvoc.txt's format for the oracle)
+    kk, n_nodes = 4, 85
+    text = ["4 3 0 0"]
+    for i in range(1, n_nodes):
+        desc = " ".join(str((i * 131 + j * 29 + (i * j) % 7) & 255) for j in range(32))
+        wgt = 0.5 + (i % 13) * 0.37 if i >= 21 else 0.0
+        text.append(f"{(i - 1) // kk} {1 if i >= 21 else 0} {desc} {wgt!r}")
+    import tempfile
+    with tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False) as f:
+        f.write("\n".join(text))
+    words, values, nodes, start, feats = po.OracleVocabulary(f.name).transform(d, 2)
+    os.unlink(f.name)
+    vsum = int((values.view(np.uint64) >> np.uint64(20)).astype(object).sum())
+    fsum = 0
+    for j in range(len(nodes)):
+        lst = feats[start[j]:start[j + 1]].astype(object)
+        fsum += int(sum((int(nodes[j]) + 1) * (int(x) + 1) * (t + 1) for t, x in enumerate(lst)))
+    assert lines["bow"] == [len(words), len(nodes), int((words.astype(np.int64) + 1).sum()), vsum, fsum]
+    assert len(words) > 30
