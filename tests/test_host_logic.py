@@ -114,3 +114,38 @@ def test_query_record_layouts_match_the_c_structs():
     for name in ("orbx_batch_assign_grid", "orbx_batch_features_in_area", "orbx_batch_search_by_projection", "orbx_batch_search_local_points",
                  "orbx_batch_search_keyframe_points", "orbx_batch_set_input_resize", "orbx_set_input_resize"):
         assert name in hdr
+
+
+def test_vocabulary_arguments_are_checked_before_the_gpu_is_touched(tmp_path):
+    """orbx_vocabulary_create / _load_text: the header bounds of TemplatedVocabulary::loadFromTextFile (TemplatedVocabulary.h:1364-1369), tree consistency,
+    missing files -> ORBX_ERR_ARG; a well-formed tree without a usable GPU -> ORBX_ERR_CUDA (no CPU fallback)."""
+    import ctypes
+    L = T.lib()
+    n = 1 + 3 + 9
+    parent = np.array([0] + [(i - 1) // 3 for i in range(1, n)], np.int32)
+    is_word = (np.arange(n) >= 4).astype(np.uint8)
+    desc = np.zeros((n, 32), np.uint8)
+    w = np.where(is_word == 1, 1.0, 0.0)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+
+    def create(k=3, Lv=2, s=0, wt=0, nn=n, par=parent, isw=is_word):
+        h = ctypes.c_void_p()
+        rc = L.orbx_vocabulary_create(99, k, Lv, s, wt, nn, p(par), p(isw), p(desc), p(w), ctypes.byref(h))
+        assert not h.value
+        return rc
+
+    assert create(k=21) == orbx.ERR_ARG and create(Lv=0) == orbx.ERR_ARG and create(Lv=11) == orbx.ERR_ARG and create(s=6) == orbx.ERR_ARG and create(wt=4) == orbx.ERR_ARG
+    assert create(nn=1) == orbx.ERR_ARG
+    bad = parent.copy()
+    bad[5] = 7   # a parent with a larger id than its child: not file order
+    assert create(par=bad) == orbx.ERR_ARG
+    inner_word = is_word.copy()
+    inner_word[1] = 1   # a word that has children
+    assert create(isw=inner_word) == orbx.ERR_ARG
+    assert create() == orbx.ERR_CUDA   # device 99: loud failure, no fallback
+    h = ctypes.c_void_p()
+    assert L.orbx_vocabulary_load_text(0, str(tmp_path / "missing.txt").encode(), ctypes.byref(h)) == orbx.ERR_ARG
+    f = tmp_path / "bad.txt"
+    f.write_text("10 7\n")
+    assert L.orbx_vocabulary_load_text(0, str(f).encode(), ctypes.byref(h)) == orbx.ERR_ARG
+    assert L.orbx_batch_compute_bow(None, None, 1, 4) == orbx.ERR_ARG
