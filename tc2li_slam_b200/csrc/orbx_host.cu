@@ -960,7 +960,7 @@ static int search_common(orbx_batch* b, const SearchArgs& a) {
             if (a.side[i] > 2 || (a.side[i] == 1 && (i == 0 || a.side[i - 1] != 0))) return fail(ORBX_ERR_ARG, "side[i] must be 0, 2, or 1 right after a 0");
     DeviceGuard dg(b->device);
     const int K = b->g.K, sides = two ? 2 : 1, KK = K * sides;
-    if (KK > 32767) return fail(ORBX_ERR_TOO_LARGE, "keypoint capacity too large for the search kernel's 16-bit indices");
+    if (KK > (two ? 32767 : 65535)) return fail(ORBX_ERR_TOO_LARGE, "keypoint capacity too large for the search kernel's 16-bit indices");   // (two-grid: signed 16-bit partner links)
     const size_t budget = kSearchSmemBudget;
     const bool anyTaken = a.taken || a.taken2, anyLinks = two && a.local && (a.l2r || a.r2l);
     // the frame's descriptors are staged in shared memory when at least 32 KB remain for the candidate list next to them
